@@ -1,0 +1,86 @@
+"""Kernel-level timing of the RoIAlign kernels on one GPU (tuning tool, not the bench contract).
+
+  python benchmarks/roi_align_sweep.py [--shape target|infer|train] [--iters 20]
+
+Prints one JSON line per configuration: device time (CUDA events, L2 flushed between
+iterations), algorithmic bytes and achieved GB/s."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from simpledet_b200 import ops, synth  # noqa: E402
+
+
+def algorithmic_bytes(rois, levels, shapes, C, pooled, strides, with_argmax):
+    """bytes = sz(out) [x3 with argmax] + sum_l min(sz(feat_l), sum of window bytes on l) + sz(rois)."""
+    B, N = rois.shape[:2]
+    out = B * N * C * pooled * pooled * 4
+    total = out * (3 if with_argmax else 1) + rois.size * 4
+    for l, ((h, w), s) in enumerate(zip(shapes, strides)):
+        m = levels == l
+        if not m.any():
+            continue
+        r = rois[m] / s
+        x1 = np.clip(np.floor(r[:, 0]), 0, w - 1)
+        x2 = np.clip(np.ceil(r[:, 2]), 0, w - 1)
+        y1 = np.clip(np.floor(r[:, 1]), 0, h - 1)
+        y2 = np.clip(np.ceil(r[:, 3]), 0, h - 1)
+        win = float(((x2 - x1 + 1) * (y2 - y1 + 1)).sum()) * C * 4
+        total += min(win, B * C * h * w * 4)
+    return int(total)
+
+
+def time_op(fn, iters, flush):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(iters)]
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    for s, e in ev:
+        flush.fill_(1.0)  # 512 MB write: evicts the 126 MB L2
+        s.record()
+        fn()
+        e.record()
+    torch.cuda.synchronize()
+    ts = sorted(s.elapsed_time(e) for s, e in ev)
+    return ts[len(ts) // 2] * 1e3, ts[0] * 1e3  # median, min (us)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="target")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--argmax", type=int, default=0)
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    B, N, pooled = {"target": (1, 512, 14), "infer": (1, 1000, 7), "train": (2, 512, 7),
+                    "mask": (2, 128, 14)}[a.shape]
+    C = 256
+    shapes = synth.fpn_shapes()
+    feats = [torch.randn((B, C, h, w), device=dev) for h, w in shapes]
+    rois_np = synth.random_rois(rng, B, N)
+    rois = torch.from_numpy(rois_np).to(dev)
+    flush = torch.empty(128 * 1024 * 1024, device=dev)
+    out, _, _, lv = ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=False)
+    lv = lv.cpu().numpy()
+    nbytes = algorithmic_bytes(rois_np, lv, shapes, C, pooled, synth.FPN_STRIDES, bool(a.argmax))
+
+    def fn():
+        ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=bool(a.argmax))
+
+    med, mn = time_op(fn, a.iters, flush)
+    print(json.dumps({"shape": a.shape, "B": B, "N": N, "pooled": pooled, "argmax": a.argmax,
+                      "cpt": os.environ.get("SDET_RA_CPT"), "phs": os.environ.get("SDET_RA_PHS"),
+                      "us_median": round(med, 2), "us_min": round(mn, 2), "alg_bytes": nbytes,
+                      "GBps": round(nbytes / med / 1e3, 1),
+                      "levels": np.bincount(lv.ravel() + 1, minlength=5).tolist()}))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,72 @@
+"""ctypes binding of the C ABI declared in include/simpledet_b200.h.
+
+There is no CPU fallback: if the shared library is missing or a call fails this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_uint64, c_void_p
+
+from .build import LIB_PATH
+
+_lib = None
+
+
+class SdetError(RuntimeError):
+    """A C-ABI entry point returned a non-zero sdet_status."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"simpledet_b200 error {code}: {msg}")
+        self.code = code
+
+
+# name -> (argtypes); every function returns int status unless listed in _RESTYPES.
+_P = c_void_p
+_SIGNATURES = {
+    "sdet_abi_version": [],
+    "sdet_last_error": [],
+    "sdet_launch_count": [],
+    "sdet_roi_align_v2_forward": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_float, _P],
+    "sdet_roi_align_v2_backward": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, _P],
+    "sdet_fpn_roi_align_v2_forward": [POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                      c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_int, _P],
+    "sdet_fpn_roi_align_v2_backward": [_P, _P, _P, _P, POINTER(_P), POINTER(c_int), POINTER(c_int),
+                                       c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "sdet_roi_pooling_v1_forward": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_int, c_float, _P],
+    "sdet_roi_pooling_v1_backward": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, _P],
+}
+_RESTYPES = {"sdet_last_error": c_char_p, "sdet_launch_count": c_uint64}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    """Load libsimpledet_b200.so (built in-tree by simpledet_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the header and the library disagree
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_int)
+        _lib = L
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise SdetError(status, lib().sdet_last_error().decode())
+
+
+def launch_count() -> int:
+    return int(lib().sdet_launch_count())
