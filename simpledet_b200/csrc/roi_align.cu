@@ -20,7 +20,9 @@
 // `(hend-hstart)/3.0` and `<= hend-h_stride+0.01` promotions to double are kept.
 #include <cfloat>
 #include <climits>
+#include <cstdint>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -31,6 +33,7 @@ constexpr int kMaxP = SDET_MAX_POOLED;   // pooled size limit per axis
 constexpr int kTab = kMaxP * kMaxS;
 constexpr int kFlagNot2 = 1;             // some non-empty bin does not have exactly 2 samples
 constexpr int kFlagOverflow = 2;         // some bin has more than kMaxS samples
+constexpr int kFlagEmpty = 4;            // some bin is empty along an axis (end <= start)
 
 struct Level {
   const float* data;
@@ -51,6 +54,7 @@ struct RoiAlignArgs {
   float* argy;
   int32_t* levels_out;
   int B, N, C, PH, PW;
+  uint64_t negzero2;  // {-0.0f,-0.0f}: opaque addend that keeps FFMA2 products exact
 };
 
 struct AxisTab {
@@ -87,6 +91,7 @@ __device__ void build_axis_bin(AxisTab& t, int p, int P, float roi_start, float 
   e = min_ref(max_ref(__fadd_rn(e, roi_start), 0.f), lim);
   if (e <= s) {
     t.cnt[p] = -1;
+    atomicOr(s_flags, kFlagEmpty);
     return;
   }
   const float stride = (float)__ddiv_rn((double)__fsub_rn(e, s), 3.0);
@@ -167,21 +172,99 @@ __device__ void element_direct(const float* __restrict__ plane, int H, int W, in
 }
 
 // ---------------------------------------------------------------------------------------------
-// Forward kernel.  grid = (B*N rois, ceil(C/CT) channel tiles).  Dynamic smem = staged window.
+// Forward kernel.  grid = (B*N rois, channel-tile groups).  One CTA = one roi x `tiles` channel
+// tiles; the per-roi preamble is paid once per CTA.  Dynamic smem (kCapFloats) holds 1 or 2
+// window buffers; the channel stride inside a buffer is a compile-time constant (kCS) so every
+// tap load is `LDS [reg + imm]`.
+//
+//   warp  = (channel group cg of CPT channels, ph chunk pc)         -> everything warp-uniform
+//   lane  = 2*pw + s : one of the two w-samples of output column pw -> the 28 lanes of a warp
+//           read 28 columns of ONE shared-memory row: bank-conflict free by layout
+//   the two lanes of a pw exchange their maxima with one shuffle; lane s=0 stores.
+//
+// Arithmetic: channel pairs run on the packed fp32x2 pipe (FFMA2 / FADD2).  Each product is
+// `fma.rn.f32x2(w, x, -0.0)` with the -0.0 coming from a kernel argument, which rounds exactly
+// like a lone multiply and cannot be contracted with the following add (ptxas fuses a bare
+// mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would change the rounding); sums are
+// add.rn.f32x2 in the reference's order.  Result: bit-identical to the scalar sequence.
 // ---------------------------------------------------------------------------------------------
-template <int CT, int CPT, bool kArg>
-__global__ void __launch_bounds__(256)
-roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int phs,
-                        const int smem_cap_floats) {
-  extern __shared__ float s_win[];
+
+struct HRow {   // per h-sample, 16 bytes, read with one LDS.128
+  int off_lo;   // BYTE offset of pixel (lo, wmin) inside a channel plane, incl. the row's 16B shift
+  int off_hi;
+  float w0;     // 1 - alpha
+  float w1;     // alpha
+};
+
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int IMM>
+__device__ __forceinline__ float lds_f32_imm(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+template <int CPT, int kCS, int K = 0>
+struct TapLoader {  // R[k][t] = smem[base_t + k*kCS*4], fully unrolled with immediate offsets
+  static __device__ __forceinline__ void run(float (&R)[CPT][2], unsigned al, unsigned ar) {
+    R[K][0] = lds_f32_imm<K * kCS * 4>(al);
+    R[K][1] = lds_f32_imm<K * kCS * 4>(ar);
+    TapLoader<CPT, kCS, K + 1>::run(R, al, ar);
+  }
+};
+template <int CPT, int kCS>
+struct TapLoader<CPT, kCS, CPT> {
+  static __device__ __forceinline__ void run(float (&)[CPT][2], unsigned, unsigned) {}
+};
+
+// kCapFloats: floats of dynamic shared memory for the window buffers (12288 = 48 KB -> 4 CTAs/SM)
+template <int CPT, bool kArg, int kPH, int kPW, int kCapFloats>
+__global__ void __launch_bounds__(128)
+roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles, const int mode_pref) {
+  extern __shared__ __align__(16) float s_win[];
   __shared__ AxisTab s_th, s_tw;
+  __shared__ __align__(16) HRow s_hrow[kTab];
   __shared__ int s_flags, s_hmin, s_hmax, s_wmin, s_wmax;
+
+  constexpr int NW = 4;  // warps per CTA
+  static_assert(CPT % 2 == 0, "channels are processed in fp32x2 pairs");
 
   const int tid = threadIdx.x;
   const int n = blockIdx.x;
-  const int c0 = blockIdx.y * CT;
-  const int C = a.C, PH = a.PH, PW = a.PW;
+  const int C = a.C;
+  const int PH = kPH ? kPH : a.PH, PW = kPW ? kPW : a.PW;
+  const int PP = PH * PW;
   const int b = n / a.N;  // roi_align_v2-inl.h:77
+  const int cgrp0 = blockIdx.y * tiles * (2 * CPT);            // first channel of this CTA
+  const int cgrp1 = min(C, cgrp0 + tiles * (2 * CPT));         // one past the last
 
   const float x1 = __ldg(a.rois + 4 * (size_t)n + 0), y1 = __ldg(a.rois + 4 * (size_t)n + 1);
   const float x2 = __ldg(a.rois + 4 * (size_t)n + 2), y2 = __ldg(a.rois + 4 * (size_t)n + 3);
@@ -195,11 +278,11 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int phs,
     if (a.levels_out != nullptr && blockIdx.y == 0 && tid == 0) a.levels_out[n] = li;
   }
 
-  const int nct = min(CT, C - c0);
-  const size_t out_base = ((size_t)n * C + c0) * PH * PW;
+  const size_t out_base = ((size_t)n * C + cgrp0) * PP;
+  const int nelem = (cgrp1 - cgrp0) * PP;
 
   if (li < 0) {  // roi matched no level: the reference zeroes it on every level -> all-empty
-    for (int e = tid; e < nct * PH * PW; e += blockDim.x) {
+    for (int e = tid; e < nelem; e += blockDim.x) {
       a.out[out_base + e] = 0.f;
       if (kArg) {
         a.argx[out_base + e] = -1.f;
@@ -233,20 +316,34 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int phs,
   const int hmin = s_hmin, wmin = s_wmin;
   const int Hwin = s_hmax - hmin + 1, Wwin = s_wmax - wmin + 1;
   const bool any = (s_hmax >= 0) && (s_wmax >= 0);
-  const size_t HW = (size_t)H * W;
-  const float* gplane0 = L.data + ((size_t)b * C + c0) * HW;
+  const int HW = H * W;
+  const float* gimg = L.data + (size_t)b * C * HW;  // image b, channel 0
 
-  const bool fast = any && (flags == 0) && ((long long)CT * Hwin * Wwin <= smem_cap_floats);
+  // 16-byte staging needs every channel plane to start 16B-aligned
+  const bool vec = ((HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(L.data) & 15) == 0);
+  const int Wp = vec ? ((Wwin + 3 + 3) & ~3) : ((Wwin + 3) & ~3);  // smem row pitch (floats)
+  const int plane = Hwin * Wp;
+
+  // Buffering mode by window size (kCS = channel stride in floats, ct = channels per tile):
+  //   0: ct=2*CPT, 2 buffers, kCS=cap/(4*CPT)   1: ct=2*CPT, 1 buffer, kCS=cap/(2*CPT)
+  //   2: ct=CPT,   2 buffers, kCS=cap/(2*CPT)   3: ct=CPT,   1 buffer, kCS=cap/CPT
+  constexpr int CS0 = kCapFloats / (4 * CPT), CS1 = kCapFloats / (2 * CPT), CS3 = kCapFloats / CPT;
+  int mode = -1;
+  if (plane <= CS0) mode = 0;
+  else if (plane <= CS1) mode = (mode_pref & 1) ? 2 : 1;
+  else if (plane <= CS3) mode = 3;
+  const bool fast = any && ((flags & (kFlagNot2 | kFlagOverflow)) == 0) && (PW <= 16) && (Wp <= 64) && (Hwin <= 128) &&
+                    (mode >= 0) && ((cgrp1 - cgrp0) % (2 * CPT) == 0);
 
   if (!fast) {
     // ---- generic path: one thread per output element, taps straight from global/L1 ----
-    for (int e = tid; e < nct * PH * PW; e += blockDim.x) {
-      const int pw = e % PW, ph = (e / PW) % PH, cl = e / (PW * PH);
-      const float* plane = gplane0 + (size_t)cl * HW;
+    for (int e = tid; e < nelem; e += blockDim.x) {
+      const int pw = e % PW, ph = (e / PW) % PH, cl = e / PP;
+      const float* pl = gimg + (size_t)(cgrp0 + cl) * HW;
       const int nh = s_th.cnt[ph], nw = s_tw.cnt[pw];
       float best = 0.f, bx = -1.f, by = -1.f;
       if (flags & kFlagOverflow) {
-        element_direct(plane, H, W, PH, PW, ph, pw, rsw, rsh, rew, reh, best, bx, by);
+        element_direct(pl, H, W, PH, PW, ph, pw, rsw, rsh, rew, reh, best, bx, by);
       } else if (nh >= 0 && nw >= 0) {
         best = -FLT_MAX;
         for (int i = 0; i < nh; ++i) {
@@ -258,9 +355,9 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int phs,
             const int wl = s_tw.lo[wj], wr = s_tw.hi[wj];
             const float b0 = s_tw.w0[wj], b1 = s_tw.w1[wj];
             const float v = bilinear_ref(__fmul_rn(a0, b0), __fmul_rn(a1, b0), __fmul_rn(a0, b1),
-                                         __fmul_rn(a1, b1), __ldg(plane + hl * W + wl),
-                                         __ldg(plane + hh * W + wl), __ldg(plane + hl * W + wr),
-                                         __ldg(plane + hh * W + wr));
+                                         __fmul_rn(a1, b1), __ldg(pl + hl * W + wl),
+                                         __ldg(pl + hh * W + wl), __ldg(pl + hl * W + wr),
+                                         __ldg(pl + hh * W + wr));
             if (v > best) {
               best = v;
               bx = s_tw.coord[wj];
@@ -278,135 +375,254 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int phs,
     return;
   }
 
-  // ---- stage the window: rows are contiguous in NCHW -> lanes walk x, warps walk rows ----
-  const int plane_sz = Hwin * Wwin;
-  {
-    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int lpr_log2 = Wwin <= 8 ? 3 : (Wwin <= 16 ? 4 : 5);
-    const int lpr = 1 << lpr_log2, rpw = 32 >> lpr_log2;
-    const int sub = lane >> lpr_log2, xl = lane & (lpr - 1);
-    const float* g0 = gplane0 + (size_t)hmin * W + wmin;
-    for (int y = warp * rpw + sub; y < Hwin; y += nwarps * rpw) {
-      for (int x = xl; x < Wwin; x += lpr) {
-        const float* g = g0 + (size_t)y * W + x;
-        float* s = s_win + y * Wwin + x;
-        float v[CT];
-#pragma unroll
-        for (int c = 0; c < CT; ++c) v[c] = (c < nct) ? __ldg(g + (size_t)c * HW) : 0.f;
-#pragma unroll
-        for (int c = 0; c < CT; ++c) s[c * plane_sz] = v[c];
-      }
+  // ---- per-roi row table: byte offsets of the lo/hi rows (with the per-row 16B shift) ----
+  if (tid < PH * kMaxS) {
+    const int ph = tid / kMaxS, s = tid % kMaxS;
+    if (s_th.cnt[ph] == 2 && s < 2) {
+      const int lo = s_th.lo[tid], hi = s_th.hi[tid];
+      const int sh_lo = vec ? ((lo * W + wmin) & 3) : 0;
+      const int sh_hi = vec ? ((hi * W + wmin) & 3) : 0;
+      s_hrow[tid] = HRow{4 * ((lo - hmin) * Wp + sh_lo), 4 * ((hi - hmin) * Wp + sh_hi),
+                         s_th.w0[tid], s_th.w1[tid]};
     }
   }
-  __syncthreads();
+  // (visibility of s_hrow is covered by the __syncthreads() before the first compute)
 
-  // ---- compute: thread = (pw, channel group, ph chunk) ----
-  constexpr int NCG = CT / CPT;
-  if (tid >= PW * NCG * phs) return;
-  const int pw = tid % PW;
-  const int rest = tid / PW;
-  const int cg = rest % NCG, pc = rest / NCG;
-  const int chunk = (PH + phs - 1) / phs;
-  const int ph_beg = pc * chunk, ph_end = min(PH, ph_beg + chunk);
-
-  const int wcnt = s_tw.cnt[pw];
-  int xo[4] = {0, 0, 0, 0};
-  float b0[2] = {0.f, 0.f}, b1[2] = {0.f, 0.f}, wc[2] = {-1.f, -1.f};
-  if (wcnt == 2) {
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int j = pw * kMaxS + s;
-      xo[2 * s] = s_tw.lo[j] - wmin;
-      xo[2 * s + 1] = s_tw.hi[j] - wmin;
-      b0[s] = s_tw.w0[j];
-      b1[s] = s_tw.w1[j];
-      wc[s] = s_tw.coord[j];
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(s_win);
+  const int warp = tid >> 5, lane = tid & 31;
+  const int pw = lane >> 1, sx = lane & 1;
+  const bool lane_on = pw < PW;
+  int wcnt = -1, xl = 0, xr = 0;
+  float b0 = 0.f, b1 = 0.f, wc = -1.f;
+  if (lane_on) {
+    wcnt = s_tw.cnt[pw];
+    if (wcnt == 2) {
+      const int j = pw * kMaxS + sx;
+      xl = s_tw.lo[j] - wmin;
+      xr = s_tw.hi[j] - wmin;
+      b0 = s_tw.w0[j];
+      b1 = s_tw.w1[j];
+      wc = s_tw.coord[j];
     }
   }
-  const float* sw = s_win + cg * CPT * plane_sz;
-  const int cbase = c0 + cg * CPT;
-  const size_t PP = (size_t)PH * PW;
-  float* outp = a.out + ((size_t)n * C + cbase) * PP + pw;
-  float* axp = kArg ? a.argx + ((size_t)n * C + cbase) * PP + pw : nullptr;
-  float* ayp = kArg ? a.argy + ((size_t)n * C + cbase) * PP + pw : nullptr;
+  const uint64_t nz2 = a.negzero2;  // {-0.0f, -0.0f}; a kernel argument on purpose (see header)
 
-  float Lr[CPT][4], Hr[CPT][4];
-#pragma unroll
-  for (int k = 0; k < CPT; ++k)
-#pragma unroll
-    for (int t = 0; t < 4; ++t) Lr[k][t] = Hr[k][t] = 0.f;
-  int rowL = -1, rowH = -1;
+  // Everything below is instantiated per (channel stride kCS, channel groups NCG, buffers NBUF).
+  auto run = [&](auto cs_tag, auto ncg_tag, auto nbuf_tag) {
+    constexpr int kCS = decltype(cs_tag)::value;
+    constexpr int NCG = decltype(ncg_tag)::value;
+    constexpr int NBUF = decltype(nbuf_tag)::value;
+    constexpr int CTILE = NCG * CPT;     // channels per tile
+    constexpr int PHS = NW / NCG;        // ph chunks
+    constexpr int BUF_BYTES = CTILE * kCS * 4;
+    const int ntiles = (cgrp1 - cgrp0) / CTILE;
+    const int cg = warp % NCG, pc = warp / NCG;
+    const int chunk = (PH + PHS - 1) / PHS;
+    const int ph_beg = pc * chunk, ph_end = min(PH, ph_beg + chunk);
 
-  for (int ph = ph_beg; ph < ph_end; ++ph) {
-    const int hcnt = s_th.cnt[ph];
-    float best[CPT];
-    int bi[CPT];
+    // ---- stage one channel tile into a window buffer with cp.async ----
+    // thread = (row slot, 16B chunk) of the window; it walks the tile's channels with constant
+    // strides (global: HW floats, shared: kCS floats = an immediate), so the per-copy cost is
+    // one 64-bit add + one LDGSTS.
+    const int nchm = Wp >> 2;                                   // max 16B chunks per row
+    const int lpr_log2 = nchm <= 4 ? 2 : (nchm <= 8 ? 3 : 4);   // lanes per row (4 / 8 / 16)
+    const int rslot = tid >> lpr_log2, jchunk = tid & ((1 << lpr_log2) - 1);
+    const int rpp = 128 >> lpr_log2;                            // rows per pass
+    auto stage = [&](int tile, unsigned buf) {
+      const float* g0 = gimg + (size_t)(cgrp0 + tile * CTILE) * HW;
+      for (int y = rslot; y < Hwin; y += rpp) {
+        const int e0 = (hmin + y) * W + wmin;  // first wanted element inside the plane
+        unsigned dst = buf + 4u * (unsigned)(y * Wp + jchunk * 4);
+        if (vec) {
+          const int sh = e0 & 3;
+          if (jchunk * 4 < sh + Wwin) {
+            const float* src = g0 + (e0 - sh + jchunk * 4);
 #pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-      best[k] = -FLT_MAX;
-      bi[k] = -1;
-    }
-    if (hcnt == 2) {
-#pragma unroll
-      for (int hs = 0; hs < 2; ++hs) {
-        const int i = ph * kMaxS + hs;
-        const int lo = s_th.lo[i] - hmin, hi = s_th.hi[i] - hmin;
-        if (lo != rowL) {
-          if (lo == rowH) {
-#pragma unroll
-            for (int k = 0; k < CPT; ++k)
-#pragma unroll
-              for (int t = 0; t < 4; ++t) Lr[k][t] = Hr[k][t];
-          } else {
-            const float* r = sw + lo * Wwin;
-#pragma unroll
-            for (int k = 0; k < CPT; ++k)
-#pragma unroll
-              for (int t = 0; t < 4; ++t) Lr[k][t] = r[k * plane_sz + xo[t]];
+            for (int c = 0; c < CTILE; ++c) {
+              cp_async16(dst + c * (kCS * 4), src);
+              src += HW;
+            }
           }
-          rowL = lo;
-        }
-        if (hi != rowH) {
-          const float* r = sw + hi * Wwin;
+        } else {
+          const float* src = g0 + (e0 + jchunk * 4);
+#pragma unroll 1
+          for (int c = 0; c < CTILE; ++c) {
 #pragma unroll
-          for (int k = 0; k < CPT; ++k)
-#pragma unroll
-            for (int t = 0; t < 4; ++t) Hr[k][t] = r[k * plane_sz + xo[t]];
-          rowH = hi;
+            for (int e = 0; e < 4; ++e)
+              if (jchunk * 4 + e < Wwin) cp_async4(dst + 4u * e, src + e);
+            dst += kCS * 4;
+            src += HW;
+          }
         }
-        const float a0 = s_th.w0[i], a1 = s_th.w1[i];
-        const float wtl0 = __fmul_rn(a0, b0[0]), wbl0 = __fmul_rn(a1, b0[0]);
-        const float wtr0 = __fmul_rn(a0, b1[0]), wbr0 = __fmul_rn(a1, b1[0]);
-        const float wtl1 = __fmul_rn(a0, b0[1]), wbl1 = __fmul_rn(a1, b0[1]);
-        const float wtr1 = __fmul_rn(a0, b1[1]), wbr1 = __fmul_rn(a1, b1[1]);
+      }
+    };
+
+    auto compute = [&](int tile, unsigned buf) {
+      const int cbase = cgrp0 + tile * CTILE + cg * CPT;
+      const unsigned sl = buf + 4u * (unsigned)(cg * CPT * kCS + xl);   // lane's left-tap column
+      const unsigned sr = buf + 4u * (unsigned)(cg * CPT * kCS + xr);   // lane's right-tap column
+      float RA[CPT][2], RB[CPT][2];
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) RA[k][0] = RA[k][1] = RB[k][0] = RB[k][1] = 0.f;
+      int rowA = -1, rowB = -1;
+      const size_t obase = ((size_t)n * C + cbase) * PP + (size_t)ph_beg * PW + pw;
+      float* outp = a.out + obase;
+      float* axp = kArg ? a.argx + obase : nullptr;
+      float* ayp = kArg ? a.argy + obase : nullptr;
+      const bool store = lane_on && sx == 0;
+
+      for (int ph = ph_beg; ph < ph_end; ++ph) {
+        const int hcnt = s_th.cnt[ph];
+        float m[CPT];
+        int mi[CPT];
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
-          const float v0 =
-              bilinear_ref(wtl0, wbl0, wtr0, wbr0, Lr[k][0], Hr[k][0], Lr[k][1], Hr[k][1]);
-          const float v1 =
-              bilinear_ref(wtl1, wbl1, wtr1, wbr1, Lr[k][2], Hr[k][2], Lr[k][3], Hr[k][3]);
-          if (v0 > best[k]) {
-            best[k] = v0;
-            bi[k] = 2 * hs;
+          m[k] = -FLT_MAX;
+          mi[k] = -1;
+        }
+        if (hcnt == 2) {
+          int4 hr_nxt = *reinterpret_cast<const int4*>(&s_hrow[ph * kMaxS]);
+#pragma unroll 1
+          for (int hs = 0; hs < 2; ++hs) {
+            const int4 hr = hr_nxt;
+            hr_nxt = *reinterpret_cast<const int4*>(&s_hrow[ph * kMaxS + 1]);  // prefetch sample 1
+            const int olo = hr.x, ohi = hr.y;
+            const float a0 = __int_as_float(hr.z), a1 = __int_as_float(hr.w);
+            const float wtl = __fmul_rn(a0, b0), wbl = __fmul_rn(a1, b0);
+            const float wtr = __fmul_rn(a0, b1), wbr = __fmul_rn(a1, b1);
+            const uint64_t wtl2 = pack2(wtl, wtl), wbl2 = pack2(wbl, wbl);
+            const uint64_t wtr2 = pack2(wtr, wtr), wbr2 = pack2(wbr, wbr);
+            auto step = [&](const float (&Lo)[CPT][2], const float (&Hi)[CPT][2]) {
+#pragma unroll
+              for (int k = 0; k < CPT; k += 2) {
+                // roi_align_v2-inl.h:137-140 for channels k, k+1: ((tl + bl) + tr) + br
+                const uint64_t ptl = fma2(wtl2, pack2(Lo[k][0], Lo[k + 1][0]), nz2);
+                const uint64_t pbl = fma2(wbl2, pack2(Hi[k][0], Hi[k + 1][0]), nz2);
+                const uint64_t ptr = fma2(wtr2, pack2(Lo[k][1], Lo[k + 1][1]), nz2);
+                const uint64_t pbr = fma2(wbr2, pack2(Hi[k][1], Hi[k + 1][1]), nz2);
+                float v0, v1;
+                unpack2(add2(add2(add2(ptl, pbl), ptr), pbr), v0, v1);
+                if (kArg) {
+                  if (v0 > m[k]) {
+                    m[k] = v0;
+                    mi[k] = 2 * hs + sx;
+                  }
+                  if (v1 > m[k + 1]) {
+                    m[k + 1] = v1;
+                    mi[k + 1] = 2 * hs + sx;
+                  }
+                } else {
+                  // == `if (v > m) m = v` incl. the NaN / -inf / -FLT_MAX cases
+                  m[k] = fmaxf(m[k], v0);
+                  m[k + 1] = fmaxf(m[k + 1], v1);
+                }
+              }
+            };
+            // 2-row register cache, no moves: whichever set holds `lo` plays the low row
+            if (olo == rowA) {
+              if (ohi != rowB) {
+                TapLoader<CPT, kCS>::run(RB, sl + ohi, sr + ohi);
+                rowB = ohi;
+              }
+              step(RA, RB);
+            } else if (olo == rowB) {
+              if (ohi != rowA) {
+                TapLoader<CPT, kCS>::run(RA, sl + ohi, sr + ohi);
+                rowA = ohi;
+              }
+              step(RB, RA);
+            } else {
+              TapLoader<CPT, kCS>::run(RA, sl + olo, sr + olo);
+              rowA = olo;
+              if (ohi != rowB) {
+                TapLoader<CPT, kCS>::run(RB, sl + ohi, sr + ohi);
+                rowB = ohi;
+              }
+              step(RA, RB);
+            }
           }
-          if (v1 > best[k]) {
-            best[k] = v1;
-            bi[k] = 2 * hs + 1;
+        }
+        // combine the two w-samples of this pw (lanes 2pw, 2pw+1); reference order is
+        // (h0,w0),(h0,w1),(h1,w0),(h1,w1) with strict '>' => on equal values the smaller index wins.
+        // Bins that are empty along an axis are written wrongly here and repaired by the fix-up
+        // pass at the end of the kernel (rare: only rois that reach outside the map).
+        if (kArg) {
+          const float hc0 = s_th.coord[ph * kMaxS], hc1 = s_th.coord[ph * kMaxS + 1];
+          const float pwc = __shfl_xor_sync(0xffffffffu, wc, 1);
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) {
+            const float pm = __shfl_xor_sync(0xffffffffu, m[k], 1);
+            const int pi = __shfl_xor_sync(0xffffffffu, mi[k], 1);
+            const float best = fmaxf(m[k], pm);
+            int bi = mi[k];
+            float bxc = wc;
+            const bool take = (pi >= 0) && (bi < 0 || pm > m[k] || (pm == m[k] && pi < bi));
+            if (take) {
+              bi = pi;
+              bxc = pwc;
+            }
+            if (store) {
+              outp[k * PP] = best;
+              axp[k * PP] = bi < 0 ? -1.f : bxc;
+              ayp[k * PP] = bi < 0 ? -1.f : ((bi & 2) ? hc1 : hc0);
+            }
           }
+          axp += PW;
+          ayp += PW;
+        } else {
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) {
+            const float best = fmaxf(m[k], __shfl_xor_sync(0xffffffffu, m[k], 1));
+            if (store) outp[k * PP] = best;
+          }
+        }
+        outp += PW;
+      }
+    };
+
+    // ---- software pipeline over the channel tiles of this roi ----
+    stage(0, sbase);
+    cp_async_commit();
+    for (int t = 0; t < ntiles; ++t) {
+      const unsigned cur = sbase + ((NBUF == 2) ? (unsigned)(t & 1) * BUF_BYTES : 0u);
+      if (NBUF == 2 && t + 1 < ntiles) {
+        stage(t + 1, sbase + (unsigned)((t + 1) & 1) * BUF_BYTES);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      compute(t, cur);
+      if (t + 1 < ntiles) {
+        __syncthreads();  // every warp is done with `cur` before it is refilled
+        if (NBUF == 1) {
+          stage(t + 1, sbase);
+          cp_async_commit();
         }
       }
     }
-    const bool empty = (hcnt < 0) || (wcnt < 0);
-    const float hc0 = s_th.coord[ph * kMaxS], hc1 = s_th.coord[ph * kMaxS + 1];
-#pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-      if (cbase + k < C) {
-        const size_t o = (size_t)k * PP + (size_t)ph * PW;
-        outp[o] = empty ? 0.f : best[k];
+  };
+
+  using std::integral_constant;
+  if (mode == 0)
+    run(integral_constant<int, CS0>{}, integral_constant<int, 2>{}, integral_constant<int, 2>{});
+  else if (mode == 1)
+    run(integral_constant<int, CS1>{}, integral_constant<int, 2>{}, integral_constant<int, 1>{});
+  else if (mode == 2)
+    run(integral_constant<int, CS1>{}, integral_constant<int, 1>{}, integral_constant<int, 2>{});
+  else
+    run(integral_constant<int, CS3>{}, integral_constant<int, 1>{}, integral_constant<int, 1>{});
+
+  if (flags & kFlagEmpty) {  // repair bins that are empty along an axis: out = 0, argmax = -1
+    __syncthreads();         // orders this CTA's earlier global stores before the overwrite
+    for (int e = tid; e < nelem; e += blockDim.x) {
+      const int pw_ = e % PW, ph_ = (e / PW) % PH;
+      if (s_th.cnt[ph_] < 0 || s_tw.cnt[pw_] < 0) {
+        a.out[out_base + e] = 0.f;
         if (kArg) {
-          const bool none = empty || bi[k] < 0;
-          axp[o] = none ? -1.f : ((bi[k] & 1) ? wc[1] : wc[0]);
-          ayp[o] = none ? -1.f : ((bi[k] & 2) ? hc1 : hc0);
+          a.argx[out_base + e] = -1.f;
+          a.argy[out_base + e] = -1.f;
         }
       }
     }
@@ -467,51 +683,53 @@ int check_common(int B, int N, int C, int ph, int pw) {
   return SDET_OK;
 }
 
-template <int CT, int CPT>
-int launch_fwd_t(const RoiAlignArgs& a, int phs, int threads, cudaStream_t st) {
-  static int smem_cap = -1;  // bytes this kernel may use; same for every instantiation
+template <int CPT, int kPH, int kPW, int kCapFloats>
+int launch_fwd_t(const RoiAlignArgs& a, cudaStream_t st) {
+  static bool configured = false;
   const bool arg = a.argx != nullptr;
-  auto k_inf = roi_align_v2_fwd_kernel<CT, CPT, false>;
-  auto k_trn = roi_align_v2_fwd_kernel<CT, CPT, true>;
-  const int want = 64 * 1024;
-  if (smem_cap < 0) {
-    SDET_CUDA(cudaFuncSetAttribute(k_inf, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
-    SDET_CUDA(cudaFuncSetAttribute(k_trn, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
-    smem_cap = want;
+  auto k_inf = roi_align_v2_fwd_kernel<CPT, false, kPH, kPW, kCapFloats>;
+  auto k_trn = roi_align_v2_fwd_kernel<CPT, true, kPH, kPW, kCapFloats>;
+  constexpr int smem_bytes = kCapFloats * 4;
+  if (!configured) {
+    SDET_CUDA(cudaFuncSetAttribute(k_inf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SDET_CUDA(cudaFuncSetAttribute(k_trn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
   }
-  dim3 grid((unsigned)(a.B * a.N), (unsigned)((a.C + CT - 1) / CT));
+  // channel tiles (of 2*CPT channels) per CTA: amortise the per-roi preamble but keep the grid
+  // at >= ~12 CTAs per SM
+  constexpr int CT = 2 * CPT;
+  const int total_tiles = (a.C + CT - 1) / CT;
+  const long long jobs = (long long)a.B * a.N * total_tiles;
+  int tpc = (int)(jobs / (148 * 12));
+  int mode_pref = 0;
+  if (const char* e = getenv("SDET_RA_TILES")) tpc = atoi(e);          // tuning only
+  if (const char* e = getenv("SDET_RA_MODEPREF")) mode_pref = atoi(e);  // tuning only
+  if (tpc < 1) tpc = 1;
+  if (tpc > total_tiles) tpc = total_tiles;
+  dim3 grid((unsigned)(a.B * a.N), (unsigned)((total_tiles + tpc - 1) / tpc));
   if (arg)
-    k_trn<<<grid, threads, smem_cap, st>>>(a, phs, smem_cap / 4);
+    k_trn<<<grid, 128, smem_bytes, st>>>(a, tpc, mode_pref);
   else
-    k_inf<<<grid, threads, smem_cap, st>>>(a, phs, smem_cap / 4);
+    k_inf<<<grid, 128, smem_bytes, st>>>(a, tpc, mode_pref);
   SDET_LAUNCH_CHECK("roi_align_v2_fwd_kernel");
   return SDET_OK;
 }
 
-int launch_fwd(const RoiAlignArgs& a, cudaStream_t st) {
+int launch_fwd(RoiAlignArgs& a, cudaStream_t st) {
   if ((a.argx == nullptr) != (a.argy == nullptr))
     return sdet::fail(SDET_ERR_INVALID_ARG, "argmax_x and argmax_y must both be given or both NULL");
-  // thread = (pw, channel group, ph chunk); pick CPT / ph split so a CTA has ~128 compute threads
-  constexpr int CT = 16;
-  const int PW = a.PW, PH = a.PH;
-  int cpt = (PW * (CT / 4) * 2 >= 96) ? 4 : 2;
-  int phs = 0;
-  // tuning overrides (benchmarks/roi_align_sweep.py); not part of the ABI
-  if (const char* e = getenv("SDET_RA_CPT")) cpt = atoi(e) == 2 ? 2 : 4;
-  if (const char* e = getenv("SDET_RA_PHS")) phs = atoi(e);
-  int ncg = CT / cpt;
-  if (phs <= 0) {
-    phs = 1;
-    while (PW * ncg * phs < 112 && phs < PH) ++phs;
-  }
-  if (phs > PH) phs = PH;
-  int threads = ((PW * ncg * phs + 31) / 32) * 32;
-  if (threads < ((PH + PW + 31) / 32) * 32) threads = ((PH + PW + 31) / 32) * 32;
-  if (threads > 256) return sdet::fail(SDET_ERR_UNSUPPORTED, "pooled size needs > 256 threads");
-  return cpt == 4 ? launch_fwd_t<CT, 4>(a, phs, threads, st) : launch_fwd_t<CT, 2>(a, phs, threads, st);
+  a.negzero2 = 0x8000000080000000ull;  // {-0.0f, -0.0f}, see the forward kernel's header
+  int cap = 0;
+  if (const char* e = getenv("SDET_RA_CAP")) cap = atoi(e);  // tuning only
+  if (cap == 8192 && a.PH == 14 && a.PW == 14) return launch_fwd_t<8, 14, 14, 8192>(a, st);
+  if (cap == 9216 && a.PH == 14 && a.PW == 14) return launch_fwd_t<8, 14, 14, 9216>(a, st);
+  if (a.PH == 7 && a.PW == 7) return launch_fwd_t<8, 7, 7, 12288>(a, st);
+  if (a.PH == 14 && a.PW == 14) return launch_fwd_t<8, 14, 14, 12288>(a, st);
+  return launch_fwd_t<8, 0, 0, 12288>(a, st);
 }
 
 }  // namespace
+
 
 extern "C" int sdet_roi_align_v2_forward(const float* data, const float* rois, float* out,
                                          float* argmax_x, float* argmax_y, int B, int N, int C,
