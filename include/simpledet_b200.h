@@ -101,6 +101,58 @@ int sdet_roi_pooling_v1_backward(const float* ograd, const float* max_idx, const
                                  float* grad_data, float* grad_rois, int B, int R, int C, int H,
                                  int W, int pooled_h, int pooled_w, int accumulate, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * _contrib_DecodeBBox   (operator_cxx/contrib/decodebbox.cc:34-133 arithmetic, :150-209 op,
+ *                        params decodebbox-inl.h:50-69)
+ *   rois (B,N,4), bbox_pred (B,N,K4), im_info (B,3) [h,w,scale]  ->  out (B,N,4) when
+ *   class_agnostic (reads class slot 1, decodebbox.cc:54) else (B,N,K4).
+ *   bbox_mean / bbox_std: HOST float[4] (op defaults 0,0,0,0 / 0.1,0.1,0.2,0.2; class_agnostic
+ *   defaults to TRUE).  decode_type 0 = "xywh", 1 = "xyxy".  All device pointers 16B-aligned.
+ * ------------------------------------------------------------------------------------------ */
+int sdet_decode_bbox(const float* rois, const float* bbox_pred, const float* im_info, float* out,
+                     int B, int N, int K4, const float* bbox_mean, const float* bbox_std,
+                     int class_agnostic, int decode_type, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * _contrib_Proposal_v3  (GPU semantics: operator_cxx/contrib/proposal_v3.cu:435-638; params
+ *                        proposal_v3-inl.h:141-183; anchors :280-318)
+ *   cls_prob (B,2A,H,W) (fg = second half), bbox_pred (B,4A,H,W), im_info (B,3)
+ *   -> out (B,post,4), out_score (B,post,1).  post = rpn_post_nms_top_n when !is_train, else
+ *   min(post, pre); pre = min(rpn_pre_nms_top_n > 0 ? it : A*H*W, A*H*W).
+ *   Padding beyond the kept boxes: zeros (is_train=0) or wrap keep[i % n_keep] (is_train=1).
+ *   scales / ratios: HOST arrays.  workspace: device, >= sdet_proposal_v3_workspace() bytes.
+ * ------------------------------------------------------------------------------------------ */
+size_t sdet_proposal_v3_workspace(int B, int A, int H, int W, int rpn_pre_nms_top_n);
+int sdet_proposal_v3(const float* cls_prob, const float* bbox_pred, const float* im_info, float* out,
+                     float* out_score, int B, int A, int H, int W, int feature_stride,
+                     const float* scales, int num_scales, const float* ratios, int num_ratios,
+                     int rpn_pre_nms_top_n, int rpn_post_nms_top_n, float threshold,
+                     int rpn_min_size, int iou_loss, int is_train, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * _contrib_NMS   (operator_cxx/contrib/nms.cu:274-364; params nms-inl.h:49-70)
+ *   proposals (B,count,5) [x1,y1,x2,y2,score] -> out (B,rpn_post_nms_top_n,4), out_score
+ *   (B,rpn_post_nms_top_n,1).  Suppresses IoU > threshold; only the first min(post,pre) rows are
+ *   written (zeros past the kept boxes), the rest are left untouched exactly like nms.cu:354-358.
+ * ------------------------------------------------------------------------------------------ */
+size_t sdet_contrib_nms_workspace(int B, int count, int rpn_pre_nms_top_n);
+int sdet_contrib_nms(const float* proposals, float* out, float* out_score, int B, int count,
+                     int rpn_pre_nms_top_n, int rpn_post_nms_top_n, float threshold,
+                     int already_sorted, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Batched greedy NMS over boxes that are ALREADY in greedy (descending-score) order: the device
+ * replacement of nms_kernel + the host scan in `_nms` (proposal_v3.cu:281-380,
+ * operator_py/cython/nms_kernel.cu:34-144).
+ *   dets (P,n,5) device; counts (P) device int32 or NULL (= n boxes everywhere); ge = 1 suppress
+ *   IoU >= thresh (Proposal_v3, cpu_nms.greedy_nms), 0 suppress IoU > thresh (_contrib_NMS,
+ *   gpu_nms).  keep (P,n) int32: kept positions in order, zero padded; nkeep (P) int32.
+ *   n <= 12288. */
+size_t sdet_nms_workspace(int problems, int n);
+int sdet_nms_sorted(const float* dets, const int* counts, int problems, int n, float thresh, int ge,
+                    int* keep, int* nkeep, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -135,3 +135,124 @@ def fpn_roi_align_v2_forward(feats, rois, strides, pooled_size, roi_canonical_sc
         o = roi_align_v2_forward(f, lvl_rois, pooled_size, 1.0 / s, with_argmax=False)
         total = o if total is None else total + o
     return total, idx
+
+
+# ---------------------------------------------------------------------------------------------
+# box decode / proposal / NMS (oracle/box_ops.c)
+# ---------------------------------------------------------------------------------------------
+def _fp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def decode_bbox(rois, bbox_pred, im_info, bbox_mean=(0, 0, 0, 0), bbox_std=(0.1, 0.1, 0.2, 0.2),
+                class_agnostic=True, bbox_decode_type="xywh"):
+    """_contrib_DecodeBBox (decodebbox.cc:34-133)."""
+    rois, bbox_pred, im_info = _f32(rois), _f32(bbox_pred), _f32(im_info)
+    B, N, _ = rois.shape
+    K4 = bbox_pred.shape[2]
+    out = np.zeros((B, N, 4 if class_agnostic else K4), np.float32)
+    m, s = _f32(bbox_mean), _f32(bbox_std)
+    lib().oracle_decode_bbox(_p(rois), _p(bbox_pred), _p(im_info), B, N, K4, _p(m), _p(s),
+                             int(bool(class_agnostic)), 0 if bbox_decode_type == "xywh" else 1, _p(out))
+    return out
+
+
+def generate_anchors_v3(feature_stride, ratios, scales):
+    r, s = _f32(ratios), _f32(scales)
+    out = np.empty((len(r) * len(s), 4), np.float32)
+    lib().oracle_generate_anchors_v3(int(feature_stride), _p(r), len(r), _p(s), len(s), _p(out))
+    return out
+
+
+def proposal_v3(cls_prob, bbox_pred, im_info, feature_stride=16, scales=(4, 8, 16, 32),
+                ratios=(0.5, 1, 2), rpn_pre_nms_top_n=6000, rpn_post_nms_top_n=300, threshold=0.7,
+                rpn_min_size=16, iou_loss=False, is_train=False, debug=False):
+    """_contrib_Proposal_v3, GPU (.cu) semantics.  -> (rois (B,post,4), scores (B,post,1))."""
+    cls_prob, bbox_pred, im_info = _f32(cls_prob), _f32(bbox_pred), _f32(im_info)
+    B, A2, H, W = cls_prob.shape
+    A = A2 // 2
+    assert A == len(scales) * len(ratios) and bbox_pred.shape == (B, 4 * A, H, W)
+    count = A * H * W
+    pre = min(rpn_pre_nms_top_n if rpn_pre_nms_top_n > 0 else count, count)
+    post = rpn_post_nms_top_n if not is_train else min(rpn_post_nms_top_n, pre)
+    out = np.empty((B, post, 4), np.float32)
+    sc = np.empty((B, post, 1), np.float32)
+    dets = np.empty((B, pre, 5), np.float32) if debug else None
+    keep = np.empty((B, pre), np.int32) if debug else None
+    nkeep = np.empty((B,), np.int32) if debug else None
+    r, s = _f32(ratios), _f32(scales)
+    lib().oracle_proposal_v3(_p(cls_prob), _p(bbox_pred), _p(im_info), B, A, H, W, int(feature_stride),
+                             _p(s), len(s), _p(r), len(r), int(rpn_pre_nms_top_n),
+                             int(rpn_post_nms_top_n), ctypes.c_float(threshold), int(rpn_min_size),
+                             int(bool(iou_loss)), int(bool(is_train)), _p(out), _p(sc), _p(dets),
+                             _p(keep), _p(nkeep))
+    return (out, sc, dets, keep, nkeep) if debug else (out, sc)
+
+
+def contrib_nms(proposals, rpn_pre_nms_top_n=6000, rpn_post_nms_top_n=300, threshold=0.7,
+                already_sorted=False):
+    """_contrib_NMS (nms.cu:274-364) -> (out (B,post,4), score (B,post,1)); rows >= min(post,pre)
+    are left untouched by the reference and returned as NaN here."""
+    proposals = _f32(proposals)
+    B, count, _ = proposals.shape
+    out = np.full((B, rpn_post_nms_top_n, 4), np.nan, np.float32)
+    sc = np.full((B, rpn_post_nms_top_n, 1), np.nan, np.float32)
+    lib().oracle_contrib_nms(_p(proposals), B, count, int(rpn_pre_nms_top_n), int(rpn_post_nms_top_n),
+                             ctypes.c_float(threshold), int(bool(already_sorted)), _p(out), _p(sc))
+    return out, sc
+
+
+def stable_argsort_desc(score):
+    score = _f32(score).ravel()
+    order = np.empty(score.shape[0], np.int32)
+    lib().oracle_stable_argsort_desc(_p(score), score.shape[0], _p(order))
+    return order
+
+
+def bbox_overlaps(boxes, query_boxes):
+    """bbox_overlaps_cython (bbox.pyx:32-73)."""
+    boxes, query_boxes = _f32(boxes), _f32(query_boxes)
+    out = np.empty((boxes.shape[0], query_boxes.shape[0]), np.float32)
+    lib().oracle_bbox_overlaps(_p(boxes), boxes.shape[0], _p(query_boxes), query_boxes.shape[0], _p(out))
+    return out
+
+
+def greedy_nms(dets, thresh, order=None):
+    """greedy_nms (cpu_nms.pyx:37-87) -> kept indices ascending (np.where(suppressed == 0)[0]).
+    `order` defaults to the reference's own `scores.argsort()[::-1]`."""
+    dets = _f32(dets)
+    if order is None:
+        order = dets[:, 4].argsort()[::-1]
+    order = np.ascontiguousarray(order, dtype=np.int64)
+    sup = np.empty(dets.shape[0], np.uint8)
+    lib().oracle_greedy_nms(_p(dets), dets.shape[0], _p(order), ctypes.c_float(thresh), _p(sup))
+    return np.where(sup == 0)[0]
+
+
+def soft_nms(boxes_in, sigma=0.5, Nt=0.3, threshold=0.001, method=0):
+    """soft_nms (cpu_nms.pyx:98-203) -> (boxes[:N], inds[:N])."""
+    boxes = _f32(boxes_in).copy()
+    inds = np.empty(boxes.shape[0], np.int64)
+    lib().oracle_soft_nms.restype = ctypes.c_int
+    n = lib().oracle_soft_nms(_p(boxes), _p(inds), boxes.shape[0], ctypes.c_float(sigma),
+                              ctypes.c_float(Nt), ctypes.c_float(threshold), ctypes.c_uint(method))
+    return boxes[:n], inds[:n]
+
+
+def ref_cython():
+    """The reference's own Cython modules built by oracle/build_ref.py (bbox, bbox_self, cpu_nms),
+    or None when oracle/_ref is absent."""
+    import importlib
+    import sys
+
+    d = os.path.join(_HERE, "_ref")
+    if not os.path.isdir(d):
+        return None
+    if not hasattr(np, "float"):
+        np.float = float  # the reference uses the alias NumPy removed (bbox_transform.py:20)
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    try:
+        return {m: importlib.import_module(m) for m in ("bbox", "bbox_self", "cpu_nms")}
+    except ImportError:
+        return None

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p
 
 from .build import LIB_PATH
 
@@ -40,8 +40,20 @@ _SIGNATURES = {
                                     c_int, c_float, _P],
     "sdet_roi_pooling_v1_backward": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, _P],
+    "sdet_decode_bbox": [_P, _P, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), c_int,
+                         c_int, _P],
+    "sdet_proposal_v3_workspace": [c_int, c_int, c_int, c_int, c_int],
+    "sdet_proposal_v3": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), c_int,
+                         POINTER(c_float), c_int, c_int, c_int, c_float, c_int, c_int, c_int, _P,
+                         c_size_t, _P],
+    "sdet_contrib_nms_workspace": [c_int, c_int, c_int],
+    "sdet_contrib_nms": [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P, c_size_t, _P],
+    "sdet_nms_workspace": [c_int, c_int],
+    "sdet_nms_sorted": [_P, _P, c_int, c_int, c_float, c_int, _P, _P, _P, c_size_t, _P],
 }
-_RESTYPES = {"sdet_last_error": c_char_p, "sdet_launch_count": c_uint64}
+_RESTYPES = {"sdet_last_error": c_char_p, "sdet_launch_count": c_uint64,
+             "sdet_proposal_v3_workspace": c_size_t, "sdet_contrib_nms_workspace": c_size_t,
+             "sdet_nms_workspace": c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

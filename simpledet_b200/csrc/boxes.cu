@@ -1,0 +1,543 @@
+// Box decode / proposal generation / NMS for sm_100a, everything on the device (the reference
+// copies to the host for DecodeBBox and for the greedy NMS scan — SURVEY.md §0.3).
+//
+//   sdet_decode_bbox       _contrib_DecodeBBox   operator_cxx/contrib/decodebbox.cc:34-133
+//   sdet_proposal_v3       _contrib_Proposal_v3  operator_cxx/contrib/proposal_v3.cu:435-638
+//   sdet_contrib_nms       _contrib_NMS          operator_cxx/contrib/nms.cu:274-364
+//   sdet_nms_sorted        batched greedy NMS over pre-sorted boxes (building block; also the
+//                          device side of the `_nms` compatibility export)
+//
+// Pipeline of a Proposal call (all (image) problems of the batch in each launch):
+//   1. proposal_topk_kernel  — one CTA per image: radix-select the top `pre` fg scores with the
+//      reference's stable order (topk.cuh), then decode + clip + min-size-filter ONLY those.
+//   2. nms_mask_kernel       — 64x64 IoU tiles -> suppression bitmask, upper triangle only.
+//   3. nms_scan_kernel       — one CTA per image walks the bitmask in 64-row blocks (the serial
+//      greedy dependency) and writes the padded outputs.  No host round trip, no sync.
+//
+// Float ops that feed an index decision (IoU vs threshold, min-size filter) are explicit
+// round-to-nearest intrinsics in the reference's source order, so keep/suppress decisions are
+// bit-identical to the oracle's for identical inputs.
+#include <cfloat>
+
+#include "common.cuh"
+#include "topk.cuh"
+
+namespace {
+
+using sdet::kTopkThreads;
+
+__device__ __forceinline__ float fmin_ref(float a, float b) { return a < b ? a : b; }  // CUDA min()
+__device__ __forceinline__ float fmax_ref(float a, float b) { return a < b ? b : a; }  // CUDA max()
+
+// --------------------------------------------------------------------------------------------
+// DecodeBBox: thread per (roi, class); float4 in / out.
+// --------------------------------------------------------------------------------------------
+struct DecodeParams {
+  float mean[4], std[4];
+  int class_agnostic, xyxy;
+};
+
+__global__ void __launch_bounds__(256)
+decode_bbox_kernel(const float4* __restrict__ rois, const float4* __restrict__ deltas,
+                   const float* __restrict__ im_info, float4* __restrict__ out, const int N,
+                   const int K, const int total, const DecodeParams p) {
+  const int ncls = p.class_agnostic ? 1 : K;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int cls = t % ncls;
+    const int ri = t / ncls;  // n*N + i
+    const int n = ri / N;
+    const float4 b = __ldg(rois + ri);
+    const float4 d = __ldg(deltas + (size_t)ri * K + (p.class_agnostic ? 1 : cls));
+    const float im_h = __ldg(im_info + n * 3), im_w = __ldg(im_info + n * 3 + 1);
+    const float width = __fadd_rn(__fsub_rn(b.z, b.x), 1.0f);
+    const float height = __fadd_rn(__fsub_rn(b.w, b.y), 1.0f);
+    const float dx = __fadd_rn(__fmul_rn(d.x, p.std[0]), p.mean[0]);
+    const float dy = __fadd_rn(__fmul_rn(d.y, p.std[1]), p.mean[1]);
+    const float dw = __fadd_rn(__fmul_rn(d.z, p.std[2]), p.mean[2]);
+    const float dh = __fadd_rn(__fmul_rn(d.w, p.std[3]), p.mean[3]);
+    float x1, y1, x2, y2;
+    if (!p.xyxy) {
+      const float ctr_x = __fadd_rn(b.x, __fmul_rn(0.5f, __fsub_rn(width, 1.0f)));
+      const float ctr_y = __fadd_rn(b.y, __fmul_rn(0.5f, __fsub_rn(height, 1.0f)));
+      const float pcx = __fadd_rn(__fmul_rn(dx, width), ctr_x);
+      const float pcy = __fadd_rn(__fmul_rn(dy, height), ctr_y);
+      const float pw = __fmul_rn(expf(dw), width);   // no exp clip in DecodeBBox (Appendix A.12)
+      const float ph = __fmul_rn(expf(dh), height);
+      const float hw = __fmul_rn(0.5f, __fsub_rn(pw, 1.0f)), hh = __fmul_rn(0.5f, __fsub_rn(ph, 1.0f));
+      x1 = __fsub_rn(pcx, hw);
+      y1 = __fsub_rn(pcy, hh);
+      x2 = __fadd_rn(pcx, hw);
+      y2 = __fadd_rn(pcy, hh);
+    } else {
+      x1 = __fadd_rn(b.x, __fmul_rn(dx, width));
+      y1 = __fadd_rn(b.y, __fmul_rn(dy, height));
+      x2 = __fadd_rn(b.z, __fmul_rn(dw, width));
+      y2 = __fadd_rn(b.w, __fmul_rn(dh, height));
+    }
+    const float mx = __fsub_rn(im_w, 1.0f), my = __fsub_rn(im_h, 1.0f);
+    float4 o;
+    o.x = fmax_ref(fmin_ref(x1, mx), 0.0f);
+    o.y = fmax_ref(fmin_ref(y1, my), 0.0f);
+    o.z = fmax_ref(fmin_ref(x2, mx), 0.0f);
+    o.w = fmax_ref(fmin_ref(y2, my), 0.0f);
+    out[(size_t)ri * ncls + cls] = o;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// NMS building blocks.  dets: (P, n, 5) rows [x1,y1,x2,y2,score] already in greedy order.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dev_iou(const float* a, const float* b) {
+  // devIoU, proposal_v3.cu:271-279
+  const float left = fmax_ref(a[0], b[0]), right = fmin_ref(a[2], b[2]);
+  const float top = fmax_ref(a[1], b[1]), bottom = fmin_ref(a[3], b[3]);
+  const float width = fmax_ref(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
+  const float height = fmax_ref(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
+  const float inter = __fmul_rn(width, height);
+  const float Sa = __fmul_rn(__fadd_rn(__fsub_rn(a[2], a[0]), 1.f), __fadd_rn(__fsub_rn(a[3], a[1]), 1.f));
+  const float Sb = __fmul_rn(__fadd_rn(__fsub_rn(b[2], b[0]), 1.f), __fadd_rn(__fsub_rn(b[3], b[1]), 1.f));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(Sa, Sb), inter));
+}
+
+// grid = (col_blocks, row_blocks, P); only col >= row tiles do work.  64 threads.
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const float* __restrict__ dets, const int* __restrict__ counts, const int n_max,
+                const float thr, const int ge, unsigned long long* __restrict__ mask) {
+  const int row_b = blockIdx.y, col_b = blockIdx.x, p = blockIdx.z;
+  if (col_b < row_b) return;  // the scan only reads words j >= row block (proposal_v3.cu:373)
+  const int n = counts ? counts[p] : n_max;
+  const int col_blocks = (n_max + 63) >> 6;
+  const int row_size = min(n - row_b * 64, 64), col_size = min(n - col_b * 64, 64);
+  if (row_size <= 0 || col_size <= 0) return;
+  const float* d = dets + (size_t)p * n_max * 5;
+  __shared__ float sb[64 * 5];
+  const int t = threadIdx.x;
+  if (t < col_size) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) sb[t * 5 + k] = d[(size_t)(col_b * 64 + t) * 5 + k];
+  }
+  __syncthreads();
+  if (t < row_size) {
+    const int cur = row_b * 64 + t;
+    float cb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cb[k] = d[(size_t)cur * 5 + k];
+    unsigned long long bits = 0;
+    const int start = (row_b == col_b) ? t + 1 : 0;
+    for (int i = start; i < col_size; ++i) {
+      const float v = dev_iou(cb, sb + i * 5);
+      if (ge ? (v >= thr) : (v > thr)) bits |= 1ull << i;
+    }
+    mask[((size_t)p * n_max + cur) * col_blocks + col_b] = bits;
+  }
+}
+
+struct ScanOut {
+  float* out;        // (P, out_rows, 4) or nullptr
+  float* out_score;  // (P, out_rows)
+  int* keep;         // (P, n_max) or nullptr: kept positions in greedy order
+  int* nkeep;        // (P) or nullptr
+  int out_rows;      // rows per problem in out/out_score
+  int write_rows;    // rows actually written (PrepareOutput's `count`)
+  int pad_mode;      // 0: zeros, 1: wrap keep[i % nkeep] (Proposal is_train)
+};
+
+// One CTA (256 threads) per problem: greedy scan of the bitmask in 64-row blocks.
+// Shared: removed words (col_blocks), kept list (n_max ints), one block of mask rows.
+__global__ void __launch_bounds__(256)
+nms_scan_kernel(const float* __restrict__ dets, const int* __restrict__ counts, const int n_max,
+                const unsigned long long* __restrict__ mask, const ScanOut o) {
+  extern __shared__ unsigned long long s_dyn[];
+  const int p = blockIdx.x;
+  const int n = counts ? counts[p] : n_max;
+  const int cbs = (n_max + 63) >> 6;
+  unsigned long long* s_removed = s_dyn;          // cbs words
+  unsigned long long* s_rows = s_dyn + cbs;       // 64 x cbs words (mask rows of one block)
+  int* s_keep = reinterpret_cast<int*>(s_rows + 64 * (size_t)cbs);  // n_max ints
+  __shared__ int s_nkeep;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < cbs; i += blockDim.x) s_removed[i] = 0ull;
+  if (tid == 0) s_nkeep = 0;
+  __syncthreads();
+  const unsigned long long* m = mask + (size_t)p * n_max * cbs;
+  const int nblocks = (n + 63) >> 6;
+  for (int rb = 0; rb < nblocks; ++rb) {
+    const int rows = min(64, n - rb * 64);
+    // stage this block's mask rows (only words >= rb are defined / needed)
+    for (int e = tid; e < rows * (cbs - rb); e += blockDim.x) {
+      const int r = e / (cbs - rb), w = rb + e % (cbs - rb);
+      s_rows[r * cbs + w] = m[(size_t)(rb * 64 + r) * cbs + w];
+    }
+    __syncthreads();
+    // the serial greedy dependency: warp 0 walks the 64 rows with the `removed` words held in
+    // registers (lane l owns words l, l+32, ...), one shuffle per row, no block barrier inside
+    if (tid < 32) {
+      constexpr int kWPL = 6;  // words per lane: up to 192 column blocks = 12288 boxes
+      unsigned long long rem[kWPL];
+#pragma unroll
+      for (int q = 0; q < kWPL; ++q) rem[q] = (tid + 32 * q < cbs) ? s_removed[tid + 32 * q] : 0ull;
+      int nk = s_nkeep;
+      const int owner = rb & 31, slot = rb >> 5;
+      for (int r = 0; r < rows; ++r) {
+        unsigned long long cur = 0ull;
+#pragma unroll
+        for (int q = 0; q < kWPL; ++q)
+          if (q == slot) cur = rem[q];
+        cur = __shfl_sync(0xffffffffu, cur, owner);
+        if (!((cur >> r) & 1ull)) {
+#pragma unroll
+          for (int q = 0; q < kWPL; ++q) {
+            const int w = tid + 32 * q;
+            if (w >= rb && w < cbs) rem[q] |= s_rows[r * cbs + w];
+          }
+          if (tid == 0) s_keep[nk] = rb * 64 + r;
+          ++nk;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kWPL; ++q)
+        if (tid + 32 * q < cbs) s_removed[tid + 32 * q] = rem[q];
+      if (tid == 0) s_nkeep = nk;
+    }
+    __syncthreads();
+  }
+  const int nk = s_nkeep;
+  if (o.nkeep && tid == 0) o.nkeep[p] = nk;
+  if (o.keep)
+    for (int i = tid; i < n_max; i += blockDim.x) o.keep[(size_t)p * n_max + i] = i < nk ? s_keep[i] : 0;
+  if (o.out) {  // PrepareOutput, proposal_v3.cu:387-419 / nms.cu:208-231
+    const float* d = dets + (size_t)p * n_max * 5;
+    for (int i = tid; i < o.write_rows; i += blockDim.x) {
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      float s = 0.f;
+      int k = -1;
+      if (i < nk) k = s_keep[i];
+      else if (o.pad_mode == 1 && nk > 0) k = s_keep[i % nk];
+      if (k >= 0) {
+        b = make_float4(d[(size_t)k * 5], d[(size_t)k * 5 + 1], d[(size_t)k * 5 + 2], d[(size_t)k * 5 + 3]);
+        s = d[(size_t)k * 5 + 4];
+      }
+      float* op = o.out + ((size_t)p * o.out_rows + i) * 4;
+      op[0] = b.x; op[1] = b.y; op[2] = b.z; op[3] = b.w;
+      o.out_score[(size_t)p * o.out_rows + i] = s;
+    }
+  }
+}
+
+size_t scan_smem_bytes(int n_max) {
+  const size_t cbs = (size_t)(n_max + 63) / 64;
+  return cbs * 8 + 64 * cbs * 8 + (size_t)n_max * 4;
+}
+
+// --------------------------------------------------------------------------------------------
+// Proposal_v3 stage 1: top-`pre` fg scores of one image -> decoded, clipped, filtered dets.
+// --------------------------------------------------------------------------------------------
+struct ProposalParams {
+  const float* cls_prob;   // (B, 2A, H, W)
+  const float* bbox_pred;  // (B, 4A, H, W)
+  const float* im_info;    // (B, 3)
+  float anchors[64 * 4];   // base anchors (A <= 64), proposal_v3-inl.h:280-318
+  int A, H, W, stride, pre, k_pow2;
+  int min_size, iou_loss;
+  float* dets;             // (B, pre, 5)
+};
+
+__global__ void __launch_bounds__(kTopkThreads)
+proposal_topk_kernel(const __grid_constant__ ProposalParams p) {
+  extern __shared__ unsigned long long s_sel[];
+  __shared__ uint32_t s_hist[sdet::kRadixBins];
+  const int b = blockIdx.x;
+  const int A = p.A, H = p.H, W = p.W, HW = H * W;
+  const int count = A * HW;
+  const float* fg = p.cls_prob + (size_t)b * 2 * count + count;  // second half = foreground (:522)
+  // element i is visited in MEMORY order (a, h, w) for coalescing; its reference index (the
+  // stable-sort tie breaker) is (h*W + w)*A + a  (ProposalGridKernel, :73-75)
+  auto key_at = [&](int i) -> uint64_t {
+    const int a = i / HW, r = i - a * HW;
+    return sdet::make_key(__ldg(fg + i), (uint32_t)(r * A + a));
+  };
+  sdet::block_topk_sorted(count, p.pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+  // decode only the winners
+  const float im_h = __ldg(p.im_info + b * 3), im_w = __ldg(p.im_info + b * 3 + 1);
+  const float im_s = __ldg(p.im_info + b * 3 + 2);
+  const int real_h = (int)__fdiv_rn(im_h, (float)p.stride), real_w = (int)__fdiv_rn(im_w, (float)p.stride);
+  const float* dl = p.bbox_pred + (size_t)b * 4 * count;
+  const float fs = (float)p.stride;
+  for (int j = threadIdx.x; j < p.pre; j += blockDim.x) {
+    const uint64_t key = reinterpret_cast<const uint64_t*>(s_sel)[j];
+    const int index = (int)sdet::key_index(key);
+    float sc = sdet::key_score(key);
+    const int a = index % A, w = (index / A) % W, h = index / A / W;
+    const float bx1 = __fadd_rn(p.anchors[a * 4 + 0], __fmul_rn((float)w, fs));  // :77-80 (int*int -> float add)
+    const float by1 = __fadd_rn(p.anchors[a * 4 + 1], __fmul_rn((float)h, fs));
+    const float bx2 = __fadd_rn(p.anchors[a * 4 + 2], __fmul_rn((float)w, fs));
+    const float by2 = __fadd_rn(p.anchors[a * 4 + 3], __fmul_rn((float)h, fs));
+    const float d0 = __ldg(dl + ((a * 4 + 0) * H + h) * W + w), d1 = __ldg(dl + ((a * 4 + 1) * H + h) * W + w);
+    const float d2 = __ldg(dl + ((a * 4 + 2) * H + h) * W + w), d3 = __ldg(dl + ((a * 4 + 3) * H + h) * W + w);
+    const float mx = __fsub_rn(im_w, 1.0f), my = __fsub_rn(im_h, 1.0f);
+    float x1, y1, x2, y2;
+    if (p.iou_loss) {  // IoUPredKernel :163-205
+      x1 = fmax_ref(fmin_ref(__fadd_rn(bx1, d0), mx), 0.0f);
+      y1 = fmax_ref(fmin_ref(__fadd_rn(by1, d1), my), 0.0f);
+      x2 = fmax_ref(fmin_ref(__fadd_rn(bx2, d2), mx), 0.0f);
+      y2 = fmax_ref(fmin_ref(__fadd_rn(by2, d3), my), 0.0f);
+      // (:200-202 would set score -1 for padded cells BEFORE the sort; handled in key_at? no —
+      //  see sdet_proposal_v3: iou_loss with padded cells is rejected as unsupported)
+    } else {           // BBoxPredKernel :93-155
+      const float width = __fadd_rn(__fsub_rn(bx2, bx1), 1.0f), height = __fadd_rn(__fsub_rn(by2, by1), 1.0f);
+      const float ctr_x = __fadd_rn(bx1, __fmul_rn(0.5f, width)), ctr_y = __fadd_rn(by1, __fmul_rn(0.5f, height));
+      const float dw = (float)fmin((double)d2, 4.135166556742356), dh = (float)fmin((double)d3, 4.135166556742356);
+      const float pcx = __fadd_rn(__fmul_rn(d0, width), ctr_x), pcy = __fadd_rn(__fmul_rn(d1, height), ctr_y);
+      const float pw = __fmul_rn(expf(dw), width), ph = __fmul_rn(expf(dh), height);
+      x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+      y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+      x2 = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.0f);
+      y2 = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), 1.0f);
+      x1 = fmax_ref(fmin_ref(x1, mx), 0.0f);
+      y1 = fmax_ref(fmin_ref(y1, my), 0.0f);
+      x2 = fmax_ref(fmin_ref(x2, mx), 0.0f);
+      y2 = fmax_ref(fmin_ref(y2, my), 0.0f);
+    }
+    (void)real_h; (void)real_w;
+    // FilterBoxKernel :211-235 (after top-k, original-image scale)
+    const float ws_o = __fadd_rn(__fdiv_rn(__fsub_rn(x2, x1), im_s), 1.0f);
+    const float hs_o = __fadd_rn(__fdiv_rn(__fsub_rn(y2, y1), im_s), 1.0f);
+    const float msm = fmax_ref((float)p.min_size, 1.0f);
+    const float ws = __fadd_rn(__fsub_rn(x2, x1), 1.0f), hs = __fadd_rn(__fsub_rn(y2, y1), 1.0f);
+    const float x_ctr = __fadd_rn(x1, __fdiv_rn(ws, 2.0f)), y_ctr = __fadd_rn(y1, __fdiv_rn(hs, 2.0f));
+    if (ws_o < msm || hs_o < msm || x_ctr >= im_w || y_ctr >= im_h) {
+      const float hm = __fdiv_rn(msm, 2.f);
+      x1 = __fsub_rn(x1, hm);
+      y1 = __fsub_rn(y1, hm);
+      x2 = __fadd_rn(x2, hm);
+      y2 = __fadd_rn(y2, hm);
+      sc = -1.0f;
+    }
+    float* o = p.dets + ((size_t)b * p.pre + j) * 5;
+    o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = sc;
+  }
+}
+
+// _contrib_NMS stage 1: top-`pre` rows of (count,5) proposals by column 4, gathered in order.
+__global__ void __launch_bounds__(kTopkThreads)
+rows_topk_kernel(const float* __restrict__ proposals, const int count, const int pre, const int k_pow2,
+                 const int already_sorted, float* __restrict__ dets) {
+  extern __shared__ unsigned long long s_sel[];
+  __shared__ uint32_t s_hist[sdet::kRadixBins];
+  const int b = blockIdx.x;
+  const float* src = proposals + (size_t)b * count * 5;
+  if (!already_sorted) {
+    auto key_at = [&](int i) -> uint64_t { return sdet::make_key(__ldg(src + (size_t)i * 5 + 4), (uint32_t)i); };
+    sdet::block_topk_sorted(count, pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), k_pow2);
+  }
+  for (int j = threadIdx.x; j < pre; j += blockDim.x) {
+    const int i = already_sorted ? j : (int)sdet::key_index(reinterpret_cast<const uint64_t*>(s_sel)[j]);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) dets[((size_t)b * pre + j) * 5 + k] = __ldg(src + (size_t)i * 5 + k);
+  }
+}
+
+// Base anchors exactly as proposal_v3-inl.h:280-318 (host, float).
+void gen_anchors_v3(int stride, const float* ratios, int nr, const float* scales, int ns, float* out) {
+  const float base2 = (float)(stride - 1.0);
+  int k = 0;
+  for (int j = 0; j < nr; ++j)
+    for (int s = 0; s < ns; ++s) {
+      const float w = base2 - 0.f + 1.0f, h = base2 - 0.f + 1.0f;
+      const float x_ctr = (float)(0.f + 0.5 * (w - 1.0f)), y_ctr = (float)(0.f + 0.5 * (h - 1.0f));
+      const float size = w * h;
+      const float size_ratios = std::floor(size / ratios[j]);
+      const float new_w = rintf(std::sqrt(size_ratios)) * scales[s];
+      const float new_h = rintf((new_w / scales[s] * ratios[j])) * scales[s];
+      out[k * 4 + 0] = x_ctr - 0.5f * (new_w - 1.0f);
+      out[k * 4 + 1] = y_ctr - 0.5f * (new_h - 1.0f);
+      out[k * 4 + 2] = x_ctr + 0.5f * (new_w - 1.0f);
+      out[k * 4 + 3] = y_ctr + 0.5f * (new_h - 1.0f);
+      ++k;
+    }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// workspace layout for P problems of n boxes: dets (P,n,5) f32 | mask (P,n,cbs) u64
+size_t nms_ws_bytes(int P, int n) {
+  const size_t cbs = (size_t)(n + 63) / 64;
+  return align_up((size_t)P * n * 5 * 4, 256) + align_up((size_t)P * n * cbs * 8, 256);
+}
+
+int run_mask_and_scan(const float* dets, const int* counts, int P, int n, float thr, int ge,
+                      unsigned long long* mask, const ScanOut& so, cudaStream_t st) {
+  const int cbs = (n + 63) / 64;
+  dim3 grid((unsigned)cbs, (unsigned)cbs, (unsigned)P);
+  nms_mask_kernel<<<grid, 64, 0, st>>>(dets, counts, n, thr, ge, mask);
+  SDET_LAUNCH_CHECK("nms_mask_kernel");
+  const size_t smem = scan_smem_bytes(n);
+  if (n > 12288 || smem > 200 * 1024)
+    return sdet::fail(SDET_ERR_UNSUPPORTED, "NMS over %d boxes needs %zu B shared memory", n, smem);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SDET_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  nms_scan_kernel<<<(unsigned)P, 256, smem, st>>>(dets, counts, n, mask, so);
+  SDET_LAUNCH_CHECK("nms_scan_kernel");
+  return SDET_OK;
+}
+
+template <typename K>
+int ensure_smem(K kernel, size_t bytes, size_t* configured) {
+  if (bytes > 200 * 1024) return sdet::fail(SDET_ERR_UNSUPPORTED, "top-k needs %zu B shared memory", bytes);
+  if (bytes > 48 * 1024 && bytes > *configured) {
+    SDET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    *configured = bytes;
+  }
+  return SDET_OK;
+}
+
+}  // namespace
+
+extern "C" int sdet_decode_bbox(const float* rois, const float* bbox_pred, const float* im_info,
+                                float* out, int B, int N, int K4, const float* bbox_mean,
+                                const float* bbox_std, int class_agnostic, int decode_type,
+                                void* stream) {
+  SDET_REQUIRE(rois && bbox_pred && im_info && out && bbox_mean && bbox_std, "NULL argument");
+  SDET_REQUIRE(B > 0 && N > 0 && K4 >= 4 && K4 % 4 == 0, "bad shape (bbox_pred last dim must be 4*K)");
+  SDET_REQUIRE(decode_type == 0 || decode_type == 1, "bbox_decode_type must be xywh(0) or xyxy(1)");
+  SDET_REQUIRE(!class_agnostic || K4 >= 8, "class_agnostic decode reads class slot 1 (decodebbox.cc:54)");
+  SDET_REQUIRE((reinterpret_cast<uintptr_t>(rois) | reinterpret_cast<uintptr_t>(bbox_pred) |
+                reinterpret_cast<uintptr_t>(out)) % 16 == 0, "rois / bbox_pred / out must be 16-byte aligned");
+  DecodeParams p;
+  for (int i = 0; i < 4; ++i) {
+    p.mean[i] = bbox_mean[i];
+    p.std[i] = bbox_std[i];
+  }
+  p.class_agnostic = class_agnostic ? 1 : 0;
+  p.xyxy = decode_type;
+  const int K = K4 / 4;
+  const int total = B * N * (class_agnostic ? 1 : K);
+  const int threads = 256;
+  int blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  decode_bbox_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(rois), reinterpret_cast<const float4*>(bbox_pred), im_info,
+      reinterpret_cast<float4*>(out), N, K, total, p);
+  SDET_LAUNCH_CHECK("decode_bbox_kernel");
+  return SDET_OK;
+}
+
+extern "C" size_t sdet_nms_workspace(int problems, int n) {
+  if (problems <= 0 || n <= 0) return 0;
+  return nms_ws_bytes(problems, n);
+}
+
+extern "C" int sdet_nms_sorted(const float* dets, const int* counts, int problems, int n, float thresh,
+                               int ge, int* keep, int* nkeep, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  SDET_REQUIRE(dets && keep && nkeep && workspace, "NULL argument");
+  SDET_REQUIRE(problems > 0 && n > 0, "problems and n must be > 0");
+  if (workspace_bytes < nms_ws_bytes(problems, n))
+    return sdet::fail(SDET_ERR_WORKSPACE, "workspace too small: need %zu bytes", nms_ws_bytes(problems, n));
+  auto* mask = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) +
+                                                     align_up((size_t)problems * n * 5 * 4, 256));
+  ScanOut so{};
+  so.keep = keep;
+  so.nkeep = nkeep;
+  return run_mask_and_scan(dets, counts, problems, n, thresh, ge, mask, so, (cudaStream_t)stream);
+}
+
+extern "C" size_t sdet_proposal_v3_workspace(int B, int A, int H, int W, int rpn_pre_nms_top_n) {
+  if (B <= 0 || A <= 0 || H <= 0 || W <= 0) return 0;
+  const int count = A * H * W;
+  int pre = rpn_pre_nms_top_n > 0 ? rpn_pre_nms_top_n : count;
+  if (pre > count) pre = count;
+  return nms_ws_bytes(B, pre);
+}
+
+extern "C" int sdet_proposal_v3(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                                float* out, float* out_score, int B, int A, int H, int W,
+                                int feature_stride, const float* scales, int num_scales,
+                                const float* ratios, int num_ratios, int rpn_pre_nms_top_n,
+                                int rpn_post_nms_top_n, float threshold, int rpn_min_size,
+                                int iou_loss, int is_train, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  SDET_REQUIRE(cls_prob && bbox_pred && im_info && out && out_score && scales && ratios && workspace,
+               "NULL argument");
+  SDET_REQUIRE(B > 0 && A > 0 && H > 0 && W > 0, "bad shape");
+  // CHECK_EQ(num_anchors, ratios.size() * scales.size())  (proposal_v3.cu:488)
+  SDET_REQUIRE(A == num_scales * num_ratios, "num_anchors (%d) != len(ratios)*len(scales) (%d)", A,
+               num_scales * num_ratios);
+  if (A > 64) return sdet::fail(SDET_ERR_UNSUPPORTED, "more than 64 anchors per cell");
+  if (iou_loss)
+    return sdet::fail(SDET_ERR_UNSUPPORTED, "iou_loss=True (IoUPredKernel masks padded cells before the sort) is not built yet");
+  SDET_REQUIRE(rpn_post_nms_top_n > 0, "rpn_post_nms_top_n must be > 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int count = A * H * W;
+  int pre = rpn_pre_nms_top_n > 0 ? rpn_pre_nms_top_n : count;  // -1 = all (proposal_v3.cu:470-471)
+  if (pre > count) pre = count;
+  int post = rpn_post_nms_top_n < pre ? rpn_post_nms_top_n : pre;
+  if (!is_train) post = rpn_post_nms_top_n;  // :473-475
+  if (workspace_bytes < nms_ws_bytes(B, pre))
+    return sdet::fail(SDET_ERR_WORKSPACE, "workspace too small: need %zu bytes", nms_ws_bytes(B, pre));
+  float* dets = static_cast<float*>(workspace);
+  auto* mask = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) +
+                                                     align_up((size_t)B * pre * 5 * 4, 256));
+  ProposalParams p{};
+  p.cls_prob = cls_prob;
+  p.bbox_pred = bbox_pred;
+  p.im_info = im_info;
+  gen_anchors_v3(feature_stride, ratios, num_ratios, scales, num_scales, p.anchors);
+  p.A = A; p.H = H; p.W = W; p.stride = feature_stride; p.pre = pre;
+  p.k_pow2 = sdet::next_pow2(pre);
+  p.min_size = rpn_min_size;
+  p.iou_loss = 0;
+  p.dets = dets;
+  static size_t configured = 0;
+  const size_t smem = (size_t)p.k_pow2 * 8;
+  if (int rc = ensure_smem(proposal_topk_kernel, smem, &configured)) return rc;
+  proposal_topk_kernel<<<(unsigned)B, kTopkThreads, smem, st>>>(p);
+  SDET_LAUNCH_CHECK("proposal_topk_kernel");
+  ScanOut so{};
+  so.out = out;
+  so.out_score = out_score;
+  so.out_rows = post;
+  so.write_rows = post;
+  so.pad_mode = is_train ? 1 : 0;
+  return run_mask_and_scan(dets, nullptr, B, pre, threshold, /*ge=*/1, mask, so, st);  // `>=` (:319)
+}
+
+extern "C" size_t sdet_contrib_nms_workspace(int B, int count, int rpn_pre_nms_top_n) {
+  if (B <= 0 || count <= 0) return 0;
+  int pre = rpn_pre_nms_top_n > 0 ? rpn_pre_nms_top_n : count;
+  if (pre > count) pre = count;
+  return nms_ws_bytes(B, pre);
+}
+
+extern "C" int sdet_contrib_nms(const float* proposals, float* out, float* out_score, int B, int count,
+                                int rpn_pre_nms_top_n, int rpn_post_nms_top_n, float threshold,
+                                int already_sorted, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  SDET_REQUIRE(proposals && out && out_score && workspace, "NULL argument");
+  SDET_REQUIRE(B > 0 && count > 0 && rpn_post_nms_top_n > 0, "bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  int pre = rpn_pre_nms_top_n > 0 ? rpn_pre_nms_top_n : count;
+  if (pre > count) pre = count;
+  const int post = rpn_post_nms_top_n < pre ? rpn_post_nms_top_n : pre;
+  if (workspace_bytes < nms_ws_bytes(B, pre))
+    return sdet::fail(SDET_ERR_WORKSPACE, "workspace too small: need %zu bytes", nms_ws_bytes(B, pre));
+  float* dets = static_cast<float*>(workspace);
+  auto* mask = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) +
+                                                     align_up((size_t)B * pre * 5 * 4, 256));
+  static size_t configured = 0;
+  const int k_pow2 = sdet::next_pow2(pre);
+  const size_t smem = (size_t)k_pow2 * 8;
+  if (int rc = ensure_smem(rows_topk_kernel, smem, &configured)) return rc;
+  rows_topk_kernel<<<(unsigned)B, kTopkThreads, smem, st>>>(proposals, count, pre, k_pow2, already_sorted, dets);
+  SDET_LAUNCH_CHECK("rows_topk_kernel");
+  ScanOut so{};
+  so.out = out;
+  so.out_score = out_score;
+  so.out_rows = rpn_post_nms_top_n;  // declared output rows (nms-inl.h:96-99)
+  so.write_rows = post;              // rows PrepareOutput touches (nms.cu:354-358)
+  so.pad_mode = 0;
+  return run_mask_and_scan(dets, nullptr, B, pre, threshold, /*ge=*/0, mask, so, st);  // `>` (nms.cu:140)
+}

@@ -1,0 +1,134 @@
+// Block-level exact top-k with the reference's ordering:  descending score, ties by ascending
+// index  ==  thrust::stable_sort_by_key(score, order, greater<float>()) truncated to k
+// (operator_cxx/contrib/proposal_v3.cu:564-568, nms.cu:307-311, models/FPN/get_top_proposal.py).
+//
+// One CTA owns one problem.  Keys are made unique by packing (sortable score bits, ~index) into
+// 64 bits; an 11-bit-digit radix SELECT finds the k-th key in <= 6 sweeps over the scores (3 when
+// the k-th score is untied), one more sweep compacts the k winners into shared memory, and a
+// bitonic network sorts them.  Only the k winners are ever decoded / gathered, never all n.
+#pragma once
+#include <cstdint>
+
+namespace sdet {
+
+constexpr int kTopkThreads = 1024;
+constexpr int kRadixBits = 11;
+constexpr int kRadixBins = 1 << kRadixBits;
+
+__device__ __forceinline__ uint32_t score_to_sortable(float s) {
+  const uint32_t u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // larger float -> larger uint
+}
+__device__ __forceinline__ uint64_t make_key(float s, uint32_t idx) {
+  return ((uint64_t)score_to_sortable(s) << 32) | (uint64_t)(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ uint32_t key_index(uint64_t key) { return 0xFFFFFFFFu - (uint32_t)key; }
+__device__ __forceinline__ float key_score(uint64_t key) {
+  const uint32_t u = (uint32_t)(key >> 32);
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+// Selects the k largest keys of {key(i) : i in [0,n)} into s_sel[0..k) (sorted descending; the
+// rest of s_sel up to next_pow2(k) is zero).  `KeyAt(i)` returns the 64-bit key of element i and
+// must be cheap and side-effect free (it is evaluated once per sweep).  All threads of the CTA
+// must call this; blockDim.x == kTopkThreads.  s_hist: kRadixBins uint32; s_sel: next_pow2(k) u64.
+template <typename KeyAt>
+__device__ void block_topk_sorted(int n, int k, KeyAt key_at, uint32_t* s_hist, uint64_t* s_sel,
+                                  int k_pow2) {
+  __shared__ uint64_t s_prefix;
+  __shared__ int s_need, s_done, s_cnt;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s_prefix = 0;
+    s_need = k;
+    s_done = (k >= n);  // everything is selected: threshold 0
+    s_cnt = 0;
+  }
+  __syncthreads();
+  for (int shift = 64 - kRadixBits; !s_done; shift -= kRadixBits) {
+    const int sh = shift < 0 ? 0 : shift;
+    const int bits = shift < 0 ? kRadixBits + shift : kRadixBits;  // last digit may be short
+    const uint64_t hi_mask = (sh + bits >= 64) ? 0ull : (~0ull << (sh + bits));
+    for (int i = tid; i < kRadixBins; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const uint64_t prefix = s_prefix;
+    // warp-aggregated histogram: equal digits inside a warp cost one shared atomic (RPN scores
+    // tie massively in degenerate inputs, e.g. the all-zero-weight detection_infer_speed harness)
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+      const int i = i0 + tid;
+      unsigned digit = 0xFFFFFFFFu;
+      if (i < n) {
+        const uint64_t key = key_at(i);
+        if ((key & hi_mask) == prefix) digit = (unsigned)(key >> sh) & ((1u << bits) - 1);
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, digit);
+      if (digit != 0xFFFFFFFFu && (tid & 31) == (__ffs(peers) - 1))
+        atomicAdd(&s_hist[digit], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    if (tid < 32) {  // one warp walks the bins from the top: find the digit of the k-th key
+      const int need = s_need;
+      const int nb = 1 << bits;
+      int cum = 0, found = -1, found_cum = 0;
+      for (int base = nb - 32; base >= 0 && found < 0; base -= 32) {
+        const int b = base + (31 - tid);  // lane 0 = highest bin of this group
+        const int h = (int)s_hist[b];
+        int inc = h;  // inclusive scan over lanes (descending bins)
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (tid >= o) inc += t;
+        }
+        const bool hit = (cum + inc >= need) && (cum + inc - h < need);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+          const int src = __ffs(m) - 1;
+          found = __shfl_sync(0xffffffffu, b, src);
+          found_cum = cum + __shfl_sync(0xffffffffu, inc - h, src);
+          const int hb = __shfl_sync(0xffffffffu, h, src);
+          if (tid == 0) {
+            s_prefix = prefix | ((uint64_t)found << sh);
+            s_need = need - found_cum;
+            if (hb == need - found_cum || sh == 0) s_done = 1;  // whole bin taken / last digit
+          }
+        }
+        cum += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    __syncthreads();
+  }
+  const uint64_t thr = s_prefix;  // every key >= thr is a winner (exactly k of them; keys unique)
+  for (int i = tid; i < k_pow2; i += blockDim.x) s_sel[i] = 0ull;
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    const uint64_t key = key_at(i);
+    if (key >= thr) {
+      const int p = atomicAdd(&s_cnt, 1);
+      if (p < k_pow2) s_sel[p] = key;
+    }
+  }
+  __syncthreads();
+  // bitonic sort, descending
+  for (int size = 2; size <= k_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (k_pow2 >> 1); t += blockDim.x) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint64_t a = s_sel[lo], b = s_sel[hi];
+        if ((a < b) == desc) {
+          s_sel[lo] = b;
+          s_sel[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+inline int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace sdet

@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import check
 
 __all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_raw",
-           "fpn_roi_align", "fpn_roi_align_raw", "OPS"]
+           "fpn_roi_align", "fpn_roi_align_raw", "DecodeBBox", "Proposal_v3", "NMS", "nms_sorted", "OPS"]
 
 
 def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor | None:
@@ -231,9 +231,123 @@ def ROIPooling_v1(data, rois, pooled_size, spatial_scale):
     return _ROIPoolingV1Fn.apply(data, rois, ph, pw, float(spatial_scale))
 
 
+# --------------------------------------------------------------------------------------------
+# _contrib_DecodeBBox  (operator_cxx/contrib/decodebbox.cc:150-209; params decodebbox-inl.h:50-69)
+# --------------------------------------------------------------------------------------------
+def _f4(v, name):
+    v = tuple(float(x) for x in v)
+    if len(v) != 4:
+        raise ValueError(f"{name} must have 4 values")
+    return (ctypes.c_float * 4)(*v)
+
+
+def DecodeBBox(rois, bbox_pred, im_info, bbox_mean=(0.0, 0.0, 0.0, 0.0), bbox_std=(0.1, 0.1, 0.2, 0.2),
+               class_agnostic=True, bbox_decode_type="xywh"):
+    """mx.sym.contrib.DecodeBBox / X.decode_bbox.  rois (B,N,4), bbox_pred (B,N,4K), im_info (B,3)
+    -> (B,N,4) if class_agnostic (the op's default!) else (B,N,4K).  No gradient (Backward writes
+    zeros, decodebbox.cc:212-229)."""
+    rois, bbox_pred, im_info = _dev(rois, "rois"), _dev(bbox_pred, "bbox_pred"), _dev(im_info, "im_info")
+    if rois.dim() != 3 or rois.shape[2] != 4:
+        raise ValueError("rois must be (B,N,4)")
+    if bbox_pred.dim() != 3 or bbox_pred.shape[:2] != rois.shape[:2] or bbox_pred.shape[2] % 4:
+        raise ValueError("bbox_pred must be (B,N,4K)")
+    if bbox_decode_type not in ("xywh", "xyxy"):
+        raise ValueError("bbox_decode_type must be 'xywh' or 'xyxy'")
+    B, N, K4 = bbox_pred.shape
+    out = torch.empty((B, N, 4 if class_agnostic else K4), device=rois.device, dtype=torch.float32)
+    check(_lib.lib().sdet_decode_bbox(_p(rois), _p(bbox_pred), _p(im_info), _p(out), B, N, K4,
+                                      _f4(bbox_mean, "bbox_mean"), _f4(bbox_std, "bbox_std"),
+                                      int(bool(class_agnostic)), 0 if bbox_decode_type == "xywh" else 1,
+                                      _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# _contrib_Proposal_v3  (operator_cxx/contrib/proposal_v3.cu:435-638)
+# --------------------------------------------------------------------------------------------
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def Proposal_v3(cls_prob, bbox_pred, im_info, rpn_pre_nms_top_n=6000, rpn_post_nms_top_n=300,
+                threshold=0.7, rpn_min_size=16, scales=(4.0, 8.0, 16.0, 32.0), ratios=(0.5, 1.0, 2.0),
+                feature_stride=16, output_score=False, iou_loss=False, is_train=False):
+    """mx.sym.contrib.Proposal_v3 with the op's own defaults (proposal_v3-inl.h:141-183).
+    Returns rois (B,post,4) — and scores (B,post,1) when output_score — exactly the visible
+    outputs of the reference op."""
+    cls_prob, bbox_pred, im_info = _dev(cls_prob, "cls_prob"), _dev(bbox_pred, "bbox_pred"), _dev(im_info, "im_info")
+    if cls_prob.dim() != 4 or cls_prob.shape[1] % 2:
+        raise ValueError("cls_prob must be (B,2A,H,W)")
+    B, A2, H, W = cls_prob.shape
+    A = A2 // 2
+    if tuple(bbox_pred.shape) != (B, 4 * A, H, W):
+        raise ValueError("bbox_pred must be (B,4A,H,W)")
+    if im_info.shape != (B, 3):
+        raise ValueError("im_info must be (B,3)")
+    count = A * H * W
+    pre = min(rpn_pre_nms_top_n if rpn_pre_nms_top_n > 0 else count, count)
+    post = rpn_post_nms_top_n if not is_train else min(rpn_post_nms_top_n, pre)
+    out = torch.empty((B, post, 4), device=cls_prob.device, dtype=torch.float32)
+    score = torch.empty((B, post, 1), device=cls_prob.device, dtype=torch.float32)
+    L = _lib.lib()
+    nbytes = L.sdet_proposal_v3_workspace(B, A, H, W, int(rpn_pre_nms_top_n))
+    ws = _ws(nbytes, cls_prob.device)
+    sc = (ctypes.c_float * len(scales))(*[float(x) for x in scales])
+    ra = (ctypes.c_float * len(ratios))(*[float(x) for x in ratios])
+    check(L.sdet_proposal_v3(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(out), _p(score), B, A, H, W,
+                             int(feature_stride), sc, len(scales), ra, len(ratios),
+                             int(rpn_pre_nms_top_n), int(rpn_post_nms_top_n), float(threshold),
+                             int(rpn_min_size), int(bool(iou_loss)), int(bool(is_train)), _p(ws), nbytes,
+                             _stream()))
+    return (out, score) if output_score else out
+
+
+# --------------------------------------------------------------------------------------------
+# _contrib_NMS  (operator_cxx/contrib/nms.cu:274-364)
+# --------------------------------------------------------------------------------------------
+def NMS(data, rpn_pre_nms_top_n=6000, rpn_post_nms_top_n=300, threshold=0.7, output_score=False,
+        already_sorted=False):
+    """mx.sym.contrib.NMS: data (B,count,5) -> rois (B,post,4) [, scores (B,post,1)].  Rows past
+    min(post, pre) are never written by the reference; they are zero here."""
+    data = _dev(data, "data")
+    if data.dim() != 3 or data.shape[2] != 5:
+        raise ValueError("data must be (B,count,5)")
+    B, count, _ = data.shape
+    out = torch.zeros((B, rpn_post_nms_top_n, 4), device=data.device, dtype=torch.float32)
+    score = torch.zeros((B, rpn_post_nms_top_n, 1), device=data.device, dtype=torch.float32)
+    L = _lib.lib()
+    nbytes = L.sdet_contrib_nms_workspace(B, count, int(rpn_pre_nms_top_n))
+    ws = _ws(nbytes, data.device)
+    check(L.sdet_contrib_nms(_p(data), _p(out), _p(score), B, count, int(rpn_pre_nms_top_n),
+                             int(rpn_post_nms_top_n), float(threshold), int(bool(already_sorted)), _p(ws),
+                             nbytes, _stream()))
+    return (out, score) if output_score else out
+
+
+def nms_sorted(dets, thresh, ge=True, counts=None):
+    """Batched greedy NMS over boxes already sorted by descending score.
+    dets (P,n,5) -> keep (P,n) int32 (kept positions, zero padded), nkeep (P) int32."""
+    dets = _dev(dets, "dets")
+    if dets.dim() != 3 or dets.shape[2] != 5:
+        raise ValueError("dets must be (P,n,5)")
+    P, n, _ = dets.shape
+    counts = _dev(counts, "counts", torch.int32)
+    keep = torch.empty((P, n), device=dets.device, dtype=torch.int32)
+    nkeep = torch.empty((P,), device=dets.device, dtype=torch.int32)
+    L = _lib.lib()
+    nbytes = L.sdet_nms_workspace(P, n)
+    ws = _ws(nbytes, dets.device)
+    check(L.sdet_nms_sorted(_p(dets), _p(counts), P, n, float(thresh), int(bool(ge)), _p(keep), _p(nkeep),
+                            _p(ws), nbytes, _stream()))
+    return keep, nkeep
+
+
 # Registry keyed by the reference's operator names (what symbol/builder.py binds by string).
 OPS = {
     "_contrib_ROIAlign_v2": ROIAlign_v2,
     "ROIPooling_v1": ROIPooling_v1,
     "fpn_roi_align": fpn_roi_align,  # fusion of assign_layer_fpn + ROIAlign_v2 x L + add_n
+    "_contrib_DecodeBBox": DecodeBBox,
+    "_contrib_Proposal_v3": Proposal_v3,
+    "_contrib_NMS": NMS,
 }

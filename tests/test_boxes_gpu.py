@@ -1,0 +1,142 @@
+"""DecodeBBox / Proposal_v3 / _contrib_NMS / batched greedy NMS: CUDA vs oracle through the C ABI.
+
+Index outputs (which boxes are selected, in which order, which are suppressed) must be exact;
+box coordinates are floats that pass through expf (CUDA's and glibc's differ by <= 2 ulp), so
+they are compared with rtol 1e-5 (north_star tolerance: 1e-4 relative)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from simpledet_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _boxes(rng, n, size=600):
+    xy = rng.uniform(0, size, (n, 2))
+    wh = rng.uniform(4, 200, (n, 2))
+    return np.concatenate([xy, xy + wh], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("agnostic", [True, False])
+@pytest.mark.parametrize("kind", ["xywh", "xyxy"])
+def test_decode_bbox(cuda, agnostic, kind):
+    rng = np.random.default_rng(1)
+    B, N, K = 2, 300, 81
+    rois = np.stack([_boxes(rng, N), _boxes(rng, N)])
+    deltas = (rng.standard_normal((B, N, 4 * K)) * 0.5).astype(np.float32)
+    im_info = np.array([[800, 1333, 1.5], [600, 700, 1.0]], np.float32)
+    mean, std = (0.0, 0.1, -0.05, 0.0), (0.1, 0.1, 0.2, 0.2)
+    ref = oracle.decode_bbox(rois, deltas, im_info, mean, std, agnostic, kind)
+    out = ops.DecodeBBox(_t(rois, cuda), _t(deltas, cuda), _t(im_info, cuda), mean, std, agnostic, kind)
+    assert out.shape == ref.shape
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-4)
+    if kind == "xyxy":  # no exp on this path: bit-exact
+        assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_decode_bbox_defaults_are_class_agnostic(cuda):
+    rois = torch.tensor([[[10.0, 10, 50, 60]]], device=cuda)
+    d = torch.zeros((1, 1, 8), device=cuda)
+    out = ops.DecodeBBox(rois, d, torch.tensor([[100.0, 100, 1]], device=cuda))
+    assert out.shape == (1, 1, 4) and torch.equal(out, rois)
+
+
+@pytest.mark.parametrize("n,thr,ge", [(1, 0.5, True), (63, 0.5, True), (64, 0.7, False), (65, 0.3, True),
+                                       (1000, 0.7, True), (2000, 0.5, False), (6000, 0.7, True)])
+def test_nms_sorted_exact(cuda, n, thr, ge):
+    rng = np.random.default_rng(n)
+    P = 3
+    dets = np.zeros((P, n, 5), np.float32)
+    for p in range(P):
+        b = _boxes(rng, n, 300 + 200 * p)
+        s = np.sort(rng.uniform(0, 1, n).astype(np.float32))[::-1]
+        dets[p] = np.concatenate([b, s[:, None]], 1)
+    keep, nkeep = ops.nms_sorted(_t(dets, cuda), thr, ge)
+    keep, nkeep = keep.cpu().numpy(), nkeep.cpu().numpy()
+    for p in range(P):
+        # oracle: greedy over the given order with the same comparator
+        if ge:
+            ref = oracle.greedy_nms(dets[p], thr, order=np.arange(n))
+        else:
+            o, _ = oracle.contrib_nms(dets[p][None], n, n, thr, already_sorted=True)
+            ref = None
+            kept_boxes = o[0][: int(nkeep[p])]
+            assert np.array_equal(kept_boxes, dets[p][keep[p, : nkeep[p]], :4])
+            assert int(nkeep[p]) == n or np.all(o[0][int(nkeep[p]):] == 0)
+        if ref is not None:
+            assert int(nkeep[p]) == len(ref)
+            assert np.array_equal(keep[p, : nkeep[p]], ref)
+
+
+def test_nms_sorted_counts_and_identical_boxes(cuda):
+    """All-identical boxes: IoU == 1 -> only the first survives; ragged counts per problem."""
+    n = 200
+    dets = np.tile(np.array([[10, 10, 50, 50, 0.5]], np.float32), (2, n, 1))
+    dets[1, :, :4] += np.arange(n, dtype=np.float32)[:, None] * 100  # disjoint -> all kept
+    counts = np.array([n, 77], np.int32)
+    keep, nkeep = ops.nms_sorted(_t(dets, cuda), 0.5, True, counts=_t(counts, cuda))
+    assert nkeep.cpu().tolist() == [1, 77]
+    assert keep[1, :77].cpu().tolist() == list(range(77))
+
+
+@pytest.mark.parametrize("is_train", [False, True])
+@pytest.mark.parametrize("hw,stride,pre,post", [((50, 84), 16, 1000, 1000), ((25, 42), 32, 2000, 2000),
+                                               ((100, 167), 8, 2000, 300)])
+def test_proposal_v3(cuda, is_train, hw, stride, pre, post):
+    rng = np.random.default_rng(pre + hw[0])
+    B, A = 2, 3
+    H, W = hw
+    cls = rng.uniform(0, 1, (B, 2 * A, H, W)).astype(np.float32)
+    # ties in the scores exercise the stable order (index ascending)
+    cls[:, A:, : H // 3] = np.round(cls[:, A:, : H // 3], 2)
+    deltas = (rng.standard_normal((B, 4 * A, H, W)) * 0.3).astype(np.float32)
+    im_info = np.array([[H * stride - 7, W * stride - 11, 1.0], [H * stride * 0.8, W * stride * 0.9, 1.6]], np.float32)
+    kw = dict(feature_stride=stride, scales=(8,), ratios=(0.5, 1, 2), rpn_pre_nms_top_n=pre,
+              rpn_post_nms_top_n=post, threshold=0.7, rpn_min_size=16 if stride > 8 else 0, is_train=is_train)
+    ro, rs, rdets, rkeep, rnk = oracle.proposal_v3(cls, deltas, im_info, debug=True, **kw)
+    out, sc = ops.Proposal_v3(_t(cls, cuda), _t(deltas, cuda), _t(im_info, cuda), output_score=True, **kw)
+    assert out.shape == ro.shape and sc.shape == rs.shape
+    # scores identify the selected anchors exactly (they are copied, not computed)
+    assert np.array_equal(sc.cpu().numpy(), rs)
+    np.testing.assert_allclose(out.cpu().numpy(), ro, rtol=1e-5, atol=1e-3)
+
+
+def test_proposal_v3_degenerate_harness(cuda):
+    """detection_infer_speed.py: zero weights -> constant fg prob 0.5, zero deltas,
+    im_info=(400, 666.5, 2): every score ties, order must be anchor-index order."""
+    B, A, H, W = 1, 3, 50, 84
+    cls = np.full((B, 2 * A, H, W), 0.5, np.float32)
+    deltas = np.zeros((B, 4 * A, H, W), np.float32)
+    im_info = np.array([[400, 666.5, 2.0]], np.float32)
+    kw = dict(feature_stride=16, scales=(8,), ratios=(0.5, 1, 2), rpn_pre_nms_top_n=1000,
+              rpn_post_nms_top_n=1000, threshold=0.7, rpn_min_size=0)
+    ro, rs = oracle.proposal_v3(cls, deltas, im_info, **kw)
+    out, sc = ops.Proposal_v3(_t(cls, cuda), _t(deltas, cuda), _t(im_info, cuda), output_score=True, **kw)
+    assert np.array_equal(sc.cpu().numpy(), rs)
+    assert np.array_equal(out.cpu().numpy(), ro)  # exp(0) = 1 exactly on both sides
+
+
+@pytest.mark.parametrize("sorted_in", [False, True])
+def test_contrib_nms(cuda, sorted_in):
+    rng = np.random.default_rng(5)
+    B, count = 2, 3000
+    props = np.zeros((B, count, 5), np.float32)
+    for b in range(B):
+        s = rng.uniform(0, 1, count).astype(np.float32)
+        s[::7] = 0.25  # ties
+        if sorted_in:
+            s = np.sort(s)[::-1]
+        props[b] = np.concatenate([_boxes(rng, count), s[:, None]], 1)
+    ro, rs = oracle.contrib_nms(props, 2000, 500, 0.6, already_sorted=sorted_in)
+    out, sc = ops.NMS(_t(props, cuda), 2000, 500, 0.6, output_score=True, already_sorted=sorted_in)
+    assert np.array_equal(out.cpu().numpy(), ro) and np.array_equal(sc.cpu().numpy(), rs)
+    # post > pre: rows beyond min(post, pre) are untouched by the reference (NaN in the oracle)
+    ro, rs = oracle.contrib_nms(props, 100, 300, 0.6, already_sorted=sorted_in)
+    out, sc = ops.NMS(_t(props, cuda), 100, 300, 0.6, output_score=True, already_sorted=sorted_in)
+    assert np.array_equal(out.cpu().numpy()[:, :100], ro[:, :100]) and np.isnan(ro[:, 100:]).all()
