@@ -131,6 +131,21 @@ int sdet_proposal_v3(const float* cls_prob, const float* bbox_pred, const float*
                      int rpn_min_size, int iou_loss, int is_train, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* All RPN levels of an FPN in one call: num_levels x _contrib_Proposal_v3 + Concat(dim=1)
+ * (models/FPN/builder.py:267-317).  cls_prob[l] (B,2A,H[l],W[l]), bbox_pred[l] (B,4A,H[l],W[l]);
+ * the pointer / H / W / feature_stride arrays are HOST arrays of length num_levels.
+ * out (B, num_levels*post, 4), out_score (B, num_levels*post, 1): level-major per image, each
+ * level's slice exactly what sdet_proposal_v3 writes for that level. */
+size_t sdet_proposal_v3_fpn_workspace(int B, int A, const int* H, const int* W, int num_levels,
+                                      int rpn_pre_nms_top_n);
+int sdet_proposal_v3_fpn(const float* const* cls_prob, const float* const* bbox_pred,
+                         const float* im_info, float* out, float* out_score, int B, int A,
+                         const int* H, const int* W, const int* feature_stride, int num_levels,
+                         const float* scales, int num_scales, const float* ratios, int num_ratios,
+                         int rpn_pre_nms_top_n, int rpn_post_nms_top_n, float threshold,
+                         int rpn_min_size, int iou_loss, int is_train, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * _contrib_NMS   (operator_cxx/contrib/nms.cu:274-364; params nms-inl.h:49-70)
  *   proposals (B,count,5) [x1,y1,x2,y2,score] -> out (B,rpn_post_nms_top_n,4), out_score
@@ -152,6 +167,28 @@ int sdet_contrib_nms(const float* proposals, float* out, float* out_score, int B
 size_t sdet_nms_workspace(int problems, int n);
 int sdet_nms_sorted(const float* dets, const int* counts, int problems, int n, float thresh, int ge,
                     int* keep, int* nkeep, void* workspace, size_t workspace_bytes, void* stream);
+
+/* get_top_proposal  (CustomOp models/FPN/get_top_proposal.py:15-40; mxnext.tvm.get_top_proposal
+ * at models/FPN/builder.py:319-321): per image keep the top_n rows by score, descending, ties by
+ * lower row index (mx.nd.argsort(is_ascend=False) treated as stable).
+ *   boxes (B,M,4), scores (B,M,1) -> out_boxes (B,top_n,4), out_scores (B,top_n,1). */
+int sdet_get_top_proposal(const float* boxes, const float* scores, float* out_boxes,
+                          float* out_scores, int B, int M, int top_n, void* stream);
+
+/* Test-time per-class NMS, batched: replaces detection_test.py:233-260 `do_nms` (a Python loop
+ * over classes inside multiprocessing.Pool) with operator_py/nms.py:41-75 semantics
+ * (score > min_det_score; greedy by descending score; keep IoU <= nms_thresh).
+ *   cls_score (B,N,K), bbox (B,N,4K) or (B,N,4); classes first_class..K-1 are processed
+ *   (detection_test.py iterates all K columns of the score it is given).
+ *   Problem p = b*(K-first_class) + (cid-first_class); n_pad = next_pow2(N) <= 4096.
+ *   dets (P,n_pad,5): class candidates in descending-score order (zero padded);
+ *   counts (P): candidates per problem; keep (P,n_pad): kept positions into dets; nkeep (P);
+ *   src_index (P,n_pad) or NULL: roi index of each candidate (-1 padding). */
+size_t sdet_multiclass_nms_workspace(int B, int N, int K, int first_class);
+int sdet_multiclass_nms(const float* cls_score, const float* bbox, int B, int N, int K, int bbox_dim,
+                        int first_class, float min_det_score, float nms_thresh, float* dets,
+                        int* counts, int* keep, int* nkeep, int* src_index, void* workspace,
+                        size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,14 +46,23 @@ _SIGNATURES = {
     "sdet_proposal_v3": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), c_int,
                          POINTER(c_float), c_int, c_int, c_int, c_float, c_int, c_int, c_int, _P,
                          c_size_t, _P],
+    "sdet_proposal_v3_fpn_workspace": [c_int, c_int, POINTER(c_int), POINTER(c_int), c_int, c_int],
+    "sdet_proposal_v3_fpn": [POINTER(_P), POINTER(_P), _P, _P, _P, c_int, c_int, POINTER(c_int),
+                             POINTER(c_int), POINTER(c_int), c_int, POINTER(c_float), c_int,
+                             POINTER(c_float), c_int, c_int, c_int, c_float, c_int, c_int, c_int, _P,
+                             c_size_t, _P],
     "sdet_contrib_nms_workspace": [c_int, c_int, c_int],
     "sdet_contrib_nms": [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P, c_size_t, _P],
+    "sdet_get_top_proposal": [_P, _P, _P, _P, c_int, c_int, c_int, _P],
+    "sdet_multiclass_nms_workspace": [c_int, c_int, c_int, c_int],
+    "sdet_multiclass_nms": [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P,
+                            _P, _P, c_size_t, _P],
     "sdet_nms_workspace": [c_int, c_int],
     "sdet_nms_sorted": [_P, _P, c_int, c_int, c_float, c_int, _P, _P, _P, c_size_t, _P],
 }
 _RESTYPES = {"sdet_last_error": c_char_p, "sdet_launch_count": c_uint64,
-             "sdet_proposal_v3_workspace": c_size_t, "sdet_contrib_nms_workspace": c_size_t,
-             "sdet_nms_workspace": c_size_t}
+             "sdet_proposal_v3_workspace": c_size_t, "sdet_proposal_v3_fpn_workspace": c_size_t, "sdet_contrib_nms_workspace": c_size_t,
+             "sdet_nms_workspace": c_size_t, "sdet_multiclass_nms_workspace": c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

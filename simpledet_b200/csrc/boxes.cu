@@ -17,7 +17,9 @@
 // Float ops that feed an index decision (IoU vs threshold, min-size filter) are explicit
 // round-to-nearest intrinsics in the reference's source order, so keep/suppress decisions are
 // bit-identical to the oracle's for identical inputs.
+#include <algorithm>
 #include <cfloat>
+#include <climits>
 
 #include "common.cuh"
 #include "topk.cuh"
@@ -140,6 +142,9 @@ struct ScanOut {
   int out_rows;      // rows per problem in out/out_score
   int write_rows;    // rows actually written (PrepareOutput's `count`)
   int pad_mode;      // 0: zeros, 1: wrap keep[i % nkeep] (Proposal is_train)
+  int level_B;       // 0: problem p writes rows [p*out_rows, ...).  >0: p = l*B + b writes image b's
+                     //    slice l of a (B, L*out_rows) level-major concat (models/FPN/builder.py:316-317)
+  int level_L;
 };
 
 // One CTA (256 threads) per problem: greedy scan of the bitmask in 64-row blocks.
@@ -169,36 +174,28 @@ nms_scan_kernel(const float* __restrict__ dets, const int* __restrict__ counts, 
       s_rows[r * cbs + w] = m[(size_t)(rb * 64 + r) * cbs + w];
     }
     __syncthreads();
-    // the serial greedy dependency: warp 0 walks the 64 rows with the `removed` words held in
-    // registers (lane l owns words l, l+32, ...), one shuffle per row, no block barrier inside
-    if (tid < 32) {
-      constexpr int kWPL = 6;  // words per lane: up to 192 column blocks = 12288 boxes
-      unsigned long long rem[kWPL];
-#pragma unroll
-      for (int q = 0; q < kWPL; ++q) rem[q] = (tid + 32 * q < cbs) ? s_removed[tid + 32 * q] : 0ull;
-      int nk = s_nkeep;
-      const int owner = rb & 31, slot = rb >> 5;
-      for (int r = 0; r < rows; ++r) {
-        unsigned long long cur = 0ull;
-#pragma unroll
-        for (int q = 0; q < kWPL; ++q)
-          if (q == slot) cur = rem[q];
-        cur = __shfl_sync(0xffffffffu, cur, owner);
-        if (!((cur >> r) & 1ull)) {
-#pragma unroll
-          for (int q = 0; q < kWPL; ++q) {
-            const int w = tid + 32 * q;
-            if (w >= rb && w < cbs) rem[q] |= s_rows[r * cbs + w];
-          }
-          if (tid == 0) s_keep[nk] = rb * 64 + r;
-          ++nk;
-        }
+    // The serial greedy dependency lives entirely inside the block's DIAGONAL word: every thread
+    // resolves it redundantly in registers (64 steps, broadcast LDS, no barrier), then the kept
+    // rows' words are OR-ed into `removed` in parallel (thread w owns word w).
+    unsigned long long alive = ~s_removed[rb];
+    if (rows < 64) alive &= (1ull << rows) - 1ull;
+    for (int r = 0; r < rows; ++r)
+      if ((alive >> r) & 1ull) alive &= ~s_rows[r * cbs + rb];
+    const int nk0 = s_nkeep;
+    __syncthreads();  // every thread has read s_removed[rb] / s_nkeep before they change
+    for (int w = rb + 1 + tid; w < cbs; w += blockDim.x) {
+      unsigned long long acc = s_removed[w];
+      unsigned long long bits = alive;
+      while (bits) {
+        const int r = __ffsll((long long)bits) - 1;
+        bits &= bits - 1ull;
+        acc |= s_rows[r * cbs + w];
       }
-#pragma unroll
-      for (int q = 0; q < kWPL; ++q)
-        if (tid + 32 * q < cbs) s_removed[tid + 32 * q] = rem[q];
-      if (tid == 0) s_nkeep = nk;
+      s_removed[w] = acc;
     }
+    if (tid < 64 && ((alive >> tid) & 1ull))
+      s_keep[nk0 + __popcll(alive & ((1ull << tid) - 1ull))] = rb * 64 + tid;
+    if (tid == 0) s_nkeep = nk0 + __popcll(alive);
     __syncthreads();
   }
   const int nk = s_nkeep;
@@ -217,9 +214,14 @@ nms_scan_kernel(const float* __restrict__ dets, const int* __restrict__ counts, 
         b = make_float4(d[(size_t)k * 5], d[(size_t)k * 5 + 1], d[(size_t)k * 5 + 2], d[(size_t)k * 5 + 3]);
         s = d[(size_t)k * 5 + 4];
       }
-      float* op = o.out + ((size_t)p * o.out_rows + i) * 4;
+      size_t row = (size_t)p * o.out_rows + i;
+      if (o.level_B > 0) {
+        const int l = p / o.level_B, bi = p - l * o.level_B;
+        row = ((size_t)bi * o.level_L + l) * o.out_rows + i;
+      }
+      float* op = o.out + row * 4;
       op[0] = b.x; op[1] = b.y; op[2] = b.z; op[3] = b.w;
-      o.out_score[(size_t)p * o.out_rows + i] = s;
+      o.out_score[row] = s;
     }
   }
 }
@@ -232,73 +234,83 @@ size_t scan_smem_bytes(int n_max) {
 // --------------------------------------------------------------------------------------------
 // Proposal_v3 stage 1: top-`pre` fg scores of one image -> decoded, clipped, filtered dets.
 // --------------------------------------------------------------------------------------------
-struct ProposalParams {
+constexpr int kMaxAnchors = 16;
+struct ProposalLevel {
   const float* cls_prob;   // (B, 2A, H, W)
   const float* bbox_pred;  // (B, 4A, H, W)
+  float anchors[kMaxAnchors * 4];  // base anchors of this stride, proposal_v3-inl.h:280-318
+  int H, W, stride, pre;   // pre = min(rpn_pre_nms_top_n, A*H*W) of this level
+};
+struct ProposalParams {
+  ProposalLevel lvl[SDET_MAX_LEVELS];
   const float* im_info;    // (B, 3)
-  float anchors[64 * 4];   // base anchors (A <= 64), proposal_v3-inl.h:280-318
-  int A, H, W, stride, pre, k_pow2;
-  int min_size, iou_loss;
-  float* dets;             // (B, pre, 5)
+  int B, A, num_levels;
+  int pre_max, k_pow2;     // row pitch of dets / smem keys (max over levels)
+  int min_size;
+  float* dets;             // (num_levels*B, pre_max, 5), problem p = l*B + b
+  int* counts;             // (num_levels*B) = pre of the level
 };
 
 __global__ void __launch_bounds__(kTopkThreads)
 proposal_topk_kernel(const __grid_constant__ ProposalParams p) {
   extern __shared__ unsigned long long s_sel[];
   __shared__ uint32_t s_hist[sdet::kRadixBins];
-  const int b = blockIdx.x;
-  const int A = p.A, H = p.H, W = p.W, HW = H * W;
-  const int count = A * HW;
-  const float* fg = p.cls_prob + (size_t)b * 2 * count + count;  // second half = foreground (:522)
+  const int prob = blockIdx.x;
+  const int l = prob / p.B, b = prob - l * p.B;
+  const ProposalLevel& L = p.lvl[l];
+  const int A = p.A, H = L.H, W = L.W, HW = H * W;
+  const int count = A * HW, pre = L.pre;
+  const float* fg = L.cls_prob + (size_t)b * 2 * count + count;  // second half = foreground (:522)
   // element i is visited in MEMORY order (a, h, w) for coalescing; its reference index (the
   // stable-sort tie breaker) is (h*W + w)*A + a  (ProposalGridKernel, :73-75)
+  const unsigned magic = 0xFFFFFFFFu / (unsigned)HW;  // a = i / HW without a divide (+ fix-up)
   auto key_at = [&](int i) -> uint64_t {
-    const int a = i / HW, r = i - a * HW;
+    int a = (int)__umulhi((unsigned)i, magic), r = i - a * HW;
+    while (r >= HW) {
+      r -= HW;
+      ++a;
+    }
     return sdet::make_key(__ldg(fg + i), (uint32_t)(r * A + a));
   };
-  sdet::block_topk_sorted(count, p.pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+  sdet::block_topk_sorted(count, pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+  if (threadIdx.x == 0) p.counts[prob] = pre;
   // decode only the winners
   const float im_h = __ldg(p.im_info + b * 3), im_w = __ldg(p.im_info + b * 3 + 1);
   const float im_s = __ldg(p.im_info + b * 3 + 2);
-  const int real_h = (int)__fdiv_rn(im_h, (float)p.stride), real_w = (int)__fdiv_rn(im_w, (float)p.stride);
-  const float* dl = p.bbox_pred + (size_t)b * 4 * count;
-  const float fs = (float)p.stride;
-  for (int j = threadIdx.x; j < p.pre; j += blockDim.x) {
+  const float* dl = L.bbox_pred + (size_t)b * 4 * count;
+  const float fs = (float)L.stride;
+  float* dets = p.dets + (size_t)prob * p.pre_max * 5;
+  for (int j = threadIdx.x; j < p.pre_max; j += blockDim.x) {
+    float* o = dets + (size_t)j * 5;
+    if (j >= pre) {  // padding rows of a level with fewer than pre_max anchors: never read (counts)
+      o[0] = o[1] = o[2] = o[3] = o[4] = 0.f;
+      continue;
+    }
     const uint64_t key = reinterpret_cast<const uint64_t*>(s_sel)[j];
     const int index = (int)sdet::key_index(key);
     float sc = sdet::key_score(key);
     const int a = index % A, w = (index / A) % W, h = index / A / W;
-    const float bx1 = __fadd_rn(p.anchors[a * 4 + 0], __fmul_rn((float)w, fs));  // :77-80 (int*int -> float add)
-    const float by1 = __fadd_rn(p.anchors[a * 4 + 1], __fmul_rn((float)h, fs));
-    const float bx2 = __fadd_rn(p.anchors[a * 4 + 2], __fmul_rn((float)w, fs));
-    const float by2 = __fadd_rn(p.anchors[a * 4 + 3], __fmul_rn((float)h, fs));
+    const float bx1 = __fadd_rn(L.anchors[a * 4 + 0], __fmul_rn((float)w, fs));  // :77-80
+    const float by1 = __fadd_rn(L.anchors[a * 4 + 1], __fmul_rn((float)h, fs));
+    const float bx2 = __fadd_rn(L.anchors[a * 4 + 2], __fmul_rn((float)w, fs));
+    const float by2 = __fadd_rn(L.anchors[a * 4 + 3], __fmul_rn((float)h, fs));
     const float d0 = __ldg(dl + ((a * 4 + 0) * H + h) * W + w), d1 = __ldg(dl + ((a * 4 + 1) * H + h) * W + w);
     const float d2 = __ldg(dl + ((a * 4 + 2) * H + h) * W + w), d3 = __ldg(dl + ((a * 4 + 3) * H + h) * W + w);
     const float mx = __fsub_rn(im_w, 1.0f), my = __fsub_rn(im_h, 1.0f);
-    float x1, y1, x2, y2;
-    if (p.iou_loss) {  // IoUPredKernel :163-205
-      x1 = fmax_ref(fmin_ref(__fadd_rn(bx1, d0), mx), 0.0f);
-      y1 = fmax_ref(fmin_ref(__fadd_rn(by1, d1), my), 0.0f);
-      x2 = fmax_ref(fmin_ref(__fadd_rn(bx2, d2), mx), 0.0f);
-      y2 = fmax_ref(fmin_ref(__fadd_rn(by2, d3), my), 0.0f);
-      // (:200-202 would set score -1 for padded cells BEFORE the sort; handled in key_at? no —
-      //  see sdet_proposal_v3: iou_loss with padded cells is rejected as unsupported)
-    } else {           // BBoxPredKernel :93-155
-      const float width = __fadd_rn(__fsub_rn(bx2, bx1), 1.0f), height = __fadd_rn(__fsub_rn(by2, by1), 1.0f);
-      const float ctr_x = __fadd_rn(bx1, __fmul_rn(0.5f, width)), ctr_y = __fadd_rn(by1, __fmul_rn(0.5f, height));
-      const float dw = (float)fmin((double)d2, 4.135166556742356), dh = (float)fmin((double)d3, 4.135166556742356);
-      const float pcx = __fadd_rn(__fmul_rn(d0, width), ctr_x), pcy = __fadd_rn(__fmul_rn(d1, height), ctr_y);
-      const float pw = __fmul_rn(expf(dw), width), ph = __fmul_rn(expf(dh), height);
-      x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
-      y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
-      x2 = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.0f);
-      y2 = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), 1.0f);
-      x1 = fmax_ref(fmin_ref(x1, mx), 0.0f);
-      y1 = fmax_ref(fmin_ref(y1, my), 0.0f);
-      x2 = fmax_ref(fmin_ref(x2, mx), 0.0f);
-      y2 = fmax_ref(fmin_ref(y2, my), 0.0f);
-    }
-    (void)real_h; (void)real_w;
+    // BBoxPredKernel :93-155
+    const float width = __fadd_rn(__fsub_rn(bx2, bx1), 1.0f), height = __fadd_rn(__fsub_rn(by2, by1), 1.0f);
+    const float ctr_x = __fadd_rn(bx1, __fmul_rn(0.5f, width)), ctr_y = __fadd_rn(by1, __fmul_rn(0.5f, height));
+    const float dw = (float)fmin((double)d2, 4.135166556742356), dh = (float)fmin((double)d3, 4.135166556742356);
+    const float pcx = __fadd_rn(__fmul_rn(d0, width), ctr_x), pcy = __fadd_rn(__fmul_rn(d1, height), ctr_y);
+    const float pw = __fmul_rn(expf(dw), width), ph = __fmul_rn(expf(dh), height);
+    float x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+    float y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+    float x2 = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.0f);
+    float y2 = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), 1.0f);
+    x1 = fmax_ref(fmin_ref(x1, mx), 0.0f);
+    y1 = fmax_ref(fmin_ref(y1, my), 0.0f);
+    x2 = fmax_ref(fmin_ref(x2, mx), 0.0f);
+    y2 = fmax_ref(fmin_ref(y2, my), 0.0f);
     // FilterBoxKernel :211-235 (after top-k, original-image scale)
     const float ws_o = __fadd_rn(__fdiv_rn(__fsub_rn(x2, x1), im_s), 1.0f);
     const float hs_o = __fadd_rn(__fdiv_rn(__fsub_rn(y2, y1), im_s), 1.0f);
@@ -313,7 +325,6 @@ proposal_topk_kernel(const __grid_constant__ ProposalParams p) {
       y2 = __fadd_rn(y2, hm);
       sc = -1.0f;
     }
-    float* o = p.dets + ((size_t)b * p.pre + j) * 5;
     o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = sc;
   }
 }
@@ -445,12 +456,94 @@ extern "C" int sdet_nms_sorted(const float* dets, const int* counts, int problem
   return run_mask_and_scan(dets, counts, problems, n, thresh, ge, mask, so, (cudaStream_t)stream);
 }
 
-extern "C" size_t sdet_proposal_v3_workspace(int B, int A, int H, int W, int rpn_pre_nms_top_n) {
-  if (B <= 0 || A <= 0 || H <= 0 || W <= 0) return 0;
+// workspace: dets (P,pre_max,5) | mask | counts (P)
+static size_t proposal_ws_bytes(int P, int pre_max) { return nms_ws_bytes(P, pre_max) + align_up((size_t)P * 4, 256); }
+
+static int level_pre(int A, int H, int W, int rpn_pre_nms_top_n) {
   const int count = A * H * W;
-  int pre = rpn_pre_nms_top_n > 0 ? rpn_pre_nms_top_n : count;
-  if (pre > count) pre = count;
-  return nms_ws_bytes(B, pre);
+  int pre = rpn_pre_nms_top_n > 0 ? rpn_pre_nms_top_n : count;  // -1 = all (proposal_v3.cu:470-471)
+  return pre > count ? count : pre;
+}
+
+extern "C" size_t sdet_proposal_v3_fpn_workspace(int B, int A, const int* H, const int* W, int num_levels,
+                                                 int rpn_pre_nms_top_n) {
+  if (B <= 0 || A <= 0 || !H || !W || num_levels <= 0) return 0;
+  int pre_max = 0;
+  for (int l = 0; l < num_levels; ++l) pre_max = std::max(pre_max, level_pre(A, H[l], W[l], rpn_pre_nms_top_n));
+  return proposal_ws_bytes(B * num_levels, pre_max);
+}
+
+extern "C" int sdet_proposal_v3_fpn(const float* const* cls_prob, const float* const* bbox_pred,
+                                    const float* im_info, float* out, float* out_score, int B, int A,
+                                    const int* H, const int* W, const int* feature_stride, int num_levels,
+                                    const float* scales, int num_scales, const float* ratios,
+                                    int num_ratios, int rpn_pre_nms_top_n, int rpn_post_nms_top_n,
+                                    float threshold, int rpn_min_size, int iou_loss, int is_train,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  SDET_REQUIRE(cls_prob && bbox_pred && im_info && out && out_score && scales && ratios && workspace && H &&
+               W && feature_stride, "NULL argument");
+  SDET_REQUIRE(B > 0 && A > 0 && num_levels >= 1 && num_levels <= SDET_MAX_LEVELS, "bad shape");
+  // CHECK_EQ(num_anchors, ratios.size() * scales.size())  (proposal_v3.cu:488)
+  SDET_REQUIRE(A == num_scales * num_ratios, "num_anchors (%d) != len(ratios)*len(scales) (%d)", A,
+               num_scales * num_ratios);
+  if (A > kMaxAnchors) return sdet::fail(SDET_ERR_UNSUPPORTED, "more than %d anchors per cell", kMaxAnchors);
+  if (iou_loss)
+    return sdet::fail(SDET_ERR_UNSUPPORTED,
+                      "iou_loss=True (IoUPredKernel masks padded cells before the sort) is not built yet");
+  SDET_REQUIRE(rpn_post_nms_top_n > 0, "rpn_post_nms_top_n must be > 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProposalParams p{};
+  int pre_max = 0, pre_min = INT_MAX;
+  for (int l = 0; l < num_levels; ++l) {
+    SDET_REQUIRE(cls_prob[l] && bbox_pred[l] && H[l] > 0 && W[l] > 0, "level %d: bad pointer / shape", l);
+    ProposalLevel& L = p.lvl[l];
+    L.cls_prob = cls_prob[l];
+    L.bbox_pred = bbox_pred[l];
+    L.H = H[l]; L.W = W[l]; L.stride = feature_stride[l];
+    L.pre = level_pre(A, H[l], W[l], rpn_pre_nms_top_n);
+    gen_anchors_v3(feature_stride[l], ratios, num_ratios, scales, num_scales, L.anchors);
+    pre_max = std::max(pre_max, L.pre);
+    pre_min = std::min(pre_min, L.pre);
+  }
+  // rows per level in the output: `post` (:472-475); with is_train it depends on the level's pre
+  int post = rpn_post_nms_top_n;
+  if (is_train) {
+    post = std::min(rpn_post_nms_top_n, pre_min);
+    if (num_levels > 1 && pre_min != pre_max && rpn_post_nms_top_n > pre_min)
+      return sdet::fail(SDET_ERR_UNSUPPORTED, "is_train with levels smaller than rpn_post_nms_top_n");
+  }
+  const int P = B * num_levels;
+  if (workspace_bytes < proposal_ws_bytes(P, pre_max))
+    return sdet::fail(SDET_ERR_WORKSPACE, "workspace too small: need %zu bytes", proposal_ws_bytes(P, pre_max));
+  char* wsb = static_cast<char*>(workspace);
+  float* dets = reinterpret_cast<float*>(wsb);
+  auto* mask = reinterpret_cast<unsigned long long*>(wsb + align_up((size_t)P * pre_max * 5 * 4, 256));
+  int* counts = reinterpret_cast<int*>(wsb + nms_ws_bytes(P, pre_max));
+  p.im_info = im_info;
+  p.B = B; p.A = A; p.num_levels = num_levels;
+  p.pre_max = pre_max;
+  p.k_pow2 = sdet::next_pow2(pre_max);
+  p.min_size = rpn_min_size;
+  p.dets = dets;
+  p.counts = counts;
+  static size_t configured = 0;
+  const size_t smem = (size_t)p.k_pow2 * 8;
+  if (int rc = ensure_smem(proposal_topk_kernel, smem, &configured)) return rc;
+  proposal_topk_kernel<<<(unsigned)P, kTopkThreads, smem, st>>>(p);
+  SDET_LAUNCH_CHECK("proposal_topk_kernel");
+  ScanOut so{};
+  so.out = out;
+  so.out_score = out_score;
+  so.out_rows = post;
+  so.write_rows = post;
+  so.pad_mode = is_train ? 1 : 0;
+  so.level_B = num_levels > 1 ? B : 0;
+  so.level_L = num_levels;
+  return run_mask_and_scan(dets, counts, P, pre_max, threshold, /*ge=*/1, mask, so, st);  // `>=` (:319)
+}
+
+extern "C" size_t sdet_proposal_v3_workspace(int B, int A, int H, int W, int rpn_pre_nms_top_n) {
+  return sdet_proposal_v3_fpn_workspace(B, A, &H, &W, 1, rpn_pre_nms_top_n);
 }
 
 extern "C" int sdet_proposal_v3(const float* cls_prob, const float* bbox_pred, const float* im_info,
@@ -460,49 +553,9 @@ extern "C" int sdet_proposal_v3(const float* cls_prob, const float* bbox_pred, c
                                 int rpn_post_nms_top_n, float threshold, int rpn_min_size,
                                 int iou_loss, int is_train, void* workspace, size_t workspace_bytes,
                                 void* stream) {
-  SDET_REQUIRE(cls_prob && bbox_pred && im_info && out && out_score && scales && ratios && workspace,
-               "NULL argument");
-  SDET_REQUIRE(B > 0 && A > 0 && H > 0 && W > 0, "bad shape");
-  // CHECK_EQ(num_anchors, ratios.size() * scales.size())  (proposal_v3.cu:488)
-  SDET_REQUIRE(A == num_scales * num_ratios, "num_anchors (%d) != len(ratios)*len(scales) (%d)", A,
-               num_scales * num_ratios);
-  if (A > 64) return sdet::fail(SDET_ERR_UNSUPPORTED, "more than 64 anchors per cell");
-  if (iou_loss)
-    return sdet::fail(SDET_ERR_UNSUPPORTED, "iou_loss=True (IoUPredKernel masks padded cells before the sort) is not built yet");
-  SDET_REQUIRE(rpn_post_nms_top_n > 0, "rpn_post_nms_top_n must be > 0");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int count = A * H * W;
-  int pre = rpn_pre_nms_top_n > 0 ? rpn_pre_nms_top_n : count;  // -1 = all (proposal_v3.cu:470-471)
-  if (pre > count) pre = count;
-  int post = rpn_post_nms_top_n < pre ? rpn_post_nms_top_n : pre;
-  if (!is_train) post = rpn_post_nms_top_n;  // :473-475
-  if (workspace_bytes < nms_ws_bytes(B, pre))
-    return sdet::fail(SDET_ERR_WORKSPACE, "workspace too small: need %zu bytes", nms_ws_bytes(B, pre));
-  float* dets = static_cast<float*>(workspace);
-  auto* mask = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) +
-                                                     align_up((size_t)B * pre * 5 * 4, 256));
-  ProposalParams p{};
-  p.cls_prob = cls_prob;
-  p.bbox_pred = bbox_pred;
-  p.im_info = im_info;
-  gen_anchors_v3(feature_stride, ratios, num_ratios, scales, num_scales, p.anchors);
-  p.A = A; p.H = H; p.W = W; p.stride = feature_stride; p.pre = pre;
-  p.k_pow2 = sdet::next_pow2(pre);
-  p.min_size = rpn_min_size;
-  p.iou_loss = 0;
-  p.dets = dets;
-  static size_t configured = 0;
-  const size_t smem = (size_t)p.k_pow2 * 8;
-  if (int rc = ensure_smem(proposal_topk_kernel, smem, &configured)) return rc;
-  proposal_topk_kernel<<<(unsigned)B, kTopkThreads, smem, st>>>(p);
-  SDET_LAUNCH_CHECK("proposal_topk_kernel");
-  ScanOut so{};
-  so.out = out;
-  so.out_score = out_score;
-  so.out_rows = post;
-  so.write_rows = post;
-  so.pad_mode = is_train ? 1 : 0;
-  return run_mask_and_scan(dets, nullptr, B, pre, threshold, /*ge=*/1, mask, so, st);  // `>=` (:319)
+  return sdet_proposal_v3_fpn(&cls_prob, &bbox_pred, im_info, out, out_score, B, A, &H, &W, &feature_stride, 1,
+                              scales, num_scales, ratios, num_ratios, rpn_pre_nms_top_n, rpn_post_nms_top_n,
+                              threshold, rpn_min_size, iou_loss, is_train, workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t sdet_contrib_nms_workspace(int B, int count, int rpn_pre_nms_top_n) {

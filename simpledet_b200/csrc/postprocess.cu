@@ -1,0 +1,136 @@
+// Cross-level top proposals and test-time per-class NMS, on the device.
+//
+//   sdet_get_top_proposal   models/FPN/get_top_proposal.py:15-40 (CustomOp `get_top_proposal`,
+//                           = mxnext.tvm.get_top_proposal at models/FPN/builder.py:319-321)
+//   sdet_multiclass_nms     detection_test.py:233-260 `do_nms` (per class: score > min_det_score,
+//                           operator_py/nms.py:41-75 `nms`, IoU <= thr kept), all (image, class)
+//                           problems of a batch in three launches instead of a Python loop inside
+//                           a multiprocessing pool.
+#include "common.cuh"
+#include "topk.cuh"
+
+namespace {
+
+using sdet::kTopkThreads;
+
+__global__ void __launch_bounds__(kTopkThreads)
+top_proposal_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, const int M,
+                    const int top_n, const int k_pow2, float* __restrict__ out_boxes,
+                    float* __restrict__ out_scores) {
+  extern __shared__ unsigned long long s_sel[];
+  __shared__ uint32_t s_hist[sdet::kRadixBins];
+  const int b = blockIdx.x;
+  const float* sc = scores + (size_t)b * M;
+  auto key_at = [&](int i) -> uint64_t { return sdet::make_key(__ldg(sc + i), (uint32_t)i); };
+  sdet::block_topk_sorted(M, top_n, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), k_pow2);
+  const float4* bx = reinterpret_cast<const float4*>(boxes) + (size_t)b * M;
+  for (int j = threadIdx.x; j < top_n; j += blockDim.x) {
+    const uint64_t key = reinterpret_cast<const uint64_t*>(s_sel)[j];
+    const int i = (int)sdet::key_index(key);
+    reinterpret_cast<float4*>(out_boxes)[(size_t)b * top_n + j] = __ldg(bx + i);
+    out_scores[(size_t)b * top_n + j] = __ldg(sc + i);
+  }
+}
+
+// One CTA per (image, class) problem, N <= 2048 candidates: threshold, sort descending
+// (ties: lower roi index first), write dets (P, n_pad, 5) + counts (P).
+__global__ void __launch_bounds__(1024)
+class_sort_kernel(const float* __restrict__ cls_score, const float* __restrict__ bbox, const int N,
+                  const int K, const int bbox_dim, const int first_class, const float min_score,
+                  const int n_pad, float* __restrict__ dets, int* __restrict__ counts,
+                  int* __restrict__ src_index) {
+  extern __shared__ unsigned long long s_keys[];
+  __shared__ int s_valid;
+  const int ncls = K - first_class;
+  const int p = blockIdx.x, b = p / ncls, cid = first_class + p % ncls;
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+    uint64_t key = 0ull;
+    if (i < N) {
+      const float s = __ldg(cls_score + ((size_t)b * N + i) * K + cid);
+      if (s > min_score) {  // detection_test.py:243
+        key = sdet::make_key(s, (uint32_t)i);
+        ++mine;
+      }
+    }
+    s_keys[i] = key;
+  }
+  if (mine) atomicAdd(&s_valid, mine);
+  __syncthreads();
+  for (int size = 2; size <= n_pad; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride), hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = s_keys[lo], c = s_keys[hi];
+        if ((a < c) == desc) {
+          s_keys[lo] = c;
+          s_keys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  const int nv = s_valid;
+  if (threadIdx.x == 0) counts[p] = nv;
+  for (int j = threadIdx.x; j < n_pad; j += blockDim.x) {
+    float* o = dets + ((size_t)p * n_pad + j) * 5;
+    if (j < nv) {
+      const uint64_t key = s_keys[j];
+      const int i = (int)sdet::key_index(key);
+      const float* bp = bbox + ((size_t)b * N + i) * bbox_dim + (bbox_dim == 4 ? 0 : cid * 4);
+      o[0] = __ldg(bp); o[1] = __ldg(bp + 1); o[2] = __ldg(bp + 2); o[3] = __ldg(bp + 3);
+      o[4] = sdet::key_score(key);
+      if (src_index) src_index[(size_t)p * n_pad + j] = i;
+    } else {
+      o[0] = o[1] = o[2] = o[3] = o[4] = 0.f;
+      if (src_index) src_index[(size_t)p * n_pad + j] = -1;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int sdet_get_top_proposal(const float* boxes, const float* scores, float* out_boxes,
+                                     float* out_scores, int B, int M, int top_n, void* stream) {
+  SDET_REQUIRE(boxes && scores && out_boxes && out_scores, "NULL argument");
+  SDET_REQUIRE(B > 0 && M > 0 && top_n > 0 && top_n <= M, "need 0 < top_n <= M");
+  SDET_REQUIRE((reinterpret_cast<uintptr_t>(boxes) | reinterpret_cast<uintptr_t>(out_boxes)) % 16 == 0,
+               "boxes must be 16-byte aligned");
+  const int k_pow2 = sdet::next_pow2(top_n);
+  const size_t smem = (size_t)k_pow2 * 8;
+  if (smem > 200 * 1024) return sdet::fail(SDET_ERR_UNSUPPORTED, "top_n too large");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SDET_CUDA(cudaFuncSetAttribute(top_proposal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  top_proposal_kernel<<<(unsigned)B, kTopkThreads, smem, (cudaStream_t)stream>>>(
+      boxes, scores, M, top_n, k_pow2, out_boxes, out_scores);
+  SDET_LAUNCH_CHECK("top_proposal_kernel");
+  return SDET_OK;
+}
+
+extern "C" size_t sdet_multiclass_nms_workspace(int B, int N, int K, int first_class) {
+  if (B <= 0 || N <= 0 || K <= first_class) return 0;
+  return sdet_nms_workspace(B * (K - first_class), sdet::next_pow2(N));
+}
+
+extern "C" int sdet_multiclass_nms(const float* cls_score, const float* bbox, int B, int N, int K,
+                                   int bbox_dim, int first_class, float min_det_score, float nms_thresh,
+                                   float* dets, int* counts, int* keep, int* nkeep, int* src_index,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  SDET_REQUIRE(cls_score && bbox && dets && counts && keep && nkeep && workspace, "NULL argument");
+  SDET_REQUIRE(B > 0 && N > 0 && K > first_class && first_class >= 0, "bad shape");
+  SDET_REQUIRE(bbox_dim == 4 || bbox_dim == 4 * K, "bbox last dim must be 4 or 4*K");
+  const int n_pad = sdet::next_pow2(N);
+  if (n_pad > 4096) return sdet::fail(SDET_ERR_UNSUPPORTED, "more than 4096 candidates per image");
+  const int P = B * (K - first_class);
+  class_sort_kernel<<<(unsigned)P, 1024, (size_t)n_pad * 8, (cudaStream_t)stream>>>(
+      cls_score, bbox, N, K, bbox_dim, first_class, min_det_score, n_pad, dets, counts, src_index);
+  SDET_LAUNCH_CHECK("class_sort_kernel");
+  // operator_py/nms.py:72 keeps ovr <= thresh  <=>  suppress ovr > thresh (ge = 0)
+  return sdet_nms_sorted(dets, counts, P, n_pad, nms_thresh, 0, keep, nkeep, workspace, workspace_bytes,
+                         stream);
+}

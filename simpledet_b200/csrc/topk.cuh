@@ -52,8 +52,8 @@ __device__ void block_topk_sorted(int n, int k, KeyAt key_at, uint32_t* s_hist, 
     for (int i = tid; i < kRadixBins; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     const uint64_t prefix = s_prefix;
-    // warp-aggregated histogram: equal digits inside a warp cost one shared atomic (RPN scores
-    // tie massively in degenerate inputs, e.g. the all-zero-weight detection_infer_speed harness)
+    // a warp whose 32 digits agree costs one shared atomic (RPN scores tie massively in degenerate
+    // inputs, e.g. the all-zero-weight detection_infer_speed harness); otherwise plain atomics
     for (int i0 = 0; i0 < n; i0 += blockDim.x) {
       const int i = i0 + tid;
       unsigned digit = 0xFFFFFFFFu;
@@ -61,9 +61,12 @@ __device__ void block_topk_sorted(int n, int k, KeyAt key_at, uint32_t* s_hist, 
         const uint64_t key = key_at(i);
         if ((key & hi_mask) == prefix) digit = (unsigned)(key >> sh) & ((1u << bits) - 1);
       }
-      const unsigned peers = __match_any_sync(0xffffffffu, digit);
-      if (digit != 0xFFFFFFFFu && (tid & 31) == (__ffs(peers) - 1))
-        atomicAdd(&s_hist[digit], (unsigned)__popc(peers));
+      const unsigned lead = __shfl_sync(0xffffffffu, digit, 0);
+      if (__all_sync(0xffffffffu, digit == lead)) {  // whole warp in one bin: one atomic
+        if ((tid & 31) == 0 && digit != 0xFFFFFFFFu) atomicAdd(&s_hist[digit], 32u);
+      } else if (digit != 0xFFFFFFFFu) {
+        atomicAdd(&s_hist[digit], 1u);
+      }
     }
     __syncthreads();
     if (tid < 32) {  // one warp walks the bins from the top: find the digit of the k-th key

@@ -19,7 +19,8 @@ from . import _lib
 from ._lib import check
 
 __all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_raw",
-           "fpn_roi_align", "fpn_roi_align_raw", "DecodeBBox", "Proposal_v3", "NMS", "nms_sorted", "OPS"]
+           "fpn_roi_align", "fpn_roi_align_raw", "DecodeBBox", "Proposal_v3", "Proposal_v3_fpn", "NMS", "nms_sorted", "get_top_proposal",
+           "multiclass_nms", "OPS"]
 
 
 def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor | None:
@@ -302,6 +303,44 @@ def Proposal_v3(cls_prob, bbox_pred, im_info, rpn_pre_nms_top_n=6000, rpn_post_n
     return (out, score) if output_score else out
 
 
+def Proposal_v3_fpn(cls_probs, bbox_preds, im_info, feature_strides, rpn_pre_nms_top_n=6000,
+                    rpn_post_nms_top_n=300, threshold=0.7, rpn_min_size=16, scales=(4.0, 8.0, 16.0, 32.0),
+                    ratios=(0.5, 1.0, 2.0), iou_loss=False, is_train=False):
+    """All FPN levels at once: [Proposal_v3(level) for level in strides] + Concat(dim=1), exactly
+    FPNRpnHead.get_all_proposal (models/FPN/builder.py:267-317).  -> (rois (B,L*post,4),
+    scores (B,L*post,1)), level-major."""
+    L_ = len(cls_probs)
+    cls_probs = [_dev(c, f"cls_prob[{i}]") for i, c in enumerate(cls_probs)]
+    bbox_preds = [_dev(c, f"bbox_pred[{i}]") for i, c in enumerate(bbox_preds)]
+    im_info = _dev(im_info, "im_info")
+    B, A2 = cls_probs[0].shape[:2]
+    A = A2 // 2
+    for c, d in zip(cls_probs, bbox_preds):
+        if c.dim() != 4 or c.shape[0] != B or c.shape[1] != A2 or tuple(d.shape) != (B, 4 * A, c.shape[2], c.shape[3]):
+            raise ValueError("each level needs cls_prob (B,2A,H,W) and bbox_pred (B,4A,H,W)")
+    pres = [min(rpn_pre_nms_top_n if rpn_pre_nms_top_n > 0 else A * c.shape[2] * c.shape[3],
+                A * c.shape[2] * c.shape[3]) for c in cls_probs]
+    post = rpn_post_nms_top_n if not is_train else min(rpn_post_nms_top_n, min(pres))
+    dev = cls_probs[0].device
+    out = torch.empty((B, L_ * post, 4), device=dev, dtype=torch.float32)
+    score = torch.empty((B, L_ * post, 1), device=dev, dtype=torch.float32)
+    cp = (ctypes.c_void_p * L_)(*[c.data_ptr() for c in cls_probs])
+    bp = (ctypes.c_void_p * L_)(*[c.data_ptr() for c in bbox_preds])
+    Hs = (ctypes.c_int * L_)(*[c.shape[2] for c in cls_probs])
+    Ws = (ctypes.c_int * L_)(*[c.shape[3] for c in cls_probs])
+    Ss = (ctypes.c_int * L_)(*[int(s) for s in feature_strides])
+    sc = (ctypes.c_float * len(scales))(*[float(x) for x in scales])
+    ra = (ctypes.c_float * len(ratios))(*[float(x) for x in ratios])
+    Lb = _lib.lib()
+    nbytes = Lb.sdet_proposal_v3_fpn_workspace(B, A, Hs, Ws, L_, int(rpn_pre_nms_top_n))
+    ws = _ws(nbytes, dev)
+    check(Lb.sdet_proposal_v3_fpn(cp, bp, _p(im_info), _p(out), _p(score), B, A, Hs, Ws, Ss, L_, sc, len(scales),
+                                  ra, len(ratios), int(rpn_pre_nms_top_n), int(rpn_post_nms_top_n),
+                                  float(threshold), int(rpn_min_size), int(bool(iou_loss)), int(bool(is_train)),
+                                  _p(ws), nbytes, _stream()))
+    return out, score
+
+
 # --------------------------------------------------------------------------------------------
 # _contrib_NMS  (operator_cxx/contrib/nms.cu:274-364)
 # --------------------------------------------------------------------------------------------
@@ -342,6 +381,49 @@ def nms_sorted(dets, thresh, ge=True, counts=None):
     return keep, nkeep
 
 
+# --------------------------------------------------------------------------------------------
+# get_top_proposal (models/FPN/get_top_proposal.py) and test-time per-class NMS
+# (detection_test.py:233-260 + operator_py/nms.py:41-75)
+# --------------------------------------------------------------------------------------------
+def get_top_proposal(bbox, score, top_n):
+    """CustomOp `get_top_proposal` / mxnext.tvm.get_top_proposal: bbox (B,M,4), score (B,M,1)
+    -> (bbox (B,top_n,4), score (B,top_n,1)) sorted by descending score."""
+    bbox, score = _dev(bbox, "bbox"), _dev(score, "score")
+    B, M, _ = bbox.shape
+    if score.shape[:2] != (B, M):
+        raise ValueError("score must be (B,M,1)")
+    ob = torch.empty((B, top_n, 4), device=bbox.device, dtype=torch.float32)
+    os_ = torch.empty((B, top_n, 1), device=bbox.device, dtype=torch.float32)
+    check(_lib.lib().sdet_get_top_proposal(_p(bbox), _p(score), _p(ob), _p(os_), B, M, int(top_n), _stream()))
+    return ob, os_
+
+
+def multiclass_nms(cls_score, bbox_xyxy, nms_thresh, min_det_score=0.05, first_class=0):
+    """All (image, class) problems of detection_test.py's `do_nms` at once.
+    cls_score (B,N,K), bbox_xyxy (B,N,4K) or (B,N,4).
+    -> dets (P,n_pad,5) candidates in descending score order, counts (P), keep (P,n_pad), nkeep (P),
+       src (P,n_pad) roi index per candidate;  P = B*(K-first_class), problem p = b*(K-fc)+(cid-fc).
+    The reference's per-class result is dets[p][keep[p,:nkeep[p]]]."""
+    cls_score, bbox_xyxy = _dev(cls_score, "cls_score"), _dev(bbox_xyxy, "bbox_xyxy")
+    B, N, K = cls_score.shape
+    bd = bbox_xyxy.shape[2]
+    P = B * (K - first_class)
+    n_pad = 1 << (N - 1).bit_length()
+    dev = cls_score.device
+    dets = torch.empty((P, n_pad, 5), device=dev, dtype=torch.float32)
+    counts = torch.empty((P,), device=dev, dtype=torch.int32)
+    keep = torch.empty((P, n_pad), device=dev, dtype=torch.int32)
+    nkeep = torch.empty((P,), device=dev, dtype=torch.int32)
+    src = torch.empty((P, n_pad), device=dev, dtype=torch.int32)
+    L = _lib.lib()
+    nbytes = L.sdet_multiclass_nms_workspace(B, N, K, int(first_class))
+    ws = _ws(nbytes, dev)
+    check(L.sdet_multiclass_nms(_p(cls_score), _p(bbox_xyxy), B, N, K, bd, int(first_class),
+                                float(min_det_score), float(nms_thresh), _p(dets), _p(counts), _p(keep),
+                                _p(nkeep), _p(src), _p(ws), nbytes, _stream()))
+    return dets, counts, keep, nkeep, src
+
+
 # Registry keyed by the reference's operator names (what symbol/builder.py binds by string).
 OPS = {
     "_contrib_ROIAlign_v2": ROIAlign_v2,
@@ -350,4 +432,5 @@ OPS = {
     "_contrib_DecodeBBox": DecodeBBox,
     "_contrib_Proposal_v3": Proposal_v3,
     "_contrib_NMS": NMS,
+    "get_top_proposal": get_top_proposal,  # mx.operator.register('get_top_proposal')
 }

@@ -140,3 +140,55 @@ def test_contrib_nms(cuda, sorted_in):
     ro, rs = oracle.contrib_nms(props, 100, 300, 0.6, already_sorted=sorted_in)
     out, sc = ops.NMS(_t(props, cuda), 100, 300, 0.6, output_score=True, already_sorted=sorted_in)
     assert np.array_equal(out.cpu().numpy()[:, :100], ro[:, :100]) and np.isnan(ro[:, 100:]).all()
+
+
+def test_get_top_proposal(cuda):
+    from oracle import np_ops
+
+    rng = np.random.default_rng(3)
+    B, M = 2, 5000
+    boxes = np.stack([_boxes(rng, M), _boxes(rng, M)])
+    scores = rng.uniform(0, 1, (B, M, 1)).astype(np.float32)
+    scores[:, ::5] = 0.5  # ties -> lower index first
+    rb, rs = np_ops.get_top_proposal(boxes, scores, 1000)
+    ob, os_ = ops.get_top_proposal(_t(boxes, cuda), _t(scores, cuda), 1000)
+    assert np.array_equal(ob.cpu().numpy(), rb) and np.array_equal(os_.cpu().numpy(), rs)
+
+
+def test_multiclass_nms_matches_do_nms(cuda):
+    from oracle import np_ops
+
+    rng = np.random.default_rng(4)
+    B, N, K = 2, 300, 9
+    score = rng.uniform(0, 1, (B, N, K)).astype(np.float32) ** 3  # distinct scores, many below 0.05
+    bbox = np.stack([np.concatenate([_boxes(rng, N, 200) for _ in range(K)], 1) for _ in range(B)])
+    dets, counts, keep, nkeep, src = ops.multiclass_nms(_t(score, cuda), _t(bbox, cuda), 0.5, 0.05)
+    dets, counts, keep, nkeep, src = [x.cpu().numpy() for x in (dets, counts, keep, nkeep, src)]
+    for b in range(B):
+        ref = np_ops.do_nms(score[b], bbox[b], 0.5, 0.05)
+        for cid in range(K):
+            p = b * K + cid
+            got = dets[p][keep[p, : nkeep[p]]]
+            assert counts[p] == (score[b, :, cid] > 0.05).sum()
+            assert np.array_equal(got, ref[cid]), (b, cid)
+            # candidates trace back to their roi
+            assert np.array_equal(score[b, src[p, : counts[p]], cid], dets[p, : counts[p], 4])
+
+
+def test_proposal_v3_fpn_equals_per_level_concat(cuda):
+    rng = np.random.default_rng(21)
+    B, A = 2, 3
+    strides = (4, 8, 16, 32, 64)
+    shapes = [(-(-320 // s), -(-416 // s)) for s in strides]
+    cls = [rng.uniform(0, 1, (B, 2 * A, h, w)).astype(np.float32) for h, w in shapes]
+    dl = [(rng.standard_normal((B, 4 * A, h, w)) * 0.3).astype(np.float32) for h, w in shapes]
+    im_info = np.array([[320, 416, 1.0], [300, 400, 1.3]], np.float32)
+    kw = dict(scales=(8,), ratios=(0.5, 1, 2), rpn_pre_nms_top_n=500, rpn_post_nms_top_n=200, threshold=0.7,
+              rpn_min_size=0)
+    ref = [oracle.proposal_v3(c, d, im_info, feature_stride=s, **kw) for c, d, s in zip(cls, dl, strides)]
+    rb = np.concatenate([r[0] for r in ref], 1)
+    rs = np.concatenate([r[1] for r in ref], 1)
+    out, sc = ops.Proposal_v3_fpn([_t(c, cuda) for c in cls], [_t(d, cuda) for d in dl], _t(im_info, cuda),
+                                  strides, **kw)
+    assert np.array_equal(sc.cpu().numpy(), rs)
+    np.testing.assert_allclose(out.cpu().numpy(), rb, rtol=1e-5, atol=1e-3)
