@@ -190,6 +190,52 @@ int sdet_multiclass_nms(const float* cls_score, const float* bbox, int B, int N,
                         int* counts, int* keep, int* nkeep, int* src_index, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * ProposalTarget   (operator_cxx/proposal_target-inl.h:81-114 params, :123-256 Forward;
+ *                   operator_cxx/proposal_target.cc:22-227 SampleROI and helpers)
+ *   rois (B,R,4) (padding rows have y2 <= 0), gt_boxes (B,G,5) [x1,y1,x2,y2,cls] (padding cls -1)
+ *   -> rois_out (B,IR,4), labels (B,IR), bbox_targets / bbox_weights (B,IR,num_classes*4),
+ *      match_gt_ious (B,IR); kept (B,IR) int32 or NULL: index of each output row in the image's
+ *      compacted [valid rois ++ valid gt] list (-1 for a row the reference leaves zero).
+ *   IR = image_rois (> 0), fg quota = (int)(image_rois * fg_fraction).  All outputs are fully
+ *   written (zero-initialised like -inl.h:188-192).  bbox_mean/std/weight: HOST float[4].
+ *   Sampling: each std::random_shuffle of the reference is "order by a 32-bit priority, ties by
+ *   index".  priorities == NULL: cuRAND Philox4x32-10 keyed (seed, image*T+candidate, draw),
+ *   T = R+G; else a DEVICE array (B, num_draws, T) uint32 supplied by the caller.  Draw 0 = fg,
+ *   1 = bg, 2 + r % (num_draws-2) = r-th negative-padding shuffle; num_draws >= 3.
+ *   priorities_used (B,num_draws,T) device or NULL receives the priorities of the draws executed. */
+int sdet_proposal_target(const float* rois, const float* gt_boxes, float* rois_out, float* labels,
+                         float* bbox_targets, float* bbox_weights, float* match_gt_ious, int* kept,
+                         int B, int R, int G, int num_classes, int image_rois, float fg_fraction,
+                         float fg_thresh, float bg_thresh_hi, float bg_thresh_lo,
+                         int proposal_without_gt, int class_agnostic, const float* bbox_mean,
+                         const float* bbox_std, const float* bbox_weight, unsigned long long seed,
+                         const uint32_t* priorities, int num_draws, uint32_t* priorities_used,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * _contrib_FocalLoss  (operator_cxx/contrib/focal_loss-inl.h:52-79 params, :90-114 forward =
+ *                      sigmoid, :116-231 backward).  data/out/gdata (B,N,K), label (B,N) with
+ *                      -1 = ignore, 0 = background, k in 1..K = class k-1 (Appendix A.18).
+ *   normalization: 0 "null", 1 "batch", 2 "valid" (divide by sum(label>=1)+1).  ograd may be
+ *   NULL (out_grad=false).  workspace: >= 4 bytes of device memory.
+ * _contrib_BBoxNorm   (bbox_norm-inl.h:99-129): forward is identity; backward divides the
+ *                      incoming gradient by max(sum(label>=1)+1, 1).  n / n_label = element counts.
+ * _contrib_SigmoidCrossEntropy (sigmoid_cross_entropy.cu:45-129): data,label (R,D); label -1 is
+ *   ignored; out (R) = per-row sum(loss)/(count+1e-5); backward d = (sigmoid(x)-t)/(count+1e-5)*scale.
+ *   workspace: >= 8*R bytes.
+ * ------------------------------------------------------------------------------------------ */
+int sdet_focal_loss_forward(const float* data, float* out, size_t n, void* stream);
+int sdet_focal_loss_backward(const float* out, const float* label, const float* ograd, float* gdata,
+                             int B, int N, int K, float alpha, float gamma, float grad_scale,
+                             int normalization, void* workspace, size_t workspace_bytes, void* stream);
+int sdet_bbox_norm_backward(const float* gout, const float* label, float* gdata, size_t n,
+                            size_t n_label, void* workspace, size_t workspace_bytes, void* stream);
+int sdet_sigmoid_ce_forward(const float* data, const float* label, float* out, int R, size_t D,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int sdet_sigmoid_ce_backward(const float* data, const float* label, float* d_data, int R, size_t D,
+                             float scale, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -256,3 +256,78 @@ def ref_cython():
         return {m: importlib.import_module(m) for m in ("bbox", "bbox_self", "cpu_nms")}
     except ImportError:
         return None
+
+
+# ---------------------------------------------------------------------------------------------
+# ProposalTarget (oracle/target_ops.c)
+# ---------------------------------------------------------------------------------------------
+def proposal_target(rois, gt_boxes, priorities, num_classes, image_rois, fg_fraction=0.25, fg_thresh=0.5,
+                    bg_thresh_hi=0.5, bg_thresh_lo=0.0, proposal_without_gt=False, class_agnostic=False,
+                    bbox_mean=(0, 0, 0, 0), bbox_std=(0.1, 0.1, 0.2, 0.2), bbox_weight=(1, 1, 1, 1)):
+    """ProposalTarget with injected shuffle priorities (B, D>=3, R+G) uint32.
+    -> rois (B,IR,4), label (B,IR), bbox_target (B,IR,NC*4), bbox_weight (B,IR,NC*4),
+       match_gt_iou (B,IR), kept (B,IR) int32."""
+    rois, gt_boxes = _f32(rois), _f32(gt_boxes)
+    B, R, _ = rois.shape
+    G = gt_boxes.shape[1]
+    pr = np.ascontiguousarray(priorities, dtype=np.uint32)
+    assert pr.shape[0] == B and pr.shape[2] == R + G and pr.shape[1] >= 3
+    IR, NC4 = image_rois, num_classes * 4
+    o_rois = np.empty((B, IR, 4), np.float32)
+    o_lab = np.empty((B, IR), np.float32)
+    o_tgt = np.empty((B, IR, NC4), np.float32)
+    o_wgt = np.empty((B, IR, NC4), np.float32)
+    o_iou = np.empty((B, IR), np.float32)
+    kept = np.empty((B, IR), np.int32)
+    m, s, w = _f32(bbox_mean), _f32(bbox_std), _f32(bbox_weight)
+    lib().oracle_proposal_target(_p(rois), _p(gt_boxes), B, R, G, int(num_classes), int(image_rois),
+                                 ctypes.c_float(fg_fraction), ctypes.c_float(fg_thresh),
+                                 ctypes.c_float(bg_thresh_hi), ctypes.c_float(bg_thresh_lo),
+                                 int(bool(proposal_without_gt)), int(bool(class_agnostic)), _p(m), _p(s), _p(w),
+                                 _p(pr), pr.shape[1], _p(o_rois), _p(o_lab), _p(o_tgt), _p(o_wgt), _p(o_iou),
+                                 _p(kept))
+    return o_rois, o_lab, o_tgt, o_wgt, o_iou, kept
+
+
+# ---------------------------------------------------------------------------------------------
+# losses (oracle/loss_ops.c)
+# ---------------------------------------------------------------------------------------------
+def sigmoid(x):
+    x = _f32(x)
+    y = np.empty_like(x)
+    lib().oracle_sigmoid(_p(x), ctypes.c_long(x.size), _p(y))
+    return y
+
+
+def focal_loss_backward(out, label, alpha=0.25, gamma=2.0, grad_scale=1.0, normalization="null", ograd=None):
+    out, label = _f32(out), _f32(label)
+    B, N, K = out.shape
+    g = np.empty_like(out)
+    og = _f32(ograd) if ograd is not None else None
+    lib().oracle_focal_loss_backward(_p(out), _p(label), _p(og), B, N, K, ctypes.c_float(alpha),
+                                     ctypes.c_float(gamma), ctypes.c_float(grad_scale),
+                                     {"null": 0, "batch": 1, "valid": 2}[normalization], _p(g))
+    return g
+
+
+def bbox_norm_backward(gout, label):
+    gout, label = _f32(gout), _f32(label)
+    g = np.empty_like(gout)
+    lib().oracle_bbox_norm_backward(_p(gout), ctypes.c_long(gout.size), _p(label), ctypes.c_long(label.size), _p(g))
+    return g
+
+
+def sigmoid_ce_forward(data, label):
+    data, label = _f32(data), _f32(label)
+    R, D = data.shape
+    out = np.empty((R,), np.float32)
+    lib().oracle_sigmoid_ce_forward(_p(data), _p(label), R, ctypes.c_long(D), _p(out))
+    return out
+
+
+def sigmoid_ce_backward(data, label, scale=1.0):
+    data, label = _f32(data), _f32(label)
+    R, D = data.shape
+    dx = np.empty_like(data)
+    lib().oracle_sigmoid_ce_backward(_p(data), _p(label), R, ctypes.c_long(D), ctypes.c_float(scale), _p(dx))
+    return dx

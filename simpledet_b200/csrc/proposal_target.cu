@@ -1,0 +1,321 @@
+// ProposalTarget on the device (the reference's "gpu" operator copies everything to the host and
+// loops there: operator_cxx/proposal_target-inl.h:146-149,251-255; there is no .cu).
+//
+// Reference semantics: operator_cxx/proposal_target-inl.h:123-256 (filter padding, append gt),
+// operator_cxx/proposal_target.cc:22-163 SampleROI, :165-185 BBoxOverlap, :187-202
+// ExpandBboxRegressionTargets, :204-227 NonLinearTransformAndNormalization.
+//
+// One CTA per image does the whole assignment in shared memory: ordered compaction of valid
+// gt / rois, IoU + first-max argmax per roi, fg / bg / neg partition (index order), priority
+// sort for each "random_shuffle", target encoding and the class-slot scatter.  A shuffle is
+// "order the candidates by a 32-bit priority, ties by index"; priorities come from cuRAND Philox
+// (seed, image, draw, candidate) or are injected by the caller (tests inject the same array into
+// the oracle, making every output comparable bit for bit — SURVEY.md §0.8).
+#include <curand_kernel.h>
+
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 1024;
+constexpr int kMaxT = 4096;  // rois + gt boxes per image
+
+struct PTParams {
+  const float* rois;      // (B,R,4)
+  const float* gt;        // (B,G,5)
+  const uint32_t* prio;   // (B,D,T) injected priorities or nullptr -> Philox
+  uint32_t* prio_used;    // (B,D,T) or nullptr: the priorities this call used
+  float* rois_out;        // (B,IR,4)
+  float* labels;          // (B,IR)
+  float* tgt;             // (B,IR,NC4)
+  float* wgt;             // (B,IR,NC4)
+  float* iou;             // (B,IR)
+  int* kept;              // (B,IR) or nullptr: index into the compacted roi list, -1 = empty row
+  int B, R, G, NC4, IR, D, fg_per_image;
+  float fg_thresh, bg_hi, bg_lo;
+  int without_gt, agnostic;
+  float mean[4], std[4], weight[4];
+  unsigned long long seed;
+};
+
+__device__ __forceinline__ float fmin_ref(float a, float b) { return a < b ? a : b; }
+__device__ __forceinline__ float fmax_ref(float a, float b) { return a < b ? b : a; }
+
+// Ordered compaction: list <- { i in [0,n) : pred(i) } in increasing i.  Returns the count.
+// All threads call; s_warp is 32 ints of scratch.
+template <typename Pred>
+__device__ int block_compact(int n, Pred pred, int* list, int* s_warp, int* s_total) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) *s_total = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + tid;
+    const bool f = (i < n) && pred(i);
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+      int v = s_warp[lane], inc = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      s_warp[lane] = inc - v;  // exclusive prefix of the warp counts
+      if (lane == 31) s_warp[32] = inc;
+    }
+    __syncthreads();
+    const int off = *s_total + s_warp[warp] + __popc(m & ((1u << lane) - 1u));
+    if (f) list[off] = i;
+    __syncthreads();
+    if (tid == 0) *s_total += s_warp[32];
+    __syncthreads();
+  }
+  const int total = *s_total;
+  __syncthreads();  // nobody may re-enter (and reset *s_total) before every thread has read it
+  return total;
+}
+
+// Sort list[0..n) by (prio[list[i]], list[i]) ascending.  keys: next_pow2(n) u64 of scratch.
+__device__ void block_priority_sort(int* list, int n, const uint32_t* prio, unsigned long long* keys) {
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (int i = threadIdx.x; i < np2; i += blockDim.x)
+    keys[i] = i < n ? (((unsigned long long)prio[list[i]] << 32) | (unsigned)list[i]) : ~0ull;
+  __syncthreads();
+  for (int size = 2; size <= np2; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride), hi = lo + stride;
+        const bool asc = ((lo & size) == 0);
+        const unsigned long long a = keys[lo], c = keys[hi];
+        if ((a > c) == asc) {
+          keys[lo] = c;
+          keys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) list[i] = (int)(keys[i] & 0xFFFFFFFFull);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads)
+proposal_target_kernel(const __grid_constant__ PTParams p) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int R = p.R, G = p.G, T = R + G, IR = p.IR, NC4 = p.NC4;
+  int np2 = 1;
+  while (np2 < T) np2 <<= 1;
+  // shared layout
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(s_raw);  // np2
+  float4* s_box = reinterpret_cast<float4*>(s_keys + np2);                    // T compacted rois
+  float* s_gt = reinterpret_cast<float*>(s_box + T);                          // G*5 compacted gt
+  float* s_maxov = s_gt + G * 5;                                              // T
+  int* s_assign = reinterpret_cast<int*>(s_maxov + T);                        // T
+  int* s_src = s_assign + T;                                                  // T  (scratch list)
+  int* s_fg = s_src + T;                                                      // T
+  int* s_bg = s_fg + T;                                                       // T
+  int* s_neg = s_bg + T;                                                      // T
+  int* s_kept = s_neg + T;                                                    // IR + T
+  uint32_t* s_prio = reinterpret_cast<uint32_t*>(s_kept + IR + T);            // T (current draw)
+  __shared__ int s_warp[33];
+  __shared__ int s_total;
+
+  const float* rois = p.rois + (size_t)b * R * 4;
+  const float* gt = p.gt + (size_t)b * G * 5;
+
+  // ---- valid gt (cls != -1, -inl.h:158) and valid rois (y2 > 0, :174), gt appended (:177-185)
+  const int ng = block_compact(G, [&](int j) { return gt[j * 5 + 4] != -1.f; }, s_src, s_warp, &s_total);
+  for (int e = tid; e < ng * 5; e += blockDim.x) s_gt[e] = gt[s_src[e / 5] * 5 + e % 5];
+  __syncthreads();
+  const int nr = block_compact(R, [&](int j) { return rois[j * 4 + 3] > 0.f; }, s_src, s_warp, &s_total);
+  for (int i = tid; i < nr; i += blockDim.x) {
+    const float* r = rois + (size_t)s_src[i] * 4;
+    s_box[i] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+  const int n = p.without_gt ? nr : nr + ng;
+  if (!p.without_gt)
+    for (int j = tid; j < ng; j += blockDim.x)
+      s_box[nr + j] = make_float4(s_gt[j * 5], s_gt[j * 5 + 1], s_gt[j * 5 + 2], s_gt[j * 5 + 3]);
+  __syncthreads();
+
+  // ---- BBoxOverlap + first-max argmax (proposal_target.cc:165-185, :51-63)
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float4 bx = s_box[i];
+    float best = 0.f;
+    int bi = 0;
+    const float ba = __fmul_rn(__fadd_rn(__fsub_rn(bx.z, bx.x), 1.f), __fadd_rn(__fsub_rn(bx.w, bx.y), 1.f));
+    for (int j = 0; j < ng; ++j) {
+      const float* q = s_gt + j * 5;
+      float ov = 0.f;
+      const float iw = __fadd_rn(__fsub_rn(fmin_ref(bx.z, q[2]), fmax_ref(bx.x, q[0])), 1.f);
+      if (iw > 0.f) {
+        const float ih = __fadd_rn(__fsub_rn(fmin_ref(bx.w, q[3]), fmax_ref(bx.y, q[1])), 1.f);
+        if (ih > 0.f) {
+          const float qa = __fmul_rn(__fadd_rn(__fsub_rn(q[2], q[0]), 1.f), __fadd_rn(__fsub_rn(q[3], q[1]), 1.f));
+          const float inter = __fmul_rn(iw, ih);
+          ov = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ba, qa), inter));
+        }
+      }
+      if (j == 0) {
+        best = ov;
+      } else if (best < ov) {
+        best = ov;
+        bi = j;
+      }
+    }
+    s_maxov[i] = best;
+    s_assign[i] = bi;
+  }
+  __syncthreads();
+
+  // ---- priorities of one draw into s_prio (injected or Philox), optionally exported
+  auto load_draw = [&](int d) {
+    for (int i = tid; i < T; i += blockDim.x) {
+      uint32_t v;
+      if (p.prio) {
+        v = p.prio[((size_t)b * p.D + d) * T + i];
+      } else {
+        curandStatePhilox4_32_10_t st;
+        curand_init(p.seed, (unsigned long long)b * T + i, (unsigned long long)d, &st);
+        v = curand(&st);
+      }
+      s_prio[i] = v;
+      if (p.prio_used) p.prio_used[((size_t)b * p.D + d) * T + i] = v;
+    }
+    __syncthreads();
+  };
+
+  // ---- fg / neg / bg partitions in index order (:72-78, :95-99)
+  const float fg_thr = p.fg_thresh, bg_hi = p.bg_hi, bg_lo = p.bg_lo;
+  const int nfg = block_compact(n, [&](int i) { return s_maxov[i] >= fg_thr; }, s_fg, s_warp, &s_total);
+  const int nneg = block_compact(n, [&](int i) { return !(s_maxov[i] >= fg_thr); }, s_neg, s_warp, &s_total);
+  const int nbg = block_compact(n, [&](int i) { return s_maxov[i] >= bg_lo && s_maxov[i] < bg_hi; }, s_bg,
+                                s_warp, &s_total);
+  const int fg_n = min(p.fg_per_image, nfg);
+  // draws are always materialised in the same order: 0 fg, 1 bg, 2+ negative padding
+  load_draw(0);
+  if (nfg > fg_n) block_priority_sort(s_fg, nfg, s_prio, s_keys);  // :81-85
+  load_draw(1);
+  const int bg_n = min(IR - fg_n, nbg);
+  if (nbg > bg_n) block_priority_sort(s_bg, nbg, s_prio, s_keys);  // :100-104
+  for (int i = tid; i < fg_n; i += blockDim.x) s_kept[i] = s_fg[i];
+  for (int i = tid; i < bg_n; i += blockDim.x) s_kept[fg_n + i] = s_bg[i];
+  int nk = fg_n + bg_n;
+  __syncthreads();
+  for (int r = 0; nk < IR && nneg > 0; ++r) {  // pad with negatives (:116-122)
+    const int gap = IR - nk;
+    load_draw(2 + r % (p.D - 2));
+    block_priority_sort(s_neg, nneg, s_prio, s_keys);
+    const int take = min(gap, nneg);
+    for (int i = tid; i < take; i += blockDim.x) s_kept[nk + i] = s_neg[i];
+    nk += take;
+    __syncthreads();
+  }
+
+  // ---- outputs.  Everything is zero-initialised by the reference (-inl.h:188-192).
+  float* o_tgt = p.tgt + (size_t)b * IR * NC4;
+  float* o_wgt = p.wgt + (size_t)b * IR * NC4;
+  for (size_t e = tid; e < (size_t)IR * NC4; e += blockDim.x) {
+    o_tgt[e] = 0.f;
+    o_wgt[e] = 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < IR; i += blockDim.x) {
+    const size_t row = (size_t)b * IR + i;
+    float4 rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    float label = 0.f, ov = 0.f;
+    int k = -1;
+    if (i < nk) {
+      k = s_kept[i];
+      rb = s_box[k];
+      ov = s_maxov[k];
+      if (ng > 0) {
+        const float* g = s_gt + s_assign[k] * 5;
+        if (i < fg_n) label = g[4];  // labels only for the first fg_n rows (:128-131)
+        // NonLinearTransformAndNormalization (:204-227); `0.5 * (w - 1.f)` is double arithmetic
+        const float ew = __fadd_rn(__fsub_rn(rb.z, rb.x), 1.f), eh = __fadd_rn(__fsub_rn(rb.w, rb.y), 1.f);
+        const float ecx = (float)__dadd_rn((double)rb.x, __dmul_rn(0.5, (double)__fsub_rn(ew, 1.f)));
+        const float ecy = (float)__dadd_rn((double)rb.y, __dmul_rn(0.5, (double)__fsub_rn(eh, 1.f)));
+        const float gw = __fadd_rn(__fsub_rn(g[2], g[0]), 1.f), gh = __fadd_rn(__fsub_rn(g[3], g[1]), 1.f);
+        const float gcx = (float)__dadd_rn((double)g[0], __dmul_rn(0.5, (double)__fsub_rn(gw, 1.f)));
+        const float gcy = (float)__dadd_rn((double)g[1], __dmul_rn(0.5, (double)__fsub_rn(gh, 1.f)));
+        float t[4];
+        t[0] = __fdiv_rn(__fsub_rn(gcx, ecx), __fadd_rn(ew, 1e-14f));
+        t[1] = __fdiv_rn(__fsub_rn(gcy, ecy), __fadd_rn(eh, 1e-14f));
+        t[2] = logf(__fdiv_rn(gw, ew));
+        t[3] = logf(__fdiv_rn(gh, eh));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) t[c] = __fdiv_rn(__fsub_rn(t[c], p.mean[c]), p.std[c]);
+        const float cls = p.agnostic ? (label < 1.f ? label : 1.f) : label;  // :151-157
+        if (cls > 0.f) {  // ExpandBboxRegressionTargets (:187-202)
+          const int start = 4 * (int)cls;
+          if (start + 4 <= NC4) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              o_tgt[(size_t)i * NC4 + start + c] = t[c];
+              o_wgt[(size_t)i * NC4 + start + c] = p.weight[c];
+            }
+          }
+        }
+      }
+    }
+    p.rois_out[row * 4 + 0] = rb.x;
+    p.rois_out[row * 4 + 1] = rb.y;
+    p.rois_out[row * 4 + 2] = rb.z;
+    p.rois_out[row * 4 + 3] = rb.w;
+    p.labels[row] = label;
+    p.iou[row] = ov;
+    if (p.kept) p.kept[row] = k;
+  }
+}
+
+size_t pt_smem_bytes(int T, int G, int IR) {
+  int np2 = 1;
+  while (np2 < T) np2 <<= 1;
+  return (size_t)np2 * 8 + (size_t)T * 16 + (size_t)G * 5 * 4 + (size_t)T * 4 * 7 + (size_t)(IR + T) * 4 + 64;
+}
+
+}  // namespace
+
+extern "C" int sdet_proposal_target(const float* rois, const float* gt_boxes, float* rois_out,
+                                    float* labels, float* bbox_targets, float* bbox_weights,
+                                    float* match_gt_ious, int* kept, int B, int R, int G, int num_classes,
+                                    int image_rois, float fg_fraction, float fg_thresh, float bg_thresh_hi,
+                                    float bg_thresh_lo, int proposal_without_gt, int class_agnostic,
+                                    const float* bbox_mean, const float* bbox_std, const float* bbox_weight,
+                                    unsigned long long seed, const uint32_t* priorities, int num_draws,
+                                    uint32_t* priorities_used, void* stream) {
+  SDET_REQUIRE(rois && gt_boxes && rois_out && labels && bbox_targets && bbox_weights && match_gt_ious &&
+               bbox_mean && bbox_std && bbox_weight, "NULL argument");
+  SDET_REQUIRE(B > 0 && R > 0 && G >= 0 && num_classes > 0 && image_rois > 0, "bad shape");
+  SDET_REQUIRE(num_draws >= 3, "num_draws must be >= 3 (fg, bg, >= 1 negative-padding draw)");
+  if (R + G > kMaxT) return sdet::fail(SDET_ERR_UNSUPPORTED, "rois + gt per image > %d", kMaxT);
+  PTParams p{};
+  p.rois = rois; p.gt = gt_boxes; p.prio = priorities; p.prio_used = priorities_used;
+  p.rois_out = rois_out; p.labels = labels; p.tgt = bbox_targets; p.wgt = bbox_weights;
+  p.iou = match_gt_ious; p.kept = kept;
+  p.B = B; p.R = R; p.G = G; p.NC4 = num_classes * 4; p.IR = image_rois; p.D = num_draws;
+  p.fg_per_image = (int)(image_rois * fg_fraction);  // index_t truncation, proposal_target-inl.h:194
+  p.fg_thresh = fg_thresh; p.bg_hi = bg_thresh_hi; p.bg_lo = bg_thresh_lo;
+  p.without_gt = proposal_without_gt ? 1 : 0;
+  p.agnostic = class_agnostic ? 1 : 0;
+  for (int i = 0; i < 4; ++i) {
+    p.mean[i] = bbox_mean[i];
+    p.std[i] = bbox_std[i];
+    p.weight[i] = bbox_weight[i];
+  }
+  p.seed = seed;
+  const size_t smem = pt_smem_bytes(R + G, G, image_rois);
+  if (smem > 220 * 1024) return sdet::fail(SDET_ERR_UNSUPPORTED, "ProposalTarget needs %zu B shared memory", smem);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SDET_CUDA(cudaFuncSetAttribute(proposal_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  proposal_target_kernel<<<(unsigned)B, kThreads, smem, (cudaStream_t)stream>>>(p);
+  SDET_LAUNCH_CHECK("proposal_target_kernel");
+  return SDET_OK;
+}

@@ -20,7 +20,8 @@ from ._lib import check
 
 __all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_raw",
            "fpn_roi_align", "fpn_roi_align_raw", "DecodeBBox", "Proposal_v3", "Proposal_v3_fpn", "NMS", "nms_sorted", "get_top_proposal",
-           "multiclass_nms", "OPS"]
+           "multiclass_nms", "ProposalTarget", "FocalLoss", "BBoxNorm",
+           "SigmoidCrossEntropy", "OPS"]
 
 
 def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor | None:
@@ -382,6 +383,158 @@ def nms_sorted(dets, thresh, ge=True, counts=None):
 
 
 # --------------------------------------------------------------------------------------------
+# ProposalTarget  (operator_cxx/proposal_target-inl.h:81-114 params; X.proposal_target at
+# models/FPN/builder.py:347-363)
+# --------------------------------------------------------------------------------------------
+_PT_CALLS = [0]
+
+
+def ProposalTarget(rois, gt_boxes, num_classes, batch_images, image_rois, fg_thresh, bg_thresh_hi,
+                   bg_thresh_lo, proposal_without_gt, fg_fraction=0.25, class_agnostic=False,
+                   output_iou=False, bbox_mean=(0.0, 0.0, 0.0, 0.0), bbox_std=(0.1, 0.1, 0.2, 0.2),
+                   bbox_weight=(1.0, 1.0, 1.0, 1.0), seed=None, priorities=None, num_draws=8,
+                   return_debug=False):
+    """mx.sym.ProposalTarget.  rois (B,R,4), gt_boxes (B,G,5) -> rois (B,IR,4), label (B,IR),
+    bbox_target (B,IR,4*num_classes), bbox_weight (same) [, match_gt_iou (B,IR) if output_iou].
+    `seed` (int) keys the on-device Philox sampling (default: a per-process call counter);
+    `priorities` (B,D,R+G) uint32-in-int32/int64 tensor injects the shuffles instead.
+    return_debug adds (kept (B,IR) int32, priorities_used (B,D,R+G) int32 bit patterns)."""
+    rois, gt_boxes = _dev(rois, "rois"), _dev(gt_boxes, "gt_boxes")
+    B = int(batch_images)
+    R = rois.numel() // (B * 4)       # -inl.h:139-140: shapes are re-derived from batch_images
+    G = gt_boxes.numel() // (B * 5)
+    IR = int(image_rois)
+    if IR <= 0:
+        raise ValueError("image_rois must be > 0 (ProposalTarget_v2 handles -1)")
+    dev = rois.device
+    NC4 = 4 * int(num_classes)
+    o_rois = torch.empty((B, IR, 4), device=dev)
+    o_lab = torch.empty((B, IR), device=dev)
+    o_tgt = torch.empty((B, IR, NC4), device=dev)
+    o_wgt = torch.empty((B, IR, NC4), device=dev)
+    o_iou = torch.empty((B, IR), device=dev)
+    kept = torch.empty((B, IR), device=dev, dtype=torch.int32) if return_debug else None
+    T = R + G
+    if priorities is not None:
+        priorities = priorities.to(device=dev, dtype=torch.int64).contiguous()
+        if priorities.shape[0] != B or priorities.shape[2] != T:
+            raise ValueError("priorities must be (B, D, R+G)")
+        num_draws = priorities.shape[1]
+        priorities = (priorities & 0xFFFFFFFF).to(torch.int64)
+        priorities = torch.where(priorities >= 2 ** 31, priorities - 2 ** 32, priorities).to(torch.int32).contiguous()
+    used = torch.zeros((B, num_draws, T), device=dev, dtype=torch.int32) if return_debug else None
+    if seed is None:
+        _PT_CALLS[0] += 1
+        seed = 0x5DE7B200 + _PT_CALLS[0]
+    check(_lib.lib().sdet_proposal_target(
+        _p(rois), _p(gt_boxes), _p(o_rois), _p(o_lab), _p(o_tgt), _p(o_wgt), _p(o_iou), _p(kept), B, R, G,
+        int(num_classes), IR, float(fg_fraction), float(fg_thresh), float(bg_thresh_hi), float(bg_thresh_lo),
+        int(bool(proposal_without_gt)), int(bool(class_agnostic)), _f4(bbox_mean, "bbox_mean"),
+        _f4(bbox_std, "bbox_std"), _f4(bbox_weight, "bbox_weight"), int(seed) & (2 ** 64 - 1), _p(priorities),
+        int(num_draws), _p(used), _stream()))
+    outs = [o_rois, o_lab, o_tgt, o_wgt]
+    if output_iou:
+        outs.append(o_iou)
+    if return_debug:
+        outs += [o_iou, kept, used]
+    return tuple(outs)
+
+
+# --------------------------------------------------------------------------------------------
+# _contrib_FocalLoss / _contrib_BBoxNorm / _contrib_SigmoidCrossEntropy
+# --------------------------------------------------------------------------------------------
+_NORM = {"null": 0, "batch": 1, "valid": 2}
+
+
+class _FocalLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, label, alpha, gamma, normalization, grad_scale, out_grad):
+        data, label = _dev(data, "data"), _dev(label, "label")
+        out = torch.empty_like(data)
+        check(_lib.lib().sdet_focal_loss_forward(_p(data), _p(out), data.numel(), _stream()))
+        ctx.save_for_backward(out, label)
+        ctx.cfg = (alpha, gamma, normalization, grad_scale, out_grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, ograd):
+        out, label = ctx.saved_tensors
+        alpha, gamma, normalization, grad_scale, use_og = ctx.cfg
+        B, N, K = out.shape
+        g = torch.empty_like(out)
+        og = _dev(ograd, "ograd") if use_og else None
+        ws = _ws(16, out.device)
+        check(_lib.lib().sdet_focal_loss_backward(_p(out), _p(label), _p(og), _p(g), B, N, K, float(alpha),
+                                                  float(gamma), float(grad_scale), _NORM[normalization], _p(ws),
+                                                  16, _stream()))
+        return g, None, None, None, None, None, None
+
+
+def FocalLoss(data, label, alpha=0.25, gamma=2.0, normalization="null", grad_scale=1.0, out_grad=False,
+              workspace=256):
+    """mx.sym.contrib.FocalLoss / X.focal_loss: data (B,N,K) logits, label (B,N) -> sigmoid(data);
+    the loss gradient is produced in backward like the reference (the incoming gradient is
+    ignored unless out_grad=True).  `workspace` is accepted and unused (no temporaries)."""
+    if data.dim() != 3 or label.shape != data.shape[:2]:
+        raise ValueError("data must be (B,N,K) and label (B,N)")
+    return _FocalLossFn.apply(data, label, float(alpha), float(gamma), normalization, float(grad_scale),
+                              bool(out_grad))
+
+
+class _BBoxNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, label):
+        ctx.save_for_backward(label)
+        return data.clone()  # Assign(out, identity(data)), bbox_norm-inl.h:96
+
+    @staticmethod
+    def backward(ctx, gout):
+        (label,) = ctx.saved_tensors
+        gout, label = _dev(gout, "gout"), _dev(label, "label")
+        g = torch.empty_like(gout)
+        ws = _ws(16, gout.device)
+        check(_lib.lib().sdet_bbox_norm_backward(_p(gout), _p(label), _p(g), gout.numel(), label.numel(), _p(ws),
+                                                 16, _stream()))
+        return g, None
+
+
+def BBoxNorm(data, label, normalization="valid"):
+    """mx.sym.contrib.BBoxNorm / X.bbox_norm: identity forward; backward divides the gradient by
+    max(sum(label >= 1) + 1, 1) (the reference ignores `normalization` in Backward too)."""
+    return _BBoxNormFn.apply(data, label)
+
+
+class _SigmoidCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, label, grad_scale):
+        data, label = _dev(data, "data"), _dev(label, "label")
+        R, D = data.shape
+        out = torch.empty((R,), device=data.device)
+        ws = _ws(8 * R, data.device)
+        check(_lib.lib().sdet_sigmoid_ce_forward(_p(data), _p(label), _p(out), R, D, _p(ws), 8 * R, _stream()))
+        ctx.save_for_backward(data, label)
+        ctx.scale = grad_scale
+        return out
+
+    @staticmethod
+    def backward(ctx, ograd):
+        data, label = ctx.saved_tensors
+        R, D = data.shape
+        g = torch.empty_like(data)
+        ws = _ws(8 * R, data.device)
+        check(_lib.lib().sdet_sigmoid_ce_backward(_p(data), _p(label), _p(g), R, D, float(ctx.scale), _p(ws), 8 * R,
+                                                  _stream()))
+        return g, None, None
+
+
+def SigmoidCrossEntropy(data, label, grad_scale=1.0):
+    """mx.sym.contrib.SigmoidCrossEntropy: data, label (R,D), label -1 ignored -> loss (R,)."""
+    if data.dim() != 2 or data.shape != label.shape:
+        raise ValueError("data and label must both be (R,D)")
+    return _SigmoidCEFn.apply(data, label, float(grad_scale))
+
+
+# --------------------------------------------------------------------------------------------
 # get_top_proposal (models/FPN/get_top_proposal.py) and test-time per-class NMS
 # (detection_test.py:233-260 + operator_py/nms.py:41-75)
 # --------------------------------------------------------------------------------------------
@@ -432,5 +585,9 @@ OPS = {
     "_contrib_DecodeBBox": DecodeBBox,
     "_contrib_Proposal_v3": Proposal_v3,
     "_contrib_NMS": NMS,
+    "ProposalTarget": ProposalTarget,
+    "_contrib_FocalLoss": FocalLoss,
+    "_contrib_BBoxNorm": BBoxNorm,
+    "_contrib_SigmoidCrossEntropy": SigmoidCrossEntropy,
     "get_top_proposal": get_top_proposal,  # mx.operator.register('get_top_proposal')
 }
