@@ -55,3 +55,74 @@ def do_nms(cls_score, bbox_xyxy, nms_thresh, min_det_score):
         det = np.concatenate((cls_box[valid], score[valid].reshape(-1, 1)), axis=1).astype(np.float32)
         out[cid] = py_nms(det, nms_thresh) if det.shape[0] else det
     return out
+
+
+# ---- operator_py/bbox_transform.py (numpy float64 utilities) — PINNED by tests/golden ----------
+BBOX_XFORM_CLIP = np.log(1000. / 16.)  # bbox_transform.py:5
+
+
+def clip_boxes(boxes, im_shape):
+    """bbox_transform.py:34-49 (in place on a copy here)."""
+    boxes = boxes.copy()
+    boxes[:, 0::4] = np.maximum(np.minimum(boxes[:, 0::4], im_shape[1] - 1), 0)
+    boxes[:, 1::4] = np.maximum(np.minimum(boxes[:, 1::4], im_shape[0] - 1), 0)
+    boxes[:, 2::4] = np.maximum(np.minimum(boxes[:, 2::4], im_shape[1] - 1), 0)
+    boxes[:, 3::4] = np.maximum(np.minimum(boxes[:, 3::4], im_shape[0] - 1), 0)
+    return boxes
+
+
+def nonlinear_transform(ex_rois, gt_rois):
+    """bbox_transform.py:52-78."""
+    ew = ex_rois[:, 2] - ex_rois[:, 0] + 1.0
+    eh = ex_rois[:, 3] - ex_rois[:, 1] + 1.0
+    ecx = ex_rois[:, 0] + 0.5 * (ew - 1.0)
+    ecy = ex_rois[:, 1] + 0.5 * (eh - 1.0)
+    gw = gt_rois[:, 2] - gt_rois[:, 0] + 1.0
+    gh = gt_rois[:, 3] - gt_rois[:, 1] + 1.0
+    gcx = gt_rois[:, 0] + 0.5 * (gw - 1.0)
+    gcy = gt_rois[:, 1] + 0.5 * (gh - 1.0)
+    return np.vstack(((gcx - ecx) / (ew + 1e-14), (gcy - ecy) / (eh + 1e-14), np.log(gw / ew),
+                      np.log(gh / eh))).transpose()
+
+
+def nonlinear_pred(boxes, box_deltas):
+    """bbox_transform.py:81-120 (float64; dw, dh clipped at log(1000/16))."""
+    if boxes.shape[0] == 0:
+        return np.zeros((0, box_deltas.shape[1]))
+    boxes = boxes.astype(np.float64, copy=False)
+    w = boxes[:, 2] - boxes[:, 0] + 1.0
+    h = boxes[:, 3] - boxes[:, 1] + 1.0
+    cx = boxes[:, 0] + 0.5 * (w - 1.0)
+    cy = boxes[:, 1] + 0.5 * (h - 1.0)
+    dx, dy = box_deltas[:, 0::4], box_deltas[:, 1::4]
+    dw = np.minimum(box_deltas[:, 2::4], BBOX_XFORM_CLIP)
+    dh = np.minimum(box_deltas[:, 3::4], BBOX_XFORM_CLIP)
+    pcx = dx * w[:, None] + cx[:, None]
+    pcy = dy * h[:, None] + cy[:, None]
+    pw = np.exp(dw) * w[:, None]
+    ph = np.exp(dh) * h[:, None]
+    out = np.zeros(box_deltas.shape)
+    out[:, 0::4] = pcx - 0.5 * (pw - 1.0)
+    out[:, 1::4] = pcy - 0.5 * (ph - 1.0)
+    out[:, 2::4] = pcx + 0.5 * (pw - 1.0)
+    out[:, 3::4] = pcy + 0.5 * (ph - 1.0)
+    return out
+
+
+def iou_pred(boxes, box_deltas):
+    """bbox_transform.py:129-161."""
+    if boxes.shape[0] == 0:
+        return np.zeros((0, box_deltas.shape[1]))
+    boxes = boxes.astype(np.float64, copy=False)
+    out = np.zeros(box_deltas.shape)
+    for k in range(4):
+        out[:, k::4] = box_deltas[:, k::4] + boxes[:, k][:, None]
+    return out
+
+
+def flip_boxes(boxes, im_width):
+    """bbox_transform.py:164-169."""
+    f = boxes.copy()
+    f[:, 0::4] = im_width - boxes[:, 2::4] - 1
+    f[:, 2::4] = im_width - boxes[:, 0::4] - 1
+    return f
