@@ -236,6 +236,19 @@ int sdet_sigmoid_ce_forward(const float* data, const float* label, float* out, i
 int sdet_sigmoid_ce_backward(const float* data, const float* label, float* d_data, int R, size_t D,
                              float scale, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * soft_nms   (operator_py/cython/cpu_nms.pyx:98-203; wrapper operator_py/nms.py:5-16), batched:
+ *   dets (P,m,5) device [x1,y1,x2,y2,score] in ANY order (the algorithm selects the max itself),
+ *   counts (P) device int32 or NULL (= m boxes everywhere).
+ *   method 0 hard, 1 linear, 2 gaussian; Nt = IoU threshold; boxes whose re-weighted score drops
+ *   below `threshold` are removed.
+ *   out_boxes (P,m,5): the surviving boxes with their final scores in the reference's output order
+ *   (zero padded), out_inds (P,m): their original row indices (-1 padding), out_counts (P).
+ * ------------------------------------------------------------------------------------------ */
+int sdet_soft_nms(const float* dets, const int* counts, int problems, int m, float sigma, float Nt,
+                  float threshold, int method, float* out_boxes, int* out_inds, int* out_counts,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,8 @@ from ._lib import check
 __all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_raw",
            "fpn_roi_align", "fpn_roi_align_raw", "DecodeBBox", "Proposal_v3", "Proposal_v3_fpn", "NMS", "nms_sorted", "get_top_proposal",
            "multiclass_nms", "ProposalTarget", "FocalLoss", "BBoxNorm",
-           "SigmoidCrossEntropy", "OPS"]
+           "SigmoidCrossEntropy", "soft_nms", "soft_nms_batched",
+           "cython_soft_nms_wrapper", "OPS"]
 
 
 def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor | None:
@@ -575,6 +576,45 @@ def multiclass_nms(cls_score, bbox_xyxy, nms_thresh, min_det_score=0.05, first_c
                                 float(min_det_score), float(nms_thresh), _p(dets), _p(counts), _p(keep),
                                 _p(nkeep), _p(src), _p(ws), nbytes, _stream()))
     return dets, counts, keep, nkeep, src
+
+
+# --------------------------------------------------------------------------------------------
+# soft_nms  (operator_py/cython/cpu_nms.pyx:98-203, operator_py/nms.py:5-16)
+# --------------------------------------------------------------------------------------------
+_SOFT_METHODS = {"hard": 0, "linear": 1, "gaussian": 2}
+
+
+def soft_nms_batched(dets, sigma=0.5, Nt=0.3, threshold=0.001, method=0, counts=None):
+    """All problems at once: dets (P,m,5) -> (boxes (P,m,5), inds (P,m) int32, counts (P) int32)."""
+    dets = _dev(dets, "dets")
+    if dets.dim() != 3 or dets.shape[2] != 5:
+        raise ValueError("dets must be (P,m,5)")
+    P, m, _ = dets.shape
+    counts = _dev(counts, "counts", torch.int32)
+    ob = torch.empty_like(dets)
+    oi = torch.empty((P, m), device=dets.device, dtype=torch.int32)
+    oc = torch.empty((P,), device=dets.device, dtype=torch.int32)
+    check(_lib.lib().sdet_soft_nms(_p(dets), _p(counts), P, m, float(sigma), float(Nt), float(threshold),
+                                   int(method), _p(ob), _p(oi), _p(oc), _stream()))
+    return ob, oi, oc
+
+
+def soft_nms(boxes_in, sigma=0.5, Nt=0.3, threshold=0.001, method=0):
+    """Same signature and result as the Cython `soft_nms`: (boxes[:N], inds[:N])."""
+    ob, oi, oc = soft_nms_batched(boxes_in[None], sigma, Nt, threshold, method)
+    n = int(oc[0])
+    return ob[0, :n], oi[0, :n].to(torch.int64)
+
+
+def cython_soft_nms_wrapper(thresh, sigma=0.5, score_thresh=0.001, method="linear"):
+    """operator_py/nms.py:5-16 — returns fn(dets (m,5)) -> dets, as pTest.nms.type expects
+    (detection_test.py:224-231)."""
+    assert method in _SOFT_METHODS, "Unknown soft_nms method: {}".format(method)
+
+    def _nms(dets):
+        return soft_nms(dets, sigma, thresh, score_thresh, _SOFT_METHODS[method])[0]
+
+    return _nms
 
 
 # Registry keyed by the reference's operator names (what symbol/builder.py binds by string).
