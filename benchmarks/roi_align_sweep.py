@@ -35,14 +35,15 @@ def algorithmic_bytes(rois, levels, shapes, C, pooled, strides, with_argmax):
     return int(total)
 
 
-def time_op(fn, iters, flush):
+def time_op(fn, iters, flush, do_flush=True):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(iters)]
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
     for s, e in ev:
-        flush.fill_(1.0)  # 512 MB write: evicts the 126 MB L2
+        if do_flush:
+            flush.fill_(1.0)  # 512 MB write: evicts the 126 MB L2
         s.record()
         fn()
         e.record()
@@ -56,6 +57,8 @@ def main():
     ap.add_argument("--shape", default="target")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--argmax", type=int, default=0)
+    ap.add_argument("--plan", type=int, default=1)
+    ap.add_argument("--noflush", type=int, default=0)
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(0)
@@ -72,10 +75,11 @@ def main():
     nbytes = algorithmic_bytes(rois_np, lv, shapes, C, pooled, synth.FPN_STRIDES, bool(a.argmax))
 
     def fn():
-        ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=bool(a.argmax))
+        ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=bool(a.argmax),
+                              use_plan=bool(a.plan))
 
-    med, mn = time_op(fn, a.iters, flush)
-    print(json.dumps({"shape": a.shape, "B": B, "N": N, "pooled": pooled, "argmax": a.argmax,
+    med, mn = time_op(fn, a.iters, flush, not a.noflush)
+    print(json.dumps({"shape": a.shape, "B": B, "N": N, "pooled": pooled, "argmax": a.argmax, "plan": a.plan, "noflush": a.noflush, "modepref": os.environ.get("SDET_RA_MODEPREF"), "tiles": os.environ.get("SDET_RA_TILES"),
                       "cpt": os.environ.get("SDET_RA_CPT"), "phs": os.environ.get("SDET_RA_PHS"),
                       "us_median": round(med, 2), "us_min": round(mn, 2), "alg_bytes": nbytes,
                       "GBps": round(nbytes / med / 1e3, 1),

@@ -50,10 +50,14 @@ uint64_t sdet_launch_count(void);
  *   data  (B,C,H,W) device, rois (B,N,4) device [x1,y1,x2,y2] image px, image = n / N.
  *   out, argmax_x, argmax_y (B,N,C,PH,PW) device.  argmax_x/argmax_y may both be NULL
  *   (inference: they are hidden outputs, roi_align_v2.cc:175-178) — then they are not written.
- * ------------------------------------------------------------------------------------------ */
+ *   workspace: optional device scratch of sdet_roi_align_v2_workspace(B,N) bytes, 16B-aligned.
+ *   With it the per-roi sample tables are computed once per roi by a small pre-kernel instead of
+ *   once per (roi, channel group) CTA; NULL / 0 selects the inline path (identical results). */
+size_t sdet_roi_align_v2_workspace(int B, int N);
 int sdet_roi_align_v2_forward(const float* data, const float* rois, float* out, float* argmax_x,
                               float* argmax_y, int B, int N, int C, int H, int W, int pooled_h,
-                              int pooled_w, float spatial_scale, void* stream);
+                              int pooled_w, float spatial_scale, void* workspace,
+                              size_t workspace_bytes, void* stream);
 
 /* _backward_ROIAlign_v2  (operator_cxx/contrib/roi_align_v2.cu:17-85 kernel, :88-143 driver).
  *   ograd, argmax_x, argmax_y (B,N,C,PH,PW); grad_data (B,C,H,W).
@@ -72,13 +76,13 @@ int sdet_roi_align_v2_backward(const float* ograd, const float* argmax_x, const 
  *   (spatial_scale = 1/stride, must be a power of two as in the reference's `2**lvl == s` test).
  *   feats/H/W/strides are HOST arrays of length num_levels (<= SDET_MAX_LEVELS).
  *   levels_out (B*N int32, device, may be NULL): assigned level index, -1 if no level matched.
- *   argmax_x/argmax_y as above (may be NULL). */
+ *   argmax_x/argmax_y and workspace as above (may be NULL). */
 int sdet_fpn_roi_align_v2_forward(const float* const* feats, const int* H, const int* W,
                                   const int* strides, int num_levels, const float* rois,
                                   float* out, float* argmax_x, float* argmax_y,
                                   int32_t* levels_out, int B, int N, int C, int pooled_h,
                                   int pooled_w, int roi_canonical_scale, int roi_canonical_level,
-                                  void* stream);
+                                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of the fused op: scatters into the grad tensor of each roi's assigned level.
  *   grad_feats[l] device (B,C,H[l],W[l]); levels (B*N int32 device) as written by the forward. */

@@ -27,13 +27,14 @@ _SIGNATURES = {
     "sdet_abi_version": [],
     "sdet_last_error": [],
     "sdet_launch_count": [],
+    "sdet_roi_align_v2_workspace": [c_int, c_int],
     "sdet_roi_align_v2_forward": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
-                                  c_int, c_float, _P],
+                                  c_int, c_float, _P, c_size_t, _P],
     "sdet_roi_align_v2_backward": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_int, _P],
     "sdet_fpn_roi_align_v2_forward": [POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                       c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
-                                      c_int, c_int, _P],
+                                      c_int, c_int, _P, c_size_t, _P],
     "sdet_fpn_roi_align_v2_backward": [_P, _P, _P, _P, POINTER(_P), POINTER(c_int), POINTER(c_int),
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "sdet_roi_pooling_v1_forward": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -72,7 +73,7 @@ _SIGNATURES = {
 }
 _RESTYPES = {"sdet_last_error": c_char_p, "sdet_launch_count": c_uint64,
              "sdet_proposal_v3_workspace": c_size_t, "sdet_proposal_v3_fpn_workspace": c_size_t, "sdet_contrib_nms_workspace": c_size_t,
-             "sdet_nms_workspace": c_size_t, "sdet_multiclass_nms_workspace": c_size_t}
+             "sdet_nms_workspace": c_size_t, "sdet_roi_align_v2_workspace": c_size_t, "sdet_multiclass_nms_workspace": c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

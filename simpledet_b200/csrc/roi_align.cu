@@ -30,7 +30,6 @@ namespace {
 
 constexpr int kMaxS = 4;                 // samples per bin per axis kept in the tables
 constexpr int kMaxP = SDET_MAX_POOLED;   // pooled size limit per axis
-constexpr int kTab = kMaxP * kMaxS;
 constexpr int kFlagNot2 = 1;             // some non-empty bin does not have exactly 2 samples
 constexpr int kFlagOverflow = 2;         // some bin has more than kMaxS samples
 constexpr int kFlagEmpty = 4;            // some bin is empty along an axis (end <= start)
@@ -54,16 +53,18 @@ struct RoiAlignArgs {
   float* argy;
   int32_t* levels_out;
   int B, N, C, PH, PW;
+  const void* plans;  // per-roi preamble records written by roi_align_plan_kernel, or nullptr
   uint64_t negzero2;  // {-0.0f,-0.0f}: opaque addend that keeps FFMA2 products exact
 };
 
+template <int TP>  // TP = max bins per axis this instantiation handles (16 or kMaxP)
 struct AxisTab {
-  float coord[kTab];
-  float w0[kTab];  // 1 - alpha
-  float w1[kTab];  // alpha
-  int lo[kTab];
-  int hi[kTab];
-  int cnt[kMaxP];  // -1: bin empty along this axis (end <= start); else #samples (may be 0)
+  float coord[TP * kMaxS];
+  float w0[TP * kMaxS];  // 1 - alpha
+  float w1[TP * kMaxS];  // alpha
+  int lo[TP * kMaxS];
+  int hi[TP * kMaxS];
+  int cnt[TP];  // -1: bin empty along this axis (end <= start); else #samples (may be 0)
 };
 
 __device__ __forceinline__ float min_ref(float a, float b) { return a < b ? a : b; }  // mshadow_op::minimum
@@ -80,7 +81,8 @@ __device__ __forceinline__ int fpn_level(float x1, float y1, float x2, float y2,
 }
 
 // roi_align_v2-inl.h:91-125 for one bin of one axis.  Thread-private; writes the axis table.
-__device__ void build_axis_bin(AxisTab& t, int p, int P, float roi_start, float roi_end,
+template <int TP>
+__device__ void build_axis_bin(AxisTab<TP>& t, int p, int P, float roi_start, float roi_end,
                                int extent, int* s_flags, int* s_min, int* s_max) {
   const float size = __fsub_rn(roi_end, roi_start);
   const float bin = __fdiv_rn(size, (float)P);
@@ -232,6 +234,12 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   return r;
 }
 
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float r;  // 3-input max (sm_100+): NaN operands are dropped like fmaxf does
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 template <int CPT, int kCS, int K = 0>
 struct TapLoader {  // R[k][t] = smem[base_t + k*kCS*4], fully unrolled with immediate offsets
   static __device__ __forceinline__ void run(float (&R)[CPT][2], unsigned al, unsigned ar) {
@@ -245,14 +253,74 @@ struct TapLoader<CPT, kCS, CPT> {
   static __device__ __forceinline__ void run(float (&)[CPT][2], unsigned, unsigned) {}
 };
 
+// ---------------------------------------------------------------------------------------------
+// Per-roi preamble: FPN level + the reference's sample loop restated into the axis tables.
+// It is a ~3 us serial dependency chain (double-precision divide + float/double loop), so the
+// forward launch runs it ONCE per roi in `roi_align_plan_kernel` and every (roi, channel group)
+// CTA of the main kernel just loads the 2.7 KB record; without a workspace the main kernel runs it
+// inline (same code, same results).
+// s_scal: {li, flags, hmin, hmax, wmin, wmax}
+// ---------------------------------------------------------------------------------------------
+template <int TP>
+__device__ __forceinline__ void roi_preamble(const RoiAlignArgs& a, const int n, const int PH, const int PW,
+                                             AxisTab<TP>& s_th, AxisTab<TP>& s_tw, int* s_scal) {
+  const int tid = threadIdx.x;
+  const float x1 = __ldg(a.rois + 4 * (size_t)n + 0), y1 = __ldg(a.rois + 4 * (size_t)n + 1);
+  const float x2 = __ldg(a.rois + 4 * (size_t)n + 2), y2 = __ldg(a.rois + 4 * (size_t)n + 3);
+  int li = 0;
+  if (a.fpn) {
+    const int t = fpn_level(x1, y1, x2, y2, a.scale0, a.lvl0, a.k_min, a.k_max);
+    li = -1;
+    for (int l = 0; l < a.num_levels; ++l)
+      if (a.lvl[l].stride_log2 == t) li = l;
+  }
+  if (tid == 0) {
+    s_scal[0] = li;
+    s_scal[1] = 0;
+    s_scal[2] = INT_MAX;
+    s_scal[3] = -1;
+    s_scal[4] = INT_MAX;
+    s_scal[5] = -1;
+  }
+  __syncthreads();
+  if (li >= 0) {
+    const Level& L = a.lvl[li];
+    const float scale = L.scale;
+    if (tid < PH)
+      build_axis_bin(s_th, tid, PH, __fmul_rn(y1, scale), __fmul_rn(y2, scale), L.H, &s_scal[1], &s_scal[2], &s_scal[3]);
+    else if (tid < PH + PW)
+      build_axis_bin(s_tw, tid - PH, PW, __fmul_rn(x1, scale), __fmul_rn(x2, scale), L.W, &s_scal[1], &s_scal[4],
+                     &s_scal[5]);
+  }
+  __syncthreads();
+}
+
+struct PlanRecord {  // what a (roi, channel group) CTA needs from the preamble (TP = 16)
+  int scal[8];
+  AxisTab<16> th, tw;
+};
+static_assert(sizeof(PlanRecord) % 16 == 0, "PlanRecord is copied with 16-byte accesses");
+
+__global__ void __launch_bounds__(64) roi_align_plan_kernel(const __grid_constant__ RoiAlignArgs a,
+                                                            PlanRecord* __restrict__ plans) {
+  __shared__ __align__(16) PlanRecord s_rec;
+  const int n = blockIdx.x;
+  roi_preamble<16>(a, n, a.PH, a.PW, s_rec.th, s_rec.tw, s_rec.scal);
+  if (a.levels_out != nullptr && threadIdx.x == 0) a.levels_out[n] = s_rec.scal[0];
+  const int4* src = reinterpret_cast<const int4*>(&s_rec);
+  int4* dst = reinterpret_cast<int4*>(plans + n);
+  for (int i = threadIdx.x; i < (int)(sizeof(PlanRecord) / 16); i += blockDim.x) dst[i] = src[i];
+}
+
 // kCapFloats: floats of dynamic shared memory for the window buffers (12288 = 48 KB -> 4 CTAs/SM)
 template <int CPT, bool kArg, int kPH, int kPW, int kCapFloats>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (kCapFloats <= 7680 ? 6 : (kCapFloats <= 9216 ? 5 : (kCapFloats <= 12288 ? 4 : 3))))
 roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles, const int mode_pref) {
   extern __shared__ __align__(16) float s_win[];
-  __shared__ AxisTab s_th, s_tw;
-  __shared__ __align__(16) HRow s_hrow[kTab];
-  __shared__ int s_flags, s_hmin, s_hmax, s_wmin, s_wmax;
+  constexpr int TP = (kPH > 0 && kPH <= 16 && kPW <= 16) ? 16 : kMaxP;
+  __shared__ __align__(16) AxisTab<TP> s_th, s_tw;
+  __shared__ __align__(16) HRow s_hrow[TP * kMaxS];
+  __shared__ __align__(16) int s_scal[8];  // {li, flags, hmin, hmax, wmin, wmax}
 
   constexpr int NW = 4;  // warps per CTA
   static_assert(CPT % 2 == 0, "channels are processed in fp32x2 pairs");
@@ -266,17 +334,23 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles,
   const int cgrp0 = blockIdx.y * tiles * (2 * CPT);            // first channel of this CTA
   const int cgrp1 = min(C, cgrp0 + tiles * (2 * CPT));         // one past the last
 
-  const float x1 = __ldg(a.rois + 4 * (size_t)n + 0), y1 = __ldg(a.rois + 4 * (size_t)n + 1);
-  const float x2 = __ldg(a.rois + 4 * (size_t)n + 2), y2 = __ldg(a.rois + 4 * (size_t)n + 3);
-
-  int li = 0;
-  if (a.fpn) {
-    const int t = fpn_level(x1, y1, x2, y2, a.scale0, a.lvl0, a.k_min, a.k_max);
-    li = -1;
-    for (int l = 0; l < a.num_levels; ++l)
-      if (a.lvl[l].stride_log2 == t) li = l;
-    if (a.levels_out != nullptr && blockIdx.y == 0 && tid == 0) a.levels_out[n] = li;
+  // ---- preamble: load the roi's record written by roi_align_plan_kernel, or compute it here
+  if (TP == 16 && a.plans != nullptr) {
+    const PlanRecord* rec = static_cast<const PlanRecord*>(a.plans) + n;
+    constexpr int kHdr = 32 / 16, kTabV = (int)(sizeof(AxisTab<16>) / 16);
+    const int4* src = reinterpret_cast<const int4*>(rec);
+    for (int i = tid; i < kHdr + 2 * kTabV; i += blockDim.x) {
+      const int4 v = __ldg(src + i);
+      if (i < kHdr) reinterpret_cast<int4*>(s_scal)[i] = v;
+      else if (i < kHdr + kTabV) reinterpret_cast<int4*>(&s_th)[i - kHdr] = v;
+      else reinterpret_cast<int4*>(&s_tw)[i - kHdr - kTabV] = v;
+    }
+    __syncthreads();
+  } else {
+    roi_preamble<TP>(a, n, PH, PW, s_th, s_tw, s_scal);
+    if (a.levels_out != nullptr && blockIdx.y == 0 && tid == 0) a.levels_out[n] = s_scal[0];
   }
+  const int li = s_scal[0];
 
   const size_t out_base = ((size_t)n * C + cgrp0) * PP;
   const int nelem = (cgrp1 - cgrp0) * PP;
@@ -294,26 +368,10 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles,
 
   const Level& L = a.lvl[li];
   const int H = L.H, W = L.W;
-  const float scale = L.scale;
-  const float rsw = __fmul_rn(x1, scale), rsh = __fmul_rn(y1, scale);
-  const float rew = __fmul_rn(x2, scale), reh = __fmul_rn(y2, scale);
 
-  if (tid == 0) {
-    s_flags = 0;
-    s_hmin = INT_MAX;
-    s_hmax = -1;
-    s_wmin = INT_MAX;
-    s_wmax = -1;
-  }
-  __syncthreads();
-  if (tid < PH)
-    build_axis_bin(s_th, tid, PH, rsh, reh, H, &s_flags, &s_hmin, &s_hmax);
-  else if (tid < PH + PW)
-    build_axis_bin(s_tw, tid - PH, PW, rsw, rew, W, &s_flags, &s_wmin, &s_wmax);
-  __syncthreads();
-
-  const int flags = s_flags;
-  const int hmin = s_hmin, wmin = s_wmin;
+  const int flags = s_scal[1];
+  const int hmin = s_scal[2], wmin = s_scal[4];
+  const int s_hmax = s_scal[3], s_wmax = s_scal[5];
   const int Hwin = s_hmax - hmin + 1, Wwin = s_wmax - wmin + 1;
   const bool any = (s_hmax >= 0) && (s_wmax >= 0);
   const int HW = H * W;
@@ -343,7 +401,11 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles,
       const int nh = s_th.cnt[ph], nw = s_tw.cnt[pw];
       float best = 0.f, bx = -1.f, by = -1.f;
       if (flags & kFlagOverflow) {
-        element_direct(pl, H, W, PH, PW, ph, pw, rsw, rsh, rew, reh, best, bx, by);
+        const float sc_ = L.scale;
+        element_direct(pl, H, W, PH, PW, ph, pw, __fmul_rn(__ldg(a.rois + 4 * (size_t)n), sc_),
+                       __fmul_rn(__ldg(a.rois + 4 * (size_t)n + 1), sc_),
+                       __fmul_rn(__ldg(a.rois + 4 * (size_t)n + 2), sc_),
+                       __fmul_rn(__ldg(a.rois + 4 * (size_t)n + 3), sc_), best, bx, by);
       } else if (nh >= 0 && nw >= 0) {
         best = -FLT_MAX;
         for (int i = 0; i < nh; ++i) {
@@ -406,6 +468,7 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles,
     }
   }
   const uint64_t nz2 = a.negzero2;  // {-0.0f, -0.0f}; a kernel argument on purpose (see header)
+  const bool has_empty = (flags & kFlagEmpty) != 0;
 
   // Everything below is instantiated per (channel stride kCS, channel groups NCG, buffers NBUF).
   auto run = [&](auto cs_tag, auto ncg_tag, auto nbuf_tag) {
@@ -461,126 +524,151 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles,
       const int cbase = cgrp0 + tile * CTILE + cg * CPT;
       const unsigned sl = buf + 4u * (unsigned)(cg * CPT * kCS + xl);   // lane's left-tap column
       const unsigned sr = buf + 4u * (unsigned)(cg * CPT * kCS + xr);   // lane's right-tap column
-      float RA[CPT][2], RB[CPT][2];
-#pragma unroll
-      for (int k = 0; k < CPT; ++k) RA[k][0] = RA[k][1] = RB[k][0] = RB[k][1] = 0.f;
+      float RA[CPT][2], RB[CPT][2];  // 2-row register cache; filled before first use (rowA/B = -1)
       int rowA = -1, rowB = -1;
       const size_t obase = ((size_t)n * C + cbase) * PP + (size_t)ph_beg * PW + pw;
       float* outp = a.out + obase;
       float* axp = kArg ? a.argx + obase : nullptr;
       float* ayp = kArg ? a.argy + obase : nullptr;
       const bool store = lane_on && sx == 0;
+      // inference: after the pair exchange both lanes of a pw hold all CPT maxima; lane s stores
+      // channels [s*CPT/2, (s+1)*CPT/2) so every store instruction has 28 active lanes
+      float* outh = outp + (size_t)(sx * (CPT / 2)) * PP;
 
-      for (int ph = ph_beg; ph < ph_end; ++ph) {
-        const int hcnt = s_th.cnt[ph];
-        float m[CPT];
-        int mi[CPT];
+      // One h-sample: make the register sets hold rows (lo, hi) — whichever set already holds
+      // `lo` plays the low row, so nothing is ever moved — then the bilinear values of the CPT
+      // channels.  The tests are warp-uniform; routing them through a vote lets ptxas emit plain
+      // branches instead of divergence bookkeeping.
+      auto sample = [&](const int4 hr, float (&v)[CPT]) {
+        const int olo = hr.x, ohi = hr.y;
+        const float a0 = __int_as_float(hr.z), a1 = __int_as_float(hr.w);
+        const float wtl = __fmul_rn(a0, b0), wbl = __fmul_rn(a1, b0);
+        const float wtr = __fmul_rn(a0, b1), wbr = __fmul_rn(a1, b1);
+        const uint64_t wtl2 = pack2(wtl, wtl), wbl2 = pack2(wbl, wbl);
+        const uint64_t wtr2 = pack2(wtr, wtr), wbr2 = pack2(wbr, wbr);
+        auto step = [&](const float (&Lo)[CPT][2], const float (&Hi)[CPT][2]) {
 #pragma unroll
-        for (int k = 0; k < CPT; ++k) {
-          m[k] = -FLT_MAX;
-          mi[k] = -1;
-        }
-        if (hcnt == 2) {
-          int4 hr_nxt = *reinterpret_cast<const int4*>(&s_hrow[ph * kMaxS]);
-#pragma unroll 1
-          for (int hs = 0; hs < 2; ++hs) {
-            const int4 hr = hr_nxt;
-            hr_nxt = *reinterpret_cast<const int4*>(&s_hrow[ph * kMaxS + 1]);  // prefetch sample 1
-            const int olo = hr.x, ohi = hr.y;
-            const float a0 = __int_as_float(hr.z), a1 = __int_as_float(hr.w);
-            const float wtl = __fmul_rn(a0, b0), wbl = __fmul_rn(a1, b0);
-            const float wtr = __fmul_rn(a0, b1), wbr = __fmul_rn(a1, b1);
-            const uint64_t wtl2 = pack2(wtl, wtl), wbl2 = pack2(wbl, wbl);
-            const uint64_t wtr2 = pack2(wtr, wtr), wbr2 = pack2(wbr, wbr);
-            auto step = [&](const float (&Lo)[CPT][2], const float (&Hi)[CPT][2]) {
-#pragma unroll
-              for (int k = 0; k < CPT; k += 2) {
-                // roi_align_v2-inl.h:137-140 for channels k, k+1: ((tl + bl) + tr) + br
-                const uint64_t ptl = fma2(wtl2, pack2(Lo[k][0], Lo[k + 1][0]), nz2);
-                const uint64_t pbl = fma2(wbl2, pack2(Hi[k][0], Hi[k + 1][0]), nz2);
-                const uint64_t ptr = fma2(wtr2, pack2(Lo[k][1], Lo[k + 1][1]), nz2);
-                const uint64_t pbr = fma2(wbr2, pack2(Hi[k][1], Hi[k + 1][1]), nz2);
-                float v0, v1;
-                unpack2(add2(add2(add2(ptl, pbl), ptr), pbr), v0, v1);
-                if (kArg) {
-                  if (v0 > m[k]) {
-                    m[k] = v0;
-                    mi[k] = 2 * hs + sx;
-                  }
-                  if (v1 > m[k + 1]) {
-                    m[k + 1] = v1;
-                    mi[k + 1] = 2 * hs + sx;
-                  }
-                } else {
-                  // == `if (v > m) m = v` incl. the NaN / -inf / -FLT_MAX cases
-                  m[k] = fmaxf(m[k], v0);
-                  m[k + 1] = fmaxf(m[k + 1], v1);
-                }
-              }
-            };
-            // 2-row register cache, no moves: whichever set holds `lo` plays the low row
-            if (olo == rowA) {
-              if (ohi != rowB) {
-                TapLoader<CPT, kCS>::run(RB, sl + ohi, sr + ohi);
-                rowB = ohi;
-              }
-              step(RA, RB);
-            } else if (olo == rowB) {
-              if (ohi != rowA) {
-                TapLoader<CPT, kCS>::run(RA, sl + ohi, sr + ohi);
-                rowA = ohi;
-              }
-              step(RB, RA);
-            } else {
-              TapLoader<CPT, kCS>::run(RA, sl + olo, sr + olo);
-              rowA = olo;
-              if (ohi != rowB) {
-                TapLoader<CPT, kCS>::run(RB, sl + ohi, sr + ohi);
-                rowB = ohi;
-              }
-              step(RA, RB);
-            }
+          for (int k = 0; k < CPT; k += 2) {
+            // roi_align_v2-inl.h:137-140 for channels k, k+1: ((tl + bl) + tr) + br
+            const uint64_t ptl = fma2(wtl2, pack2(Lo[k][0], Lo[k + 1][0]), nz2);
+            const uint64_t pbl = fma2(wbl2, pack2(Hi[k][0], Hi[k + 1][0]), nz2);
+            const uint64_t ptr = fma2(wtr2, pack2(Lo[k][1], Lo[k + 1][1]), nz2);
+            const uint64_t pbr = fma2(wbr2, pack2(Hi[k][1], Hi[k + 1][1]), nz2);
+            unpack2(add2(add2(add2(ptl, pbl), ptr), pbr), v[k], v[k + 1]);
           }
+        };
+        if (__all_sync(0xffffffffu, olo == rowA)) {
+          if (__any_sync(0xffffffffu, ohi != rowB)) {
+            TapLoader<CPT, kCS>::run(RB, sl + ohi, sr + ohi);
+            rowB = ohi;
+          }
+          step(RA, RB);
+        } else if (__all_sync(0xffffffffu, olo == rowB)) {
+          if (__any_sync(0xffffffffu, ohi != rowA)) {
+            TapLoader<CPT, kCS>::run(RA, sl + ohi, sr + ohi);
+            rowA = ohi;
+          }
+          step(RB, RA);
+        } else {
+          TapLoader<CPT, kCS>::run(RA, sl + olo, sr + olo);
+          rowA = olo;
+          if (__any_sync(0xffffffffu, ohi != rowB)) {
+            TapLoader<CPT, kCS>::run(RB, sl + ohi, sr + ohi);
+            rowB = ohi;
+          }
+          step(RA, RB);
         }
-        // combine the two w-samples of this pw (lanes 2pw, 2pw+1); reference order is
-        // (h0,w0),(h0,w1),(h1,w0),(h1,w1) with strict '>' => on equal values the smaller index wins.
-        // Bins that are empty along an axis are written wrongly here and repaired by the fix-up
-        // pass at the end of the kernel (rare: only rois that reach outside the map).
+      };
+
+      const int4* tab = reinterpret_cast<const int4*>(s_hrow);
+      for (int ph = ph_beg; ph < ph_end; ++ph) {
+        float v0[CPT], v1[CPT];
+        const bool hvalid = !has_empty || s_th.cnt[ph] == 2;   // warp-uniform
+        if (hvalid) {
+          const int4 h0 = tab[ph * kMaxS], h1 = tab[ph * kMaxS + 1];
+          sample(h0, v0);
+          sample(h1, v1);
+        } else {
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) v0[k] = v1[k] = -FLT_MAX;  // bin empty along h: zeroed below
+        }
+        // bins that are empty along an axis (end <= start) pool to 0 / argmax -1
+        // (roi_align_v2-inl.h:111-117); only CTAs whose roi has such bins pay for the selects
+        const bool zero_out = has_empty && (!hvalid || wcnt < 0);
+        // combine: reference order is (h0,w0),(h0,w1),(h1,w0),(h1,w1) with strict '>' starting from
+        // -FLT_MAX => maximum, first index on ties, NaN / -inf never win.
         if (kArg) {
           const float hc0 = s_th.coord[ph * kMaxS], hc1 = s_th.coord[ph * kMaxS + 1];
           const float pwc = __shfl_xor_sync(0xffffffffu, wc, 1);
 #pragma unroll
           for (int k = 0; k < CPT; ++k) {
-            const float pm = __shfl_xor_sync(0xffffffffu, m[k], 1);
-            const int pi = __shfl_xor_sync(0xffffffffu, mi[k], 1);
-            const float best = fmaxf(m[k], pm);
-            int bi = mi[k];
+            float mk = -FLT_MAX;
+            int mi = -1;
+            if (v0[k] > mk) {
+              mk = v0[k];
+              mi = sx;
+            }
+            if (v1[k] > mk) {
+              mk = v1[k];
+              mi = 2 + sx;
+            }
+            const float pm = __shfl_xor_sync(0xffffffffu, mk, 1);
+            const int pi = __shfl_xor_sync(0xffffffffu, mi, 1);
+            const float best = fmaxf(mk, pm);
+            int bi = mi;
             float bxc = wc;
-            const bool take = (pi >= 0) && (bi < 0 || pm > m[k] || (pm == m[k] && pi < bi));
+            const bool take = (pi >= 0) && (bi < 0 || pm > mk || (pm == mk && pi < bi));
             if (take) {
               bi = pi;
               bxc = pwc;
             }
             if (store) {
-              outp[k * PP] = best;
-              axp[k * PP] = bi < 0 ? -1.f : bxc;
-              ayp[k * PP] = bi < 0 ? -1.f : ((bi & 2) ? hc1 : hc0);
+              const bool none = zero_out || bi < 0;
+              outp[k * PP] = zero_out ? 0.f : best;
+              axp[k * PP] = none ? -1.f : bxc;
+              ayp[k * PP] = none ? -1.f : ((bi & 2) ? hc1 : hc0);
             }
           }
           axp += PW;
           ayp += PW;
+          outp += PW;
         } else {
+          float best[CPT];
 #pragma unroll
           for (int k = 0; k < CPT; ++k) {
-            const float best = fmaxf(m[k], __shfl_xor_sync(0xffffffffu, m[k], 1));
-            if (store) outp[k * PP] = best;
+            const float mk = fmaxf(v0[k], v1[k]);  // fmaxf drops a NaN operand like `v > m` does
+            best[k] = max3f(mk, __shfl_xor_sync(0xffffffffu, mk, 1), -FLT_MAX);
           }
+          if (lane_on) {
+            if (!has_empty) {
+#pragma unroll
+              for (int k = 0; k < CPT / 2; ++k) outh[k * PP] = sx ? best[CPT / 2 + k] : best[k];
+            } else {
+#pragma unroll
+              for (int k = 0; k < CPT / 2; ++k)
+                outh[k * PP] = zero_out ? 0.f : (sx ? best[CPT / 2 + k] : best[k]);
+            }
+          }
+          outh += PW;
         }
-        outp += PW;
       }
     };
 
     // ---- software pipeline over the channel tiles of this roi ----
+    const bool dbg_nostage = (mode_pref & 2) != 0, dbg_nocompute = (mode_pref & 4) != 0;  // profiling only
+    if (dbg_nostage || dbg_nocompute) {
+      for (int t = 0; t < ntiles; ++t) {
+        if (!dbg_nostage) {
+          stage(t, sbase);
+          cp_async_commit();
+          cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (!dbg_nocompute) compute(t, sbase);
+        __syncthreads();
+      }
+      return;
+    }
     stage(0, sbase);
     cp_async_commit();
     for (int t = 0; t < ntiles; ++t) {
@@ -614,19 +702,6 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles,
   else
     run(integral_constant<int, CS3>{}, integral_constant<int, 1>{}, integral_constant<int, 1>{});
 
-  if (flags & kFlagEmpty) {  // repair bins that are empty along an axis: out = 0, argmax = -1
-    __syncthreads();         // orders this CTA's earlier global stores before the overwrite
-    for (int e = tid; e < nelem; e += blockDim.x) {
-      const int pw_ = e % PW, ph_ = (e / PW) % PH;
-      if (s_th.cnt[ph_] < 0 || s_tw.cnt[pw_] < 0) {
-        a.out[out_base + e] = 0.f;
-        if (kArg) {
-          a.argx[out_base + e] = -1.f;
-          a.argy[out_base + e] = -1.f;
-        }
-      }
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -715,13 +790,23 @@ int launch_fwd_t(const RoiAlignArgs& a, cudaStream_t st) {
   return SDET_OK;
 }
 
-int launch_fwd(RoiAlignArgs& a, cudaStream_t st) {
+int launch_fwd(RoiAlignArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if ((a.argx == nullptr) != (a.argy == nullptr))
     return sdet::fail(SDET_ERR_INVALID_ARG, "argmax_x and argmax_y must both be given or both NULL");
   a.negzero2 = 0x8000000080000000ull;  // {-0.0f, -0.0f}, see the forward kernel's header
+  a.plans = nullptr;
+  if (workspace != nullptr && a.PH <= 16 && a.PW <= 16) {
+    const size_t need = sizeof(PlanRecord) * (size_t)a.B * a.N;
+    if (workspace_bytes < need)
+      return sdet::fail(SDET_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
+    if (reinterpret_cast<uintptr_t>(workspace) % 16)
+      return sdet::fail(SDET_ERR_INVALID_ARG, "workspace must be 16-byte aligned");
+    roi_align_plan_kernel<<<(unsigned)(a.B * a.N), 64, 0, st>>>(a, static_cast<PlanRecord*>(workspace));
+    SDET_LAUNCH_CHECK("roi_align_plan_kernel");
+    a.plans = workspace;
+  }
   int cap = 0;
   if (const char* e = getenv("SDET_RA_CAP")) cap = atoi(e);  // tuning only
-  if (cap == 8192 && a.PH == 14 && a.PW == 14) return launch_fwd_t<8, 14, 14, 8192>(a, st);
   if (cap == 9216 && a.PH == 14 && a.PW == 14) return launch_fwd_t<8, 14, 14, 9216>(a, st);
   if (a.PH == 7 && a.PW == 7) return launch_fwd_t<8, 7, 7, 12288>(a, st);
   if (a.PH == 14 && a.PW == 14) return launch_fwd_t<8, 14, 14, 12288>(a, st);
@@ -731,10 +816,15 @@ int launch_fwd(RoiAlignArgs& a, cudaStream_t st) {
 }  // namespace
 
 
+extern "C" size_t sdet_roi_align_v2_workspace(int B, int N) {
+  return (B > 0 && N > 0) ? sizeof(PlanRecord) * (size_t)B * N : 0;
+}
+
 extern "C" int sdet_roi_align_v2_forward(const float* data, const float* rois, float* out,
                                          float* argmax_x, float* argmax_y, int B, int N, int C,
                                          int H, int W, int pooled_h, int pooled_w,
-                                         float spatial_scale, void* stream) {
+                                         float spatial_scale, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
   if (int rc = check_common(B, N, C, pooled_h, pooled_w)) return rc;
   SDET_REQUIRE(data && rois && out, "data, rois and out must be non-NULL");
   SDET_REQUIRE(H > 0 && W > 0, "H, W must be > 0");
@@ -750,7 +840,7 @@ extern "C" int sdet_roi_align_v2_forward(const float* data, const float* rois, f
   a.argy = argmax_y;
   a.levels_out = nullptr;
   a.B = B; a.N = N; a.C = C; a.PH = pooled_h; a.PW = pooled_w;
-  return launch_fwd(a, (cudaStream_t)stream);
+  return launch_fwd(a, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 static int ilog2_exact(int v) {
@@ -765,7 +855,8 @@ extern "C" int sdet_fpn_roi_align_v2_forward(const float* const* feats, const in
                                              float* out, float* argmax_x, float* argmax_y,
                                              int32_t* levels_out, int B, int N, int C, int pooled_h,
                                              int pooled_w, int roi_canonical_scale,
-                                             int roi_canonical_level, void* stream) {
+                                             int roi_canonical_level, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
   if (int rc = check_common(B, N, C, pooled_h, pooled_w)) return rc;
   SDET_REQUIRE(feats && H && W && strides && rois && out, "NULL argument");
   SDET_REQUIRE(num_levels >= 1 && num_levels <= SDET_MAX_LEVELS, "num_levels must be in [1, %d]",
@@ -794,7 +885,7 @@ extern "C" int sdet_fpn_roi_align_v2_forward(const float* const* feats, const in
   a.argy = argmax_y;
   a.levels_out = levels_out;
   a.B = B; a.N = N; a.C = C; a.PH = pooled_h; a.PW = pooled_w;
-  return launch_fwd(a, (cudaStream_t)stream);
+  return launch_fwd(a, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 static int launch_bwd(BwdArgs& a, int num_levels, const int* H, const int* W, float* const* grads,

@@ -40,7 +40,7 @@ def test_ctypes_binding_covers_header(built):
 
     L = _lib.lib()
     assert sorted(_lib.EXPORTED_SYMBOLS) == _declared()
-    assert L.sdet_abi_version() == 1
+    assert L.sdet_abi_version() == 2
     assert L.sdet_last_error() == b""
     assert L.sdet_launch_count() == 0
 
@@ -56,13 +56,13 @@ def test_arg_validation_without_gpu(built):
     from simpledet_b200 import _lib
 
     L = _lib.lib()
-    rc = L.sdet_roi_align_v2_forward(None, None, None, None, None, 1, 1, 1, 4, 4, 7, 7, 0.5, None)
+    rc = L.sdet_roi_align_v2_forward(None, None, None, None, None, 1, 1, 1, 4, 4, 7, 7, 0.5, None, 0, None)
     assert rc == 1 and b"non-NULL" in L.sdet_last_error()
-    rc = L.sdet_roi_align_v2_forward(8, 8, 8, None, None, 1, 1, 1, 4, 4, 0, 7, 0.5, None)
+    rc = L.sdet_roi_align_v2_forward(8, 8, 8, None, None, 1, 1, 1, 4, 4, 0, 7, 0.5, None, 0, None)
     assert rc == 1 and b"pooled_size" in L.sdet_last_error()
-    rc = L.sdet_roi_align_v2_forward(8, 8, 8, None, None, 1, 1, 1, 4, 4, 64, 7, 0.5, None)
+    rc = L.sdet_roi_align_v2_forward(8, 8, 8, None, None, 1, 1, 1, 4, 4, 64, 7, 0.5, None, 0, None)
     assert rc == 2
-    rc = L.sdet_roi_align_v2_forward(8, 8, 8, None, None, 1, 1, 1, 4, 4, 7, 7, 1.5, None)
+    rc = L.sdet_roi_align_v2_forward(8, 8, 8, None, None, 1, 1, 1, 4, 4, 7, 7, 1.5, None, 0, None)
     assert rc == 1 and b"spatial_scale" in L.sdet_last_error()
 
 

@@ -25,6 +25,9 @@ def _check_fwd(data, rois, pooled, scale, dev):
     assert np.array_equal(x, rx) and np.array_equal(y, ry)
     out2, _, _ = ops.roi_align_v2_raw(_t(data, dev), _t(rois, dev), pooled, scale, with_argmax=False)
     assert np.array_equal(out2.cpu().numpy(), ro)
+    # the inline-preamble path (no workspace) must agree with the pre-kernel path
+    o3, x3, y3 = ops.roi_align_v2_raw(_t(data, dev), _t(rois, dev), pooled, scale, use_plan=False)
+    assert torch.equal(o3, out) and torch.equal(x3, ax) and torch.equal(y3, ay)
     return ro, rx, ry
 
 
