@@ -253,6 +253,24 @@ int sdet_soft_nms(const float* dets, const int* counts, int problems, int m, flo
                   float threshold, int method, float* out_boxes, int* out_inds, int* out_counts,
                   void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Deformable convolution v1 sampling  (mx.sym.contrib.DeformableConvolution — upstream
+ * apache/incubator-mxnet src/operator/contrib/nn/deformable_im2col.cuh, NOT in the reference
+ * tree; call sites models/dcn/builder.py:14-17; parity unpinned).
+ *   data (B,C,H,W), offset (B, dg*2*KH*KW, Ho, Wo) [per tap: (dy, dx)],
+ *   col (B, C*KH*KW, Ho*Wo): the sampled columns; the dense product with the (F, C/groups*KH*KW)
+ *   weights is a library GEMM done by the caller.
+ *   col2im: gradient of the gather w.r.t. data (grad_data, zero-filled first) and offset
+ *   (grad_offset); either may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+int sdet_deformable_im2col(const float* data, const float* offset, float* col, int B, int C, int H, int W,
+                           int kernel_h, int kernel_w, int pad_h, int pad_w, int stride_h, int stride_w,
+                           int dilate_h, int dilate_w, int num_deformable_group, void* stream);
+int sdet_deformable_col2im(const float* grad_col, const float* data, const float* offset, float* grad_data,
+                           float* grad_offset, int B, int C, int H, int W, int kernel_h, int kernel_w,
+                           int pad_h, int pad_w, int stride_h, int stride_w, int dilate_h, int dilate_w,
+                           int num_deformable_group, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

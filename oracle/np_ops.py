@@ -126,3 +126,50 @@ def flip_boxes(boxes, im_width):
     f[:, 0::4] = im_width - boxes[:, 2::4] - 1
     f[:, 2::4] = im_width - boxes[:, 0::4] - 1
     return f
+
+
+# ---- DCNv1 sampling: restated from the published formulation (upstream MXNet
+# src/operator/contrib/nn/deformable_im2col.h/.cuh; not in the reference tree) — PARITY UNPINNED ----
+def deformable_im2col(data, offset, kernel, stride=(1, 1), dilate=(1, 1), pad=(0, 0), num_deformable_group=1):
+    """data (B,C,H,W), offset (B, dg*2*KH*KW, Ho, Wo) -> col (B, C*KH*KW, Ho*Wo), float32 arithmetic."""
+    f = np.float32
+    data = np.asarray(data, f)
+    offset = np.asarray(offset, f)
+    B, C, H, W = data.shape
+    kh, kw = kernel
+    Ho = (H + 2 * pad[0] - (dilate[0] * (kh - 1) + 1)) // stride[0] + 1
+    Wo = (W + 2 * pad[1] - (dilate[1] * (kw - 1) + 1)) // stride[1] + 1
+    cpg = C // num_deformable_group
+    col = np.zeros((B, C * kh * kw, Ho * Wo), f)
+    hc, wc = np.meshgrid(np.arange(Ho), np.arange(Wo), indexing="ij")
+    for b in range(B):
+        for c in range(C):
+            g = c // cpg
+            im = data[b, c]
+            for i in range(kh):
+                for j in range(kw):
+                    t = i * kw + j
+                    oh = offset[b, g * 2 * kh * kw + 2 * t]
+                    ow = offset[b, g * 2 * kh * kw + 2 * t + 1]
+                    h = (hc * stride[0] - pad[0] + i * dilate[0]).astype(f) + oh
+                    w = (wc * stride[1] - pad[1] + j * dilate[1]).astype(f) + ow
+                    inside = (h >= 0) & (w >= 0) & (h < H) & (w < W)
+                    hl = np.floor(h).astype(np.int64)
+                    wl = np.floor(w).astype(np.int64)
+                    hcl = hl >= H - 1
+                    wcl = wl >= W - 1
+                    hl = np.where(hcl, H - 1, hl)
+                    wl = np.where(wcl, W - 1, wl)
+                    hh_ = np.where(hcl, H - 1, hl + 1)
+                    wh_ = np.where(wcl, W - 1, wl + 1)
+                    h2 = np.where(hcl, hl.astype(f), h)
+                    w2 = np.where(wcl, wl.astype(f), w)
+                    hl_c, wl_c = np.clip(hl, 0, H - 1), np.clip(wl, 0, W - 1)
+                    hh_c, wh_c = np.clip(hh_, 0, H - 1), np.clip(wh_, 0, W - 1)
+                    lh = (h2 - hl.astype(f)).astype(f)
+                    lw = (w2 - wl.astype(f)).astype(f)
+                    hhw, hww = f(1) - lh, f(1) - lw
+                    v = (hhw * hww * im[hl_c, wl_c] + hhw * lw * im[hl_c, wh_c] + lh * hww * im[hh_c, wl_c]
+                         + lh * lw * im[hh_c, wh_c]).astype(f)
+                    col[b, c * kh * kw + t] = np.where(inside, v, f(0)).reshape(-1)
+    return col

@@ -22,7 +22,7 @@ __all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_r
            "fpn_roi_align", "fpn_roi_align_raw", "DecodeBBox", "Proposal_v3", "Proposal_v3_fpn", "NMS", "nms_sorted", "get_top_proposal",
            "multiclass_nms", "ProposalTarget", "FocalLoss", "BBoxNorm",
            "SigmoidCrossEntropy", "soft_nms", "soft_nms_batched",
-           "cython_soft_nms_wrapper", "OPS"]
+           "cython_soft_nms_wrapper", "DeformableConvolution", "OPS"]
 
 
 def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor | None:
@@ -542,6 +542,67 @@ def SigmoidCrossEntropy(data, label, grad_scale=1.0):
 
 
 # --------------------------------------------------------------------------------------------
+# _contrib_DeformableConvolution (DCNv1; models/dcn/builder.py:14-17)
+# --------------------------------------------------------------------------------------------
+class _DeformConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, offset, weight, bias, geo):
+        kh, kw, ph_, pw_, sh, sw, dh, dw, ng, dg = geo
+        data, offset, weight = _dev(data, "data"), _dev(offset, "offset"), _dev(weight, "weight")
+        B, C, H, W = data.shape
+        F = weight.shape[0]
+        Ho = (H + 2 * ph_ - (dh * (kh - 1) + 1)) // sh + 1
+        Wo = (W + 2 * pw_ - (dw * (kw - 1) + 1)) // sw + 1
+        if tuple(offset.shape) != (B, dg * 2 * kh * kw, Ho, Wo):
+            raise ValueError(f"offset must be {(B, dg * 2 * kh * kw, Ho, Wo)}, got {tuple(offset.shape)}")
+        col = torch.empty((B, C * kh * kw, Ho * Wo), device=data.device, dtype=torch.float32)
+        check(_lib.lib().sdet_deformable_im2col(_p(data), _p(offset), _p(col), B, C, H, W, kh, kw, ph_, pw_, sh,
+                                                sw, dh, dw, dg, _stream()))
+        # dense contraction: library GEMM (cuBLAS via torch), grouped like the reference's num_group
+        wg = weight.reshape(ng, F // ng, (C // ng) * kh * kw)
+        cg = col.reshape(B, ng, (C // ng) * kh * kw, Ho * Wo)
+        out = torch.einsum("gfk,bgkp->bgfp", wg, cg).reshape(B, F, Ho, Wo)
+        if bias is not None:
+            out = out + bias.view(1, F, 1, 1)
+        ctx.save_for_backward(data, offset, weight, col)
+        ctx.geo, ctx.has_bias = geo, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        data, offset, weight, col = ctx.saved_tensors
+        kh, kw, ph_, pw_, sh, sw, dh, dw, ng, dg = ctx.geo
+        B, C, H, W = data.shape
+        F = weight.shape[0]
+        gout = _dev(gout, "gout")
+        P = gout.shape[2] * gout.shape[3]
+        go = gout.reshape(B, ng, F // ng, P)
+        wg = weight.reshape(ng, F // ng, (C // ng) * kh * kw)
+        gcol = torch.einsum("gfk,bgfp->bgkp", wg, go).reshape(B, C * kh * kw, P).contiguous()
+        gweight = torch.einsum("bgfp,bgkp->gfk", go, col.reshape(B, ng, (C // ng) * kh * kw, P)).reshape(weight.shape)
+        gdata = torch.empty_like(data)
+        goff = torch.empty_like(offset)
+        check(_lib.lib().sdet_deformable_col2im(_p(gcol), _p(data), _p(offset), _p(gdata), _p(goff), B, C, H, W, kh,
+                                                kw, ph_, pw_, sh, sw, dh, dw, dg, _stream()))
+        gbias = gout.sum((0, 2, 3)) if ctx.has_bias else None
+        return gdata, goff, gweight, gbias, None
+
+
+def DeformableConvolution(data, offset, weight, bias=None, kernel=(3, 3), stride=(1, 1), dilate=(1, 1),
+                          pad=(0, 0), num_filter=None, num_group=1, num_deformable_group=1, no_bias=False):
+    """mx.sym.contrib.DeformableConvolution (DCNv1).  data (B,C,H,W), offset
+    (B, 2*KH*KW*num_deformable_group, Ho, Wo), weight (num_filter, C/num_group, KH, KW)."""
+    kh, kw = _pair(kernel)
+    sh, sw = _pair(stride)
+    dh, dw = _pair(dilate)
+    ph_, pw_ = _pair(pad)
+    if num_filter is not None and weight.shape[0] != num_filter:
+        raise ValueError("weight.shape[0] != num_filter")
+    geo = (kh, kw, ph_, pw_, sh, sw, dh, dw, int(num_group), int(num_deformable_group))
+    return _DeformConvFn.apply(data, offset, weight, None if no_bias else bias, geo)
+
+
+# --------------------------------------------------------------------------------------------
 # get_top_proposal (models/FPN/get_top_proposal.py) and test-time per-class NMS
 # (detection_test.py:233-260 + operator_py/nms.py:41-75)
 # --------------------------------------------------------------------------------------------
@@ -632,6 +693,7 @@ OPS = {
     "_contrib_Proposal_v3": Proposal_v3,
     "_contrib_NMS": NMS,
     "ProposalTarget": ProposalTarget,
+    "_contrib_DeformableConvolution": DeformableConvolution,
     "_contrib_FocalLoss": FocalLoss,
     "_contrib_BBoxNorm": BBoxNorm,
     "_contrib_SigmoidCrossEntropy": SigmoidCrossEntropy,

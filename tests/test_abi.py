@@ -73,3 +73,17 @@ def test_ops_refuse_cpu_tensors(built):
 
     with pytest.raises(RuntimeError, match="CUDA-only"):
         ops.ROIAlign_v2(torch.zeros(1, 1, 4, 4), torch.zeros(1, 1, 4), (2, 2), 1.0)
+
+
+def test_ctypes_arity_matches_header(built):
+    """Every binding in simpledet_b200/_lib.py has exactly as many argtypes as the C declaration."""
+    from simpledet_b200 import _lib
+
+    src = open(os.path.join(ROOT, "include", "simpledet_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = dict(re.findall(r"\b(sdet_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    assert set(decls) == set(_lib._SIGNATURES)
+    for name, params in decls.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib._SIGNATURES[name]), f"{name}: header has {n} parameters, binding has {len(_lib._SIGNATURES[name])}"
