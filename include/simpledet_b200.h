@@ -207,7 +207,9 @@ int sdet_multiclass_nms(const float* cls_score, const float* bbox, int B, int N,
  *   index".  priorities == NULL: cuRAND Philox4x32-10 keyed (seed, image*T+candidate, draw),
  *   T = R+G; else a DEVICE array (B, num_draws, T) uint32 supplied by the caller.  Draw 0 = fg,
  *   1 = bg, 2 + r % (num_draws-2) = r-th negative-padding shuffle; num_draws >= 3.
- *   priorities_used (B,num_draws,T) device or NULL receives the priorities of the draws executed. */
+ *   priorities_used (B,num_draws,T) device or NULL receives the priorities of the draws executed.
+ *   gt_index (B,IR) int32 or NULL: source row in gt_boxes of each output row's matched gt (-1: none);
+ *   fg_count (B) int32 or NULL: foreground rows per image. */
 int sdet_proposal_target(const float* rois, const float* gt_boxes, float* rois_out, float* labels,
                          float* bbox_targets, float* bbox_weights, float* match_gt_ious, int* kept,
                          int B, int R, int G, int num_classes, int image_rois, float fg_fraction,
@@ -215,7 +217,22 @@ int sdet_proposal_target(const float* rois, const float* gt_boxes, float* rois_o
                          int proposal_without_gt, int class_agnostic, const float* bbox_mean,
                          const float* bbox_std, const float* bbox_weight, unsigned long long seed,
                          const uint32_t* priorities, int num_draws, uint32_t* priorities_used,
-                         void* stream);
+                         int* gt_index, int* fg_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ProposalMaskTarget  (operator_cxx/proposal_mask_target-inl.h:87-130 params, :139-337 Forward;
+ *                      operator_cxx/proposal_mask_target.cc:155-213 convertPoly2Mask, :219-379
+ *                      SampleROIMask) = sdet_proposal_target(..., gt_index, fg_count) followed by
+ *   sdet_poly_mask_target: for image b and output row i < min(fg_count[b], num_mask_rows) the
+ *   polygon gt_polys[b, gt_index[b,i]] ([category, n_seg, len_1..len_n, x,y,x,y,...], padded; see
+ *   models/maskrcnn/input.py:166-175) is rasterised into mask_target[b,i] (mask_size^2, values
+ *   0/1) in the roi-normalised frame; other rows are filled with -1 (ignored by
+ *   SigmoidCrossEntropy).  num_mask_rows = (int)(image_rois * fg_fraction).  gt_index / fg_count
+ *   are the optional outputs of sdet_proposal_target (int32, device).
+ *   Not built: output_ratio (MS-RCNN mask ratio), filter_scales / valid_ranges (num_args = 4). */
+int sdet_poly_mask_target(const float* rois_out, const float* gt_polys, const int* gt_index,
+                          const int* fg_count, float* mask_target, int B, int image_rois, int G,
+                          int poly_len, int num_mask_rows, int mask_size, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * _contrib_FocalLoss  (operator_cxx/contrib/focal_loss-inl.h:52-79 params, :90-114 forward =

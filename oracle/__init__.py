@@ -263,7 +263,8 @@ def ref_cython():
 # ---------------------------------------------------------------------------------------------
 def proposal_target(rois, gt_boxes, priorities, num_classes, image_rois, fg_fraction=0.25, fg_thresh=0.5,
                     bg_thresh_hi=0.5, bg_thresh_lo=0.0, proposal_without_gt=False, class_agnostic=False,
-                    bbox_mean=(0, 0, 0, 0), bbox_std=(0.1, 0.1, 0.2, 0.2), bbox_weight=(1, 1, 1, 1)):
+                    bbox_mean=(0, 0, 0, 0), bbox_std=(0.1, 0.1, 0.2, 0.2), bbox_weight=(1, 1, 1, 1),
+                    return_match=False):
     """ProposalTarget with injected shuffle priorities (B, D>=3, R+G) uint32.
     -> rois (B,IR,4), label (B,IR), bbox_target (B,IR,NC*4), bbox_weight (B,IR,NC*4),
        match_gt_iou (B,IR), kept (B,IR) int32."""
@@ -279,14 +280,43 @@ def proposal_target(rois, gt_boxes, priorities, num_classes, image_rois, fg_frac
     o_wgt = np.empty((B, IR, NC4), np.float32)
     o_iou = np.empty((B, IR), np.float32)
     kept = np.empty((B, IR), np.int32)
+    gt_index = np.empty((B, IR), np.int32)
+    fg_count = np.empty((B,), np.int32)
     m, s, w = _f32(bbox_mean), _f32(bbox_std), _f32(bbox_weight)
     lib().oracle_proposal_target(_p(rois), _p(gt_boxes), B, R, G, int(num_classes), int(image_rois),
                                  ctypes.c_float(fg_fraction), ctypes.c_float(fg_thresh),
                                  ctypes.c_float(bg_thresh_hi), ctypes.c_float(bg_thresh_lo),
                                  int(bool(proposal_without_gt)), int(bool(class_agnostic)), _p(m), _p(s), _p(w),
                                  _p(pr), pr.shape[1], _p(o_rois), _p(o_lab), _p(o_tgt), _p(o_wgt), _p(o_iou),
-                                 _p(kept))
+                                 _p(kept), _p(gt_index), _p(fg_count))
+    if return_match:
+        return o_rois, o_lab, o_tgt, o_wgt, o_iou, kept, gt_index, fg_count
     return o_rois, o_lab, o_tgt, o_wgt, o_iou, kept
+
+
+def poly2mask(roi, poly, mask_size):
+    """convertPoly2Mask (proposal_mask_target.cc:155-213) -> (M,M) float32 of 0/1."""
+    roi, poly = _f32(roi), _f32(poly)
+    out = np.empty(mask_size * mask_size, np.float32)
+    lib().oracle_poly2mask(_p(roi), _p(poly), int(mask_size), _p(out))
+    return out.reshape(mask_size, mask_size)
+
+
+def proposal_mask_target(rois, gt_boxes, gt_polys, priorities, num_classes, image_rois, mask_size,
+                         fg_fraction=0.25, **kw):
+    """ProposalMaskTarget (proposal_mask_target-inl.h:139-337, proposal_mask_target.cc:219-379) =
+    ProposalTarget + masks of the first fg rows; mask_target (B, int(IR*fg_fraction), M, M) is
+    pre-filled with -1 (-inl.h:242-243)."""
+    r = proposal_target(rois, gt_boxes, priorities, num_classes, image_rois, fg_fraction, return_match=True, **kw)
+    o_rois, gt_index, fg_count = r[0], r[6], r[7]
+    gt_polys = _f32(gt_polys)
+    B = o_rois.shape[0]
+    nm = int(image_rois * fg_fraction)
+    mask = np.full((B, nm, mask_size, mask_size), -1, np.float32)
+    for b in range(B):
+        for i in range(min(int(fg_count[b]), nm)):
+            mask[b, i] = poly2mask(o_rois[b, i], gt_polys[b, gt_index[b, i]], mask_size)
+    return r[:5] + (mask,)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -50,7 +50,7 @@ void oracle_proposal_target(const float* rois, const float* gt_boxes, int B, int
                             int class_agnostic, const float* bbox_mean, const float* bbox_std,
                             const float* bbox_weight, const uint32_t* priorities, int D,
                             float* rois_out, float* labels, float* bbox_targets, float* bbox_weights,
-                            float* match_gt_ious, int* dbg_kept) {
+                            float* match_gt_ious, int* dbg_kept, int* gt_index, int* fg_count) {
   const int NC4 = num_classes * 4, T = R + G;
   memset(rois_out, 0, sizeof(float) * (size_t)B * image_rois * 4);
   memset(labels, 0, sizeof(float) * (size_t)B * image_rois);
@@ -60,6 +60,7 @@ void oracle_proposal_target(const float* rois, const float* gt_boxes, int B, int
   const int fg_rois_per_image = (int)(image_rois * fg_fraction); /* -inl.h:194 truncation */
   float* all = (float*)malloc(sizeof(float) * 4 * (size_t)T);
   float* gts = (float*)malloc(sizeof(float) * 5 * (size_t)(G > 0 ? G : 1));
+  int* gsrc = (int*)malloc(sizeof(int) * (size_t)(G > 0 ? G : 1));
   float* maxov = (float*)malloc(sizeof(float) * (size_t)T);
   float* lab = (float*)malloc(sizeof(float) * (size_t)T);
   int* assign = (int*)malloc(sizeof(int) * (size_t)T);
@@ -69,7 +70,7 @@ void oracle_proposal_target(const float* rois, const float* gt_boxes, int B, int
     const uint32_t* prio = priorities + (size_t)b * D * T;
     int ng = 0, n = 0;
     for (int j = 0; j < G; ++j) /* -inl.h:155-161: padding gt has cls == -1 */
-      if (gt_boxes[((size_t)b * G + j) * 5 + 4] != -1.f) memcpy(gts + 5 * ng++, gt_boxes + ((size_t)b * G + j) * 5, 20);
+      if (gt_boxes[((size_t)b * G + j) * 5 + 4] != -1.f) { gsrc[ng] = j; memcpy(gts + 5 * ng++, gt_boxes + ((size_t)b * G + j) * 5, 20); }
     for (int j = 0; j < R; ++j) /* :171-176: y2 == 0 indicates padding */
       if (rois[((size_t)b * R + j) * 4 + 3] > 0) memcpy(all + 4 * n++, rois + ((size_t)b * R + j) * 4, 16);
     if (!proposal_without_gt) /* :177-185: all valid gt boxes appended after the rois */
@@ -107,9 +108,11 @@ void oracle_proposal_target(const float* rois, const float* gt_boxes, int B, int
       shuffle_by_priority(neg, nneg, prio + (size_t)(2 + r % (D - 2)) * T);
       for (int i = 0; i < gap && i < nneg; ++i) kept[nk++] = neg[i];
     }
+    if (fg_count) fg_count[b] = fg_n;
     for (int i = 0; i < image_rois; ++i) {
       size_t row = (size_t)b * image_rois + i;
       if (dbg_kept) dbg_kept[row] = i < nk ? kept[i] : -1;
+      if (gt_index) gt_index[row] = (i < nk && ng > 0) ? gsrc[assign[kept[i]]] : -1;
       if (i >= nk) continue;
       const int k = kept[i];
       float label = i < fg_n ? lab[k] : 0.f; /* :128-131 */
@@ -133,5 +136,5 @@ void oracle_proposal_target(const float* rois, const float* gt_boxes, int B, int
       }
     }
   }
-  free(all); free(gts); free(maxov); free(lab); free(assign); free(fg); free(bg); free(neg); free(kept);
+  free(all); free(gts); free(gsrc); free(maxov); free(lab); free(assign); free(fg); free(bg); free(neg); free(kept);
 }

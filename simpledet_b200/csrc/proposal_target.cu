@@ -33,6 +33,8 @@ struct PTParams {
   float* wgt;             // (B,IR,NC4)
   float* iou;             // (B,IR)
   int* kept;              // (B,IR) or nullptr: index into the compacted roi list, -1 = empty row
+  int* gt_index;          // (B,IR) or nullptr: source row (0..G-1) of the matched gt box, -1 = none
+  int* fg_count;          // (B) or nullptr: number of foreground rows (labels may be > 0 only there)
   int B, R, G, NC4, IR, D, fg_per_image;
   float fg_thresh, bg_hi, bg_lo;
   int without_gt, agnostic;
@@ -120,6 +122,7 @@ proposal_target_kernel(const __grid_constant__ PTParams p) {
   int* s_neg = s_bg + T;                                                      // T
   int* s_kept = s_neg + T;                                                    // IR + T
   uint32_t* s_prio = reinterpret_cast<uint32_t*>(s_kept + IR + T);            // T (current draw)
+  int* s_gsrc = reinterpret_cast<int*>(s_prio + T);                           // G source rows of valid gt
   __shared__ int s_warp[33];
   __shared__ int s_total;
 
@@ -129,6 +132,7 @@ proposal_target_kernel(const __grid_constant__ PTParams p) {
   // ---- valid gt (cls != -1, -inl.h:158) and valid rois (y2 > 0, :174), gt appended (:177-185)
   const int ng = block_compact(G, [&](int j) { return gt[j * 5 + 4] != -1.f; }, s_src, s_warp, &s_total);
   for (int e = tid; e < ng * 5; e += blockDim.x) s_gt[e] = gt[s_src[e / 5] * 5 + e % 5];
+  for (int j = tid; j < ng; j += blockDim.x) s_gsrc[j] = s_src[j];
   __syncthreads();
   const int nr = block_compact(R, [&](int j) { return rois[j * 4 + 3] > 0.f; }, s_src, s_warp, &s_total);
   for (int i = tid; i < nr; i += blockDim.x) {
@@ -269,13 +273,154 @@ proposal_target_kernel(const __grid_constant__ PTParams p) {
     p.labels[row] = label;
     p.iou[row] = ov;
     if (p.kept) p.kept[row] = k;
+    if (p.gt_index) p.gt_index[row] = (k >= 0 && ng > 0) ? s_gsrc[s_assign[k]] : -1;
   }
+  if (p.fg_count && tid == 0) p.fg_count[b] = fg_n;
+}
+
+// --------------------------------------------------------------------------------------------
+// ProposalMaskTarget's rasteriser: convertPoly2Mask (operator_cxx/proposal_mask_target.cc:155-213)
+// on top of cocoapi's rleFrPoly / rleDecode (RogerChern/cocoapi common/maskApi.c — not vendored
+// in the reference, restated from the published algorithm; parity unpinned).
+//
+// One CTA per (image, foreground row).  rleFrPoly is: upsample x5, walk every edge with integer
+// DDA, keep the points where the (upsampled) column changes, snap them to pixel-column boundaries
+// and SORT them; the mask is the run-length decode of the sorted positions.  The decode of sorted
+// toggle positions is "pixel p is set iff an odd number of positions are <= p", so no sort is needed:
+// every edge thread toggles a per-position counter in shared memory and a parity prefix scan over
+// the M*M + 1 positions produces the mask.  All coordinate arithmetic is the reference's
+// float -> double -> int sequence with explicit rounding (no contraction).
+// --------------------------------------------------------------------------------------------
+struct MaskParams {
+  const float* rois_out;   // (B,IR,4)
+  const float* gt_polys;   // (B,G,PL)
+  const int* gt_index;     // (B,IR)
+  const int* fg_count;     // (B)
+  float* mask;             // (B,NM,M,M)
+  int IR, G, PL, NM, M;
+};
+
+__device__ __forceinline__ void dda_point(int xs, int ys, int dx, int dy, double sl, bool flip, int d, int& u,
+                                          int& v) {
+  // maskApi.c rleFrPoly: t = flip ? (len - d) : d; major axis advances by t, minor = (int)(start + s*t + .5)
+  if (dx >= dy) {
+    const int t = flip ? dx - d : d;
+    u = t + xs;
+    v = (int)__dadd_rn(__dadd_rn((double)ys, __dmul_rn(sl, (double)t)), .5);
+  } else {
+    const int t = flip ? dy - d : d;
+    v = t + ys;
+    u = (int)__dadd_rn(__dadd_rn((double)xs, __dmul_rn(sl, (double)t)), .5);
+  }
+}
+
+__global__ void __launch_bounds__(256) poly_mask_kernel(const MaskParams p) {
+  extern __shared__ int s_tog[];  // M*M + 2 toggle counters, then the OR-accumulated mask (M*M bytes as ints)
+  const int row = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int M = p.M, MM = M * M;
+  float* out = p.mask + ((size_t)b * p.NM + row) * MM;
+  const int nfg = min(p.fg_count[b], p.NM);
+  if (row >= nfg) {  // rows beyond the foreground count keep the ignore value (-inl.h:242-243)
+    for (int j = tid; j < MM; j += blockDim.x) out[j] = -1.f;
+    return;
+  }
+  int* s_acc = s_tog + MM + 2;
+  const float* roi = p.rois_out + ((size_t)b * p.IR + row) * 4;
+  const int gi = p.gt_index[(size_t)b * p.IR + row];
+  for (int j = tid; j < MM; j += blockDim.x) s_acc[j] = 0;
+  __syncthreads();
+  if (gi >= 0) {
+    const float* poly = p.gt_polys + ((size_t)b * p.G + gi) * p.PL;
+    float w = __fsub_rn(roi[2], roi[0]), h = __fsub_rn(roi[3], roi[1]);
+    w = 1.f > w ? 1.f : w;
+    h = 1.f > h ? 1.f : h;
+    const int n_seg = (int)poly[1];
+    int offset = 2 + n_seg;
+    for (int sg = 0; sg < n_seg; ++sg) {
+      const int cur_len = (int)poly[sg + 2];
+      const int k = cur_len / 2;
+      for (int j = tid; j < MM + 2; j += blockDim.x) s_tog[j] = 0;
+      __syncthreads();
+      // vertex j in upsampled integer coordinates; note the (y', x') order of :182-187
+      auto vert = [&](int j, int& X, int& Y) {
+        j = (j == k) ? 0 : j;
+        const double a = (double)__fdiv_rn(__fmul_rn(__fsub_rn(poly[offset + 2 * j + 1], roi[1]), (float)M), h);
+        const double c = (double)__fdiv_rn(__fmul_rn(__fsub_rn(poly[offset + 2 * j], roi[0]), (float)M), w);
+        X = (int)__dadd_rn(__dmul_rn(5.0, a), .5);
+        Y = (int)__dadd_rn(__dmul_rn(5.0, c), .5);
+      };
+      for (int e = tid; e < k; e += blockDim.x) {  // one edge per thread
+        int xs, ys, xe, ye;
+        vert(e, xs, ys);
+        vert(e + 1, xe, ye);
+        int dx = abs(xe - xs), dy = abs(ys - ye);
+        const bool flip = (dx >= dy && xs > xe) || (dx < dy && ys > ye);
+        if (flip) {
+          int t = xs; xs = xe; xe = t;
+          t = ys; ys = ye; ye = t;
+        }
+        const double sl = dx >= dy ? __ddiv_rn((double)(ye - ys), (double)dx) : __ddiv_rn((double)(xe - xs), (double)dy);
+        const int npts = max(dx, dy) + 1;
+        // previous point of the concatenated point list: the last point of the previous edge
+        int pu = 0, pv = 0;
+        bool have_prev = false;
+        if (e > 0) {
+          int axs, ays, axe, aye;
+          vert(e - 1, axs, ays);
+          vert(e, axe, aye);
+          int adx = abs(axe - axs), ady = abs(ays - aye);
+          const bool af = (adx >= ady && axs > axe) || (adx < ady && ays > aye);
+          if (af) {
+            int t = axs; axs = axe; axe = t;
+            t = ays; ays = aye; aye = t;
+          }
+          const double asl = adx >= ady ? __ddiv_rn((double)(aye - ays), (double)adx)
+                                        : __ddiv_rn((double)(axe - axs), (double)ady);
+          dda_point(axs, ays, adx, ady, asl, af, max(adx, ady), pu, pv);
+          have_prev = true;
+        }
+        for (int d = 0; d < npts; ++d) {
+          int u, v;
+          dda_point(xs, ys, dx, dy, sl, flip, d, u, v);
+          if (have_prev && u != pu) {
+            double xd = (double)(u < pu ? u : u - 1);
+            xd = __dsub_rn(__ddiv_rn(__dadd_rn(xd, .5), 5.0), .5);
+            if (!(floor(xd) != xd || xd < 0 || xd > (double)(M - 1))) {
+              double yd = (double)(v < pv ? v : pv);
+              yd = __dsub_rn(__ddiv_rn(__dadd_rn(yd, .5), 5.0), .5);
+              if (yd < 0) yd = 0;
+              else if (yd > (double)M) yd = (double)M;
+              yd = ceil(yd);
+              const int pos = (int)xd * M + (int)yd;  // <= M*M
+              atomicAdd(&s_tog[min(pos, MM)], 1);
+            }
+          }
+          pu = u;
+          pv = v;
+          have_prev = true;
+        }
+      }
+      __syncthreads();
+      // parity prefix over positions (serial per 32-position chunk, chunks combined by thread 0)
+      if (tid == 0) {
+        int par = 0;
+        for (int j = 0; j < MM; ++j) {
+          par ^= (s_tog[j] & 1);
+          if (par) s_acc[j] = 1;
+        }
+      }
+      __syncthreads();
+      offset += cur_len;
+    }
+  }
+  for (int j = tid; j < MM; j += blockDim.x) out[j] = s_acc[j] ? 1.f : 0.f;
 }
 
 size_t pt_smem_bytes(int T, int G, int IR) {
   int np2 = 1;
   while (np2 < T) np2 <<= 1;
-  return (size_t)np2 * 8 + (size_t)T * 16 + (size_t)G * 5 * 4 + (size_t)T * 4 * 7 + (size_t)(IR + T) * 4 + 64;
+  return (size_t)np2 * 8 + (size_t)T * 16 + (size_t)G * 5 * 4 + (size_t)T * 4 * 7 + (size_t)(IR + T) * 4 +
+         (size_t)G * 4 + 64;
 }
 
 }  // namespace
@@ -287,7 +432,7 @@ extern "C" int sdet_proposal_target(const float* rois, const float* gt_boxes, fl
                                     float bg_thresh_lo, int proposal_without_gt, int class_agnostic,
                                     const float* bbox_mean, const float* bbox_std, const float* bbox_weight,
                                     unsigned long long seed, const uint32_t* priorities, int num_draws,
-                                    uint32_t* priorities_used, void* stream) {
+                                    uint32_t* priorities_used, int* gt_index, int* fg_count, void* stream) {
   SDET_REQUIRE(rois && gt_boxes && rois_out && labels && bbox_targets && bbox_weights && match_gt_ious &&
                bbox_mean && bbox_std && bbox_weight, "NULL argument");
   SDET_REQUIRE(B > 0 && R > 0 && G >= 0 && num_classes > 0 && image_rois > 0, "bad shape");
@@ -296,7 +441,7 @@ extern "C" int sdet_proposal_target(const float* rois, const float* gt_boxes, fl
   PTParams p{};
   p.rois = rois; p.gt = gt_boxes; p.prio = priorities; p.prio_used = priorities_used;
   p.rois_out = rois_out; p.labels = labels; p.tgt = bbox_targets; p.wgt = bbox_weights;
-  p.iou = match_gt_ious; p.kept = kept;
+  p.iou = match_gt_ious; p.kept = kept; p.gt_index = gt_index; p.fg_count = fg_count;
   p.B = B; p.R = R; p.G = G; p.NC4 = num_classes * 4; p.IR = image_rois; p.D = num_draws;
   p.fg_per_image = (int)(image_rois * fg_fraction);  // index_t truncation, proposal_target-inl.h:194
   p.fg_thresh = fg_thresh; p.bg_hi = bg_thresh_hi; p.bg_lo = bg_thresh_lo;
@@ -317,5 +462,25 @@ extern "C" int sdet_proposal_target(const float* rois, const float* gt_boxes, fl
   }
   proposal_target_kernel<<<(unsigned)B, kThreads, smem, (cudaStream_t)stream>>>(p);
   SDET_LAUNCH_CHECK("proposal_target_kernel");
+  return SDET_OK;
+}
+
+extern "C" int sdet_poly_mask_target(const float* rois_out, const float* gt_polys, const int* gt_index,
+                                     const int* fg_count, float* mask_target, int B, int image_rois, int G,
+                                     int poly_len, int num_mask_rows, int mask_size, void* stream) {
+  SDET_REQUIRE(rois_out && gt_polys && gt_index && fg_count && mask_target, "NULL argument");
+  SDET_REQUIRE(B > 0 && image_rois > 0 && G > 0 && poly_len > 2 && num_mask_rows > 0 && mask_size > 0, "bad shape");
+  SDET_REQUIRE(num_mask_rows <= image_rois, "mask rows exceed image_rois");
+  if (mask_size > 112) return sdet::fail(SDET_ERR_UNSUPPORTED, "mask_size > 112");
+  MaskParams p{rois_out, gt_polys, gt_index, fg_count, mask_target, image_rois, G, poly_len, num_mask_rows, mask_size};
+  const size_t smem = sizeof(int) * (size_t)(2 * mask_size * mask_size + 2);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SDET_CUDA(cudaFuncSetAttribute(poly_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid((unsigned)num_mask_rows, (unsigned)B);
+  poly_mask_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  SDET_LAUNCH_CHECK("poly_mask_kernel");
   return SDET_OK;
 }

@@ -22,7 +22,7 @@ __all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_r
            "fpn_roi_align", "fpn_roi_align_raw", "DecodeBBox", "Proposal_v3", "Proposal_v3_fpn", "NMS", "nms_sorted", "get_top_proposal",
            "multiclass_nms", "ProposalTarget", "FocalLoss", "BBoxNorm",
            "SigmoidCrossEntropy", "soft_nms", "soft_nms_batched",
-           "cython_soft_nms_wrapper", "DeformableConvolution", "OPS"]
+           "cython_soft_nms_wrapper", "DeformableConvolution", "ProposalMaskTarget", "OPS"]
 
 
 def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor | None:
@@ -400,7 +400,7 @@ def ProposalTarget(rois, gt_boxes, num_classes, batch_images, image_rois, fg_thr
                    bg_thresh_lo, proposal_without_gt, fg_fraction=0.25, class_agnostic=False,
                    output_iou=False, bbox_mean=(0.0, 0.0, 0.0, 0.0), bbox_std=(0.1, 0.1, 0.2, 0.2),
                    bbox_weight=(1.0, 1.0, 1.0, 1.0), seed=None, priorities=None, num_draws=8,
-                   return_debug=False):
+                   return_debug=False, _match_out=None):
     """mx.sym.ProposalTarget.  rois (B,R,4), gt_boxes (B,G,5) -> rois (B,IR,4), label (B,IR),
     bbox_target (B,IR,4*num_classes), bbox_weight (same) [, match_gt_iou (B,IR) if output_iou].
     `seed` (int) keys the on-device Philox sampling (default: a per-process call counter);
@@ -438,7 +438,8 @@ def ProposalTarget(rois, gt_boxes, num_classes, batch_images, image_rois, fg_thr
         int(num_classes), IR, float(fg_fraction), float(fg_thresh), float(bg_thresh_hi), float(bg_thresh_lo),
         int(bool(proposal_without_gt)), int(bool(class_agnostic)), _f4(bbox_mean, "bbox_mean"),
         _f4(bbox_std, "bbox_std"), _f4(bbox_weight, "bbox_weight"), int(seed) & (2 ** 64 - 1), _p(priorities),
-        int(num_draws), _p(used), _stream()))
+        int(num_draws), _p(used), _p(_match_out[0]) if _match_out else None,
+        _p(_match_out[1]) if _match_out else None, _stream()))
     outs = [o_rois, o_lab, o_tgt, o_wgt]
     if output_iou:
         outs.append(o_iou)
@@ -539,6 +540,35 @@ def SigmoidCrossEntropy(data, label, grad_scale=1.0):
     if data.dim() != 2 or data.shape != label.shape:
         raise ValueError("data and label must both be (R,D)")
     return _SigmoidCEFn.apply(data, label, float(grad_scale))
+
+
+def ProposalMaskTarget(rois, gt_boxes, gt_polys, num_classes, batch_images, image_rois, mask_size, fg_thresh,
+                       bg_thresh_hi, bg_thresh_lo, proposal_without_gt, fg_fraction=0.25, class_agnostic=False,
+                       output_iou=False, output_ratio=False, filter_scales=False, num_args=3,
+                       bbox_mean=(0.0, 0.0, 0.0, 0.0), bbox_std=(0.1, 0.1, 0.2, 0.2),
+                       bbox_weight=(1.0, 1.0, 1.0, 1.0), seed=None, priorities=None):
+    """mx.sym.ProposalMaskTarget (models/maskrcnn/builder.py:184-203): ProposalTarget's outputs +
+    mask_target (B, int(image_rois*fg_fraction), M, M) with -1 = ignore."""
+    if output_ratio or filter_scales or num_args != 3:
+        raise NotImplementedError("output_ratio / filter_scales / valid_ranges are not built yet")
+    gt_polys = _dev(gt_polys, "gt_polys")
+    B = int(batch_images)
+    IR = int(image_rois)
+    G = gt_boxes.numel() // (B * 5)
+    PL = gt_polys.numel() // (B * G)
+    dev = rois.device
+    gt_index = torch.empty((B, IR), device=dev, dtype=torch.int32)
+    fg_count = torch.empty((B,), device=dev, dtype=torch.int32)
+    outs = ProposalTarget(rois, gt_boxes, num_classes, B, IR, fg_thresh, bg_thresh_hi, bg_thresh_lo,
+                          proposal_without_gt, fg_fraction=fg_fraction, class_agnostic=class_agnostic,
+                          output_iou=output_iou, bbox_mean=bbox_mean, bbox_std=bbox_std, bbox_weight=bbox_weight,
+                          seed=seed, priorities=priorities, _match_out=(gt_index, fg_count))
+    NM = int(IR * fg_fraction)
+    M = int(mask_size)
+    mask = torch.empty((B, NM, M, M), device=dev, dtype=torch.float32)
+    check(_lib.lib().sdet_poly_mask_target(_p(outs[0]), _p(gt_polys), _p(gt_index), _p(fg_count), _p(mask), B, IR, G,
+                                           PL, NM, M, _stream()))
+    return tuple(outs) + (mask,)
 
 
 # --------------------------------------------------------------------------------------------
@@ -693,6 +723,7 @@ OPS = {
     "_contrib_Proposal_v3": Proposal_v3,
     "_contrib_NMS": NMS,
     "ProposalTarget": ProposalTarget,
+    "ProposalMaskTarget": ProposalMaskTarget,
     "_contrib_DeformableConvolution": DeformableConvolution,
     "_contrib_FocalLoss": FocalLoss,
     "_contrib_BBoxNorm": BBoxNorm,

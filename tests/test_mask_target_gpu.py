@@ -1,0 +1,78 @@
+"""ProposalMaskTarget: device rasteriser vs the oracle restatement of cocoapi's rleFrPoly +
+convertPoly2Mask (parity unpinned: maskApi.c is not vendored in the reference).  Masks are integer
+(0/1/-1) outputs: compared exactly, with the same injected shuffle priorities on both sides."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from simpledet_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _scene(rng, B, R, G, PL):
+    gt = np.full((B, G, 5), -1, np.float32)
+    polys = np.full((B, G, PL), -1, np.float32)
+    rois = np.zeros((B, R, 4), np.float32)
+    for b in range(B):
+        k = int(rng.integers(2, G))
+        for j in range(k):
+            x1, y1 = rng.uniform(0, 500, 2)
+            w, h = rng.uniform(40, 300, 2)
+            gt[b, j] = [x1, y1, x1 + w, y1 + h, rng.integers(1, 81)]
+            nseg = int(rng.integers(1, 4))
+            row, coords = [float(gt[b, j, 4]), float(nseg)], []
+            for _ in range(nseg):
+                nv = int(rng.integers(3, 30))
+                ang = np.sort(rng.uniform(0, 2 * np.pi, nv))
+                rad = rng.uniform(0.15, 0.5, nv)
+                cx, cy = x1 + w * rng.uniform(0.3, 0.7), y1 + h * rng.uniform(0.3, 0.7)
+                xs, ys = cx + w * rad * np.cos(ang), cy + h * rad * np.sin(ang)
+                row.append(float(2 * nv))
+                coords += np.stack([xs, ys], 1).reshape(-1).tolist()
+            row += coords
+            polys[b, j, :len(row)] = row
+        m = R - 20
+        near = gt[b, rng.integers(0, k, m), :4] + rng.normal(0, 12, (m, 4))
+        near[:, 3] = np.maximum(near[:, 3], 1)
+        rois[b, :m] = near
+    return rois, gt, polys
+
+
+@pytest.mark.parametrize("M", [14, 28])
+def test_mask_target_exact(cuda, M):
+    rng = np.random.default_rng(M)
+    B, R, G, PL, IR = 2, 400, 12, 2500, 128
+    rois, gt, polys = _scene(rng, B, R, G, PL)
+    pr = rng.integers(0, 2 ** 32, (B, 4, R + G), dtype=np.uint64).astype(np.uint32)
+    ref = oracle.proposal_mask_target(rois, gt, polys, pr, 81, IR, M, fg_fraction=0.25, fg_thresh=0.5,
+                                      bg_thresh_hi=0.5, bg_thresh_lo=0.0)
+    res = ops.ProposalMaskTarget(_t(rois, cuda), _t(gt, cuda), _t(polys, cuda), 81, B, IR, M, 0.5, 0.5, 0.0, False,
+                                 priorities=_t(pr.astype(np.int64), cuda))
+    assert len(res) == 5 and res[4].shape == (B, 32, M, M)
+    assert np.array_equal(res[0].cpu().numpy(), ref[0]) and np.array_equal(res[1].cpu().numpy(), ref[1])
+    got, want = res[4].cpu().numpy(), ref[5]
+    assert set(np.unique(got)) <= {-1.0, 0.0, 1.0}
+    assert np.array_equal(got, want), f"{(got != want).sum()} mask pixels differ"
+    assert (want == 1).sum() > 100  # the scene really has masks
+
+
+def test_poly2mask_shapes(cuda):
+    """Known shapes through the op: an axis-aligned half box and a triangle."""
+    rois = np.zeros((1, 8, 4), np.float32)
+    rois[0, 0] = [10, 20, 110, 120]
+    gt = np.full((1, 2, 5), -1, np.float32)
+    gt[0, 0] = [10, 20, 110, 120, 5]
+    polys = np.full((1, 2, 40), -1, np.float32)
+    polys[0, 0, :11] = [5, 1, 8, 10, 20, 60, 20, 60, 120, 10, 120, ][:11]
+    pr = np.zeros((1, 3, 10), np.uint32)
+    res = ops.ProposalMaskTarget(_t(rois, cuda), _t(gt, cuda), _t(polys, cuda), 81, 1, 4, 28, 0.5, 0.5, 0.0, False,
+                                 priorities=_t(pr.astype(np.int64), cuda))
+    m = res[4].cpu().numpy()[0, 0]
+    want = oracle.poly2mask(rois[0, 0], polys[0, 0], 28)
+    assert np.array_equal(m, want) and m[:, :14].sum() == 28 * 14 and m[:, 14:].sum() == 0
