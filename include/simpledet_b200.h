@@ -219,6 +219,20 @@ int sdet_proposal_target(const float* rois, const float* gt_boxes, float* rois_o
                          const uint32_t* priorities, int num_draws, uint32_t* priorities_used,
                          int* gt_index, int* fg_count, void* stream);
 
+/* ProposalTarget_v2  (operator_cxx/proposal_target_v2-inl.h:145-270, proposal_target_v2.cc:22-175;
+ * used by TridentNet, models/tridentnet/builder.py:281): ProposalTarget plus
+ *   valid_ranges (B,2) device + filter_scales: gt boxes whose area is outside [min^2, max^2] are
+ *   not appended to the proposals (they still take part in the IoU matching);
+ *   image_rois == -1: every foreground roi is kept and each image yields R output rows. */
+int sdet_proposal_target_v2(const float* rois, const float* gt_boxes, const float* valid_ranges,
+                            float* rois_out, float* labels, float* bbox_targets, float* bbox_weights,
+                            float* match_gt_ious, int* kept, int B, int R, int G, int num_classes,
+                            int image_rois, float fg_fraction, float fg_thresh, float bg_thresh_hi,
+                            float bg_thresh_lo, int proposal_without_gt, int class_agnostic,
+                            int filter_scales, const float* bbox_mean, const float* bbox_std,
+                            const float* bbox_weight, unsigned long long seed, const uint32_t* priorities,
+                            int num_draws, uint32_t* priorities_used, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * ProposalMaskTarget  (operator_cxx/proposal_mask_target-inl.h:87-130 params, :139-337 Forward;
  *                      operator_cxx/proposal_mask_target.cc:155-213 convertPoly2Mask, :219-379

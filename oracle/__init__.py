@@ -264,7 +264,7 @@ def ref_cython():
 def proposal_target(rois, gt_boxes, priorities, num_classes, image_rois, fg_fraction=0.25, fg_thresh=0.5,
                     bg_thresh_hi=0.5, bg_thresh_lo=0.0, proposal_without_gt=False, class_agnostic=False,
                     bbox_mean=(0, 0, 0, 0), bbox_std=(0.1, 0.1, 0.2, 0.2), bbox_weight=(1, 1, 1, 1),
-                    return_match=False):
+                    return_match=False, valid_ranges=None, filter_scales=False):
     """ProposalTarget with injected shuffle priorities (B, D>=3, R+G) uint32.
     -> rois (B,IR,4), label (B,IR), bbox_target (B,IR,NC*4), bbox_weight (B,IR,NC*4),
        match_gt_iou (B,IR), kept (B,IR) int32."""
@@ -273,6 +273,10 @@ def proposal_target(rois, gt_boxes, priorities, num_classes, image_rois, fg_frac
     G = gt_boxes.shape[1]
     pr = np.ascontiguousarray(priorities, dtype=np.uint32)
     assert pr.shape[0] == B and pr.shape[2] == R + G and pr.shape[1] >= 3
+    no_cap = image_rois == -1  # ProposalTarget_v2: keep every fg roi, R rows per image
+    if no_cap:
+        image_rois = R
+    vr = _f32(valid_ranges) if valid_ranges is not None else None
     IR, NC4 = image_rois, num_classes * 4
     o_rois = np.empty((B, IR, 4), np.float32)
     o_lab = np.empty((B, IR), np.float32)
@@ -288,7 +292,8 @@ def proposal_target(rois, gt_boxes, priorities, num_classes, image_rois, fg_frac
                                  ctypes.c_float(bg_thresh_hi), ctypes.c_float(bg_thresh_lo),
                                  int(bool(proposal_without_gt)), int(bool(class_agnostic)), _p(m), _p(s), _p(w),
                                  _p(pr), pr.shape[1], _p(o_rois), _p(o_lab), _p(o_tgt), _p(o_wgt), _p(o_iou),
-                                 _p(kept), _p(gt_index), _p(fg_count))
+                                 _p(kept), _p(gt_index), _p(fg_count), _p(vr), int(bool(filter_scales)),
+                                 int(no_cap))
     if return_match:
         return o_rois, o_lab, o_tgt, o_wgt, o_iou, kept, gt_index, fg_count
     return o_rois, o_lab, o_tgt, o_wgt, o_iou, kept

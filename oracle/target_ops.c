@@ -50,7 +50,12 @@ void oracle_proposal_target(const float* rois, const float* gt_boxes, int B, int
                             int class_agnostic, const float* bbox_mean, const float* bbox_std,
                             const float* bbox_weight, const uint32_t* priorities, int D,
                             float* rois_out, float* labels, float* bbox_targets, float* bbox_weights,
-                            float* match_gt_ious, int* dbg_kept, int* gt_index, int* fg_count) {
+                            float* match_gt_ious, int* dbg_kept, int* gt_index, int* fg_count,
+                            const float* valid_ranges, int filter_scales, int no_fg_cap) {
+  /* ProposalTarget_v2 deltas (proposal_target_v2-inl.h:145-270, proposal_target_v2.cc:80-85):
+   * valid_ranges (B,2) + filter_scales: gt boxes whose area lies outside [min^2, max^2] are not
+   * APPENDED to the rois (they still take part in the IoU); no_fg_cap (image_rois == -1): keep
+   * every foreground roi, rows per image = R. */
   const int NC4 = num_classes * 4, T = R + G;
   memset(rois_out, 0, sizeof(float) * (size_t)B * image_rois * 4);
   memset(labels, 0, sizeof(float) * (size_t)B * image_rois);
@@ -74,7 +79,15 @@ void oracle_proposal_target(const float* rois, const float* gt_boxes, int B, int
     for (int j = 0; j < R; ++j) /* :171-176: y2 == 0 indicates padding */
       if (rois[((size_t)b * R + j) * 4 + 3] > 0) memcpy(all + 4 * n++, rois + ((size_t)b * R + j) * 4, 16);
     if (!proposal_without_gt) /* :177-185: all valid gt boxes appended after the rois */
-      for (int j = 0; j < ng; ++j) memcpy(all + 4 * n++, gts + 5 * j, 16);
+      for (int j = 0; j < ng; ++j) {
+        if (filter_scales && valid_ranges) { /* v2-inl.h:191-200 */
+          float vmin = valid_ranges[b * 2] * valid_ranges[b * 2], vmax = valid_ranges[b * 2 + 1] * valid_ranges[b * 2 + 1];
+          float gw = (float)((double)(gts[5 * j + 2] - gts[5 * j + 0]) + 1.0);
+          float gh = (float)((double)(gts[5 * j + 3] - gts[5 * j + 1]) + 1.0);
+          if (gw * gh < vmin || gw * gh > vmax) continue;
+        }
+        memcpy(all + 4 * n++, gts + 5 * j, 16);
+      }
     /* BBoxOverlap (proposal_target.cc:165-185) + row argmax with strict '<' (:51-63) */
     for (int i = 0; i < n; ++i) {
       const float* bx = all + 4 * i;
@@ -96,7 +109,7 @@ void oracle_proposal_target(const float* rois, const float* gt_boxes, int B, int
     }
     int nfg = 0, nbg = 0, nneg = 0, nk = 0;
     for (int i = 0; i < n; ++i) { if (maxov[i] >= fg_thresh) fg[nfg++] = i; else neg[nneg++] = i; }
-    int fg_n = fg_rois_per_image < nfg ? fg_rois_per_image : nfg;
+    int fg_n = no_fg_cap ? nfg : (fg_rois_per_image < nfg ? fg_rois_per_image : nfg);
     if (nfg > fg_n) shuffle_by_priority(fg, nfg, prio + 0 * (size_t)T); /* :81-85 */
     for (int i = 0; i < n; ++i) if (maxov[i] >= bg_thresh_lo && maxov[i] < bg_thresh_hi) bg[nbg++] = i;
     int bg_n = (image_rois - fg_n) < nbg ? (image_rois - fg_n) : nbg;

@@ -38,6 +38,8 @@ struct PTParams {
   int B, R, G, NC4, IR, D, fg_per_image;
   float fg_thresh, bg_hi, bg_lo;
   int without_gt, agnostic;
+  const float* valid_ranges;  // (B,2) or nullptr (ProposalTarget_v2)
+  int filter_scales, no_fg_cap;
   float mean[4], std[4], weight[4];
   unsigned long long seed;
 };
@@ -139,10 +141,28 @@ proposal_target_kernel(const __grid_constant__ PTParams p) {
     const float* r = rois + (size_t)s_src[i] * 4;
     s_box[i] = make_float4(r[0], r[1], r[2], r[3]);
   }
-  const int n = p.without_gt ? nr : nr + ng;
-  if (!p.without_gt)
-    for (int j = tid; j < ng; j += blockDim.x)
-      s_box[nr + j] = make_float4(s_gt[j * 5], s_gt[j * 5 + 1], s_gt[j * 5 + 2], s_gt[j * 5 + 3]);
+  int n = nr;
+  if (!p.without_gt) {
+    int napp = ng;
+    if (p.filter_scales && p.valid_ranges) {  // ProposalTarget_v2: only gt inside the valid scale range
+      const float v0 = p.valid_ranges[b * 2], v1 = p.valid_ranges[b * 2 + 1];
+      const float vmin = __fmul_rn(v0, v0), vmax = __fmul_rn(v1, v1);
+      napp = block_compact(ng, [&](int j) {
+        const float gw = (float)__dadd_rn((double)__fsub_rn(s_gt[j * 5 + 2], s_gt[j * 5 + 0]), 1.0);
+        const float gh = (float)__dadd_rn((double)__fsub_rn(s_gt[j * 5 + 3], s_gt[j * 5 + 1]), 1.0);
+        const float ar = __fmul_rn(gw, gh);
+        return !(ar < vmin || ar > vmax);
+      }, s_src, s_warp, &s_total);
+    } else {
+      for (int j = tid; j < ng; j += blockDim.x) s_src[j] = j;
+      __syncthreads();
+    }
+    for (int q = tid; q < napp; q += blockDim.x) {
+      const int j = s_src[q];
+      s_box[nr + q] = make_float4(s_gt[j * 5], s_gt[j * 5 + 1], s_gt[j * 5 + 2], s_gt[j * 5 + 3]);
+    }
+    n = nr + napp;
+  }
   __syncthreads();
 
   // ---- BBoxOverlap + first-max argmax (proposal_target.cc:165-185, :51-63)
@@ -198,7 +218,7 @@ proposal_target_kernel(const __grid_constant__ PTParams p) {
   const int nneg = block_compact(n, [&](int i) { return !(s_maxov[i] >= fg_thr); }, s_neg, s_warp, &s_total);
   const int nbg = block_compact(n, [&](int i) { return s_maxov[i] >= bg_lo && s_maxov[i] < bg_hi; }, s_bg,
                                 s_warp, &s_total);
-  const int fg_n = min(p.fg_per_image, nfg);
+  const int fg_n = p.no_fg_cap ? nfg : min(p.fg_per_image, nfg);
   // draws are always materialised in the same order: 0 fg, 1 bg, 2+ negative padding
   load_draw(0);
   if (nfg > fg_n) block_priority_sort(s_fg, nfg, s_prio, s_keys);  // :81-85
@@ -425,14 +445,17 @@ size_t pt_smem_bytes(int T, int G, int IR) {
 
 }  // namespace
 
-extern "C" int sdet_proposal_target(const float* rois, const float* gt_boxes, float* rois_out,
-                                    float* labels, float* bbox_targets, float* bbox_weights,
-                                    float* match_gt_ious, int* kept, int B, int R, int G, int num_classes,
-                                    int image_rois, float fg_fraction, float fg_thresh, float bg_thresh_hi,
-                                    float bg_thresh_lo, int proposal_without_gt, int class_agnostic,
-                                    const float* bbox_mean, const float* bbox_std, const float* bbox_weight,
-                                    unsigned long long seed, const uint32_t* priorities, int num_draws,
-                                    uint32_t* priorities_used, int* gt_index, int* fg_count, void* stream) {
+static int proposal_target_core(const float* rois, const float* gt_boxes, const float* valid_ranges,
+                                float* rois_out, float* labels, float* bbox_targets, float* bbox_weights,
+                                float* match_gt_ious, int* kept, int B, int R, int G, int num_classes,
+                                int image_rois, float fg_fraction, float fg_thresh, float bg_thresh_hi,
+                                float bg_thresh_lo, int proposal_without_gt, int class_agnostic,
+                                int filter_scales, const float* bbox_mean, const float* bbox_std,
+                                const float* bbox_weight, unsigned long long seed, const uint32_t* priorities,
+                                int num_draws, uint32_t* priorities_used, int* gt_index, int* fg_count,
+                                void* stream) {
+  const int no_fg_cap = (image_rois == -1);  // ProposalTarget_v2: keep all foreground rois, R rows
+  if (no_fg_cap) image_rois = R;
   SDET_REQUIRE(rois && gt_boxes && rois_out && labels && bbox_targets && bbox_weights && match_gt_ious &&
                bbox_mean && bbox_std && bbox_weight, "NULL argument");
   SDET_REQUIRE(B > 0 && R > 0 && G >= 0 && num_classes > 0 && image_rois > 0, "bad shape");
@@ -447,6 +470,9 @@ extern "C" int sdet_proposal_target(const float* rois, const float* gt_boxes, fl
   p.fg_thresh = fg_thresh; p.bg_hi = bg_thresh_hi; p.bg_lo = bg_thresh_lo;
   p.without_gt = proposal_without_gt ? 1 : 0;
   p.agnostic = class_agnostic ? 1 : 0;
+  p.valid_ranges = valid_ranges;
+  p.filter_scales = filter_scales ? 1 : 0;
+  p.no_fg_cap = no_fg_cap;
   for (int i = 0; i < 4; ++i) {
     p.mean[i] = bbox_mean[i];
     p.std[i] = bbox_std[i];
@@ -463,6 +489,40 @@ extern "C" int sdet_proposal_target(const float* rois, const float* gt_boxes, fl
   proposal_target_kernel<<<(unsigned)B, kThreads, smem, (cudaStream_t)stream>>>(p);
   SDET_LAUNCH_CHECK("proposal_target_kernel");
   return SDET_OK;
+}
+
+extern "C" int sdet_proposal_target(const float* rois, const float* gt_boxes, float* rois_out,
+                                    float* labels, float* bbox_targets, float* bbox_weights,
+                                    float* match_gt_ious, int* kept, int B, int R, int G, int num_classes,
+                                    int image_rois, float fg_fraction, float fg_thresh, float bg_thresh_hi,
+                                    float bg_thresh_lo, int proposal_without_gt, int class_agnostic,
+                                    const float* bbox_mean, const float* bbox_std, const float* bbox_weight,
+                                    unsigned long long seed, const uint32_t* priorities, int num_draws,
+                                    uint32_t* priorities_used, int* gt_index, int* fg_count, void* stream) {
+  if (image_rois <= 0) return sdet::fail(SDET_ERR_INVALID_ARG, "image_rois must be > 0 (ProposalTarget_v2 takes -1)");
+  return proposal_target_core(rois, gt_boxes, nullptr, rois_out, labels, bbox_targets, bbox_weights, match_gt_ious,
+                              kept, B, R, G, num_classes, image_rois, fg_fraction, fg_thresh, bg_thresh_hi,
+                              bg_thresh_lo, proposal_without_gt, class_agnostic, 0, bbox_mean, bbox_std, bbox_weight,
+                              seed, priorities, num_draws, priorities_used, gt_index, fg_count, stream);
+}
+
+extern "C" int sdet_proposal_target_v2(const float* rois, const float* gt_boxes, const float* valid_ranges,
+                                       float* rois_out, float* labels, float* bbox_targets,
+                                       float* bbox_weights, float* match_gt_ious, int* kept, int B, int R,
+                                       int G, int num_classes, int image_rois, float fg_fraction,
+                                       float fg_thresh, float bg_thresh_hi, float bg_thresh_lo,
+                                       int proposal_without_gt, int class_agnostic, int filter_scales,
+                                       const float* bbox_mean, const float* bbox_std, const float* bbox_weight,
+                                       unsigned long long seed, const uint32_t* priorities, int num_draws,
+                                       uint32_t* priorities_used, void* stream) {
+  if (image_rois <= 0 && image_rois != -1)
+    return sdet::fail(SDET_ERR_INVALID_ARG, "image_rois must be > 0 or -1");
+  if (filter_scales && !valid_ranges) return sdet::fail(SDET_ERR_INVALID_ARG, "filter_scales needs valid_ranges");
+  return proposal_target_core(rois, gt_boxes, valid_ranges, rois_out, labels, bbox_targets, bbox_weights,
+                              match_gt_ious, kept, B, R, G, num_classes, image_rois, fg_fraction, fg_thresh,
+                              bg_thresh_hi, bg_thresh_lo, proposal_without_gt, class_agnostic, filter_scales,
+                              bbox_mean, bbox_std, bbox_weight, seed, priorities, num_draws, priorities_used, nullptr,
+                              nullptr, stream);
 }
 
 extern "C" int sdet_poly_mask_target(const float* rois_out, const float* gt_polys, const int* gt_index,

@@ -22,7 +22,7 @@ __all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_r
            "fpn_roi_align", "fpn_roi_align_raw", "DecodeBBox", "Proposal_v3", "Proposal_v3_fpn", "NMS", "nms_sorted", "get_top_proposal",
            "multiclass_nms", "ProposalTarget", "FocalLoss", "BBoxNorm",
            "SigmoidCrossEntropy", "soft_nms", "soft_nms_batched",
-           "cython_soft_nms_wrapper", "DeformableConvolution", "ProposalMaskTarget", "OPS"]
+           "cython_soft_nms_wrapper", "DeformableConvolution", "ProposalMaskTarget", "ProposalTarget_v2", "OPS"]
 
 
 def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor | None:
@@ -542,6 +542,49 @@ def SigmoidCrossEntropy(data, label, grad_scale=1.0):
     return _SigmoidCEFn.apply(data, label, float(grad_scale))
 
 
+def ProposalTarget_v2(rois, gt_boxes, valid_ranges, num_classes, batch_images, image_rois, fg_thresh, bg_thresh_hi,
+                      bg_thresh_lo, proposal_without_gt, fg_fraction=0.25, class_agnostic=False, output_iou=False,
+                      filter_scales=False, bbox_mean=(0.0, 0.0, 0.0, 0.0), bbox_std=(0.1, 0.1, 0.2, 0.2),
+                      bbox_weight=(1.0, 1.0, 1.0, 1.0), seed=None, priorities=None, num_draws=8, return_debug=False):
+    """mx.sym.ProposalTarget_v2 (TridentNet): ProposalTarget + valid_ranges (B,2) / filter_scales,
+    and image_rois = -1 to keep every foreground roi (R rows per image)."""
+    rois, gt_boxes = _dev(rois, "rois"), _dev(gt_boxes, "gt_boxes")
+    valid_ranges = _dev(valid_ranges, "valid_ranges")
+    B = int(batch_images)
+    R = rois.numel() // (B * 4)
+    G = gt_boxes.numel() // (B * 5)
+    IR = R if int(image_rois) == -1 else int(image_rois)
+    dev = rois.device
+    NC4 = 4 * int(num_classes)
+    o_rois = torch.empty((B, IR, 4), device=dev)
+    o_lab = torch.empty((B, IR), device=dev)
+    o_tgt = torch.empty((B, IR, NC4), device=dev)
+    o_wgt = torch.empty((B, IR, NC4), device=dev)
+    o_iou = torch.empty((B, IR), device=dev)
+    kept = torch.empty((B, IR), device=dev, dtype=torch.int32) if return_debug else None
+    T = R + G
+    if priorities is not None:
+        priorities = priorities.to(device=dev, dtype=torch.int64).contiguous()
+        num_draws = priorities.shape[1]
+        priorities = (priorities & 0xFFFFFFFF)
+        priorities = torch.where(priorities >= 2 ** 31, priorities - 2 ** 32, priorities).to(torch.int32).contiguous()
+    if seed is None:
+        _PT_CALLS[0] += 1
+        seed = 0x5DE7B200 + _PT_CALLS[0]
+    check(_lib.lib().sdet_proposal_target_v2(
+        _p(rois), _p(gt_boxes), _p(valid_ranges), _p(o_rois), _p(o_lab), _p(o_tgt), _p(o_wgt), _p(o_iou), _p(kept), B,
+        R, G, int(num_classes), int(image_rois), float(fg_fraction), float(fg_thresh), float(bg_thresh_hi),
+        float(bg_thresh_lo), int(bool(proposal_without_gt)), int(bool(class_agnostic)), int(bool(filter_scales)),
+        _f4(bbox_mean, "bbox_mean"), _f4(bbox_std, "bbox_std"), _f4(bbox_weight, "bbox_weight"),
+        int(seed) & (2 ** 64 - 1), _p(priorities), int(num_draws), None, _stream()))
+    outs = [o_rois, o_lab, o_tgt, o_wgt]
+    if output_iou or return_debug:
+        outs.append(o_iou)
+    if return_debug:
+        outs.append(kept)
+    return tuple(outs)
+
+
 def ProposalMaskTarget(rois, gt_boxes, gt_polys, num_classes, batch_images, image_rois, mask_size, fg_thresh,
                        bg_thresh_hi, bg_thresh_lo, proposal_without_gt, fg_fraction=0.25, class_agnostic=False,
                        output_iou=False, output_ratio=False, filter_scales=False, num_args=3,
@@ -724,6 +767,7 @@ OPS = {
     "_contrib_NMS": NMS,
     "ProposalTarget": ProposalTarget,
     "ProposalMaskTarget": ProposalMaskTarget,
+    "ProposalTarget_v2": ProposalTarget_v2,
     "_contrib_DeformableConvolution": DeformableConvolution,
     "_contrib_FocalLoss": FocalLoss,
     "_contrib_BBoxNorm": BBoxNorm,

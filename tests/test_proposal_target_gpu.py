@@ -113,3 +113,20 @@ def test_visible_outputs_follow_output_iou(cuda):
     b = ops.ProposalTarget(_t(rois, cuda), _t(gt, cuda), 81, 1, 32, 0.5, 0.5, 0.0, False, seed=1, output_iou=True)
     assert len(a) == 4 and len(b) == 5 and b[4].shape == (1, 32)
     assert a[2].shape == (1, 32, 324)
+
+
+@pytest.mark.parametrize("image_rois,filter_scales", [(128, True), (-1, False), (-1, True)])
+def test_proposal_target_v2(cuda, image_rois, filter_scales):
+    rng = np.random.default_rng(17)
+    B, R, G = 2, 600, 30
+    rois, gt = _scene(rng, B, R, G, n_gt=[9, 4], n_valid=[600, 350])
+    vr = np.array([[0, 120], [90, 1e4]], np.float32)  # image 0 drops big gts, image 1 drops small ones
+    pr = rng.integers(0, 2 ** 32, (B, 4, R + G), dtype=np.uint64).astype(np.uint32)
+    ref = oracle.proposal_target(rois, gt, pr, 81, image_rois, 0.25, 0.5, 0.5, 0.0, valid_ranges=vr,
+                                 filter_scales=filter_scales)
+    res = ops.ProposalTarget_v2(_t(rois, cuda), _t(gt, cuda), _t(vr, cuda), 81, B, image_rois, 0.5, 0.5, 0.0, False,
+                                filter_scales=filter_scales, priorities=_t(pr.astype(np.int64), cuda),
+                                return_debug=True)
+    IR = R if image_rois == -1 else image_rois
+    assert res[0].shape == (B, IR, 4)
+    _compare(res[:6], ref, IR)
