@@ -59,6 +59,7 @@ def main():
     ap.add_argument("--argmax", type=int, default=0)
     ap.add_argument("--plan", type=int, default=1)
     ap.add_argument("--noflush", type=int, default=0)
+    ap.add_argument("--backward", type=int, default=0, help="time the backward pass (incl. zero-fill of the grads)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(0)
@@ -78,8 +79,27 @@ def main():
         ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=bool(a.argmax),
                               use_plan=bool(a.plan))
 
+    if a.backward:
+        import ctypes
+        from simpledet_b200 import _lib
+        out, ax, ay, lvt = ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=True)
+        ograd = torch.randn_like(out)
+        grads = [torch.empty_like(f) for f in feats]
+        L = len(grads)
+        ptrs = (ctypes.c_void_p * L)(*[g.data_ptr() for g in grads])
+        Hs = (ctypes.c_int * L)(*[h for h, w in shapes])
+        Ws = (ctypes.c_int * L)(*[w for h, w in shapes])
+        lib = _lib.lib()
+        # algorithmic: read ograd + both argmax planes, zero-fill every level, 4 read-modify-writes per element
+        nbytes = 3 * out.numel() * 4 + sum(g.numel() * 4 for g in grads)
+
+        def fn():  # noqa: F811
+            _lib.check(lib.sdet_fpn_roi_align_v2_backward(
+                ograd.data_ptr(), ax.data_ptr(), ay.data_ptr(), lvt.data_ptr(), ptrs, Hs, Ws, L, B, N, C, pooled,
+                pooled, 0, torch.cuda.current_stream().cuda_stream))
+
     med, mn = time_op(fn, a.iters, flush, not a.noflush)
-    print(json.dumps({"shape": a.shape, "B": B, "N": N, "pooled": pooled, "argmax": a.argmax, "plan": a.plan, "noflush": a.noflush, "modepref": os.environ.get("SDET_RA_MODEPREF"), "tiles": os.environ.get("SDET_RA_TILES"),
+    print(json.dumps({"shape": a.shape, "B": B, "N": N, "pooled": pooled, "argmax": a.argmax, "backward": a.backward, "plan": a.plan, "noflush": a.noflush, "modepref": os.environ.get("SDET_RA_MODEPREF"), "tiles": os.environ.get("SDET_RA_TILES"),
                       "cpt": os.environ.get("SDET_RA_CPT"), "phs": os.environ.get("SDET_RA_PHS"),
                       "us_median": round(med, 2), "us_min": round(mn, 2), "alg_bytes": nbytes,
                       "GBps": round(nbytes / med / 1e3, 1),

@@ -135,6 +135,50 @@ int sdet_proposal_v3(const float* cls_prob, const float* bbox_pred, const float*
                      int rpn_min_size, int iou_loss, int is_train, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* _contrib_Proposal (version 1: operator_cxx/contrib/proposal.cu:430-620; X.proposal at
+ * symbol/builder.py:241-255) and _contrib_Proposal_v2 (version 2: proposal_v2.cu:405-600, TridentNet):
+ * the legacy pipeline — floor(x+0.5) anchors, legacy decode without exp clip, padded-cell mask and
+ * min-size (rpn_min_size * im_scale) filter BEFORE the sort, NMS removes IoU > threshold.
+ * version 1 honours is_train (wrap padding, post = rpn_post_nms_top_n at test time); version 2
+ * takes valid_ranges (B,2) device + filter_scales and always zero-pads with post = min(post, pre). */
+size_t sdet_proposal_legacy_workspace(int B, int A, int H, int W, int rpn_pre_nms_top_n);
+int sdet_proposal_legacy(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                         const float* valid_ranges, int version, float* out, float* out_score, int B,
+                         int A, int H, int W, int feature_stride, const float* scales, int num_scales,
+                         const float* ratios, int num_ratios, int rpn_pre_nms_top_n,
+                         int rpn_post_nms_top_n, float threshold, int rpn_min_size, int iou_loss,
+                         int is_train, int filter_scales, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* _contrib_GenProposal (generate_proposal.cu:289-430): the legacy decode + mask + min-size filter on
+ * caller-supplied shifted anchors (H*W*A,4), stable sort, NO NMS.  out (B, rpn_pre_nms_top_n, 5) =
+ * (x1,y1,x2,y2,score); rows past min(rpn_pre_nms_top_n, A*H*W) are zero. */
+size_t sdet_gen_proposal_workspace(int B, int A, int H, int W, int rpn_pre_nms_top_n);
+int sdet_gen_proposal(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                      const float* anchors, float* out, int B, int A, int H, int W, int feature_stride,
+                      int rpn_pre_nms_top_n, int rpn_min_size, int iou_loss, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* _contrib_GenAnchor (generate_anchor.cu:62-140): out (H*W*A, 4) fp32 = float(double base anchor +
+ * shift); scales/ratios are host doubles (GenAnchorParam keeps doubles "for consistency with python"). */
+int sdet_gen_anchor(float* out, int H, int W, int feature_stride, const double* scales, int num_scales,
+                    const double* ratios, int num_ratios, void* stream);
+
+/* _contrib_GenProposalRetina (generate_proposal_retina.cu:307-469; models/retinanet/builder.py:374-387).
+ * cls_prob (B, A*K, H, W) sigmoid probabilities, bbox_pred (B, A*4, H, W), anchors (H*W*A, 4).
+ * out (B, rpn_pre_nms_top_n, 4), out_score (B, rpn_pre_nms_top_n, K+1 | 1): the top pairs by score
+ * among those with score > thresh and both sides >= rpn_min_size*im_scale; every other row is zero.
+ * anchor_mean/anchor_std: host float[4] (NULL = 0 / 1).  Unsupported (the reference reads out of
+ * range there): iou_loss, batch_wise_anchor with K > 1; thresh must be >= 0. */
+size_t sdet_gen_proposal_retina_workspace(int B, int AK, int H, int W);
+int sdet_gen_proposal_retina(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                             const float* anchors, float* out, float* out_score, int B, int AK, int H,
+                             int W, int num_anchors, int feature_stride, int rpn_pre_nms_top_n,
+                             int rpn_min_size, float thresh, const float* anchor_mean,
+                             const float* anchor_std, int iou_loss, int output_one_hot,
+                             int batch_wise_anchor, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
 /* All RPN levels of an FPN in one call: num_levels x _contrib_Proposal_v3 + Concat(dim=1)
  * (models/FPN/builder.py:267-317).  cls_prob[l] (B,2A,H[l],W[l]), bbox_pred[l] (B,4A,H[l],W[l]);
  * the pointer / H / W / feature_stride arrays are HOST arrays of length num_levels.

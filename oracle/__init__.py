@@ -366,3 +366,64 @@ def sigmoid_ce_backward(data, label, scale=1.0):
     dx = np.empty_like(data)
     lib().oracle_sigmoid_ce_backward(_p(data), _p(label), R, ctypes.c_long(D), ctypes.c_float(scale), _p(dx))
     return dx
+
+
+def proposal_legacy(cls_prob, bbox_pred, im_info, version=1, valid_ranges=None, feature_stride=16,
+                    scales=(4, 8, 16, 32), ratios=(0.5, 1, 2), rpn_pre_nms_top_n=6000, rpn_post_nms_top_n=300,
+                    threshold=0.7, rpn_min_size=16, iou_loss=False, is_train=False, filter_scales=False):
+    """_contrib_Proposal (version=1) / _contrib_Proposal_v2 (version=2): legacy pipeline."""
+    cls_prob, bbox_pred, im_info = _f32(cls_prob), _f32(bbox_pred), _f32(im_info)
+    B, A2, H, W = cls_prob.shape
+    A = A2 // 2
+    count = A * H * W
+    pre = min(rpn_pre_nms_top_n if rpn_pre_nms_top_n > 0 else count, count)
+    post = min(rpn_post_nms_top_n, pre)
+    if version == 1 and not is_train:
+        post = rpn_post_nms_top_n
+    out = np.empty((B, post, 4), np.float32)
+    sc = np.empty((B, post, 1), np.float32)
+    vr = _f32(valid_ranges) if valid_ranges is not None else None
+    r, s_ = _f32(ratios), _f32(scales)
+    lib().oracle_proposal_legacy(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(vr), int(version), B, A, H, W,
+                                 int(feature_stride), _p(s_), len(s_), _p(r), len(r), int(rpn_pre_nms_top_n),
+                                 int(rpn_post_nms_top_n), ctypes.c_float(threshold), int(rpn_min_size),
+                                 int(bool(iou_loss)), int(bool(is_train)), int(bool(filter_scales)), _p(out), _p(sc))
+    return out, sc
+
+
+def gen_anchor(H, W, feature_stride=16, scales=(4, 8, 16, 32), ratios=(0.5, 1, 2)):
+    """_contrib_GenAnchor -> (H*W*A, 4) float32."""
+    sc = np.ascontiguousarray(scales, np.float64)
+    ra = np.ascontiguousarray(ratios, np.float64)
+    out = np.empty((H * W * len(sc) * len(ra), 4), np.float32)
+    lib().oracle_gen_anchor(int(H), int(W), int(feature_stride), _p(sc), len(sc), _p(ra), len(ra), _p(out))
+    return out
+
+
+def gen_proposal(cls_prob, bbox_pred, im_info, anchors, feature_stride=16, rpn_pre_nms_top_n=6000,
+                 rpn_min_size=16, iou_loss=False):
+    """_contrib_GenProposal -> (B, pre, 5)."""
+    cls_prob, bbox_pred, im_info, anchors = _f32(cls_prob), _f32(bbox_pred), _f32(im_info), _f32(anchors)
+    B, A2, H, W = cls_prob.shape
+    out = np.empty((B, rpn_pre_nms_top_n, 5), np.float32)
+    lib().oracle_gen_proposal(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(anchors), B, A2 // 2, H, W,
+                              int(feature_stride), int(rpn_pre_nms_top_n), int(rpn_min_size), int(bool(iou_loss)),
+                              _p(out))
+    return out
+
+
+def gen_proposal_retina(cls_prob, bbox_pred, im_info, anchors, num_anchors, rpn_pre_nms_top_n=1000,
+                        rpn_min_size=0, thresh=0.0, anchor_mean=(0, 0, 0, 0), anchor_std=(1, 1, 1, 1),
+                        output_one_hot=True):
+    """_contrib_GenProposalRetina -> (bbox (B,pre,4), score (B,pre,K+1|1))."""
+    cls_prob, bbox_pred, im_info, anchors = _f32(cls_prob), _f32(bbox_pred), _f32(im_info), _f32(anchors)
+    B, AK, H, W = cls_prob.shape
+    K = AK // num_anchors
+    oc = K + 1 if output_one_hot else 1
+    out = np.empty((B, rpn_pre_nms_top_n, 4), np.float32)
+    sc = np.empty((B, rpn_pre_nms_top_n, oc), np.float32)
+    m, s_ = _f32(anchor_mean), _f32(anchor_std)
+    lib().oracle_gen_proposal_retina(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(anchors), B, AK, H, W,
+                                     int(num_anchors), int(rpn_pre_nms_top_n), int(rpn_min_size),
+                                     ctypes.c_float(thresh), _p(m), _p(s_), int(bool(output_one_hot)), _p(out), _p(sc))
+    return out, sc

@@ -240,6 +240,248 @@ void oracle_proposal_v3(const float* cls_prob, const float* bbox_pred, const flo
   free(anchors); free(prop); free(score); free(order); free(dets); free(keep);
 }
 
+
+/* ---- _contrib_Proposal (version 1, operator_cxx/contrib/proposal.cu:65-420,430-620) and
+ * _contrib_Proposal_v2 (version 2, proposal_v2.cu): legacy pipeline.  Differences from v3:
+ * anchors round with floor(x + 0.5) (proposal-inl.h:302-303), legacy decode without the exp clip,
+ * padded cells (h >= im_h/stride or w >= im_w/stride) get score -1, the min-size filter
+ * (rpn_min_size * im_scale, on the decoded box) runs on ALL anchors BEFORE the sort, NMS removes
+ * IoU > thr.  v2 adds the valid-range filter (proposal_v2.cu:217-219), always zero-pads and has
+ * post = min(post, pre). ---- */
+void oracle_generate_anchors_legacy(int feature_stride, const float* ratios, int nr, const float* scales,
+                                    int ns, float* anchors) {
+  const float b2 = (float)(feature_stride - 1.0);
+  int k = 0;
+  for (int j = 0; j < nr; ++j)
+    for (int s = 0; s < ns; ++s) {
+      float w = b2 - 0.f + 1.0f, h = b2 - 0.f + 1.0f;
+      float x_ctr = (float)(0.f + 0.5 * (w - 1.0f)), y_ctr = (float)(0.f + 0.5 * (h - 1.0f));
+      float size = w * h;
+      float size_ratios = floorf(size / ratios[j]);
+      float new_w = floorf(sqrtf(size_ratios) + 0.5f) * scales[s];
+      float new_h = floorf((new_w / scales[s] * ratios[j]) + 0.5f) * scales[s];
+      anchors[k * 4 + 0] = x_ctr - 0.5f * (new_w - 1.0f);
+      anchors[k * 4 + 1] = y_ctr - 0.5f * (new_h - 1.0f);
+      anchors[k * 4 + 2] = x_ctr + 0.5f * (new_w - 1.0f);
+      anchors[k * 4 + 3] = y_ctr + 0.5f * (new_h - 1.0f);
+      ++k;
+    }
+}
+
+void oracle_proposal_legacy(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                            const float* valid_ranges, int version, int B, int A, int H, int W,
+                            int feature_stride, const float* scales, int ns, const float* ratios, int nr,
+                            int pre_nms_top_n, int post_nms_top_n, float threshold, int rpn_min_size,
+                            int iou_loss, int is_train, int filter_scales, float* out, float* out_score) {
+  const int count = A * H * W;
+  int pre = pre_nms_top_n > 0 ? pre_nms_top_n : count;
+  if (pre > count) pre = count;
+  int post = post_nms_top_n < pre ? post_nms_top_n : pre;
+  if (version == 1 && !is_train) post = post_nms_top_n; /* proposal.cu:453-455 */
+  float* anchors = (float*)malloc(sizeof(float) * 4 * (size_t)A);
+  oracle_generate_anchors_legacy(feature_stride, ratios, nr, scales, ns, anchors);
+  float* prop = (float*)malloc(sizeof(float) * 5 * (size_t)count);
+  float* score = (float*)malloc(sizeof(float) * (size_t)count);
+  int* order = (int*)malloc(sizeof(int) * (size_t)count);
+  float* dets = (float*)malloc(sizeof(float) * 5 * (size_t)pre);
+  int* keep = (int*)calloc((size_t)pre, sizeof(int));
+  for (int b = 0; b < B; ++b) {
+    const float im_h = im_info[b * 3 + 0], im_w = im_info[b * 3 + 1], im_s = im_info[b * 3 + 2];
+    const int real_h = (int)(im_h / feature_stride), real_w = (int)(im_w / feature_stride);
+    const float* fg = cls_prob + (long)b * 2 * count + count;
+    const float* dl = bbox_pred + (long)b * 4 * count;
+    const float min_size = rpn_min_size * im_s; /* int * float (proposal.cu:533) */
+    for (int index = 0; index < count; ++index) {
+      int a = index % A, w = (index / A) % W, h = index / A / W;
+      float bx1 = anchors[a * 4 + 0] + w * feature_stride, by1 = anchors[a * 4 + 1] + h * feature_stride;
+      float bx2 = anchors[a * 4 + 2] + w * feature_stride, by2 = anchors[a * 4 + 3] + h * feature_stride;
+      float sc = fg[(a * H + h) * W + w];
+      float d0 = dl[((a * 4 + 0) * H + h) * W + w], d1 = dl[((a * 4 + 1) * H + h) * W + w];
+      float d2 = dl[((a * 4 + 2) * H + h) * W + w], d3 = dl[((a * 4 + 3) * H + h) * W + w];
+      float x1, y1, x2, y2;
+      if (iou_loss) {
+        x1 = bx1 + d0; y1 = by1 + d1; x2 = bx2 + d2; y2 = by2 + d3;
+      } else { /* BBoxPredKernel proposal.cu:93-145 */
+        float width = bx2 - bx1 + 1.0f, height = by2 - by1 + 1.0f;
+        float ctr_x = bx1 + 0.5f * (width - 1.0f), ctr_y = by1 + 0.5f * (height - 1.0f);
+        float pcx = d0 * width + ctr_x, pcy = d1 * height + ctr_y;
+        float pw = expf(d2) * width, ph = expf(d3) * height;
+        x1 = pcx - 0.5f * (pw - 1.0f); y1 = pcy - 0.5f * (ph - 1.0f);
+        x2 = pcx + 0.5f * (pw - 1.0f); y2 = pcy + 0.5f * (ph - 1.0f);
+      }
+      x1 = fmax_(fmin_(x1, im_w - 1.0f), 0.0f); y1 = fmax_(fmin_(y1, im_h - 1.0f), 0.0f);
+      x2 = fmax_(fmin_(x2, im_w - 1.0f), 0.0f); y2 = fmax_(fmin_(y2, im_h - 1.0f), 0.0f);
+      if (h >= real_h || w >= real_w) sc = -1.0f;
+      /* FilterBoxKernel (proposal.cu:207-224 / proposal_v2.cu:200-222), before the sort */
+      float iw = x2 - x1 + 1.0f, ih = y2 - y1 + 1.0f;
+      if (iw < min_size || ih < min_size) {
+        x1 -= min_size / 2; y1 -= min_size / 2; x2 += min_size / 2; y2 += min_size / 2; sc = -1.0f;
+      } else if (version == 2 && filter_scales) {
+        float vmin = valid_ranges[b * 2] * valid_ranges[b * 2], vmax = valid_ranges[b * 2 + 1] * valid_ranges[b * 2 + 1];
+        if (iw * ih < vmin || iw * ih > vmax) sc = -1.0f;
+      }
+      float* p = prop + (long)index * 5;
+      p[0] = x1; p[1] = y1; p[2] = x2; p[3] = y2; p[4] = sc;
+      score[index] = sc;
+    }
+    oracle_stable_argsort_desc(score, count, order);
+    for (int i = 0; i < pre; ++i) memcpy(dets + (long)i * 5, prop + (long)order[i] * 5, 5 * sizeof(float));
+    int nk = greedy_scan(dets, pre, threshold, /*ge=*/0, keep); /* proposal.cu:301 uses > */
+    for (int i = 0; i < post; ++i) {
+      float* o = out + ((long)b * post + i) * 4;
+      int k = -1;
+      if (i < nk) k = keep[i];
+      else if (version == 1 && is_train) k = keep[i % nk];
+      if (k >= 0) { memcpy(o, dets + (long)k * 5, 16); out_score[(long)b * post + i] = dets[(long)k * 5 + 4]; }
+      else { o[0] = o[1] = o[2] = o[3] = 0.f; out_score[(long)b * post + i] = 0.f; }
+    }
+  }
+  free(anchors); free(prop); free(score); free(order); free(dets); free(keep);
+}
+
+
+/* ---- _contrib_GenAnchor (generate_anchor-inl.h:139-183 GenerateAnchors in double with rint;
+ * generate_anchor.cu:62-81 AnchorGridKernel casts double + int shift to float). ---- */
+void oracle_gen_anchor(int H, int W, int feature_stride, const double* scales, int ns, const double* ratios,
+                       int nr, float* out) {
+  const int A = ns * nr;
+  double* base = (double*)malloc(sizeof(double) * 4 * (size_t)A);
+  const double b2 = feature_stride - 1.0f;
+  int k = 0;
+  for (int j = 0; j < nr; ++j)
+    for (int s = 0; s < ns; ++s) {
+      double w = b2 - 0.0 + 1.0f, h = b2 - 0.0 + 1.0f;
+      double x_ctr = 0.0 + 0.5 * (w - 1.0f), y_ctr = 0.0 + 0.5 * (h - 1.0f);
+      double size_ratios = (w * h) / ratios[j];
+      double new_w = rint(sqrt(size_ratios)) * scales[s];
+      double new_h = rint((new_w / scales[s] * ratios[j])) * scales[s];
+      base[k * 4 + 0] = x_ctr - 0.5f * (new_w - 1.0f);
+      base[k * 4 + 1] = y_ctr - 0.5f * (new_h - 1.0f);
+      base[k * 4 + 2] = x_ctr + 0.5f * (new_w - 1.0f);
+      base[k * 4 + 3] = y_ctr + 0.5f * (new_h - 1.0f);
+      ++k;
+    }
+  for (int index = 0; index < H * W * A; ++index) {
+    int a = index % A, w = (index / A) % W, h = index / A / W;
+    out[index * 4 + 0] = (float)(base[a * 4 + 0] + w * feature_stride);
+    out[index * 4 + 1] = (float)(base[a * 4 + 1] + h * feature_stride);
+    out[index * 4 + 2] = (float)(base[a * 4 + 2] + w * feature_stride);
+    out[index * 4 + 3] = (float)(base[a * 4 + 3] + h * feature_stride);
+  }
+  free(base);
+}
+
+/* ---- _contrib_GenProposal (generate_proposal.cu:289-430): legacy decode on supplied anchors, mask,
+ * min-size filter, stable sort, no NMS; out (B, pre_param, 5).  Column 0 of padded rows is left
+ * untouched by the reference; written as 0 here. ---- */
+void oracle_gen_proposal(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                         const float* anchors, int B, int A, int H, int W, int feature_stride,
+                         int pre_nms_top_n, int rpn_min_size, int iou_loss, float* out) {
+  const int count = A * H * W;
+  int pre = pre_nms_top_n > 0 ? pre_nms_top_n : count;
+  if (pre > count) pre = count;
+  float* prop = (float*)malloc(sizeof(float) * 5 * (size_t)count);
+  float* score = (float*)malloc(sizeof(float) * (size_t)count);
+  int* order = (int*)malloc(sizeof(int) * (size_t)count);
+  for (int b = 0; b < B; ++b) {
+    const float im_h = im_info[b * 3 + 0], im_w = im_info[b * 3 + 1], im_s = im_info[b * 3 + 2];
+    const int real_h = (int)(im_h / feature_stride), real_w = (int)(im_w / feature_stride);
+    const float* fg = cls_prob + (long)b * 2 * count + count;
+    const float* dl = bbox_pred + (long)b * 4 * count;
+    const float min_size = rpn_min_size * im_s;
+    for (int index = 0; index < count; ++index) {
+      int a = index % A, w = (index / A) % W, h = index / A / W;
+      float bx1 = anchors[index * 4 + 0], by1 = anchors[index * 4 + 1];
+      float bx2 = anchors[index * 4 + 2], by2 = anchors[index * 4 + 3];
+      float sc = fg[(a * H + h) * W + w];
+      float d0 = dl[((a * 4 + 0) * H + h) * W + w], d1 = dl[((a * 4 + 1) * H + h) * W + w];
+      float d2 = dl[((a * 4 + 2) * H + h) * W + w], d3 = dl[((a * 4 + 3) * H + h) * W + w];
+      float x1, y1, x2, y2;
+      if (iou_loss) {
+        x1 = bx1 + d0; y1 = by1 + d1; x2 = bx2 + d2; y2 = by2 + d3;
+      } else {
+        float width = bx2 - bx1 + 1.0f, height = by2 - by1 + 1.0f;
+        float ctr_x = bx1 + 0.5f * (width - 1.0f), ctr_y = by1 + 0.5f * (height - 1.0f);
+        float pcx = d0 * width + ctr_x, pcy = d1 * height + ctr_y;
+        float pw = expf(d2) * width, ph = expf(d3) * height;
+        x1 = pcx - 0.5f * (pw - 1.0f); y1 = pcy - 0.5f * (ph - 1.0f);
+        x2 = pcx + 0.5f * (pw - 1.0f); y2 = pcy + 0.5f * (ph - 1.0f);
+      }
+      x1 = fmax_(fmin_(x1, im_w - 1.0f), 0.0f); y1 = fmax_(fmin_(y1, im_h - 1.0f), 0.0f);
+      x2 = fmax_(fmin_(x2, im_w - 1.0f), 0.0f); y2 = fmax_(fmin_(y2, im_h - 1.0f), 0.0f);
+      if (h >= real_h || w >= real_w) sc = -1.0f;
+      float iw = x2 - x1 + 1.0f, ih = y2 - y1 + 1.0f;
+      if (iw < min_size || ih < min_size) {
+        x1 -= min_size / 2; y1 -= min_size / 2; x2 += min_size / 2; y2 += min_size / 2; sc = -1.0f;
+      }
+      float* p = prop + (long)index * 5;
+      p[0] = x1; p[1] = y1; p[2] = x2; p[3] = y2; p[4] = sc;
+      score[index] = sc;
+    }
+    oracle_stable_argsort_desc(score, count, order);
+    float* o = out + (long)b * pre_nms_top_n * 5;
+    for (int i = 0; i < pre_nms_top_n; ++i) {
+      if (i < pre) memcpy(o + (long)i * 5, prop + (long)order[i] * 5, 20);
+      else memset(o + (long)i * 5, 0, 20);
+    }
+  }
+  free(prop); free(score); free(order);
+}
+
+/* ---- _contrib_GenProposalRetina (generate_proposal_retina.cu:307-469). ---- */
+void oracle_gen_proposal_retina(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                                const float* anchors, int B, int AK, int H, int W, int num_anchors,
+                                int pre_nms_top_n, int rpn_min_size, float thresh, const float* mean,
+                                const float* stdv, int output_one_hot, float* out, float* out_score) {
+  const int K = AK / num_anchors, count = AK * H * W;
+  int pre = pre_nms_top_n > 0 ? pre_nms_top_n : count;
+  if (pre > count) pre = count;
+  const int oc = output_one_hot ? K + 1 : 1;
+  float* prop = (float*)malloc(sizeof(float) * 5 * (size_t)count);
+  float* score = (float*)malloc(sizeof(float) * (size_t)count);
+  int* order = (int*)malloc(sizeof(int) * (size_t)count);
+  memset(out, 0, sizeof(float) * 4 * (size_t)B * pre_nms_top_n);
+  memset(out_score, 0, sizeof(float) * (size_t)oc * B * pre_nms_top_n);
+  for (int b = 0; b < B; ++b) {
+    const float im_h = im_info[b * 3 + 0], im_w = im_info[b * 3 + 1], im_s = im_info[b * 3 + 2];
+    const float* sc = cls_prob + (long)b * count;
+    const float* dl = bbox_pred + (long)b * 4 * count / K;
+    const float min_size = rpn_min_size * im_s;
+    for (int index = 0; index < count; ++index) {
+      int a = index % AK, w = (index / AK) % W, h = index / AK / W;
+      int ai = (h * W + w) * (AK / K) + a / K;
+      float bx1 = anchors[ai * 4 + 0], by1 = anchors[ai * 4 + 1], bx2 = anchors[ai * 4 + 2], by2 = anchors[ai * 4 + 3];
+      float s = sc[(a * H + h) * W + w];
+      float width = bx2 - bx1 + 1.0f, height = by2 - by1 + 1.0f;
+      float ctr_x = bx1 + 0.5f * (width - 1.0f), ctr_y = by1 + 0.5f * (height - 1.0f);
+      float dx = dl[((a / K * 4) * H + h) * W + w] * stdv[0] + mean[0];
+      float dy = dl[((a / K * 4 + 1) * H + h) * W + w] * stdv[1] + mean[1];
+      float dw = dl[((a / K * 4 + 2) * H + h) * W + w] * stdv[2] + mean[2];
+      float dh = dl[((a / K * 4 + 3) * H + h) * W + w] * stdv[3] + mean[3];
+      float pcx = dx * width + ctr_x, pcy = dy * height + ctr_y;
+      float pw = expf(dw) * width, ph = expf(dh) * height;
+      float x1 = pcx - 0.5f * (pw - 1.0f), y1 = pcy - 0.5f * (ph - 1.0f);
+      float x2 = pcx + 0.5f * (pw - 1.0f), y2 = pcy + 0.5f * (ph - 1.0f);
+      x1 = fmax_(fmin_(x1, im_w - 1.0f), 0.0f); y1 = fmax_(fmin_(y1, im_h - 1.0f), 0.0f);
+      x2 = fmax_(fmin_(x2, im_w - 1.0f), 0.0f); y2 = fmax_(fmin_(y2, im_h - 1.0f), 0.0f);
+      float iw = x2 - x1 + 1.0f, ih = y2 - y1 + 1.0f;
+      if (iw < min_size || ih < min_size || s <= thresh) { x1 = y1 = x2 = y2 = s = 0.0f; }
+      float* p = prop + (long)index * 5;
+      p[0] = x1; p[1] = y1; p[2] = x2; p[3] = y2; p[4] = s;
+      score[index] = s;
+    }
+    oracle_stable_argsort_desc(score, count, order);
+    for (int i = 0; i < pre && i < pre_nms_top_n; ++i) {
+      const float* p = prop + (long)order[i] * 5;
+      memcpy(out + ((long)b * pre_nms_top_n + i) * 4, p, 16);
+      int cid = order[i] % K + 1;
+      if (cid > oc - 1) cid = oc - 1;
+      out_score[((long)b * pre_nms_top_n + i) * oc + cid] = p[4];
+    }
+  }
+  free(prop); free(score); free(order);
+}
+
 /* ---- _contrib_NMS (nms.cu:274-364): proposals (B,count,5) -> out (B,post,4), score (B,post);
  * IoU > thr, zero padding (nms.cu:208-231). ---- */
 void oracle_contrib_nms(const float* proposals, int B, int count, int pre_nms_top_n,

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_size_t, c_uint64, c_void_p
 
 from .build import LIB_PATH
 
@@ -52,6 +52,16 @@ _SIGNATURES = {
                              POINTER(c_int), POINTER(c_int), c_int, POINTER(c_float), c_int,
                              POINTER(c_float), c_int, c_int, c_int, c_float, c_int, c_int, c_int, _P,
                              c_size_t, _P],
+    "sdet_proposal_legacy_workspace": [c_int, c_int, c_int, c_int, c_int],
+    "sdet_proposal_legacy": [_P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, POINTER(c_float),
+                             c_int, POINTER(c_float), c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_int,
+                             _P, c_size_t, _P],
+    "sdet_gen_proposal_workspace": [c_int, c_int, c_int, c_int, c_int],
+    "sdet_gen_proposal": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P],
+    "sdet_gen_anchor": [_P, c_int, c_int, c_int, POINTER(c_double), c_int, POINTER(c_double), c_int, _P],
+    "sdet_gen_proposal_retina_workspace": [c_int, c_int, c_int, c_int],
+    "sdet_gen_proposal_retina": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_float, POINTER(c_float), POINTER(c_float), c_int, c_int, c_int, _P, c_size_t, _P],
     "sdet_contrib_nms_workspace": [c_int, c_int, c_int],
     "sdet_contrib_nms": [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P, c_size_t, _P],
     "sdet_get_top_proposal": [_P, _P, _P, _P, c_int, c_int, c_int, _P],
@@ -78,7 +88,8 @@ _SIGNATURES = {
     "sdet_nms_sorted": [_P, _P, c_int, c_int, c_float, c_int, _P, _P, _P, c_size_t, _P],
 }
 _RESTYPES = {"sdet_last_error": c_char_p, "sdet_launch_count": c_uint64,
-             "sdet_proposal_v3_workspace": c_size_t, "sdet_proposal_v3_fpn_workspace": c_size_t, "sdet_contrib_nms_workspace": c_size_t,
+             "sdet_proposal_v3_workspace": c_size_t, "sdet_proposal_legacy_workspace": c_size_t,
+             "sdet_gen_proposal_workspace": c_size_t, "sdet_gen_proposal_retina_workspace": c_size_t, "sdet_proposal_v3_fpn_workspace": c_size_t, "sdet_contrib_nms_workspace": c_size_t,
              "sdet_nms_workspace": c_size_t, "sdet_roi_align_v2_workspace": c_size_t, "sdet_multiclass_nms_workspace": c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

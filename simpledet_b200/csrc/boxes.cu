@@ -368,6 +368,107 @@ void gen_anchors_v3(int stride, const float* ratios, int nr, const float* scales
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// Legacy _contrib_Proposal / _contrib_Proposal_v2 (operator_cxx/contrib/proposal.cu, proposal_v2.cu):
+// the padded-cell mask and the min-size (and v2 scale) filter run BEFORE the sort, so every anchor
+// has to be decoded: one coalesced pass writes (count,5) rows in reference index order, then the
+// generic rows_topk -> mask -> scan pipeline takes over.
+// --------------------------------------------------------------------------------------------
+struct LegacyParams {
+  const float* cls_prob;
+  const float* bbox_pred;
+  const float* im_info;
+  const float* valid_ranges;  // (B,2) or nullptr
+  const float* grid_anchors;  // (H*W*A,4) or nullptr: _contrib_GenProposal takes the shifted anchors as input
+  float anchors[kMaxAnchors * 4];
+  int A, H, W, stride, min_size, iou_loss, version, filter_scales;
+  float* props;  // (B, count, 5)
+};
+
+__global__ void __launch_bounds__(256) proposal_legacy_decode_kernel(const __grid_constant__ LegacyParams p) {
+  const int b = blockIdx.y;
+  const int A = p.A, H = p.H, W = p.W, HW = H * W, count = A * HW;
+  const float im_h = __ldg(p.im_info + b * 3), im_w = __ldg(p.im_info + b * 3 + 1), im_s = __ldg(p.im_info + b * 3 + 2);
+  const int real_h = (int)__fdiv_rn(im_h, (float)p.stride), real_w = (int)__fdiv_rn(im_w, (float)p.stride);
+  const float min_size = __fmul_rn((float)p.min_size, im_s);
+  const float mx = __fsub_rn(im_w, 1.0f), my = __fsub_rn(im_h, 1.0f);
+  const float* fg = p.cls_prob + (size_t)b * 2 * count + count;
+  const float* dl = p.bbox_pred + (size_t)b * 4 * count;
+  const float fs = (float)p.stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const int a = i / HW, r = i - a * HW, h = r / W, w = r - h * W;  // memory order (a,h,w): coalesced reads
+    float bx1, by1, bx2, by2;
+    if (p.grid_anchors) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(p.grid_anchors) + (size_t)r * A + a);
+      bx1 = g.x; by1 = g.y; bx2 = g.z; by2 = g.w;
+    } else {
+      bx1 = __fadd_rn(p.anchors[a * 4 + 0], __fmul_rn((float)w, fs));
+      by1 = __fadd_rn(p.anchors[a * 4 + 1], __fmul_rn((float)h, fs));
+      bx2 = __fadd_rn(p.anchors[a * 4 + 2], __fmul_rn((float)w, fs));
+      by2 = __fadd_rn(p.anchors[a * 4 + 3], __fmul_rn((float)h, fs));
+    }
+    float sc = __ldg(fg + i);
+    const float d0 = __ldg(dl + (a * 4 + 0) * HW + r), d1 = __ldg(dl + (a * 4 + 1) * HW + r);
+    const float d2 = __ldg(dl + (a * 4 + 2) * HW + r), d3 = __ldg(dl + (a * 4 + 3) * HW + r);
+    float x1, y1, x2, y2;
+    if (p.iou_loss) {
+      x1 = __fadd_rn(bx1, d0); y1 = __fadd_rn(by1, d1); x2 = __fadd_rn(bx2, d2); y2 = __fadd_rn(by2, d3);
+    } else {
+      const float width = __fadd_rn(__fsub_rn(bx2, bx1), 1.0f), height = __fadd_rn(__fsub_rn(by2, by1), 1.0f);
+      const float ctr_x = __fadd_rn(bx1, __fmul_rn(0.5f, __fsub_rn(width, 1.0f)));
+      const float ctr_y = __fadd_rn(by1, __fmul_rn(0.5f, __fsub_rn(height, 1.0f)));
+      const float pcx = __fadd_rn(__fmul_rn(d0, width), ctr_x), pcy = __fadd_rn(__fmul_rn(d1, height), ctr_y);
+      const float pw = __fmul_rn(expf(d2), width), ph = __fmul_rn(expf(d3), height);
+      const float hw_ = __fmul_rn(0.5f, __fsub_rn(pw, 1.0f)), hh_ = __fmul_rn(0.5f, __fsub_rn(ph, 1.0f));
+      x1 = __fsub_rn(pcx, hw_); y1 = __fsub_rn(pcy, hh_); x2 = __fadd_rn(pcx, hw_); y2 = __fadd_rn(pcy, hh_);
+    }
+    x1 = fmax_ref(fmin_ref(x1, mx), 0.0f); y1 = fmax_ref(fmin_ref(y1, my), 0.0f);
+    x2 = fmax_ref(fmin_ref(x2, mx), 0.0f); y2 = fmax_ref(fmin_ref(y2, my), 0.0f);
+    if (h >= real_h || w >= real_w) sc = -1.0f;
+    const float iw = __fadd_rn(__fsub_rn(x2, x1), 1.0f), ih = __fadd_rn(__fsub_rn(y2, y1), 1.0f);
+    if (iw < min_size || ih < min_size) {
+      const float hm = __fdiv_rn(min_size, 2.f);
+      x1 = __fsub_rn(x1, hm); y1 = __fsub_rn(y1, hm); x2 = __fadd_rn(x2, hm); y2 = __fadd_rn(y2, hm);
+      sc = -1.0f;
+    } else if (p.version == 2 && p.filter_scales) {
+      const float v0 = __ldg(p.valid_ranges + b * 2), v1 = __ldg(p.valid_ranges + b * 2 + 1);
+      const float ar = __fmul_rn(iw, ih);
+      if (ar < __fmul_rn(v0, v0) || ar > __fmul_rn(v1, v1)) sc = -1.0f;
+    }
+    float* o = p.props + ((size_t)b * count + (size_t)r * A + a) * 5;  // reference index (h*W+w)*A + a
+    o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = sc;
+  }
+}
+
+// _contrib_GenProposal PrepareOutput (generate_proposal.cu:268-287): rows < out_size are the sorted
+// proposals (x1,y1,x2,y2,score); later rows get columns 1..4 zeroed (column 0 is zeroed here too — the
+// reference leaves it uninitialised).
+__global__ void gen_proposal_out_kernel(const float* __restrict__ dets, const int pre, const int out_rows,
+                                        float* __restrict__ out) {
+  const int b = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < out_rows * 5; i += gridDim.x * blockDim.x)
+    out[(size_t)b * out_rows * 5 + i] = (i / 5 < pre) ? dets[(size_t)b * pre * 5 + i] : 0.f;
+}
+
+void gen_anchors_legacy(int stride, const float* ratios, int nr, const float* scales, int ns, float* out) {
+  const float base2 = (float)(stride - 1.0);
+  int k = 0;
+  for (int j = 0; j < nr; ++j)
+    for (int s = 0; s < ns; ++s) {
+      const float w = base2 - 0.f + 1.0f, h = base2 - 0.f + 1.0f;
+      const float x_ctr = (float)(0.f + 0.5 * (w - 1.0f)), y_ctr = (float)(0.f + 0.5 * (h - 1.0f));
+      const float size = w * h;
+      const float size_ratios = std::floor(size / ratios[j]);
+      const float new_w = std::floor(std::sqrt(size_ratios) + 0.5f) * scales[s];   // proposal-inl.h:302
+      const float new_h = std::floor((new_w / scales[s] * ratios[j]) + 0.5f) * scales[s];
+      out[k * 4 + 0] = x_ctr - 0.5f * (new_w - 1.0f);
+      out[k * 4 + 1] = y_ctr - 0.5f * (new_h - 1.0f);
+      out[k * 4 + 2] = x_ctr + 0.5f * (new_w - 1.0f);
+      out[k * 4 + 3] = y_ctr + 0.5f * (new_h - 1.0f);
+      ++k;
+    }
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // workspace layout for P problems of n boxes: dets (P,n,5) f32 | mask (P,n,cbs) u64
@@ -593,4 +694,103 @@ extern "C" int sdet_contrib_nms(const float* proposals, float* out, float* out_s
   so.write_rows = post;              // rows PrepareOutput touches (nms.cu:354-358)
   so.pad_mode = 0;
   return run_mask_and_scan(dets, nullptr, B, pre, threshold, /*ge=*/0, mask, so, st);  // `>` (nms.cu:140)
+}
+
+// workspace: props (B,count,5) | nms workspace (dets, mask) for pre boxes
+extern "C" size_t sdet_proposal_legacy_workspace(int B, int A, int H, int W, int rpn_pre_nms_top_n) {
+  if (B <= 0 || A <= 0 || H <= 0 || W <= 0) return 0;
+  const int count = A * H * W;
+  return align_up((size_t)B * count * 5 * 4, 256) + nms_ws_bytes(B, level_pre(A, H, W, rpn_pre_nms_top_n));
+}
+
+extern "C" int sdet_proposal_legacy(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                                    const float* valid_ranges, int version, float* out, float* out_score,
+                                    int B, int A, int H, int W, int feature_stride, const float* scales,
+                                    int num_scales, const float* ratios, int num_ratios, int rpn_pre_nms_top_n,
+                                    int rpn_post_nms_top_n, float threshold, int rpn_min_size, int iou_loss,
+                                    int is_train, int filter_scales, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  SDET_REQUIRE(cls_prob && bbox_pred && im_info && out && out_score && scales && ratios && workspace, "NULL argument");
+  SDET_REQUIRE(version == 1 || version == 2, "version must be 1 (_contrib_Proposal) or 2 (_contrib_Proposal_v2)");
+  SDET_REQUIRE(B > 0 && A > 0 && H > 0 && W > 0 && rpn_post_nms_top_n > 0, "bad shape");
+  SDET_REQUIRE(A == num_scales * num_ratios, "num_anchors (%d) != len(ratios)*len(scales) (%d)", A, num_scales * num_ratios);
+  SDET_REQUIRE(!(version == 2 && filter_scales) || valid_ranges, "filter_scales needs valid_ranges");
+  if (A > kMaxAnchors) return sdet::fail(SDET_ERR_UNSUPPORTED, "more than %d anchors per cell", kMaxAnchors);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int count = A * H * W;
+  const int pre = level_pre(A, H, W, rpn_pre_nms_top_n);
+  int post = std::min(rpn_post_nms_top_n, pre);
+  if (version == 1 && !is_train) post = rpn_post_nms_top_n;
+  if (workspace_bytes < sdet_proposal_legacy_workspace(B, A, H, W, rpn_pre_nms_top_n))
+    return sdet::fail(SDET_ERR_WORKSPACE, "workspace too small: need %zu bytes",
+                      sdet_proposal_legacy_workspace(B, A, H, W, rpn_pre_nms_top_n));
+  char* wsb = static_cast<char*>(workspace);
+  float* props = reinterpret_cast<float*>(wsb);
+  char* nws = wsb + align_up((size_t)B * count * 5 * 4, 256);
+  float* dets = reinterpret_cast<float*>(nws);
+  auto* mask = reinterpret_cast<unsigned long long*>(nws + align_up((size_t)B * pre * 5 * 4, 256));
+  LegacyParams p{};
+  p.cls_prob = cls_prob; p.bbox_pred = bbox_pred; p.im_info = im_info; p.valid_ranges = valid_ranges;
+  gen_anchors_legacy(feature_stride, ratios, num_ratios, scales, num_scales, p.anchors);
+  p.A = A; p.H = H; p.W = W; p.stride = feature_stride; p.min_size = rpn_min_size; p.iou_loss = iou_loss ? 1 : 0;
+  p.version = version; p.filter_scales = filter_scales ? 1 : 0;
+  p.props = props;
+  dim3 grid((unsigned)std::min((count + 255) / 256, 148 * 8), (unsigned)B);
+  proposal_legacy_decode_kernel<<<grid, 256, 0, st>>>(p);
+  SDET_LAUNCH_CHECK("proposal_legacy_decode_kernel");
+  static size_t configured = 0;
+  const int k_pow2 = sdet::next_pow2(pre);
+  const size_t smem = (size_t)k_pow2 * 8;
+  if (int rc = ensure_smem(rows_topk_kernel, smem, &configured)) return rc;
+  rows_topk_kernel<<<(unsigned)B, kTopkThreads, smem, st>>>(props, count, pre, k_pow2, 0, dets);
+  SDET_LAUNCH_CHECK("rows_topk_kernel");
+  ScanOut so{};
+  so.out = out;
+  so.out_score = out_score;
+  so.out_rows = post;
+  so.write_rows = post;
+  so.pad_mode = (version == 1 && is_train) ? 1 : 0;
+  return run_mask_and_scan(dets, nullptr, B, pre, threshold, /*ge=*/0, mask, so, st);  // `>` (proposal.cu:301)
+}
+
+extern "C" size_t sdet_gen_proposal_workspace(int B, int A, int H, int W, int rpn_pre_nms_top_n) {
+  if (B <= 0 || A <= 0 || H <= 0 || W <= 0) return 0;
+  const int count = A * H * W;
+  return align_up((size_t)B * count * 5 * 4, 256) + align_up((size_t)B * level_pre(A, H, W, rpn_pre_nms_top_n) * 5 * 4, 256);
+}
+
+extern "C" int sdet_gen_proposal(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                                 const float* anchors, float* out, int B, int A, int H, int W, int feature_stride,
+                                 int rpn_pre_nms_top_n, int rpn_min_size, int iou_loss, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  SDET_REQUIRE(cls_prob && bbox_pred && im_info && anchors && out && workspace, "NULL argument");
+  SDET_REQUIRE(B > 0 && A > 0 && H > 0 && W > 0 && rpn_pre_nms_top_n > 0, "bad shape");
+  SDET_REQUIRE((reinterpret_cast<uintptr_t>(anchors) & 15) == 0, "anchors must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int count = A * H * W;
+  const int pre = level_pre(A, H, W, rpn_pre_nms_top_n);
+  if (workspace_bytes < sdet_gen_proposal_workspace(B, A, H, W, rpn_pre_nms_top_n))
+    return sdet::fail(SDET_ERR_WORKSPACE, "workspace too small: need %zu bytes",
+                      sdet_gen_proposal_workspace(B, A, H, W, rpn_pre_nms_top_n));
+  char* wsb = static_cast<char*>(workspace);
+  float* props = reinterpret_cast<float*>(wsb);
+  float* dets = reinterpret_cast<float*>(wsb + align_up((size_t)B * count * 5 * 4, 256));
+  LegacyParams p{};
+  p.cls_prob = cls_prob; p.bbox_pred = bbox_pred; p.im_info = im_info; p.grid_anchors = anchors;
+  p.A = A; p.H = H; p.W = W; p.stride = feature_stride; p.min_size = rpn_min_size; p.iou_loss = iou_loss ? 1 : 0;
+  p.version = 1;
+  p.props = props;
+  dim3 grid((unsigned)std::min((count + 255) / 256, 148 * 8), (unsigned)B);
+  proposal_legacy_decode_kernel<<<grid, 256, 0, st>>>(p);
+  SDET_LAUNCH_CHECK("proposal_legacy_decode_kernel");
+  static size_t configured = 0;
+  const int k_pow2 = sdet::next_pow2(pre);
+  const size_t smem = (size_t)k_pow2 * 8;
+  if (int rc = ensure_smem(rows_topk_kernel, smem, &configured)) return rc;
+  rows_topk_kernel<<<(unsigned)B, kTopkThreads, smem, st>>>(props, count, pre, k_pow2, 0, dets);
+  SDET_LAUNCH_CHECK("rows_topk_kernel");
+  dim3 g2((unsigned)((rpn_pre_nms_top_n * 5 + 255) / 256), (unsigned)B);
+  gen_proposal_out_kernel<<<g2, 256, 0, st>>>(dets, pre, rpn_pre_nms_top_n, out);
+  SDET_LAUNCH_CHECK("gen_proposal_out_kernel");
+  return SDET_OK;
 }

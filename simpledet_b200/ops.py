@@ -22,7 +22,7 @@ __all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_r
            "fpn_roi_align", "fpn_roi_align_raw", "DecodeBBox", "Proposal_v3", "Proposal_v3_fpn", "NMS", "nms_sorted", "get_top_proposal",
            "multiclass_nms", "ProposalTarget", "FocalLoss", "BBoxNorm",
            "SigmoidCrossEntropy", "soft_nms", "soft_nms_batched",
-           "cython_soft_nms_wrapper", "DeformableConvolution", "ProposalMaskTarget", "ProposalTarget_v2", "OPS"]
+           "cython_soft_nms_wrapper", "DeformableConvolution", "ProposalMaskTarget", "ProposalTarget_v2", "Proposal", "Proposal_v2", "GenAnchor", "GenProposal", "GenProposalRetina", "OPS"]
 
 
 def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor | None:
@@ -309,6 +309,111 @@ def Proposal_v3(cls_prob, bbox_pred, im_info, rpn_pre_nms_top_n=6000, rpn_post_n
                              int(rpn_min_size), int(bool(iou_loss)), int(bool(is_train)), _p(ws), nbytes,
                              _stream()))
     return (out, score) if output_score else out
+
+
+def _proposal_legacy(version, cls_prob, bbox_pred, im_info, valid_ranges, rpn_pre_nms_top_n, rpn_post_nms_top_n,
+                     threshold, rpn_min_size, scales, ratios, feature_stride, output_score, iou_loss, is_train,
+                     filter_scales):
+    cls_prob, bbox_pred, im_info = _dev(cls_prob, "cls_prob"), _dev(bbox_pred, "bbox_pred"), _dev(im_info, "im_info")
+    valid_ranges = _dev(valid_ranges, "valid_ranges")
+    B, A2, H, W = cls_prob.shape
+    A = A2 // 2
+    if tuple(bbox_pred.shape) != (B, 4 * A, H, W):
+        raise ValueError("bbox_pred must be (B,4A,H,W)")
+    count = A * H * W
+    pre = min(rpn_pre_nms_top_n if rpn_pre_nms_top_n > 0 else count, count)
+    post = min(rpn_post_nms_top_n, pre)
+    if version == 1 and not is_train:
+        post = rpn_post_nms_top_n
+    out = torch.empty((B, post, 4), device=cls_prob.device, dtype=torch.float32)
+    score = torch.empty((B, post, 1), device=cls_prob.device, dtype=torch.float32)
+    L = _lib.lib()
+    nbytes = L.sdet_proposal_legacy_workspace(B, A, H, W, int(rpn_pre_nms_top_n))
+    ws = _ws(nbytes, cls_prob.device)
+    sc = (ctypes.c_float * len(scales))(*[float(x) for x in scales])
+    ra = (ctypes.c_float * len(ratios))(*[float(x) for x in ratios])
+    check(L.sdet_proposal_legacy(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(valid_ranges), version, _p(out),
+                                 _p(score), B, A, H, W, int(feature_stride), sc, len(scales), ra, len(ratios),
+                                 int(rpn_pre_nms_top_n), int(rpn_post_nms_top_n), float(threshold),
+                                 int(rpn_min_size), int(bool(iou_loss)), int(bool(is_train)),
+                                 int(bool(filter_scales)), _p(ws), nbytes, _stream()))
+    return (out, score) if output_score else out
+
+
+def Proposal(cls_prob, bbox_pred, im_info, rpn_pre_nms_top_n=6000, rpn_post_nms_top_n=300, threshold=0.7,
+             rpn_min_size=16, scales=(4.0, 8.0, 16.0, 32.0), ratios=(0.5, 1.0, 2.0), feature_stride=16,
+             output_score=False, iou_loss=False, is_train=False):
+    """mx.sym.contrib.Proposal / X.proposal (symbol/builder.py:241-255): the legacy RPN proposal op."""
+    return _proposal_legacy(1, cls_prob, bbox_pred, im_info, None, rpn_pre_nms_top_n, rpn_post_nms_top_n, threshold,
+                            rpn_min_size, scales, ratios, feature_stride, output_score, iou_loss, is_train, False)
+
+
+def Proposal_v2(cls_prob, bbox_pred, im_info, valid_ranges, rpn_pre_nms_top_n=6000, rpn_post_nms_top_n=300,
+                threshold=0.7, rpn_min_size=16, scales=(4.0, 8.0, 16.0, 32.0), ratios=(0.5, 1.0, 2.0),
+                feature_stride=16, output_score=False, iou_loss=False, filter_scales=False):
+    """mx.sym.contrib.Proposal_v2 (TridentNet, models/tridentnet/builder.py:239): Proposal + valid_ranges."""
+    return _proposal_legacy(2, cls_prob, bbox_pred, im_info, valid_ranges, rpn_pre_nms_top_n, rpn_post_nms_top_n,
+                            threshold, rpn_min_size, scales, ratios, feature_stride, output_score, iou_loss, False,
+                            filter_scales)
+
+
+def GenAnchor(cls_prob, scales=(4.0, 8.0, 16.0, 32.0), ratios=(0.5, 1.0, 2.0), feature_stride=16):
+    """mx.sym.contrib.GenAnchor (models/retinanet/builder.py:365): only cls_prob's (H, W) is used."""
+    cls_prob = _dev(cls_prob, "cls_prob")
+    H, W = int(cls_prob.shape[2]), int(cls_prob.shape[3])
+    A = len(scales) * len(ratios)
+    out = torch.empty((H * W * A, 4), device=cls_prob.device, dtype=torch.float32)
+    sc = (ctypes.c_double * len(scales))(*[float(x) for x in scales])
+    ra = (ctypes.c_double * len(ratios))(*[float(x) for x in ratios])
+    check(_lib.lib().sdet_gen_anchor(_p(out), H, W, int(feature_stride), sc, len(scales), ra, len(ratios), _stream()))
+    return out
+
+
+def GenProposal(cls_prob, bbox_pred, im_info, anchors, rpn_pre_nms_top_n=6000, rpn_min_size=16, feature_stride=16,
+                iou_loss=False):
+    """mx.sym.contrib.GenProposal (generate_proposal.cu): sorted pre-NMS proposals (B, pre, 5), no NMS."""
+    cls_prob, bbox_pred, im_info = _dev(cls_prob, "cls_prob"), _dev(bbox_pred, "bbox_pred"), _dev(im_info, "im_info")
+    anchors = _dev(anchors, "anchors")
+    B, A2, H, W = cls_prob.shape
+    A = A2 // 2
+    if tuple(bbox_pred.shape) != (B, 4 * A, H, W) or anchors.numel() != H * W * A * 4:
+        raise ValueError("bbox_pred must be (B,4A,H,W) and anchors (H*W*A,4)")
+    out = torch.empty((B, int(rpn_pre_nms_top_n), 5), device=cls_prob.device, dtype=torch.float32)
+    L = _lib.lib()
+    nbytes = L.sdet_gen_proposal_workspace(B, A, H, W, int(rpn_pre_nms_top_n))
+    ws = _ws(nbytes, cls_prob.device)
+    check(L.sdet_gen_proposal(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(anchors), _p(out), B, A, H, W,
+                              int(feature_stride), int(rpn_pre_nms_top_n), int(rpn_min_size), int(bool(iou_loss)),
+                              _p(ws), nbytes, _stream()))
+    return out
+
+
+def GenProposalRetina(cls_prob, bbox_pred, im_info, anchors, num_anchors, feature_stride=16, rpn_pre_nms_top_n=6000,
+                      rpn_min_size=16, thresh=0.0, anchor_mean=(0.0, 0.0, 0.0, 0.0), anchor_std=(1.0, 1.0, 1.0, 1.0),
+                      iou_loss=False, output_one_hot=True, batch_wise_anchor=False, workspace=None):
+    """mx.sym.contrib.GenProposalRetina (models/retinanet/builder.py:374-387) -> (bbox_xyxy, cls_score)."""
+    cls_prob, bbox_pred, im_info = _dev(cls_prob, "cls_prob"), _dev(bbox_pred, "bbox_pred"), _dev(im_info, "im_info")
+    anchors = _dev(anchors, "anchors")
+    B, AK, H, W = cls_prob.shape
+    if AK % num_anchors:
+        raise ValueError("cls_prob channels must be a multiple of num_anchors")
+    if tuple(bbox_pred.shape) != (B, 4 * num_anchors, H, W):
+        raise ValueError("bbox_pred must be (B, 4*num_anchors, H, W)")
+    K = AK // num_anchors
+    oc = K + 1 if output_one_hot else 1
+    pre = int(rpn_pre_nms_top_n)
+    out = torch.empty((B, pre, 4), device=cls_prob.device, dtype=torch.float32)
+    score = torch.empty((B, pre, oc), device=cls_prob.device, dtype=torch.float32)
+    L = _lib.lib()
+    nbytes = L.sdet_gen_proposal_retina_workspace(B, AK, H, W)
+    ws = _ws(nbytes, cls_prob.device)
+    m = (ctypes.c_float * 4)(*[float(x) for x in anchor_mean])
+    sd = (ctypes.c_float * 4)(*[float(x) for x in anchor_std])
+    check(L.sdet_gen_proposal_retina(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(anchors), _p(out), _p(score), B, AK,
+                                     H, W, int(num_anchors), int(feature_stride), pre, int(rpn_min_size),
+                                     float(thresh), m, sd, int(bool(iou_loss)), int(bool(output_one_hot)),
+                                     int(bool(batch_wise_anchor)), _p(ws), nbytes, _stream()))
+    return out, score
 
 
 def Proposal_v3_fpn(cls_probs, bbox_preds, im_info, feature_strides, rpn_pre_nms_top_n=6000,
@@ -764,6 +869,11 @@ OPS = {
     "fpn_roi_align": fpn_roi_align,  # fusion of assign_layer_fpn + ROIAlign_v2 x L + add_n
     "_contrib_DecodeBBox": DecodeBBox,
     "_contrib_Proposal_v3": Proposal_v3,
+    "_contrib_Proposal": Proposal,
+    "_contrib_GenAnchor": GenAnchor,
+    "_contrib_GenProposal": GenProposal,
+    "_contrib_GenProposalRetina": GenProposalRetina,
+    "_contrib_Proposal_v2": Proposal_v2,
     "_contrib_NMS": NMS,
     "ProposalTarget": ProposalTarget,
     "ProposalMaskTarget": ProposalMaskTarget,

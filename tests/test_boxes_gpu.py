@@ -192,3 +192,92 @@ def test_proposal_v3_fpn_equals_per_level_concat(cuda):
                                   strides, **kw)
     assert np.array_equal(sc.cpu().numpy(), rs)
     np.testing.assert_allclose(out.cpu().numpy(), rb, rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("version,is_train,filt", [(1, False, False), (1, True, False), (2, False, True)])
+def test_proposal_legacy(cuda, version, is_train, filt):
+    """_contrib_Proposal / _contrib_Proposal_v2: filter and padded-cell mask BEFORE the sort."""
+    rng = np.random.default_rng(40 + version)
+    B, A, H, W, stride = 2, 12, 38, 50, 16
+    cls = rng.uniform(0, 1, (B, 2 * A, H, W)).astype(np.float32)
+    deltas = (rng.standard_normal((B, 4 * A, H, W)) * 0.4).astype(np.float32)
+    deltas[:, 2::4] -= 1.0  # shrink many boxes below rpn_min_size
+    im_info = np.array([[H * stride - 40, W * stride - 64, 1.0], [H * stride, W * stride, 1.5]], np.float32)
+    vr = np.array([[0, 200], [60, 1e5]], np.float32)
+    kw = dict(feature_stride=stride, scales=(2, 4, 8, 16), ratios=(0.5, 1, 2), rpn_pre_nms_top_n=3000,
+              rpn_post_nms_top_n=400, threshold=0.7, rpn_min_size=16)
+    ro, rs = oracle.proposal_legacy(cls, deltas, im_info, version=version, valid_ranges=vr, is_train=is_train,
+                                    filter_scales=filt, **kw)
+    if version == 1:
+        out, sc = ops.Proposal(_t(cls, cuda), _t(deltas, cuda), _t(im_info, cuda), output_score=True,
+                               is_train=is_train, **kw)
+    else:
+        out, sc = ops.Proposal_v2(_t(cls, cuda), _t(deltas, cuda), _t(im_info, cuda), _t(vr, cuda),
+                                  output_score=True, filter_scales=filt, **kw)
+    assert out.shape == ro.shape
+    assert np.array_equal(sc.cpu().numpy(), rs)
+    np.testing.assert_allclose(out.cpu().numpy(), ro, rtol=1e-5, atol=1e-3)
+
+
+def test_gen_anchor(cuda):
+    for (H, W, stride) in [(100, 168, 8), (7, 11, 128), (1, 1, 64)]:
+        scales = tuple(4 * 2 ** (i / 3) for i in range(3))  # retinanet: 3 octave scales (non-integer doubles)
+        ref = oracle.gen_anchor(H, W, stride, scales, (0.5, 1, 2))
+        got = ops.GenAnchor(torch.empty((1, 9, H, W), device=cuda), scales=scales, ratios=(0.5, 1, 2),
+                            feature_stride=stride)
+        assert np.array_equal(got.cpu().numpy(), ref)
+
+
+def test_gen_proposal(cuda):
+    rng = np.random.default_rng(51)
+    B, A, H, W, stride = 2, 9, 25, 34, 16
+    cls = rng.uniform(0, 1, (B, 2 * A, H, W)).astype(np.float32)
+    deltas = (rng.standard_normal((B, 4 * A, H, W)) * 0.4).astype(np.float32)
+    deltas[:, 2::4] -= 0.8
+    im_info = np.array([[H * stride - 30, W * stride - 50, 1.0], [H * stride, W * stride, 2.0]], np.float32)
+    anchors = oracle.gen_anchor(H, W, stride, (2, 4, 8), (0.5, 1, 2))
+    for pre in (2000, A * H * W + 50):
+        ref = oracle.gen_proposal(cls, deltas, im_info, anchors, feature_stride=stride, rpn_pre_nms_top_n=pre,
+                                  rpn_min_size=8)
+        got = ops.GenProposal(_t(cls, cuda), _t(deltas, cuda), _t(im_info, cuda), _t(anchors, cuda),
+                              feature_stride=stride, rpn_pre_nms_top_n=pre, rpn_min_size=8).cpu().numpy()
+        assert np.array_equal(got[..., 4], ref[..., 4])
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("thresh,K", [(0.05, 80), (0.0, 80), (0.3, 1)])
+def test_gen_proposal_retina(cuda, thresh, K):
+    rng = np.random.default_rng(52)
+    B, A, H, W, stride = 2, 9, 13, 21, 32
+    cls = (rng.uniform(0, 1, (B, A * K, H, W)) ** 4).astype(np.float32)  # mostly below thresh, like sigmoid outputs
+    cls[0, :4] = cls[0, 4:8]  # exact score ties -> order by reference index
+    deltas = (rng.standard_normal((B, 4 * A, H, W)) * 0.5).astype(np.float32)
+    im_info = np.array([[H * stride - 20, W * stride - 40, 1.0], [H * stride, W * stride, 1.6]], np.float32)
+    scales = tuple(4 * 2 ** (i / 3) for i in range(3))
+    anchors = oracle.gen_anchor(H, W, stride, scales, (0.5, 1, 2))
+    kw = dict(num_anchors=A, rpn_pre_nms_top_n=1000, rpn_min_size=40, thresh=thresh,
+              anchor_mean=(0.0, 0.1, 0.0, -0.1), anchor_std=(0.1, 0.1, 0.2, 0.2))
+    rb, rs = oracle.gen_proposal_retina(cls, deltas, im_info, anchors, **kw)
+    gb, gs = ops.GenProposalRetina(_t(cls, cuda), _t(deltas, cuda), _t(im_info, cuda), _t(anchors, cuda),
+                                   feature_stride=stride, **kw)
+    assert gs.shape == rs.shape == (B, 1000, K + 1)
+    assert np.array_equal(gs.cpu().numpy(), rs)
+    np.testing.assert_allclose(gb.cpu().numpy(), rb, rtol=1e-5, atol=1e-3)
+    assert (rs > 0).any()
+
+
+def test_gen_proposal_retina_few_survivors(cuda):
+    """Fewer survivors than rpn_pre_nms_top_n (and none at all): remaining rows are all-zero."""
+    rng = np.random.default_rng(53)
+    B, A, K, H, W = 2, 9, 80, 4, 6
+    cls = rng.uniform(0, 0.04, (B, A * K, H, W)).astype(np.float32)
+    cls[0, 7, 1, 2] = 0.9
+    cls[0, 85, 3, 5] = 0.5
+    deltas = np.zeros((B, 4 * A, H, W), np.float32)
+    im_info = np.array([[512, 768, 1.0]] * 2, np.float32)
+    anchors = oracle.gen_anchor(H, W, 128, (4, 5, 6), (0.5, 1, 2))
+    kw = dict(num_anchors=A, rpn_pre_nms_top_n=1000, rpn_min_size=0, thresh=0.05)
+    rb, rs = oracle.gen_proposal_retina(cls, deltas, im_info, anchors, **kw)
+    gb, gs = ops.GenProposalRetina(_t(cls, cuda), _t(deltas, cuda), _t(im_info, cuda), _t(anchors, cuda), **kw)
+    assert np.array_equal(gs.cpu().numpy(), rs) and np.array_equal(gb.cpu().numpy(), rb)
+    assert np.count_nonzero(rs) == 2
