@@ -240,6 +240,9 @@ struct ProposalLevel {
   const float* bbox_pred;  // (B, 4A, H, W)
   float anchors[kMaxAnchors * 4];  // base anchors of this stride, proposal_v3-inl.h:280-318
   int H, W, stride, pre;   // pre = min(rpn_pre_nms_top_n, A*H*W) of this level
+  int nchunks;             // > 1: the level is pre-selected chunk by chunk (proposal_chunk_topk_kernel)
+  int chunk_base;          // first CTA of this level in the chunk kernel's grid
+  size_t cand_off;         // offset (keys) of this level's candidates: [b][chunk][pre]
 };
 struct ProposalParams {
   ProposalLevel lvl[SDET_MAX_LEVELS];
@@ -249,7 +252,49 @@ struct ProposalParams {
   int min_size;
   float* dets;             // (num_levels*B, pre_max, 5), problem p = l*B + b
   int* counts;             // (num_levels*B) = pre of the level
+  unsigned long long* cand;  // chunk winners (keys), zero-padded
 };
+
+// Large levels (P2 of an 800x1333 image has 201 600 anchors) would leave one CTA sweeping the whole
+// score map while 147 SMs idle.  They are split into chunks of kChunkElems scores: every chunk's
+// CTA selects its own top-`pre` keys; the per-problem CTA then selects among nchunks*pre keys.
+// Exact: the top-k of a union is contained in the union of the parts' top-k, and keys are unique.
+constexpr int kChunkElems = 16384;
+inline int level_chunks(int count) { return count > 2 * kChunkElems ? (count + kChunkElems - 1) / kChunkElems : 1; }
+
+__device__ __forceinline__ uint64_t proposal_key(const float* fg, int i, int HW, int A, unsigned magic) {
+  // element i is visited in MEMORY order (a, h, w) for coalescing; its reference index (the
+  // stable-sort tie breaker) is (h*W + w)*A + a  (ProposalGridKernel, :73-75)
+  int a = (int)__umulhi((unsigned)i, magic), r = i - a * HW;  // a = i / HW without a divide (+ fix-up)
+  while (r >= HW) {
+    r -= HW;
+    ++a;
+  }
+  return sdet::make_key(__ldg(fg + i), (uint32_t)(r * A + a));
+}
+
+__global__ void __launch_bounds__(kTopkThreads)
+proposal_chunk_topk_kernel(const __grid_constant__ ProposalParams p) {
+  extern __shared__ unsigned long long s_sel[];
+  __shared__ uint32_t s_hist[sdet::kRadixBins];
+  int l = 0;
+  for (int i = 1; i < p.num_levels; ++i)
+    if (p.lvl[i].nchunks > 1 && (int)blockIdx.x >= p.lvl[i].chunk_base) l = i;
+  while (p.lvl[l].nchunks <= 1) ++l;  // (the first chunked level, when blockIdx.x precedes every later base)
+  const ProposalLevel& L = p.lvl[l];
+  const int rel = blockIdx.x - L.chunk_base;
+  const int b = rel / L.nchunks, chunk = rel - b * L.nchunks;
+  const int A = p.A, HW = L.H * L.W, count = A * HW, pre = L.pre;
+  const float* fg = L.cls_prob + (size_t)b * 2 * count + count;
+  const unsigned magic = 0xFFFFFFFFu / (unsigned)HW;
+  const int i0 = chunk * kChunkElems;
+  const int n = min(kChunkElems, count - i0);
+  auto key_at = [&](int i) -> uint64_t { return proposal_key(fg, i0 + i, HW, A, magic); };
+  const int k = min(pre, n);
+  sdet::block_topk_sorted(n, k, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+  unsigned long long* dst = p.cand + L.cand_off + ((size_t)b * L.nchunks + chunk) * pre;
+  for (int j = threadIdx.x; j < pre; j += blockDim.x) dst[j] = (j < k) ? s_sel[j] : 0ull;  // 0 < every real key
+}
 
 __global__ void __launch_bounds__(kTopkThreads)
 proposal_topk_kernel(const __grid_constant__ ProposalParams p) {
@@ -261,18 +306,15 @@ proposal_topk_kernel(const __grid_constant__ ProposalParams p) {
   const int A = p.A, H = L.H, W = L.W, HW = H * W;
   const int count = A * HW, pre = L.pre;
   const float* fg = L.cls_prob + (size_t)b * 2 * count + count;  // second half = foreground (:522)
-  // element i is visited in MEMORY order (a, h, w) for coalescing; its reference index (the
-  // stable-sort tie breaker) is (h*W + w)*A + a  (ProposalGridKernel, :73-75)
-  const unsigned magic = 0xFFFFFFFFu / (unsigned)HW;  // a = i / HW without a divide (+ fix-up)
-  auto key_at = [&](int i) -> uint64_t {
-    int a = (int)__umulhi((unsigned)i, magic), r = i - a * HW;
-    while (r >= HW) {
-      r -= HW;
-      ++a;
-    }
-    return sdet::make_key(__ldg(fg + i), (uint32_t)(r * A + a));
-  };
-  sdet::block_topk_sorted(count, pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+  if (L.nchunks > 1) {  // chunk winners, written by proposal_chunk_topk_kernel
+    const unsigned long long* cand = p.cand + L.cand_off + (size_t)b * L.nchunks * pre;
+    auto key_at = [&](int i) -> uint64_t { return cand[i]; };
+    sdet::block_topk_sorted(L.nchunks * pre, pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+  } else {
+    const unsigned magic = 0xFFFFFFFFu / (unsigned)HW;
+    auto key_at = [&](int i) -> uint64_t { return proposal_key(fg, i, HW, A, magic); };
+    sdet::block_topk_sorted(count, pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+  }
   if (threadIdx.x == 0) p.counts[prob] = pre;
   // decode only the winners
   const float im_h = __ldg(p.im_info + b * 3), im_w = __ldg(p.im_info + b * 3 + 1);
@@ -566,12 +608,23 @@ static int level_pre(int A, int H, int W, int rpn_pre_nms_top_n) {
   return pre > count ? count : pre;
 }
 
+static size_t proposal_cand_keys(int B, int A, const int* H, const int* W, int num_levels, int rpn_pre_nms_top_n) {
+  size_t keys = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    const int nch = level_chunks(A * H[l] * W[l]);
+    if (nch > 1) keys += (size_t)B * nch * level_pre(A, H[l], W[l], rpn_pre_nms_top_n);
+  }
+  return keys;
+}
+
+
 extern "C" size_t sdet_proposal_v3_fpn_workspace(int B, int A, const int* H, const int* W, int num_levels,
                                                  int rpn_pre_nms_top_n) {
   if (B <= 0 || A <= 0 || !H || !W || num_levels <= 0) return 0;
   int pre_max = 0;
   for (int l = 0; l < num_levels; ++l) pre_max = std::max(pre_max, level_pre(A, H[l], W[l], rpn_pre_nms_top_n));
-  return proposal_ws_bytes(B * num_levels, pre_max);
+  return proposal_ws_bytes(B * num_levels, pre_max) +
+         align_up(proposal_cand_keys(B, A, H, W, num_levels, rpn_pre_nms_top_n) * 8, 256);
 }
 
 extern "C" int sdet_proposal_v3_fpn(const float* const* cls_prob, const float* const* bbox_pred,
@@ -594,7 +647,8 @@ extern "C" int sdet_proposal_v3_fpn(const float* const* cls_prob, const float* c
   SDET_REQUIRE(rpn_post_nms_top_n > 0, "rpn_post_nms_top_n must be > 0");
   cudaStream_t st = (cudaStream_t)stream;
   ProposalParams p{};
-  int pre_max = 0, pre_min = INT_MAX;
+  int pre_max = 0, pre_min = INT_MAX, chunk_ctas = 0;
+  size_t cand_keys = 0;
   for (int l = 0; l < num_levels; ++l) {
     SDET_REQUIRE(cls_prob[l] && bbox_pred[l] && H[l] > 0 && W[l] > 0, "level %d: bad pointer / shape", l);
     ProposalLevel& L = p.lvl[l];
@@ -605,6 +659,13 @@ extern "C" int sdet_proposal_v3_fpn(const float* const* cls_prob, const float* c
     gen_anchors_v3(feature_stride[l], ratios, num_ratios, scales, num_scales, L.anchors);
     pre_max = std::max(pre_max, L.pre);
     pre_min = std::min(pre_min, L.pre);
+    L.nchunks = level_chunks(A * H[l] * W[l]);
+    L.chunk_base = chunk_ctas;
+    L.cand_off = cand_keys;
+    if (L.nchunks > 1) {
+      chunk_ctas += B * L.nchunks;
+      cand_keys += (size_t)B * L.nchunks * L.pre;
+    }
   }
   // rows per level in the output: `post` (:472-475); with is_train it depends on the level's pre
   int post = rpn_post_nms_top_n;
@@ -614,8 +675,8 @@ extern "C" int sdet_proposal_v3_fpn(const float* const* cls_prob, const float* c
       return sdet::fail(SDET_ERR_UNSUPPORTED, "is_train with levels smaller than rpn_post_nms_top_n");
   }
   const int P = B * num_levels;
-  if (workspace_bytes < proposal_ws_bytes(P, pre_max))
-    return sdet::fail(SDET_ERR_WORKSPACE, "workspace too small: need %zu bytes", proposal_ws_bytes(P, pre_max));
+  const size_t need = proposal_ws_bytes(P, pre_max) + align_up(cand_keys * 8, 256);
+  if (workspace_bytes < need) return sdet::fail(SDET_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
   char* wsb = static_cast<char*>(workspace);
   float* dets = reinterpret_cast<float*>(wsb);
   auto* mask = reinterpret_cast<unsigned long long*>(wsb + align_up((size_t)P * pre_max * 5 * 4, 256));
@@ -627,8 +688,14 @@ extern "C" int sdet_proposal_v3_fpn(const float* const* cls_prob, const float* c
   p.min_size = rpn_min_size;
   p.dets = dets;
   p.counts = counts;
-  static size_t configured = 0;
+  p.cand = reinterpret_cast<unsigned long long*>(wsb + proposal_ws_bytes(P, pre_max));
+  static size_t configured = 0, configured_chunk = 0;
   const size_t smem = (size_t)p.k_pow2 * 8;
+  if (chunk_ctas > 0) {
+    if (int rc = ensure_smem(proposal_chunk_topk_kernel, smem, &configured_chunk)) return rc;
+    proposal_chunk_topk_kernel<<<(unsigned)chunk_ctas, kTopkThreads, smem, st>>>(p);
+    SDET_LAUNCH_CHECK("proposal_chunk_topk_kernel");
+  }
   if (int rc = ensure_smem(proposal_topk_kernel, smem, &configured)) return rc;
   proposal_topk_kernel<<<(unsigned)P, kTopkThreads, smem, st>>>(p);
   SDET_LAUNCH_CHECK("proposal_topk_kernel");

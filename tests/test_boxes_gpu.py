@@ -87,7 +87,8 @@ def test_nms_sorted_counts_and_identical_boxes(cuda):
 
 @pytest.mark.parametrize("is_train", [False, True])
 @pytest.mark.parametrize("hw,stride,pre,post", [((50, 84), 16, 1000, 1000), ((25, 42), 32, 2000, 2000),
-                                               ((100, 167), 8, 2000, 300)])
+                                               ((100, 167), 8, 2000, 300),
+                                               ((200, 336), 4, 1000, 1000)])  # chunked pre-selection
 def test_proposal_v3(cuda, is_train, hw, stride, pre, post):
     rng = np.random.default_rng(pre + hw[0])
     B, A = 2, 3
