@@ -220,7 +220,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import __graft_entry__ as g
-    from simpledet_b200 import _lib, ops
+    from simpledet_b200 import _lib, ops, shard
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -266,33 +266,65 @@ def run_ours(args):
         e1.record()
         sync_all()
     launches = _lib.launch_count() - n0
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = shard.max_over_ranks(e0.elapsed_time(e1), dev)
     ra_us = float(np.mean([a.elapsed_time(b) for a, b in kev])) * 1e3
 
     # ---- end to end through the public API with HOST buffers (`e2e`) ----
-    def e2e_step(i):
-        d = {k: v.to(dev, non_blocking=True) for k, v in pinned[i % R].items()}
-        rois, roi_feat, dets, counts, keep, nkeep = hot_path_step(ops, d)
-        res = [x.to("cpu", non_blocking=True) for x in (dets, counts, keep, nkeep)]
-        return res
+    # Every step copies its inputs from pinned host memory and reads its detections back into pinned
+    # host memory; all of it is inside the timed region.  Steps are independent images, so the copy of
+    # step i+1 runs on a second stream while step i computes (two device input slots, event-ordered).
+    main = torch.cuda.current_stream()
+    copy_s, back_s = torch.cuda.Stream(), torch.cuda.Stream()
+    slots = [{k: torch.empty_like(v, device=dev) for k, v in pinned[0].items()} for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    host_out = [None, None]
+    done_ev = [torch.cuda.Event() for _ in range(2)]
 
-    for i in range(2):
-        res = e2e_step(i)
+    def e2e_upload(i):
+        j = i % 2
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(consumed[j])  # the step that last read this slot has finished
+            for k, v in pinned[i % R].items():
+                slots[j][k].copy_(v, non_blocking=True)
+            copied[j].record(copy_s)
+
+    def e2e_compute(i):
+        j = i % 2
+        main.wait_event(copied[j])
+        rois, roi_feat, dets, counts, keep, nkeep = hot_path_step(ops, slots[j])
+        consumed[j].record(main)
+        res = (dets, counts, keep, nkeep)
+        if host_out[j] is None:
+            host_out[j] = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in res]
+        done_ev[j].record(main)
+        with torch.cuda.stream(back_s):
+            back_s.wait_event(done_ev[j])
+            for h, x in zip(host_out[j], res):
+                x.record_stream(back_s)
+                h.copy_(x, non_blocking=True)
+        return host_out[j]
+
+    def e2e_run(n):
+        for ev in consumed:
+            ev.record(main)
+        e2e_upload(0)
+        for i in range(n):
+            if i + 1 < n:
+                e2e_upload(i + 1)
+            res_ = e2e_compute(i)
+        main.wait_stream(back_s)
+        main.wait_stream(copy_s)
+        return res_
+
+    res = e2e_run(3)
     d2h_bytes = sum(x.numel() * x.element_size() for x in res)
     sync_all()
     e0.record()
-    for i in range(K):
-        e2e_step(i)
+    e2e_run(K)
     e1.record()
     sync_all()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_ms = shard.max_over_ranks(e0.elapsed_time(e1), dev)
 
     if rank != 0:
         if world > 1:

@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(64) roi_align_plan_kernel(const __grid_constan
 
 // kCapFloats: floats of dynamic shared memory for the window buffers (12288 = 48 KB -> 4 CTAs/SM)
 template <int CPT, bool kArg, int kPH, int kPW, int kCapFloats>
-__global__ void __launch_bounds__(128, (kCapFloats <= 7680 ? 6 : (kCapFloats <= 9216 ? 5 : (kCapFloats <= 12288 ? 4 : 3))))
-roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles, const int mode_pref) {
+__global__ void __launch_bounds__(128, 4)
+roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles) {
   extern __shared__ __align__(16) float s_win[];
   constexpr int TP = (kPH > 0 && kPH <= 16 && kPW <= 16) ? 16 : kMaxP;
   __shared__ __align__(16) AxisTab<TP> s_th, s_tw;
@@ -388,7 +388,7 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles,
   constexpr int CS0 = kCapFloats / (4 * CPT), CS1 = kCapFloats / (2 * CPT), CS3 = kCapFloats / CPT;
   int mode = -1;
   if (plane <= CS0) mode = 0;
-  else if (plane <= CS1) mode = (mode_pref & 1) ? 2 : 1;
+  else if (plane <= CS1) mode = 1;
   else if (plane <= CS3) mode = 3;
   const bool fast = any && ((flags & (kFlagNot2 | kFlagOverflow)) == 0) && (PW <= 16) && (Wp <= 64) && (Hwin <= 128) &&
                     (mode >= 0) && ((cgrp1 - cgrp0) % (2 * CPT) == 0);
@@ -487,13 +487,16 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles,
     // thread = (row slot, 16B chunk) of the window; it walks the tile's channels with constant
     // strides (global: HW floats, shared: kCS floats = an immediate), so the per-copy cost is
     // one 64-bit add + one LDGSTS.
-    const int nchm = Wp >> 2;                                   // max 16B chunks per row
-    const int lpr_log2 = nchm <= 4 ? 2 : (nchm <= 8 ? 3 : 4);   // lanes per row (4 / 8 / 16)
-    const int rslot = tid >> lpr_log2, jchunk = tid & ((1 << lpr_log2) - 1);
-    const int rpp = 128 >> lpr_log2;                            // rows per pass
+    // The (row, chunk) items of the window are flattened over the CTA's threads, so a pass of 128
+    // threads copies 128 useful chunks whatever the window's aspect (an LDGSTS costs the same LSU
+    // time with 1 or 32 active lanes).
+    const int nch = vec ? ((Wwin + 3 + 3) >> 2) : (Wp >> 2);    // 16B chunks per row (upper bound)
+    const int nitems = Hwin * nch;
+    const unsigned nch_magic = 0xFFFFFFFFu / (unsigned)nch + 1u; // idx / nch for idx < 2^16
     auto stage = [&](int tile, unsigned buf) {
       const float* g0 = gimg + (size_t)(cgrp0 + tile * CTILE) * HW;
-      for (int y = rslot; y < Hwin; y += rpp) {
+      for (int idx = tid; idx < nitems; idx += 128) {
+        const int y = (int)__umulhi((unsigned)idx, nch_magic), jchunk = idx - y * nch;
         const int e0 = (hmin + y) * W + wmin;  // first wanted element inside the plane
         unsigned dst = buf + 4u * (unsigned)(y * Wp + jchunk * 4);
         if (vec) {
@@ -655,20 +658,6 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles,
     };
 
     // ---- software pipeline over the channel tiles of this roi ----
-    const bool dbg_nostage = (mode_pref & 2) != 0, dbg_nocompute = (mode_pref & 4) != 0;  // profiling only
-    if (dbg_nostage || dbg_nocompute) {
-      for (int t = 0; t < ntiles; ++t) {
-        if (!dbg_nostage) {
-          stage(t, sbase);
-          cp_async_commit();
-          cp_async_wait<0>();
-        }
-        __syncthreads();
-        if (!dbg_nocompute) compute(t, sbase);
-        __syncthreads();
-      }
-      return;
-    }
     stage(0, sbase);
     cp_async_commit();
     for (int t = 0; t < ntiles; ++t) {
@@ -697,8 +686,6 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles,
     run(integral_constant<int, CS0>{}, integral_constant<int, 2>{}, integral_constant<int, 2>{});
   else if (mode == 1)
     run(integral_constant<int, CS1>{}, integral_constant<int, 2>{}, integral_constant<int, 1>{});
-  else if (mode == 2)
-    run(integral_constant<int, CS1>{}, integral_constant<int, 1>{}, integral_constant<int, 2>{});
   else
     run(integral_constant<int, CS3>{}, integral_constant<int, 1>{}, integral_constant<int, 1>{});
 
@@ -776,16 +763,13 @@ int launch_fwd_t(const RoiAlignArgs& a, cudaStream_t st) {
   const int total_tiles = (a.C + CT - 1) / CT;
   const long long jobs = (long long)a.B * a.N * total_tiles;
   int tpc = (int)(jobs / (148 * 12));
-  int mode_pref = 0;
-  if (const char* e = getenv("SDET_RA_TILES")) tpc = atoi(e);          // tuning only
-  if (const char* e = getenv("SDET_RA_MODEPREF")) mode_pref = atoi(e);  // tuning only
   if (tpc < 1) tpc = 1;
   if (tpc > total_tiles) tpc = total_tiles;
   dim3 grid((unsigned)(a.B * a.N), (unsigned)((total_tiles + tpc - 1) / tpc));
   if (arg)
-    k_trn<<<grid, 128, smem_bytes, st>>>(a, tpc, mode_pref);
+    k_trn<<<grid, 128, smem_bytes, st>>>(a, tpc);
   else
-    k_inf<<<grid, 128, smem_bytes, st>>>(a, tpc, mode_pref);
+    k_inf<<<grid, 128, smem_bytes, st>>>(a, tpc);
   SDET_LAUNCH_CHECK("roi_align_v2_fwd_kernel");
   return SDET_OK;
 }
@@ -805,9 +789,6 @@ int launch_fwd(RoiAlignArgs& a, void* workspace, size_t workspace_bytes, cudaStr
     SDET_LAUNCH_CHECK("roi_align_plan_kernel");
     a.plans = workspace;
   }
-  int cap = 0;
-  if (const char* e = getenv("SDET_RA_CAP")) cap = atoi(e);  // tuning only
-  if (cap == 9216 && a.PH == 14 && a.PW == 14) return launch_fwd_t<8, 14, 14, 9216>(a, st);
   if (a.PH == 7 && a.PW == 7) return launch_fwd_t<8, 7, 7, 12288>(a, st);
   if (a.PH == 14 && a.PW == 14) return launch_fwd_t<8, 14, 14, 12288>(a, st);
   return launch_fwd_t<8, 0, 0, 12288>(a, st);
