@@ -320,10 +320,12 @@ def run_ours(args):
     res = e2e_run(3)
     d2h_bytes = sum(x.numel() * x.element_size() for x in res)
     sync_all()
-    e0.record()
-    e2e_run(K)
-    e1.record()
-    sync_all()
+    with ClockSampler(local) as clk2:
+        e0.record()
+        e2e_run(K)
+        e1.record()
+        sync_all()
+    clk.rows += clk2.rows  # clocks are reported over both timed regions
     e2e_ms = shard.max_over_ranks(e0.elapsed_time(e1), dev)
 
     if rank != 0:
@@ -379,7 +381,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images-per-gpu", type=int, default=2)

@@ -346,6 +346,25 @@ int sdet_deformable_col2im(const float* grad_col, const float* data, const float
                            int pad_h, int pad_w, int stride_h, int stride_w, int dilate_h, int dilate_w,
                            int num_deformable_group, void* stream);
 
+/* AnchorTarget2D (core/detection_input.py:353-565) and PyramidAnchorTarget2D (models/FPN/input.py:55-148)
+ * for a batch, on the device.  gt_bbox (B,G,gt_stride) with gt_stride 4 or 5; rows whose x1 == -1 are
+ * padding.  Level l has stride strides[l] and a (long x short) grid oriented by the image (h >= w puts
+ * `long` on the height axis).  scales / aspects are host doubles (the reference computes base anchors in
+ * float64).  Outputs, per image, in the pyramid layout: cls_label (A * S), reg_target and reg_weight
+ * (4A, S) with S = sum_l short_l*long_l — for one level this is AnchorTarget2D's (A*fh*fw) / (4A,fh,fw).
+ * fg_quota = int(pos_fraction * image_anchor), evaluated by the caller in double like the reference.
+ * Sub-sampling disables the surplus anchors with the smallest 32-bit priority (ties: larger anchor
+ * index first); priorities (B, A*S) device or NULL = Philox4x32-10(seed, image*A*S + anchor).
+ * priorities[n] = n reproduces the reference's DEBUG mode. */
+size_t sdet_anchor_target_workspace(int B, int total_anchors, int max_gt);
+int sdet_anchor_target(const float* im_info, const float* gt_bbox, int gt_stride, float* cls_label,
+                       float* reg_target, float* reg_weight, int B, int G, int num_levels,
+                       const int* strides, const int* shorts, const int* longs, const double* scales,
+                       int num_scales, const double* aspects, int num_aspects, float allowed_border,
+                       float neg_thr, float pos_thr, float min_pos_thr, int image_anchor, int fg_quota,
+                       const uint32_t* priorities, unsigned long long seed, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -173,3 +173,95 @@ def deformable_im2col(data, offset, kernel, stride=(1, 1), dilate=(1, 1), pad=(0
                          + lh * lw * im[hh_c, wh_c]).astype(f)
                     col[b, c * kh * kw + t] = np.where(inside, v, f(0)).reshape(-1)
     return col
+
+
+# ---------------------------------------------------------------------------------------------
+# AnchorTarget2D (core/detection_input.py:353-565) and PyramidAnchorTarget2D (models/FPN/input.py:55-148)
+# ---------------------------------------------------------------------------------------------
+def anchor_base(stride, scales, aspects):
+    """base_anchor property (detection_input.py:377-403): (len(aspects)*len(scales), 4) float64,
+    aspect-major; np.round = round-half-even."""
+    side = float(stride)                      # w = h = stride of the (0,0,stride-1,stride-1) cell
+    ctr = 0.5 * (side - 1)
+    asp = np.asarray(aspects, np.float64)
+    wr = np.round(np.sqrt(side * side / asp))
+    hr = np.round(wr * asp)
+    sc = np.asarray(scales, np.float64)
+    ws, hs = np.outer(wr, sc).ravel(), np.outer(hr, sc).ravel()
+    return np.stack([ctr - 0.5 * (ws - 1), ctr - 0.5 * (hs - 1), ctr + 0.5 * (ws - 1), ctr + 0.5 * (hs - 1)], 1)
+
+
+def anchor_grid(fh, fw, stride, base):
+    """v_all_anchor / h_all_anchor (:405-441): float32 shifts + float64 base -> (fh*fw*A, 4) float64,
+    cell-major (y, x), anchor-minor."""
+    sx = np.arange(fw, dtype=np.float32) * stride
+    sy = np.arange(fh, dtype=np.float32) * stride
+    gx, gy = np.meshgrid(sx, sy)
+    cell = np.stack([gx.ravel(), gy.ravel(), gx.ravel(), gy.ravel()], 1)
+    return (cell[:, None, :] + base[None, :, :]).reshape(-1, 4)
+
+
+def anchor_target(im_info, gt_bbox, strides, shorts, longs, scales, aspects, allowed_border, neg_thr, pos_thr,
+                  min_pos_thr, image_anchor, pos_fraction, priorities=None, overlaps_fn=None):
+    """One image.  strides/shorts/longs: sequences over pyramid levels (length 1 = AnchorTarget2D).
+    `priorities` (one float per anchor over ALL levels) replaces np.random.choice in _sample_anchor
+    (:477-494): of the surplus fg (then bg) anchors, the ones with the SMALLEST priority are disabled,
+    ties by larger index first; priorities = arange reproduces the reference's DEBUG mode (the first
+    surplus indices are disabled).  Returns (cls_label (A*sum HW,), reg_target (4A, sum HW),
+    reg_weight (4A, sum HW)) in the pyramid layout of models/FPN/input.py:117-140 — for one level
+    that is AnchorTarget2D's (A*fh*fw,), (4A, fh, fw) memory order."""
+    from . import bbox_overlaps as c_overlaps
+    overlaps_fn = overlaps_fn or c_overlaps
+    h, w = float(im_info[0]), float(im_info[1])
+    vertical = h >= w                                                   # :449, :547-551
+    dims = [(lo, sh) if vertical else (sh, lo) for sh, lo in zip(shorts, longs)]
+    per_level = [anchor_grid(fh, fw, s, anchor_base(s, scales, aspects)) for (fh, fw), s in zip(dims, strides)]
+    anchors = np.concatenate(per_level)
+    n_all = anchors.shape[0]
+    A = len(scales) * len(aspects)
+    gt = np.asarray(gt_bbox, np.float32)
+    gt = gt[gt[:, 0] != -1][:, :4]                                      # :531-535
+    inside = np.flatnonzero((anchors[:, 0] >= -allowed_border) & (anchors[:, 1] >= -allowed_border) &
+                            (anchors[:, 2] < w + allowed_border) & (anchors[:, 3] < h + allowed_border))
+    va = anchors[inside]
+    label = np.full(len(va), -1, np.float32)
+    if len(gt):                                                         # _assign_label_to_anchor :455-475
+        ov = overlaps_fn(va.astype(np.float32), gt)
+        best = ov.max(1)
+        which = ov.argmax(1)
+        per_gt = ov.max(0)
+        hit = ((ov == per_gt[None, :]) & (ov >= min_pos_thr)).any(1)
+        label[best < neg_thr] = 0
+        label[hit] = 1
+        label[best >= pos_thr] = 1
+    else:
+        label[:] = 0
+        which = np.zeros(len(va), np.int64)
+    pr = np.arange(n_all, dtype=np.float64) if priorities is None else np.asarray(priorities, np.float64)
+    pr = pr[inside]
+
+    def cap(value, quota):                                              # _sample_anchor :477-494
+        idx = np.flatnonzero(label == value)
+        if len(idx) > quota:
+            order = np.lexsort((idx, -pr[idx]))                         # priority desc, index asc
+            label[idx[order[quota:]]] = -1
+    cap(1, int(pos_fraction * image_anchor))
+    cap(0, image_anchor - int(np.sum(label == 1)))
+    tgt = np.zeros((len(va), 4), np.float32)
+    wgt = np.zeros((len(va), 4), np.float32)
+    fg = np.flatnonzero(label == 1)
+    if len(fg):                                                         # _cal_anchor_target :496-506
+        tgt[fg] = nonlinear_transform(va[fg], gt[which[fg], :4])
+        wgt[fg] = 1.0
+    all_label = np.full(n_all, -1, np.float32)
+    all_tgt = np.zeros((n_all, 4), np.float32)
+    all_wgt = np.zeros((n_all, 4), np.float32)
+    all_label[inside], all_tgt[inside], all_wgt[inside] = label, tgt, wgt
+    labs, tgts, wgts, o = [], [], [], 0
+    for (fh, fw) in dims:                                               # per-level (h,w,A) -> (A, h*w)
+        n = fh * fw * A
+        labs.append(all_label[o:o + n].reshape(fh * fw, A).T)
+        tgts.append(all_tgt[o:o + n].reshape(fh * fw, A * 4).T)
+        wgts.append(all_wgt[o:o + n].reshape(fh * fw, A * 4).T)
+        o += n
+    return np.concatenate(labs, 1).reshape(-1), np.concatenate(tgts, 1), np.concatenate(wgts, 1)

@@ -62,6 +62,10 @@ _SIGNATURES = {
     "sdet_gen_proposal_retina_workspace": [c_int, c_int, c_int, c_int],
     "sdet_gen_proposal_retina": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_float, POINTER(c_float), POINTER(c_float), c_int, c_int, c_int, _P, c_size_t, _P],
+    "sdet_anchor_target_workspace": [c_int, c_int, c_int],
+    "sdet_anchor_target": [_P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int),
+                           POINTER(c_int), POINTER(c_double), c_int, POINTER(c_double), c_int, c_float, c_float,
+                           c_float, c_float, c_int, c_int, _P, c_uint64, _P, c_size_t, _P],
     "sdet_contrib_nms_workspace": [c_int, c_int, c_int],
     "sdet_contrib_nms": [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P, c_size_t, _P],
     "sdet_get_top_proposal": [_P, _P, _P, _P, c_int, c_int, c_int, _P],
@@ -89,7 +93,7 @@ _SIGNATURES = {
 }
 _RESTYPES = {"sdet_last_error": c_char_p, "sdet_launch_count": c_uint64,
              "sdet_proposal_v3_workspace": c_size_t, "sdet_proposal_legacy_workspace": c_size_t,
-             "sdet_gen_proposal_workspace": c_size_t, "sdet_gen_proposal_retina_workspace": c_size_t, "sdet_proposal_v3_fpn_workspace": c_size_t, "sdet_contrib_nms_workspace": c_size_t,
+             "sdet_gen_proposal_workspace": c_size_t, "sdet_anchor_target_workspace": c_size_t, "sdet_gen_proposal_retina_workspace": c_size_t, "sdet_proposal_v3_fpn_workspace": c_size_t, "sdet_contrib_nms_workspace": c_size_t,
              "sdet_nms_workspace": c_size_t, "sdet_roi_align_v2_workspace": c_size_t, "sdet_multiclass_nms_workspace": c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

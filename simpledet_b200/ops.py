@@ -22,7 +22,7 @@ __all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_r
            "fpn_roi_align", "fpn_roi_align_raw", "DecodeBBox", "Proposal_v3", "Proposal_v3_fpn", "NMS", "nms_sorted", "get_top_proposal",
            "multiclass_nms", "ProposalTarget", "FocalLoss", "BBoxNorm",
            "SigmoidCrossEntropy", "soft_nms", "soft_nms_batched",
-           "cython_soft_nms_wrapper", "DeformableConvolution", "ProposalMaskTarget", "ProposalTarget_v2", "Proposal", "Proposal_v2", "GenAnchor", "GenProposal", "GenProposalRetina", "OPS"]
+           "cython_soft_nms_wrapper", "DeformableConvolution", "ProposalMaskTarget", "ProposalTarget_v2", "Proposal", "Proposal_v2", "GenAnchor", "GenProposal", "GenProposalRetina", "AnchorTarget2D", "PyramidAnchorTarget2D", "OPS"]
 
 
 def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor | None:
@@ -192,6 +192,58 @@ def fpn_roi_align(feats, rois, strides=(4, 8, 16, 32), out_size=7, roi_canonical
     ph, pw = _pair(out_size)
     return _FpnRoiAlignFn.apply(rois, tuple(int(s) for s in strides), ph, pw,
                                 int(roi_canonical_scale), int(roi_canonical_level), *feats)
+
+
+# --------------------------------------------------------------------------------------------
+# AnchorTarget2D / PyramidAnchorTarget2D  (core/detection_input.py:353-565, models/FPN/input.py:55-148)
+# --------------------------------------------------------------------------------------------
+def _seq(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v,)
+
+
+def PyramidAnchorTarget2D(im_info, gt_bbox, stride, short, long, scales, aspects, allowed_border=9999, pos_thr=0.7,
+                          neg_thr=0.3, min_pos_thr=0.0, image_anchor=256, pos_fraction=0.5, priorities=None,
+                          seed=0):
+    """Batched RPN targets.  im_info (B,3), gt_bbox (B,G,4|5) device tensors; stride/short/long per
+    pyramid level (scalars = one level).  Returns rpn_cls_label (B, A*S), rpn_reg_target (B,4A,S),
+    rpn_reg_weight (B,4A,S), S = sum of level cells — the arrays the reference's loader emits per image."""
+    im_info, gt_bbox = _dev(im_info, "im_info"), _dev(gt_bbox, "gt_bbox")
+    strides, shorts, longs = _seq(stride), _seq(short), _seq(long)
+    if not (len(strides) == len(shorts) == len(longs)):
+        raise ValueError("stride / short / long must have one entry per level")
+    if gt_bbox.dim() != 3 or gt_bbox.shape[2] not in (4, 5) or gt_bbox.shape[0] != im_info.shape[0]:
+        raise ValueError("gt_bbox must be (B,G,4) or (B,G,5)")
+    B, G = int(gt_bbox.shape[0]), int(gt_bbox.shape[1])
+    A = len(scales) * len(aspects)
+    S = sum(int(a) * int(b) for a, b in zip(shorts, longs))
+    N = A * S
+    dev = im_info.device
+    label = torch.empty((B, N), device=dev, dtype=torch.float32)
+    target = torch.empty((B, 4 * A, S), device=dev, dtype=torch.float32)
+    weight = torch.empty((B, 4 * A, S), device=dev, dtype=torch.float32)
+    if priorities is not None:
+        if not priorities.is_cuda or priorities.dtype not in (torch.int32, torch.uint32) or priorities.numel() != B * N:
+            raise ValueError("priorities must be a CUDA int32/uint32 tensor with B*A*S elements")
+        priorities = priorities.contiguous()
+    L = _lib.lib()
+    nbytes = L.sdet_anchor_target_workspace(B, N, G)
+    ws = _ws(nbytes, dev)
+    ia = lambda v: (ctypes.c_int * len(v))(*[int(x) for x in v])  # noqa: E731
+    da = lambda v: (ctypes.c_double * len(v))(*[float(x) for x in v])  # noqa: E731
+    check(L.sdet_anchor_target(_p(im_info), _p(gt_bbox), int(gt_bbox.shape[2]), _p(label), _p(target), _p(weight),
+                               B, G, len(strides), ia(strides), ia(shorts), ia(longs), da(scales), len(scales),
+                               da(aspects), len(aspects), float(allowed_border), float(neg_thr), float(pos_thr),
+                               float(min_pos_thr), int(image_anchor), int(pos_fraction * image_anchor),
+                               _p(priorities), int(seed), _p(ws), nbytes, _stream()))
+    return label, target, weight
+
+
+def AnchorTarget2D(im_info, gt_bbox, stride, short, long, scales, aspects, allowed_border=0, **kw):
+    """Single-level variant: rpn_reg_target / weight come back as (B, 4A, fh, fw) with (fh, fw) =
+    (long, short) when h >= w else (short, long) — fixed per call, so one orientation per batch."""
+    label, target, weight = PyramidAnchorTarget2D(im_info, gt_bbox, (stride,), (short,), (long,), scales, aspects,
+                                                  allowed_border=allowed_border, **kw)
+    return label, target, weight
 
 
 # --------------------------------------------------------------------------------------------

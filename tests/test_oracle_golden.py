@@ -1,10 +1,13 @@
 """Pins the oracle: (1) the reference's only known-answer vector for this path — the ROIPooling
 docstring example (operator_cxx/roi_pooling_v1.cc:265-285); (2) a second independent pure-Python
 restatement of ROIAlign_v2 (tests/pyref.py) on a tiny case; (3) structural properties."""
+import os
+
 import numpy as np
 import pytest
 
 import oracle
+import oracle.np_ops
 from tests import pyref
 
 
@@ -95,3 +98,22 @@ def test_roi_pool_backward_routes_to_argmax():
     g = np.ones_like(out)
     grad = oracle.roi_pool_v1_backward(g, idx, rois, data.shape)
     assert grad.sum() == (idx >= 0).sum()
+
+
+# ---- AnchorTarget2D / PyramidAnchorTarget2D: oracle restatement vs the reference classes (DEBUG mode) ----
+_A2D = dict(strides=(16,), shorts=(12,), longs=(18,), scales=(2, 4, 8), aspects=(0.5, 1.0, 2.0), allowed_border=0,
+            neg_thr=0.3, pos_thr=0.7, min_pos_thr=0.0, image_anchor=64, pos_fraction=0.5)
+_P2D = dict(strides=(4, 8, 16, 32), shorts=(40, 20, 10, 5), longs=(60, 30, 15, 8), scales=(8,),
+            aspects=(0.5, 1.0, 2.0), allowed_border=9999, neg_thr=0.3, pos_thr=0.7, min_pos_thr=0.0,
+            image_anchor=256, pos_fraction=0.5)
+ANCHOR_CASES = [("a2d_h", _A2D), ("a2d_v", _A2D), ("a2d_fgcap", dict(_A2D, image_anchor=8, pos_thr=0.5)),
+                ("p2d_h", _P2D), ("p2d_v", _P2D), ("p2d_empty", _P2D)]
+
+
+@pytest.mark.parametrize("tag,cfg", ANCHOR_CASES)
+def test_anchor_target_matches_reference_classes(tag, cfg):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_anchor_target.npz"))
+    lab, tgt, wgt = oracle.np_ops.anchor_target(g[f"{tag}_im_info"], g[f"{tag}_gt"], **cfg)
+    assert np.array_equal(lab, g[f"{tag}_label"])
+    assert np.array_equal(wgt.reshape(-1), g[f"{tag}_weight"].reshape(-1))
+    assert np.array_equal(tgt.reshape(-1), g[f"{tag}_target"].reshape(-1))
