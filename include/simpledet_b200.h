@@ -275,7 +275,8 @@ int sdet_proposal_target_v2(const float* rois, const float* gt_boxes, const floa
                             float bg_thresh_lo, int proposal_without_gt, int class_agnostic,
                             int filter_scales, const float* bbox_mean, const float* bbox_std,
                             const float* bbox_weight, unsigned long long seed, const uint32_t* priorities,
-                            int num_draws, uint32_t* priorities_used, void* stream);
+                            int num_draws, uint32_t* priorities_used, int* gt_index, int* fg_count,
+                            void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * ProposalMaskTarget  (operator_cxx/proposal_mask_target-inl.h:87-130 params, :139-337 Forward;
@@ -345,6 +346,20 @@ int sdet_deformable_col2im(const float* grad_col, const float* data, const float
                            float* grad_offset, int B, int C, int H, int W, int kernel_h, int kernel_w,
                            int pad_h, int pad_w, int stride_h, int stride_w, int dilate_h, int dilate_w,
                            int num_deformable_group, void* stream);
+
+/* operator_py/cython/bbox.pyx:32-73 (mode 0, IoU) and bbox_self.pyx:32-75 (mode 1, intersection over the
+ * area of boxes[n]): boxes (N,4), query_boxes (K,4) -> overlaps (N,K), float32, bit-exact with the
+ * compiled Cython (whose `+ 1` terms are evaluated in double). */
+int sdet_bbox_overlaps(const float* boxes, const float* query_boxes, float* overlaps, int N, int K,
+                       int mode, void* stream);
+/* operator_py/bbox_transform.py:52-78 nonlinear_transform, float64: (N,4),(N,4) -> (N,4). */
+int sdet_bbox_nonlinear_transform(const double* ex_rois, const double* gt_rois, double* targets, int N,
+                                  void* stream);
+/* bbox_transform.py:81-120 nonlinear_pred (iou = 0; dw, dh clipped at log(1000/16)) or :129-161 iou_pred
+ * (iou = 1), optionally followed by clip_boxes(:34-49) to (im_h, im_w).  boxes (N,4) float32,
+ * box_deltas / pred_boxes (N,4K) float64. */
+int sdet_bbox_pred(const float* boxes, const double* box_deltas, double* pred_boxes, int N, int K,
+                   int iou, int clip, double im_h, double im_w, void* stream);
 
 /* AnchorTarget2D (core/detection_input.py:353-565) and PyramidAnchorTarget2D (models/FPN/input.py:55-148)
  * for a batch, on the device.  gt_bbox (B,G,gt_stride) with gt_stride 4 or 5; rows whose x1 == -1 are

@@ -217,6 +217,14 @@ def bbox_overlaps(boxes, query_boxes):
     return out
 
 
+def bbox_selfoverlaps(boxes, query_boxes):
+    """bbox_selfoverlaps_cython (bbox_self.pyx:32-75): intersection / area(boxes[n])."""
+    boxes, query_boxes = _f32(boxes), _f32(query_boxes)
+    out = np.empty((boxes.shape[0], query_boxes.shape[0]), np.float32)
+    lib().oracle_bbox_selfoverlaps(_p(boxes), boxes.shape[0], _p(query_boxes), query_boxes.shape[0], _p(out))
+    return out
+
+
 def greedy_nms(dets, thresh, order=None):
     """greedy_nms (cpu_nms.pyx:37-87) -> kept indices ascending (np.where(suppressed == 0)[0]).
     `order` defaults to the reference's own `scores.argsort()[::-1]`."""

@@ -541,6 +541,27 @@ void oracle_bbox_overlaps(const float* boxes, int N, const float* query, int K, 
   }
 }
 
+
+/* ---- bbox_selfoverlaps_cython (operator_py/cython/bbox_self.pyx:32-75): intersection over the area
+ * of `boxes[n]` (IoA).  Same double promotions as bbox_overlaps above. ---- */
+void oracle_bbox_selfoverlaps(const float* boxes, int N, const float* query, int K, float* overlaps) {
+  memset(overlaps, 0, sizeof(float) * (size_t)N * K);
+  for (int k = 0; k < K; ++k) {
+    const float* q = query + (long)k * 4;
+    for (int n = 0; n < N; ++n) {
+      const float* b = boxes + (long)n * 4;
+      float iw = (float)((double)(fmin_(b[2], q[2]) - fmax_(b[0], q[0])) + 1.0);
+      if (iw > 0) {
+        float ih = (float)((double)(fmin_(b[3], q[3]) - fmax_(b[1], q[1])) + 1.0);
+        if (ih > 0) {
+          float ub = (float)(((double)(b[2] - b[0]) + 1.0) * ((double)(b[3] - b[1]) + 1.0));
+          overlaps[(long)n * K + k] = iw * ih / ub;
+        }
+      }
+    }
+  }
+}
+
 /* ---- greedy_nms (cpu_nms.pyx:37-87).  `order` = scores.argsort()[::-1] is supplied by the
  * caller (numpy's unstable sort decides ties); suppressed (ndets) is the output mask. ---- */
 void oracle_greedy_nms(const float* dets5, int ndets, const long* order, float thresh,

@@ -62,6 +62,9 @@ _SIGNATURES = {
     "sdet_gen_proposal_retina_workspace": [c_int, c_int, c_int, c_int],
     "sdet_gen_proposal_retina": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_float, POINTER(c_float), POINTER(c_float), c_int, c_int, c_int, _P, c_size_t, _P],
+    "sdet_bbox_overlaps": [_P, _P, _P, c_int, c_int, c_int, _P],
+    "sdet_bbox_nonlinear_transform": [_P, _P, _P, c_int, _P],
+    "sdet_bbox_pred": [_P, _P, _P, c_int, c_int, c_int, c_int, c_double, c_double, _P],
     "sdet_anchor_target_workspace": [c_int, c_int, c_int],
     "sdet_anchor_target": [_P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int),
                            POINTER(c_int), POINTER(c_double), c_int, POINTER(c_double), c_int, c_float, c_float,
@@ -77,7 +80,7 @@ _SIGNATURES = {
                              POINTER(c_float), c_uint64, _P, c_int, _P, _P, _P, _P],
     "sdet_proposal_target_v2": [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float,
                                 c_float, c_float, c_float, c_int, c_int, c_int, POINTER(c_float),
-                                POINTER(c_float), POINTER(c_float), c_uint64, _P, c_int, _P, _P],
+                                POINTER(c_float), POINTER(c_float), c_uint64, _P, c_int, _P, _P, _P, _P],
     "sdet_poly_mask_target": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "sdet_focal_loss_forward": [_P, _P, c_size_t, _P],
     "sdet_focal_loss_backward": [_P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float, c_int, _P,

@@ -250,6 +250,7 @@ struct ProposalParams {
   int B, A, num_levels;
   int pre_max, k_pow2;     // row pitch of dets / smem keys (max over levels)
   int min_size;
+  int iou_loss;            // IoUPredKernel (:163-205): additive decode, padded cells score -1 BEFORE the sort
   float* dets;             // (num_levels*B, pre_max, 5), problem p = l*B + b
   int* counts;             // (num_levels*B) = pre of the level
   unsigned long long* cand;  // chunk winners (keys), zero-padded
@@ -262,7 +263,9 @@ struct ProposalParams {
 constexpr int kChunkElems = 16384;
 inline int level_chunks(int count) { return count > 2 * kChunkElems ? (count + kChunkElems - 1) / kChunkElems : 1; }
 
-__device__ __forceinline__ uint64_t proposal_key(const float* fg, int i, int HW, int A, unsigned magic) {
+// (rh, rw) = cells inside the un-padded image, only consulted by the iou_loss path; pass W for rw to disable
+__device__ __forceinline__ uint64_t proposal_key(const float* fg, int i, int HW, int A, unsigned magic, int W = 1,
+                                                 int rh = 0x7FFFFFFF, int rw = 0x7FFFFFFF) {
   // element i is visited in MEMORY order (a, h, w) for coalescing; its reference index (the
   // stable-sort tie breaker) is (h*W + w)*A + a  (ProposalGridKernel, :73-75)
   int a = (int)__umulhi((unsigned)i, magic), r = i - a * HW;  // a = i / HW without a divide (+ fix-up)
@@ -270,7 +273,12 @@ __device__ __forceinline__ uint64_t proposal_key(const float* fg, int i, int HW,
     r -= HW;
     ++a;
   }
-  return sdet::make_key(__ldg(fg + i), (uint32_t)(r * A + a));
+  float sc = __ldg(fg + i);
+  if (rh != 0x7FFFFFFF) {
+    const int h = r / W, w = r - h * W;
+    if (h >= rh || w >= rw) sc = -1.0f;
+  }
+  return sdet::make_key(sc, (uint32_t)(r * A + a));
 }
 
 __global__ void __launch_bounds__(kTopkThreads)
@@ -289,7 +297,12 @@ proposal_chunk_topk_kernel(const __grid_constant__ ProposalParams p) {
   const unsigned magic = 0xFFFFFFFFu / (unsigned)HW;
   const int i0 = chunk * kChunkElems;
   const int n = min(kChunkElems, count - i0);
-  auto key_at = [&](int i) -> uint64_t { return proposal_key(fg, i0 + i, HW, A, magic); };
+  int rh = 0x7FFFFFFF, rw = 0x7FFFFFFF;
+  if (p.iou_loss) {
+    rh = (int)__fdiv_rn(__ldg(p.im_info + b * 3), (float)L.stride);
+    rw = (int)__fdiv_rn(__ldg(p.im_info + b * 3 + 1), (float)L.stride);
+  }
+  auto key_at = [&](int i) -> uint64_t { return proposal_key(fg, i0 + i, HW, A, magic, L.W, rh, rw); };
   const int k = min(pre, n);
   sdet::block_topk_sorted(n, k, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
   unsigned long long* dst = p.cand + L.cand_off + ((size_t)b * L.nchunks + chunk) * pre;
@@ -312,7 +325,12 @@ proposal_topk_kernel(const __grid_constant__ ProposalParams p) {
     sdet::block_topk_sorted(L.nchunks * pre, pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
   } else {
     const unsigned magic = 0xFFFFFFFFu / (unsigned)HW;
-    auto key_at = [&](int i) -> uint64_t { return proposal_key(fg, i, HW, A, magic); };
+    int rh = 0x7FFFFFFF, rw = 0x7FFFFFFF;
+    if (p.iou_loss) {
+      rh = (int)__fdiv_rn(__ldg(p.im_info + b * 3), (float)L.stride);
+      rw = (int)__fdiv_rn(__ldg(p.im_info + b * 3 + 1), (float)L.stride);
+    }
+    auto key_at = [&](int i) -> uint64_t { return proposal_key(fg, i, HW, A, magic, W, rh, rw); };
     sdet::block_topk_sorted(count, pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
   }
   if (threadIdx.x == 0) p.counts[prob] = pre;
@@ -339,16 +357,20 @@ proposal_topk_kernel(const __grid_constant__ ProposalParams p) {
     const float d0 = __ldg(dl + ((a * 4 + 0) * H + h) * W + w), d1 = __ldg(dl + ((a * 4 + 1) * H + h) * W + w);
     const float d2 = __ldg(dl + ((a * 4 + 2) * H + h) * W + w), d3 = __ldg(dl + ((a * 4 + 3) * H + h) * W + w);
     const float mx = __fsub_rn(im_w, 1.0f), my = __fsub_rn(im_h, 1.0f);
-    // BBoxPredKernel :93-155
-    const float width = __fadd_rn(__fsub_rn(bx2, bx1), 1.0f), height = __fadd_rn(__fsub_rn(by2, by1), 1.0f);
-    const float ctr_x = __fadd_rn(bx1, __fmul_rn(0.5f, width)), ctr_y = __fadd_rn(by1, __fmul_rn(0.5f, height));
-    const float dw = (float)fmin((double)d2, 4.135166556742356), dh = (float)fmin((double)d3, 4.135166556742356);
-    const float pcx = __fadd_rn(__fmul_rn(d0, width), ctr_x), pcy = __fadd_rn(__fmul_rn(d1, height), ctr_y);
-    const float pw = __fmul_rn(expf(dw), width), ph = __fmul_rn(expf(dh), height);
-    float x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
-    float y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
-    float x2 = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.0f);
-    float y2 = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), 1.0f);
+    float x1, y1, x2, y2;
+    if (p.iou_loss) {  // IoUPredKernel :163-205
+      x1 = __fadd_rn(bx1, d0); y1 = __fadd_rn(by1, d1); x2 = __fadd_rn(bx2, d2); y2 = __fadd_rn(by2, d3);
+    } else {           // BBoxPredKernel :93-155
+      const float width = __fadd_rn(__fsub_rn(bx2, bx1), 1.0f), height = __fadd_rn(__fsub_rn(by2, by1), 1.0f);
+      const float ctr_x = __fadd_rn(bx1, __fmul_rn(0.5f, width)), ctr_y = __fadd_rn(by1, __fmul_rn(0.5f, height));
+      const float dw = (float)fmin((double)d2, 4.135166556742356), dh = (float)fmin((double)d3, 4.135166556742356);
+      const float pcx = __fadd_rn(__fmul_rn(d0, width), ctr_x), pcy = __fadd_rn(__fmul_rn(d1, height), ctr_y);
+      const float pw = __fmul_rn(expf(dw), width), ph = __fmul_rn(expf(dh), height);
+      x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+      y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+      x2 = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.0f);
+      y2 = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), 1.0f);
+    }
     x1 = fmax_ref(fmin_ref(x1, mx), 0.0f);
     y1 = fmax_ref(fmin_ref(y1, my), 0.0f);
     x2 = fmax_ref(fmin_ref(x2, mx), 0.0f);
@@ -641,9 +663,6 @@ extern "C" int sdet_proposal_v3_fpn(const float* const* cls_prob, const float* c
   SDET_REQUIRE(A == num_scales * num_ratios, "num_anchors (%d) != len(ratios)*len(scales) (%d)", A,
                num_scales * num_ratios);
   if (A > kMaxAnchors) return sdet::fail(SDET_ERR_UNSUPPORTED, "more than %d anchors per cell", kMaxAnchors);
-  if (iou_loss)
-    return sdet::fail(SDET_ERR_UNSUPPORTED,
-                      "iou_loss=True (IoUPredKernel masks padded cells before the sort) is not built yet");
   SDET_REQUIRE(rpn_post_nms_top_n > 0, "rpn_post_nms_top_n must be > 0");
   cudaStream_t st = (cudaStream_t)stream;
   ProposalParams p{};
@@ -686,6 +705,7 @@ extern "C" int sdet_proposal_v3_fpn(const float* const* cls_prob, const float* c
   p.pre_max = pre_max;
   p.k_pow2 = sdet::next_pow2(pre_max);
   p.min_size = rpn_min_size;
+  p.iou_loss = iou_loss ? 1 : 0;
   p.dets = dets;
   p.counts = counts;
   p.cand = reinterpret_cast<unsigned long long*>(wsb + proposal_ws_bytes(P, pre_max));

@@ -6,6 +6,6 @@ thread_local char g_last_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
 }  // namespace sdet
 
-extern "C" int sdet_abi_version(void) { return 2; }
+extern "C" int sdet_abi_version(void) { return 3; }
 extern "C" const char* sdet_last_error(void) { return sdet::g_last_error; }
 extern "C" uint64_t sdet_launch_count(void) { return sdet::g_launches.load(); }

@@ -514,15 +514,15 @@ extern "C" int sdet_proposal_target_v2(const float* rois, const float* gt_boxes,
                                        int proposal_without_gt, int class_agnostic, int filter_scales,
                                        const float* bbox_mean, const float* bbox_std, const float* bbox_weight,
                                        unsigned long long seed, const uint32_t* priorities, int num_draws,
-                                       uint32_t* priorities_used, void* stream) {
+                                       uint32_t* priorities_used, int* gt_index, int* fg_count, void* stream) {
   if (image_rois <= 0 && image_rois != -1)
     return sdet::fail(SDET_ERR_INVALID_ARG, "image_rois must be > 0 or -1");
   if (filter_scales && !valid_ranges) return sdet::fail(SDET_ERR_INVALID_ARG, "filter_scales needs valid_ranges");
   return proposal_target_core(rois, gt_boxes, valid_ranges, rois_out, labels, bbox_targets, bbox_weights,
                               match_gt_ious, kept, B, R, G, num_classes, image_rois, fg_fraction, fg_thresh,
                               bg_thresh_hi, bg_thresh_lo, proposal_without_gt, class_agnostic, filter_scales,
-                              bbox_mean, bbox_std, bbox_weight, seed, priorities, num_draws, priorities_used, nullptr,
-                              nullptr, stream);
+                              bbox_mean, bbox_std, bbox_weight, seed, priorities, num_draws, priorities_used, gt_index,
+                              fg_count, stream);
 }
 
 extern "C" int sdet_poly_mask_target(const float* rois_out, const float* gt_polys, const int* gt_index,

@@ -22,7 +22,8 @@ __all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_r
            "fpn_roi_align", "fpn_roi_align_raw", "DecodeBBox", "Proposal_v3", "Proposal_v3_fpn", "NMS", "nms_sorted", "get_top_proposal",
            "multiclass_nms", "ProposalTarget", "FocalLoss", "BBoxNorm",
            "SigmoidCrossEntropy", "soft_nms", "soft_nms_batched",
-           "cython_soft_nms_wrapper", "DeformableConvolution", "ProposalMaskTarget", "ProposalTarget_v2", "Proposal", "Proposal_v2", "GenAnchor", "GenProposal", "GenProposalRetina", "AnchorTarget2D", "PyramidAnchorTarget2D", "OPS"]
+           "cython_soft_nms_wrapper", "DeformableConvolution", "ProposalMaskTarget", "ProposalTarget_v2", "Proposal", "Proposal_v2", "GenAnchor", "GenProposal", "GenProposalRetina", "AnchorTarget2D", "PyramidAnchorTarget2D", "bbox_overlaps",
+           "nonlinear_transform", "nonlinear_pred", "iou_pred", "OPS"]
 
 
 def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor | None:
@@ -192,6 +193,51 @@ def fpn_roi_align(feats, rois, strides=(4, 8, 16, 32), out_size=7, roi_canonical
     ph, pw = _pair(out_size)
     return _FpnRoiAlignFn.apply(rois, tuple(int(s) for s in strides), ph, pw,
                                 int(roi_canonical_scale), int(roi_canonical_level), *feats)
+
+
+# --------------------------------------------------------------------------------------------
+# operator_py/bbox_transform.py + operator_py/cython/{bbox,bbox_self}.pyx on the device
+# --------------------------------------------------------------------------------------------
+def bbox_overlaps(boxes, query_boxes, mode="iou"):
+    """bbox_overlaps_cython (mode='iou') / bbox_selfoverlaps_cython (mode='ioa'): (N,4),(K,4) -> (N,K)."""
+    boxes, query_boxes = _dev(boxes, "boxes"), _dev(query_boxes, "query_boxes")
+    N, K = int(boxes.shape[0]), int(query_boxes.shape[0])
+    out = torch.empty((N, K), device=boxes.device, dtype=torch.float32)
+    check(_lib.lib().sdet_bbox_overlaps(_p(boxes), _p(query_boxes), _p(out), N, K, {"iou": 0, "ioa": 1}[mode],
+                                        _stream()))
+    return out
+
+
+def nonlinear_transform(ex_rois, gt_rois):
+    """bbox_transform.nonlinear_transform in float64: (N,4),(N,4) -> (N,4)."""
+    ex_rois, gt_rois = _dev(ex_rois, "ex_rois", torch.float64), _dev(gt_rois, "gt_rois", torch.float64)
+    if ex_rois.shape != gt_rois.shape:
+        raise ValueError("inconsistent rois number")
+    out = torch.empty_like(ex_rois)
+    check(_lib.lib().sdet_bbox_nonlinear_transform(_p(ex_rois), _p(gt_rois), _p(out), int(ex_rois.shape[0]),
+                                                   _stream()))
+    return out
+
+
+def _bbox_pred(boxes, box_deltas, iou, im_shape):
+    boxes, box_deltas = _dev(boxes, "boxes"), _dev(box_deltas, "box_deltas", torch.float64)
+    N, K4 = int(box_deltas.shape[0]), int(box_deltas.shape[1])
+    out = torch.empty_like(box_deltas)
+    h, w = (float(im_shape[0]), float(im_shape[1])) if im_shape is not None else (0.0, 0.0)
+    check(_lib.lib().sdet_bbox_pred(_p(boxes), _p(box_deltas), _p(out), N, K4 // 4, int(iou),
+                                    int(im_shape is not None), h, w, _stream()))
+    return out
+
+
+def nonlinear_pred(boxes, box_deltas, im_shape=None):
+    """bbox_transform.nonlinear_pred (boxes float32 (N,4), deltas float64 (N,4K)); im_shape=(h,w) fuses
+    clip_boxes."""
+    return _bbox_pred(boxes, box_deltas, False, im_shape)
+
+
+def iou_pred(boxes, box_deltas, im_shape=None):
+    """bbox_transform.iou_pred, optionally fused with clip_boxes."""
+    return _bbox_pred(boxes, box_deltas, True, im_shape)
 
 
 # --------------------------------------------------------------------------------------------
@@ -702,7 +748,8 @@ def SigmoidCrossEntropy(data, label, grad_scale=1.0):
 def ProposalTarget_v2(rois, gt_boxes, valid_ranges, num_classes, batch_images, image_rois, fg_thresh, bg_thresh_hi,
                       bg_thresh_lo, proposal_without_gt, fg_fraction=0.25, class_agnostic=False, output_iou=False,
                       filter_scales=False, bbox_mean=(0.0, 0.0, 0.0, 0.0), bbox_std=(0.1, 0.1, 0.2, 0.2),
-                      bbox_weight=(1.0, 1.0, 1.0, 1.0), seed=None, priorities=None, num_draws=8, return_debug=False):
+                      bbox_weight=(1.0, 1.0, 1.0, 1.0), seed=None, priorities=None, num_draws=8, return_debug=False,
+                      _match_out=None):
     """mx.sym.ProposalTarget_v2 (TridentNet): ProposalTarget + valid_ranges (B,2) / filter_scales,
     and image_rois = -1 to keep every foreground roi (R rows per image)."""
     rois, gt_boxes = _dev(rois, "rois"), _dev(gt_boxes, "gt_boxes")
@@ -733,7 +780,8 @@ def ProposalTarget_v2(rois, gt_boxes, valid_ranges, num_classes, batch_images, i
         R, G, int(num_classes), int(image_rois), float(fg_fraction), float(fg_thresh), float(bg_thresh_hi),
         float(bg_thresh_lo), int(bool(proposal_without_gt)), int(bool(class_agnostic)), int(bool(filter_scales)),
         _f4(bbox_mean, "bbox_mean"), _f4(bbox_std, "bbox_std"), _f4(bbox_weight, "bbox_weight"),
-        int(seed) & (2 ** 64 - 1), _p(priorities), int(num_draws), None, _stream()))
+        int(seed) & (2 ** 64 - 1), _p(priorities), int(num_draws), None,
+        _p(_match_out[0]) if _match_out else None, _p(_match_out[1]) if _match_out else None, _stream()))
     outs = [o_rois, o_lab, o_tgt, o_wgt]
     if output_iou or return_debug:
         outs.append(o_iou)
@@ -746,11 +794,16 @@ def ProposalMaskTarget(rois, gt_boxes, gt_polys, num_classes, batch_images, imag
                        bg_thresh_hi, bg_thresh_lo, proposal_without_gt, fg_fraction=0.25, class_agnostic=False,
                        output_iou=False, output_ratio=False, filter_scales=False, num_args=3,
                        bbox_mean=(0.0, 0.0, 0.0, 0.0), bbox_std=(0.1, 0.1, 0.2, 0.2),
-                       bbox_weight=(1.0, 1.0, 1.0, 1.0), seed=None, priorities=None):
+                       bbox_weight=(1.0, 1.0, 1.0, 1.0), seed=None, priorities=None, valid_ranges=None):
     """mx.sym.ProposalMaskTarget (models/maskrcnn/builder.py:184-203): ProposalTarget's outputs +
-    mask_target (B, int(image_rois*fg_fraction), M, M) with -1 = ignore."""
-    if output_ratio or filter_scales or num_args != 3:
-        raise NotImplementedError("output_ratio / filter_scales / valid_ranges are not built yet")
+    mask_target (B, int(image_rois*fg_fraction), M, M) with -1 = ignore.  filter_scales=True takes the
+    4th input valid_ranges (B,2) (models/tridentnet/builder.py:377-398): gt boxes outside the range are
+    not appended to the candidates (proposal_mask_target-inl.h:222-229)."""
+    if output_ratio:
+        raise NotImplementedError("output_ratio (Mask Scoring R-CNN's mask/box area ratio) is not built")
+    if filter_scales and valid_ranges is None:
+        raise ValueError("filter_scales=True needs valid_ranges (B,2)")
+    del num_args
     gt_polys = _dev(gt_polys, "gt_polys")
     B = int(batch_images)
     IR = int(image_rois)
@@ -759,10 +812,15 @@ def ProposalMaskTarget(rois, gt_boxes, gt_polys, num_classes, batch_images, imag
     dev = rois.device
     gt_index = torch.empty((B, IR), device=dev, dtype=torch.int32)
     fg_count = torch.empty((B,), device=dev, dtype=torch.int32)
-    outs = ProposalTarget(rois, gt_boxes, num_classes, B, IR, fg_thresh, bg_thresh_hi, bg_thresh_lo,
-                          proposal_without_gt, fg_fraction=fg_fraction, class_agnostic=class_agnostic,
-                          output_iou=output_iou, bbox_mean=bbox_mean, bbox_std=bbox_std, bbox_weight=bbox_weight,
-                          seed=seed, priorities=priorities, _match_out=(gt_index, fg_count))
+    common = dict(fg_fraction=fg_fraction, class_agnostic=class_agnostic, output_iou=output_iou, bbox_mean=bbox_mean,
+                  bbox_std=bbox_std, bbox_weight=bbox_weight, seed=seed, priorities=priorities,
+                  _match_out=(gt_index, fg_count))
+    if filter_scales:
+        outs = ProposalTarget_v2(rois, gt_boxes, valid_ranges, num_classes, B, IR, fg_thresh, bg_thresh_hi,
+                                 bg_thresh_lo, proposal_without_gt, filter_scales=True, **common)
+    else:
+        outs = ProposalTarget(rois, gt_boxes, num_classes, B, IR, fg_thresh, bg_thresh_hi, bg_thresh_lo,
+                              proposal_without_gt, **common)
     NM = int(IR * fg_fraction)
     M = int(mask_size)
     mask = torch.empty((B, NM, M, M), device=dev, dtype=torch.float32)

@@ -134,6 +134,7 @@ def main():
     b, q = boxes(rng, 257), boxes(rng, 19)
     out["overlaps_boxes"], out["overlaps_query"] = b, q
     out["overlaps_out"] = cy["bbox"].bbox_overlaps_cython(b, q)
+    out["selfoverlaps_out"] = cy["bbox_self"].bbox_selfoverlaps_cython(b, q)
     # --- greedy / soft NMS (distinct scores: the tie order of argsort()[::-1] is unspecified)
     d = np.concatenate([boxes(rng, 400, 300.0), rng.permutation(400)[:, None].astype(np.float32) / 400 + 1e-3], 1)
     d = d.astype(np.float32)

@@ -108,6 +108,23 @@ def test_proposal_v3(cuda, is_train, hw, stride, pre, post):
     np.testing.assert_allclose(out.cpu().numpy(), ro, rtol=1e-5, atol=1e-3)
 
 
+def test_proposal_v3_iou_loss(cuda):
+    """IoUPredKernel path: additive decode and the padded-cell mask applied BEFORE the sort (both
+    the single-CTA and the chunked selection)."""
+    rng = np.random.default_rng(77)
+    for (H, W, stride, pre) in ((38, 50, 16, 1500), (120, 160, 4, 1000)):
+        B, A = 2, 3
+        cls = rng.uniform(0, 1, (B, 2 * A, H, W)).astype(np.float32)
+        deltas = (rng.standard_normal((B, 4 * A, H, W)) * 6).astype(np.float32)
+        im_info = np.array([[H * stride - 70, W * stride - 90, 1.0], [H * stride, W * stride, 1.3]], np.float32)
+        kw = dict(feature_stride=stride, scales=(8,), ratios=(0.5, 1, 2), rpn_pre_nms_top_n=pre,
+                  rpn_post_nms_top_n=600, threshold=0.7, rpn_min_size=4, iou_loss=True)
+        ro, rs = oracle.proposal_v3(cls, deltas, im_info, **kw)
+        out, sc = ops.Proposal_v3(_t(cls, cuda), _t(deltas, cuda), _t(im_info, cuda), output_score=True, **kw)
+        assert np.array_equal(sc.cpu().numpy(), rs)
+        np.testing.assert_allclose(out.cpu().numpy(), ro, rtol=1e-6, atol=1e-4)
+
+
 def test_proposal_v3_degenerate_harness(cuda):
     """detection_infer_speed.py: zero weights -> constant fg prob 0.5, zero deltas,
     im_info=(400, 666.5, 2): every score ties, order must be anchor-index order."""

@@ -76,3 +76,24 @@ def test_poly2mask_shapes(cuda):
     m = res[4].cpu().numpy()[0, 0]
     want = oracle.poly2mask(rois[0, 0], polys[0, 0], 28)
     assert np.array_equal(m, want) and m[:, :14].sum() == 28 * 14 and m[:, 14:].sum() == 0
+
+
+def test_mask_target_filter_scales(cuda):
+    """TridentNet form (4 inputs): gt boxes outside valid_ranges are not appended as candidates."""
+    rng = np.random.default_rng(9)
+    B, R, G, PL, IR, M = 2, 300, 12, 2500, 64, 14
+    rois, gt, polys = _scene(rng, B, R, G, PL)
+    vr = np.array([[0, 150], [120, 1e5]], np.float32)
+    pr = rng.integers(2 ** 20, 2 ** 32, (B, 4, R + G), dtype=np.uint64).astype(np.uint32)
+    # candidates = the R-20 non-padding rois, then the appended gt boxes: those win every shuffle
+    pr[:, :, R - 20:R - 20 + G] = np.arange(G).astype(np.uint32)  # (a shuffle orders by ascending priority)
+    ref = oracle.proposal_mask_target(rois, gt, polys, pr, 81, IR, M, fg_fraction=0.25, fg_thresh=0.5,
+                                      bg_thresh_hi=0.5, bg_thresh_lo=0.0, valid_ranges=vr, filter_scales=True)
+    plain = oracle.proposal_mask_target(rois, gt, polys, pr, 81, IR, M, fg_fraction=0.25, fg_thresh=0.5,
+                                        bg_thresh_hi=0.5, bg_thresh_lo=0.0)
+    assert not np.array_equal(ref[0], plain[0])  # the filter changes the candidate set
+    res = ops.ProposalMaskTarget(_t(rois, cuda), _t(gt, cuda), _t(polys, cuda), 81, B, IR, M, 0.5, 0.5, 0.0, False,
+                                 priorities=_t(pr.astype(np.int64), cuda), filter_scales=True, num_args=4,
+                                 valid_ranges=_t(vr, cuda))
+    assert np.array_equal(res[0].cpu().numpy(), ref[0]) and np.array_equal(res[1].cpu().numpy(), ref[1])
+    assert np.array_equal(res[4].cpu().numpy(), ref[5])

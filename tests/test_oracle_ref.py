@@ -15,6 +15,7 @@ G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_python_
 
 def test_bbox_overlaps_golden():
     assert np.array_equal(oracle.bbox_overlaps(G["overlaps_boxes"], G["overlaps_query"]), G["overlaps_out"])
+    assert np.array_equal(oracle.bbox_selfoverlaps(G["overlaps_boxes"], G["overlaps_query"]), G["selfoverlaps_out"])
 
 
 def test_greedy_nms_golden():
