@@ -148,17 +148,18 @@ struct ScanOut {
 };
 
 // One CTA (256 threads) per problem: greedy scan of the bitmask in 64-row blocks.
-// Shared: removed words (col_blocks), kept list (n_max ints), one block of mask rows.
+// Shared: removed words (col_blocks), `nbuf` blocks of mask rows, kept list (n_max ints).  With
+// nbuf = 2 the next block's rows stream in (cp.async) while the current block is resolved.
 __global__ void __launch_bounds__(256)
 nms_scan_kernel(const float* __restrict__ dets, const int* __restrict__ counts, const int n_max,
-                const unsigned long long* __restrict__ mask, const ScanOut o) {
+                const unsigned long long* __restrict__ mask, const ScanOut o, const int nbuf) {
   extern __shared__ unsigned long long s_dyn[];
   const int p = blockIdx.x;
   const int n = counts ? counts[p] : n_max;
   const int cbs = (n_max + 63) >> 6;
   unsigned long long* s_removed = s_dyn;          // cbs words
-  unsigned long long* s_rows = s_dyn + cbs;       // 64 x cbs words (mask rows of one block)
-  int* s_keep = reinterpret_cast<int*>(s_rows + 64 * (size_t)cbs);  // n_max ints
+  unsigned long long* s_rows0 = s_dyn + cbs;      // nbuf x 64 x cbs words (mask rows of a block)
+  int* s_keep = reinterpret_cast<int*>(s_rows0 + (size_t)nbuf * 64 * cbs);  // n_max ints
   __shared__ int s_nkeep;
   const int tid = threadIdx.x;
   for (int i = tid; i < cbs; i += blockDim.x) s_removed[i] = 0ull;
@@ -166,14 +167,24 @@ nms_scan_kernel(const float* __restrict__ dets, const int* __restrict__ counts, 
   __syncthreads();
   const unsigned long long* m = mask + (size_t)p * n_max * cbs;
   const int nblocks = (n + 63) >> 6;
+  // stage a block's mask rows (only words >= rb are defined / needed)
+  auto stage_rows = [&](int rb, unsigned long long* dst) {
+    const int rows = min(64, n - rb * 64), wpr = cbs - rb;
+    for (int e = tid; e < rows * wpr; e += blockDim.x) {
+      const int r = e / wpr, w = rb + e - r * wpr;
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + r * cbs + w);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(m + (size_t)(rb * 64 + r) * cbs + w)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (nblocks > 0) stage_rows(0, s_rows0);
   for (int rb = 0; rb < nblocks; ++rb) {
     const int rows = min(64, n - rb * 64);
-    // stage this block's mask rows (only words >= rb are defined / needed)
-    for (int e = tid; e < rows * (cbs - rb); e += blockDim.x) {
-      const int r = e / (cbs - rb), w = rb + e % (cbs - rb);
-      s_rows[r * cbs + w] = m[(size_t)(rb * 64 + r) * cbs + w];
-    }
+    unsigned long long* s_rows = s_rows0 + (nbuf == 2 ? (size_t)(rb & 1) * 64 * cbs : 0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    if (nbuf == 2 && rb + 1 < nblocks) stage_rows(rb + 1, s_rows0 + (size_t)((rb + 1) & 1) * 64 * cbs);
     // The serial greedy dependency lives entirely inside the block's DIAGONAL word: every thread
     // resolves it redundantly in registers (64 steps, broadcast LDS, no barrier), then the kept
     // rows' words are OR-ed into `removed` in parallel (thread w owns word w).
@@ -197,6 +208,7 @@ nms_scan_kernel(const float* __restrict__ dets, const int* __restrict__ counts, 
       s_keep[nk0 + __popcll(alive & ((1ull << tid) - 1ull))] = rb * 64 + tid;
     if (tid == 0) s_nkeep = nk0 + __popcll(alive);
     __syncthreads();
+    if (nbuf == 1 && rb + 1 < nblocks) stage_rows(rb + 1, s_rows0);
   }
   const int nk = s_nkeep;
   if (o.nkeep && tid == 0) o.nkeep[p] = nk;
@@ -226,9 +238,9 @@ nms_scan_kernel(const float* __restrict__ dets, const int* __restrict__ counts, 
   }
 }
 
-size_t scan_smem_bytes(int n_max) {
+size_t scan_smem_bytes(int n_max, int nbuf) {
   const size_t cbs = (size_t)(n_max + 63) / 64;
-  return cbs * 8 + 64 * cbs * 8 + (size_t)n_max * 4;
+  return cbs * 8 + (size_t)nbuf * 64 * cbs * 8 + (size_t)n_max * 4;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -547,7 +559,8 @@ int run_mask_and_scan(const float* dets, const int* counts, int P, int n, float 
   dim3 grid((unsigned)cbs, (unsigned)cbs, (unsigned)P);
   nms_mask_kernel<<<grid, 64, 0, st>>>(dets, counts, n, thr, ge, mask);
   SDET_LAUNCH_CHECK("nms_mask_kernel");
-  const size_t smem = scan_smem_bytes(n);
+  const int nbuf = scan_smem_bytes(n, 2) <= 96 * 1024 ? 2 : 1;
+  const size_t smem = scan_smem_bytes(n, nbuf);
   if (n > 12288 || smem > 200 * 1024)
     return sdet::fail(SDET_ERR_UNSUPPORTED, "NMS over %d boxes needs %zu B shared memory", n, smem);
   static size_t configured = 0;
@@ -555,7 +568,7 @@ int run_mask_and_scan(const float* dets, const int* counts, int P, int n, float 
     SDET_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  nms_scan_kernel<<<(unsigned)P, 256, smem, st>>>(dets, counts, n, mask, so);
+  nms_scan_kernel<<<(unsigned)P, 256, smem, st>>>(dets, counts, n, mask, so, nbuf);
   SDET_LAUNCH_CHECK("nms_scan_kernel");
   return SDET_OK;
 }
