@@ -59,16 +59,23 @@ def main():
     ap.add_argument("--argmax", type=int, default=0)
     ap.add_argument("--plan", type=int, default=1)
     ap.add_argument("--noflush", type=int, default=0)
+    ap.add_argument("--sorted", type=int, default=0, help="1: rois pre-sorted by (level, y, x) on the host (locality probe)")
     ap.add_argument("--backward", type=int, default=0, help="time the backward pass (incl. zero-fill of the grads)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(0)
     B, N, pooled = {"target": (1, 512, 14), "infer": (1, 1000, 7), "train": (2, 512, 7),
-                    "mask": (2, 128, 14)}[a.shape]
+                    "mask": (2, 128, 14), "bench": (2, 1000, 7)}[a.shape]
     C = 256
     shapes = synth.fpn_shapes()
     feats = [torch.randn((B, C, h, w), device=dev) for h, w in shapes]
     rois_np = synth.random_rois(rng, B, N)
+    if a.sorted:
+        for b in range(B):
+            r = rois_np[b]
+            wh = np.sqrt((r[:, 2] - r[:, 0] + 1) * (r[:, 3] - r[:, 1] + 1))
+            lvl = np.clip(np.floor(4 + np.log2(wh / 224 + 1e-6)), 2, 5)
+            rois_np[b] = r[np.lexsort((r[:, 0], r[:, 1] // 32, lvl))]
     rois = torch.from_numpy(rois_np).to(dev)
     flush = torch.empty(128 * 1024 * 1024, device=dev)
     out, _, _, lv = ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=False)
@@ -99,7 +106,7 @@ def main():
                 pooled, 0, torch.cuda.current_stream().cuda_stream))
 
     med, mn = time_op(fn, a.iters, flush, not a.noflush)
-    print(json.dumps({"shape": a.shape, "B": B, "N": N, "pooled": pooled, "argmax": a.argmax, "backward": a.backward, "plan": a.plan, "noflush": a.noflush, "modepref": os.environ.get("SDET_RA_MODEPREF"), "tiles": os.environ.get("SDET_RA_TILES"),
+    print(json.dumps({"shape": a.shape, "B": B, "N": N, "pooled": pooled, "argmax": a.argmax, "sorted": a.sorted, "backward": a.backward, "plan": a.plan, "noflush": a.noflush, "modepref": os.environ.get("SDET_RA_MODEPREF"), "tiles": os.environ.get("SDET_RA_TILES"),
                       "cpt": os.environ.get("SDET_RA_CPT"), "phs": os.environ.get("SDET_RA_PHS"),
                       "us_median": round(med, 2), "us_min": round(mn, 2), "alg_bytes": nbytes,
                       "GBps": round(nbytes / med / 1e3, 1),

@@ -38,7 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH, *sources()]
+    extra = os.environ.get("SDET_NVCC_EXTRA", "").split()  # e.g. -DSDET_RA_ABLATE for a profiling build
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH, *sources()]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

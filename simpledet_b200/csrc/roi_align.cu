@@ -313,6 +313,10 @@ __global__ void __launch_bounds__(64) roi_align_plan_kernel(const __grid_constan
 }
 
 // kCapFloats: floats of dynamic shared memory for the window buffers (12288 = 48 KB -> 4 CTAs/SM)
+#ifdef SDET_RA_ABLATE  // profiling builds only: bit 0 skips compute, bit 1 skips staging (results are garbage)
+__device__ int g_ra_ablate = 0;
+#endif
+
 template <int CPT, bool kArg, int kPH, int kPW, int kCapFloats>
 __global__ void __launch_bounds__(128, 4)
 roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles) {
@@ -323,7 +327,7 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
   __shared__ __align__(16) int s_scal[8];  // {li, flags, hmin, hmax, wmin, wmax}
 
   constexpr int NW = 4;  // warps per CTA
-  static_assert(CPT % 2 == 0, "channels are processed in fp32x2 pairs");
+  static_assert(CPT % 4 == 0, "channels are processed in fp32x2 pairs, per half-warp when PW <= 8");
 
   const int tid = threadIdx.x;
   const int n = blockIdx.x;
@@ -452,7 +456,9 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
 
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(s_win);
   const int warp = tid >> 5, lane = tid & 31;
-  const int pw = lane >> 1, sx = lane & 1;
+  constexpr int kSub = (kPW > 0 && kPW <= 8) ? 2 : 1;  // half-warps per warp that own their own channels
+  const int half = (kSub == 2) ? (lane >> 4) : 0;
+  const int pw = (kSub == 2 ? (lane & 15) : lane) >> 1, sx = lane & 1;
   const bool lane_on = pw < PW;
   int wcnt = -1, xl = 0, xr = 0;
   float b0 = 0.f, b1 = 0.f, wc = -1.f;
@@ -524,34 +530,37 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
     };
 
     auto compute = [&](int tile, unsigned buf) {
-      const int cbase = cgrp0 + tile * CTILE + cg * CPT;
-      const unsigned sl = buf + 4u * (unsigned)(cg * CPT * kCS + xl);   // lane's left-tap column
-      const unsigned sr = buf + 4u * (unsigned)(cg * CPT * kCS + xr);   // lane's right-tap column
-      float RA[CPT][2], RB[CPT][2];  // 2-row register cache; filled before first use (rowA/B = -1)
+      // CL = channels per lane: a 7-wide roi fills only 14 lanes of a warp, so its two half-warps
+      // take the two halves of the warp's channels (kSub = 2) instead of idling
+      constexpr int CL = CPT / kSub;
+      const int cbase = cgrp0 + tile * CTILE + cg * CPT + half * CL;
+      const unsigned sl = buf + 4u * (unsigned)((cg * CPT + half * CL) * kCS + xl);   // lane's left-tap column
+      const unsigned sr = buf + 4u * (unsigned)((cg * CPT + half * CL) * kCS + xr);   // lane's right-tap column
+      float RA[CL][2], RB[CL][2];  // 2-row register cache; filled before first use (rowA/B = -1)
       int rowA = -1, rowB = -1;
       const size_t obase = ((size_t)n * C + cbase) * PP + (size_t)ph_beg * PW + pw;
       float* outp = a.out + obase;
       float* axp = kArg ? a.argx + obase : nullptr;
       float* ayp = kArg ? a.argy + obase : nullptr;
       const bool store = lane_on && sx == 0;
-      // inference: after the pair exchange both lanes of a pw hold all CPT maxima; lane s stores
-      // channels [s*CPT/2, (s+1)*CPT/2) so every store instruction has 28 active lanes
-      float* outh = outp + (size_t)(sx * (CPT / 2)) * PP;
+      // inference: after the pair exchange both lanes of a pw hold all CL maxima; lane s stores
+      // channels [s*CL/2, (s+1)*CL/2) so every store instruction has 28 active lanes
+      float* outh = outp + (size_t)(sx * (CL / 2)) * PP;
 
       // One h-sample: make the register sets hold rows (lo, hi) — whichever set already holds
-      // `lo` plays the low row, so nothing is ever moved — then the bilinear values of the CPT
+      // `lo` plays the low row, so nothing is ever moved — then the bilinear values of the CL
       // channels.  The tests are warp-uniform; routing them through a vote lets ptxas emit plain
       // branches instead of divergence bookkeeping.
-      auto sample = [&](const int4 hr, float (&v)[CPT]) {
+      auto sample = [&](const int4 hr, float (&v)[CL]) {
         const int olo = hr.x, ohi = hr.y;
         const float a0 = __int_as_float(hr.z), a1 = __int_as_float(hr.w);
         const float wtl = __fmul_rn(a0, b0), wbl = __fmul_rn(a1, b0);
         const float wtr = __fmul_rn(a0, b1), wbr = __fmul_rn(a1, b1);
         const uint64_t wtl2 = pack2(wtl, wtl), wbl2 = pack2(wbl, wbl);
         const uint64_t wtr2 = pack2(wtr, wtr), wbr2 = pack2(wbr, wbr);
-        auto step = [&](const float (&Lo)[CPT][2], const float (&Hi)[CPT][2]) {
+        auto step = [&](const float (&Lo)[CL][2], const float (&Hi)[CL][2]) {
 #pragma unroll
-          for (int k = 0; k < CPT; k += 2) {
+          for (int k = 0; k < CL; k += 2) {
             // roi_align_v2-inl.h:137-140 for channels k, k+1: ((tl + bl) + tr) + br
             const uint64_t ptl = fma2(wtl2, pack2(Lo[k][0], Lo[k + 1][0]), nz2);
             const uint64_t pbl = fma2(wbl2, pack2(Hi[k][0], Hi[k + 1][0]), nz2);
@@ -562,21 +571,21 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
         };
         if (__all_sync(0xffffffffu, olo == rowA)) {
           if (__any_sync(0xffffffffu, ohi != rowB)) {
-            TapLoader<CPT, kCS>::run(RB, sl + ohi, sr + ohi);
+            TapLoader<CL, kCS>::run(RB, sl + ohi, sr + ohi);
             rowB = ohi;
           }
           step(RA, RB);
         } else if (__all_sync(0xffffffffu, olo == rowB)) {
           if (__any_sync(0xffffffffu, ohi != rowA)) {
-            TapLoader<CPT, kCS>::run(RA, sl + ohi, sr + ohi);
+            TapLoader<CL, kCS>::run(RA, sl + ohi, sr + ohi);
             rowA = ohi;
           }
           step(RB, RA);
         } else {
-          TapLoader<CPT, kCS>::run(RA, sl + olo, sr + olo);
+          TapLoader<CL, kCS>::run(RA, sl + olo, sr + olo);
           rowA = olo;
           if (__any_sync(0xffffffffu, ohi != rowB)) {
-            TapLoader<CPT, kCS>::run(RB, sl + ohi, sr + ohi);
+            TapLoader<CL, kCS>::run(RB, sl + ohi, sr + ohi);
             rowB = ohi;
           }
           step(RA, RB);
@@ -585,7 +594,7 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
 
       const int4* tab = reinterpret_cast<const int4*>(s_hrow);
       for (int ph = ph_beg; ph < ph_end; ++ph) {
-        float v0[CPT], v1[CPT];
+        float v0[CL], v1[CL];
         const bool hvalid = !has_empty || s_th.cnt[ph] == 2;   // warp-uniform
         if (hvalid) {
           const int4 h0 = tab[ph * kMaxS], h1 = tab[ph * kMaxS + 1];
@@ -593,7 +602,7 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
           sample(h1, v1);
         } else {
 #pragma unroll
-          for (int k = 0; k < CPT; ++k) v0[k] = v1[k] = -FLT_MAX;  // bin empty along h: zeroed below
+          for (int k = 0; k < CL; ++k) v0[k] = v1[k] = -FLT_MAX;  // bin empty along h: zeroed below
         }
         // bins that are empty along an axis (end <= start) pool to 0 / argmax -1
         // (roi_align_v2-inl.h:111-117); only CTAs whose roi has such bins pay for the selects
@@ -604,7 +613,7 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
           const float hc0 = s_th.coord[ph * kMaxS], hc1 = s_th.coord[ph * kMaxS + 1];
           const float pwc = __shfl_xor_sync(0xffffffffu, wc, 1);
 #pragma unroll
-          for (int k = 0; k < CPT; ++k) {
+          for (int k = 0; k < CL; ++k) {
             float mk = -FLT_MAX;
             int mi = -1;
             if (v0[k] > mk) {
@@ -636,20 +645,20 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
           ayp += PW;
           outp += PW;
         } else {
-          float best[CPT];
+          float best[CL];
 #pragma unroll
-          for (int k = 0; k < CPT; ++k) {
+          for (int k = 0; k < CL; ++k) {
             const float mk = fmaxf(v0[k], v1[k]);  // fmaxf drops a NaN operand like `v > m` does
             best[k] = max3f(mk, __shfl_xor_sync(0xffffffffu, mk, 1), -FLT_MAX);
           }
           if (lane_on) {
             if (!has_empty) {
 #pragma unroll
-              for (int k = 0; k < CPT / 2; ++k) outh[k * PP] = sx ? best[CPT / 2 + k] : best[k];
+              for (int k = 0; k < CL / 2; ++k) outh[k * PP] = sx ? best[CL / 2 + k] : best[k];
             } else {
 #pragma unroll
-              for (int k = 0; k < CPT / 2; ++k)
-                outh[k * PP] = zero_out ? 0.f : (sx ? best[CPT / 2 + k] : best[k]);
+              for (int k = 0; k < CL / 2; ++k)
+                outh[k * PP] = zero_out ? 0.f : (sx ? best[CL / 2 + k] : best[k]);
             }
           }
           outh += PW;
@@ -657,30 +666,34 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
       }
     };
 
-    // ---- software pipeline over the channel tiles of this roi ----
-    stage(0, sbase);
-    cp_async_commit();
+    // ---- software pipeline over the channel tiles of this roi: a ring of NBUF window buffers,
+    // NBUF - 1 tiles in flight while one is computed ----
+#pragma unroll
+    for (int s = 0; s < NBUF - 1; ++s) {
+      if (s < ntiles) stage(s, sbase + (unsigned)s * BUF_BYTES);
+      cp_async_commit();  // (possibly empty: keeps the group count uniform)
+    }
     for (int t = 0; t < ntiles; ++t) {
-      const unsigned cur = sbase + ((NBUF == 2) ? (unsigned)(t & 1) * BUF_BYTES : 0u);
-      if (NBUF == 2 && t + 1 < ntiles) {
-        stage(t + 1, sbase + (unsigned)((t + 1) & 1) * BUF_BYTES);
-        cp_async_commit();
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
+      const int tn = t + NBUF - 1;  // its buffer was released by the barrier that ended iteration t-1
+#ifdef SDET_RA_ABLATE
+      if (!(g_ra_ablate & 2))
+#endif
+      if (tn < ntiles) stage(tn, sbase + (unsigned)(tn % NBUF) * BUF_BYTES);
+      cp_async_commit();
+      cp_async_wait<NBUF - 1>();    // tile t has landed
       __syncthreads();
-      compute(t, cur);
-      if (t + 1 < ntiles) {
-        __syncthreads();  // every warp is done with `cur` before it is refilled
-        if (NBUF == 1) {
-          stage(t + 1, sbase);
-          cp_async_commit();
-        }
-      }
+#ifdef SDET_RA_ABLATE
+      if (!(g_ra_ablate & 1))
+#endif
+      compute(t, sbase + (unsigned)(t % NBUF) * BUF_BYTES);
+      if (t + 1 < ntiles) __syncthreads();  // every warp is done with the buffer before it is refilled
     }
   };
 
+  // (channel stride, channel groups per tile, ring depth) by window size.  Measured on 7x7 rois
+  // (profiles/r01_roi_align_7x7_ablation.txt): stage and compute time ADD (the kernel is issue-bound,
+  // not latency-bound), so deeper rings of smaller tiles only add per-tile barriers — two channel
+  // groups per tile, double-buffered when the window is small, is the fastest layout found.
   using std::integral_constant;
   if (mode == 0)
     run(integral_constant<int, CS0>{}, integral_constant<int, 2>{}, integral_constant<int, 2>{});
@@ -688,7 +701,6 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
     run(integral_constant<int, CS1>{}, integral_constant<int, 2>{}, integral_constant<int, 1>{});
   else
     run(integral_constant<int, CS3>{}, integral_constant<int, 1>{}, integral_constant<int, 1>{});
-
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -765,6 +777,15 @@ int launch_fwd_t(const RoiAlignArgs& a, cudaStream_t st) {
   int tpc = (int)(jobs / (148 * 12));
   if (tpc < 1) tpc = 1;
   if (tpc > total_tiles) tpc = total_tiles;
+#ifdef SDET_RA_ABLATE
+  if (const char* e = getenv("SDET_RA_TILES")) tpc = atoi(e);
+  {
+    const int v = getenv("SDET_RA_ABLATE") ? atoi(getenv("SDET_RA_ABLATE")) : 0;
+    cudaMemcpyToSymbolAsync(g_ra_ablate, &v, sizeof(int), 0, cudaMemcpyHostToDevice, st);
+  }
+  if (tpc < 1) tpc = 1;
+  if (tpc > total_tiles) tpc = total_tiles;
+#endif
   dim3 grid((unsigned)(a.B * a.N), (unsigned)((total_tiles + tpc - 1) / tpc));
   if (arg)
     k_trn<<<grid, 128, smem_bytes, st>>>(a, tpc);
