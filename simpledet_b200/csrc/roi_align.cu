@@ -204,10 +204,26 @@ __device__ __forceinline__ void cp_async16(unsigned smem_dst, const float* gsrc)
 __device__ __forceinline__ void cp_async4(unsigned smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+// mbarrier helpers (CTA scope) for the producer-warp pipeline
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrives on `bar` once every cp.async this thread has issued so far has landed (count pre-charged)
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra W_%=;\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
 }
 template <int IMM>
 __device__ __forceinline__ float lds_f32_imm(unsigned addr) {
@@ -317,14 +333,21 @@ __global__ void __launch_bounds__(64) roi_align_plan_kernel(const __grid_constan
 __device__ int g_ra_ablate = 0;
 #endif
 
+// CTA = 4 consumer warps (the arithmetic) + 1 producer warp (all cp.async staging).  Staging and
+// arithmetic were measured to ADD, not overlap, when the same four warps did both (issue slots at
+// 16 warps/SM); a dedicated producer takes the LDGSTS + address arithmetic off the consumers' path
+// and replaces the two CTA-wide barriers per tile by full/empty mbarriers.
+constexpr int kFwdThreads = 160;
+
 template <int CPT, bool kArg, int kPH, int kPW, int kCapFloats>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(kFwdThreads, 4)
 roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles) {
   extern __shared__ __align__(16) float s_win[];
   constexpr int TP = (kPH > 0 && kPH <= 16 && kPW <= 16) ? 16 : kMaxP;
   __shared__ __align__(16) AxisTab<TP> s_th, s_tw;
   __shared__ __align__(16) HRow s_hrow[TP * kMaxS];
   __shared__ __align__(16) int s_scal[8];  // {li, flags, hmin, hmax, wmin, wmax}
+  __shared__ __align__(8) unsigned long long s_bar[4];  // full[0..1], empty[0..1]
 
   constexpr int NW = 4;  // warps per CTA
   static_assert(CPT % 4 == 0, "channels are processed in fp32x2 pairs, per half-warp when PW <= 8");
@@ -452,7 +475,14 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
                          s_th.w0[tid], s_th.w1[tid]};
     }
   }
-  // (visibility of s_hrow is covered by the __syncthreads() before the first compute)
+  if (tid == 0) {
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(s_bar);
+    mbar_init(bar0, 32);          // full[0]: the 32 producer lanes (cp.async completion arrivals)
+    mbar_init(bar0 + 8, 32);      // full[1]
+    mbar_init(bar0 + 16, NW);     // empty[0]: one arrival per consumer warp
+    mbar_init(bar0 + 24, NW);     // empty[1]
+  }
+  __syncthreads();  // s_hrow and the mbarriers are visible to every warp
 
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(s_win);
   const int warp = tid >> 5, lane = tid & 31;
@@ -499,9 +529,9 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
     const int nch = vec ? ((Wwin + 3 + 3) >> 2) : (Wp >> 2);    // 16B chunks per row (upper bound)
     const int nitems = Hwin * nch;
     const unsigned nch_magic = 0xFFFFFFFFu / (unsigned)nch + 1u; // idx / nch for idx < 2^16
-    auto stage = [&](int tile, unsigned buf) {
+    auto stage = [&](int tile, unsigned buf) {  // executed by the producer warp only
       const float* g0 = gimg + (size_t)(cgrp0 + tile * CTILE) * HW;
-      for (int idx = tid; idx < nitems; idx += 128) {
+      for (int idx = lane; idx < nitems; idx += 32) {
         const int y = (int)__umulhi((unsigned)idx, nch_magic), jchunk = idx - y * nch;
         const int e0 = (hmin + y) * W + wmin;  // first wanted element inside the plane
         unsigned dst = buf + 4u * (unsigned)(y * Wp + jchunk * 4);
@@ -666,27 +696,23 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
       }
     };
 
-    // ---- software pipeline over the channel tiles of this roi: a ring of NBUF window buffers,
-    // NBUF - 1 tiles in flight while one is computed ----
-#pragma unroll
-    for (int s = 0; s < NBUF - 1; ++s) {
-      if (s < ntiles) stage(s, sbase + (unsigned)s * BUF_BYTES);
-      cp_async_commit();  // (possibly empty: keeps the group count uniform)
+    // ---- producer / consumer pipeline over the channel tiles of this roi (ring of NBUF buffers) ----
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(s_bar);
+    if (warp == NW) {
+      for (int t = 0; t < ntiles; ++t) {
+        const int b = t % NBUF, k = t / NBUF;
+        if (k > 0) mbar_wait(bar0 + 8u * (2 + b), (unsigned)((k - 1) & 1));  // consumers released the buffer
+        stage(t, sbase + (unsigned)b * BUF_BYTES);
+        cp_async_mbar_arrive(bar0 + 8u * b);
+      }
+      return;
     }
     for (int t = 0; t < ntiles; ++t) {
-      const int tn = t + NBUF - 1;  // its buffer was released by the barrier that ended iteration t-1
-#ifdef SDET_RA_ABLATE
-      if (!(g_ra_ablate & 2))
-#endif
-      if (tn < ntiles) stage(tn, sbase + (unsigned)(tn % NBUF) * BUF_BYTES);
-      cp_async_commit();
-      cp_async_wait<NBUF - 1>();    // tile t has landed
-      __syncthreads();
-#ifdef SDET_RA_ABLATE
-      if (!(g_ra_ablate & 1))
-#endif
-      compute(t, sbase + (unsigned)(t % NBUF) * BUF_BYTES);
-      if (t + 1 < ntiles) __syncthreads();  // every warp is done with the buffer before it is refilled
+      const int b = t % NBUF, k = t / NBUF;
+      mbar_wait(bar0 + 8u * b, (unsigned)(k & 1));   // tile t has landed
+      compute(t, sbase + (unsigned)b * BUF_BYTES);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8u * (2 + b));
     }
   };
 
@@ -788,9 +814,9 @@ int launch_fwd_t(const RoiAlignArgs& a, cudaStream_t st) {
 #endif
   dim3 grid((unsigned)(a.B * a.N), (unsigned)((total_tiles + tpc - 1) / tpc));
   if (arg)
-    k_trn<<<grid, 128, smem_bytes, st>>>(a, tpc);
+    k_trn<<<grid, kFwdThreads, smem_bytes, st>>>(a, tpc);
   else
-    k_inf<<<grid, 128, smem_bytes, st>>>(a, tpc);
+    k_inf<<<grid, kFwdThreads, smem_bytes, st>>>(a, tpc);
   SDET_LAUNCH_CHECK("roi_align_v2_fwd_kernel");
   return SDET_OK;
 }
