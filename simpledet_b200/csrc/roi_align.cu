@@ -347,7 +347,7 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
   __shared__ __align__(16) AxisTab<TP> s_th, s_tw;
   __shared__ __align__(16) HRow s_hrow[TP * kMaxS];
   __shared__ __align__(16) int s_scal[8];  // {li, flags, hmin, hmax, wmin, wmax}
-  __shared__ __align__(8) unsigned long long s_bar[4];  // full[0..1], empty[0..1]
+  __shared__ __align__(8) unsigned long long s_bar[8];  // full[0..3], empty[0..3]
 
   constexpr int NW = 4;  // warps per CTA
   static_assert(CPT % 4 == 0, "channels are processed in fp32x2 pairs, per half-warp when PW <= 8");
@@ -477,10 +477,10 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
   }
   if (tid == 0) {
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(s_bar);
-    mbar_init(bar0, 32);          // full[0]: the 32 producer lanes (cp.async completion arrivals)
-    mbar_init(bar0 + 8, 32);      // full[1]
-    mbar_init(bar0 + 16, NW);     // empty[0]: one arrival per consumer warp
-    mbar_init(bar0 + 24, NW);     // empty[1]
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar0 + 8u * i, 32);        // full[i]: the 32 producer lanes (cp.async completion arrivals)
+      mbar_init(bar0 + 8u * (4 + i), NW);  // empty[i]: one arrival per consumer warp
+    }
   }
   __syncthreads();  // s_hrow and the mbarriers are visible to every warp
 
@@ -701,7 +701,7 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
     if (warp == NW) {
       for (int t = 0; t < ntiles; ++t) {
         const int b = t % NBUF, k = t / NBUF;
-        if (k > 0) mbar_wait(bar0 + 8u * (2 + b), (unsigned)((k - 1) & 1));  // consumers released the buffer
+        if (k > 0) mbar_wait(bar0 + 8u * (4 + b), (unsigned)((k - 1) & 1));  // consumers released the buffer
         stage(t, sbase + (unsigned)b * BUF_BYTES);
         cp_async_mbar_arrive(bar0 + 8u * b);
       }
@@ -712,21 +712,28 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
       mbar_wait(bar0 + 8u * b, (unsigned)(k & 1));   // tile t has landed
       compute(t, sbase + (unsigned)b * BUF_BYTES);
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + 8u * (2 + b));
+      if (lane == 0) mbar_arrive(bar0 + 8u * (4 + b));
     }
   };
 
-  // (channel stride, channel groups per tile, ring depth) by window size.  Measured on 7x7 rois
-  // (profiles/r01_roi_align_7x7_ablation.txt): stage and compute time ADD (the kernel is issue-bound,
-  // not latency-bound), so deeper rings of smaller tiles only add per-tile barriers — two channel
-  // groups per tile, double-buffered when the window is small, is the fastest layout found.
+  // (channel stride, channel groups per tile, ring depth) by window size.  With the producer warp a
+  // deeper ring of one-channel-group tiles is a small win (7x7 bench shape 234.6 -> 228.4 us, 14x14
+  // target 115.7 -> 113.7 us; profiles/r01_roi_align_7x7_ablation.txt), so it is the default;
+  // -DSDET_RA_DEEP=0 restores two channel groups per tile.
   using std::integral_constant;
-  if (mode == 0)
-    run(integral_constant<int, CS0>{}, integral_constant<int, 2>{}, integral_constant<int, 2>{});
-  else if (mode == 1)
-    run(integral_constant<int, CS1>{}, integral_constant<int, 2>{}, integral_constant<int, 1>{});
-  else
+#ifndef SDET_RA_DEEP
+#define SDET_RA_DEEP 2
+#endif
+  constexpr bool kDeep = (SDET_RA_DEEP == 2) || (SDET_RA_DEEP == 1 && kPW > 0 && kPW <= 8);
+  if (mode == 0) {
+    if (kDeep) run(integral_constant<int, CS0>{}, integral_constant<int, 1>{}, integral_constant<int, 4>{});
+    else run(integral_constant<int, CS0>{}, integral_constant<int, 2>{}, integral_constant<int, 2>{});
+  } else if (mode == 1) {
+    if (kDeep) run(integral_constant<int, CS1>{}, integral_constant<int, 1>{}, integral_constant<int, 2>{});
+    else run(integral_constant<int, CS1>{}, integral_constant<int, 2>{}, integral_constant<int, 1>{});
+  } else {
     run(integral_constant<int, CS3>{}, integral_constant<int, 1>{}, integral_constant<int, 1>{});
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
