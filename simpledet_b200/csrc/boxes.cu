@@ -190,8 +190,13 @@ nms_scan_kernel(const float* __restrict__ dets, const int* __restrict__ counts, 
     // rows' words are OR-ed into `removed` in parallel (thread w owns word w).
     unsigned long long alive = ~s_removed[rb];
     if (rows < 64) alive &= (1ull << rows) - 1ull;
-    for (int r = 0; r < rows; ++r)
-      if ((alive >> r) & 1ull) alive &= ~s_rows[r * cbs + rb];
+    // branch-free and unrolled: the diagonal words are loaded in batches ahead of the dependent
+    // AND chain (rows beyond `rows` are already cleared in `alive`, their words are never applied)
+#pragma unroll 16
+    for (int r = 0; r < 64; ++r) {
+      const unsigned long long w = (r < rows) ? s_rows[r * cbs + rb] : 0ull;
+      alive &= ~(((alive >> r) & 1ull) ? w : 0ull);
+    }
     const int nk0 = s_nkeep;
     __syncthreads();  // every thread has read s_removed[rb] / s_nkeep before they change
     for (int w = rb + 1 + tid; w < cbs; w += blockDim.x) {
@@ -316,7 +321,7 @@ proposal_chunk_topk_kernel(const __grid_constant__ ProposalParams p) {
   }
   auto key_at = [&](int i) -> uint64_t { return proposal_key(fg, i0 + i, HW, A, magic, L.W, rh, rw); };
   const int k = min(pre, n);
-  sdet::block_topk_sorted(n, k, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+  sdet::block_topk_sorted<false>(n, k, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
   unsigned long long* dst = p.cand + L.cand_off + ((size_t)b * L.nchunks + chunk) * pre;
   for (int j = threadIdx.x; j < pre; j += blockDim.x) dst[j] = (j < k) ? s_sel[j] : 0ull;  // 0 < every real key
 }
