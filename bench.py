@@ -172,6 +172,7 @@ def time_cpu(d, budget_s=12.0):
     import oracle
 
     oracle.build()
+    oracle.set_threads()
     t0 = time.perf_counter()
     cpu_hot_path(d, 1)
     one = time.perf_counter() - t0
@@ -192,9 +193,12 @@ def run_reference(args):
     does compile is pinned against the port in tests).  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    import oracle
+
+    oracle.build()
     rng = np.random.default_rng(0)
     d = make_inputs_np(rng, 1)
-    cores = os.cpu_count() or 1
+    cores = oracle.set_threads() or 1  # (torchrun exports OMP_NUM_THREADS=1: undo it for the CPU arm)
     for _ in range(min(args.warmup, 1)):
         cpu_hot_path(d, 1)
     t0 = time.perf_counter()

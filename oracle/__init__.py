@@ -435,3 +435,18 @@ def gen_proposal_retina(cls_prob, bbox_pred, im_info, anchors, num_anchors, rpn_
                                      int(num_anchors), int(rpn_pre_nms_top_n), int(rpn_min_size),
                                      ctypes.c_float(thresh), _p(m), _p(s_), int(bool(output_one_hot)), _p(out), _p(sc))
     return out, sc
+
+
+def set_threads(n=None):
+    """OpenMP team size of the C restatements.  torchrun exports OMP_NUM_THREADS=1 to its children;
+    the CPU baseline is meant to use every host core, so bench.py calls this explicitly."""
+    import os
+    n = int(n or os.cpu_count() or 1)
+    lib()  # make sure libgomp is mapped
+    for name in ("libgomp.so.1", "libgomp.so"):
+        try:
+            ctypes.CDLL(name).omp_set_num_threads(n)
+            return n
+        except OSError:
+            continue
+    return 0
