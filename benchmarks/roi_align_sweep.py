@@ -75,7 +75,12 @@ def main():
             r = rois_np[b]
             wh = np.sqrt((r[:, 2] - r[:, 0] + 1) * (r[:, 3] - r[:, 1] + 1))
             lvl = np.clip(np.floor(4 + np.log2(wh / 224 + 1e-6)), 2, 5)
-            rois_np[b] = r[np.lexsort((r[:, 0], r[:, 1] // 32, lvl))]
+            if a.sorted == 1:
+                rois_np[b] = r[np.lexsort((r[:, 0], r[:, 1] // 32, lvl))]
+            else:  # 2: largest window first (longest-processing-time order: a scheduling probe)
+                s_ = 2.0 ** (lvl + 2)
+                cells = (np.ceil(r[:, 2] / s_) - np.floor(r[:, 0] / s_) + 2) * (np.ceil(r[:, 3] / s_) - np.floor(r[:, 1] / s_) + 2)
+                rois_np[b] = r[np.argsort(-cells, kind="stable")]
     rois = torch.from_numpy(rois_np).to(dev)
     flush = torch.empty(128 * 1024 * 1024, device=dev)
     out, _, _, lv = ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=False)
@@ -106,9 +111,22 @@ def main():
                 pooled, 0, torch.cuda.current_stream().cuda_stream))
 
     med, mn = time_op(fn, a.iters, flush, not a.noflush)
+    prof = None
+    try:  # profiling builds (-DSDET_RA_ABLATE) export per-phase cycle counters of the forward kernel
+        import ctypes as _ct
+        from simpledet_b200 import _lib as _l
+        f = _l.lib().sdet_debug_ra_prof  # AttributeError in product builds
+        f.argtypes, f.restype = [_ct.c_void_p, _ct.c_int], _ct.c_int
+        buf = (_ct.c_ulonglong * 4)()
+        f(buf, 1)
+        fn()
+        f(buf, 1)
+        prof = {"consumer_wait_cyc": buf[0], "consumer_compute_cyc": buf[1], "producer_wait_cyc": buf[3]}
+    except (AttributeError, OSError):
+        pass
     print(json.dumps({"shape": a.shape, "B": B, "N": N, "pooled": pooled, "argmax": a.argmax, "sorted": a.sorted, "backward": a.backward, "plan": a.plan, "noflush": a.noflush, "modepref": os.environ.get("SDET_RA_MODEPREF"), "tiles": os.environ.get("SDET_RA_TILES"),
                       "cpt": os.environ.get("SDET_RA_CPT"), "phs": os.environ.get("SDET_RA_PHS"),
-                      "us_median": round(med, 2), "us_min": round(mn, 2), "alg_bytes": nbytes,
+                      "prof": prof, "us_median": round(med, 2), "us_min": round(mn, 2), "alg_bytes": nbytes,
                       "GBps": round(nbytes / med / 1e3, 1),
                       "levels": np.bincount(lv.ravel() + 1, minlength=5).tolist()}))
 

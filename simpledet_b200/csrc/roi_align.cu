@@ -54,6 +54,7 @@ struct RoiAlignArgs {
   int32_t* levels_out;
   int B, N, C, PH, PW;
   const void* plans;  // per-roi preamble records written by roi_align_plan_kernel, or nullptr
+  const int* order;   // CTA x -> roi, largest window first (roi_align_order_kernel), or nullptr = identity
   uint64_t negzero2;  // {-0.0f,-0.0f}: opaque addend that keeps FFMA2 products exact
 };
 
@@ -317,8 +318,20 @@ struct PlanRecord {  // what a (roi, channel group) CTA needs from the preamble 
 };
 static_assert(sizeof(PlanRecord) % 16 == 0, "PlanRecord is copied with 16-byte accesses");
 
+// Scheduling.  CTA run time grows with the roi's window (bytes staged), and windows span 100..1500
+// cells: in launch order the last wave is held up by whichever large rois happen to start late
+// (measured: 17 % of the 7x7 kernel, 8 % of the 14x14 one).  The plan kernel therefore also files
+// every roi into one of kCostBuckets window-size classes (atomic rank inside the class) and
+// roi_align_order_kernel turns that into a largest-first order for the main kernel's blockIdx.x.
+constexpr int kCostBuckets = 64;
+struct PlanSched {
+  int* counts;   // kCostBuckets, zeroed before the plan kernel
+  int2* slot;    // (bucket, rank) per roi
+  int* order;    // position -> roi
+};
+
 __global__ void __launch_bounds__(64) roi_align_plan_kernel(const __grid_constant__ RoiAlignArgs a,
-                                                            PlanRecord* __restrict__ plans) {
+                                                            PlanRecord* __restrict__ plans, const PlanSched sc) {
   __shared__ __align__(16) PlanRecord s_rec;
   const int n = blockIdx.x;
   roi_preamble<16>(a, n, a.PH, a.PW, s_rec.th, s_rec.tw, s_rec.scal);
@@ -326,11 +339,40 @@ __global__ void __launch_bounds__(64) roi_align_plan_kernel(const __grid_constan
   const int4* src = reinterpret_cast<const int4*>(&s_rec);
   int4* dst = reinterpret_cast<int4*>(plans + n);
   for (int i = threadIdx.x; i < (int)(sizeof(PlanRecord) / 16); i += blockDim.x) dst[i] = src[i];
+  if (threadIdx.x == 0) {
+    int bucket = 0;  // no level / empty window: cheapest
+    if (s_rec.scal[0] >= 0 && s_rec.scal[3] >= 0 && s_rec.scal[5] >= 0) {
+      const int hwin = s_rec.scal[3] - s_rec.scal[2] + 1, wwin = s_rec.scal[5] - s_rec.scal[4] + 1;
+      const int cells = hwin * ((wwin + 6) & ~3);
+      bucket = min(kCostBuckets - 1, 1 + cells / 24);
+      if (s_rec.scal[1] & (kFlagNot2 | kFlagOverflow)) bucket = kCostBuckets - 1;  // generic path: slowest
+    }
+    sc.slot[n] = make_int2(bucket, atomicAdd(&sc.counts[bucket], 1));
+  }
+}
+
+__global__ void __launch_bounds__(256) roi_align_order_kernel(const PlanSched sc, const int total) {
+  __shared__ int s_base[kCostBuckets];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = kCostBuckets - 1; b >= 0; --b) {  // largest class first
+      s_base[b] = acc;
+      acc += sc.counts[b];
+    }
+  }
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < total) {
+    const int2 s = sc.slot[n];
+    sc.order[s_base[s.x] + s.y] = n;
+  }
 }
 
 // kCapFloats: floats of dynamic shared memory for the window buffers (12288 = 48 KB -> 4 CTAs/SM)
 #ifdef SDET_RA_ABLATE  // profiling builds only: bit 0 skips compute, bit 1 skips staging (results are garbage)
 __device__ int g_ra_ablate = 0;
+// consumer-warp cycle counters: [0] waiting for a full buffer, [1] computing, [2] whole kernel body, [3] producer waiting
+__device__ unsigned long long g_ra_prof[4] = {0, 0, 0, 0};
 #endif
 
 // CTA = 4 consumer warps (the arithmetic) + 1 producer warp (all cp.async staging).  Staging and
@@ -353,7 +395,7 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
   static_assert(CPT % 4 == 0, "channels are processed in fp32x2 pairs, per half-warp when PW <= 8");
 
   const int tid = threadIdx.x;
-  const int n = blockIdx.x;
+  const int n = a.order ? __ldg(a.order + blockIdx.x) : (int)blockIdx.x;
   const int C = a.C;
   const int PH = kPH ? kPH : a.PH, PW = kPW ? kPW : a.PW;
   const int PP = PH * PW;
@@ -698,22 +740,50 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
 
     // ---- producer / consumer pipeline over the channel tiles of this roi (ring of NBUF buffers) ----
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(s_bar);
+#ifdef SDET_RA_ABLATE
+    long long prof_wait = 0, prof_comp = 0;
+#endif
     if (warp == NW) {
       for (int t = 0; t < ntiles; ++t) {
         const int b = t % NBUF, k = t / NBUF;
+#ifdef SDET_RA_ABLATE
+        const long long c0 = clock64();
+#endif
         if (k > 0) mbar_wait(bar0 + 8u * (4 + b), (unsigned)((k - 1) & 1));  // consumers released the buffer
+#ifdef SDET_RA_ABLATE
+        prof_wait += clock64() - c0;
+#endif
         stage(t, sbase + (unsigned)b * BUF_BYTES);
         cp_async_mbar_arrive(bar0 + 8u * b);
       }
+#ifdef SDET_RA_ABLATE
+      if (lane == 0) atomicAdd(&g_ra_prof[3], (unsigned long long)prof_wait);
+#endif
       return;
     }
     for (int t = 0; t < ntiles; ++t) {
       const int b = t % NBUF, k = t / NBUF;
+#ifdef SDET_RA_ABLATE
+      const long long c0 = clock64();
+#endif
       mbar_wait(bar0 + 8u * b, (unsigned)(k & 1));   // tile t has landed
+#ifdef SDET_RA_ABLATE
+      const long long c1 = clock64();
+#endif
       compute(t, sbase + (unsigned)b * BUF_BYTES);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar0 + 8u * (4 + b));
+#ifdef SDET_RA_ABLATE
+      prof_wait += c1 - c0;
+      prof_comp += clock64() - c1;
+#endif
     }
+#ifdef SDET_RA_ABLATE
+    if (lane == 0) {
+      atomicAdd(&g_ra_prof[0], (unsigned long long)prof_wait);
+      atomicAdd(&g_ra_prof[1], (unsigned long long)prof_comp);
+    }
+#endif
   };
 
   // (channel stride, channel groups per tile, ring depth) by window size.  With the producer warp a
@@ -828,20 +898,37 @@ int launch_fwd_t(const RoiAlignArgs& a, cudaStream_t st) {
   return SDET_OK;
 }
 
+// PlanRecord[B*N] | counts[64] | (bucket, rank)[B*N] | order[B*N]
+size_t plan_workspace_bytes(int B, int N) {
+  const size_t total = (size_t)B * N;
+  return sizeof(PlanRecord) * total + 256 + 8 * total + 4 * total;
+}
+
 int launch_fwd(RoiAlignArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if ((a.argx == nullptr) != (a.argy == nullptr))
     return sdet::fail(SDET_ERR_INVALID_ARG, "argmax_x and argmax_y must both be given or both NULL");
   a.negzero2 = 0x8000000080000000ull;  // {-0.0f, -0.0f}, see the forward kernel's header
   a.plans = nullptr;
+  a.order = nullptr;
   if (workspace != nullptr && a.PH <= 16 && a.PW <= 16) {
-    const size_t need = sizeof(PlanRecord) * (size_t)a.B * a.N;
+    const size_t total = (size_t)a.B * a.N;
+    const size_t need = plan_workspace_bytes(a.B, a.N);
     if (workspace_bytes < need)
       return sdet::fail(SDET_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
     if (reinterpret_cast<uintptr_t>(workspace) % 16)
       return sdet::fail(SDET_ERR_INVALID_ARG, "workspace must be 16-byte aligned");
-    roi_align_plan_kernel<<<(unsigned)(a.B * a.N), 64, 0, st>>>(a, static_cast<PlanRecord*>(workspace));
+    char* w = static_cast<char*>(workspace);
+    PlanSched sc{};
+    sc.counts = reinterpret_cast<int*>(w + sizeof(PlanRecord) * total);
+    sc.slot = reinterpret_cast<int2*>(w + sizeof(PlanRecord) * total + 256);
+    sc.order = reinterpret_cast<int*>(w + sizeof(PlanRecord) * total + 256 + 8 * total);
+    SDET_CUDA(cudaMemsetAsync(sc.counts, 0, sizeof(int) * kCostBuckets, st));
+    roi_align_plan_kernel<<<(unsigned)total, 64, 0, st>>>(a, static_cast<PlanRecord*>(workspace), sc);
     SDET_LAUNCH_CHECK("roi_align_plan_kernel");
+    roi_align_order_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sc, (int)total);
+    SDET_LAUNCH_CHECK("roi_align_order_kernel");
     a.plans = workspace;
+    a.order = sc.order;
   }
   if (a.PH == 7 && a.PW == 7) return launch_fwd_t<8, 7, 7, 12288>(a, st);
   if (a.PH == 14 && a.PW == 14) return launch_fwd_t<8, 14, 14, 12288>(a, st);
@@ -851,8 +938,20 @@ int launch_fwd(RoiAlignArgs& a, void* workspace, size_t workspace_bytes, cudaStr
 }  // namespace
 
 
+#ifdef SDET_RA_ABLATE
+extern "C" int sdet_debug_ra_prof(unsigned long long* out4, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out4, g_ra_prof, sizeof(unsigned long long) * 4);
+  if (reset) {
+    unsigned long long z[4] = {0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_ra_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
+
 extern "C" size_t sdet_roi_align_v2_workspace(int B, int N) {
-  return (B > 0 && N > 0) ? sizeof(PlanRecord) * (size_t)B * N : 0;
+  return (B > 0 && N > 0) ? plan_workspace_bytes(B, N) : 0;
 }
 
 extern "C" int sdet_roi_align_v2_forward(const float* data, const float* rois, float* out,
