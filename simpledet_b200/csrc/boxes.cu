@@ -126,8 +126,17 @@ nms_mask_kernel(const float* __restrict__ dets, const int* __restrict__ counts, 
     for (int k = 0; k < 4; ++k) cb[k] = d[(size_t)cur * 5 + k];
     unsigned long long bits = 0;
     const int start = (row_b == col_b) ? t + 1 : 0;
+    // Disjoint pairs (the vast majority) have IoU = 0/union: never above a positive threshold, and a
+    // NaN union compares false as well — decided without the division.  thr <= 0 takes the full path.
+    const bool skip_disjoint = thr > 0.f;
     for (int i = start; i < col_size; ++i) {
-      const float v = dev_iou(cb, sb + i * 5);
+      const float* q = sb + i * 5;
+      if (skip_disjoint) {
+        const float w = __fadd_rn(__fsub_rn(fmin_ref(cb[2], q[2]), fmax_ref(cb[0], q[0])), 1.f);
+        const float h = __fadd_rn(__fsub_rn(fmin_ref(cb[3], q[3]), fmax_ref(cb[1], q[1])), 1.f);
+        if (!(w > 0.f && h > 0.f)) continue;
+      }
+      const float v = dev_iou(cb, q);
       if (ge ? (v >= thr) : (v > thr)) bits |= 1ull << i;
     }
     mask[((size_t)p * n_max + cur) * col_blocks + col_b] = bits;
@@ -161,6 +170,7 @@ nms_scan_kernel(const float* __restrict__ dets, const int* __restrict__ counts, 
   unsigned long long* s_rows0 = s_dyn + cbs;      // nbuf x 64 x cbs words (mask rows of a block)
   int* s_keep = reinterpret_cast<int*>(s_rows0 + (size_t)nbuf * 64 * cbs);  // n_max ints
   __shared__ int s_nkeep;
+  __shared__ unsigned long long s_alive;
   const int tid = threadIdx.x;
   for (int i = tid; i < cbs; i += blockDim.x) s_removed[i] = 0ull;
   if (tid == 0) s_nkeep = 0;
@@ -185,20 +195,33 @@ nms_scan_kernel(const float* __restrict__ dets, const int* __restrict__ counts, 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (nbuf == 2 && rb + 1 < nblocks) stage_rows(rb + 1, s_rows0 + (size_t)((rb + 1) & 1) * 64 * cbs);
-    // The serial greedy dependency lives entirely inside the block's DIAGONAL word: every thread
-    // resolves it redundantly in registers (64 steps, broadcast LDS, no barrier), then the kept
-    // rows' words are OR-ed into `removed` in parallel (thread w owns word w).
-    unsigned long long alive = ~s_removed[rb];
-    if (rows < 64) alive &= (1ull << rows) - 1ull;
-    // branch-free and unrolled: the diagonal words are loaded in batches ahead of the dependent
-    // AND chain (rows beyond `rows` are already cleared in `alive`, their words are never applied)
-#pragma unroll 16
-    for (int r = 0; r < 64; ++r) {
-      const unsigned long long w = (r < rows) ? s_rows[r * cbs + rb] : 0ull;
-      alive &= ~(((alive >> r) & 1ull) ? w : 0ull);
+    // The serial greedy dependency lives entirely inside the block's DIAGONAL words; afterwards the
+    // kept rows' words are OR-ed into `removed` in parallel (thread w owns word w).
+    // The serial part: one warp walks the 64 diagonal words in 32-bit halves (row r's word only has
+    // bits above r, so rows >= 32 never touch the low half); fully predicated, 4 instructions a row.
+    if (tid < 32) {
+      unsigned long long alive = ~s_removed[rb];
+      if (rows < 64) alive &= (1ull << rows) - 1ull;   // (their words are never applied below)
+      unsigned lo = (unsigned)alive, hi = (unsigned)(alive >> 32);
+      const uint2* diag = reinterpret_cast<const uint2*>(s_rows + rb);
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const uint2 w = diag[(size_t)r * cbs];
+        if (lo & (1u << r)) {
+          lo &= ~w.x;
+          hi &= ~w.y;
+        }
+      }
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const uint2 w = diag[(size_t)(r + 32) * cbs];
+        if (hi & (1u << r)) hi &= ~w.y;
+      }
+      if (tid == 0) s_alive = ((unsigned long long)hi << 32) | lo;
     }
     const int nk0 = s_nkeep;
-    __syncthreads();  // every thread has read s_removed[rb] / s_nkeep before they change
+    __syncthreads();  // s_alive is published; s_removed[rb] / s_nkeep have been read before they change
+    const unsigned long long alive = s_alive;
     for (int w = rb + 1 + tid; w < cbs; w += blockDim.x) {
       unsigned long long acc = s_removed[w];
       unsigned long long bits = alive;
