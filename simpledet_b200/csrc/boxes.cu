@@ -195,42 +195,50 @@ nms_scan_kernel(const float* __restrict__ dets, const int* __restrict__ counts, 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (nbuf == 2 && rb + 1 < nblocks) stage_rows(rb + 1, s_rows0 + (size_t)((rb + 1) & 1) * 64 * cbs);
-    // The serial greedy dependency lives entirely inside the block's DIAGONAL words; afterwards the
-    // kept rows' words are OR-ed into `removed` in parallel (thread w owns word w).
-    // The serial part: one warp walks the 64 diagonal words in 32-bit halves (row r's word only has
-    // bits above r, so rows >= 32 never touch the low half); fully predicated, 4 instructions a row.
+    // The serial greedy dependency lives entirely inside the block's DIAGONAL words.  Warp 0 holds
+    // them in registers (lane l: rows l and l+32) and walks the 64 rows with shuffles whose source
+    // lane is known in advance — only three ALU operations per row sit on the dependent chain.
+    // Row r's word has bits above r only, so rows >= 32 never touch the low half.
     if (tid < 32) {
-      unsigned long long alive = ~s_removed[rb];
-      if (rows < 64) alive &= (1ull << rows) - 1ull;   // (their words are never applied below)
-      unsigned lo = (unsigned)alive, hi = (unsigned)(alive >> 32);
+      unsigned long long alive0 = ~s_removed[rb];
+      if (rows < 64) alive0 &= (1ull << rows) - 1ull;   // (their words are never applied below)
+      unsigned lo = (unsigned)alive0, hi = (unsigned)(alive0 >> 32);
       const uint2* diag = reinterpret_cast<const uint2*>(s_rows + rb);
-#pragma unroll 8
+      const uint2 wa = diag[(size_t)tid * cbs], wb = diag[(size_t)(tid + 32) * cbs];
+#pragma unroll
       for (int r = 0; r < 32; ++r) {
-        const uint2 w = diag[(size_t)r * cbs];
-        if (lo & (1u << r)) {
-          lo &= ~w.x;
-          hi &= ~w.y;
-        }
+        const unsigned wx = __shfl_sync(0xffffffffu, wa.x, r), wy = __shfl_sync(0xffffffffu, wa.y, r);
+        const unsigned m = (unsigned)((int)(lo << (31 - r)) >> 31);   // all ones if row r is alive
+        lo &= ~(wx & m);
+        hi &= ~(wy & m);
       }
-#pragma unroll 8
+#pragma unroll
       for (int r = 0; r < 32; ++r) {
-        const uint2 w = diag[(size_t)(r + 32) * cbs];
-        if (hi & (1u << r)) hi &= ~w.y;
+        const unsigned wy = __shfl_sync(0xffffffffu, wb.y, r);
+        const unsigned m = (unsigned)((int)(hi << (31 - r)) >> 31);
+        hi &= ~(wy & m);
       }
       if (tid == 0) s_alive = ((unsigned long long)hi << 32) | lo;
     }
     const int nk0 = s_nkeep;
     __syncthreads();  // s_alive is published; s_removed[rb] / s_nkeep have been read before they change
     const unsigned long long alive = s_alive;
-    for (int w = rb + 1 + tid; w < cbs; w += blockDim.x) {
-      unsigned long long acc = s_removed[w];
-      unsigned long long bits = alive;
-      while (bits) {
-        const int r = __ffsll((long long)bits) - 1;
-        bits &= bits - 1ull;
-        acc |= s_rows[r * cbs + w];
+    // OR the kept rows' words into `removed`: 16 lanes per word, each takes the rows r = g (mod 16);
+    // the loads are independent, the 16 partial words meet in a shuffle tree.
+    {
+      const int g = tid & 15;
+      const unsigned hmask = 0xFFFFu << (tid & 16);  // the two half-warps own different words
+      for (int w = rb + 1 + (tid >> 4); w < cbs; w += (int)(blockDim.x >> 4)) {
+        unsigned long long acc = 0ull;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = g + 16 * j;
+          if ((alive >> r) & 1ull) acc |= s_rows[r * cbs + w];
+        }
+#pragma unroll
+        for (int o = 8; o; o >>= 1) acc |= __shfl_xor_sync(hmask, acc, o);
+        if (g == 0) s_removed[w] |= acc;
       }
-      s_removed[w] = acc;
     }
     if (tid < 64 && ((alive >> tid) & 1ull))
       s_keep[nk0 + __popcll(alive & ((1ull << tid) - 1ull))] = rb * 64 + tid;
