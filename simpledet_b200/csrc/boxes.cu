@@ -302,6 +302,10 @@ struct ProposalParams {
   float* dets;             // (num_levels*B, pre_max, 5), problem p = l*B + b
   int* counts;             // (num_levels*B) = pre of the level
   unsigned long long* cand;  // chunk winners (keys), zero-padded
+  int cache_keys;            // u64 slots of shared memory after the selection buffer (0 = none): the keys of
+                             // a problem are materialised there once instead of being re-derived from
+                             // global memory in each of the 4-5 selection sweeps (those sweeps are
+                             // latency-bound: one dependent load per 1024 elements)
 };
 
 // Large levels (P2 of an 800x1333 image has 201 600 anchors) would leave one CTA sweeping the whole
@@ -309,7 +313,7 @@ struct ProposalParams {
 // CTA selects its own top-`pre` keys; the per-problem CTA then selects among nchunks*pre keys.
 // Exact: the top-k of a union is contained in the union of the parts' top-k, and keys are unique.
 constexpr int kChunkElems = 16384;
-inline int level_chunks(int count) { return count > 2 * kChunkElems ? (count + kChunkElems - 1) / kChunkElems : 1; }
+inline int level_chunks(int count) { return count > kChunkElems ? (count + kChunkElems - 1) / kChunkElems : 1; }
 
 // (rh, rw) = cells inside the un-padded image, only consulted by the iou_loss path; pass W for rw to disable
 __device__ __forceinline__ uint64_t proposal_key(const float* fg, int i, int HW, int A, unsigned magic, int W = 1,
@@ -350,9 +354,21 @@ proposal_chunk_topk_kernel(const __grid_constant__ ProposalParams p) {
     rh = (int)__fdiv_rn(__ldg(p.im_info + b * 3), (float)L.stride);
     rw = (int)__fdiv_rn(__ldg(p.im_info + b * 3 + 1), (float)L.stride);
   }
-  auto key_at = [&](int i) -> uint64_t { return proposal_key(fg, i0 + i, HW, A, magic, L.W, rh, rw); };
   const int k = min(pre, n);
-  sdet::block_topk_sorted<false>(n, k, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+  if (p.cache_keys >= kChunkElems) {
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_sel) + p.k_pow2;
+#pragma unroll
+    for (int it = 0; it < kChunkElems / kTopkThreads; ++it) {  // independent loads, all in flight together
+      const int i = threadIdx.x + it * kTopkThreads;
+      if (i < n) s_keys[i] = proposal_key(fg, i0 + i, HW, A, magic, L.W, rh, rw);
+    }
+    __syncthreads();
+    auto key_at = [&](int i) -> uint64_t { return s_keys[i]; };
+    sdet::block_topk_sorted<false>(n, k, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+  } else {
+    auto key_at = [&](int i) -> uint64_t { return proposal_key(fg, i0 + i, HW, A, magic, L.W, rh, rw); };
+    sdet::block_topk_sorted<false>(n, k, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+  }
   unsigned long long* dst = p.cand + L.cand_off + ((size_t)b * L.nchunks + chunk) * pre;
   for (int j = threadIdx.x; j < pre; j += blockDim.x) dst[j] = (j < k) ? s_sel[j] : 0ull;  // 0 < every real key
 }
@@ -369,8 +385,18 @@ proposal_topk_kernel(const __grid_constant__ ProposalParams p) {
   const float* fg = L.cls_prob + (size_t)b * 2 * count + count;  // second half = foreground (:522)
   if (L.nchunks > 1) {  // chunk winners, written by proposal_chunk_topk_kernel
     const unsigned long long* cand = p.cand + L.cand_off + (size_t)b * L.nchunks * pre;
-    auto key_at = [&](int i) -> uint64_t { return cand[i]; };
-    sdet::block_topk_sorted(L.nchunks * pre, pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+    const int nc = L.nchunks * pre;
+    if (nc <= p.cache_keys) {
+      uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_sel) + p.k_pow2;
+#pragma unroll 4
+      for (int i = threadIdx.x; i < nc; i += kTopkThreads) s_keys[i] = cand[i];
+      __syncthreads();
+      auto key_at = [&](int i) -> uint64_t { return s_keys[i]; };
+      sdet::block_topk_sorted(nc, pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+    } else {
+      auto key_at = [&](int i) -> uint64_t { return cand[i]; };
+      sdet::block_topk_sorted(nc, pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+    }
   } else {
     const unsigned magic = 0xFFFFFFFFu / (unsigned)HW;
     int rh = 0x7FFFFFFF, rw = 0x7FFFFFFF;
@@ -378,8 +404,17 @@ proposal_topk_kernel(const __grid_constant__ ProposalParams p) {
       rh = (int)__fdiv_rn(__ldg(p.im_info + b * 3), (float)L.stride);
       rw = (int)__fdiv_rn(__ldg(p.im_info + b * 3 + 1), (float)L.stride);
     }
-    auto key_at = [&](int i) -> uint64_t { return proposal_key(fg, i, HW, A, magic, W, rh, rw); };
-    sdet::block_topk_sorted(count, pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+    if (count <= p.cache_keys) {
+      uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_sel) + p.k_pow2;
+#pragma unroll 4
+      for (int i = threadIdx.x; i < count; i += kTopkThreads) s_keys[i] = proposal_key(fg, i, HW, A, magic, W, rh, rw);
+      __syncthreads();
+      auto key_at = [&](int i) -> uint64_t { return s_keys[i]; };
+      sdet::block_topk_sorted(count, pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+    } else {
+      auto key_at = [&](int i) -> uint64_t { return proposal_key(fg, i, HW, A, magic, W, rh, rw); };
+      sdet::block_topk_sorted(count, pre, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), p.k_pow2);
+    }
   }
   if (threadIdx.x == 0) p.counts[prob] = pre;
   // decode only the winners
@@ -759,7 +794,9 @@ extern "C" int sdet_proposal_v3_fpn(const float* const* cls_prob, const float* c
   p.counts = counts;
   p.cand = reinterpret_cast<unsigned long long*>(wsb + proposal_ws_bytes(P, pre_max));
   static size_t configured = 0, configured_chunk = 0;
-  const size_t smem = (size_t)p.k_pow2 * 8;
+  // key cache: kChunkElems slots if the selection buffer leaves room for them (176 KB budget)
+  p.cache_keys = ((size_t)p.k_pow2 * 8 + (size_t)kChunkElems * 8 <= 176 * 1024) ? kChunkElems : 0;
+  const size_t smem = (size_t)p.k_pow2 * 8 + (size_t)p.cache_keys * 8;
   if (chunk_ctas > 0) {
     if (int rc = ensure_smem(proposal_chunk_topk_kernel, smem, &configured_chunk)) return rc;
     proposal_chunk_topk_kernel<<<(unsigned)chunk_ctas, kTopkThreads, smem, st>>>(p);
