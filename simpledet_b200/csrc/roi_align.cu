@@ -382,7 +382,7 @@ __device__ unsigned long long g_ra_prof[4] = {0, 0, 0, 0};
 constexpr int kFwdThreads = 160;
 
 template <int CPT, bool kArg, int kPH, int kPW, int kCapFloats>
-__global__ void __launch_bounds__(kFwdThreads, 4)
+__global__ void __launch_bounds__(kFwdThreads, (kCapFloats <= 10240 ? 5 : 4))
 roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles) {
   extern __shared__ __align__(16) float s_win[];
   constexpr int TP = (kPH > 0 && kPH <= 16 && kPW <= 16) ? 16 : kMaxP;
@@ -930,6 +930,9 @@ int launch_fwd(RoiAlignArgs& a, void* workspace, size_t workspace_bytes, cudaStr
     a.plans = workspace;
     a.order = sc.order;
   }
+#ifdef SDET_RA_CAP7
+  if (a.PH == 7 && a.PW == 7) return launch_fwd_t<8, 7, 7, SDET_RA_CAP7>(a, st);
+#endif
   if (a.PH == 7 && a.PW == 7) return launch_fwd_t<8, 7, 7, 12288>(a, st);
   if (a.PH == 14 && a.PW == 14) return launch_fwd_t<8, 14, 14, 12288>(a, st);
   return launch_fwd_t<8, 0, 0, 12288>(a, st);
