@@ -347,6 +347,20 @@ int sdet_deformable_col2im(const float* grad_col, const float* data, const float
                            int pad_h, int pad_w, int stride_h, int stride_w, int dilate_h, int dilate_w,
                            int num_deformable_group, void* stream);
 
+/* operator_py/nms.py:77-107 set_nms over boxes already sorted by descending score: like sdet_nms_sorted
+ * with `>` (the reference keeps ovr <= thresh), but boxes whose `sets` value (P,n; column 5 of the
+ * reference's dets) is equal never suppress each other. */
+int sdet_set_nms_sorted(const float* dets, const float* sets, const int* counts, int problems, int n,
+                        float thresh, int* keep, int* nkeep, void* workspace, size_t workspace_bytes,
+                        void* stream);
+/* operator_py/nms.py:110-157 py_weighted_nms over pre-sorted boxes: out (P,n,5) rows [score-weighted
+ * mean box of the pool members with IoU > thresh_hi, score of the top box], nout (P) rows valid.  Sums
+ * are float32 in warp order (numpy's pairwise order differs in the last bits). */
+size_t sdet_weighted_nms_workspace(int problems, int n);
+int sdet_weighted_nms_sorted(const float* dets, const int* counts, int problems, int n, float thresh_lo,
+                             float thresh_hi, float* out, int* nout, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* operator_py/cython/bbox.pyx:32-73 (mode 0, IoU) and bbox_self.pyx:32-75 (mode 1, intersection over the
  * area of boxes[n]): boxes (N,4), query_boxes (K,4) -> overlaps (N,K), float32, bit-exact with the
  * compiled Cython (whose `+ 1` terms are evaluated in double). */

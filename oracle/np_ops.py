@@ -45,6 +45,49 @@ def py_nms(dets, thresh):
     return dets[keep, :]
 
 
+def _pair_iou(dets, i, js):
+    """IoU of box i with boxes js, float32, the expression order of operator_py/nms.py:62-69."""
+    x1, y1, x2, y2 = dets[:, 0], dets[:, 1], dets[:, 2], dets[:, 3]
+    areas = (x2 - x1 + 1) * (y2 - y1 + 1)
+    w = np.maximum(0.0, np.minimum(x2[i], x2[js]) - np.maximum(x1[i], x1[js]) + 1)
+    h = np.maximum(0.0, np.minimum(y2[i], y2[js]) - np.maximum(y1[i], y1[js]) + 1)
+    inter = w * h
+    return inter / (areas[i] + areas[js] - inter)
+
+
+def set_nms(dets, thresh):
+    """operator_py/nms.py:77-107: greedy NMS in which boxes of the same set (column 5) never
+    suppress each other -> kept rows (m', 6)."""
+    dets = np.asarray(dets, np.float32)
+    order = dets[:, 4].argsort()[::-1]
+    keep = []
+    while order.size:
+        i, rest = order[0], order[1:]
+        keep.append(i)
+        ovr = _pair_iou(dets, i, rest)
+        order = rest[(ovr <= thresh) | (dets[rest, 5] == dets[i, 5])]
+    return dets[keep, :]
+
+
+def py_weighted_nms(dets, thresh_lo, thresh_hi):
+    """operator_py/nms.py:110-157: every surviving top box is replaced by the score-weighted mean of
+    the remaining boxes with IoU > thresh_hi; boxes with IoU > thresh_lo leave the pool."""
+    dets = np.asarray(dets, np.float32)
+    scores = dets[:, 4]
+    order = scores.argsort()[::-1]
+    out = []
+    while order.size:
+        i = order[0]
+        ovr = _pair_iou(dets, i, order)
+        voters = order[ovr > thresh_hi]
+        if len(voters) == 0:
+            break
+        sw = np.sum(scores[voters])
+        out.append([np.sum(scores[voters] * dets[voters, k]) / sw for k in range(4)] + [scores[i]])
+        order = order[ovr <= thresh_lo]
+    return np.array(out)
+
+
 def do_nms(cls_score, bbox_xyxy, nms_thresh, min_det_score):
     """detection_test.py:233-260 for one image: {cid: kept dets (m,5)}."""
     out = {}

@@ -62,6 +62,9 @@ _SIGNATURES = {
     "sdet_gen_proposal_retina_workspace": [c_int, c_int, c_int, c_int],
     "sdet_gen_proposal_retina": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_float, POINTER(c_float), POINTER(c_float), c_int, c_int, c_int, _P, c_size_t, _P],
+    "sdet_set_nms_sorted": [_P, _P, _P, c_int, c_int, c_float, _P, _P, _P, c_size_t, _P],
+    "sdet_weighted_nms_workspace": [c_int, c_int],
+    "sdet_weighted_nms_sorted": [_P, _P, c_int, c_int, c_float, c_float, _P, _P, _P, c_size_t, _P],
     "sdet_bbox_overlaps": [_P, _P, _P, c_int, c_int, c_int, _P],
     "sdet_bbox_nonlinear_transform": [_P, _P, _P, c_int, _P],
     "sdet_bbox_pred": [_P, _P, _P, c_int, c_int, c_int, c_int, c_double, c_double, _P],
@@ -96,7 +99,7 @@ _SIGNATURES = {
 }
 _RESTYPES = {"sdet_last_error": c_char_p, "sdet_launch_count": c_uint64,
              "sdet_proposal_v3_workspace": c_size_t, "sdet_proposal_legacy_workspace": c_size_t,
-             "sdet_gen_proposal_workspace": c_size_t, "sdet_anchor_target_workspace": c_size_t, "sdet_gen_proposal_retina_workspace": c_size_t, "sdet_proposal_v3_fpn_workspace": c_size_t, "sdet_contrib_nms_workspace": c_size_t,
+             "sdet_gen_proposal_workspace": c_size_t, "sdet_anchor_target_workspace": c_size_t, "sdet_weighted_nms_workspace": c_size_t, "sdet_gen_proposal_retina_workspace": c_size_t, "sdet_proposal_v3_fpn_workspace": c_size_t, "sdet_contrib_nms_workspace": c_size_t,
              "sdet_nms_workspace": c_size_t, "sdet_roi_align_v2_workspace": c_size_t, "sdet_multiclass_nms_workspace": c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -104,7 +104,8 @@ __device__ __forceinline__ float dev_iou(const float* a, const float* b) {
 // grid = (col_blocks, row_blocks, P); only col >= row tiles do work.  64 threads.
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const float* __restrict__ dets, const int* __restrict__ counts, const int n_max,
-                const float thr, const int ge, unsigned long long* __restrict__ mask) {
+                const float thr, const int ge, unsigned long long* __restrict__ mask,
+                const float* __restrict__ sets) {  // sets (P,n_max) or nullptr: set_nms (nms.py:77-107)
   const int row_b = blockIdx.y, col_b = blockIdx.x, p = blockIdx.z;
   if (col_b < row_b) return;  // the scan only reads words j >= row block (proposal_v3.cu:373)
   const int n = counts ? counts[p] : n_max;
@@ -113,10 +114,12 @@ nms_mask_kernel(const float* __restrict__ dets, const int* __restrict__ counts, 
   if (row_size <= 0 || col_size <= 0) return;
   const float* d = dets + (size_t)p * n_max * 5;
   __shared__ float sb[64 * 5];
+  __shared__ float s_set[64];
   const int t = threadIdx.x;
   if (t < col_size) {
 #pragma unroll
     for (int k = 0; k < 5; ++k) sb[t * 5 + k] = d[(size_t)(col_b * 64 + t) * 5 + k];
+    if (sets) s_set[t] = sets[(size_t)p * n_max + col_b * 64 + t];
   }
   __syncthreads();
   if (t < row_size) {
@@ -125,6 +128,7 @@ nms_mask_kernel(const float* __restrict__ dets, const int* __restrict__ counts, 
 #pragma unroll
     for (int k = 0; k < 4; ++k) cb[k] = d[(size_t)cur * 5 + k];
     unsigned long long bits = 0;
+    const float my_set = sets ? sets[(size_t)p * n_max + cur] : 0.f;
     const int start = (row_b == col_b) ? t + 1 : 0;
     // Disjoint pairs (the vast majority) have IoU = 0/union: never above a positive threshold, and a
     // NaN union compares false as well — decided without the division.  thr <= 0 takes the full path.
@@ -136,6 +140,7 @@ nms_mask_kernel(const float* __restrict__ dets, const int* __restrict__ counts, 
         const float h = __fadd_rn(__fsub_rn(fmin_ref(cb[3], q[3]), fmax_ref(cb[1], q[1])), 1.f);
         if (!(w > 0.f && h > 0.f)) continue;
       }
+      if (sets && s_set[i] == my_set) continue;  // members of one set never suppress each other
       const float v = dev_iou(cb, q);
       if (ge ? (v >= thr) : (v > thr)) bits |= 1ull << i;
     }
@@ -625,10 +630,10 @@ size_t nms_ws_bytes(int P, int n) {
 }
 
 int run_mask_and_scan(const float* dets, const int* counts, int P, int n, float thr, int ge,
-                      unsigned long long* mask, const ScanOut& so, cudaStream_t st) {
+                      unsigned long long* mask, const ScanOut& so, cudaStream_t st, const float* sets = nullptr) {
   const int cbs = (n + 63) / 64;
   dim3 grid((unsigned)cbs, (unsigned)cbs, (unsigned)P);
-  nms_mask_kernel<<<grid, 64, 0, st>>>(dets, counts, n, thr, ge, mask);
+  nms_mask_kernel<<<grid, 64, 0, st>>>(dets, counts, n, thr, ge, mask, sets);
   SDET_LAUNCH_CHECK("nms_mask_kernel");
   const int nbuf = scan_smem_bytes(n, 2) <= 96 * 1024 ? 2 : 1;
   const size_t smem = scan_smem_bytes(n, nbuf);
@@ -703,6 +708,117 @@ extern "C" int sdet_nms_sorted(const float* dets, const int* counts, int problem
   so.keep = keep;
   so.nkeep = nkeep;
   return run_mask_and_scan(dets, counts, problems, n, thresh, ge, mask, so, (cudaStream_t)stream);
+}
+
+
+// set_nms (operator_py/nms.py:77-107) over pre-sorted boxes: `sets` (P,n) holds column 5.
+extern "C" int sdet_set_nms_sorted(const float* dets, const float* sets, const int* counts, int problems, int n,
+                                   float thresh, int* keep, int* nkeep, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  SDET_REQUIRE(dets && sets && keep && nkeep && workspace, "NULL argument");
+  SDET_REQUIRE(problems > 0 && n > 0, "problems and n must be > 0");
+  if (workspace_bytes < nms_ws_bytes(problems, n))
+    return sdet::fail(SDET_ERR_WORKSPACE, "workspace too small: need %zu bytes", nms_ws_bytes(problems, n));
+  auto* mask = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) +
+                                                     align_up((size_t)problems * n * 5 * 4, 256));
+  ScanOut so{};
+  so.keep = keep;
+  so.nkeep = nkeep;
+  return run_mask_and_scan(dets, counts, problems, n, thresh, /*ge=*/0, mask, so, (cudaStream_t)stream, sets);
+}
+
+namespace {
+// py_weighted_nms (operator_py/nms.py:110-157) after the greedy scan at thresh_lo.  A box j leaves the
+// pool at the first kept box k with IoU(k,j) > lo (itself if it is kept: IoU = 1), so "still in the
+// pool when i is on top" is first_suppressor(j) >= i, and every kept i averages the boxes of the pool
+// with IoU(i,j) > hi, weighted by score.
+__global__ void __launch_bounds__(256)
+weighted_vote_kernel(const float* __restrict__ dets, const int* __restrict__ counts, const int n_max,
+                     const unsigned long long* __restrict__ mask, const int* __restrict__ keep,
+                     const int* __restrict__ nkeep, const float thr_hi, int* __restrict__ first_sup,
+                     float* __restrict__ out, int* __restrict__ nout) {
+  const int p = blockIdx.x;
+  const int n = counts ? counts[p] : n_max;
+  const int cbs = (n_max + 63) >> 6;
+  const float* d = dets + (size_t)p * n_max * 5;
+  const unsigned long long* m = mask + (size_t)p * n_max * cbs;
+  const int* kp = keep + (size_t)p * n_max;
+  int* fs = first_sup + (size_t)p * n_max;
+  float* o = out + (size_t)p * n_max * 5;
+  const int nk = thr_hi < 1.0f ? nkeep[p] : 0;  // hi >= 1: the top box does not even vote for itself -> break
+  if (threadIdx.x == 0) nout[p] = nk;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    int f = n;  // (every box is kept or suppressed by a kept one, so this is always overwritten)
+    for (int q = 0; q < nk; ++q) {
+      const int k = kp[q];
+      if (k > j) break;
+      if (k == j || ((m[(size_t)k * cbs + (j >> 6)] >> (j & 63)) & 1ull)) {
+        f = k;
+        break;
+      }
+    }
+    fs[j] = f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int q = warp; q < nk; q += nwarps) {
+    const int k = kp[q];
+    const float* bk = d + (size_t)k * 5;
+    float sw = 0.f, sx1 = 0.f, sy1 = 0.f, sx2 = 0.f, sy2 = 0.f;
+    for (int j = k + lane; j < n; j += 32) {
+      if (fs[j] < k) continue;
+      const float* bj = d + (size_t)j * 5;
+      if (dev_iou(bk, bj) > thr_hi) {
+        const float s = bj[4];
+        sw += s;
+        sx1 += s * bj[0];
+        sy1 += s * bj[1];
+        sx2 += s * bj[2];
+        sy2 += s * bj[3];
+      }
+    }
+    for (int off = 16; off; off >>= 1) {
+      sw += __shfl_xor_sync(0xffffffffu, sw, off);
+      sx1 += __shfl_xor_sync(0xffffffffu, sx1, off);
+      sy1 += __shfl_xor_sync(0xffffffffu, sy1, off);
+      sx2 += __shfl_xor_sync(0xffffffffu, sx2, off);
+      sy2 += __shfl_xor_sync(0xffffffffu, sy2, off);
+    }
+    if (lane == 0) {
+      float* r = o + (size_t)q * 5;
+      r[0] = sx1 / sw; r[1] = sy1 / sw; r[2] = sx2 / sw; r[3] = sy2 / sw; r[4] = bk[4];
+    }
+  }
+}
+}  // namespace
+
+extern "C" size_t sdet_weighted_nms_workspace(int problems, int n) {
+  if (problems <= 0 || n <= 0) return 0;
+  return nms_ws_bytes(problems, n) + align_up((size_t)problems * n * 4, 256) * 2 + align_up((size_t)problems * 4, 256);
+}
+
+extern "C" int sdet_weighted_nms_sorted(const float* dets, const int* counts, int problems, int n, float thresh_lo,
+                                        float thresh_hi, float* out, int* nout, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  SDET_REQUIRE(dets && out && nout && workspace, "NULL argument");
+  SDET_REQUIRE(problems > 0 && n > 0, "problems and n must be > 0");
+  SDET_REQUIRE(thresh_lo < 1.0f, "thresh_lo must be < 1 (a box always leaves the pool with itself)");
+  if (workspace_bytes < sdet_weighted_nms_workspace(problems, n))
+    return sdet::fail(SDET_ERR_WORKSPACE, "workspace too small: need %zu bytes", sdet_weighted_nms_workspace(problems, n));
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = static_cast<char*>(workspace);
+  auto* mask = reinterpret_cast<unsigned long long*>(w + align_up((size_t)problems * n * 5 * 4, 256));
+  char* x = w + nms_ws_bytes(problems, n);
+  int* keep = reinterpret_cast<int*>(x); x += align_up((size_t)problems * n * 4, 256);
+  int* fsup = reinterpret_cast<int*>(x); x += align_up((size_t)problems * n * 4, 256);
+  int* nkeep = reinterpret_cast<int*>(x);
+  ScanOut so{};
+  so.keep = keep;
+  so.nkeep = nkeep;
+  if (int rc = run_mask_and_scan(dets, counts, problems, n, thresh_lo, /*ge=*/0, mask, so, st)) return rc;
+  weighted_vote_kernel<<<(unsigned)problems, 256, 0, st>>>(dets, counts, n, mask, keep, nkeep, thresh_hi, fsup, out, nout);
+  SDET_LAUNCH_CHECK("weighted_vote_kernel");
+  return SDET_OK;
 }
 
 // workspace: dets (P,pre_max,5) | mask | counts (P)

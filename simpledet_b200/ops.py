@@ -23,7 +23,8 @@ __all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_r
            "multiclass_nms", "ProposalTarget", "FocalLoss", "BBoxNorm",
            "SigmoidCrossEntropy", "soft_nms", "soft_nms_batched",
            "cython_soft_nms_wrapper", "DeformableConvolution", "ProposalMaskTarget", "ProposalTarget_v2", "Proposal", "Proposal_v2", "GenAnchor", "GenProposal", "GenProposalRetina", "AnchorTarget2D", "PyramidAnchorTarget2D", "bbox_overlaps",
-           "nonlinear_transform", "nonlinear_pred", "iou_pred", "OPS"]
+           "nonlinear_transform", "nonlinear_pred", "iou_pred", "set_nms", "py_weighted_nms", "py_set_nms_wrapper",
+           "wnms_wrapper", "OPS"]
 
 
 def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor | None:
@@ -590,6 +591,55 @@ def nms_sorted(dets, thresh, ge=True, counts=None):
     check(L.sdet_nms_sorted(_p(dets), _p(counts), P, n, float(thresh), int(bool(ge)), _p(keep), _p(nkeep),
                             _p(ws), nbytes, _stream()))
     return keep, nkeep
+
+
+def set_nms(dets, thresh):
+    """operator_py/nms.py set_nms: dets (m,6) rows [x1,y1,x2,y2,score,set] on the device -> kept rows."""
+    dets = _dev(dets, "dets")
+    if dets.dim() != 2 or dets.shape[1] != 6:
+        raise ValueError("dets must be (m,6)")
+    if dets.shape[0] == 0:
+        return dets
+    order = torch.sort(dets[:, 4], descending=True, stable=True).indices
+    srt = dets[order].contiguous()
+    boxes, sets = srt[:, :5].contiguous()[None], srt[:, 5].contiguous()[None]
+    n = int(srt.shape[0])
+    keep = torch.empty((1, n), device=dets.device, dtype=torch.int32)
+    nkeep = torch.empty((1,), device=dets.device, dtype=torch.int32)
+    L = _lib.lib()
+    nbytes = L.sdet_nms_workspace(1, n)
+    ws = _ws(nbytes, dets.device)
+    check(L.sdet_set_nms_sorted(_p(boxes), _p(sets), None, 1, n, float(thresh), _p(keep), _p(nkeep), _p(ws), nbytes,
+                                _stream()))
+    return srt[keep[0, :int(nkeep.item())].long()]
+
+
+def py_weighted_nms(dets, thresh_lo, thresh_hi):
+    """operator_py/nms.py py_weighted_nms: dets (m,5) -> (m',5) voted boxes with the top boxes' scores."""
+    dets = _dev(dets, "dets")
+    if dets.dim() != 2 or dets.shape[1] != 5:
+        raise ValueError("dets must be (m,5)")
+    if dets.shape[0] == 0:
+        return dets
+    order = torch.sort(dets[:, 4], descending=True, stable=True).indices
+    srt = dets[order].contiguous()[None]
+    n = int(srt.shape[1])
+    out = torch.empty((1, n, 5), device=dets.device, dtype=torch.float32)
+    nout = torch.empty((1,), device=dets.device, dtype=torch.int32)
+    L = _lib.lib()
+    nbytes = L.sdet_weighted_nms_workspace(1, n)
+    ws = _ws(nbytes, dets.device)
+    check(L.sdet_weighted_nms_sorted(_p(srt), None, 1, n, float(thresh_lo), float(thresh_hi), _p(out), _p(nout),
+                                     _p(ws), nbytes, _stream()))
+    return out[0, :int(nout.item())]
+
+
+def py_set_nms_wrapper(thresh):
+    return lambda dets: set_nms(dets, thresh)
+
+
+def wnms_wrapper(thresh_lo, thresh_hi):
+    return lambda dets: py_weighted_nms(dets, thresh_lo, thresh_hi)
 
 
 # --------------------------------------------------------------------------------------------

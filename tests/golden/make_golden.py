@@ -145,6 +145,11 @@ def main():
         out[f"soft_boxes_{method}"], out[f"soft_inds_{method}"] = bx, idx
     out["py_nms_0.5"] = nm.nms(d, 0.5)
     out["soft_wrapper_linear"] = nm.cython_soft_nms_wrapper(0.5)(d)
+    d6 = np.concatenate([d, rng.integers(0, 7, (400, 1)).astype(np.float32)], 1)
+    out["set_nms_dets"] = d6
+    out["set_nms_0.4"] = nm.set_nms(d6, 0.4)
+    out["weighted_nms_0.3_0.6"] = nm.py_weighted_nms(d, 0.3, 0.6)
+    out["weighted_nms_0.5_0.5"] = nm.py_weighted_nms(d, 0.5, 0.5)
     # --- numpy box transforms (float64)
     ex, gt = boxes(rng, 64).astype(np.float64), boxes(rng, 64).astype(np.float64)
     out["xf_ex"], out["xf_gt"] = ex, gt

@@ -22,6 +22,10 @@ def test_greedy_nms_golden():
     assert np.array_equal(oracle.greedy_nms(G["nms_dets"], 0.5), G["greedy_keep_0.5"])
     # operator_py/nms.py `nms` keeps ovr <= thr; with distinct IoUs != thr it equals greedy_nms' set
     assert np.array_equal(np_ops.py_nms(G["nms_dets"], 0.5), G["py_nms_0.5"])
+    assert np.array_equal(np_ops.set_nms(G["set_nms_dets"], 0.4), G["set_nms_0.4"])
+    for lo, hi in ((0.3, 0.6), (0.5, 0.5)):
+        got, want = np_ops.py_weighted_nms(G["nms_dets"], lo, hi), G[f"weighted_nms_{lo}_{hi}"]
+        assert got.shape == want.shape and got.dtype == want.dtype and np.array_equal(got, want)
 
 
 @pytest.mark.parametrize("method", [0, 1, 2])

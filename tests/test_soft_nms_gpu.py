@@ -49,3 +49,19 @@ def test_batched_random_with_ties_and_ragged_counts(cuda, method):
         assert oc[p] == len(ri), p
         assert np.array_equal(ob[p, : oc[p]], rb) and np.array_equal(oi[p, : oc[p]], ri), p
         assert (oi[p, oc[p]:] == -1).all()
+
+
+def test_set_nms_and_weighted_nms_match_reference_goldens(cuda):
+    """operator_py/nms.py set_nms / py_weighted_nms: goldens produced by the reference's own Python."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_python_ops.npz"))
+    got = ops.set_nms(torch.from_numpy(g["set_nms_dets"]).to(cuda), 0.4).cpu().numpy()
+    assert np.array_equal(got, g["set_nms_0.4"])
+    d = torch.from_numpy(g["nms_dets"]).to(cuda)
+    for lo, hi in ((0.3, 0.6), (0.5, 0.5)):
+        want = g[f"weighted_nms_{lo}_{hi}"]
+        got = ops.py_weighted_nms(d, lo, hi).cpu().numpy()
+        assert got.shape == want.shape
+        assert np.array_equal(got[:, 4], want[:, 4])                    # same top boxes, same order
+        np.testing.assert_allclose(got[:, :4], want[:, :4], rtol=2e-6, atol=1e-4)  # float32 sums, other order
+    assert ops.py_weighted_nms(d, 0.3, 1.0).shape[0] == 0               # nothing can vote: the reference breaks
