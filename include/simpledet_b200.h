@@ -375,6 +375,14 @@ int sdet_bbox_nonlinear_transform(const double* ex_rois, const double* gt_rois, 
 int sdet_bbox_pred(const float* boxes, const double* box_deltas, double* pred_boxes, int N, int K,
                    int iou, int clip, double im_h, double im_w, void* stream);
 
+/* bbox_transform.py:164-169 flip_boxes on (num_boxes,4) float32 (is_double = 0) or float64 boxes. */
+int sdet_bbox_flip(const void* boxes, void* out, size_t num_boxes, double im_width, int is_double,
+                   void* stream);
+/* bbox_transform.py:172-221 box_voting: top_dets (T,5), all_dets (N,5) float32 -> out (T,5).
+ * scoring_method: 0 ID, 1 TEMP_AVG, 2 AVG, 3 IOU_AVG, 4 GENERALIZED_AVG, 5 QUASI_SUM. */
+int sdet_box_voting(const float* top_dets, const float* all_dets, float* out, int T, int N, float thresh,
+                    int scoring_method, float beta, void* stream);
+
 /* AnchorTarget2D (core/detection_input.py:353-565) and PyramidAnchorTarget2D (models/FPN/input.py:55-148)
  * for a batch, on the device.  gt_bbox (B,G,gt_stride) with gt_stride 4 or 5; rows whose x1 == -1 are
  * padding.  Level l has stride strides[l] and a (long x short) grid oriented by the image (h >= w puts

@@ -171,6 +171,39 @@ def flip_boxes(boxes, im_width):
     return f
 
 
+def box_voting(top_dets, all_dets, thresh=0.5, scoring_method="ID", beta=1.0, overlaps_fn=None):
+    """operator_py/bbox_transform.py:172-221: every top box becomes the score-weighted mean of the boxes
+    of `all_dets` overlapping it by >= thresh (float32 Cython IoU); the score is re-derived by
+    `scoring_method`."""
+    from . import bbox_overlaps as c_overlaps
+    overlaps_fn = overlaps_fn or c_overlaps
+    out = top_dets.copy()
+    boxes, scores = all_dets[:, :4], all_dets[:, 4]
+    ov = overlaps_fn(top_dets[:, :4], boxes)
+    for k in range(out.shape[0]):
+        sel = np.where(ov[k] >= thresh)[0]
+        ws = scores[sel]
+        out[k, :4] = np.average(boxes[sel, :], axis=0, weights=ws)
+        if scoring_method == "ID":
+            pass
+        elif scoring_method == "TEMP_AVG":
+            P = np.vstack((ws, 1.0 - ws))
+            X = np.log(P / np.max(P, axis=0))
+            E = np.exp(X / beta)
+            out[k, 4] = (E / np.sum(E, axis=0))[0].mean()
+        elif scoring_method == "AVG":
+            out[k, 4] = ws.mean()
+        elif scoring_method == "IOU_AVG":
+            out[k, 4] = np.average(ws, weights=ov[k, sel])
+        elif scoring_method == "GENERALIZED_AVG":
+            out[k, 4] = np.mean(ws ** beta) ** (1.0 / beta)
+        elif scoring_method == "QUASI_SUM":
+            out[k, 4] = ws.sum() / float(len(ws)) ** beta
+        else:
+            raise NotImplementedError("Unknown scoring method {}".format(scoring_method))
+    return out
+
+
 # ---- DCNv1 sampling: restated from the published formulation (upstream MXNet
 # src/operator/contrib/nn/deformable_im2col.h/.cuh; not in the reference tree) — PARITY UNPINNED ----
 def deformable_im2col(data, offset, kernel, stride=(1, 1), dilate=(1, 1), pad=(0, 0), num_deformable_group=1):

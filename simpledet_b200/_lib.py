@@ -65,6 +65,8 @@ _SIGNATURES = {
     "sdet_set_nms_sorted": [_P, _P, _P, c_int, c_int, c_float, _P, _P, _P, c_size_t, _P],
     "sdet_weighted_nms_workspace": [c_int, c_int],
     "sdet_weighted_nms_sorted": [_P, _P, c_int, c_int, c_float, c_float, _P, _P, _P, c_size_t, _P],
+    "sdet_bbox_flip": [_P, _P, c_size_t, c_double, c_int, _P],
+    "sdet_box_voting": [_P, _P, _P, c_int, c_int, c_float, c_int, c_float, _P],
     "sdet_bbox_overlaps": [_P, _P, _P, c_int, c_int, c_int, _P],
     "sdet_bbox_nonlinear_transform": [_P, _P, _P, c_int, _P],
     "sdet_bbox_pred": [_P, _P, _P, c_int, c_int, c_int, c_int, c_double, c_double, _P],

@@ -24,7 +24,7 @@ __all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_r
            "SigmoidCrossEntropy", "soft_nms", "soft_nms_batched",
            "cython_soft_nms_wrapper", "DeformableConvolution", "ProposalMaskTarget", "ProposalTarget_v2", "Proposal", "Proposal_v2", "GenAnchor", "GenProposal", "GenProposalRetina", "AnchorTarget2D", "PyramidAnchorTarget2D", "bbox_overlaps",
            "nonlinear_transform", "nonlinear_pred", "iou_pred", "set_nms", "py_weighted_nms", "py_set_nms_wrapper",
-           "wnms_wrapper", "OPS"]
+           "wnms_wrapper", "flip_boxes", "box_voting", "OPS"]
 
 
 def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor | None:
@@ -239,6 +239,32 @@ def nonlinear_pred(boxes, box_deltas, im_shape=None):
 def iou_pred(boxes, box_deltas, im_shape=None):
     """bbox_transform.iou_pred, optionally fused with clip_boxes."""
     return _bbox_pred(boxes, box_deltas, True, im_shape)
+
+
+def flip_boxes(boxes, im_width):
+    """bbox_transform.flip_boxes: (N, 4K) float32 or float64."""
+    if boxes.dtype not in (torch.float32, torch.float64):
+        raise TypeError("boxes must be float32 or float64")
+    boxes = _dev(boxes, "boxes", boxes.dtype)
+    out = torch.empty_like(boxes)
+    check(_lib.lib().sdet_bbox_flip(_p(boxes), _p(out), boxes.numel() // 4, float(im_width),
+                                    int(boxes.dtype == torch.float64), _stream()))
+    return out
+
+
+_VOTE_METHODS = {"ID": 0, "TEMP_AVG": 1, "AVG": 2, "IOU_AVG": 3, "GENERALIZED_AVG": 4, "QUASI_SUM": 5}
+
+
+def box_voting(top_dets, all_dets, thresh=0.5, scoring_method="ID", beta=1.0):
+    """bbox_transform.box_voting: top_dets (T,5), all_dets (N,5) float32 on the device -> (T,5)."""
+    if scoring_method not in _VOTE_METHODS:
+        raise NotImplementedError("Unknown scoring method {}".format(scoring_method))
+    top_dets, all_dets = _dev(top_dets, "top_dets"), _dev(all_dets, "all_dets")
+    out = torch.empty_like(top_dets)
+    check(_lib.lib().sdet_box_voting(_p(top_dets), _p(all_dets), _p(out), int(top_dets.shape[0]),
+                                     int(all_dets.shape[0]), float(thresh), _VOTE_METHODS[scoring_method],
+                                     float(beta), _stream()))
+    return out
 
 
 # --------------------------------------------------------------------------------------------

@@ -161,6 +161,13 @@ def main():
     out["iou_pred"] = bt.iou_pred(ex.astype(np.float32), deltas)
     out["clip_boxes"] = bt.clip_boxes(out["nonlinear_pred"].copy(), (400, 500))
     out["flip_boxes"] = bt.flip_boxes(ex, 640)
+    # --- box voting (float32 dets; every scoring method)
+    bt.bbox_overlaps = cy["bbox"].bbox_overlaps_cython
+    top = d[np.argsort(-d[:, 4])[:60]].copy()
+    out["vote_top"] = top
+    for meth, beta in (("ID", 1.0), ("AVG", 1.0), ("IOU_AVG", 1.0), ("GENERALIZED_AVG", 2.0), ("QUASI_SUM", 0.5),
+                       ("TEMP_AVG", 0.7)):
+        out[f"vote_{meth}"] = bt.box_voting(top, d, 0.5, meth, beta)
     np.savez_compressed(os.path.join(HERE, "reference_python_ops.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_python_ops.npz"), {k: v.shape for k, v in out.items()})
 

@@ -6,6 +6,7 @@ import pytest
 import torch
 
 import oracle
+import oracle.np_ops
 from simpledet_b200 import ops
 
 pytestmark = pytest.mark.gpu
@@ -52,3 +53,16 @@ def test_encode_decode_golden(cuda):
     # round trip: decode(encode(ex -> gt)) == gt
     rt = ops.nonlinear_pred(_t(ex32, cuda), ops.nonlinear_transform(_t(ex32.astype(np.float64), cuda), _t(gt, cuda)))
     np.testing.assert_allclose(rt.cpu().numpy(), gt, rtol=1e-9, atol=1e-9)
+
+
+def test_flip_and_box_voting_golden(cuda):
+    ex = G["xf_ex"]
+    assert np.array_equal(ops.flip_boxes(_t(ex, cuda), 640).cpu().numpy(), G["flip_boxes"])
+    f32 = ex.astype(np.float32)
+    assert np.array_equal(ops.flip_boxes(_t(f32, cuda), 640).cpu().numpy(), oracle.np_ops.flip_boxes(f32, 640))
+    top, alld = G["vote_top"], G["nms_dets"]
+    for meth, beta in (("ID", 1.0), ("AVG", 1.0), ("IOU_AVG", 1.0), ("GENERALIZED_AVG", 2.0), ("QUASI_SUM", 0.5),
+                       ("TEMP_AVG", 0.7)):
+        got = ops.box_voting(_t(top, cuda), _t(alld, cuda), 0.5, meth, beta).cpu().numpy()
+        # voter sets are exact (bit-exact IoU); the float32 sums run in warp order, numpy's in pairwise order
+        np.testing.assert_allclose(got, G[f"vote_{meth}"], rtol=3e-6, atol=1e-4, err_msg=meth)

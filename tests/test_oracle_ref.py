@@ -67,3 +67,10 @@ def test_live_against_compiled_reference():
             r1 = oracle.soft_nms(d, 0.5, 0.3, 0.001, m)
             r2 = ref["cpu_nms"].soft_nms(d, np.float32(0.5), np.float32(0.3), np.float32(0.001), np.uint8(m))
             assert np.array_equal(r1[0], r2[0]) and np.array_equal(r1[1], r2[1])
+
+
+def test_box_voting_matches_reference():
+    for meth, beta in (("ID", 1.0), ("AVG", 1.0), ("IOU_AVG", 1.0), ("GENERALIZED_AVG", 2.0), ("QUASI_SUM", 0.5),
+                       ("TEMP_AVG", 0.7)):
+        got = np_ops.box_voting(G["vote_top"], G["nms_dets"], 0.5, meth, beta)
+        assert got.dtype == G[f"vote_{meth}"].dtype and np.array_equal(got, G[f"vote_{meth}"]), meth
