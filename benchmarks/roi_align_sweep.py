@@ -117,11 +117,12 @@ def main():
         from simpledet_b200 import _lib as _l
         f = _l.lib().sdet_debug_ra_prof  # AttributeError in product builds
         f.argtypes, f.restype = [_ct.c_void_p, _ct.c_int], _ct.c_int
-        buf = (_ct.c_ulonglong * 4)()
+        buf = (_ct.c_ulonglong * 8)()
         f(buf, 1)
         fn()
         f(buf, 1)
-        prof = {"consumer_wait_cyc": buf[0], "consumer_compute_cyc": buf[1], "producer_wait_cyc": buf[3]}
+        prof = {"consumer_wait_cyc": buf[0], "consumer_compute_cyc": buf[1], "producer_wait_cyc": buf[3],
+                "cta_preamble_cyc": buf[2], "cta_lifetime_cyc": buf[4]}
     except (AttributeError, OSError):
         pass
     print(json.dumps({"shape": a.shape, "B": B, "N": N, "pooled": pooled, "argmax": a.argmax, "sorted": a.sorted, "backward": a.backward, "plan": a.plan, "noflush": a.noflush, "modepref": os.environ.get("SDET_RA_MODEPREF"), "tiles": os.environ.get("SDET_RA_TILES"),

@@ -371,8 +371,9 @@ __global__ void __launch_bounds__(256) roi_align_order_kernel(const PlanSched sc
 // kCapFloats: floats of dynamic shared memory for the window buffers (12288 = 48 KB -> 4 CTAs/SM)
 #ifdef SDET_RA_ABLATE  // profiling builds only: bit 0 skips compute, bit 1 skips staging (results are garbage)
 __device__ int g_ra_ablate = 0;
-// consumer-warp cycle counters: [0] waiting for a full buffer, [1] computing, [2] whole kernel body, [3] producer waiting
-__device__ unsigned long long g_ra_prof[4] = {0, 0, 0, 0};
+// cycle counters: [0] consumer warps waiting for a full buffer, [1] computing, [2] CTA lifetime up to the tile
+// loop (preamble, tables, barrier init; thread 0), [3] producer waiting, [4] whole CTA lifetime (thread 0)
+__device__ unsigned long long g_ra_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
 
 // CTA = 4 consumer warps (the arithmetic) + 1 producer warp (all cp.async staging).  Staging and
@@ -395,6 +396,9 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
   static_assert(CPT % 4 == 0, "channels are processed in fp32x2 pairs, per half-warp when PW <= 8");
 
   const int tid = threadIdx.x;
+#ifdef SDET_RA_ABLATE
+  const long long prof_t0 = clock64();
+#endif
   const int n = a.order ? __ldg(a.order + blockIdx.x) : (int)blockIdx.x;
   const int C = a.C;
   const int PH = kPH ? kPH : a.PH, PW = kPW ? kPW : a.PW;
@@ -641,7 +645,16 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
             unpack2(add2(add2(add2(ptl, pbl), ptr), pbr), v[k], v[k + 1]);
           }
         };
-        if (__all_sync(0xffffffffu, olo == rowA)) {
+#ifndef SDET_RA_NOCACHE
+#define SDET_RA_NOCACHE 0
+#endif
+        if (SDET_RA_NOCACHE && kSub == 2) {
+          // narrow outputs: bins are ~2 rows tall, consecutive samples rarely share a row, so the
+          // row cache's votes and branches cost more than the reloads they save
+          TapLoader<CL, kCS>::run(RA, sl + olo, sr + olo);
+          TapLoader<CL, kCS>::run(RB, sl + ohi, sr + ohi);
+          step(RA, RB);
+        } else if (__all_sync(0xffffffffu, olo == rowA)) {
           if (__any_sync(0xffffffffu, ohi != rowB)) {
             TapLoader<CL, kCS>::run(RB, sl + ohi, sr + ohi);
             rowB = ohi;
@@ -741,6 +754,9 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
     // ---- producer / consumer pipeline over the channel tiles of this roi (ring of NBUF buffers) ----
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(s_bar);
 #ifdef SDET_RA_ABLATE
+    if (tid == 0) atomicAdd(&g_ra_prof[2], (unsigned long long)(clock64() - prof_t0));
+#endif
+#ifdef SDET_RA_ABLATE
     long long prof_wait = 0, prof_comp = 0;
 #endif
     if (warp == NW) {
@@ -783,6 +799,7 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
       atomicAdd(&g_ra_prof[0], (unsigned long long)prof_wait);
       atomicAdd(&g_ra_prof[1], (unsigned long long)prof_comp);
     }
+    if (tid == 0) atomicAdd(&g_ra_prof[4], (unsigned long long)(clock64() - prof_t0));
 #endif
   };
 
@@ -944,9 +961,9 @@ int launch_fwd(RoiAlignArgs& a, void* workspace, size_t workspace_bytes, cudaStr
 #ifdef SDET_RA_ABLATE
 extern "C" int sdet_debug_ra_prof(unsigned long long* out4, int reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out4, g_ra_prof, sizeof(unsigned long long) * 4);
+  cudaMemcpyFromSymbol(out4, g_ra_prof, sizeof(unsigned long long) * 8);
   if (reset) {
-    unsigned long long z[4] = {0, 0, 0, 0};
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaMemcpyToSymbol(g_ra_prof, z, sizeof(z));
   }
   return 0;
