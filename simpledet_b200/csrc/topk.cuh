@@ -38,6 +38,7 @@ __device__ void block_topk_sorted(int n, int k, KeyAt key_at, uint32_t* s_hist, 
                                   int k_pow2) {
   __shared__ uint64_t s_prefix;
   __shared__ int s_need, s_done, s_cnt;
+  __shared__ int s_wsum[32];
   const int tid = threadIdx.x;
   if (tid == 0) {
     s_prefix = 0;
@@ -70,32 +71,37 @@ __device__ void block_topk_sorted(int n, int k, KeyAt key_at, uint32_t* s_hist, 
       }
     }
     __syncthreads();
-    if (tid < 32) {  // one warp walks the bins from the top: find the digit of the k-th key
+    {  // find the digit of the k-th key: block-wide scan of the histogram (two bins per thread) instead
+       // of one warp walking 64 groups of bins (that serial walk was most of a sweep's latency)
       const int need = s_need;
-      const int nb = 1 << bits;
-      int cum = 0, found = -1, found_cum = 0;
-      for (int base = nb - 32; base >= 0 && found < 0; base -= 32) {
-        const int b = base + (31 - tid);  // lane 0 = highest bin of this group
-        const int h = (int)s_hist[b];
-        int inc = h;  // inclusive scan over lanes (descending bins)
+      const int b0 = 2 * tid, b1 = 2 * tid + 1;
+      const int h0 = (int)s_hist[b0], h1 = (int)s_hist[b1];
+      int inc = h0 + h1;  // inclusive scan over threads (ascending bins)
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((tid & 31) >= o) inc += t;
+      }
+      if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
+      __syncthreads();
+      if (tid < 32) {
+        int w = s_wsum[tid];
         for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, inc, o);
-          if (tid >= o) inc += t;
+          const int t = __shfl_up_sync(0xffffffffu, w, o);
+          if (tid >= o) w += t;
         }
-        const bool hit = (cum + inc >= need) && (cum + inc - h < need);
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (m) {
-          const int src = __ffs(m) - 1;
-          found = __shfl_sync(0xffffffffu, b, src);
-          found_cum = cum + __shfl_sync(0xffffffffu, inc - h, src);
-          const int hb = __shfl_sync(0xffffffffu, h, src);
-          if (tid == 0) {
-            s_prefix = prefix | ((uint64_t)found << sh);
-            s_need = need - found_cum;
-            if (hb == need - found_cum || sh == 0) s_done = 1;  // whole bin taken / last digit
-          }
-        }
-        cum += __shfl_sync(0xffffffffu, inc, 31);
+        s_wsum[tid] = w;
+      }
+      __syncthreads();
+      const int total = s_wsum[31];
+      const int upto = inc + ((tid >> 5) ? s_wsum[(tid >> 5) - 1] : 0);  // keys in bins <= b1
+      const int above1 = total - upto, above0 = above1 + h1;             // keys in bins above b1 / above b0
+      int found = -1, found_cum = 0, hb = 0;
+      if (above1 < need && need <= above1 + h1) { found = b1; found_cum = above1; hb = h1; }
+      else if (above0 < need && need <= above0 + h0) { found = b0; found_cum = above0; hb = h0; }
+      if (found >= 0) {  // exactly one thread
+        s_prefix = prefix | ((uint64_t)found << sh);
+        s_need = need - found_cum;
+        if (hb == need - found_cum || sh == 0) s_done = 1;  // whole bin taken / last digit
       }
     }
     __syncthreads();
