@@ -59,19 +59,7 @@ class_sort_kernel(const float* __restrict__ cls_score, const float* __restrict__
   }
   if (mine) atomicAdd(&s_valid, mine);
   __syncthreads();
-  for (int size = 2; size <= n_pad; size <<= 1)
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
-        const int lo = ((t / stride) * (stride << 1)) + (t % stride), hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const unsigned long long a = s_keys[lo], c = s_keys[hi];
-        if ((a < c) == desc) {
-          s_keys[lo] = c;
-          s_keys[hi] = a;
-        }
-      }
-      __syncthreads();
-    }
+  sdet::block_bitonic_sort_desc(reinterpret_cast<uint64_t*>(s_keys), n_pad);
   const int nv = s_valid;
   if (threadIdx.x == 0) counts[p] = nv;
   for (int j = threadIdx.x; j < n_pad; j += blockDim.x) {

@@ -28,6 +28,54 @@ __device__ __forceinline__ float key_score(uint64_t key) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
 
+// Sorts s[0..k_pow2) descending (k_pow2 a power of two); all threads of the CTA must call it.
+__device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* s_sel, int k_pow2) {
+  const int tid = threadIdx.x;
+  if (k_pow2 <= (int)blockDim.x) {
+    // one key per thread in a register: compare-exchange partners closer than a warp meet through
+    // shuffles, only the strides >= 32 go through shared memory (15 barrier pairs instead of 55 for
+    // 1024 keys)
+    const bool on = tid < k_pow2;
+    uint64_t v = on ? s_sel[tid] : 0ull;
+    for (int size = 2; size <= k_pow2; size <<= 1) {
+      const bool desc = ((tid & size) == 0);
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        uint64_t o;
+        if (stride >= 32) {
+          __syncthreads();
+          if (on) s_sel[tid] = v;
+          __syncthreads();
+          o = on ? s_sel[tid ^ stride] : 0ull;
+        } else {
+          o = __shfl_xor_sync(0xffffffffu, v, stride);
+        }
+        const bool lower = (tid & stride) == 0;           // this thread keeps the pair's first slot
+        const bool take_max = (lower == desc);            // descending run: first slot holds the max
+        v = take_max ? (v > o ? v : o) : (v < o ? v : o);
+      }
+    }
+    __syncthreads();
+    if (on) s_sel[tid] = v;
+    __syncthreads();
+    return;
+  }
+  for (int size = 2; size <= k_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (k_pow2 >> 1); t += blockDim.x) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint64_t a = s_sel[lo], b = s_sel[hi];
+        if ((a < b) == desc) {
+          s_sel[lo] = b;
+          s_sel[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // Selects the k largest keys of {key(i) : i in [0,n)} into s_sel[0..k) (sorted descending; the
 // rest of s_sel up to next_pow2(k) is zero).  `KeyAt(i)` returns the 64-bit key of element i and
 // must be cheap and side-effect free (it is evaluated once per sweep).  All threads of the CTA
@@ -117,51 +165,7 @@ __device__ void block_topk_sorted(int n, int k, KeyAt key_at, uint32_t* s_hist, 
     }
   }
   __syncthreads();
-  if (!kSort) return;
-  // bitonic sort, descending
-  if (k_pow2 <= (int)blockDim.x) {
-    // one key per thread in a register: compare-exchange partners closer than a warp meet through
-    // shuffles, only the strides >= 32 go through shared memory (15 barrier pairs instead of 55 for
-    // 1024 keys)
-    const bool on = tid < k_pow2;
-    uint64_t v = on ? s_sel[tid] : 0ull;
-    for (int size = 2; size <= k_pow2; size <<= 1) {
-      const bool desc = ((tid & size) == 0);
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        uint64_t o;
-        if (stride >= 32) {
-          __syncthreads();
-          if (on) s_sel[tid] = v;
-          __syncthreads();
-          o = on ? s_sel[tid ^ stride] : 0ull;
-        } else {
-          o = __shfl_xor_sync(0xffffffffu, v, stride);
-        }
-        const bool lower = (tid & stride) == 0;           // this thread keeps the pair's first slot
-        const bool take_max = (lower == desc);            // descending run: first slot holds the max
-        v = take_max ? (v > o ? v : o) : (v < o ? v : o);
-      }
-    }
-    __syncthreads();
-    if (on) s_sel[tid] = v;
-    __syncthreads();
-    return;
-  }
-  for (int size = 2; size <= k_pow2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = tid; t < (k_pow2 >> 1); t += blockDim.x) {
-        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
-        const int hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const uint64_t a = s_sel[lo], b = s_sel[hi];
-        if ((a < b) == desc) {
-          s_sel[lo] = b;
-          s_sel[hi] = a;
-        }
-      }
-      __syncthreads();
-    }
-  }
+  if (kSort) block_bitonic_sort_desc(s_sel, k_pow2);
 }
 
 inline int next_pow2(int v) {
