@@ -101,50 +101,61 @@ __device__ __forceinline__ float dev_iou(const float* a, const float* b) {
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(Sa, Sb), inter));
 }
 
-// grid = (col_blocks, row_blocks, P); only col >= row tiles do work.  64 threads.
+// grid = (ceil(col_blocks / tpc), row_blocks, P); 64 threads = the 64 rows of a row block; a CTA walks
+// `tpc` column tiles (only col >= row tiles do work).  tpc = 1 spreads a few large problems over the
+// SMs; many small problems (per-class NMS: 160 x 136 tiles) take tpc = col_blocks so that the launch
+// is not 20 000 64-thread CTAs of which most exit at once.
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const float* __restrict__ dets, const int* __restrict__ counts, const int n_max,
                 const float thr, const int ge, unsigned long long* __restrict__ mask,
-                const float* __restrict__ sets) {  // sets (P,n_max) or nullptr: set_nms (nms.py:77-107)
-  const int row_b = blockIdx.y, col_b = blockIdx.x, p = blockIdx.z;
-  if (col_b < row_b) return;  // the scan only reads words j >= row block (proposal_v3.cu:373)
+                const float* __restrict__ sets,  // (P,n_max) or nullptr: set_nms (nms.py:77-107)
+                const int tpc) {
+  const int row_b = blockIdx.y, p = blockIdx.z;
   const int n = counts ? counts[p] : n_max;
-  const int col_blocks = (n_max + 63) >> 6;
-  const int row_size = min(n - row_b * 64, 64), col_size = min(n - col_b * 64, 64);
-  if (row_size <= 0 || col_size <= 0) return;
+  const int col_blocks = (n_max + 63) >> 6, nb = (n + 63) >> 6;
+  const int c_beg = max((int)blockIdx.x * tpc, row_b), c_end = min((int)(blockIdx.x + 1) * tpc, nb);
+  if (row_b >= nb || c_beg >= c_end) return;  // the scan only reads words j >= row block (proposal_v3.cu:373)
+  const int row_size = min(n - row_b * 64, 64);
   const float* d = dets + (size_t)p * n_max * 5;
   __shared__ float sb[64 * 5];
   __shared__ float s_set[64];
   const int t = threadIdx.x;
-  if (t < col_size) {
-#pragma unroll
-    for (int k = 0; k < 5; ++k) sb[t * 5 + k] = d[(size_t)(col_b * 64 + t) * 5 + k];
-    if (sets) s_set[t] = sets[(size_t)p * n_max + col_b * 64 + t];
-  }
-  __syncthreads();
+  const int cur = row_b * 64 + t;
+  float cb[4] = {0.f, 0.f, 0.f, 0.f};
+  float my_set = 0.f;
   if (t < row_size) {
-    const int cur = row_b * 64 + t;
-    float cb[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) cb[k] = d[(size_t)cur * 5 + k];
-    unsigned long long bits = 0;
-    const float my_set = sets ? sets[(size_t)p * n_max + cur] : 0.f;
-    const int start = (row_b == col_b) ? t + 1 : 0;
-    // Disjoint pairs (the vast majority) have IoU = 0/union: never above a positive threshold, and a
-    // NaN union compares false as well — decided without the division.  thr <= 0 takes the full path.
-    const bool skip_disjoint = thr > 0.f;
-    for (int i = start; i < col_size; ++i) {
-      const float* q = sb + i * 5;
-      if (skip_disjoint) {
-        const float w = __fadd_rn(__fsub_rn(fmin_ref(cb[2], q[2]), fmax_ref(cb[0], q[0])), 1.f);
-        const float h = __fadd_rn(__fsub_rn(fmin_ref(cb[3], q[3]), fmax_ref(cb[1], q[1])), 1.f);
-        if (!(w > 0.f && h > 0.f)) continue;
-      }
-      if (sets && s_set[i] == my_set) continue;  // members of one set never suppress each other
-      const float v = dev_iou(cb, q);
-      if (ge ? (v >= thr) : (v > thr)) bits |= 1ull << i;
+    if (sets) my_set = sets[(size_t)p * n_max + cur];
+  }
+  // Disjoint pairs (the vast majority) have IoU = 0/union: never above a positive threshold, and a
+  // NaN union compares false as well — decided without the division.  thr <= 0 takes the full path.
+  const bool skip_disjoint = thr > 0.f;
+  for (int col_b = c_beg; col_b < c_end; ++col_b) {
+    const int col_size = min(n - col_b * 64, 64);
+    __syncthreads();  // the previous tile has been consumed
+    if (t < col_size) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) sb[t * 5 + k] = d[(size_t)(col_b * 64 + t) * 5 + k];
+      if (sets) s_set[t] = sets[(size_t)p * n_max + col_b * 64 + t];
     }
-    mask[((size_t)p * n_max + cur) * col_blocks + col_b] = bits;
+    __syncthreads();
+    if (t < row_size) {
+      unsigned long long bits = 0;
+      const int start = (row_b == col_b) ? t + 1 : 0;
+      for (int i = start; i < col_size; ++i) {
+        const float* q = sb + i * 5;
+        if (skip_disjoint) {
+          const float w = __fadd_rn(__fsub_rn(fmin_ref(cb[2], q[2]), fmax_ref(cb[0], q[0])), 1.f);
+          const float h = __fadd_rn(__fsub_rn(fmin_ref(cb[3], q[3]), fmax_ref(cb[1], q[1])), 1.f);
+          if (!(w > 0.f && h > 0.f)) continue;
+        }
+        if (sets && s_set[i] == my_set) continue;  // members of one set never suppress each other
+        const float v = dev_iou(cb, q);
+        if (ge ? (v >= thr) : (v > thr)) bits |= 1ull << i;
+      }
+      mask[((size_t)p * n_max + cur) * col_blocks + col_b] = bits;
+    }
   }
 }
 
@@ -632,8 +643,10 @@ size_t nms_ws_bytes(int P, int n) {
 int run_mask_and_scan(const float* dets, const int* counts, int P, int n, float thr, int ge,
                       unsigned long long* mask, const ScanOut& so, cudaStream_t st, const float* sets = nullptr) {
   const int cbs = (n + 63) / 64;
-  dim3 grid((unsigned)cbs, (unsigned)cbs, (unsigned)P);
-  nms_mask_kernel<<<grid, 64, 0, st>>>(dets, counts, n, thr, ge, mask, sets);
+  const long long tiles = (long long)P * cbs * (cbs + 1) / 2;
+  const int tpc = (int)std::max<long long>(1, std::min<long long>(cbs, tiles / 1200));
+  dim3 grid((unsigned)((cbs + tpc - 1) / tpc), (unsigned)cbs, (unsigned)P);
+  nms_mask_kernel<<<grid, 64, 0, st>>>(dets, counts, n, thr, ge, mask, sets, tpc);
   SDET_LAUNCH_CHECK("nms_mask_kernel");
   const int nbuf = scan_smem_bytes(n, 2) <= 96 * 1024 ? 2 : 1;
   const size_t smem = scan_smem_bytes(n, nbuf);
