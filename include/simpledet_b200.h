@@ -347,6 +347,14 @@ int sdet_deformable_col2im(const float* grad_col, const float* data, const float
                            int pad_h, int pad_w, int stride_h, int stride_w, int dilate_h, int dilate_w,
                            int num_deformable_group, void* stream);
 
+/* detection_test.py:268-291 after sdet_multiclass_nms: per image, the `max_det` highest-scoring kept
+ * detections over all classes (ties: the later (class, rank) entry wins, as Python's stable ascending sort
+ * followed by [-max_det:] does).  dets (B*num_classes, n_pad, 5), keep (B*num_classes, n_pad), nkeep
+ * (B*num_classes) as written by sdet_multiclass_nms.  out (B, max_det, 6) rows [x, y, w, h, score,
+ * class index] in ascending score order, unused rows zero with class -1; out_count (B). */
+int sdet_final_detections(const float* dets, const int* keep, const int* nkeep, int B, int num_classes,
+                          int n_pad, int max_det, float* out, int* out_count, void* stream);
+
 /* operator_py/nms.py:77-107 set_nms over boxes already sorted by descending score: like sdet_nms_sorted
  * with `>` (the reference keeps ovr <= thresh), but boxes whose `sets` value (P,n; column 5 of the
  * reference's dets) is equal never suppress each other. */

@@ -100,6 +100,19 @@ def do_nms(cls_score, bbox_xyxy, nms_thresh, min_det_score):
     return out
 
 
+def final_detections(cls_score, bbox_xyxy, nms_thresh, min_det_score, max_det):
+    """detection_test.py:233-291 for one image: do_nms per class, then the COCO rows
+    sorted(result, key=score)[-max_det:] -> (rows, 6) [x, y, w, h, score, class index]."""
+    per_class = do_nms(cls_score, bbox_xyxy, nms_thresh, min_det_score)
+    result = []
+    for cid, det in per_class.items():
+        for k in range(det.shape[0]):
+            result.append((float(det[k, 0]), float(det[k, 1]), float(det[k, 2] - det[k, 0] + 1),
+                           float(det[k, 3] - det[k, 1] + 1), float(det[k, 4]), cid))
+    result = sorted(result, key=lambda r: r[4])[-max_det:]
+    return np.array(result, np.float32).reshape(-1, 6)
+
+
 # ---- operator_py/bbox_transform.py (numpy float64 utilities) — PINNED by tests/golden ----------
 BBOX_XFORM_CLIP = np.log(1000. / 16.)  # bbox_transform.py:5
 

@@ -78,7 +78,86 @@ class_sort_kernel(const float* __restrict__ cls_score, const float* __restrict__
   }
 }
 
+// detection_test.py:268-291: the kept detections of all classes of an image, listed class by class in
+// NMS order, `sorted(result, key=score)[-max_det:]` — a stable ascending sort, so among equal scores
+// the LATER list entries survive.  Key = (sortable score, list position): the top `max_det` keys in
+// descending order are the reference's slice read backwards.  One CTA per image.
+__global__ void __launch_bounds__(kTopkThreads)
+final_dets_kernel(const float* __restrict__ dets, const int* __restrict__ keep, const int* __restrict__ nkeep,
+                  const int ncls, const int n_pad, const int max_det, const int k_pow2,
+                  float* __restrict__ out, int* __restrict__ out_count) {
+  extern __shared__ unsigned long long s_sel[];
+  __shared__ uint32_t s_hist[sdet::kRadixBins];
+  __shared__ int s_base[1025];  // list position of every class's first kept detection
+  const int b = blockIdx.x;
+  const int* nk = nkeep + (size_t)b * ncls;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int c = 0; c < ncls; ++c) {
+      s_base[c] = acc;
+      acc += nk[c];
+    }
+    s_base[ncls] = acc;
+  }
+  __syncthreads();
+  const int total = s_base[ncls];
+  const int k = min(max_det, total);
+  auto key_at = [&](int i) -> uint64_t {
+    const int c = i / n_pad, j = i - c * n_pad;
+    if (j >= __ldg(nk + c)) return 0ull;  // not a kept slot: below every real key
+    const size_t p = (size_t)b * ncls + c;
+    const int row = __ldg(keep + p * n_pad + j);
+    const float sc = __ldg(dets + (p * n_pad + row) * 5 + 4);
+    return ((uint64_t)sdet::score_to_sortable(sc) << 32) | (uint64_t)(uint32_t)(s_base[c] + j + 1);
+  };
+  if (k > 0) sdet::block_topk_sorted(ncls * n_pad, k, key_at, s_hist, reinterpret_cast<uint64_t*>(s_sel), k_pow2);
+  if (threadIdx.x == 0) out_count[b] = k;
+  for (int r = threadIdx.x; r < max_det; r += blockDim.x) {
+    float* o = out + ((size_t)b * max_det + r) * 6;
+    if (r >= k) {
+      o[0] = o[1] = o[2] = o[3] = o[4] = 0.f;
+      o[5] = -1.f;
+      continue;
+    }
+    const uint64_t key = s_sel[k - 1 - r];  // ascending score like the reference's slice
+    const int pos = (int)(uint32_t)key - 1;
+    int c = 0;
+    for (int lo = 0, hi = ncls; lo < hi;) {  // largest c with s_base[c] <= pos
+      const int mid = (lo + hi) >> 1;
+      if (s_base[mid + 1] <= pos) lo = mid + 1; else hi = mid;
+      c = lo;
+    }
+    const size_t p = (size_t)b * ncls + c;
+    const float* d = dets + (p * n_pad + __ldg(keep + p * n_pad + (pos - s_base[c]))) * 5;
+    // COCO box: x, y, w = x2 - x1 + 1, h = y2 - y1 + 1 (detection_test.py:277-280)
+    o[0] = d[0]; o[1] = d[1];
+    o[2] = __fadd_rn(__fsub_rn(d[2], d[0]), 1.f);
+    o[3] = __fadd_rn(__fsub_rn(d[3], d[1]), 1.f);
+    o[4] = d[4];
+    o[5] = (float)c;
+  }
+}
+
 }  // namespace
+
+extern "C" int sdet_final_detections(const float* dets, const int* keep, const int* nkeep, int B, int num_classes,
+                                     int n_pad, int max_det, float* out, int* out_count, void* stream) {
+  SDET_REQUIRE(dets && keep && nkeep && out && out_count, "NULL argument");
+  SDET_REQUIRE(B > 0 && num_classes > 0 && n_pad > 0 && max_det > 0, "bad shape");
+  if (num_classes > 1024) return sdet::fail(SDET_ERR_UNSUPPORTED, "more than 1024 classes");
+  const int k_pow2 = sdet::next_pow2(max_det);
+  const size_t smem = (size_t)k_pow2 * 8;
+  if (smem > 160 * 1024) return sdet::fail(SDET_ERR_UNSUPPORTED, "max_det too large");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SDET_CUDA(cudaFuncSetAttribute(final_dets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  final_dets_kernel<<<(unsigned)B, kTopkThreads, smem, (cudaStream_t)stream>>>(dets, keep, nkeep, num_classes, n_pad,
+                                                                              max_det, k_pow2, out, out_count);
+  SDET_LAUNCH_CHECK("final_dets_kernel");
+  return SDET_OK;
+}
 
 extern "C" int sdet_get_top_proposal(const float* boxes, const float* scores, float* out_boxes,
                                      float* out_scores, int B, int M, int top_n, void* stream) {

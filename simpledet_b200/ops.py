@@ -24,7 +24,7 @@ __all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_r
            "SigmoidCrossEntropy", "soft_nms", "soft_nms_batched",
            "cython_soft_nms_wrapper", "DeformableConvolution", "ProposalMaskTarget", "ProposalTarget_v2", "Proposal", "Proposal_v2", "GenAnchor", "GenProposal", "GenProposalRetina", "AnchorTarget2D", "PyramidAnchorTarget2D", "bbox_overlaps",
            "nonlinear_transform", "nonlinear_pred", "iou_pred", "set_nms", "py_weighted_nms", "py_set_nms_wrapper",
-           "wnms_wrapper", "flip_boxes", "box_voting", "OPS"]
+           "wnms_wrapper", "flip_boxes", "box_voting", "final_detections", "OPS"]
 
 
 def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor | None:
@@ -1007,6 +1007,20 @@ def multiclass_nms(cls_score, bbox_xyxy, nms_thresh, min_det_score=0.05, first_c
                                 float(min_det_score), float(nms_thresh), _p(dets), _p(counts), _p(keep),
                                 _p(nkeep), _p(src), _p(ws), nbytes, _stream()))
     return dets, counts, keep, nkeep, src
+
+
+def final_detections(cls_score, bbox_xyxy, nms_thresh, min_det_score=0.05, max_det_per_image=100, first_class=0):
+    """detection_test.py:233-291 on the device: per-class NMS, then the `max_det_per_image` best detections of
+    every image.  -> (out (B, max_det, 6) rows [x, y, w, h, score, class index] ascending by score,
+    count (B)); class index counts from `first_class` (map it through coco.getCatIds() on the host)."""
+    dets, counts, keep, nkeep, _ = multiclass_nms(cls_score, bbox_xyxy, nms_thresh, min_det_score, first_class)
+    B, _, K = cls_score.shape
+    ncls = K - first_class
+    out = torch.empty((B, int(max_det_per_image), 6), device=dets.device, dtype=torch.float32)
+    cnt = torch.empty((B,), device=dets.device, dtype=torch.int32)
+    check(_lib.lib().sdet_final_detections(_p(dets), _p(keep), _p(nkeep), B, ncls, int(dets.shape[1]),
+                                           int(max_det_per_image), _p(out), _p(cnt), _stream()))
+    return out, cnt
 
 
 # --------------------------------------------------------------------------------------------

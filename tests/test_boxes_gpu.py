@@ -299,3 +299,26 @@ def test_gen_proposal_retina_few_survivors(cuda):
     gb, gs = ops.GenProposalRetina(_t(cls, cuda), _t(deltas, cuda), _t(im_info, cuda), _t(anchors, cuda), **kw)
     assert np.array_equal(gs.cpu().numpy(), rs) and np.array_equal(gb.cpu().numpy(), rb)
     assert np.count_nonzero(rs) == 2
+
+
+def test_final_detections(cuda):
+    """detection_test.py:233-291: per-class NMS then sorted(result, key=score)[-max_det:] per image,
+    including equal scores across classes (the later class survives the cut)."""
+    from oracle import np_ops
+    rng = np.random.default_rng(61)
+    B, N, K = 2, 300, 12
+    score = rng.uniform(0, 1, (B, N, K)).astype(np.float32) ** 3
+    score[:, :, 7] = score[:, :, 2]          # ties between classes 2 and 7
+    score[1, :, 4] = 0.01                    # a class without detections
+    xy = rng.uniform(0, 400, (B, N, 1, 2))
+    wh = rng.uniform(10, 200, (B, N, K, 2))
+    bbox = np.concatenate([np.broadcast_to(xy, (B, N, K, 2)) + rng.uniform(-5, 5, (B, N, K, 2)), xy + wh], 3)
+    bbox = bbox.reshape(B, N, K * 4).astype(np.float32)
+    for max_det in (100, 7, 5000):
+        out, cnt = ops.final_detections(_t(score, cuda), _t(bbox, cuda), 0.5, 0.05, max_det)
+        out, cnt = out.cpu().numpy(), cnt.cpu().numpy()
+        for b in range(B):
+            ref = np_ops.final_detections(score[b], bbox[b], 0.5, 0.05, max_det)
+            assert cnt[b] == ref.shape[0]
+            assert np.array_equal(out[b, :cnt[b]], ref), (max_det, b)
+            assert np.all(out[b, cnt[b]:, 5] == -1)
