@@ -347,6 +347,20 @@ int sdet_deformable_col2im(const float* grad_col, const float* data, const float
                            int pad_h, int pad_w, int stride_h, int stride_w, int dilate_h, int dilate_w,
                            int num_deformable_group, void* stream);
 
+/* DCNv2 (modulated) sampling, upstream MXNet `_contrib_ModulatedDeformableConvolution`
+ * (modulated_deformable_im2col.cuh; not in the reference tree, restated from the published formulation):
+ * like the v1 pair with an extra mask (B, num_deformable_group*KH*KW, Ho, Wo) multiplying every tap,
+ * zero-padded (not clamped) corners and the sampling range -1 < h < H, -1 < w < W. */
+int sdet_modulated_deformable_im2col(const float* data, const float* offset, const float* mask, float* col,
+                                     int B, int C, int H, int W, int kernel_h, int kernel_w, int pad_h,
+                                     int pad_w, int stride_h, int stride_w, int dilate_h, int dilate_w,
+                                     int num_deformable_group, void* stream);
+int sdet_modulated_deformable_col2im(const float* grad_col, const float* data, const float* offset,
+                                     const float* mask, float* grad_data, float* grad_offset,
+                                     float* grad_mask, int B, int C, int H, int W, int kernel_h,
+                                     int kernel_w, int pad_h, int pad_w, int stride_h, int stride_w,
+                                     int dilate_h, int dilate_w, int num_deformable_group, void* stream);
+
 /* detection_test.py:268-291 after sdet_multiclass_nms: per image, the `max_det` highest-scoring kept
  * detections over all classes (ties: the later (class, rank) entry wins, as Python's stable ascending sort
  * followed by [-max_det:] does).  dets (B*num_classes, n_pad, 5), keep (B*num_classes, n_pad), nkeep

@@ -62,6 +62,8 @@ _SIGNATURES = {
     "sdet_gen_proposal_retina_workspace": [c_int, c_int, c_int, c_int],
     "sdet_gen_proposal_retina": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_float, POINTER(c_float), POINTER(c_float), c_int, c_int, c_int, _P, c_size_t, _P],
+    "sdet_modulated_deformable_im2col": [_P, _P, _P, _P] + [c_int] * 13 + [_P],
+    "sdet_modulated_deformable_col2im": [_P, _P, _P, _P, _P, _P, _P] + [c_int] * 13 + [_P],
     "sdet_final_detections": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P],
     "sdet_set_nms_sorted": [_P, _P, _P, c_int, c_int, c_float, _P, _P, _P, c_size_t, _P],
     "sdet_weighted_nms_workspace": [c_int, c_int],

@@ -24,7 +24,7 @@ __all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_r
            "SigmoidCrossEntropy", "soft_nms", "soft_nms_batched",
            "cython_soft_nms_wrapper", "DeformableConvolution", "ProposalMaskTarget", "ProposalTarget_v2", "Proposal", "Proposal_v2", "GenAnchor", "GenProposal", "GenProposalRetina", "AnchorTarget2D", "PyramidAnchorTarget2D", "bbox_overlaps",
            "nonlinear_transform", "nonlinear_pred", "iou_pred", "set_nms", "py_weighted_nms", "py_set_nms_wrapper",
-           "wnms_wrapper", "flip_boxes", "box_voting", "final_detections", "OPS"]
+           "wnms_wrapper", "flip_boxes", "box_voting", "final_detections", "ModulatedDeformableConvolution", "OPS"]
 
 
 def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor | None:
@@ -966,6 +966,64 @@ def DeformableConvolution(data, offset, weight, bias=None, kernel=(3, 3), stride
     return _DeformConvFn.apply(data, offset, weight, None if no_bias else bias, geo)
 
 
+class _ModDeformConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, offset, mask, weight, bias, geo):
+        kh, kw, ph_, pw_, sh, sw, dh, dw, ng, dg = geo
+        data, offset, mask, weight = (_dev(data, "data"), _dev(offset, "offset"), _dev(mask, "mask"),
+                                      _dev(weight, "weight"))
+        B, C, H, W = data.shape
+        F = weight.shape[0]
+        Ho = (H + 2 * ph_ - (dh * (kh - 1) + 1)) // sh + 1
+        Wo = (W + 2 * pw_ - (dw * (kw - 1) + 1)) // sw + 1
+        if tuple(offset.shape) != (B, dg * 2 * kh * kw, Ho, Wo) or tuple(mask.shape) != (B, dg * kh * kw, Ho, Wo):
+            raise ValueError("offset must be (B, 2*dg*KH*KW, Ho, Wo) and mask (B, dg*KH*KW, Ho, Wo)")
+        col = torch.empty((B, C * kh * kw, Ho * Wo), device=data.device, dtype=torch.float32)
+        check(_lib.lib().sdet_modulated_deformable_im2col(_p(data), _p(offset), _p(mask), _p(col), B, C, H, W, kh, kw,
+                                                          ph_, pw_, sh, sw, dh, dw, dg, _stream()))
+        wg = weight.reshape(ng, F // ng, (C // ng) * kh * kw)
+        out = torch.einsum("gfk,bgkp->bgfp", wg, col.reshape(B, ng, (C // ng) * kh * kw, Ho * Wo)).reshape(B, F, Ho, Wo)
+        if bias is not None:
+            out = out + bias.view(1, F, 1, 1)
+        ctx.save_for_backward(data, offset, mask, weight, col)
+        ctx.geo, ctx.has_bias = geo, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        data, offset, mask, weight, col = ctx.saved_tensors
+        kh, kw, ph_, pw_, sh, sw, dh, dw, ng, dg = ctx.geo
+        B, C, H, W = data.shape
+        F = weight.shape[0]
+        gout = _dev(gout, "gout")
+        P = gout.shape[2] * gout.shape[3]
+        go = gout.reshape(B, ng, F // ng, P)
+        wg = weight.reshape(ng, F // ng, (C // ng) * kh * kw)
+        gcol = torch.einsum("gfk,bgfp->bgkp", wg, go).reshape(B, C * kh * kw, P).contiguous()
+        gweight = torch.einsum("bgfp,bgkp->gfk", go, col.reshape(B, ng, (C // ng) * kh * kw, P)).reshape(weight.shape)
+        gdata, goff, gmask = torch.empty_like(data), torch.empty_like(offset), torch.empty_like(mask)
+        check(_lib.lib().sdet_modulated_deformable_col2im(_p(gcol), _p(data), _p(offset), _p(mask), _p(gdata), _p(goff),
+                                                          _p(gmask), B, C, H, W, kh, kw, ph_, pw_, sh, sw, dh, dw, dg,
+                                                          _stream()))
+        gbias = gout.sum((0, 2, 3)) if ctx.has_bias else None
+        return gdata, goff, gmask, gweight, gbias, None
+
+
+def ModulatedDeformableConvolution(data, offset, mask, weight, bias=None, kernel=(3, 3), stride=(1, 1),
+                                   dilate=(1, 1), pad=(0, 0), num_filter=None, num_group=1, num_deformable_group=1,
+                                   no_bias=False):
+    """mx.sym.contrib.ModulatedDeformableConvolution (DCNv2): DeformableConvolution with a per-tap mask
+    (B, num_deformable_group*KH*KW, Ho, Wo) — the caller applies the sigmoid, as the upstream models do."""
+    kh, kw = _pair(kernel)
+    sh, sw = _pair(stride)
+    dh, dw = _pair(dilate)
+    ph_, pw_ = _pair(pad)
+    if num_filter is not None and weight.shape[0] != num_filter:
+        raise ValueError("weight.shape[0] != num_filter")
+    geo = (kh, kw, ph_, pw_, sh, sw, dh, dw, int(num_group), int(num_deformable_group))
+    return _ModDeformConvFn.apply(data, offset, mask, weight, None if no_bias else bias, geo)
+
+
 # --------------------------------------------------------------------------------------------
 # get_top_proposal (models/FPN/get_top_proposal.py) and test-time per-class NMS
 # (detection_test.py:233-260 + operator_py/nms.py:41-75)
@@ -1070,6 +1128,7 @@ OPS = {
     "_contrib_DecodeBBox": DecodeBBox,
     "_contrib_Proposal_v3": Proposal_v3,
     "_contrib_Proposal": Proposal,
+    "_contrib_ModulatedDeformableConvolution": ModulatedDeformableConvolution,
     "_contrib_GenAnchor": GenAnchor,
     "_contrib_GenProposal": GenProposal,
     "_contrib_GenProposalRetina": GenProposalRetina,

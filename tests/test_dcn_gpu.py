@@ -103,3 +103,65 @@ def test_backward_matches_autograd(cuda):
     torch.testing.assert_close(xs.grad.double(), xd.grad, rtol=1e-3, atol=1e-4)
     torch.testing.assert_close(ws.grad.double(), wd.grad, rtol=1e-3, atol=1e-4)
     torch.testing.assert_close(os_.grad.double(), od.grad, rtol=1e-3, atol=1e-3)
+
+
+def _dcn2_torch(data, offset, mask, weight, kh, kw, stride, pad, dil, dg):
+    """Differentiable float64 restatement of DCNv2 (zero-padded bilinear taps x mask, then the dense
+    contraction) used as the gradient reference."""
+    B, C, H, W = data.shape
+    Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) // stride + 1
+    Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) // stride + 1
+    hc = torch.arange(Ho, dtype=data.dtype).view(Ho, 1).expand(Ho, Wo)
+    wc = torch.arange(Wo, dtype=data.dtype).view(1, Wo).expand(Ho, Wo)
+    cpg = C // dg
+    cols = []
+    padded = torch.nn.functional.pad(data, (1, 1, 1, 1))  # zero ring: corners outside the map read 0
+    for t in range(kh * kw):
+        i, j = divmod(t, kw)
+        taps = []
+        for g in range(dg):
+            h = hc * stride - pad + i * dil + offset[:, g * 2 * kh * kw + 2 * t]
+            w = wc * stride - pad + j * dil + offset[:, g * 2 * kh * kw + 2 * t + 1]
+            inside = ((h > -1) & (w > -1) & (h < H) & (w < W)).to(data.dtype)
+            hl, wl = torch.floor(h).detach(), torch.floor(w).detach()
+            lh, lw = h - hl, w - wl
+            hl_i = hl.long().clamp(-1, H - 1) + 1
+            wl_i = wl.long().clamp(-1, W - 1) + 1
+            hh_i, wh_i = (hl_i + 1).clamp(max=H + 1), (wl_i + 1).clamp(max=W + 1)
+            src = padded[:, g * cpg:(g + 1) * cpg]
+            bi = torch.arange(B).view(B, 1, 1, 1)
+            ci = torch.arange(cpg).view(1, cpg, 1, 1)
+            def at(hi, wi):
+                return src[bi, ci, hi.unsqueeze(1), wi.unsqueeze(1)]
+            v = ((1 - lh) * (1 - lw)).unsqueeze(1) * at(hl_i, wl_i) + ((1 - lh) * lw).unsqueeze(1) * at(hl_i, wh_i) \
+                + (lh * (1 - lw)).unsqueeze(1) * at(hh_i, wl_i) + (lh * lw).unsqueeze(1) * at(hh_i, wh_i)
+            taps.append(v * (inside * mask[:, g * kh * kw + t]).unsqueeze(1))
+        cols.append(torch.cat(taps, 1))
+    col = torch.stack(cols, 2).reshape(B, C * kh * kw, Ho * Wo)  # (B, C, T, P) -> channel-major taps
+    out = torch.einsum("fk,bkp->bfp", weight.reshape(weight.shape[0], -1), col)
+    return out.reshape(B, weight.shape[0], Ho, Wo), col
+
+
+@pytest.mark.parametrize("stride,dilate,pad,dg", [(1, 1, 1, 4), (2, 2, 2, 1)])
+def test_modulated_dcn_forward_backward(stride, dilate, pad, dg):
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(11 + stride)
+    B, C, H, W, F, k = 2, 8, 13, 17, 6, 3
+    Ho = (H + 2 * pad - (dilate * (k - 1) + 1)) // stride + 1
+    Wo = (W + 2 * pad - (dilate * (k - 1) + 1)) // stride + 1
+    data = rng.standard_normal((B, C, H, W))
+    offset = rng.standard_normal((B, dg * 2 * k * k, Ho, Wo)) * 2.5 + 0.013   # reaches outside the map
+    mask = rng.uniform(0, 1, (B, dg * k * k, Ho, Wo))
+    weight = rng.standard_normal((F, C, k, k)) * 0.2
+    ref_in = [torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (data, offset, mask, weight)]
+    ref_out, ref_col = _dcn2_torch(*ref_in, k, k, stride, pad, dilate, dg)
+    gout = torch.tensor(rng.standard_normal(tuple(ref_out.shape)))
+    ref_out.backward(gout)
+    ins = [torch.tensor(a, dtype=torch.float32, device=dev, requires_grad=True) for a in (data, offset, mask, weight)]
+    out = ops.ModulatedDeformableConvolution(*ins[:3], ins[3], None, kernel=(k, k), stride=(stride, stride),
+                                             dilate=(dilate, dilate), pad=(pad, pad), num_deformable_group=dg,
+                                             no_bias=True)
+    out.backward(gout.to(dev, torch.float32))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref_out.detach().numpy(), rtol=2e-4, atol=2e-4)
+    for got, ref, name in zip(ins, ref_in, ("data", "offset", "mask", "weight")):
+        np.testing.assert_allclose(got.grad.cpu().numpy(), ref.grad.numpy(), rtol=2e-3, atol=2e-3, err_msg=name)
