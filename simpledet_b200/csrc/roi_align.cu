@@ -5,15 +5,19 @@
 // (level assignment).  NOT a port: the reference runs one thread per output element with 16
 // scattered global loads; here one CTA owns (roi, channel tile):
 //
-//   1. preamble  — PH+PW threads restate the reference's float/double sample loop ONCE per roi
-//                  (the sample coordinates depend only on (roi, ph) / (roi, pw), not on the
-//                  channel) into shared-memory axis tables: coordinate, lo/hi pixel, weights.
-//   2. stage     — the roi's feature window [CT, Hwin, Wwin] is copied NCHW-row-coalesced into
-//                  shared memory (each global byte of the window is read once per CTA).
-//   3. compute   — thread = (pw, channel group, ph chunk) walks down the rows with a 2-row
-//                  register cache, so a window element is read from shared memory ~once per
-//                  column tap instead of once per sample; bilinear weights are shared across
-//                  the CPT channels a thread owns.
+//   0. plan      — (with a workspace) one small kernel restates the reference's float/double sample
+//                  loop ONCE per roi (the sample coordinates depend only on (roi, ph) / (roi, pw),
+//                  not on the channel) into axis tables — coordinate, lo/hi pixel, weights — and
+//                  files the roi into a window-size class; a second one turns the classes into a
+//                  largest-window-first order for the main kernel's blockIdx.x.
+//   1. preamble  — the CTA loads its roi's tables (or computes them inline without a workspace).
+//   2. stage     — ONE producer warp copies the roi's feature window [CT, Hwin, Wwin]
+//                  NCHW-row-coalesced into a ring of shared-memory buffers with cp.async and
+//                  signals full/empty mbarriers.
+//   3. compute   — FOUR consumer warps; thread = (pw, w-sample[, channel half]) x (channel group,
+//                  ph chunk) walks down the rows with a 2-row register cache, so a window element
+//                  is read from shared memory ~once per column tap instead of once per sample;
+//                  bilinear weights are shared across the channels a thread owns.
 //
 // Arithmetic is bit-identical to the reference's CPU build: every float op on the coordinate
 // and value path is an explicit round-to-nearest intrinsic (no FMA contraction), the
