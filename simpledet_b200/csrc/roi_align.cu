@@ -59,6 +59,7 @@ struct RoiAlignArgs {
   int B, N, C, PH, PW;
   const void* plans;  // per-roi preamble records written by roi_align_plan_kernel, or nullptr
   const int* order;   // CTA x -> roi, largest window first (roi_align_order_kernel), or nullptr = identity
+  const int* order_count;  // device count of valid `order` entries (CTAs beyond it exit), or nullptr = all
   uint64_t negzero2;  // {-0.0f,-0.0f}: opaque addend that keeps FFMA2 products exact
 };
 
@@ -403,6 +404,7 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
 #ifdef SDET_RA_ABLATE
   const long long prof_t0 = clock64();
 #endif
+  if (a.order_count != nullptr && (int)blockIdx.x >= __ldg(a.order_count)) return;
   const int n = a.order ? __ldg(a.order + blockIdx.x) : (int)blockIdx.x;
   const int C = a.C;
   const int PH = kPH ? kPH : a.PH, PW = kPW ? kPW : a.PW;
@@ -827,6 +829,400 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
   }
 }
 
+
+// =============================================================================================
+// Window sharing (opt-in prototype, SDET_RA_SHARE=1): rois of one (image, level) whose windows
+// overlap are processed by ONE CTA against their union window, staged once per channel tile.
+// 7x7 launches are paced by L2 -> SM delivery of per-roi windows (profiles/r01_roi_align_7x7_ablation.txt);
+// benchmarks/window_sharing_sim.py estimates 1.9x (uniform random rois) to 5.5x (proposal-like) fewer
+// staged cells.  Inference only (no argmax planes), exactly-2-sample rois, 16-byte-stageable levels;
+// everything else stays with roi_align_v2_fwd_kernel through `left_order`.
+// =============================================================================================
+constexpr int kGMax = 6;            // members per group (6 x 1 KB of tables keeps 4 CTAs/SM next to 48 KB windows)
+constexpr int kGroupMaxRois = 4096; // per launch (B*N), bounded by the grouping kernel's shared memory
+constexpr int kGroupBuckets = 4096; // (segment = level*B + image) x 16 x 32 spatial cells of 16x16 pixels
+
+struct GroupRec {
+  int first, count;              // members = sorted_roi[first .. first+count)
+  int li, b;
+  int hmin, hmax, wmin, wmax;    // union window
+};
+struct GroupSched {
+  GroupRec* groups;
+  int* sorted_roi;
+  int* grp_order;    // CTA x -> group, costliest first
+  int* left_order;   // rois that stay with the per-roi kernel
+  int* counters;     // [0] number of groups, [1] number of left-over rois
+};
+
+__device__ __forceinline__ int win_plane(const int4 w) {  // rows x 16-byte padded pitch, as the kernel lays it out
+  return (w.y - w.x + 1) * ((w.w - w.z + 1 + 6) & ~3);
+}
+
+// One CTA.  Counting sort of the rois by (segment, 16x16-cell bucket of the window origin), greedy merge of
+// list neighbours inside a segment while the union window fits `cap_cells`, then a largest-first order.
+__global__ void __launch_bounds__(1024)
+roi_align_group_kernel(const __grid_constant__ RoiAlignArgs a, const PlanRecord* __restrict__ plans,
+                       const GroupSched gs, const int total, const int cap_cells) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  int* s_hist = reinterpret_cast<int*>(s_raw);                          // kGroupBuckets + 1 (+ pad)
+  int4* s_w4 = reinterpret_cast<int4*>(s_raw + (kGroupBuckets + 4) * 4);   // window per sorted position
+  unsigned short* s_n = reinterpret_cast<unsigned short*>(s_w4 + kGroupMaxRois);  // roi per sorted position
+  unsigned short* s_bkt = s_n + kGroupMaxRois;                          // bucket per roi (then: rank)
+  unsigned short* s_rank = s_bkt + kGroupMaxRois;
+  unsigned char* s_seg = reinterpret_cast<unsigned char*>(s_rank + kGroupMaxRois);  // segment per sorted position
+  unsigned char* s_start = s_seg + kGroupMaxRois;                       // member count at a group's first position
+  __shared__ int s_wsum[32];
+  __shared__ int s_cls[64], s_clsbase[64];
+  const int tid = threadIdx.x;
+  const int B = a.B, nseg = a.num_levels * B;
+  for (int i = tid; i <= kGroupBuckets; i += blockDim.x) s_hist[i] = 0;
+  if (tid < 64) s_cls[tid] = 0;
+  __syncthreads();
+  // ---- 1. bucket + rank
+  for (int n = tid; n < total; n += blockDim.x) {
+    const int4 h0 = __ldg(reinterpret_cast<const int4*>(plans + n));        // li, flags, hmin, hmax
+    const int4 h1 = __ldg(reinterpret_cast<const int4*>(plans + n) + 1);    // wmin, wmax, -, -
+    const int li = h0.x, flags = h0.y;
+    int bucket = kGroupBuckets;  // not shareable
+    if (nseg <= kGroupBuckets / 512 && li >= 0 && h0.w >= 0 && h1.y >= 0 &&
+        (flags & (kFlagNot2 | kFlagOverflow | kFlagEmpty)) == 0) {
+      const Level& L = a.lvl[li];
+      const bool vec = (((L.H * L.W) & 3) == 0) && ((reinterpret_cast<uintptr_t>(L.data) & 15) == 0);
+      const int4 w = make_int4(h0.z, h0.w, h1.x, h1.y);
+      const int hw_ = w.y - w.x + 1, wp = (w.w - w.z + 1 + 6) & ~3;
+      if (vec && win_plane(w) <= cap_cells && wp <= 64 && hw_ <= 128) {
+        const int seg = li * B + n / a.N;
+        bucket = seg * 512 + min(15, w.x >> 4) * 32 + min(31, w.z >> 4);
+      }
+    }
+    s_bkt[n] = (unsigned short)bucket;
+    s_rank[n] = (unsigned short)atomicAdd(&s_hist[bucket], 1);
+  }
+  __syncthreads();
+  // ---- 2. exclusive scan of the histogram (4 bins per thread + the spill bin)
+  {
+    int v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = s_hist[tid * 4 + k]; sum += v[k]; }
+    int inc = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((tid & 31) >= o) inc += t;
+    }
+    if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
+    __syncthreads();
+    if (tid < 32) {
+      int w = s_wsum[tid];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (tid >= o) w += t;
+      }
+      s_wsum[tid] = w;
+    }
+    __syncthreads();
+    int run = inc - sum + ((tid >> 5) ? s_wsum[(tid >> 5) - 1] : 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s_hist[tid * 4 + k] = run; run += v[k]; }
+    if (tid == 1023) s_hist[kGroupBuckets] = run;  // first position of the non-shareable rois
+  }
+  __syncthreads();
+  const int ngp = s_hist[kGroupBuckets];  // shareable rois come first (none when there are too many segments)
+  // ---- 3. scatter
+  for (int n = tid; n < total; n += blockDim.x) {
+    const int bucket = s_bkt[n];
+    const int pos = s_hist[bucket] + s_rank[n];
+    const int4 h0 = __ldg(reinterpret_cast<const int4*>(plans + n));
+    const int4 h1 = __ldg(reinterpret_cast<const int4*>(plans + n) + 1);
+    s_n[pos] = (unsigned short)n;
+    s_w4[pos] = make_int4(h0.z, h0.w, h1.x, h1.y);
+    s_seg[pos] = (unsigned char)(bucket < kGroupBuckets ? bucket / 512 : 255);
+    s_start[pos] = 0;
+  }
+  __syncthreads();
+  // ---- 4. greedy merge, one thread per segment (the list of a segment is contiguous)
+  for (int p = tid; p < ngp; p += blockDim.x) {
+    if (p > 0 && s_seg[p - 1] == s_seg[p]) continue;
+    const int seg = s_seg[p];
+    int first = p, cnt = 1;
+    int4 cur = s_w4[p];
+    for (int q = p + 1; q < ngp && s_seg[q] == seg; ++q) {
+      const int4 w = s_w4[q];
+      const int4 u = make_int4(min(cur.x, w.x), max(cur.y, w.y), min(cur.z, w.z), max(cur.w, w.w));
+      if (cnt < kGMax && win_plane(u) <= cap_cells && ((u.w - u.z + 1 + 6) & ~3) <= 64 && (u.y - u.x + 1) <= 128) {
+        cur = u;
+        ++cnt;
+      } else {
+        s_start[first] = (unsigned char)cnt;
+        s_w4[first] = cur;
+        first = q;
+        cur = w;
+        cnt = 1;
+      }
+    }
+    s_start[first] = (unsigned char)cnt;
+    s_w4[first] = cur;
+  }
+  __syncthreads();
+  // ---- 5. number the groups (scan over the start flags), write records, cost classes
+  {
+    int f[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int p = tid * 4 + k;
+      f[k] = (p < ngp && s_start[p] != 0) ? 1 : 0;
+      sum += f[k];
+    }
+    int inc = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((tid & 31) >= o) inc += t;
+    }
+    if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
+    __syncthreads();
+    if (tid < 32) {
+      int w = s_wsum[tid];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (tid >= o) w += t;
+      }
+      s_wsum[tid] = w;
+    }
+    __syncthreads();
+    int g = inc - sum + ((tid >> 5) ? s_wsum[(tid >> 5) - 1] : 0);
+    const int ngroups = s_wsum[31];
+    if (tid == 0) {
+      gs.counters[0] = ngroups;
+      gs.counters[1] = total - ngp;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int p = tid * 4 + k;
+      if (!f[k]) continue;
+      const int4 u = s_w4[p];
+      const int seg = s_seg[p], cnt = s_start[p];
+      GroupRec r;
+      r.first = p; r.count = cnt; r.li = seg / B; r.b = seg - r.li * B;
+      r.hmin = u.x; r.hmax = u.y; r.wmin = u.z; r.wmax = u.w;
+      gs.groups[g] = r;
+      // cost class for the largest-first order: staged cells + per-member arithmetic
+      const int cls = min(63, (win_plane(u) + 160 * cnt) / 48);
+      s_bkt[g] = (unsigned short)cls;                       // (s_bkt / s_rank are free again)
+      s_rank[g] = (unsigned short)atomicAdd(&s_cls[cls], 1);
+      ++g;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int acc = 0;
+      for (int c = 63; c >= 0; --c) {
+        s_clsbase[c] = acc;
+        acc += s_cls[c];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < ngroups; i += blockDim.x) gs.grp_order[s_clsbase[s_bkt[i]] + s_rank[i]] = i;
+  }
+  for (int p = tid; p < total; p += blockDim.x) {
+    gs.sorted_roi[p] = s_n[p];
+    if (p >= ngp) gs.left_order[p - ngp] = s_n[p];
+  }
+}
+
+template <int CPT, int kPH, int kPW, int kCapFloats>
+__global__ void __launch_bounds__(kFwdThreads, 4)
+roi_align_v2_fwd_grouped_kernel(const __grid_constant__ RoiAlignArgs a, const GroupSched gs, const int tiles) {
+  extern __shared__ __align__(16) float s_win[];
+  __shared__ __align__(16) int4 s_hrow_g[kGMax][32];    // per member, per (ph, h-sample): off_lo, off_hi, w0, w1
+  __shared__ __align__(16) int4 s_wtab_g[kGMax][32];    // per member, per (pw, w-sample): xl, xr, w0, w1
+  __shared__ int s_member[kGMax];
+  __shared__ __align__(8) unsigned long long s_bar[8];
+  constexpr int NW = 4;
+  constexpr int PH = kPH, PW = kPW, PP = kPH * kPW;
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x >= __ldg(gs.counters)) return;
+  const GroupRec G = gs.groups[__ldg(gs.grp_order + blockIdx.x)];
+  const int C = a.C;
+  const int cgrp0 = blockIdx.y * tiles * (2 * CPT), cgrp1 = min(C, cgrp0 + tiles * (2 * CPT));
+  const Level& L = a.lvl[G.li];
+  const int H = L.H, W = L.W, HW = H * W;
+  const int hmin = G.hmin, wmin = G.wmin;
+  const int Hwin = G.hmax - hmin + 1, Wwin = G.wmax - wmin + 1;
+  const float* gimg = L.data + (size_t)G.b * C * HW;
+  const int Wp = (Wwin + 3 + 3) & ~3;   // (the grouping kernel only admits 16-byte-stageable levels)
+  const int plane = Hwin * Wp;
+  constexpr int CS0 = kCapFloats / (4 * CPT), CS1 = kCapFloats / (2 * CPT), CS3 = kCapFloats / CPT;
+  const int mode = plane <= CS0 ? 0 : (plane <= CS1 ? 1 : 3);
+
+  // ---- member tables from the plan records
+  if (tid < G.count) s_member[tid] = __ldg(gs.sorted_roi + G.first + tid);
+  __syncthreads();
+  const PlanRecord* plans = static_cast<const PlanRecord*>(a.plans);
+  for (int idx = tid; idx < G.count * 64; idx += blockDim.x) {
+    const int m = idx >> 6, e = idx & 63;
+    const PlanRecord* rec = plans + s_member[m];
+    if (e < 32) {
+      const int ph = e >> 1, sidx = e & 1;
+      if (ph < PH) {
+        const int j = ph * kMaxS + sidx;
+        const int lo = __ldg(rec->th.lo + j), hi = __ldg(rec->th.hi + j);
+        const int sh_lo = (lo * W + wmin) & 3, sh_hi = (hi * W + wmin) & 3;
+        s_hrow_g[m][e] = make_int4(4 * ((lo - hmin) * Wp + sh_lo), 4 * ((hi - hmin) * Wp + sh_hi),
+                                   __float_as_int(__ldg(rec->th.w0 + j)), __float_as_int(__ldg(rec->th.w1 + j)));
+      }
+    } else {
+      const int pw_ = (e - 32) >> 1, sidx = e & 1;
+      if (pw_ < PW) {
+        const int j = pw_ * kMaxS + sidx;
+        s_wtab_g[m][e - 32] = make_int4(__ldg(rec->tw.lo + j) - wmin, __ldg(rec->tw.hi + j) - wmin,
+                                        __float_as_int(__ldg(rec->tw.w0 + j)), __float_as_int(__ldg(rec->tw.w1 + j)));
+      }
+    }
+  }
+  if (tid == 0) {
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(s_bar);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar0 + 8u * i, 32);
+      mbar_init(bar0 + 8u * (4 + i), NW);
+    }
+  }
+  __syncthreads();
+
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(s_win);
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr int kSub = (kPW <= 8) ? 2 : 1;
+  const int half = (kSub == 2) ? (lane >> 4) : 0;
+  const int pw = (kSub == 2 ? (lane & 15) : lane) >> 1, sx = lane & 1;
+  const bool lane_on = pw < PW;
+  const uint64_t nz2 = a.negzero2;
+
+  auto run = [&](auto cs_tag, auto ncg_tag, auto nbuf_tag) {
+    constexpr int kCS = decltype(cs_tag)::value;
+    constexpr int NCG = decltype(ncg_tag)::value;
+    constexpr int NBUF = decltype(nbuf_tag)::value;
+    constexpr int CTILE = NCG * CPT;
+    constexpr int PHS = NW / NCG;
+    constexpr int BUF_BYTES = CTILE * kCS * 4;
+    constexpr int CL = CPT / kSub;
+    const int ntiles = (cgrp1 - cgrp0) / CTILE;
+    const int cg = warp % NCG, pc = warp / NCG;
+    const int chunk = (PH + PHS - 1) / PHS;
+    const int ph_beg = pc * chunk, ph_end = min(PH, ph_beg + chunk);
+    const int nch = (Wwin + 3 + 3) >> 2;
+    const int nitems = Hwin * nch;
+    const unsigned nch_magic = 0xFFFFFFFFu / (unsigned)nch + 1u;
+    auto stage = [&](int tile, unsigned buf) {
+      const float* g0 = gimg + (size_t)(cgrp0 + tile * CTILE) * HW;
+      for (int idx = lane; idx < nitems; idx += 32) {
+        const int y = (int)__umulhi((unsigned)idx, nch_magic), jchunk = idx - y * nch;
+        const int e0 = (hmin + y) * W + wmin;
+        const unsigned dst = buf + 4u * (unsigned)(y * Wp + jchunk * 4);
+        const int sh = e0 & 3;
+        if (jchunk * 4 < sh + Wwin) {
+          const float* src = g0 + (e0 - sh + jchunk * 4);
+#pragma unroll
+          for (int c = 0; c < CTILE; ++c) {
+            cp_async16(dst + c * (kCS * 4), src);
+            src += HW;
+          }
+        }
+      }
+    };
+    // one member roi of the group against the staged tile
+    auto compute = [&](int tile, unsigned buf, int m) {
+      const int n = s_member[m];
+      int xl = 0, xr = 0;
+      float b0 = 0.f, b1 = 0.f;
+      if (lane_on) {
+        const int4 wt = s_wtab_g[m][pw * 2 + sx];
+        xl = wt.x; xr = wt.y; b0 = __int_as_float(wt.z); b1 = __int_as_float(wt.w);
+      }
+      const int cbase = cgrp0 + tile * CTILE + cg * CPT + half * CL;
+      const unsigned sl = buf + 4u * (unsigned)((cg * CPT + half * CL) * kCS + xl);
+      const unsigned sr = buf + 4u * (unsigned)((cg * CPT + half * CL) * kCS + xr);
+      float RA[CL][2], RB[CL][2];
+      int rowA = -1, rowB = -1;
+      float* outh = a.out + ((size_t)n * C + cbase) * PP + (size_t)ph_beg * PW + pw + (size_t)(sx * (CL / 2)) * PP;
+      auto sample = [&](const int4 hr, float (&v)[CL]) {
+        const int olo = hr.x, ohi = hr.y;
+        const float a0 = __int_as_float(hr.z), a1 = __int_as_float(hr.w);
+        const float wtl = __fmul_rn(a0, b0), wbl = __fmul_rn(a1, b0);
+        const float wtr = __fmul_rn(a0, b1), wbr = __fmul_rn(a1, b1);
+        const uint64_t wtl2 = pack2(wtl, wtl), wbl2 = pack2(wbl, wbl);
+        const uint64_t wtr2 = pack2(wtr, wtr), wbr2 = pack2(wbr, wbr);
+        auto step = [&](const float (&Lo)[CL][2], const float (&Hi)[CL][2]) {
+#pragma unroll
+          for (int k = 0; k < CL; k += 2) {
+            const uint64_t ptl = fma2(wtl2, pack2(Lo[k][0], Lo[k + 1][0]), nz2);
+            const uint64_t pbl = fma2(wbl2, pack2(Hi[k][0], Hi[k + 1][0]), nz2);
+            const uint64_t ptr = fma2(wtr2, pack2(Lo[k][1], Lo[k + 1][1]), nz2);
+            const uint64_t pbr = fma2(wbr2, pack2(Hi[k][1], Hi[k + 1][1]), nz2);
+            unpack2(add2(add2(add2(ptl, pbl), ptr), pbr), v[k], v[k + 1]);
+          }
+        };
+        if (__all_sync(0xffffffffu, olo == rowA)) {
+          if (__any_sync(0xffffffffu, ohi != rowB)) {
+            TapLoader<CL, kCS>::run(RB, sl + ohi, sr + ohi);
+            rowB = ohi;
+          }
+          step(RA, RB);
+        } else if (__all_sync(0xffffffffu, olo == rowB)) {
+          if (__any_sync(0xffffffffu, ohi != rowA)) {
+            TapLoader<CL, kCS>::run(RA, sl + ohi, sr + ohi);
+            rowA = ohi;
+          }
+          step(RB, RA);
+        } else {
+          TapLoader<CL, kCS>::run(RA, sl + olo, sr + olo);
+          rowA = olo;
+          if (__any_sync(0xffffffffu, ohi != rowB)) {
+            TapLoader<CL, kCS>::run(RB, sl + ohi, sr + ohi);
+            rowB = ohi;
+          }
+          step(RA, RB);
+        }
+      };
+      const int4* tab = s_hrow_g[m];
+      for (int ph = ph_beg; ph < ph_end; ++ph) {
+        float v0[CL], v1[CL];
+        sample(tab[ph * 2], v0);
+        sample(tab[ph * 2 + 1], v1);
+        float best[CL];
+#pragma unroll
+        for (int k = 0; k < CL; ++k) {
+          const float mk = fmaxf(v0[k], v1[k]);
+          best[k] = max3f(mk, __shfl_xor_sync(0xffffffffu, mk, 1), -FLT_MAX);
+        }
+        if (lane_on) {
+#pragma unroll
+          for (int k = 0; k < CL / 2; ++k) outh[k * PP] = sx ? best[CL / 2 + k] : best[k];
+        }
+        outh += PW;
+      }
+    };
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(s_bar);
+    if (warp == NW) {
+      for (int t = 0; t < ntiles; ++t) {
+        const int b = t % NBUF, k = t / NBUF;
+        if (k > 0) mbar_wait(bar0 + 8u * (4 + b), (unsigned)((k - 1) & 1));
+        stage(t, sbase + (unsigned)b * BUF_BYTES);
+        cp_async_mbar_arrive(bar0 + 8u * b);
+      }
+      return;
+    }
+    for (int t = 0; t < ntiles; ++t) {
+      const int b = t % NBUF, k = t / NBUF;
+      mbar_wait(bar0 + 8u * b, (unsigned)(k & 1));
+      for (int m = 0; m < G.count; ++m) compute(t, sbase + (unsigned)b * BUF_BYTES, m);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8u * (4 + b));
+    }
+  };
+  using std::integral_constant;
+  if (mode == 0) run(integral_constant<int, CS0>{}, integral_constant<int, 1>{}, integral_constant<int, 4>{});
+  else if (mode == 1) run(integral_constant<int, CS1>{}, integral_constant<int, 1>{}, integral_constant<int, 2>{});
+  else run(integral_constant<int, CS3>{}, integral_constant<int, 1>{}, integral_constant<int, 1>{});
+}
+
 // ---------------------------------------------------------------------------------------------
 // Backward (roi_align_v2.cu:35-84): one thread per output-gradient element, 4 red.global adds.
 // ---------------------------------------------------------------------------------------------
@@ -919,10 +1315,48 @@ int launch_fwd_t(const RoiAlignArgs& a, cudaStream_t st) {
   return SDET_OK;
 }
 
-// PlanRecord[B*N] | counts[64] | (bucket, rank)[B*N] | order[B*N]
+// PlanRecord[B*N] | counts[64] | (bucket, rank)[B*N] | order[B*N] | GroupRec[B*N] | sorted_roi[B*N] |
+// grp_order[B*N] | left_order[B*N] | counters[64]      (the group arrays serve SDET_RA_SHARE=1 only)
+size_t ws_align16(size_t v) { return (v + 15) & ~(size_t)15; }
 size_t plan_workspace_bytes(int B, int N) {
   const size_t total = (size_t)B * N;
-  return sizeof(PlanRecord) * total + 256 + 8 * total + 4 * total;
+  return sizeof(PlanRecord) * total + 256 + 8 * total + ws_align16(4 * total) + sizeof(GroupRec) * total +
+         3 * ws_align16(4 * total) + 256;
+}
+
+template <int CPT, int kPH, int kPW, int kCapFloats>
+int launch_fwd_t(const RoiAlignArgs& a, cudaStream_t st);
+
+// Window-sharing path: grouping kernel, grouped kernel for the shareable rois, per-roi kernel for the rest.
+template <int CPT, int kPH, int kPW, int kCapFloats>
+int launch_fwd_grouped_t(RoiAlignArgs a, const GroupSched gs, cudaStream_t st) {
+  static bool configured = false;
+  auto k_grp = roi_align_v2_fwd_grouped_kernel<CPT, kPH, kPW, kCapFloats>;
+  constexpr int smem_bytes = kCapFloats * 4;
+  constexpr size_t group_smem = (size_t)(kGroupBuckets + 4) * 4 + (size_t)kGroupMaxRois * (16 + 3 * 2 + 2);
+  if (!configured) {
+    SDET_CUDA(cudaFuncSetAttribute(k_grp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SDET_CUDA(cudaFuncSetAttribute(roi_align_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem));
+    configured = true;
+  }
+  const int total = a.B * a.N;
+  roi_align_group_kernel<<<1, 1024, group_smem, st>>>(a, static_cast<const PlanRecord*>(a.plans), gs, total,
+                                                       kCapFloats / CPT);
+  SDET_LAUNCH_CHECK("roi_align_group_kernel");
+  constexpr int CT = 2 * CPT;
+  const int total_tiles = (a.C + CT - 1) / CT;
+  // a group carries several rois' arithmetic, and there are several times fewer groups than rois (their
+  // number is only known on the device): split the channels finer than the per-roi kernel does
+  int tpc = (int)((long long)total * total_tiles / (148 * 12)) / 4;
+  if (const char* e = getenv("SDET_RA_SHARE_TPC")) tpc = atoi(e);
+  if (tpc < 1) tpc = 1;
+  if (tpc > total_tiles) tpc = total_tiles;
+  dim3 grid((unsigned)total, (unsigned)((total_tiles + tpc - 1) / tpc));
+  k_grp<<<grid, kFwdThreads, smem_bytes, st>>>(a, gs, tpc);
+  SDET_LAUNCH_CHECK("roi_align_v2_fwd_grouped_kernel");
+  a.order = gs.left_order;
+  a.order_count = gs.counters + 1;
+  return launch_fwd_t<CPT, kPH, kPW, kCapFloats>(a, st);
 }
 
 int launch_fwd(RoiAlignArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -931,6 +1365,7 @@ int launch_fwd(RoiAlignArgs& a, void* workspace, size_t workspace_bytes, cudaStr
   a.negzero2 = 0x8000000080000000ull;  // {-0.0f, -0.0f}, see the forward kernel's header
   a.plans = nullptr;
   a.order = nullptr;
+  a.order_count = nullptr;
   if (workspace != nullptr && a.PH <= 16 && a.PW <= 16) {
     const size_t total = (size_t)a.B * a.N;
     const size_t need = plan_workspace_bytes(a.B, a.N);
@@ -950,6 +1385,19 @@ int launch_fwd(RoiAlignArgs& a, void* workspace, size_t workspace_bytes, cudaStr
     SDET_LAUNCH_CHECK("roi_align_order_kernel");
     a.plans = workspace;
     a.order = sc.order;
+    // opt-in prototype: rois with overlapping windows share one staged union window
+    static const bool share = getenv("SDET_RA_SHARE") != nullptr && atoi(getenv("SDET_RA_SHARE")) != 0;
+    const bool sq7 = a.PH == 7 && a.PW == 7, sq14 = a.PH == 14 && a.PW == 14;
+    if (share && a.argx == nullptr && (sq7 || sq14) && total <= (size_t)kGroupMaxRois && a.C % 16 == 0) {
+      char* g = w + sizeof(PlanRecord) * total + 256 + 8 * total + ws_align16(4 * total);
+      GroupSched gs{};
+      gs.groups = reinterpret_cast<GroupRec*>(g); g += sizeof(GroupRec) * total;
+      gs.sorted_roi = reinterpret_cast<int*>(g); g += ws_align16(4 * total);
+      gs.grp_order = reinterpret_cast<int*>(g); g += ws_align16(4 * total);
+      gs.left_order = reinterpret_cast<int*>(g); g += ws_align16(4 * total);
+      gs.counters = reinterpret_cast<int*>(g);
+      return sq7 ? launch_fwd_grouped_t<8, 7, 7, 12288>(a, gs, st) : launch_fwd_grouped_t<8, 14, 14, 12288>(a, gs, st);
+    }
   }
 #ifdef SDET_RA_CAP7
   if (a.PH == 7 && a.PW == 7) return launch_fwd_t<8, 7, 7, SDET_RA_CAP7>(a, st);
