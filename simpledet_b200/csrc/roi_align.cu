@@ -379,6 +379,11 @@ __device__ int g_ra_ablate = 0;
 // cycle counters: [0] consumer warps waiting for a full buffer, [1] computing, [2] CTA lifetime up to the tile
 // loop (preamble, tables, barrier init; thread 0), [3] producer waiting, [4] whole CTA lifetime (thread 0)
 __device__ unsigned long long g_ra_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+// Timeline of ONE CTA (blockIdx.x == g_ra_trace_cta, blockIdx.y == 0), clock64 ticks relative to its start:
+// row 0 = consumer warp 0 {after preamble, then per tile: data arrived, compute done}, row 1 = producer warp
+// {per tile: buffer free, copies issued}.  Read back with sdet_debug_ra_trace.
+__device__ int g_ra_trace_cta = -1;
+__device__ long long g_ra_trace[2][520];
 #endif
 
 // CTA = 4 consumer warps (the arithmetic) + 1 producer warp (all cp.async staging).  Staging and
@@ -764,6 +769,11 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
 #endif
 #ifdef SDET_RA_ABLATE
     long long prof_wait = 0, prof_comp = 0;
+    const bool trace = ((int)blockIdx.x == g_ra_trace_cta) && blockIdx.y == 0 && lane == 0;
+    if (trace && warp == 0) {
+      g_ra_trace[0][0] = clock64() - prof_t0;
+      g_ra_trace[0][1] = ntiles;
+    }
 #endif
     if (warp == NW) {
       for (int t = 0; t < ntiles; ++t) {
@@ -774,9 +784,13 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
         if (k > 0) mbar_wait(bar0 + 8u * (4 + b), (unsigned)((k - 1) & 1));  // consumers released the buffer
 #ifdef SDET_RA_ABLATE
         prof_wait += clock64() - c0;
+        if (trace && t < 256) g_ra_trace[1][2 + 2 * t] = clock64() - prof_t0;
 #endif
         stage(t, sbase + (unsigned)b * BUF_BYTES);
         cp_async_mbar_arrive(bar0 + 8u * b);
+#ifdef SDET_RA_ABLATE
+        if (trace && t < 256) g_ra_trace[1][3 + 2 * t] = clock64() - prof_t0;
+#endif
       }
 #ifdef SDET_RA_ABLATE
       if (lane == 0) atomicAdd(&g_ra_prof[3], (unsigned long long)prof_wait);
@@ -798,6 +812,10 @@ roi_align_v2_fwd_kernel(const __grid_constant__ RoiAlignArgs a, const int tiles)
 #ifdef SDET_RA_ABLATE
       prof_wait += c1 - c0;
       prof_comp += clock64() - c1;
+      if (trace && warp == 0 && t < 256) {
+        g_ra_trace[0][2 + 2 * t] = c1 - prof_t0;
+        g_ra_trace[0][3 + 2 * t] = clock64() - prof_t0;
+      }
 #endif
     }
 #ifdef SDET_RA_ABLATE
@@ -1418,6 +1436,16 @@ extern "C" int sdet_debug_ra_prof(unsigned long long* out4, int reset) {
     unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaMemcpyToSymbol(g_ra_prof, z, sizeof(z));
   }
+  return 0;
+}
+#endif
+
+#ifdef SDET_RA_ABLATE
+// cta >= 0: arm the timeline for that CTA (call before the launch); out != NULL: copy the 2 x 520 ticks back.
+extern "C" int sdet_debug_ra_trace(int cta, long long* out) {
+  cudaDeviceSynchronize();
+  if (out) cudaMemcpyFromSymbol(out, g_ra_trace, sizeof(long long) * 2 * 520);
+  cudaMemcpyToSymbol(g_ra_trace_cta, &cta, sizeof(int));
   return 0;
 }
 #endif
