@@ -60,6 +60,7 @@ def main():
     ap.add_argument("--plan", type=int, default=1)
     ap.add_argument("--noflush", type=int, default=0)
     ap.add_argument("--sorted", type=int, default=0, help="1: rois pre-sorted by (level, y, x) on the host (locality probe)")
+    ap.add_argument("--path", type=int, default=0, help="0: automatic (band-stationary kernel), 1: per-roi kernel only")
     ap.add_argument("--backward", type=int, default=0, help="time the backward pass (incl. zero-fill of the grads)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -89,7 +90,7 @@ def main():
 
     def fn():
         ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=bool(a.argmax),
-                              use_plan=bool(a.plan))
+                              use_plan=bool(a.plan), path=a.path)
 
     if a.backward:
         import ctypes
@@ -111,23 +112,7 @@ def main():
                 pooled, 0, torch.cuda.current_stream().cuda_stream))
 
     med, mn = time_op(fn, a.iters, flush, not a.noflush)
-    prof = None
-    try:  # profiling builds (-DSDET_RA_ABLATE) export per-phase cycle counters of the forward kernel
-        import ctypes as _ct
-        from simpledet_b200 import _lib as _l
-        f = _l.lib().sdet_debug_ra_prof  # AttributeError in product builds
-        f.argtypes, f.restype = [_ct.c_void_p, _ct.c_int], _ct.c_int
-        buf = (_ct.c_ulonglong * 8)()
-        f(buf, 1)
-        fn()
-        f(buf, 1)
-        prof = {"consumer_wait_cyc": buf[0], "consumer_compute_cyc": buf[1], "producer_wait_cyc": buf[3],
-                "cta_preamble_cyc": buf[2], "cta_lifetime_cyc": buf[4]}
-    except (AttributeError, OSError):
-        pass
-    print(json.dumps({"shape": a.shape, "B": B, "N": N, "pooled": pooled, "argmax": a.argmax, "sorted": a.sorted, "backward": a.backward, "plan": a.plan, "noflush": a.noflush, "modepref": os.environ.get("SDET_RA_MODEPREF"), "tiles": os.environ.get("SDET_RA_TILES"),
-                      "cpt": os.environ.get("SDET_RA_CPT"), "phs": os.environ.get("SDET_RA_PHS"),
-                      "prof": prof, "us_median": round(med, 2), "us_min": round(mn, 2), "alg_bytes": nbytes,
+    print(json.dumps({"shape": a.shape, "path": a.path, "B": B, "N": N, "pooled": pooled, "argmax": a.argmax, "sorted": a.sorted, "backward": a.backward, "plan": a.plan, "noflush": a.noflush, "us_median": round(med, 2), "us_min": round(mn, 2), "alg_bytes": nbytes,
                       "GBps": round(nbytes / med / 1e3, 1),
                       "levels": np.bincount(lv.ravel() + 1, minlength=5).tolist()}))
 

@@ -58,6 +58,15 @@ int sdet_roi_align_v2_forward(const float* data, const float* rois, float* out, 
                               float* argmax_y, int B, int N, int C, int H, int W, int pooled_h,
                               int pooled_w, float spatial_scale, void* workspace,
                               size_t workspace_bytes, void* stream);
+/* Same operator with an explicit kernel choice (tests and A/B timing; results are bit-identical):
+ *   path = 0  automatic: with a workspace and no argmax planes the band-stationary kernel (bulk-TMA
+ *             staged feature bands, roi_align_band.cu) takes every roi it can and the per-roi kernel
+ *             the rest;  path = 1  per-roi kernel only.
+ *   path_used (host int, may be NULL): 0 inline per-roi, 1 planned per-roi, 2 band-stationary. */
+int sdet_roi_align_v2_forward_ex(const float* data, const float* rois, float* out, float* argmax_x,
+                                 float* argmax_y, int B, int N, int C, int H, int W, int pooled_h,
+                                 int pooled_w, float spatial_scale, void* workspace,
+                                 size_t workspace_bytes, void* stream, int path, int* path_used);
 
 /* _backward_ROIAlign_v2  (operator_cxx/contrib/roi_align_v2.cu:17-85 kernel, :88-143 driver).
  *   ograd, argmax_x, argmax_y (B,N,C,PH,PW); grad_data (B,C,H,W).
@@ -83,6 +92,14 @@ int sdet_fpn_roi_align_v2_forward(const float* const* feats, const int* H, const
                                   int32_t* levels_out, int B, int N, int C, int pooled_h,
                                   int pooled_w, int roi_canonical_scale, int roi_canonical_level,
                                   void* workspace, size_t workspace_bytes, void* stream);
+/* ... with the kernel choice of sdet_roi_align_v2_forward_ex. */
+int sdet_fpn_roi_align_v2_forward_ex(const float* const* feats, const int* H, const int* W,
+                                     const int* strides, int num_levels, const float* rois,
+                                     float* out, float* argmax_x, float* argmax_y,
+                                     int32_t* levels_out, int B, int N, int C, int pooled_h,
+                                     int pooled_w, int roi_canonical_scale, int roi_canonical_level,
+                                     void* workspace, size_t workspace_bytes, void* stream, int path,
+                                     int* path_used);
 
 /* Backward of the fused op: scatters into the grad tensor of each roi's assigned level.
  *   grad_feats[l] device (B,C,H[l],W[l]); levels (B*N int32 device) as written by the forward. */

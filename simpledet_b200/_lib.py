@@ -30,11 +30,16 @@ _SIGNATURES = {
     "sdet_roi_align_v2_workspace": [c_int, c_int],
     "sdet_roi_align_v2_forward": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_float, _P, c_size_t, _P],
+    "sdet_roi_align_v2_forward_ex": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_float, _P, c_size_t, _P, c_int, POINTER(c_int)],
     "sdet_roi_align_v2_backward": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_int, _P],
     "sdet_fpn_roi_align_v2_forward": [POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                       c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_int, _P, c_size_t, _P],
+    "sdet_fpn_roi_align_v2_forward_ex": [POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                         c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, c_int, _P, c_size_t, _P, c_int, POINTER(c_int)],
     "sdet_fpn_roi_align_v2_backward": [_P, _P, _P, _P, POINTER(_P), POINTER(c_int), POINTER(c_int),
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "sdet_roi_pooling_v1_forward": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -58,7 +58,8 @@ def _pair(v) -> tuple[int, int]:
 # --------------------------------------------------------------------------------------------
 # _contrib_ROIAlign_v2  (operator_cxx/contrib/roi_align_v2.cc:170-228)
 # --------------------------------------------------------------------------------------------
-def roi_align_v2_raw(data, rois, pooled_size, spatial_scale, with_argmax=True, use_plan=True):
+def roi_align_v2_raw(data, rois, pooled_size, spatial_scale, with_argmax=True, use_plan=True, path=0,
+                     return_path=False):
     """All three outputs of the reference op: (out, argmax_x, argmax_y), each (B,N,C,PH,PW).
 
     Shape rules of ROIAlign_v2 FInferShape (roi_align_v2.cc:187-210): data 4-D, rois 3-D
@@ -80,8 +81,12 @@ def roi_align_v2_raw(data, rois, pooled_size, spatial_scale, with_argmax=True, u
     L = _lib.lib()
     nbytes = L.sdet_roi_align_v2_workspace(B, N) if use_plan else 0
     ws = torch.empty(nbytes, dtype=torch.uint8, device=data.device) if nbytes else None
-    check(L.sdet_roi_align_v2_forward(_p(data), _p(rois), _p(out), _p(ax), _p(ay), B, N, C, H, W, ph, pw,
-                                      float(spatial_scale), _p(ws), nbytes, _stream()))
+    used = ctypes.c_int(-1)
+    check(L.sdet_roi_align_v2_forward_ex(_p(data), _p(rois), _p(out), _p(ax), _p(ay), B, N, C, H, W, ph, pw,
+                                         float(spatial_scale), _p(ws), nbytes, _stream(), int(path),
+                                         ctypes.byref(used)))
+    if return_path:
+        return out, ax, ay, used.value
     return out, ax, ay
 
 
@@ -137,7 +142,7 @@ def _level_arrays(feats: Sequence[torch.Tensor], strides: Sequence[int]):
 
 
 def fpn_roi_align_raw(feats, rois, strides, out_size, roi_canonical_scale=224,
-                      roi_canonical_level=4, with_argmax=True, use_plan=True):
+                      roi_canonical_level=4, with_argmax=True, use_plan=True, path=0, return_path=False):
     """-> (out, argmax_x, argmax_y, levels).  out (B,N,C,PH,PW); levels (B,N) int32 index into
     `strides` (-1: the roi matched no level and pools to zeros)."""
     feats, ptrs, Hs, Ws, Ss, B, C = _level_arrays(feats, strides)
@@ -153,9 +158,13 @@ def fpn_roi_align_raw(feats, rois, strides, out_size, roi_canonical_scale=224,
     L = _lib.lib()
     nbytes = L.sdet_roi_align_v2_workspace(B, N) if use_plan else 0
     ws = torch.empty(nbytes, dtype=torch.uint8, device=rois.device) if nbytes else None
-    check(L.sdet_fpn_roi_align_v2_forward(
+    used = ctypes.c_int(-1)
+    check(L.sdet_fpn_roi_align_v2_forward_ex(
         ptrs, Hs, Ws, Ss, len(feats), _p(rois), _p(out), _p(ax), _p(ay), _p(levels), B, N, C, ph, pw,
-        int(roi_canonical_scale), int(roi_canonical_level), _p(ws), nbytes, _stream()))
+        int(roi_canonical_scale), int(roi_canonical_level), _p(ws), nbytes, _stream(), int(path),
+        ctypes.byref(used)))
+    if return_path:  # 0 inline per-roi, 1 planned per-roi, 2 band-stationary (+ per-roi leftovers)
+        return out, ax, ay, levels, used.value
     return out, ax, ay, levels
 
 
