@@ -55,8 +55,11 @@ void oracle_decode_bbox(const float* rois, const float* deltas, const float* im_
           float dh = d[3] * stds[3] + means[3];
           float pred_ctr_x = dx * width + ctr_x;
           float pred_ctr_y = dy * height + ctr_y;
-          float pred_w = expf(dw) * width; /* `exp(float)` resolves to the float overload */
-          float pred_h = expf(dh) * height;
+          /* decodebbox.cc:62-63 `exp(dw) * width` with a float dw: the unqualified call binds to ::exp(double)
+           * (the file pulls in <cmath> only, no float overload in the global namespace), the product is formed
+           * in double and narrowed once.  Pinned by the compiled reference (tests/test_oracle_ref_cxx.py). */
+          float pred_w = (float)(exp((double)dw) * (double)width);
+          float pred_h = (float)(exp((double)dh) * (double)height);
           x1 = pred_ctr_x - 0.5f * (pred_w - 1.0f);
           y1 = pred_ctr_y - 0.5f * (pred_h - 1.0f);
           x2 = pred_ctr_x + 0.5f * (pred_w - 1.0f);

@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Compile the reference's OWN C++/CUDA operator sources, unmodified and where they lie under
+/root/reference/operator_cxx, into oracle/_ref/libref_cxx.so — test infrastructure only.
+
+`operator_cxx/**` includes MXNet / mshadow / nnvm / dmlc headers that are not in this image (and the
+reference's build is "drop the files into an MXNet checkout and build MXNet": not runnable here).  The
+few types those files touch are supplied by oracle/shim/mxnet_shim.h (force-included; the shim tree also
+answers their relative `#include "../mshadow_op.h"` etc.).  The `.cu` files are compiled as plain C++:
+their device functors run on the host through the shim's serial `Kernel<OP, gpu>::Launch` and
+`atomicAdd`.  proposal_target*.cc call std::random_shuffle -> rand(): the undefined `rand` symbol of
+those two objects is renamed to `ref_shim_rand` (objcopy), which oracle/ref_harness.cc defines, so
+the pin tests control the shuffles.  Nothing from the reference is copied into the repo; objects are
+built in a temp dir and only the .so lands in oracle/_ref/ (git-ignored, travels to the GPU box).
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+REF = "/root/reference/operator_cxx"
+HERE = os.path.dirname(os.path.abspath(__file__))
+SHIM = os.path.join(HERE, "shim")
+OUT = os.path.join(HERE, "_ref", "libref_cxx.so")
+
+# (source under operator_cxx, needs the rand rename)
+SOURCES = [
+    ("contrib/roi_align_v2.cc", False),   # functor roi_align_v2-inl.h:61-153, CPU gather backward, registration
+    ("contrib/roi_align_v2.cu", False),   # ROIAlignBackwardKernelGPU_v2 (:17-85) + driver (:88-143)
+    ("roi_pooling_v1.cc", False),         # ROIPoolForward_v1 / ROIPoolBackwardAcc_v1 (:40-221) + op
+    ("contrib/decodebbox.cc", False),     # BBoxTransformXYWH/XYXY (:34-133) + DecodeBBoxOp::Forward
+    ("proposal_target.cc", True),         # SampleROI, BBoxOverlap, targets (:22-227) + ProposalTargetOp::Forward
+    ("proposal_target_v2.cc", True),
+    ("contrib/generate_anchor.cc", False),  # GenAnchorOp<cpu>::Forward + gen_anchor_utils (generate_anchor-inl.h:139-183)
+]
+# -O2 without -march: like MXNet's x86-64 CPU build there is no FMA instruction to contract into;
+# -ffp-contract=off makes that explicit.
+CXXFLAGS = ["-std=c++14", "-O2", "-fPIC", "-ffp-contract=off", "-w"]
+
+
+def stale() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(HERE, "ref_harness.cc"), os.path.join(SHIM, "mxnet_shim.h"), __file__]
+    deps += [os.path.join(REF, s) for s, _ in SOURCES]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def main() -> int:
+    if not os.path.isdir(REF):
+        print("reference not present; keeping prebuilt oracle/_ref/libref_cxx.so", file=sys.stderr)
+        return 0
+    if not stale():
+        return 0
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    inc = ["-I", SHIM, "-I", os.path.join(SHIM, "l1"), "-I", os.path.join(SHIM, "l1", "l2")]
+    with tempfile.TemporaryDirectory() as tmp:
+        objs = []
+        for src, rename_rand in SOURCES:
+            obj = os.path.join(tmp, src.replace("/", "_").replace(".", "_") + ".o")
+            cmd = ["g++", *CXXFLAGS, *inc, "-include", os.path.join(SHIM, "mxnet_shim.h"), "-x", "c++", "-c",
+                   os.path.join(REF, src), "-o", obj]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                print(r.stderr[-4000:], file=sys.stderr)
+                return 1
+            if rename_rand:
+                subprocess.run(["objcopy", "--redefine-sym", "rand=ref_shim_rand", obj], check=True)
+            objs.append(obj)
+        hobj = os.path.join(tmp, "ref_harness.o")
+        r = subprocess.run(["g++", *CXXFLAGS, "-I", HERE, "-c", os.path.join(HERE, "ref_harness.cc"), "-o", hobj],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            print(r.stderr[-4000:], file=sys.stderr)
+            return 1
+        r = subprocess.run(["g++", "-shared", "-o", OUT, hobj, *objs], capture_output=True, text=True)
+        if r.returncode != 0:
+            print(r.stderr[-4000:], file=sys.stderr)
+            return 1
+    print("built", OUT)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

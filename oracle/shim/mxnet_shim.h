@@ -143,6 +143,7 @@ struct Tensor {
       : dptr_(p), shape_(s), stride_(stride), stream_(st) {}
   index_t size(int i) const { return shape_[i]; }
   size_t MSize() const { return shape_.Size(); }
+  bool CheckContiguous() const { return true; }
   Tensor<Device, dimension - 1, DType> operator[](index_t idx) const {
     Shape<dimension - 1> s;
     size_t inner = 1;
@@ -170,6 +171,7 @@ struct Tensor<Device, 1, DType> {
   Tensor(DType* p, const Shape<1>& s, index_t stride, Stream<Device>* st) : dptr_(p), shape_(s), stride_(stride), stream_(st) {}
   index_t size(int) const { return shape_[0]; }
   size_t MSize() const { return (size_t)shape_[0]; }
+  bool CheckContiguous() const { return true; }
   DType& operator[](index_t i) const { return dptr_[i]; }
   Tensor Slice(index_t begin, index_t end) const { return Tensor(dptr_ + begin, Shape1(end - begin)); }
   Tensor& operator=(const Tensor&) = default;
@@ -687,9 +689,25 @@ inline T atomicAdd(T* addr, T v) { T old = *addr; *addr = old + v; return old; }
 #define MXNET_REGISTER_OP_PROPERTY(name, OperatorPropertyType)                                      \
   static ::mxnet::shim_reg::PropEntry& SHIM_CAT(__shim_prop_##name, __COUNTER__) =                  \
       ::mxnet::shim_reg::PropEntry::Register(#name, []() -> ::mxnet::OperatorProperty* { return new OperatorPropertyType(); })
+// operator_common.h's form for MXNET_USE_CUDA == 0
 #define DO_BIND_DISPATCH(Method, ...)                                             \
-  if (ctx.dev_mask() == ::mshadow::cpu::kDevMask) return Method<::mshadow::cpu>(__VA_ARGS__); \
-  else return Method<::mshadow::gpu>(__VA_ARGS__)
+  if (ctx.dev_mask() == ::mshadow::cpu::kDevMask) {                               \
+    return Method<::mshadow::cpu>(__VA_ARGS__);                                   \
+  } else {                                                                        \
+    LOG(FATAL) << "GPU is not enabled";                                           \
+    return nullptr;                                                               \
+  }
+#define ADD_FILELINE "\n\nFrom:" __FILE__
+// operator_common.h's Assign(out, req, exp) for the plain-value uses in the files we build
+#define Assign(out, req, exp)                              \
+  {                                                        \
+    switch (req) {                                         \
+      case ::mxnet::kNullOp: break;                        \
+      case ::mxnet::kWriteTo:                              \
+      case ::mxnet::kWriteInplace: (out) = (exp); break;   \
+      case ::mxnet::kAddTo: LOG(FATAL) << "shim: kAddTo"; break; \
+    }                                                      \
+  }
 #define SHAPE_ASSIGN_CHECK(shape_array, index, shape)                            \
   {                                                                              \
     if ((shape_array)[index].ndim() == 0) (shape_array)[index] = ::mxnet::TShape(shape); \

@@ -63,8 +63,10 @@ decode_bbox_kernel(const float4* __restrict__ rois, const float4* __restrict__ d
       const float ctr_y = __fadd_rn(b.y, __fmul_rn(0.5f, __fsub_rn(height, 1.0f)));
       const float pcx = __fadd_rn(__fmul_rn(dx, width), ctr_x);
       const float pcy = __fadd_rn(__fmul_rn(dy, height), ctr_y);
-      const float pw = __fmul_rn(expf(dw), width);   // no exp clip in DecodeBBox (Appendix A.12)
-      const float ph = __fmul_rn(expf(dh), height);
+      // decodebbox.cc:62-63: `exp(dw) * width` binds to ::exp(double) on the host - double exp, double product,
+      // one narrowing (pinned by the compiled reference).  No exp clip in DecodeBBox (Appendix A.12).
+      const float pw = (float)__dmul_rn(exp((double)dw), (double)width);
+      const float ph = (float)__dmul_rn(exp((double)dh), (double)height);
       const float hw = __fmul_rn(0.5f, __fsub_rn(pw, 1.0f)), hh = __fmul_rn(0.5f, __fsub_rn(ph, 1.0f));
       x1 = __fsub_rn(pcx, hw);
       y1 = __fsub_rn(pcy, hh);

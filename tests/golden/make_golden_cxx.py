@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Generates tests/golden/reference_cxx_ops.npz by RUNNING THE REFERENCE'S OWN operator_cxx SOURCES, compiled
+unmodified by oracle/build_ref_cxx.py (oracle/_ref/libref_cxx.so).  Only input/output vectors are committed.
+Run:  python tests/golden/make_golden_cxx.py     (needs /root/reference or the prebuilt library)"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import ref_cxx  # noqa: E402
+from simpledet_b200 import synth  # noqa: E402
+import test_oracle_ref_cxx as T  # noqa: E402
+
+
+def main():
+    g = {}
+    rng = np.random.default_rng(0)
+    # RoIAlign_v2: config-1-like (fewer channels) + edge rois, forward and GPU-functor backward
+    data, rois, pooled, scale = synth.config1(0)
+    data = np.ascontiguousarray(data[:, :6])
+    kw = dict(pooled_size=pooled, spatial_scale=scale)
+    out, ax, ay = ref_cxx.forward("_contrib_ROIAlign_v2", kw, [data, rois])
+    og = rng.standard_normal(out.shape).astype(np.float32)
+    gd, _ = ref_cxx.forward("_backward_ROIAlign_v2", kw, [og, rois, ax, ay], out_shapes=[data.shape, rois.shape], dev="gpu")
+    g.update(ra_data=data, ra_rois=rois, ra_out=out, ra_ax=ax, ra_ay=ay, ra_ograd=og, ra_gdata=gd)
+    edata = rng.standard_normal((1, 3, 25, 42)).astype(np.float32)
+    for p in (7, 14):
+        o, x, y = ref_cxx.forward("_contrib_ROIAlign_v2", dict(pooled_size=(p, p), spatial_scale=1 / 32), [edata, T.EDGE_ROIS])
+        g.update({f"ra_edge{p}_out": o, f"ra_edge{p}_ax": x, f"ra_edge{p}_ay": y})
+    g.update(ra_edge_data=edata, ra_edge_rois=T.EDGE_ROIS)
+    # ROIPooling_v1
+    pdata = rng.standard_normal((2, 3, 30, 40)).astype(np.float32)
+    r = synth.random_rois(rng, 1, 40, 480, 640)[0]
+    prois = np.concatenate([rng.integers(0, 2, (40, 1)).astype(np.float32), r], 1)
+    po, pi = ref_cxx.forward("ROIPooling_v1", dict(pooled_size=(7, 7), spatial_scale=1 / 16), [pdata, prois])
+    g.update(rp_data=pdata, rp_rois=prois, rp_out=po, rp_idx=pi)
+    # DecodeBBox
+    drois = synth.random_rois(rng, 2, 100)
+    ddel = (rng.standard_normal((2, 100, 12)) * np.array([1, 1, 2.5, 2.5] * 3)).astype(np.float32)
+    dinfo = np.array([[800, 1333, 1.0], [600, 901, 1.5]], np.float32)
+    for ag in (True, False):
+        for ty in ("xywh", "xyxy"):
+            (o,) = ref_cxx.forward("_contrib_DecodeBBox", dict(class_agnostic=ag, bbox_decode_type=ty), [drois, ddel, dinfo])
+            g[f"db_{int(ag)}_{ty}"] = o
+    g.update(db_rois=drois, db_deltas=ddel, db_info=dinfo)
+    # GenAnchor
+    (a,) = ref_cxx.forward("_contrib_GenAnchor", dict(feature_stride=8, scales=(4.0, 5.04, 6.35), ratios=(0.5, 1.0, 2.0)),
+                           [np.zeros((1, 18, 10, 17), np.float32)])
+    g["ga_out"] = a
+    # ProposalTarget with rand() == 0 (every shuffle rotates right by one); the matching priorities are rebuilt by the test
+    trois, tgt = T._pt_inputs(np.random.default_rng(10), 2, 120, 10, 4, 40)
+    ref_cxx.set_rand_const(0)
+    outs = ref_cxx.forward("ProposalTarget", dict(T.BASE, batch_images=2, image_rois=32), [trois, tgt])
+    g.update(pt_rois=trois, pt_gt=tgt, **{f"pt_out{i}": o for i, o in enumerate(outs)})
+    path = os.path.join(HERE, "reference_cxx_ops.npz")
+    np.savez_compressed(path, **g)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

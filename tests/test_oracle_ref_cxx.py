@@ -1,0 +1,276 @@
+"""Pins the oracle (oracle/*.c restatements) to the REFERENCE ITSELF: the reference's own operator_cxx sources,
+compiled unmodified from /root/reference against oracle/shim (oracle/build_ref_cxx.py ->
+oracle/_ref/libref_cxx.so), are run on the same inputs and every output is compared BIT FOR BIT.
+
+CPU-only.  Needs /root/reference (to build) or the prebuilt oracle/_ref/libref_cxx.so; the committed goldens
+under tests/golden/reference_cxx_ops.npz (made by tests/golden/make_golden_cxx.py from the same library) keep
+the pin alive where neither exists."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import ref_cxx
+from simpledet_b200 import synth
+
+pytestmark = pytest.mark.skipif(not ref_cxx.available(), reason="compiled reference (oracle/_ref/libref_cxx.so) unavailable")
+
+EDGE_ROIS = np.array([[
+    [0, 0, 0, 0], [-500, -400, -100, -50], [5000, 4000, 6000, 5000], [0, 0, 1343, 799],
+    [96, 96, 96 + 7 * 48, 96 + 7 * 48], [100, 100, 100.2, 100.2], [100, 100, 101.5, 250],
+    [64, 64, 64.96, 64.96], [300, 200, 100, 50], [1200, 700, 1400, 900], [-30, -30, 60, 60],
+]], np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ RoIAlign_v2
+def _ra(data, rois, pooled, scale):
+    kw = dict(pooled_size=pooled, spatial_scale=scale)
+    shapes, nvis = ref_cxx.infer_shape("_contrib_ROIAlign_v2", kw, [data.shape, rois.shape])
+    assert nvis == 1 and len(shapes) == 3  # roi_align_v2.cc:175-178: only `output` is visible
+    B, N = rois.shape[:2]
+    assert shapes[0] == (B, N, data.shape[1], pooled[0], pooled[1])
+    out, ax, ay = ref_cxx.forward("_contrib_ROIAlign_v2", kw, [data, rois])
+    ro, rx, ry = oracle.roi_align_v2_forward(data, rois, pooled, scale)
+    assert np.array_equal(out, ro) and np.array_equal(ax, rx) and np.array_equal(ay, ry)
+    return out, ax, ay
+
+
+def test_roi_align_forward_config1_and_shapes():
+    data, rois, pooled, scale = synth.config1(0)
+    _ra(data, rois, pooled, scale)
+    _ra(data[:, :8], rois, (14, 14), scale)
+    _ra(data[:, :5], rois[:, :40], (3, 5), scale)
+
+
+def test_roi_align_forward_edge_cases():
+    """zero roi, rois outside, whole map, integer-aligned samples, sub-0.01 strides
+    (3 samples per axis), inverted roi, border straddling; ties (first max wins)."""
+    rng = np.random.default_rng(7)
+    data = rng.standard_normal((1, 6, 25, 42)).astype(np.float32)
+    _ra(data, EDGE_ROIS, (7, 7), 1 / 32)
+    _ra(data, EDGE_ROIS, (14, 14), 1 / 32)
+    const = np.ones((1, 4, 50, 50), np.float32)
+    const[:, 1] = 0.0
+    const[:, 2, ::2] = 2.0
+    const[:, 3] = -1.0
+    _ra(const, synth.random_rois(np.random.default_rng(2), 1, 64, 800, 800), (7, 7), 1 / 16)
+
+
+def test_roi_align_two_images():
+    rng = np.random.default_rng(3)
+    data = rng.standard_normal((2, 4, 30, 40)).astype(np.float32)
+    rois = synth.random_rois(rng, 2, 20, 480, 640)
+    _ra(data, rois, (7, 7), 1 / 16)   # image index = n / num_rois_per_batch (roi_align_v2-inl.h:77)
+
+
+def test_roi_align_backward_gpu_functor():
+    """ROIAlignBackwardKernelGPU_v2 (roi_align_v2.cu:17-85) through the driver (:88-143), serial atomicAdd order;
+    kWriteTo zero-fills, kAddTo accumulates, grad_rois is zero."""
+    data, rois, pooled, scale = synth.config1(1)
+    data = data[:, :16]
+    kw = dict(pooled_size=pooled, spatial_scale=scale)
+    out, ax, ay = ref_cxx.forward("_contrib_ROIAlign_v2", kw, [data, rois])
+    g = np.random.default_rng(1).standard_normal(out.shape).astype(np.float32)
+    gd, gr = ref_cxx.forward("_backward_ROIAlign_v2", kw, [g, rois, ax, ay], out_shapes=[data.shape, rois.shape], dev="gpu")
+    assert np.array_equal(gd, oracle.roi_align_v2_backward(g, ax, ay, data.shape))
+    assert not gr.any()
+    acc = np.full(data.shape, 0.5, np.float32)
+    acc_ref = acc.copy()
+    ref_cxx.forward("_backward_ROIAlign_v2", kw, [g, rois, ax, ay], outputs=[acc_ref, np.zeros_like(rois)], dev="gpu",
+                    reqs=[ref_cxx.K_ADD, ref_cxx.K_WRITE])
+    assert np.array_equal(acc_ref, oracle.roi_align_v2_backward(g, ax, ay, data.shape, accumulate_into=acc))
+
+
+def test_roi_align_param_checks():
+    """ROIAlignParam_v2 (roi_align_v2-inl.h:27-38): spatial_scale in [0,1], pooled_size 2-D and non-zero."""
+    d, r = (1, 4, 10, 10), (1, 3, 4)
+    for kw in (dict(pooled_size=(7, 7), spatial_scale=1.5), dict(pooled_size=(7, 7), spatial_scale=-0.1),
+               dict(pooled_size=(7, 0), spatial_scale=0.5), dict(pooled_size=(7,), spatial_scale=0.5),
+               dict(pooled_size=(7, 7))):
+        with pytest.raises(RuntimeError):
+            ref_cxx.infer_shape("_contrib_ROIAlign_v2", kw, [d, r])
+    with pytest.raises(RuntimeError):  # bbox must be (B, N, 4)
+        ref_cxx.infer_shape("_contrib_ROIAlign_v2", dict(pooled_size=(7, 7), spatial_scale=0.5), [d, (1, 3, 5)])
+
+
+# ------------------------------------------------------------------------------------------------ ROIPooling_v1
+def test_roi_pooling_v1():
+    rng = np.random.default_rng(4)
+    data = rng.standard_normal((2, 5, 30, 40)).astype(np.float32)
+    r = synth.random_rois(rng, 1, 50, 480, 640)[0]
+    rois = np.concatenate([rng.integers(0, 2, (50, 1)).astype(np.float32), r], 1)
+    rois[0, 1:] = 0
+    rois[1, 1:] = [700, 500, 800, 600]  # outside: empty bins
+    for pooled, scale in (((7, 7), 1 / 16), ((2, 3), 1 / 16), ((6, 6), 0.7 / 16)):
+        kw = dict(pooled_size=pooled, spatial_scale=scale)
+        out, idx = ref_cxx.forward("ROIPooling_v1", kw, [data, rois])
+        ro, ri = oracle.roi_pool_v1_forward(data, rois, pooled, scale)
+        assert np.array_equal(out, ro) and np.array_equal(idx, ri)
+    # the docstring vector of the reference (roi_pooling_v1.cc:265-285)
+    x = np.arange(48, dtype=np.float32).reshape(1, 1, 8, 6)
+    y = np.array([[0, 0, 0, 4, 4]], np.float32)
+    out, _ = ref_cxx.forward("ROIPooling_v1", dict(pooled_size=(2, 2), spatial_scale=1.0), [x, y])
+    assert out.ravel().tolist() == [14, 16, 26, 28]
+    out, _ = ref_cxx.forward("ROIPooling_v1", dict(pooled_size=(2, 2), spatial_scale=0.7), [x, y])
+    assert out.ravel().tolist() == [7, 9, 19, 21]
+
+
+# ------------------------------------------------------------------------------------------------ DecodeBBox
+@pytest.mark.parametrize("agnostic", [True, False])
+@pytest.mark.parametrize("dtype", ["xywh", "xyxy"])
+def test_decode_bbox(agnostic, dtype):
+    rng = np.random.default_rng(5)
+    B, N, K = 2, 300, 5
+    rois = synth.random_rois(rng, B, N)
+    deltas = (rng.standard_normal((B, N, 4 * K)) * np.array([1, 1, 2.5, 2.5] * K)).astype(np.float32)
+    im_info = np.array([[800, 1333, 1.0], [600, 901, 1.5]], np.float32)
+    kw = dict(class_agnostic=agnostic, bbox_decode_type=dtype, bbox_mean=(0.0, 0.1, 0.0, -0.1), bbox_std=(0.1, 0.1, 0.2, 0.2))
+    (out,) = ref_cxx.forward("_contrib_DecodeBBox", kw, [rois, deltas, im_info])
+    ref = oracle.decode_bbox(rois, deltas, im_info, kw["bbox_mean"], kw["bbox_std"], agnostic, dtype)
+    assert np.array_equal(out, ref)
+
+
+def test_decode_bbox_defaults():
+    """DecodeBBoxParam defaults (decodebbox-inl.h:55-67): class_agnostic=True, xywh, mean 0, std (.1,.1,.2,.2)."""
+    rng = np.random.default_rng(6)
+    rois = synth.random_rois(rng, 1, 50)
+    deltas = rng.standard_normal((1, 50, 8)).astype(np.float32)
+    im_info = np.array([[800, 1333, 1.0]], np.float32)
+    shapes, _ = ref_cxx.infer_shape("_contrib_DecodeBBox", {}, [rois.shape, deltas.shape, im_info.shape])
+    assert shapes == [(1, 50, 4)]
+    (out,) = ref_cxx.forward("_contrib_DecodeBBox", {}, [rois, deltas, im_info])
+    assert np.array_equal(out, oracle.decode_bbox(rois, deltas, im_info))
+
+
+# ------------------------------------------------------------------------------------------------ GenAnchor
+@pytest.mark.parametrize("stride,scales,ratios,hw", [(16, (8.0,), (0.5, 1.0, 2.0), (13, 21)), (8, (4.0, 5.04, 6.35), (0.5, 1.0, 2.0), (10, 17)),
+                                                     (32, (2.0, 4.0), (0.33, 1.7), (7, 9))])
+def test_gen_anchor(stride, scales, ratios, hw):
+    cls_prob = np.zeros((1, 2 * len(scales) * len(ratios), hw[0], hw[1]), np.float32)
+    (out,) = ref_cxx.forward("_contrib_GenAnchor", dict(feature_stride=stride, scales=scales, ratios=ratios), [cls_prob])
+    ref = oracle.gen_anchor(hw[0], hw[1], stride, scales, ratios)
+    assert np.array_equal(out.reshape(-1, 4), ref)
+
+
+# ------------------------------------------------------------------------------------------------ ProposalTarget
+def _rot(lst, k):
+    lst = list(lst)
+    for _ in range(k):
+        lst = [lst[-1]] + lst[:-1] if lst else lst
+    return lst
+
+
+def _pt_inputs(rng, B, R, G, n_gt, n_fg_like):
+    """rois = jittered copies of the gt boxes (many foreground) + random boxes, some zero-padded rows;
+    gt (B,G,5) with class -1 padding."""
+    gt = np.full((B, G, 5), -1, np.float32)
+    rois = np.zeros((B, R, 4), np.float32)
+    for b in range(B):
+        g = synth.random_rois(rng, 1, n_gt, min_side=40, max_side=300)[0]
+        gt[b, :n_gt, :4] = g
+        gt[b, :n_gt, 4] = rng.integers(1, 81, n_gt)
+        jit = g[rng.integers(0, n_gt, n_fg_like)] + rng.uniform(-12, 12, (n_fg_like, 4)).astype(np.float32)
+        rnd = synth.random_rois(rng, 1, R - n_fg_like - 3)[0]
+        rois[b, :n_fg_like] = jit
+        rois[b, n_fg_like:R - 3] = rnd
+    return rois, gt
+
+
+def oracle_under_constant_rand(rois, gt, kw, rand_const, v2=False, valid_ranges=None):
+    """The oracle's ProposalTarget with the priorities that reproduce what libstdc++'s std::random_shuffle does
+    when every rand() returns `rand_const` (0: rotate right by one; 27719: identity for lists <= 12)."""
+    B, R, _ = rois.shape
+    G = gt.shape[1]
+    IR = kw["image_rois"]
+    # the oracle's candidate lists, to express the reference's shuffles as priorities: run the oracle with
+    # image_rois large enough to keep every candidate in index order (priority = index), read max-overlaps back
+    T = R + G
+    okw = dict(num_classes=kw["num_classes"], fg_fraction=kw.get("fg_fraction", 0.25), fg_thresh=kw["fg_thresh"],
+               bg_thresh_hi=kw["bg_thresh_hi"], bg_thresh_lo=kw["bg_thresh_lo"],
+               proposal_without_gt=kw["proposal_without_gt"], class_agnostic=kw.get("class_agnostic", False),
+               bbox_mean=kw.get("bbox_mean", (0, 0, 0, 0)), bbox_std=kw.get("bbox_std", (0.1, 0.1, 0.2, 0.2)),
+               bbox_weight=kw.get("bbox_weight", (1, 1, 1, 1)))
+    if v2:
+        okw.update(valid_ranges=valid_ranges, filter_scales=kw.get("filter_scales", False))
+    ident = np.tile(np.arange(T, dtype=np.uint32), (B, 3, 1))
+    probe = oracle.proposal_target(rois, gt, ident, image_rois=T, **dict(okw, fg_fraction=1.0, bg_thresh_lo=-1.0,
+                                                                           bg_thresh_hi=kw["fg_thresh"]))
+    # probe keeps [all fg in index order, then all non-fg in index order]: recover per-candidate max overlap
+    fgq = int(IR * kw.get("fg_fraction", 0.25))
+    rounds = 8
+    pr = np.zeros((B, 2 + rounds, T), np.uint32)
+    for b in range(B):
+        kept, iou = probe[5][b], probe[4][b]
+        n = int(kept.max()) + 1   # rows beyond the n distinct candidates are the probe's own negative padding
+        ov = np.zeros(n, np.float32)
+        ov[kept[:n]] = iou[:n]
+        fg = [i for i in range(n) if ov[i] >= kw["fg_thresh"]]
+        neg = [i for i in range(n) if not ov[i] >= kw["fg_thresh"]]
+        bg = [i for i in range(n) if kw["bg_thresh_lo"] <= ov[i] < kw["bg_thresh_hi"]]
+        if rand_const == 0:      # libstdc++ random_shuffle with rand() == 0: rotate right by one
+            sh = lambda l, k: _rot(l, k)
+        else:                     # rand() % (i+1) == i for every i <= 11: identity
+            assert max(len(fg), len(bg), len(neg)) <= 12
+            sh = lambda l, k: list(l)
+        for d, lst in ((0, sh(fg, 1)), (1, sh(bg, 1))):
+            pr[b, d] = T  # anything not in the list sorts last
+            for pos, i in enumerate(lst):
+                pr[b, d, i] = pos
+        for r in range(rounds):
+            pr[b, 2 + r] = T
+            for pos, i in enumerate(sh(neg, r + 1)):
+                pr[b, 2 + r, i] = pos
+    return oracle.proposal_target(rois, gt, pr, image_rois=IR, **okw)
+
+
+def _run_pair(rois, gt, kw, rand_const, v2=False, valid_ranges=None):
+    op = "ProposalTarget_v2" if v2 else "ProposalTarget"
+    ref_cxx.set_rand_const(rand_const)
+    ins = [rois, gt] + ([valid_ranges] if v2 else [])
+    r_rois, r_lab, r_tgt, r_wgt, r_iou = ref_cxx.forward(op, dict(kw, batch_images=rois.shape[0]), ins)
+    o = oracle_under_constant_rand(rois, gt, kw, rand_const, v2, valid_ranges)
+    assert np.array_equal(r_rois, o[0]), "rois"
+    assert np.array_equal(r_lab, o[1]), "labels"
+    assert np.array_equal(r_tgt, o[2]), "bbox_target"
+    assert np.array_equal(r_wgt, o[3]), "bbox_weight"
+    assert np.array_equal(r_iou, o[4]), "match_gt_iou"
+    return o
+
+
+BASE = dict(num_classes=81, image_rois=64, fg_thresh=0.5, bg_thresh_hi=0.5, bg_thresh_lo=0.0, proposal_without_gt=False)
+
+
+def test_proposal_target_truncating_shuffles():
+    """Plenty of fg and bg: both shuffles truncate (proposal_target.cc:81-85, 100-104); gt appended after the
+    rois (-inl.h:177-185); zero-padded rois dropped by y2 > 0 (:174); padding gt by cls != -1 (:158)."""
+    rng = np.random.default_rng(10)
+    rois, gt = _pt_inputs(rng, 2, 300, 20, 6, 90)
+    o = _run_pair(rois, gt, BASE, 0)
+    assert (o[1][:, :16] > 0).all() and (o[1][:, 16:] == 0).all()   # labels only for the first fg_n rows
+    _run_pair(rois, gt, dict(BASE, class_agnostic=True, num_classes=2), 0)
+    _run_pair(rois, gt, dict(BASE, proposal_without_gt=True), 0)
+    _run_pair(rois, gt, dict(BASE, bg_thresh_lo=0.1, fg_fraction=0.5, bbox_mean=(0.0, 0.0, 0.1, 0.1),
+                             bbox_std=(0.2, 0.2, 0.3, 0.3), bbox_weight=(1.0, 2.0, 3.0, 4.0)), 0)
+
+
+def test_proposal_target_negative_padding_rounds():
+    """Few candidates: kept < image_rois, padded by re-shuffled negatives over several rounds (:116-122)."""
+    rng = np.random.default_rng(11)
+    rois, gt = _pt_inputs(rng, 2, 16, 6, 2, 5)
+    _run_pair(rois, gt, dict(BASE, image_rois=64), 0)       # rotations
+    _run_pair(rois, gt, dict(BASE, image_rois=48), 27719)   # identity shuffles (lists <= 12)
+
+
+def test_proposal_target_v2():
+    """ProposalTarget_v2: valid_ranges + filter_scales (proposal_target_v2-inl.h:186-203)."""
+    rng = np.random.default_rng(12)
+    rois, gt = _pt_inputs(rng, 2, 200, 12, 6, 60)
+    vr = np.array([[0, 120], [100, 1000]], np.float32)
+    _run_pair(rois, gt, dict(BASE, filter_scales=True), 0, v2=True, valid_ranges=vr)
+    _run_pair(rois, gt, dict(BASE, filter_scales=False), 0, v2=True, valid_ranges=vr)
+
+
+def test_proposal_target_shapes_and_visible_outputs():
+    shapes, nvis = ref_cxx.infer_shape("ProposalTarget", dict(BASE, batch_images=2), [(2, 300, 4), (2, 20, 5)])
+    assert shapes == [(2, 64, 4), (2, 64), (2, 64, 324), (2, 64, 324), (2, 64)] and nvis == 4
+    _, nvis = ref_cxx.infer_shape("ProposalTarget", dict(BASE, batch_images=2, output_iou=True), [(2, 300, 4), (2, 20, 5)])
+    assert nvis == 5
