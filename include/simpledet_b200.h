@@ -38,6 +38,9 @@ typedef enum sdet_status {
 
 /* ABI version of this header; bumped on any signature change. */
 int sdet_abi_version(void);
+/* sha256 prefix of the sources/headers/flags the library was built from; simpledet_b200.build.source_digest()
+ * recomputes it from the tree, so a stale prebuilt binary is detected (__graft_entry__.smoke() checks it). */
+const char* sdet_build_digest(void);
 /* Thread-local message of the last failing call on this thread ("" if none). */
 const char* sdet_last_error(void);
 /* Number of kernels this library has launched in this process (all threads); used by bench.py's
@@ -100,6 +103,14 @@ int sdet_fpn_roi_align_v2_forward_ex(const float* const* feats, const int* H, co
                                      int pooled_w, int roi_canonical_scale, int roi_canonical_level,
                                      void* workspace, size_t workspace_bytes, void* stream, int path,
                                      int* path_used);
+
+/* assign_layer_fpn as a stand-alone operator (CustomOp 'assign_layer_fpn', models/FPN/assign_layer_fpn.py:17-40;
+ * mxnext.tvm.fpn_roi_assign): rois (total_rois,4) device; strides HOST array; out_rois HOST array of num_levels
+ * device pointers (total_rois,4) - the roi where it is assigned to that level, zeros elsewhere (may be NULL, or
+ * hold NULL entries); levels_out (total_rois int32 device, may be NULL) index into strides, -1 if none. */
+int sdet_fpn_assign(const float* rois, int total_rois, const int* strides, int num_levels,
+                    int roi_canonical_scale, int roi_canonical_level, float* const* out_rois,
+                    int32_t* levels_out, void* stream);
 
 /* Backward of the fused op: scatters into the grad tensor of each roi's assigned level.
  *   grad_feats[l] device (B,C,H[l],W[l]); levels (B*N int32 device) as written by the forward. */
@@ -232,6 +243,15 @@ int sdet_contrib_nms(const float* proposals, float* out, float* out_score, int B
 size_t sdet_nms_workspace(int problems, int n);
 int sdet_nms_sorted(const float* dets, const int* counts, int problems, int n, float thresh, int ge,
                     int* keep, int* nkeep, void* workspace, size_t workspace_bytes, void* stream);
+
+/* `_nms`: the reference's own C ABI (operator_py/cython/gpu_nms.hpp:1-2; implementation nms_kernel.cu:91-144,
+ * bound by gpu_nms.pyx:13-14), kept under the exact symbol and signature so gpu_nms.pyx links against this
+ * library unchanged.  HOST pointers in, blocking, allocates and frees its device buffers per call like the
+ * reference; boxes_host (boxes_num, boxes_dim >= 4) must already be sorted by descending score (gpu_nms.pyx:25-29);
+ * suppresses IoU > nms_overlap_thresh (nms_kernel.cu:71); keep_out (boxes_num ints) receives the kept positions,
+ * *num_out their count.  Errors are printed to stderr (the reference's CUDA_CHECK only prints) and *num_out = 0. */
+void _nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim,
+          float nms_overlap_thresh, int device_id);
 
 /* get_top_proposal  (CustomOp models/FPN/get_top_proposal.py:15-40; mxnext.tvm.get_top_proposal
  * at models/FPN/builder.py:319-321): per image keep the top_n rows by score, descending, ties by
@@ -385,6 +405,11 @@ int sdet_modulated_deformable_col2im(const float* grad_col, const float* data, c
  * class index] in ascending score order, unused rows zero with class -1; out_count (B). */
 int sdet_final_detections(const float* dets, const int* keep, const int* nkeep, int B, int num_classes,
                           int n_pad, int max_det, float* out, int* out_count, void* stream);
+/* Same selection with the row format of CustomOp 'BboxPostProcessing' (models/maskrcnn/bbox_post_processing.py:
+ * 6-32): xyxy != 0 keeps [x1, y1, x2, y2, score, class]; descending != 0 lists the highest score first. */
+int sdet_final_detections_ex(const float* dets, const int* keep, const int* nkeep, int B, int num_classes,
+                             int n_pad, int max_det, float* out, int* out_count, int xyxy, int descending,
+                             void* stream);
 
 /* operator_py/nms.py:77-107 set_nms over boxes already sorted by descending score: like sdet_nms_sorted
  * with `>` (the reference keeps ovr <= thresh), but boxes whose `sets` value (P,n; column 5 of the

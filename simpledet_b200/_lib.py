@@ -26,6 +26,7 @@ _P = c_void_p
 _SIGNATURES = {
     "sdet_abi_version": [],
     "sdet_last_error": [],
+    "sdet_build_digest": [],
     "sdet_launch_count": [],
     "sdet_roi_align_v2_workspace": [c_int, c_int],
     "sdet_roi_align_v2_forward": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -40,6 +41,7 @@ _SIGNATURES = {
     "sdet_fpn_roi_align_v2_forward_ex": [POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                          c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_int, _P, c_size_t, _P, c_int, POINTER(c_int)],
+    "sdet_fpn_assign": [_P, c_int, POINTER(c_int), c_int, c_int, c_int, POINTER(_P), _P, _P],
     "sdet_fpn_roi_align_v2_backward": [_P, _P, _P, _P, POINTER(_P), POINTER(c_int), POINTER(c_int),
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "sdet_roi_pooling_v1_forward": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -70,6 +72,7 @@ _SIGNATURES = {
     "sdet_modulated_deformable_im2col": [_P, _P, _P, _P] + [c_int] * 13 + [_P],
     "sdet_modulated_deformable_col2im": [_P, _P, _P, _P, _P, _P, _P] + [c_int] * 13 + [_P],
     "sdet_final_detections": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P],
+    "sdet_final_detections_ex": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P],
     "sdet_set_nms_sorted": [_P, _P, _P, c_int, c_int, c_float, _P, _P, _P, c_size_t, _P],
     "sdet_weighted_nms_workspace": [c_int, c_int],
     "sdet_weighted_nms_sorted": [_P, _P, c_int, c_int, c_float, c_float, _P, _P, _P, c_size_t, _P],
@@ -105,9 +108,10 @@ _SIGNATURES = {
     "sdet_deformable_im2col": [_P, _P, _P] + [c_int] * 13 + [_P],
     "sdet_deformable_col2im": [_P, _P, _P, _P, _P] + [c_int] * 13 + [_P],
     "sdet_nms_workspace": [c_int, c_int],
+    "_nms": [_P, POINTER(c_int), _P, c_int, c_int, c_float, c_int],
     "sdet_nms_sorted": [_P, _P, c_int, c_int, c_float, c_int, _P, _P, _P, c_size_t, _P],
 }
-_RESTYPES = {"sdet_last_error": c_char_p, "sdet_launch_count": c_uint64,
+_RESTYPES = {"_nms": None, "sdet_last_error": c_char_p, "sdet_build_digest": c_char_p, "sdet_launch_count": c_uint64,
              "sdet_proposal_v3_workspace": c_size_t, "sdet_proposal_legacy_workspace": c_size_t,
              "sdet_gen_proposal_workspace": c_size_t, "sdet_anchor_target_workspace": c_size_t, "sdet_weighted_nms_workspace": c_size_t, "sdet_gen_proposal_retina_workspace": c_size_t, "sdet_proposal_v3_fpn_workspace": c_size_t, "sdet_contrib_nms_workspace": c_size_t,
              "sdet_nms_workspace": c_size_t, "sdet_roi_align_v2_workspace": c_size_t, "sdet_multiclass_nms_workspace": c_size_t}
@@ -135,6 +139,10 @@ def lib() -> ctypes.CDLL:
 def check(status: int) -> None:
     if status != 0:
         raise SdetError(status, lib().sdet_last_error().decode())
+
+
+def build_digest() -> str:
+    return lib().sdet_build_digest().decode()
 
 
 def launch_count() -> int:

@@ -365,11 +365,8 @@ extern "C" int sdet_anchor_target(const float* im_info, const float* gt_bbox, in
   anchor_label_kernel<<<grid, 256, 0, st>>>(p);
   SDET_LAUNCH_CHECK("anchor_label_kernel");
   const size_t smem = (size_t)p.k_pow2 * 8;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024)  // per device and cheap: set on every launch, no process-wide cache
     SDET_CUDA(cudaFuncSetAttribute(anchor_quota_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   anchor_quota_kernel<<<(unsigned)B, kTopkThreads, smem, st>>>(p);
   SDET_LAUNCH_CHECK("anchor_quota_kernel");
   anchor_write_kernel<<<grid, 256, 0, st>>>(p);

@@ -654,23 +654,21 @@ int run_mask_and_scan(const float* dets, const int* counts, int P, int n, float 
   const size_t smem = scan_smem_bytes(n, nbuf);
   if (n > 12288 || smem > 200 * 1024)
     return sdet::fail(SDET_ERR_UNSUPPORTED, "NMS over %d boxes needs %zu B shared memory", n, smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024)  // per device and cheap: set on every launch, no process-wide cache
     SDET_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   nms_scan_kernel<<<(unsigned)P, 256, smem, st>>>(dets, counts, n, mask, so, nbuf);
   SDET_LAUNCH_CHECK("nms_scan_kernel");
   return SDET_OK;
 }
 
+// The opt-in for more than 48 KB of dynamic shared memory is per device and per kernel: it is set on every launch
+// that needs it (cheap) instead of being cached in process-wide statics, which broke when a second entry point
+// asked for less, on a second device, or from a second thread.
 template <typename K>
-int ensure_smem(K kernel, size_t bytes, size_t* configured) {
+int ensure_smem(K kernel, size_t bytes) {
   if (bytes > 200 * 1024) return sdet::fail(SDET_ERR_UNSUPPORTED, "top-k needs %zu B shared memory", bytes);
-  if (bytes > 48 * 1024 && bytes > *configured) {
+  if (bytes > 48 * 1024)
     SDET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    *configured = bytes;
-  }
   return SDET_OK;
 }
 
@@ -924,16 +922,15 @@ extern "C" int sdet_proposal_v3_fpn(const float* const* cls_prob, const float* c
   p.dets = dets;
   p.counts = counts;
   p.cand = reinterpret_cast<unsigned long long*>(wsb + proposal_ws_bytes(P, pre_max));
-  static size_t configured = 0, configured_chunk = 0;
   // key cache: kChunkElems slots if the selection buffer leaves room for them (176 KB budget)
   p.cache_keys = ((size_t)p.k_pow2 * 8 + (size_t)kChunkElems * 8 <= 176 * 1024) ? kChunkElems : 0;
   const size_t smem = (size_t)p.k_pow2 * 8 + (size_t)p.cache_keys * 8;
   if (chunk_ctas > 0) {
-    if (int rc = ensure_smem(proposal_chunk_topk_kernel, smem, &configured_chunk)) return rc;
+    if (int rc = ensure_smem(proposal_chunk_topk_kernel, smem)) return rc;
     proposal_chunk_topk_kernel<<<(unsigned)chunk_ctas, kTopkThreads, smem, st>>>(p);
     SDET_LAUNCH_CHECK("proposal_chunk_topk_kernel");
   }
-  if (int rc = ensure_smem(proposal_topk_kernel, smem, &configured)) return rc;
+  if (int rc = ensure_smem(proposal_topk_kernel, smem)) return rc;
   proposal_topk_kernel<<<(unsigned)P, kTopkThreads, smem, st>>>(p);
   SDET_LAUNCH_CHECK("proposal_topk_kernel");
   ScanOut so{};
@@ -985,10 +982,9 @@ extern "C" int sdet_contrib_nms(const float* proposals, float* out, float* out_s
   float* dets = static_cast<float*>(workspace);
   auto* mask = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) +
                                                      align_up((size_t)B * pre * 5 * 4, 256));
-  static size_t configured = 0;
   const int k_pow2 = sdet::next_pow2(pre);
   const size_t smem = (size_t)k_pow2 * 8;
-  if (int rc = ensure_smem(rows_topk_kernel, smem, &configured)) return rc;
+  if (int rc = ensure_smem(rows_topk_kernel, smem)) return rc;
   rows_topk_kernel<<<(unsigned)B, kTopkThreads, smem, st>>>(proposals, count, pre, k_pow2, already_sorted, dets);
   SDET_LAUNCH_CHECK("rows_topk_kernel");
   ScanOut so{};
@@ -1042,10 +1038,9 @@ extern "C" int sdet_proposal_legacy(const float* cls_prob, const float* bbox_pre
   dim3 grid((unsigned)std::min((count + 255) / 256, 148 * 8), (unsigned)B);
   proposal_legacy_decode_kernel<<<grid, 256, 0, st>>>(p);
   SDET_LAUNCH_CHECK("proposal_legacy_decode_kernel");
-  static size_t configured = 0;
   const int k_pow2 = sdet::next_pow2(pre);
   const size_t smem = (size_t)k_pow2 * 8;
-  if (int rc = ensure_smem(rows_topk_kernel, smem, &configured)) return rc;
+  if (int rc = ensure_smem(rows_topk_kernel, smem)) return rc;
   rows_topk_kernel<<<(unsigned)B, kTopkThreads, smem, st>>>(props, count, pre, k_pow2, 0, dets);
   SDET_LAUNCH_CHECK("rows_topk_kernel");
   ScanOut so{};
@@ -1087,10 +1082,9 @@ extern "C" int sdet_gen_proposal(const float* cls_prob, const float* bbox_pred, 
   dim3 grid((unsigned)std::min((count + 255) / 256, 148 * 8), (unsigned)B);
   proposal_legacy_decode_kernel<<<grid, 256, 0, st>>>(p);
   SDET_LAUNCH_CHECK("proposal_legacy_decode_kernel");
-  static size_t configured = 0;
   const int k_pow2 = sdet::next_pow2(pre);
   const size_t smem = (size_t)k_pow2 * 8;
-  if (int rc = ensure_smem(rows_topk_kernel, smem, &configured)) return rc;
+  if (int rc = ensure_smem(rows_topk_kernel, smem)) return rc;
   rows_topk_kernel<<<(unsigned)B, kTopkThreads, smem, st>>>(props, count, pre, k_pow2, 0, dets);
   SDET_LAUNCH_CHECK("rows_topk_kernel");
   dim3 g2((unsigned)((rpn_pre_nms_top_n * 5 + 255) / 256), (unsigned)B);

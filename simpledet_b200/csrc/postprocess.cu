@@ -85,7 +85,7 @@ class_sort_kernel(const float* __restrict__ cls_score, const float* __restrict__
 __global__ void __launch_bounds__(kTopkThreads)
 final_dets_kernel(const float* __restrict__ dets, const int* __restrict__ keep, const int* __restrict__ nkeep,
                   const int ncls, const int n_pad, const int max_det, const int k_pow2,
-                  float* __restrict__ out, int* __restrict__ out_count) {
+                  float* __restrict__ out, int* __restrict__ out_count, const int xyxy, const int descending) {
   extern __shared__ unsigned long long s_sel[];
   __shared__ uint32_t s_hist[sdet::kRadixBins];
   __shared__ int s_base[1025];  // list position of every class's first kept detection
@@ -119,7 +119,7 @@ final_dets_kernel(const float* __restrict__ dets, const int* __restrict__ keep, 
       o[5] = -1.f;
       continue;
     }
-    const uint64_t key = s_sel[k - 1 - r];  // ascending score like the reference's slice
+    const uint64_t key = s_sel[descending ? r : k - 1 - r];  // ascending score like the reference's slice
     const int pos = (int)(uint32_t)key - 1;
     int c = 0;
     for (int lo = 0, hi = ncls; lo < hi;) {  // largest c with s_base[c] <= pos
@@ -131,8 +131,8 @@ final_dets_kernel(const float* __restrict__ dets, const int* __restrict__ keep, 
     const float* d = dets + (p * n_pad + __ldg(keep + p * n_pad + (pos - s_base[c]))) * 5;
     // COCO box: x, y, w = x2 - x1 + 1, h = y2 - y1 + 1 (detection_test.py:277-280)
     o[0] = d[0]; o[1] = d[1];
-    o[2] = __fadd_rn(__fsub_rn(d[2], d[0]), 1.f);
-    o[3] = __fadd_rn(__fsub_rn(d[3], d[1]), 1.f);
+    o[2] = xyxy ? d[2] : __fadd_rn(__fsub_rn(d[2], d[0]), 1.f);
+    o[3] = xyxy ? d[3] : __fadd_rn(__fsub_rn(d[3], d[1]), 1.f);
     o[4] = d[4];
     o[5] = (float)c;
   }
@@ -140,23 +140,27 @@ final_dets_kernel(const float* __restrict__ dets, const int* __restrict__ keep, 
 
 }  // namespace
 
-extern "C" int sdet_final_detections(const float* dets, const int* keep, const int* nkeep, int B, int num_classes,
-                                     int n_pad, int max_det, float* out, int* out_count, void* stream) {
+extern "C" int sdet_final_detections_ex(const float* dets, const int* keep, const int* nkeep, int B, int num_classes,
+                                        int n_pad, int max_det, float* out, int* out_count, int xyxy, int descending,
+                                        void* stream) {
   SDET_REQUIRE(dets && keep && nkeep && out && out_count, "NULL argument");
   SDET_REQUIRE(B > 0 && num_classes > 0 && n_pad > 0 && max_det > 0, "bad shape");
   if (num_classes > 1024) return sdet::fail(SDET_ERR_UNSUPPORTED, "more than 1024 classes");
   const int k_pow2 = sdet::next_pow2(max_det);
   const size_t smem = (size_t)k_pow2 * 8;
   if (smem > 160 * 1024) return sdet::fail(SDET_ERR_UNSUPPORTED, "max_det too large");
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  // per device and cheap: set on every launch that needs it instead of caching in a process-wide static
+  if (smem > 48 * 1024)
     SDET_CUDA(cudaFuncSetAttribute(final_dets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  final_dets_kernel<<<(unsigned)B, kTopkThreads, smem, (cudaStream_t)stream>>>(dets, keep, nkeep, num_classes, n_pad,
-                                                                              max_det, k_pow2, out, out_count);
+  final_dets_kernel<<<(unsigned)B, kTopkThreads, smem, (cudaStream_t)stream>>>(
+      dets, keep, nkeep, num_classes, n_pad, max_det, k_pow2, out, out_count, xyxy != 0, descending != 0);
   SDET_LAUNCH_CHECK("final_dets_kernel");
   return SDET_OK;
+}
+
+extern "C" int sdet_final_detections(const float* dets, const int* keep, const int* nkeep, int B, int num_classes,
+                                     int n_pad, int max_det, float* out, int* out_count, void* stream) {
+  return sdet_final_detections_ex(dets, keep, nkeep, B, num_classes, n_pad, max_det, out, out_count, 0, 0, stream);
 }
 
 extern "C" int sdet_get_top_proposal(const float* boxes, const float* scores, float* out_boxes,
@@ -168,11 +172,8 @@ extern "C" int sdet_get_top_proposal(const float* boxes, const float* scores, fl
   const int k_pow2 = sdet::next_pow2(top_n);
   const size_t smem = (size_t)k_pow2 * 8;
   if (smem > 200 * 1024) return sdet::fail(SDET_ERR_UNSUPPORTED, "top_n too large");
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024)
     SDET_CUDA(cudaFuncSetAttribute(top_proposal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   top_proposal_kernel<<<(unsigned)B, kTopkThreads, smem, (cudaStream_t)stream>>>(
       boxes, scores, M, top_n, k_pow2, out_boxes, out_scores);
   SDET_LAUNCH_CHECK("top_proposal_kernel");

@@ -481,11 +481,8 @@ static int proposal_target_core(const float* rois, const float* gt_boxes, const 
   p.seed = seed;
   const size_t smem = pt_smem_bytes(R + G, G, image_rois);
   if (smem > 220 * 1024) return sdet::fail(SDET_ERR_UNSUPPORTED, "ProposalTarget needs %zu B shared memory", smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024)  // per device and cheap: set on every launch, no process-wide cache
     SDET_CUDA(cudaFuncSetAttribute(proposal_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   proposal_target_kernel<<<(unsigned)B, kThreads, smem, (cudaStream_t)stream>>>(p);
   SDET_LAUNCH_CHECK("proposal_target_kernel");
   return SDET_OK;
@@ -534,11 +531,8 @@ extern "C" int sdet_poly_mask_target(const float* rois_out, const float* gt_poly
   if (mask_size > 112) return sdet::fail(SDET_ERR_UNSUPPORTED, "mask_size > 112");
   MaskParams p{rois_out, gt_polys, gt_index, fg_count, mask_target, image_rois, G, poly_len, num_mask_rows, mask_size};
   const size_t smem = sizeof(int) * (size_t)(2 * mask_size * mask_size + 2);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024)  // per device and cheap: set on every launch, no process-wide cache
     SDET_CUDA(cudaFuncSetAttribute(poly_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   dim3 grid((unsigned)num_mask_rows, (unsigned)B);
   poly_mask_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
   SDET_LAUNCH_CHECK("poly_mask_kernel");

@@ -223,11 +223,8 @@ extern "C" int sdet_gen_proposal_retina(const float* cls_prob, const float* bbox
   SDET_LAUNCH_CHECK("retina_candidates_kernel");
   const size_t smem = (size_t)sdet::next_pow2(p.pre) * 8;
   if (smem > 200 * 1024) return sdet::fail(SDET_ERR_UNSUPPORTED, "rpn_pre_nms_top_n too large for shared-memory select");
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024)  // per device and cheap: set on every launch, no process-wide cache
     SDET_CUDA(cudaFuncSetAttribute(retina_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   retina_select_kernel<<<(unsigned)B, kTopkThreads, smem, st>>>(p);
   SDET_LAUNCH_CHECK("retina_select_kernel");
   return SDET_OK;

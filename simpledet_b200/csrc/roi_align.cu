@@ -763,6 +763,59 @@ extern "C" int sdet_fpn_roi_align_v2_forward(const float* const* feats, const in
                                           roi_canonical_level, workspace, workspace_bytes, stream, 0, nullptr);
 }
 
+// assign_layer_fpn (models/FPN/assign_layer_fpn.py:17-40, CustomOp 'assign_layer_fpn') as its own operator: one
+// output per level, the roi where it is assigned and zeros elsewhere.
+struct FpnAssignArgs {
+  float* out[SDET_MAX_LEVELS];
+  int stride_log2[SDET_MAX_LEVELS];
+  int num_levels;
+  float scale0, lvl0, k_min, k_max;
+};
+__global__ void __launch_bounds__(256)
+fpn_assign_kernel(const float4* __restrict__ rois, const int total, const __grid_constant__ FpnAssignArgs a,
+                  int32_t* __restrict__ levels) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float4 r = __ldg(rois + i);
+  const int t = fpn_level(r.x, r.y, r.z, r.w, a.scale0, a.lvl0, a.k_min, a.k_max);
+  int li = -1;
+  for (int l = 0; l < a.num_levels; ++l) {
+    const bool mine = a.stride_log2[l] == t;
+    if (mine) li = l;
+    if (a.out[l]) reinterpret_cast<float4*>(a.out[l])[i] = mine ? r : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (levels) levels[i] = li;
+}
+
+extern "C" int sdet_fpn_assign(const float* rois, int total_rois, const int* strides, int num_levels,
+                               int roi_canonical_scale, int roi_canonical_level, float* const* out_rois,
+                               int32_t* levels_out, void* stream) {
+  SDET_REQUIRE(rois && strides && total_rois > 0, "NULL argument / no rois");
+  SDET_REQUIRE(num_levels >= 1 && num_levels <= SDET_MAX_LEVELS, "num_levels must be in [1, %d]", SDET_MAX_LEVELS);
+  SDET_REQUIRE(roi_canonical_scale > 0, "roi_canonical_scale must be > 0");
+  SDET_REQUIRE((reinterpret_cast<uintptr_t>(rois) & 15) == 0, "rois must be 16-byte aligned");
+  FpnAssignArgs a{};
+  int smin = INT_MAX, smax = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    const int lg = ilog2_exact(strides[l]);
+    if (lg < 0) return sdet::fail(SDET_ERR_UNSUPPORTED, "stride %d is not a power of two", strides[l]);
+    a.stride_log2[l] = lg;
+    a.out[l] = out_rois ? out_rois[l] : nullptr;
+    SDET_REQUIRE((reinterpret_cast<uintptr_t>(a.out[l]) & 15) == 0, "out_rois[%d] must be 16-byte aligned", l);
+    smin = strides[l] < smin ? strides[l] : smin;
+    smax = strides[l] > smax ? strides[l] : smax;
+  }
+  a.num_levels = num_levels;
+  a.scale0 = (float)roi_canonical_scale;
+  a.lvl0 = (float)roi_canonical_level;
+  a.k_min = (float)ilog2_exact(smin);
+  a.k_max = (float)ilog2_exact(smax);
+  fpn_assign_kernel<<<(unsigned)((total_rois + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(rois), total_rois, a, levels_out);
+  SDET_LAUNCH_CHECK("fpn_assign_kernel");
+  return SDET_OK;
+}
+
 static int launch_bwd(BwdArgs& a, int num_levels, const int* H, const int* W, float* const* grads,
                       int accumulate, float* grad_rois, cudaStream_t st) {
   for (int l = 0; l < num_levels; ++l) {

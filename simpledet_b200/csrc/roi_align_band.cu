@@ -22,6 +22,8 @@
 // Every feature byte is staged 1.5x (halo) instead of once per covering roi; rows are read as whole
 // 1.3 KB bursts.  Rois the band path cannot take (bins taller than the halo, sample counts != 2,
 // unaligned or very wide levels) go to the per-roi kernel through `left_order`.
+#include <type_traits>
+
 #include "roi_align_common.cuh"
 
 using namespace sdet_ra;
@@ -30,8 +32,14 @@ namespace sdet_ra {
 
 namespace {
 
-constexpr int kBandThreads = 512;     // warp 0: producer; warps 1..15: consumers
-constexpr int kBandConsumers = 15;
+#ifndef SDET_BAND_CONSUMERS
+#define SDET_BAND_CONSUMERS 11
+#endif
+#ifndef SDET_BAND_CL8
+#define SDET_BAND_CL8 1
+#endif
+constexpr int kBandConsumers = SDET_BAND_CONSUMERS;      // consumer warps; warp 0 is the producer
+constexpr int kBandThreads = 32 * (kBandConsumers + 1);  // 12 warps: 168 registers per thread for the 8-channel jobs
 constexpr int kStageBytes = kBandStageFloats * 4;
 
 struct StageDesc {   // 64 bytes, written by the producer before it arms the stage's `full` barrier
@@ -106,6 +114,7 @@ roi_align_band_plan_kernel(const __grid_constant__ RoiAlignArgs a, const __grid_
                            PlanRecord* __restrict__ plans) {
   __shared__ __align__(16) PlanRecord s_rec;
   __shared__ int s_bd[16];
+  __shared__ int s_code[32];
   __shared__ int s_ok;
   const int n = blockIdx.x, tid = threadIdx.x;
   const int PH = a.PH, PW = a.PW;
@@ -132,6 +141,32 @@ roi_align_band_plan_kernel(const __grid_constant__ RoiAlignArgs a, const __grid_
       for (int ph = 0; ph < PH; ++ph) {
         if (s_bd[ph] < 0) s_bd[ph] = cur;
         else cur = s_bd[ph];
+      }
+      // Row-cache codes: simulate band_compute's two register sets (tags = absolute rows) over each item.
+      // bits [1:0]: 0 low row is in set A, 1 in set B, 2 load it into A; bit 16: load the high row into the other set.
+      int tagA = -1, tagB = -1, prev_bd = -1;
+      for (int ph = 0; ph < PH; ++ph) {
+        if (s_bd[ph] != prev_bd) {  // a new item starts with an empty cache
+          tagA = tagB = -1;
+          prev_bd = s_bd[ph];
+        }
+        for (int s = 0; s < 2; ++s) {
+          int code = 0;
+          if (s_rec.th.cnt[ph] == 2) {
+            const int lo = s_rec.th.lo[ph * kMaxS + s], hi = s_rec.th.hi[ph * kMaxS + s];
+            if (lo == tagA) {
+              if (hi != tagB) { code |= 0x10000; tagB = hi; }
+            } else if (lo == tagB) {
+              code |= 1;
+              if (hi != tagA) { code |= 0x10000; tagA = hi; }
+            } else {
+              code |= 2;
+              tagA = lo;
+              if (hi != tagB) { code |= 0x10000; tagB = hi; }
+            }
+          }
+          s_code[ph * 2 + s] = code;
+        }
       }
     }
     s_ok = ok ? 1 : 0;
@@ -169,7 +204,8 @@ roi_align_band_plan_kernel(const __grid_constant__ RoiAlignArgs a, const __grid_
     if (ph < PH && s_rec.th.cnt[ph] == 2) {
       const int k = ph * kMaxS + s;
       const int r0 = s_bd[ph] * kBandR;
-      e.x = (unsigned)((s_rec.th.lo[k] - r0) * W4) | ((unsigned)((s_rec.th.hi[k] - r0) * W4) << 16);
+      e.x = (unsigned)((s_rec.th.lo[k] - r0) * W4) | ((unsigned)((s_rec.th.hi[k] - r0) * W4) << 16) |
+            (unsigned)s_code[ph * 2 + s];
       e.y = __float_as_uint(s_rec.th.w1[k]);
       hc = s_rec.th.coord[k];
     }
@@ -290,11 +326,15 @@ roi_align_band_layout_kernel(const __grid_constant__ BandArgs ba, const int num_
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
-template <int kCS>
+// One job = one item x CL channels.  The row cache (two register sets RA / RB, each one staged row of the
+// lane's two taps for CL channels) is driven by codes the plan kernel precomputed by simulating exactly this
+// replacement policy from the item's first bin: bits [1:0] of an entry's low half say where the sample's low
+// row lives (0: in RA, 1: in RB, 2: nowhere -> load it into RA), bit 16 says the high row must be loaded into
+// the other set.  No run-time tag compares, no votes.
+template <int kCS, int CL>
 __device__ __forceinline__ void band_compute(const RoiAlignArgs& a, const unsigned chbase, const unsigned slot,
                                              const int2 it, const int c, const unsigned oddshift, const int lane,
                                              const uint64_t nz2) {
-  constexpr int CL = 4;
   const int n = it.x, ph0 = it.y & 0xFF, nph = (it.y >> 8) & 0xFF;
   const bool has_empty = ((it.y >> 16) & kFlagEmpty) != 0;
   const int PH = a.PH, PW = a.PW, PP = PH * PW;
@@ -306,13 +346,13 @@ __device__ __forceinline__ void band_compute(const RoiAlignArgs& a, const unsign
   const float b1 = __uint_as_float(le.y), b0 = __fsub_rn(1.f, b1);
   const unsigned ale = chbase + xl, are = chbase + xr, alo = ale + oddshift, aro = are + oddshift;
   float RA[CL][2], RB[CL][2];
-  unsigned rowA = 0xFFFFFFFFu, rowB = 0xFFFFFFFFu;
   // after the pair exchange both lanes of a pw hold all CL maxima; lane s stores channels
   // [s*CL/2, (s+1)*CL/2) so every store instruction has 2*PW active lanes
   float* outh = a.out + ((size_t)n * a.C + c + sx * (CL / 2)) * PP + (size_t)ph0 * PW + pw;
 
-  auto sample = [&](const unsigned offs, const float a1, float (&v)[CL]) {
-    const unsigned olo = offs & 0xFFFFu, ohi = offs >> 16;
+  auto sample = [&](const unsigned offs, const float a1, float (&m)[CL], auto first_tag) {
+    constexpr bool kFirst = decltype(first_tag)::value;
+    const unsigned olo = offs & 0xFFFCu, ohi = (offs >> 16) & 0xFFFCu;
     const float a0 = __fsub_rn(1.f, a1);
     const float wtl = __fmul_rn(a0, b0), wbl = __fmul_rn(a1, b0);
     const float wtr = __fmul_rn(a0, b1), wbr = __fmul_rn(a1, b1);
@@ -326,31 +366,21 @@ __device__ __forceinline__ void band_compute(const RoiAlignArgs& a, const unsign
         const uint64_t pbl = fma2(wbl2, pack2(Hi[k][0], Hi[k + 1][0]), nz2);
         const uint64_t ptr = fma2(wtr2, pack2(Lo[k][1], Lo[k + 1][1]), nz2);
         const uint64_t pbr = fma2(wbr2, pack2(Hi[k][1], Hi[k + 1][1]), nz2);
-        unpack2(add2(add2(add2(ptl, pbl), ptr), pbr), v[k], v[k + 1]);
+        float va, vb;
+        unpack2(add2(add2(add2(ptl, pbl), ptr), pbr), va, vb);
+        // running maximum over the bin's samples; fmaxf drops a NaN operand like `v > m` does
+        m[k] = kFirst ? va : fmaxf(m[k], va);
+        m[k + 1] = kFirst ? vb : fmaxf(m[k + 1], vb);
       }
     };
-    // 2-row register cache: the set that already holds `lo` plays the low row, nothing is moved
-    // the tests are warp-uniform (table entries are broadcast loads); routing them through a vote
-    // lets ptxas emit plain branches instead of divergence bookkeeping
-    if (__all_sync(0xffffffffu, olo == rowA)) {
-      if (__any_sync(0xffffffffu, ohi != rowB)) {
-        TapLoaderEO<CL, kCS>::run(RB, ale + ohi, are + ohi, alo + ohi, aro + ohi);
-        rowB = ohi;
-      }
-      step(RA, RB);
-    } else if (__all_sync(0xffffffffu, olo == rowB)) {
-      if (__any_sync(0xffffffffu, ohi != rowA)) {
-        TapLoaderEO<CL, kCS>::run(RA, ale + ohi, are + ohi, alo + ohi, aro + ohi);
-        rowA = ohi;
-      }
+    const unsigned path = offs & 3u;
+    const bool ldhi = (offs & 0x10000u) != 0;
+    if (path == 1u) {  // low row in RB
+      if (ldhi) TapLoaderEO<CL, kCS>::run(RA, ale + ohi, are + ohi, alo + ohi, aro + ohi);
       step(RB, RA);
     } else {
-      TapLoaderEO<CL, kCS>::run(RA, ale + olo, are + olo, alo + olo, aro + olo);
-      rowA = olo;
-      if (__any_sync(0xffffffffu, ohi != rowB)) {
-        TapLoaderEO<CL, kCS>::run(RB, ale + ohi, are + ohi, alo + ohi, aro + ohi);
-        rowB = ohi;
-      }
+      if (path == 2u) TapLoaderEO<CL, kCS>::run(RA, ale + olo, are + olo, alo + olo, aro + olo);
+      if (ldhi) TapLoaderEO<CL, kCS>::run(RB, ale + ohi, are + ohi, alo + ohi, aro + ohi);
       step(RA, RB);
     }
   };
@@ -358,23 +388,20 @@ __device__ __forceinline__ void band_compute(const RoiAlignArgs& a, const unsign
   const unsigned rowtab = slot + 256u + (unsigned)ph0 * 16u;
   for (int i = 0; i < nph; ++i) {
     const uint4 re = lds128(rowtab + (unsigned)i * 16u);  // {offs s0, alpha s0, offs s1, alpha s1}
-    float v0[CL], v1[CL];
-    const bool hvalid = re.x != 0xFFFFFFFFu;  // warp-uniform
-    if (hvalid) {
-      sample(re.x, __uint_as_float(re.y), v0);
-      sample(re.z, __uint_as_float(re.w), v1);
-    } else {
+    if (re.x == 0xFFFFFFFFu) {  // bin empty along h (warp-uniform): pools to 0 (roi_align_v2-inl.h:111-117)
+      if (lane_on) {
 #pragma unroll
-      for (int k = 0; k < CL; ++k) v0[k] = v1[k] = -FLT_MAX;
+        for (int k = 0; k < CL / 2; ++k) __stcs(outh + k * PP, 0.f);
+      }
+      outh += PW;
+      continue;
     }
-    // bins empty along an axis pool to 0 (roi_align_v2-inl.h:111-117)
-    const bool zero_out = has_empty && (!hvalid || !wvalid);
     float best[CL];
+    sample(re.x, __uint_as_float(re.y), best, std::true_type{});
+    sample(re.z, __uint_as_float(re.w), best, std::false_type{});
+    const bool zero_out = has_empty && !wvalid;  // bin empty along w
 #pragma unroll
-    for (int k = 0; k < CL; ++k) {
-      const float mk = fmaxf(v0[k], v1[k]);  // fmaxf drops a NaN operand like `v > m` does
-      best[k] = max3f(mk, __shfl_xor_sync(0xffffffffu, mk, 1), -FLT_MAX);
-    }
+    for (int k = 0; k < CL; ++k) best[k] = max3f(best[k], __shfl_xor_sync(0xffffffffu, best[k], 1), -FLT_MAX);
     if (lane_on) {
 #pragma unroll
       for (int k = 0; k < CL / 2; ++k) {
@@ -471,6 +498,7 @@ roi_align_band_kernel(const __grid_constant__ RoiAlignArgs a, const __grid_const
           sts32(d + 24, G.oddshift);
           sts32(d + 28, st == nst - 1);
           sts32(d + 32, 0);
+          sts32(d + 36, (int)(0xFFFFFFFFu / (unsigned)nit + 1u));  // w / nit == umulhi(w, magic) for w < 2^16
           mbar_expect_tx(full, tx);
         }
         __syncwarp();
@@ -498,11 +526,16 @@ roi_align_band_kernel(const __grid_constant__ RoiAlignArgs a, const __grid_const
     const uint4 d0 = lds128(d), d1 = lds128(d + 16);
     if (d0.x) break;
     const int nitems = (int)d0.y, tbl = (int)d0.z, cbase = (int)d0.w;
-    const int nq = (int)d1.x >> 2, cs_log2 = (int)d1.y;
+    const int nchs = (int)d1.x, cs_log2 = (int)d1.y;
     const unsigned oddshift = d1.z;
     const int last = (int)d1.w;
-    const int total = nitems * nq;
+    const uint4 d2 = lds128(d + 32);  // {next, magic = ceil(2^32 / nitems), -, -}
+    const unsigned magic = d2.y;
     const unsigned sbase = s0 + (unsigned)slot * kStageBytes;
+    // classes with >= 8 channels per stage run 8 channels per lane (weights, table reads and row-cache control
+    // are paid once per sample whatever the channel count); the widest class (4 channels per stage) runs 4
+    const int cl_log2 = (!SDET_BAND_CL8 || cs_log2 == 12 || (nchs & 7)) ? 2 : 3;
+    const int total = nitems * (nchs >> cl_log2);
     for (;;) {
       int w = 0;
       if (lane == 0) {
@@ -510,17 +543,26 @@ roi_align_band_kernel(const __grid_constant__ RoiAlignArgs a, const __grid_const
       }
       w = __shfl_sync(0xffffffffu, w, 0);
       if (w >= total) break;
-      const int q = w / nitems, item = w - q * nitems;
+      const int q = nitems == 1 ? w : (int)__umulhi((unsigned)w, magic);
+      const int item = w - q * nitems;
       const uint2 itv = lds64(items0 + (unsigned)(tbl * 32 + item) * 8u);
       const int2 it = make_int2((int)itv.x, (int)itv.y);
       const unsigned slot_addr = tbl0 + (unsigned)(tbl * kCap + item) * kSlot;
-      const unsigned chbase = sbase + ((unsigned)(q * 4) << (cs_log2 + 2));
-      const int c = cbase + q * 4;
-      switch (cs_log2) {
-        case 9: band_compute<512>(a, chbase, slot_addr, it, c, oddshift, lane, nz2); break;
-        case 10: band_compute<1024>(a, chbase, slot_addr, it, c, oddshift, lane, nz2); break;
-        case 11: band_compute<2048>(a, chbase, slot_addr, it, c, oddshift, lane, nz2); break;
-        default: band_compute<4096>(a, chbase, slot_addr, it, c, oddshift, lane, nz2); break;
+      const unsigned chbase = sbase + ((unsigned)(q << cl_log2) << (cs_log2 + 2));
+      const int c = cbase + (q << cl_log2);
+      if (cl_log2 == 2) {
+        switch (cs_log2) {
+          case 9: band_compute<512, 4>(a, chbase, slot_addr, it, c, oddshift, lane, nz2); break;
+          case 10: band_compute<1024, 4>(a, chbase, slot_addr, it, c, oddshift, lane, nz2); break;
+          case 11: band_compute<2048, 4>(a, chbase, slot_addr, it, c, oddshift, lane, nz2); break;
+          default: band_compute<4096, 4>(a, chbase, slot_addr, it, c, oddshift, lane, nz2); break;
+        }
+      } else {
+        switch (cs_log2) {
+          case 9: band_compute<512, 8>(a, chbase, slot_addr, it, c, oddshift, lane, nz2); break;
+          case 10: band_compute<1024, 8>(a, chbase, slot_addr, it, c, oddshift, lane, nz2); break;
+          default: band_compute<2048, 8>(a, chbase, slot_addr, it, c, oddshift, lane, nz2); break;
+        }
       }
     }
     __syncwarp();

@@ -185,9 +185,9 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "{\n"
       ".reg .pred p;\n"
       "W_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"   // HW-suspended wait, woken by the arrival
       "@!p bra W_%=;\n"
-      "}\n" ::"r"(bar), "r"(parity)
+      "}\n" ::"r"(bar), "r"(parity), "r"(0x989680)
       : "memory");
 }
 template <int IMM>

@@ -190,11 +190,8 @@ extern "C" int sdet_soft_nms(const float* dets, const int* counts, int problems,
   SDET_REQUIRE(method >= 0 && method <= 2, "method must be 0 (hard), 1 (linear) or 2 (gaussian)");
   const size_t smem = (size_t)m * (5 * 4 + 4 * 4);
   if (smem > 200 * 1024) return sdet::fail(SDET_ERR_UNSUPPORTED, "soft-NMS over %d boxes per problem", m);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024)  // per device and cheap: set on every launch, no process-wide cache
     SDET_CUDA(cudaFuncSetAttribute(soft_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   soft_nms_kernel<<<(unsigned)problems, kThreads, smem, (cudaStream_t)stream>>>(
       dets, counts, m, sigma, Nt, threshold, method, out_boxes, out_inds, out_counts);
   SDET_LAUNCH_CHECK("soft_nms_kernel");

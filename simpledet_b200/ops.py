@@ -18,7 +18,7 @@ import torch
 from . import _lib
 from ._lib import check
 
-__all__ = ["ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_raw",
+__all__ = ["gpu_nms", "greedy_nms", "bbox_overlaps_cython", "assign_layer_fpn", "BboxPostProcessing", "ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_raw",
            "fpn_roi_align", "fpn_roi_align_raw", "DecodeBBox", "Proposal_v3", "Proposal_v3_fpn", "NMS", "nms_sorted", "get_top_proposal",
            "multiclass_nms", "ProposalTarget", "FocalLoss", "BBoxNorm",
            "SigmoidCrossEntropy", "soft_nms", "soft_nms_batched",
@@ -1129,6 +1129,77 @@ def cython_soft_nms_wrapper(thresh, sigma=0.5, score_thresh=0.001, method="linea
     return _nms
 
 
+# --------------------------------------------------------------------------------------------
+# Drop-in callables and CustomOp twins (SURVEY §8b "Secondary API 1/2/3")
+# --------------------------------------------------------------------------------------------
+def gpu_nms(dets, thresh, device_id=0):
+    """operator_py/cython/gpu_nms.pyx:16-31 with the library's `_nms` export behind it: dets (m,5) float32 NUMPY
+    array on the host -> list of kept indices into dets (descending score, `IoU > thresh` suppressed)."""
+    import numpy as np
+
+    dets = np.ascontiguousarray(dets, dtype=np.float32)
+    n, dim = dets.shape
+    order = dets[:, 4].argsort()[::-1]
+    sorted_dets = np.ascontiguousarray(dets[order, :])
+    keep = np.zeros(n, dtype=np.int32)
+    num_out = ctypes.c_int(0)
+    _lib.lib()._nms(keep.ctypes.data, ctypes.byref(num_out), sorted_dets.ctypes.data, int(n), int(dim), float(thresh),
+                    int(device_id))
+    return list(order[keep[:num_out.value]])
+
+
+def greedy_nms(dets, thresh):
+    """operator_py/cython/cpu_nms.pyx:37-87 greedy_nms: dets (m,5) CUDA tensor -> kept indices ascending
+    (`np.where(suppressed == 0)[0]`), suppression at IoU >= thresh."""
+    dets = _dev(dets, "dets")
+    if dets.shape[0] == 0:
+        return torch.empty((0,), dtype=torch.int64, device=dets.device)
+    order = torch.sort(dets[:, 4], descending=True, stable=True).indices
+    keep, nkeep = nms_sorted(dets[order].contiguous()[None], thresh, ge=True)
+    return torch.sort(order[keep[0, :int(nkeep.item())].long()]).values
+
+
+def bbox_overlaps_cython(boxes, query_boxes):
+    """operator_py/cython/bbox.pyx:32-73 on the device: (N,4), (K,4) -> (N,K) IoU."""
+    return bbox_overlaps(boxes, query_boxes, "iou")
+
+
+def assign_layer_fpn(rois, rcnn_stride=(4, 8, 16, 32), roi_canonical_scale=224, roi_canonical_level=4,
+                     return_levels=False):
+    """CustomOp 'assign_layer_fpn' (models/FPN/assign_layer_fpn.py:17-40): rois (B,N,4) -> one (B,N,4) tensor per
+    stride holding the roi where it is assigned to that level and zeros elsewhere."""
+    rois = _dev(rois, "rois")
+    if rois.dim() != 3 or rois.shape[2] != 4:
+        raise ValueError("rois must be (B,N,4)")
+    L = len(rcnn_stride)
+    outs = [torch.empty_like(rois) for _ in range(L)]
+    levels = torch.empty(rois.shape[:2], device=rois.device, dtype=torch.int32)
+    ptrs = (ctypes.c_void_p * L)(*[o.data_ptr() for o in outs])
+    Ss = (ctypes.c_int * L)(*[int(s) for s in rcnn_stride])
+    check(_lib.lib().sdet_fpn_assign(_p(rois), rois.shape[0] * rois.shape[1], Ss, L, int(roi_canonical_scale),
+                                     int(roi_canonical_level), ptrs, _p(levels), _stream()))
+    return (tuple(outs), levels) if return_levels else tuple(outs)
+
+
+def BboxPostProcessing(cls_score, bbox_xyxy, max_det_per_image=100, min_det_score=0.05, nms_type="nms", nms_thr=0.5):
+    """CustomOp 'BboxPostProcessing' (models/maskrcnn/bbox_post_processing.py:6-76): background column dropped,
+    per-class py_nms, the max_det_per_image highest scores of the image -> post_score (B,M,1), post_bbox_xyxy
+    (B,M,4), post_cls (B,M,1) (class index without background, -1 padding), descending score.  Among equal scores
+    the reference's `np.argsort(scores)[::-1]` order is numpy's introsort order; here ties go to the later class."""
+    if nms_type != "nms":
+        raise NotImplementedError
+    dets, counts, keep, nkeep, _ = multiclass_nms(cls_score, bbox_xyxy, nms_thr, min_det_score, first_class=1)
+    B, _, K = cls_score.shape
+    M = int(max_det_per_image)
+    out = torch.empty((B, M, 6), device=dets.device, dtype=torch.float32)
+    cnt = torch.empty((B,), device=dets.device, dtype=torch.int32)
+    check(_lib.lib().sdet_final_detections_ex(_p(dets), _p(keep), _p(nkeep), B, K - 1, int(dets.shape[1]), M, _p(out),
+                                              _p(cnt), 1, 1, _stream()))
+    # rows beyond the count are [0,0,0,0,0,-1]: exactly the reference's zero / -1 initialised outputs
+    post_bbox, post_score, post_cls = out[..., :4].contiguous(), out[..., 4:5].contiguous(), out[..., 5:6].contiguous()
+    return post_score, post_bbox, post_cls
+
+
 # Registry keyed by the reference's operator names (what symbol/builder.py binds by string).
 OPS = {
     "_contrib_ROIAlign_v2": ROIAlign_v2,
@@ -1151,4 +1222,14 @@ OPS = {
     "_contrib_BBoxNorm": BBoxNorm,
     "_contrib_SigmoidCrossEntropy": SigmoidCrossEntropy,
     "get_top_proposal": get_top_proposal,  # mx.operator.register('get_top_proposal')
+    "assign_layer_fpn": assign_layer_fpn,  # mx.operator.register('assign_layer_fpn')
+    "BboxPostProcessing": BboxPostProcessing,  # mx.operator.register('BboxPostProcessing')
+    # plain callables of operator_py (same names and argument meaning)
+    "gpu_nms": gpu_nms,
+    "greedy_nms": greedy_nms,
+    "bbox_overlaps_cython": bbox_overlaps_cython,
+    "soft_nms": soft_nms,
+    "cython_soft_nms_wrapper": cython_soft_nms_wrapper,
+    "py_set_nms_wrapper": py_set_nms_wrapper,
+    "wnms_wrapper": wnms_wrapper,
 }

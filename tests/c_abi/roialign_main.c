@@ -32,7 +32,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&ws, wsb));
   CK(cudaMemcpy(dd, hd, nd * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dr, hr, nr * 4, cudaMemcpyHostToDevice));
-  if (sdet_abi_version() != 3) { fprintf(stderr, "unexpected ABI version %d\n", sdet_abi_version()); return 3; }
+  if (sdet_abi_version() != 4) { fprintf(stderr, "unexpected ABI version %d\n", sdet_abi_version()); return 3; }
   /* an invalid call must fail loudly and leave a message */
   if (sdet_roi_align_v2_forward(dd, dr, dout, dax, NULL, B, N, C, H, W, PH, PW, scale, ws, wsb, NULL) == SDET_OK) return 4;
   if (!sdet_last_error() || !sdet_last_error()[0]) return 5;

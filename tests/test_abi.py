@@ -40,7 +40,7 @@ def test_ctypes_binding_covers_header(built):
 
     L = _lib.lib()
     assert sorted(_lib.EXPORTED_SYMBOLS) == _declared()
-    assert L.sdet_abi_version() == 3
+    assert L.sdet_abi_version() == 4
     assert L.sdet_last_error() == b""
     assert L.sdet_launch_count() == 0
 

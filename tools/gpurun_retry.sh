@@ -1,0 +1,10 @@
+#!/bin/bash
+# usage: tools/gpurun_retry.sh <timeout-seconds> '<command>'   - retries while the pod answers "busy" (exit 3)
+t=$1; shift
+for i in $(seq 1 20); do
+  /usr/local/graft/bin/gpurun --timeout "$t" -- "$@"
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  sleep 45
+done
+exit 3
