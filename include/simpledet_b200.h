@@ -129,9 +129,12 @@ int sdet_fpn_roi_align_v2_backward(const float* ograd, const float* argmax_x,
 int sdet_roi_pooling_v1_forward(const float* data, const float* rois, float* out, float* max_idx,
                                 int B, int R, int C, int H, int W, int pooled_h, int pooled_w,
                                 float spatial_scale, void* stream);
+/* Backward takes spatial_scale like ROIPoolBackwardAcc (roi_pooling_v1-inl.h:128-129): the bins are re-derived
+ * from the rois so that gradients can be gathered per feature pixel. */
 int sdet_roi_pooling_v1_backward(const float* ograd, const float* max_idx, const float* rois,
                                  float* grad_data, float* grad_rois, int B, int R, int C, int H,
-                                 int W, int pooled_h, int pooled_w, int accumulate, void* stream);
+                                 int W, int pooled_h, int pooled_w, float spatial_scale, int accumulate,
+                                 void* stream);
 
 
 /* ------------------------------------------------------------------------------------------

@@ -47,7 +47,7 @@ _SIGNATURES = {
     "sdet_roi_pooling_v1_forward": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_float, _P],
     "sdet_roi_pooling_v1_backward": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
-                                     c_int, c_int, _P],
+                                     c_int, c_float, c_int, _P],
     "sdet_decode_bbox": [_P, _P, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), c_int,
                          c_int, _P],
     "sdet_proposal_v3_workspace": [c_int, c_int, c_int, c_int, c_int],

@@ -73,6 +73,155 @@ deform_im2col_kernel(const float* __restrict__ data, const float* __restrict__ o
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiled im2col (3x3-class kernels): CTA = (image, deformable group, run of up to 192 consecutive output pixels,
+// channel slice).  The offsets of a deformable group are shared by all its channels, so each thread derives the
+// sampling geometry of ITS output pixel once - per tap: patch-relative corner index, corner strides, the four
+// bilinear weights - and keeps it in registers; the channel loop then is 4 shared-memory reads, 4 products, 3 sums
+// and one coalesced store per col element.  The rows of the input a run can reach (its own rows, the kernel extent
+// and a margin of kDcnMargin rows for the offsets) are contiguous per channel plane and are staged with 16-byte
+// cp.async into a double-buffered shared-memory patch, channel sub-tile s+1 in flight while sub-tile s is gathered.
+// Samples displaced beyond the margin read their four corners from global memory instead (flagged per tap).
+// Arithmetic is the generic kernel's, operation for operation.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDcnThreads = 192;
+constexpr int kDcnMaxTaps = 9;
+constexpr int kDcnMargin = 6;
+constexpr int kDcnStageFloats = 12288;  // 48 KB per stage, two stages
+
+__device__ __forceinline__ void dcn_cp16(unsigned dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void dcn_cp4(unsigned dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int kTaps>
+__global__ void __launch_bounds__(kDcnThreads)
+deform_im2col_tiled_kernel(const float* __restrict__ data, const float* __restrict__ offset, float* __restrict__ col,
+                           const DcnShape s, const int B, const int ct, const int ch_slices, const int runs_per_image) {
+  extern __shared__ __align__(16) float s_patch[];  // [2][ct][chan_floats]
+  const int tid = threadIdx.x;
+  const int HWo = s.Ho * s.Wo, cpg = s.C / s.dg;
+  int bid = blockIdx.x;
+  const int slice = bid % ch_slices; bid /= ch_slices;
+  const int run = bid % runs_per_image; bid /= runs_per_image;
+  const int g = bid % s.dg, b = bid / s.dg;
+  const int p0 = run * kDcnThreads, npx = min(kDcnThreads, HWo - p0);
+  const int c_per = (cpg + ch_slices - 1) / ch_slices;
+  const int c_begin = g * cpg + slice * c_per, c_end = min((g + 1) * cpg, c_begin + c_per);
+  // rows of the input this run can reach
+  const int h_lo = p0 / s.Wo, h_hi = (p0 + npx - 1) / s.Wo;
+  const int r_lo = max(0, h_lo * s.stride_h - s.pad_h - kDcnMargin);
+  const int r_hi = min(s.H, h_hi * s.stride_h - s.pad_h + (s.KH - 1) * s.dil_h + 2 + kDcnMargin);
+  const int patch = max(r_hi - r_lo, 0) * s.W;       // floats per channel
+  const int chan_floats = (patch + 3 + 4) & ~3;     // + alignment shift, rounded to 16 bytes
+
+  // ---- per-thread sampling geometry (registers)
+  float w1[kTaps], w2[kTaps], w3[kTaps], w4[kTaps];
+  int idx[kTaps];   // patch-relative index of the top-left corner; -1: sample is zero; -2: corners come from global
+  int dxy[kTaps];   // (w_high - w_low) | ((h_high - h_low) * W) << 1   [patch]   or  absolute top-left index [global]
+  const bool active = tid < npx;
+  const int p = p0 + (active ? tid : 0);
+  const int h_col = p / s.Wo, w_col = p - h_col * s.Wo;
+  {
+    const float* off = offset + ((size_t)b * s.dg + g) * 2 * kTaps * HWo + p;
+#pragma unroll
+    for (int t = 0; t < kTaps; ++t) {
+      const int i = t / s.KW, j = t - i * s.KW;
+      const float oh = __ldg(off + (size_t)(2 * t) * HWo), ow = __ldg(off + (size_t)(2 * t + 1) * HWo);
+      float h = (float)(h_col * s.stride_h - s.pad_h + i * s.dil_h) + oh;
+      float w = (float)(w_col * s.stride_w - s.pad_w + j * s.dil_w) + ow;
+      idx[t] = -1;
+      dxy[t] = 0;
+      w1[t] = w2[t] = w3[t] = w4[t] = 0.f;
+      if (active && h >= 0.f && w >= 0.f && h < (float)s.H && w < (float)s.W) {
+        int h_low = (int)floorf(h), w_low = (int)floorf(w), h_high, w_high;
+        if (h_low >= s.H - 1) { h_high = h_low = s.H - 1; h = (float)h_low; } else h_high = h_low + 1;
+        if (w_low >= s.W - 1) { w_high = w_low = s.W - 1; w = (float)w_low; } else w_high = w_low + 1;
+        const float lh = h - (float)h_low, lw = w - (float)w_low, hh = 1.f - lh, hw = 1.f - lw;
+        w1[t] = hh * hw; w2[t] = hh * lw; w3[t] = lh * hw; w4[t] = lh * lw;
+        const int d = (w_high - w_low) | (((h_high - h_low) * s.W) << 1);
+        if (h_low >= r_lo && h_high < r_hi) {
+          idx[t] = (h_low - r_lo) * s.W + w_low;
+          dxy[t] = d;
+        } else {
+          idx[t] = -2;
+          dxy[t] = ((h_low * s.W + w_low) << 1) | (w_high - w_low);  // absolute; the row step is re-derived below
+          w4[t] = lh * lw;
+          // h_high - h_low in bit 30 (indices stay far below 2^29)
+          if (h_high != h_low) dxy[t] |= 1 << 30;
+        }
+      }
+    }
+  }
+
+  const size_t plane = (size_t)s.H * s.W;
+  const float* tensor_begin = data;
+  const float* tensor_end = data + (size_t)B * s.C * plane;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(s_patch);
+  __shared__ int s_shift[2][32];
+
+  // stage `nc` channels starting at channel c0 into buffer `buf`: the patch of a channel is one contiguous run
+  auto stage = [&](int c0, int nc, int buf) {
+    for (int k = 0; k < nc; ++k) {
+      const float* src = data + ((size_t)b * s.C + c0 + k) * plane + (size_t)r_lo * s.W;
+      const int shift = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);  // floats past a 16-byte boundary
+      if (tid == 0) s_shift[buf][k] = shift;
+      const float* a0 = src - shift;                                         // 16-byte aligned
+      const unsigned d0 = sbase + 4u * (unsigned)((buf * ct + k) * chan_floats);
+      const int nchunks = (patch + shift + 3) >> 2;
+      for (int q = tid; q < nchunks; q += kDcnThreads) {
+        const float* a = a0 + 4 * q;
+        if (a >= tensor_begin && a + 4 <= tensor_end) {
+          dcn_cp16(d0 + 16u * q, a);
+        } else {  // first / last chunk of the whole tensor: element-wise, in range only
+          for (int e = 0; e < 4; ++e)
+            if (a + e >= tensor_begin && a + e < tensor_end) dcn_cp4(d0 + 16u * q + 4u * e, a + e);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int nct = c_end - c_begin;
+  const int nst = (nct + ct - 1) / ct;
+  if (nst > 0) stage(c_begin, min(ct, nct), 0);
+  for (int st = 0; st < nst; ++st) {
+    const int buf = st & 1;
+    if (st + 1 < nst) {
+      stage(c_begin + (st + 1) * ct, min(ct, nct - (st + 1) * ct), buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int c0 = c_begin + st * ct, nc = min(ct, nct - st * ct);
+    if (active) {
+      for (int k = 0; k < nc; ++k) {
+        const float* sp = s_patch + (size_t)(buf * ct + k) * chan_floats + s_shift[buf][k];
+        const float* im = data + ((size_t)b * s.C + c0 + k) * plane;
+        float* out = col + (((size_t)b * s.C + c0 + k) * kTaps) * HWo + p;
+#pragma unroll
+        for (int t = 0; t < kTaps; ++t) {
+          float v = 0.f;
+          if (idx[t] >= 0) {
+            const int dx = dxy[t] & 1, dy = dxy[t] >> 1;
+            const float* q = sp + idx[t];
+            v = w1[t] * q[0] + w2[t] * q[dx] + w3[t] * q[dy] + w4[t] * q[dy + dx];
+          } else if (idx[t] == -2) {
+            const int dx = dxy[t] & 1, dy = (dxy[t] >> 30) ? s.W : 0;
+            const float* q = im + ((dxy[t] & 0x3FFFFFFF) >> 1);
+            v = w1[t] * __ldg(q) + w2[t] * __ldg(q + dx) + w3[t] * __ldg(q + dy) + w4[t] * __ldg(q + dy + dx);
+          }
+          __stcs(out + (size_t)t * HWo, v);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Backward of the gather: thread = one col element; scatters to data grad (4 atomics) and
 // accumulates the offset gradient of its (group, tap, pixel) (2 atomics: channels of a group share it).
 __global__ void __launch_bounds__(256)
@@ -245,6 +394,26 @@ extern "C" int sdet_deformable_im2col(const float* data, const float* offset, fl
   if (int rc = fill_shape(s, C, H, W, kernel_h, kernel_w, pad_h, pad_w, stride_h, stride_w, dilate_h, dilate_w,
                           num_deformable_group))
     return rc;
+  // tiled path: 3x3-class kernels whose reachable input rows fit the staging buffer with >= 4 channels per stage
+  const int HWo = s.Ho * s.Wo;
+  const int rows_max = ((kDcnThreads + s.Wo - 1) / s.Wo + 1) * stride_h + (kernel_h - 1) * dilate_h + 2 + 2 * kDcnMargin;
+  const int chan_floats_max = ((rows_max < H ? rows_max : H) * W + 7) & ~3;
+  int ct = kDcnStageFloats / chan_floats_max;
+  if (ct > 8) ct = 8;
+  if (kernel_h * kernel_w == kDcnMaxTaps && ct >= 4 && (size_t)H * W < (1u << 28)) {
+    const int cpg = C / num_deformable_group;
+    const int runs = (HWo + kDcnThreads - 1) / kDcnThreads;
+    // enough CTAs for ~3 waves: split the channels of a group when the pixel runs alone are too few
+    int slices = 1;
+    while (slices < 8 && (long long)B * num_deformable_group * runs * slices < 148 * 3 && cpg / (slices * 2) >= ct) slices *= 2;
+    const size_t smem = (size_t)2 * ct * chan_floats_max * sizeof(float);
+    SDET_CUDA(cudaFuncSetAttribute(deform_im2col_tiled_kernel<kDcnMaxTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)(B * num_deformable_group * runs * slices);
+    deform_im2col_tiled_kernel<kDcnMaxTaps><<<grid, kDcnThreads, smem, (cudaStream_t)stream>>>(data, offset, col, s, B, ct,
+                                                                                              slices, runs);
+    SDET_LAUNCH_CHECK("deform_im2col_tiled_kernel");
+    return SDET_OK;
+  }
   const size_t total = (size_t)B * C * s.Ho * s.Wo;
   deform_im2col_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(data, offset, col, s, B);
   SDET_LAUNCH_CHECK("deform_im2col_kernel");

@@ -354,6 +354,7 @@ class _ROIPoolingV1Fn(torch.autograd.Function):
         out, idx = roi_pooling_v1_raw(data, rois, (ph, pw), spatial_scale)
         ctx.save_for_backward(idx, rois)
         ctx.dshape = tuple(data.shape)
+        ctx.scale = float(spatial_scale)
         return out
 
     @staticmethod
@@ -364,7 +365,7 @@ class _ROIPoolingV1Fn(torch.autograd.Function):
         R, _, ph, pw = ograd.shape
         grad = torch.empty(ctx.dshape, device=ograd.device, dtype=torch.float32)
         check(_lib.lib().sdet_roi_pooling_v1_backward(_p(ograd), _p(idx), _p(rois), _p(grad), None, B,
-                                                      R, C, H, W, ph, pw, 0, _stream()))
+                                                      R, C, H, W, ph, pw, ctx.scale, 0, _stream()))
         return grad, None, None, None, None
 
 

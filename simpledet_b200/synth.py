@@ -41,3 +41,35 @@ def config1(seed: int = 0):
     wh = rng.uniform(8, 400, (1, 128, 2))
     rois = np.concatenate([xy, np.clip(xy + wh, 0, 799)], -1).astype(np.float32)
     return data, rois, (7, 7), 1.0 / 16
+
+
+def mask_scene(rng: np.random.Generator, B: int, R: int, G: int, PL: int):
+    """BASELINE config 4 inputs: rois (B,R,4) jittered around the gt boxes plus padding rows,
+    gt (B,G,5) with class -1 padding, gt_polys (B,G,PL) encoded [cls, nseg, len_1..len_n, xy...] padded with -1
+    (models/maskrcnn/input.py:166-175): 1-3 segments of 3-30 vertices per instance."""
+    gt = np.full((B, G, 5), -1, np.float32)
+    polys = np.full((B, G, PL), -1, np.float32)
+    rois = np.zeros((B, R, 4), np.float32)
+    for b in range(B):
+        k = int(rng.integers(2, G))
+        for j in range(k):
+            x1, y1 = rng.uniform(0, 500, 2)
+            w, h = rng.uniform(40, 300, 2)
+            gt[b, j] = [x1, y1, x1 + w, y1 + h, rng.integers(1, 81)]
+            nseg = int(rng.integers(1, 4))
+            row, coords = [float(gt[b, j, 4]), float(nseg)], []
+            for _ in range(nseg):
+                nv = int(rng.integers(3, 30))
+                ang = np.sort(rng.uniform(0, 2 * np.pi, nv))
+                rad = rng.uniform(0.15, 0.5, nv)
+                cx, cy = x1 + w * rng.uniform(0.3, 0.7), y1 + h * rng.uniform(0.3, 0.7)
+                xs, ys = cx + w * rad * np.cos(ang), cy + h * rad * np.sin(ang)
+                row.append(float(2 * nv))
+                coords += np.stack([xs, ys], 1).reshape(-1).tolist()
+            row += coords
+            polys[b, j, :len(row)] = row
+        m = R - 20
+        near = gt[b, rng.integers(0, k, m), :4] + rng.normal(0, 12, (m, 4))
+        near[:, 3] = np.maximum(near[:, 3], 1)
+        rois[b, :m] = near
+    return rois, gt, polys

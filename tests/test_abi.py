@@ -22,13 +22,14 @@ def built():
 def _declared():
     src = open(os.path.join(ROOT, "include", "simpledet_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(sdet_[a-z0-9_]+)\s*\(", src)))
+    # every sdet_* entry point plus `_nms`, the reference's own C symbol kept for compatibility (gpu_nms.hpp:1-2)
+    return sorted(set(re.findall(r"\b(sdet_[a-z0-9_]+|_nms)\s*\(", src)))
 
 
 def test_header_symbols_exported(built):
     out = subprocess.run(["nm", "-D", "--defined-only", built], capture_output=True, text=True,
                          check=True).stdout
-    exported = set(re.findall(r" T (sdet_[a-z0-9_]+)", out))
+    exported = set(re.findall(r" T (sdet_[a-z0-9_]+|_nms)\b", out))
     declared = _declared()
     assert declared, "header parse found no functions"
     missing = [s for s in declared if s not in exported]
@@ -81,7 +82,7 @@ def test_ctypes_arity_matches_header(built):
 
     src = open(os.path.join(ROOT, "include", "simpledet_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    decls = dict(re.findall(r"\b(sdet_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    decls = dict(re.findall(r"\b(sdet_[a-z0-9_]+|_nms)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
     assert set(decls) == set(_lib._SIGNATURES)
     for name, params in decls.items():
         params = params.strip()

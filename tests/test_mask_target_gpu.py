@@ -15,33 +15,7 @@ def _t(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
 
-def _scene(rng, B, R, G, PL):
-    gt = np.full((B, G, 5), -1, np.float32)
-    polys = np.full((B, G, PL), -1, np.float32)
-    rois = np.zeros((B, R, 4), np.float32)
-    for b in range(B):
-        k = int(rng.integers(2, G))
-        for j in range(k):
-            x1, y1 = rng.uniform(0, 500, 2)
-            w, h = rng.uniform(40, 300, 2)
-            gt[b, j] = [x1, y1, x1 + w, y1 + h, rng.integers(1, 81)]
-            nseg = int(rng.integers(1, 4))
-            row, coords = [float(gt[b, j, 4]), float(nseg)], []
-            for _ in range(nseg):
-                nv = int(rng.integers(3, 30))
-                ang = np.sort(rng.uniform(0, 2 * np.pi, nv))
-                rad = rng.uniform(0.15, 0.5, nv)
-                cx, cy = x1 + w * rng.uniform(0.3, 0.7), y1 + h * rng.uniform(0.3, 0.7)
-                xs, ys = cx + w * rad * np.cos(ang), cy + h * rad * np.sin(ang)
-                row.append(float(2 * nv))
-                coords += np.stack([xs, ys], 1).reshape(-1).tolist()
-            row += coords
-            polys[b, j, :len(row)] = row
-        m = R - 20
-        near = gt[b, rng.integers(0, k, m), :4] + rng.normal(0, 12, (m, 4))
-        near[:, 3] = np.maximum(near[:, 3], 1)
-        rois[b, :m] = near
-    return rois, gt, polys
+from simpledet_b200.synth import mask_scene as _scene  # noqa: E402
 
 
 @pytest.mark.parametrize("M", [14, 28])
