@@ -60,7 +60,9 @@ def main():
     ap.add_argument("--plan", type=int, default=1)
     ap.add_argument("--noflush", type=int, default=0)
     ap.add_argument("--sorted", type=int, default=0, help="1: rois pre-sorted by (level, y, x) on the host (locality probe)")
-    ap.add_argument("--path", type=int, default=0, help="0: automatic (band-stationary kernel), 1: per-roi kernel only")
+    ap.add_argument("--path", type=int, default=0, help="0: automatic, 1: per-roi kernel, 2: band-stationary, 3: channels-last "
+                    "(NCHW in, re-layout inside the call), 4: channels-last with NHWC features given (no re-layout)")
+    ap.add_argument("--same-roi", type=int, default=0, help="1: every roi is a copy of the first (cache-hit probe: compute-bound rate)")
     ap.add_argument("--backward", type=int, default=0, help="time the backward pass (incl. zero-fill of the grads)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -82,15 +84,22 @@ def main():
                 s_ = 2.0 ** (lvl + 2)
                 cells = (np.ceil(r[:, 2] / s_) - np.floor(r[:, 0] / s_) + 2) * (np.ceil(r[:, 3] / s_) - np.floor(r[:, 1] / s_) + 2)
                 rois_np[b] = r[np.argsort(-cells, kind="stable")]
+    if a.same_roi:
+        rois_np[:] = np.array([400, 300, 624, 524], np.float32)  # 224 px: level P4, 14 x 14 cells
     rois = torch.from_numpy(rois_np).to(dev)
     flush = torch.empty(128 * 1024 * 1024, device=dev)
     out, _, _, lv = ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=False)
     lv = lv.cpu().numpy()
     nbytes = algorithmic_bytes(rois_np, lv, shapes, C, pooled, synth.FPN_STRIDES, bool(a.argmax))
 
+    feats_cl = [f.permute(0, 2, 3, 1).contiguous() for f in feats] if a.path == 4 else None
+
     def fn():
-        ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=bool(a.argmax),
-                              use_plan=bool(a.plan), path=a.path)
+        if a.path == 4:
+            ops.fpn_roi_align_nhwc(feats_cl, rois, synth.FPN_STRIDES, pooled)
+        else:
+            ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=bool(a.argmax),
+                                  use_plan=bool(a.plan), path=a.path)
 
     if a.backward:
         import ctypes

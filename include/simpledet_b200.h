@@ -62,10 +62,12 @@ int sdet_roi_align_v2_forward(const float* data, const float* rois, float* out, 
                               int pooled_w, float spatial_scale, void* workspace,
                               size_t workspace_bytes, void* stream);
 /* Same operator with an explicit kernel choice (tests and A/B timing; results are bit-identical):
- *   path = 0  automatic: with a workspace and no argmax planes the band-stationary kernel (bulk-TMA
- *             staged feature bands, roi_align_band.cu) takes every roi it can and the per-roi kernel
- *             the rest;  path = 1  per-roi kernel only.
- *   path_used (host int, may be NULL): 0 inline per-roi, 1 planned per-roi, 2 band-stationary. */
+ *   path = 0  automatic;  1  per-roi kernel (roi_align.cu);  2  band-stationary kernel (bulk-TMA staged feature
+ *   bands, roi_align_band.cu) for every roi it can take, per-roi kernel for the rest;  3  channels-last kernel
+ *   (roi_align_cl.cu): the features are re-laid to NHWC in the scratch part of a workspace of
+ *   sdet_fpn_roi_align_v2_workspace() bytes, then gathered with warp = 64 channels of one output bin.
+ *   Automatic = 3 when the workspace is that large and no argmax planes are asked for, else 2, else 1.
+ *   path_used (host int, may be NULL): 0 inline per-roi, 1 planned per-roi, 2 band-stationary, 3 channels-last. */
 int sdet_roi_align_v2_forward_ex(const float* data, const float* rois, float* out, float* argmax_x,
                                  float* argmax_y, int B, int N, int C, int H, int W, int pooled_h,
                                  int pooled_w, float spatial_scale, void* workspace,
@@ -95,6 +97,16 @@ int sdet_fpn_roi_align_v2_forward(const float* const* feats, const int* H, const
                                   int32_t* levels_out, int B, int N, int C, int pooled_h,
                                   int pooled_w, int roi_canonical_scale, int roi_canonical_level,
                                   void* workspace, size_t workspace_bytes, void* stream);
+/* Workspace including the NHWC scratch of the channels-last path (H, W: HOST arrays of num_levels entries; the
+ * plain _contrib_ROIAlign_v2 is num_levels = 1). */
+size_t sdet_fpn_roi_align_v2_workspace(int B, int N, int C, const int* H, const int* W, int num_levels);
+/* Features already channels-last, feats_nhwc[l] = (B, H_l, W_l, C) device: no re-layout pass, inference only
+ * (no argmax planes).  workspace: sdet_roi_align_v2_workspace(B, N) bytes, required. */
+int sdet_fpn_roi_align_v2_forward_nhwc(const float* const* feats_nhwc, const int* H, const int* W,
+                                       const int* strides, int num_levels, const float* rois, float* out,
+                                       int32_t* levels_out, int B, int N, int C, int pooled_h, int pooled_w,
+                                       int roi_canonical_scale, int roi_canonical_level, void* workspace,
+                                       size_t workspace_bytes, void* stream);
 /* ... with the kernel choice of sdet_roi_align_v2_forward_ex. */
 int sdet_fpn_roi_align_v2_forward_ex(const float* const* feats, const int* H, const int* W,
                                      const int* strides, int num_levels, const float* rois,

@@ -86,6 +86,7 @@ template <typename DType> struct DataType;
 template <> struct DataType<float> { static const int kFlag = kFloat32; };
 template <> struct DataType<double> { static const int kFlag = kFloat64; };
 template <> struct DataType<int32_t> { static const int kFlag = kInt32; };
+template <> struct DataType<uint8_t> { static const int kFlag = kUint8; };
 namespace expr {}
 namespace red {
 namespace limits {
@@ -95,7 +96,13 @@ template <> MSHADOW_XINLINE double MinValue<double>() { return -DBL_MAX; }
 }  // namespace limits
 }  // namespace red
 
-template <typename Device> struct Stream {};
+}  // namespace mshadow
+struct CUstream_st;
+typedef CUstream_st* cudaStream_t;  // only the handle type: the shim never touches the CUDA runtime
+namespace mshadow {
+template <typename Device> struct Stream {
+  static cudaStream_t GetStream(Stream<Device>*) { return nullptr; }
+};
 
 template <int dimension>
 struct Shape {

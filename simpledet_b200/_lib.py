@@ -41,6 +41,9 @@ _SIGNATURES = {
     "sdet_fpn_roi_align_v2_forward_ex": [POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                          c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_int, _P, c_size_t, _P, c_int, POINTER(c_int)],
+    "sdet_fpn_roi_align_v2_workspace": [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), c_int],
+    "sdet_fpn_roi_align_v2_forward_nhwc": [POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_int), c_int, _P, _P, _P,
+                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P],
     "sdet_fpn_assign": [_P, c_int, POINTER(c_int), c_int, c_int, c_int, POINTER(_P), _P, _P],
     "sdet_fpn_roi_align_v2_backward": [_P, _P, _P, _P, POINTER(_P), POINTER(c_int), POINTER(c_int),
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
@@ -114,7 +117,7 @@ _SIGNATURES = {
 _RESTYPES = {"_nms": None, "sdet_last_error": c_char_p, "sdet_build_digest": c_char_p, "sdet_launch_count": c_uint64,
              "sdet_proposal_v3_workspace": c_size_t, "sdet_proposal_legacy_workspace": c_size_t,
              "sdet_gen_proposal_workspace": c_size_t, "sdet_anchor_target_workspace": c_size_t, "sdet_weighted_nms_workspace": c_size_t, "sdet_gen_proposal_retina_workspace": c_size_t, "sdet_proposal_v3_fpn_workspace": c_size_t, "sdet_contrib_nms_workspace": c_size_t,
-             "sdet_nms_workspace": c_size_t, "sdet_roi_align_v2_workspace": c_size_t, "sdet_multiclass_nms_workspace": c_size_t}
+             "sdet_nms_workspace": c_size_t, "sdet_roi_align_v2_workspace": c_size_t, "sdet_fpn_roi_align_v2_workspace": c_size_t, "sdet_multiclass_nms_workspace": c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

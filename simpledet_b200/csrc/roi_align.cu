@@ -612,9 +612,22 @@ size_t plan_workspace_bytes(int B, int N) {
   return per_roi_workspace_bytes(total) + band_workspace_bytes(total);
 }
 
-// mode: 0 = automatic (band-stationary kernel where it applies, per-roi kernel for the rest),
-//       1 = per-roi kernel only.  What ran is reported through sdet_roi_align_v2_last_path().
+// mode: 0 = automatic, 1 = per-roi kernel only, 2 = band-stationary kernel (+ per-roi leftovers),
+//       3 = channels-last kernel (features re-laid to NHWC in the scratch that follows the plan workspace).
+// g_last_path reports what ran: 0 inline per-roi, 1 planned per-roi, 2 band-stationary, 3 channels-last.
 thread_local int g_last_path = 0;
+
+int plan_and_order(const RoiAlignArgs& a, char* w, size_t total, PlanSched& sc, cudaStream_t st) {
+  sc.counts = reinterpret_cast<int*>(w + sizeof(PlanRecord) * total);
+  sc.slot = reinterpret_cast<int2*>(w + sizeof(PlanRecord) * total + 256);
+  sc.order = reinterpret_cast<int*>(w + sizeof(PlanRecord) * total + 256 + 8 * total);
+  SDET_CUDA(cudaMemsetAsync(sc.counts, 0, sizeof(int) * kCostBuckets, st));
+  roi_align_plan_kernel<<<(unsigned)total, 64, 0, st>>>(a, reinterpret_cast<PlanRecord*>(w), sc);
+  SDET_LAUNCH_CHECK("roi_align_plan_kernel");
+  roi_align_order_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sc, (int)total);
+  SDET_LAUNCH_CHECK("roi_align_order_kernel");
+  return SDET_OK;
+}
 
 int launch_fwd(RoiAlignArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st, int mode = 0) {
   if ((a.argx == nullptr) != (a.argy == nullptr))
@@ -633,8 +646,26 @@ int launch_fwd(RoiAlignArgs& a, void* workspace, size_t workspace_bytes, cudaStr
     if (reinterpret_cast<uintptr_t>(workspace) % 16)
       return sdet::fail(SDET_ERR_INVALID_ARG, "workspace must be 16-byte aligned");
     char* w = static_cast<char*>(workspace);
+    // channels-last: needs the NHWC scratch behind the plan/band sections, no argmax planes, an even channel count
+    {
+      int Hs[SDET_MAX_LEVELS], Ws[SDET_MAX_LEVELS];
+      for (int l = 0; l < a.num_levels; ++l) { Hs[l] = a.lvl[l].H; Ws[l] = a.lvl[l].W; }
+      const size_t scratch = cl_scratch_bytes(a.B, a.C, Hs, Ws, a.num_levels);
+      const bool cl_ok = a.argx == nullptr && (a.C & 1) == 0 && workspace_bytes >= need + scratch;
+      if (mode == 3 && !cl_ok)
+        return sdet::fail(SDET_ERR_WORKSPACE, "channels-last path: needs no argmax planes, even C and a workspace of "
+                          "sdet_fpn_roi_align_v2_workspace() = %zu bytes", need + scratch);
+      if (cl_ok && (mode == 3 || mode == 0)) {
+        PlanSched sc{};
+        if (int rc = plan_and_order(a, w, total, sc, st)) return rc;
+        RoiAlignArgs t = a;  // levels re-pointed at the NHWC copies
+        if (int rc = cl_transpose(t, w + need, st)) return rc;
+        g_last_path = 3;
+        return cl_launch(t, static_cast<const PlanRecord*>(workspace), sc.order, st);
+      }
+    }
     BandArgs ba{};
-    if (mode == 0 && band_setup(a, w + per_roi_workspace_bytes(total), ba)) {
+    if ((mode == 0 || mode == 2) && band_setup(a, w + per_roi_workspace_bytes(total), ba)) {
       if (int rc = band_launch(a, ba, static_cast<PlanRecord*>(workspace), st)) return rc;
       g_last_path = 2;
       a.plans = workspace;
@@ -643,14 +674,7 @@ int launch_fwd(RoiAlignArgs& a, void* workspace, size_t workspace_bytes, cudaStr
       return launch_per_roi(a, total_i, st);  // CTAs beyond the leftover count exit at once
     }
     PlanSched sc{};
-    sc.counts = reinterpret_cast<int*>(w + sizeof(PlanRecord) * total);
-    sc.slot = reinterpret_cast<int2*>(w + sizeof(PlanRecord) * total + 256);
-    sc.order = reinterpret_cast<int*>(w + sizeof(PlanRecord) * total + 256 + 8 * total);
-    SDET_CUDA(cudaMemsetAsync(sc.counts, 0, sizeof(int) * kCostBuckets, st));
-    roi_align_plan_kernel<<<(unsigned)total, 64, 0, st>>>(a, static_cast<PlanRecord*>(workspace), sc);
-    SDET_LAUNCH_CHECK("roi_align_plan_kernel");
-    roi_align_order_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sc, (int)total);
-    SDET_LAUNCH_CHECK("roi_align_order_kernel");
+    if (int rc = plan_and_order(a, w, total, sc, st)) return rc;
     a.plans = workspace;
     a.order = sc.order;
     g_last_path = 1;
@@ -687,7 +711,7 @@ extern "C" int sdet_roi_align_v2_forward_ex(const float* data, const float* rois
   a.argy = argmax_y;
   a.levels_out = nullptr;
   a.B = B; a.N = N; a.C = C; a.PH = pooled_h; a.PW = pooled_w;
-  SDET_REQUIRE(path == 0 || path == 1, "path must be 0 (automatic) or 1 (per-roi kernel only)");
+  SDET_REQUIRE(path >= 0 && path <= 3, "path must be 0 (automatic), 1 (per-roi), 2 (band-stationary) or 3 (channels-last)");
   const int rc = launch_fwd(a, workspace, workspace_bytes, (cudaStream_t)stream, path);
   if (path_used) *path_used = g_last_path;
   return rc;
@@ -745,10 +769,56 @@ extern "C" int sdet_fpn_roi_align_v2_forward_ex(const float* const* feats, const
   a.argy = argmax_y;
   a.levels_out = levels_out;
   a.B = B; a.N = N; a.C = C; a.PH = pooled_h; a.PW = pooled_w;
-  SDET_REQUIRE(path == 0 || path == 1, "path must be 0 (automatic) or 1 (per-roi kernel only)");
+  SDET_REQUIRE(path >= 0 && path <= 3, "path must be 0 (automatic), 1 (per-roi), 2 (band-stationary) or 3 (channels-last)");
   const int rc = launch_fwd(a, workspace, workspace_bytes, (cudaStream_t)stream, path);
   if (path_used) *path_used = g_last_path;
   return rc;
+}
+
+// Workspace that also holds the NHWC re-layout of the feature maps (enables the channels-last kernel).
+extern "C" size_t sdet_fpn_roi_align_v2_workspace(int B, int N, int C, const int* H, const int* W, int num_levels) {
+  if (B <= 0 || N <= 0 || C <= 0 || !H || !W || num_levels < 1 || num_levels > SDET_MAX_LEVELS) return 0;
+  return plan_workspace_bytes(B, N) + cl_scratch_bytes(B, C, H, W, num_levels);
+}
+
+// Features already channels-last (B, H_l, W_l, C): no re-layout pass.  workspace >= sdet_roi_align_v2_workspace(B, N).
+extern "C" int sdet_fpn_roi_align_v2_forward_nhwc(const float* const* feats_nhwc, const int* H, const int* W,
+                                                  const int* strides, int num_levels, const float* rois, float* out,
+                                                  int32_t* levels_out, int B, int N, int C, int pooled_h, int pooled_w,
+                                                  int roi_canonical_scale, int roi_canonical_level, void* workspace,
+                                                  size_t workspace_bytes, void* stream) {
+  if (int rc = check_common(B, N, C, pooled_h, pooled_w)) return rc;
+  SDET_REQUIRE(feats_nhwc && H && W && strides && rois && out && workspace, "NULL argument");
+  SDET_REQUIRE(num_levels >= 1 && num_levels <= SDET_MAX_LEVELS, "num_levels must be in [1, %d]", SDET_MAX_LEVELS);
+  SDET_REQUIRE(roi_canonical_scale > 0, "roi_canonical_scale must be > 0");
+  SDET_REQUIRE(pooled_h <= 16 && pooled_w <= 16 && (C & 1) == 0, "channels-last path: pooled_size <= 16, even C");
+  RoiAlignArgs a{};
+  int smin = INT_MAX, smax = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    const int lg = ilog2_exact(strides[l]);
+    if (lg < 0) return sdet::fail(SDET_ERR_UNSUPPORTED, "stride %d is not a power of two", strides[l]);
+    SDET_REQUIRE(feats_nhwc[l] && H[l] > 0 && W[l] > 0, "level %d: bad feature pointer / shape", l);
+    SDET_REQUIRE((reinterpret_cast<uintptr_t>(feats_nhwc[l]) & 7) == 0, "level %d: features must be 8-byte aligned", l);
+    a.lvl[l] = Level{feats_nhwc[l], nullptr, H[l], W[l], 1.0f / (float)strides[l], lg};
+    smin = strides[l] < smin ? strides[l] : smin;
+    smax = strides[l] > smax ? strides[l] : smax;
+  }
+  a.num_levels = num_levels;
+  a.fpn = num_levels > 1 ? 1 : 0;
+  a.scale0 = (float)roi_canonical_scale;
+  a.lvl0 = (float)roi_canonical_level;
+  a.k_min = (float)ilog2_exact(smin);
+  a.k_max = (float)ilog2_exact(smax);
+  a.rois = rois; a.out = out; a.levels_out = levels_out;
+  a.B = B; a.N = N; a.C = C; a.PH = pooled_h; a.PW = pooled_w;
+  a.negzero2 = 0x8000000080000000ull;
+  const size_t total = (size_t)B * N;
+  if (workspace_bytes < per_roi_workspace_bytes(total))
+    return sdet::fail(SDET_ERR_WORKSPACE, "workspace too small: need %zu bytes", per_roi_workspace_bytes(total));
+  SDET_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "workspace must be 16-byte aligned");
+  PlanSched sc{};
+  if (int rc = plan_and_order(a, static_cast<char*>(workspace), total, sc, (cudaStream_t)stream)) return rc;
+  return cl_launch(a, static_cast<const PlanRecord*>(workspace), sc.order, (cudaStream_t)stream);
 }
 
 extern "C" int sdet_fpn_roi_align_v2_forward(const float* const* feats, const int* H, const int* W,

@@ -32,14 +32,16 @@ namespace sdet_ra {
 
 namespace {
 
+// A/B knobs (measured, profiles/r02_band_ab.txt): 15 consumer warps with 4-channel jobs is the best point -
+// 8-channel jobs need 236 registers (spills at any useful warp count), 11 warps lose 16 % to latency.
 #ifndef SDET_BAND_CONSUMERS
-#define SDET_BAND_CONSUMERS 11
+#define SDET_BAND_CONSUMERS 15
 #endif
 #ifndef SDET_BAND_CL8
-#define SDET_BAND_CL8 1
+#define SDET_BAND_CL8 0
 #endif
 constexpr int kBandConsumers = SDET_BAND_CONSUMERS;      // consumer warps; warp 0 is the producer
-constexpr int kBandThreads = 32 * (kBandConsumers + 1);  // 12 warps: 168 registers per thread for the 8-channel jobs
+constexpr int kBandThreads = 32 * (kBandConsumers + 1);
 constexpr int kStageBytes = kBandStageFloats * 4;
 
 struct StageDesc {   // 64 bytes, written by the producer before it arms the stage's `full` barrier

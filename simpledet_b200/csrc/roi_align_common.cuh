@@ -118,7 +118,7 @@ __device__ __forceinline__ float bilinear_ref(float wtl, float wbl, float wtr, f
 
 // One output element by the reference's own loop (no tables).  Only used when a bin has more
 // samples than the tables hold — unreachable for finite rois on maps narrower than 2^17 px.
-__device__ inline void element_direct(const float* __restrict__ plane, int H, int W, int PH, int PW, int ph,
+__device__ inline void element_direct_strided(const float* __restrict__ plane, const int pstride, int H, int W, int PH, int PW, int ph,
                                int pw, float rsw, float rsh, float rew, float reh, float& best,
                                float& bx, float& by) {
   const float bh = __fdiv_rn(__fsub_rn(reh, rsh), (float)PH);
@@ -144,8 +144,8 @@ __device__ inline void element_direct(const float* __restrict__ plane, int H, in
       float be = (wl == wr) ? 0.5f : __fdiv_rn(__fsub_rn(w, (float)wl), (float)(wr - wl));
       float a0 = __fsub_rn(1.f, al), b0 = __fsub_rn(1.f, be);
       float v = bilinear_ref(__fmul_rn(a0, b0), __fmul_rn(al, b0), __fmul_rn(a0, be),
-                             __fmul_rn(al, be), plane[hl * W + wl], plane[hh * W + wl],
-                             plane[hl * W + wr], plane[hh * W + wr]);
+                             __fmul_rn(al, be), plane[(size_t)(hl * W + wl) * pstride], plane[(size_t)(hh * W + wl) * pstride],
+                             plane[(size_t)(hl * W + wr) * pstride], plane[(size_t)(hh * W + wr) * pstride]);
       if (v > best) {
         best = v;
         bx = w;
@@ -154,6 +154,12 @@ __device__ inline void element_direct(const float* __restrict__ plane, int H, in
       if (++guard > (1 << 20)) return;
     }
   }
+}
+
+__device__ inline void element_direct(const float* __restrict__ plane, int H, int W, int PH, int PW, int ph,
+                               int pw, float rsw, float rsh, float rew, float reh, float& best,
+                               float& bx, float& by) {
+  element_direct_strided(plane, 1, H, W, PH, PW, ph, pw, rsw, rsh, rew, reh, best, bx, by);
 }
 
 struct HRow {   // per h-sample, 16 bytes, read with one LDS.128
@@ -348,5 +354,9 @@ struct BandArgs {
 size_t band_workspace_bytes(size_t total_rois);
 bool band_setup(const RoiAlignArgs& a, void* ws, BandArgs& ba);
 int band_launch(const RoiAlignArgs& a, const BandArgs& ba, PlanRecord* plans, cudaStream_t st);
+// channels-last path (roi_align_cl.cu)
+size_t cl_scratch_bytes(int B, int C, const int* H, const int* W, int num_levels);
+int cl_transpose(RoiAlignArgs& a, void* scratch, cudaStream_t st);
+int cl_launch(const RoiAlignArgs& a, const PlanRecord* plans, const int* order, cudaStream_t st);
 
 }  // namespace sdet_ra

@@ -1,0 +1,471 @@
+"""Shape inference and torch execution of façade graphs.
+
+Generic NN operators run as library calls (torch -> cuDNN / cuBLAS: the tensor-core part of the model, not this
+repository's product); detection operators are dispatched BY THE REFERENCE'S REGISTRATION STRING to
+`simpledet_b200.ops.OPS`, i.e. to the C ABI.  Parameters the caller did not supply are zero-initialised, which is what
+`detection_infer_speed.py` times (`mod.set_params({}, {}, True)`, core/detection_module.py:374-383)."""
+from __future__ import annotations
+
+import ast
+import math
+
+from . import symbol as S
+
+
+def _t(v):
+    if isinstance(v, str):
+        try:
+            return ast.literal_eval(v)
+        except (ValueError, SyntaxError):
+            return v
+    return v
+
+
+def _tup(v, n=2):
+    v = _t(v)
+    return tuple(int(x) for x in v) if isinstance(v, (tuple, list)) else (int(v),) * n
+
+
+def _b(v):
+    return _t(v) in (True, 1, "True", "true")
+
+
+def mx_reshape(shape, target):
+    """MXNet Reshape with the special codes 0 (copy), -1 (infer), -2 (copy the rest), -3 (merge two), -4 (split)."""
+    shape, target = list(shape), list(_t(target))
+    out, i, j, infer = [], 0, 0, None
+    while j < len(target):
+        t = target[j]
+        if t == 0:
+            out.append(shape[i]); i += 1
+        elif t == -1:
+            infer = len(out); out.append(-1); i += 1
+        elif t == -2:
+            out.extend(shape[i:]); i = len(shape)
+        elif t == -3:
+            out.append(shape[i] * shape[i + 1]); i += 2
+        elif t == -4:
+            a, b = target[j + 1], target[j + 2]
+            if a == -1:
+                a = shape[i] // b
+            if b == -1:
+                b = shape[i] // a
+            out.extend([a, b]); i += 1; j += 2
+        else:
+            out.append(t); i += 1
+        j += 1
+    if infer is not None:
+        total = math.prod(shape)
+        known = math.prod(x for x in out if x != -1)
+        out[infer] = total // max(known, 1)
+    return tuple(out)
+
+
+def _conv_out(x, k, s, p, d):
+    return (x + 2 * p - (d * (k - 1) + 1)) // s + 1
+
+
+# ------------------------------------------------------------------------------------------------
+# shape rules: fn(attrs, in_shapes: list[tuple|None], arg_names) -> (in_shapes completed, out_shapes)
+# ------------------------------------------------------------------------------------------------
+def _shape_conv(a, ins, names):
+    x = ins[0]
+    k, s, p, d = _tup(a["kernel"]), _tup(a.get("stride", 1)), _tup(a.get("pad", 0)), _tup(a.get("dilate", 1))
+    nf, g = int(_t(a["num_filter"])), int(_t(a.get("num_group", 1)))
+    ins = list(ins)
+    for i, n in enumerate(names):
+        if n == "weight":
+            ins[i] = (nf, x[1] // g, k[0], k[1])
+        elif n == "bias":
+            ins[i] = (nf,)
+    return ins, [(x[0], nf, _conv_out(x[2], k[0], s[0], p[0], d[0]), _conv_out(x[3], k[1], s[1], p[1], d[1]))]
+
+
+def _shape_fc(a, ins, names):
+    x = ins[0]
+    nh = int(_t(a["num_hidden"]))
+    flat = _b(a.get("flatten", True))
+    k = math.prod(x[1:]) if flat else x[-1]
+    ins = list(ins)
+    for i, n in enumerate(names):
+        if n == "weight":
+            ins[i] = (nh, k)
+        elif n == "bias":
+            ins[i] = (nh,)
+    return ins, [(x[0], nh) if flat else tuple(x[:-1]) + (nh,)]
+
+
+def _shape_bn(a, ins, names):
+    c = ins[0][1]
+    return [ins[0]] + [(c,)] * (len(ins) - 1), [ins[0]]
+
+
+def _shape_pool(a, ins, names):
+    x = ins[0]
+    if _b(a.get("global_pool", False)):
+        return ins, [(x[0], x[1], 1, 1)]
+    k, s, p = _tup(a["kernel"]), _tup(a.get("stride", 1)), _tup(a.get("pad", 0))
+    full = str(a.get("pooling_convention", "valid")) == "full"
+    def o(n, kk, ss, pp):
+        v = (n + 2 * pp - kk)
+        return (-(-v // ss) if full else v // ss) + 1
+    return ins, [(x[0], x[1], o(x[2], k[0], s[0], p[0]), o(x[3], k[1], s[1], p[1]))]
+
+
+def _same(a, ins, names):
+    return ins, [ins[0]]
+
+
+def _shape_concat(a, ins, names):
+    d = int(_t(a.get("dim", 1)))
+    out = list(ins[0])
+    out[d] = sum(s[d] for s in ins)
+    return ins, [tuple(out)]
+
+
+def _shape_upsample(a, ins, names):
+    x, sc = ins[0], int(_t(a["scale"]))
+    return ins, [(x[0], x[1], x[2] * sc, x[3] * sc)]
+
+
+def _shape_slice_like(a, ins, names):
+    axes = _t(a.get("axes", ()))
+    out = list(ins[0])
+    for ax in (axes if axes else range(len(out))):
+        out[ax] = ins[1][ax]
+    return ins, [tuple(out)]
+
+
+def _shape_slice_axis(a, ins, names):
+    ax, b, e = int(_t(a["axis"])), int(_t(a["begin"])), _t(a["end"])
+    out = list(ins[0])
+    e = out[ax] if e in (None, "None") else int(e)
+    if e < 0:
+        e += out[ax]
+    out[ax] = e - b
+    return ins, [tuple(out)]
+
+
+def _shape_proposal(a, ins, names):
+    B = ins[0][0]
+    post = int(_t(a.get("rpn_post_nms_top_n", 300)))
+    return ins, [(B, post, 4), (B, post, 1)]
+
+
+def _shape_roialign(a, ins, names):
+    d, r = ins[0], ins[1]
+    ph, pw = _tup(a["pooled_size"])
+    s = (r[0], r[1], d[1], ph, pw)
+    return ins, [s, s, s]
+
+
+def _shape_decode(a, ins, names):
+    r, d = ins[0], ins[1]
+    return ins, [(r[0], r[1], 4) if _b(a.get("class_agnostic", True)) else tuple(d)]
+
+
+def _shape_custom(a, ins, names):
+    t = a.get("op_type")
+    if t == "get_top_proposal":
+        B, n = ins[0][0], int(_t(a["top_n"]))
+        return ins, [(B, n, 4), (B, n, 1)]
+    if t == "assign_layer_fpn":
+        return ins, [ins[0]] * len(_t(a["rcnn_stride"]))
+    if t == "BboxPostProcessing":
+        B, m = ins[0][0], int(_t(a["max_det_per_image"]))
+        return ins, [(B, m, 1), (B, m, 4), (B, m, 1)]
+    raise NotImplementedError(f"Custom op_type {t!r}")
+
+
+SHAPE_RULES = {
+    "Convolution": _shape_conv, "FullyConnected": _shape_fc, "BatchNorm": _shape_bn, "Pooling": _shape_pool,
+    "Activation": _same, "relu": _same, "Cast": _same, "BlockGrad": _same, "softmax": _same, "SoftmaxActivation": _same,
+    "SoftmaxOutput": _same, "Dropout": _same, "MakeLoss": _same, "smooth_l1": _same, "identity": _same,
+    "_plus_scalar": _same, "_minus_scalar": _same, "_mul_scalar": _same, "_div_scalar": _same,
+    "elemwise_add": _same, "elemwise_sub": _same, "elemwise_mul": _same, "elemwise_div": _same, "add_n": _same,
+    "broadcast_add": _same, "broadcast_mul": _same,
+    "Concat": _shape_concat, "UpSampling": _shape_upsample, "slice_like": _shape_slice_like, "slice_axis": _shape_slice_axis,
+    "Reshape": lambda a, ins, n: (ins, [mx_reshape(ins[0], a["shape"])]),
+    "Flatten": lambda a, ins, n: (ins, [(ins[0][0], math.prod(ins[0][1:]))]),
+    "_contrib_Proposal_v3": _shape_proposal, "_contrib_Proposal": _shape_proposal,
+    "_contrib_ROIAlign_v2": _shape_roialign, "_contrib_DecodeBBox": _shape_decode, "Custom": _shape_custom,
+}
+
+
+def infer_shapes(sym: S.Symbol, known: dict):
+    """mx Symbol.infer_shape: (arg_shapes, out_shapes, aux_shapes) in list_arguments / list_outputs / aux order."""
+    shapes: dict[int, list] = {}
+    var_shape: dict[str, tuple] = {k: tuple(v) for k, v in known.items()}
+    for node in sym._topo():
+        if node.op is None:
+            s = var_shape.get(node.name) or node.attrs.get("__shape__")
+            shapes[id(node)] = [tuple(s) if s is not None else None]
+            continue
+        ins = [shapes[id(n)][i] for s_ in node.inputs for n, i in s_.entries]
+        names = _flat_names(node)
+        rule = SHAPE_RULES.get(node.op)
+        if rule is None:
+            raise NotImplementedError(f"shape rule for operator {node.op!r} ({node.name})")
+        ins2, outs = rule(node.attrs, ins, names)
+        k = 0
+        for s_ in node.inputs:
+            for n, i in s_.entries:
+                if n.op is None and shapes[id(n)][0] is None and ins2[k] is not None:
+                    shapes[id(n)][0] = tuple(ins2[k])
+                    var_shape[n.name] = tuple(ins2[k])
+                k += 1
+        shapes[id(node)] = [tuple(o) for o in outs]
+    args = [var_shape.get(n) for n in sym.list_arguments()]
+    aux = [var_shape.get(n) for n in sym.list_auxiliary_states()]
+    outs = [shapes[id(n)][i] for n, i in sym.entries]
+    return args, outs, aux
+
+
+def _flat_names(node):
+    names = []
+    k = 0
+    for s_ in node.inputs:
+        for _ in s_.entries:
+            names.append(node.arg_names[k] if k < len(node.arg_names) else None)
+        k += 1
+    return names
+
+
+# ------------------------------------------------------------------------------------------------
+# execution
+# ------------------------------------------------------------------------------------------------
+class Executor:
+    """Evaluates a façade Symbol with torch on one device.  `channels_last=True` keeps 4-D activations in torch's
+    channels_last memory format (what the tensor-core convolutions prefer) and hands the FPN levels to the fused
+    RoIAlign as NHWC - no re-layout pass."""
+
+    def __init__(self, sym: S.Symbol, device="cuda:0", channels_last=True, fuse_fpn_roi_align=True):
+        import torch
+
+        self.sym, self.device = sym, torch.device(device)
+        self.channels_last, self.fuse = channels_last, fuse_fpn_roi_align
+        self.params: dict = {}
+        self.order = sym._topo()
+        self._fusions = self._find_fpn_roi_align() if fuse_fpn_roi_align else {}
+
+    # ---- parameters
+    def init_params(self, input_shapes: dict, arg_params=None, aux_params=None, rng_std=None):
+        """Zero-initialise every parameter the caller did not give (detection_infer_speed.py's setting); `rng_std`
+        draws N(0, rng_std) weights instead (BatchNorm: gamma 1, var 1)."""
+        import torch
+
+        args, _, aux = infer_shapes(self.sym, input_shapes)
+        given = dict(arg_params or {})
+        given.update(aux_params or {})
+        g = torch.Generator(device=self.device).manual_seed(0)
+        for name, shp in list(zip(self.sym.list_arguments(), args)) + list(zip(self.sym.list_auxiliary_states(), aux)):
+            if name in input_shapes:
+                continue
+            if name in given:
+                v = given[name]
+                v = v.t if hasattr(v, "t") and not callable(v.t) else torch.as_tensor(v)
+                self.params[name] = v.to(self.device, torch.float32)
+            elif shp is None:
+                raise ValueError(f"cannot infer the shape of parameter {name}")
+            elif rng_std is None:
+                self.params[name] = torch.zeros(shp, device=self.device)
+            elif name.endswith(("gamma", "moving_var")):
+                self.params[name] = torch.ones(shp, device=self.device)
+            elif name.endswith(("beta", "moving_mean", "bias")):
+                self.params[name] = torch.zeros(shp, device=self.device)
+            else:
+                self.params[name] = torch.randn(shp, device=self.device, generator=g) * rng_std
+        return self
+
+    # ---- pattern: assign_layer_fpn -> L x ROIAlign_v2 -> add_n  ==> one fused FPN RoIAlign
+    def _find_fpn_roi_align(self):
+        fus = {}
+        for node in self.order:
+            if node.op != "add_n":
+                continue
+            ins = [e for s_ in node.inputs for e in s_.entries]
+            # models/FPN/builder.py:588-605 reshapes every level's (B,N,C,ph,pw) result with (-3,-2) before the add_n
+            reshape = None
+            if ins and all(n.op == "Reshape" and len(n.inputs) == 1 for n, _ in ins):
+                shp = {str(_t(n.attrs["shape"])) for n, _ in ins}
+                if len(shp) == 1:
+                    reshape = _t(ins[0][0].attrs["shape"])
+                    self._skipped_reshapes = getattr(self, "_skipped_reshapes", set()) | {id(n) for n, _ in ins}
+                    ins = [n.inputs[0].entries[0] for n, _ in ins]
+            if not ins or any(n.op != "_contrib_ROIAlign_v2" or i != 0 for n, i in ins):
+                continue
+            ras = [n for n, _ in ins]
+            roi_srcs = [ra.inputs[1].entries[0] for ra in ras]
+            asg = roi_srcs[0][0]
+            if asg.op != "Custom" or asg.attrs.get("op_type") != "assign_layer_fpn":
+                continue
+            if any(n is not asg for n, _ in roi_srcs) or sorted(i for _, i in roi_srcs) != list(range(len(ras))):
+                continue
+            fus[id(node)] = (asg, ras, reshape)
+        return fus
+
+    def forward(self, **inputs):
+        import torch
+
+        from .. import ops
+
+        vals: dict[int, list] = {}
+        for node in self.order:
+            if node.op is None:
+                if node.name in inputs:
+                    v = inputs[node.name]
+                    v = v.t if hasattr(v, "t") and not callable(getattr(v, "t")) else torch.as_tensor(v)
+                    vals[id(node)] = [v.to(self.device, torch.float32)]
+                elif node.name in self.params:
+                    vals[id(node)] = [self.params[node.name]]
+                else:
+                    raise KeyError(f"no value for variable {node.name}")
+                continue
+            if id(node) in self._fusions:
+                asg, ras, reshape = self._fusions[id(node)]
+                rois = vals[id(asg.inputs[0].entries[0][0])][asg.inputs[0].entries[0][1]]
+                strides = [int(s) for s in _t(asg.attrs["rcnn_stride"])]
+                feats = []
+                for k in range(len(ras)):
+                    ra = next(r for r in ras if r.inputs[1].entries[0][1] == k)
+                    fn, fi = ra.inputs[0].entries[0]
+                    feats.append(vals[id(fn)][fi])
+                ph, pw = _tup(ras[0].attrs["pooled_size"])
+                scale0, lvl0 = int(_t(asg.attrs["roi_canonical_scale"])), int(_t(asg.attrs["roi_canonical_level"]))
+                if self.channels_last and all(f.is_contiguous(memory_format=torch.channels_last) for f in feats):
+                    out, _ = ops.fpn_roi_align_nhwc([f.permute(0, 2, 3, 1) for f in feats], rois.contiguous(), strides,
+                                                    (ph, pw), scale0, lvl0)
+                else:
+                    out = ops.fpn_roi_align_raw([f.contiguous() for f in feats], rois.contiguous(), strides, (ph, pw),
+                                                scale0, lvl0, with_argmax=False)[0]
+                if reshape is not None:
+                    out = out.reshape(mx_reshape(tuple(out.shape), reshape))
+                vals[id(node)] = [out]
+                continue
+            if node.op in ("_contrib_ROIAlign_v2",) and self._is_fused_member(node):
+                continue
+            if node.op == "Reshape" and id(node) in getattr(self, "_skipped_reshapes", ()) and self._feeds_fused(node):
+                continue
+            if node.op == "Custom" and node.attrs.get("op_type") == "assign_layer_fpn" and self._only_feeds_fusion(node):
+                continue
+            ins = [vals[id(n)][i] for s_ in node.inputs for n, i in s_.entries]
+            vals[id(node)] = self._run(node, ins, ops, torch)
+        return [vals[id(n)][i] for n, i in self.sym.entries]
+
+    def _is_fused_member(self, node):
+        return any(node in ras for _, ras, _r in self._fusions.values())
+
+    def _feeds_fused(self, node):
+        src = node.inputs[0].entries[0][0]
+        return self._is_fused_member(src)
+
+    def _only_feeds_fusion(self, node):
+        return any(asg is node for asg, _, _r in self._fusions.values())
+
+    def _run(self, node, x, ops, torch):
+        F = torch.nn.functional
+        a, op = node.attrs, node.op
+        names = _flat_names(node)
+        arg = {n: v for n, v in zip(names, x) if n}
+        if op == "Convolution":
+            data = arg.get("data", x[0])
+            if self.channels_last and data.dim() == 4:
+                data = data.contiguous(memory_format=torch.channels_last)
+            return [F.conv2d(data, arg["weight"], arg.get("bias"), _tup(a.get("stride", 1)), _tup(a.get("pad", 0)),
+                             _tup(a.get("dilate", 1)), int(_t(a.get("num_group", 1))))]
+        if op == "FullyConnected":
+            data = arg.get("data", x[0])
+            if _b(a.get("flatten", True)):
+                data = data.reshape(data.shape[0], -1)
+            return [F.linear(data, arg["weight"], arg.get("bias"))]
+        if op == "BatchNorm":  # inference form (use_global_stats / is_train=False): moving statistics
+            data = arg.get("data", x[0])
+            g = torch.ones_like(arg["gamma"]) if _b(a.get("fix_gamma", True)) else arg["gamma"]
+            return [F.batch_norm(data, arg["moving_mean"], arg["moving_var"], g, arg["beta"], False, 0.0,
+                                 float(_t(a.get("eps", 1e-3))))]
+        if op in ("Activation", "relu"):
+            t = str(a.get("act_type", "relu"))
+            return [{"relu": F.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh}[t](x[0])]
+        if op == "Pooling":
+            if _b(a.get("global_pool", False)):
+                return [x[0].mean((2, 3), keepdim=True) if str(a.get("pool_type", "max")) == "avg" else x[0].amax((2, 3), keepdim=True)]
+            k, s, p = _tup(a["kernel"]), _tup(a.get("stride", 1)), _tup(a.get("pad", 0))
+            ceil = str(a.get("pooling_convention", "valid")) == "full"
+            if str(a.get("pool_type", "max")) == "max":
+                return [F.max_pool2d(x[0], k, s, p, ceil_mode=ceil)]
+            return [F.avg_pool2d(x[0], k, s, p, ceil_mode=ceil)]
+        if op in ("Cast", "BlockGrad", "identity", "Dropout", "MakeLoss"):
+            return [x[0]]
+        if op == "UpSampling":
+            sc = int(_t(a["scale"]))
+            return [F.interpolate(x[0], scale_factor=sc, mode="nearest")]
+        if op == "slice_like":
+            axes = _t(a.get("axes", ())) or range(x[0].dim())
+            sl = [slice(None)] * x[0].dim()
+            for ax in axes:
+                sl[ax] = slice(0, x[1].shape[ax])
+            return [x[0][tuple(sl)]]
+        if op == "slice_axis":
+            ax, b = int(_t(a["axis"])), int(_t(a["begin"]))
+            e = _t(a["end"])
+            sl = [slice(None)] * x[0].dim()
+            sl[ax] = slice(b, None if e in (None, "None") else int(e))
+            return [x[0][tuple(sl)]]
+        if op in ("add_n", "elemwise_add", "broadcast_add"):
+            out = x[0]
+            for v in x[1:]:
+                out = out + v
+            return [out]
+        if op in ("elemwise_sub",):
+            return [x[0] - x[1]]
+        if op in ("elemwise_mul", "broadcast_mul"):
+            return [x[0] * x[1]]
+        if op == "elemwise_div":
+            return [x[0] / x[1]]
+        if op.endswith("_scalar"):
+            s, rev = float(a["scalar"]), bool(a.get("__rev__", False))
+            return [{"_plus_scalar": lambda v: v + s, "_mul_scalar": lambda v: v * s,
+                     "_minus_scalar": lambda v: (s - v) if rev else (v - s),
+                     "_div_scalar": lambda v: (s / v) if rev else (v / s)}[op](x[0])]
+        if op == "Concat":
+            return [torch.cat(x, int(_t(a.get("dim", 1))))]
+        if op == "Reshape":
+            return [x[0].reshape(mx_reshape(tuple(x[0].shape), a["shape"]))]
+        if op == "Flatten":
+            return [x[0].reshape(x[0].shape[0], -1)]
+        if op == "softmax":
+            return [torch.softmax(x[0], int(_t(a.get("axis", -1))))]
+        if op == "SoftmaxActivation":
+            return [torch.softmax(x[0], 1 if str(a.get("mode", "instance")) == "channel" else -1)]
+        if op == "SoftmaxOutput":
+            return [torch.softmax(x[0], 1 if _b(a.get("multi_output", False)) else -1)]
+        # ---- detection operators: by registration string, through the C ABI
+        if op == "_contrib_Proposal_v3":
+            r = ops.OPS[op](arg["cls_prob"].contiguous(), arg["bbox_pred"].contiguous(), arg["im_info"].contiguous(),
+                            rpn_pre_nms_top_n=int(_t(a.get("rpn_pre_nms_top_n", 6000))),
+                            rpn_post_nms_top_n=int(_t(a.get("rpn_post_nms_top_n", 300))),
+                            threshold=float(_t(a.get("threshold", 0.7))), rpn_min_size=int(_t(a.get("rpn_min_size", 16))),
+                            scales=tuple(float(s) for s in _t(a.get("scales", (4, 8, 16, 32)))),
+                            ratios=tuple(float(s) for s in _t(a.get("ratios", (0.5, 1, 2)))),
+                            feature_stride=int(_t(a.get("feature_stride", 16))), output_score=True,
+                            iou_loss=_b(a.get("iou_loss", False)))
+            return list(r)
+        if op == "_contrib_ROIAlign_v2":
+            out, ax, ay = ops.roi_align_v2_raw(arg["data"].contiguous(), arg["rois"].contiguous(), _tup(a["pooled_size"]),
+                                               float(_t(a["spatial_scale"])), with_argmax=False)
+            return [out, ax, ay]
+        if op == "_contrib_DecodeBBox":
+            return [ops.OPS[op](arg["rois"].contiguous(), arg["bbox_pred"].contiguous(), arg["im_info"].contiguous(),
+                                tuple(_t(a.get("bbox_mean", (0, 0, 0, 0)))), tuple(_t(a.get("bbox_std", (0.1, 0.1, 0.2, 0.2)))),
+                                class_agnostic=_b(a.get("class_agnostic", True)))]
+        if op == "Custom":
+            t = a.get("op_type")
+            if t == "get_top_proposal":
+                return list(ops.OPS[t](arg["bbox"].contiguous(), arg["score"].contiguous(), int(_t(a["top_n"]))))
+            if t == "assign_layer_fpn":
+                return list(ops.OPS[t](x[0].contiguous(), tuple(_t(a["rcnn_stride"])), int(_t(a["roi_canonical_scale"])),
+                                       int(_t(a["roi_canonical_level"]))))
+            if t == "BboxPostProcessing":
+                return list(ops.OPS[t](x[0].contiguous(), x[1].contiguous(), int(_t(a["max_det_per_image"])),
+                                       float(_t(a["min_det_score"])), str(a.get("nms_type", "nms")), float(_t(a["nms_thr"]))))
+        raise NotImplementedError(f"operator {op!r} ({node.name}) is not wired into the façade executor")

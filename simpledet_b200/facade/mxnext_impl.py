@@ -1,0 +1,283 @@
+"""A stand-in for the third-party `mxnext` package (RogerChern/mxnext, un-pinned and not vendored in the reference:
+SURVEY §8c(3)) - written from the reference's CALL SITES (symbol/builder.py, models/FPN/builder.py, config/*): the
+`X.*` graph helpers, `normalizer_factory`, the ResNet-v1 FPN backbone builder and the `mxnext.tvm.*` operator
+helpers.  Graph helpers only create façade symbols with the MXNet operator names the real package emits
+(`X.conv` -> Convolution, `X.roi_align` -> _contrib_ROIAlign_v2, `X.proposal_target` -> ProposalTarget, ...:
+SURVEY §8b's name <-> kwargs table)."""
+from __future__ import annotations
+
+from . import symbol as S
+
+sym = S._OpNamespace("")
+contrib = S._OpNamespace("_contrib_")
+
+
+# ---- initialisers / variables ---------------------------------------------------------------------------------
+class _Init:
+    def __init__(self, kind, **kw):
+        self.kind, self.kw = kind, kw
+
+    def dumps(self):
+        import json
+
+        return json.dumps([self.kind, self.kw])
+
+
+def gauss(std):
+    return _Init("normal", sigma=std)
+
+
+def zero_init():
+    return _Init("zeros")
+
+
+def one_init():
+    return _Init("ones")
+
+
+def var(name, init=None, lr_mult=None, wd_mult=None, shape=None, dtype=None, **kw):
+    return S.Variable(name, shape=shape, lr_mult=lr_mult, wd_mult=wd_mult, dtype=dtype, init=init, **kw)
+
+
+def _pair(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (int(v), int(v))
+
+
+# ---- layers ----------------------------------------------------------------------------------------------------
+def conv(data, name, filter, kernel=1, stride=1, pad=-1, dilate=1, num_group=1, no_bias=True, init=None, lr_mult=1.0,
+         wd_mult=1.0, weight=None, bias=None):
+    k, s, d = _pair(kernel), _pair(stride), _pair(dilate)
+    p = _pair(pad) if pad != -1 else tuple(((kk - 1) * dd + 1) // 2 for kk, dd in zip(k, d))   # "same" for odd kernels
+    weight = weight if weight is not None else var(name + "_weight", init=init, lr_mult=lr_mult, wd_mult=wd_mult)
+    kw = dict(data=data, weight=weight, kernel=k, stride=s, pad=p, dilate=d, num_filter=int(filter), num_group=num_group,
+              no_bias=bool(no_bias), name=name)
+    if not no_bias:
+        kw["bias"] = bias if bias is not None else var(name + "_bias", init=zero_init(), lr_mult=lr_mult, wd_mult=wd_mult)
+    return sym.Convolution(**kw)
+
+
+def fc(data, name, filter, no_bias=False, flatten=True, init=None, weight=None, bias=None, lr_mult=1.0, wd_mult=1.0):
+    weight = weight if weight is not None else var(name + "_weight", init=init, lr_mult=lr_mult, wd_mult=wd_mult)
+    kw = dict(data=data, weight=weight, num_hidden=int(filter), no_bias=bool(no_bias), flatten=flatten, name=name)
+    if not no_bias:
+        kw["bias"] = bias if bias is not None else var(name + "_bias", init=zero_init(), lr_mult=lr_mult, wd_mult=wd_mult)
+    return sym.FullyConnected(**kw)
+
+
+def relu(data, name=None):
+    return sym.Activation(data=data, act_type="relu", name=name)
+
+
+def pool(data, name=None, kernel=3, stride=2, pad=-1, pool_type="max", pooling_convention="valid", global_pool=False):
+    k, s = _pair(kernel), _pair(stride)
+    p = _pair(pad) if pad != -1 else tuple(kk // 2 for kk in k)
+    return sym.Pooling(data=data, kernel=k, stride=s, pad=p, pool_type=pool_type, pooling_convention=pooling_convention,
+                       global_pool=global_pool, name=name)
+
+
+def max_pool(data, name=None, kernel=3, stride=2, pad=-1, **kw):
+    return pool(data, name, kernel, stride, pad, "max", **kw)
+
+
+def avg_pool(data, name=None, kernel=3, stride=2, pad=-1, **kw):
+    return pool(data, name, kernel, stride, pad, "avg", **kw)
+
+
+def global_avg_pool(data, name=None):
+    return sym.Pooling(data=data, kernel=(1, 1), pool_type="avg", global_pool=True, name=name)
+
+
+def fixbn(data, name, eps=1e-5, **kw):
+    return sym.BatchNorm(data=data, name=name, use_global_stats=True, fix_gamma=False, eps=eps)
+
+
+def bn(data, name, eps=1e-5, mom=0.9, **kw):
+    return sym.BatchNorm(data=data, name=name, use_global_stats=False, fix_gamma=False, eps=eps, momentum=mom)
+
+
+def convrelu(data, name, filter, kernel=1, stride=1, pad=-1, dilate=1, no_bias=False, init=None, **kw):
+    return relu(conv(data, name, filter, kernel, stride, pad, dilate, no_bias=no_bias, init=init), name + "_relu")
+
+
+def convnorm(normalizer, data, name, filter, kernel=1, stride=1, pad=-1, dilate=1, no_bias=True, init=None, **kw):
+    return normalizer(conv(data, name, filter, kernel, stride, pad, dilate, no_bias=no_bias, init=init), name=name + "_bn")
+
+
+def convnormrelu(normalizer, data, name, filter, kernel=1, stride=1, pad=-1, dilate=1, no_bias=True, init=None, **kw):
+    return relu(convnorm(normalizer, data, name, filter, kernel, stride, pad, dilate, no_bias, init), name + "_relu")
+
+
+def to_fp16(data, name=None):
+    return sym.Cast(data=data, dtype="float16", name=name)
+
+
+def to_fp32(data, name=None):
+    return sym.Cast(data=data, dtype="float32", name=name)
+
+
+def reshape(data, shape, name=None):
+    return sym.Reshape(data=data, shape=tuple(shape), name=name)
+
+
+def flatten(data, name=None):
+    return sym.Flatten(data=data, name=name)
+
+
+def concat(data, axis=1, name=None):
+    return sym.Concat(*data, dim=axis, num_args=len(data), name=name)
+
+
+def add(lhs, rhs, name=None):
+    return sym.elemwise_add(lhs, rhs, name=name)
+
+
+def add_n(*args, name=None):
+    return sym.add_n(*args, num_args=len(args), name=name)
+
+
+def group(symbols):
+    return S.Group(list(symbols))
+
+
+def softmax(data, axis=-1, name=None):
+    return sym.softmax(data=data, axis=axis, name=name)
+
+
+def sigmoid(data, name=None):
+    return sym.Activation(data=data, act_type="sigmoid", name=name)
+
+
+def softmax_output(data, label, name=None, **kw):
+    return sym.SoftmaxOutput(data=data, label=label, name=name, **kw)
+
+
+def smooth_l1(data, scalar=1.0, name=None):
+    return sym.smooth_l1(data=data, scalar=scalar, name=name)
+
+
+def loss(data, grad_scale=1.0, name=None):
+    return sym.MakeLoss(data=data, grad_scale=grad_scale, name=name)
+
+
+def stop_grad(data, name=None):
+    return sym.BlockGrad(data=data, name=name)
+
+
+block_grad = stop_grad
+
+
+def dropout(data, p=0.5, name=None):
+    return sym.Dropout(data=data, p=p, name=name)
+
+
+# ---- detection operators (names of SURVEY §8b) --------------------------------------------------------------------
+def roi_align(feat, rois, out_size, stride, name=None):
+    s = _pair(out_size)
+    return contrib.ROIAlign_v2(data=feat, rois=rois, pooled_size=s, spatial_scale=1.0 / stride, name=name)
+
+
+def proposal(cls_prob, bbox_pred, im_info, name=None, **kw):
+    return contrib.Proposal(cls_prob=cls_prob, bbox_pred=bbox_pred, im_info=im_info, name=name, **kw)
+
+
+def proposal_target(rois, gt_boxes, name=None, **kw):
+    return sym.ProposalTarget(rois=rois, gt_boxes=gt_boxes, name=name, **kw)
+
+
+def decode_bbox(rois, bbox_pred, im_info, name=None, **kw):
+    return contrib.DecodeBBox(rois=rois, bbox_pred=bbox_pred, im_info=im_info, name=name, **kw)
+
+
+def focal_loss(data, label, name=None, **kw):
+    return contrib.FocalLoss(data=data, label=label, name=name, **kw)
+
+
+def bbox_norm(data, label, name=None, **kw):
+    return contrib.BBoxNorm(data=data, label=label, name=name, **kw)
+
+
+# ---- mxnext.complicate -----------------------------------------------------------------------------------------------
+def normalizer_factory(type="local", ndev=None, eps=1e-5, mom=0.9, wd_mult=1.0, lr_mult=1.0):
+    def fix_bn(data, name=None, **kw):
+        return fixbn(data, name, eps=eps)
+
+    def local_bn(data, name=None, **kw):
+        return bn(data, name, eps=eps, mom=mom)
+
+    def dummy(data, name=None, **kw):
+        return data
+
+    table = {"fixbn": fix_bn, "fix_bn": fix_bn, "local": local_bn, "localbn": local_bn, "local_bn": local_bn,
+             "dummy": dummy}
+    if type not in table:
+        raise NotImplementedError(f"normalizer {type!r}: only fixbn / local / dummy are built in the stand-in")
+    return table[type]
+
+
+# ---- mxnext.backbone.resnet_v1 ------------------------------------------------------------------------------------------
+class ResNetV1Builder:
+    """ResNet-v1 (MSRA layout: stride on the first 1x1 conv of a downsampling unit) with the parameter names of the
+    reference's pretrained checkpoints (conv0, bn0, stage{s}_unit{u}_conv{1,2,3}, _bn{1,2,3}, _sc, _sc_bn)."""
+    depth_config = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 152: (3, 8, 36, 3)}
+
+    @staticmethod
+    def unit(data, name, filter, stride, dilate, proj, norm):
+        c1 = convnormrelu(norm, data, name + "_conv1", filter // 4, kernel=1, stride=stride)
+        c2 = convnormrelu(norm, c1, name + "_conv2", filter // 4, kernel=3, dilate=dilate)
+        c3 = convnorm(norm, c2, name + "_conv3", filter, kernel=1)
+        sc = convnorm(norm, data, name + "_sc", filter, kernel=1, stride=stride) if proj else data
+        return relu(add(c3, sc, name=name + "_plus"), name=name + "_relu")
+
+    @classmethod
+    def stage(cls, data, name, num_unit, filter, stride, dilate, norm):
+        x = cls.unit(data, f"{name}_unit1", filter, stride, dilate, True, norm)
+        for i in range(2, num_unit + 1):
+            x = cls.unit(x, f"{name}_unit{i}", filter, 1, dilate, False, norm)
+        return x
+
+    def get_backbone(self, variant, depth, endpoint, normalizer, fp16):
+        units = self.depth_config[depth]
+        data = var("data")
+        if fp16:
+            data = to_fp16(data, "data_fp16")
+        c1 = convnormrelu(normalizer, data, "conv0", 64, kernel=7, stride=2)
+        c1 = max_pool(c1, name="pool0", kernel=3, stride=2)
+        c2 = self.stage(c1, "stage1", units[0], 256, 1, 1, normalizer)
+        c3 = self.stage(c2, "stage2", units[1], 512, 2, 1, normalizer)
+        c4 = self.stage(c3, "stage3", units[2], 1024, 2, 1, normalizer)
+        if endpoint == "c4":
+            return c4
+        c5 = self.stage(c4, "stage4", units[3], 2048, 2, 1, normalizer)
+        if endpoint == "c5":
+            return c5
+        if endpoint == "fpn":
+            return c2, c3, c4, c5
+        raise NotImplementedError(endpoint)
+
+    # the reference also calls these through thin wrappers
+    def get_stage_endpoints(self, *a, **kw):
+        return self.get_backbone(*a, **kw)
+
+
+# ---- mxnext.tvm.* -----------------------------------------------------------------------------------------------------------
+def tvm_proposal(cls_prob, bbox_pred, im_info, anchors=None, name="proposal", feature_stride=16, scales=(8,),
+                 ratios=(0.5, 1.0, 2.0), rpn_pre_nms_top_n=1000, rpn_post_nms_top_n=1000, threshold=0.7, batch_size=1,
+                 max_side=-1, output_score=True, variant="simpledet", rpn_min_size=0, **kw):
+    """mxnext.tvm.proposal.proposal(variant="simpledet"): the TVM-built twin of _contrib_Proposal_v3 used for the
+    large levels (models/FPN/builder.py:289-311).  The stand-in emits _contrib_Proposal_v3 itself - the anchors input
+    carries no information beyond (stride, scales, ratios)."""
+    return contrib.Proposal_v3(cls_prob=cls_prob, bbox_pred=bbox_pred, im_info=im_info,
+                               rpn_pre_nms_top_n=rpn_pre_nms_top_n, rpn_post_nms_top_n=rpn_post_nms_top_n,
+                               feature_stride=feature_stride, output_score=output_score, scales=tuple(scales),
+                               ratios=tuple(ratios), rpn_min_size=rpn_min_size, threshold=threshold, iou_loss=False,
+                               name=f"{name}_stride{feature_stride}")
+
+
+def tvm_get_top_proposal(F, bbox, score, top_n, batch_size=1, **kw):
+    return sym.Custom(bbox=bbox, score=score, op_type="get_top_proposal", top_n=top_n, name="get_top_proposal")
+
+
+def tvm_fpn_roi_assign(F, rois, rcnn_stride, roi_canonical_scale, roi_canonical_level, **kw):
+    return sym.Custom(rois=rois, op_type="assign_layer_fpn", rcnn_stride=tuple(rcnn_stride),
+                      roi_canonical_scale=roi_canonical_scale, roi_canonical_level=roi_canonical_level,
+                      name="assign_layer_fpn")

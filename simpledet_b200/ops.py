@@ -18,7 +18,7 @@ import torch
 from . import _lib
 from ._lib import check
 
-__all__ = ["gpu_nms", "greedy_nms", "bbox_overlaps_cython", "assign_layer_fpn", "BboxPostProcessing", "ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_raw",
+__all__ = ["fpn_roi_align_nhwc", "gpu_nms", "greedy_nms", "bbox_overlaps_cython", "assign_layer_fpn", "BboxPostProcessing", "ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_raw",
            "fpn_roi_align", "fpn_roi_align_raw", "DecodeBBox", "Proposal_v3", "Proposal_v3_fpn", "NMS", "nms_sorted", "get_top_proposal",
            "multiclass_nms", "ProposalTarget", "FocalLoss", "BBoxNorm",
            "SigmoidCrossEntropy", "soft_nms", "soft_nms_batched",
@@ -80,6 +80,8 @@ def roi_align_v2_raw(data, rois, pooled_size, spatial_scale, with_argmax=True, u
     ay = torch.empty_like(out) if with_argmax else None
     L = _lib.lib()
     nbytes = L.sdet_roi_align_v2_workspace(B, N) if use_plan else 0
+    if use_plan and not with_argmax and path in (0, 3):  # room for the NHWC re-layout: channels-last kernel
+        nbytes = L.sdet_fpn_roi_align_v2_workspace(B, N, C, (ctypes.c_int * 1)(H), (ctypes.c_int * 1)(W), 1)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=data.device) if nbytes else None
     used = ctypes.c_int(-1)
     check(L.sdet_roi_align_v2_forward_ex(_p(data), _p(rois), _p(out), _p(ax), _p(ay), B, N, C, H, W, ph, pw,
@@ -157,7 +159,9 @@ def fpn_roi_align_raw(feats, rois, strides, out_size, roi_canonical_scale=224,
     levels = torch.empty((B, N), device=rois.device, dtype=torch.int32)
     L = _lib.lib()
     nbytes = L.sdet_roi_align_v2_workspace(B, N) if use_plan else 0
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=rois.device) if nbytes else None
+    if use_plan and not with_argmax and path in (0, 3):  # room for the NHWC re-layout: channels-last kernel
+        nbytes = L.sdet_fpn_roi_align_v2_workspace(B, N, C, Hs, Ws, len(feats))
+    ws = _ws_cached(nbytes, rois.device) if nbytes else None
     used = ctypes.c_int(-1)
     check(L.sdet_fpn_roi_align_v2_forward_ex(
         ptrs, Hs, Ws, Ss, len(feats), _p(rois), _p(out), _p(ax), _p(ay), _p(levels), B, N, C, ph, pw,
@@ -166,6 +170,45 @@ def fpn_roi_align_raw(feats, rois, strides, out_size, roi_canonical_scale=224,
     if return_path:  # 0 inline per-roi, 1 planned per-roi, 2 band-stationary (+ per-roi leftovers)
         return out, ax, ay, levels, used.value
     return out, ax, ay, levels
+
+
+_WS_CACHE: dict = {}
+
+
+def _ws_cached(nbytes: int, device) -> torch.Tensor:
+    """One grow-only workspace per device and stream (the RoIAlign workspace holds a re-layout of the feature maps:
+    allocating ~100 MB per call would cost more than the kernels)."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    t = _WS_CACHE.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = t
+    return t
+
+
+def fpn_roi_align_nhwc(feats_nhwc, rois, strides, out_size, roi_canonical_scale=224, roi_canonical_level=4):
+    """Fused FPN RoIAlign over channels-last features: feats_nhwc[l] is (B, H_l, W_l, C) contiguous (what a
+    tensor-core convolution in channels_last memory format produces: `y.permute(0, 2, 3, 1)` of it is such a
+    view).  Inference (no argmax planes).  -> (out (B,N,C,PH,PW), levels (B,N))."""
+    feats = [_dev(f, f"feat[{i}]") for i, f in enumerate(feats_nhwc)]
+    rois = _dev(rois, "rois")
+    B, C = feats[0].shape[0], feats[0].shape[3]
+    ph, pw = _pair(out_size)
+    N = rois.shape[1]
+    Lv = len(feats)
+    out = torch.empty((B, N, C, ph, pw), device=rois.device, dtype=torch.float32)
+    levels = torch.empty((B, N), device=rois.device, dtype=torch.int32)
+    ptrs = (ctypes.c_void_p * Lv)(*[f.data_ptr() for f in feats])
+    Hs = (ctypes.c_int * Lv)(*[f.shape[1] for f in feats])
+    Ws = (ctypes.c_int * Lv)(*[f.shape[2] for f in feats])
+    Ss = (ctypes.c_int * Lv)(*[int(s) for s in strides])
+    L = _lib.lib()
+    nbytes = L.sdet_roi_align_v2_workspace(B, N)
+    ws = _ws_cached(nbytes, rois.device)
+    check(L.sdet_fpn_roi_align_v2_forward_nhwc(ptrs, Hs, Ws, Ss, Lv, _p(rois), _p(out), _p(levels), B, N, C, ph, pw,
+                                               int(roi_canonical_scale), int(roi_canonical_level), _p(ws), nbytes,
+                                               _stream()))
+    return out, levels
 
 
 class _FpnRoiAlignFn(torch.autograd.Function):

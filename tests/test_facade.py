@@ -1,0 +1,59 @@
+"""The `mx` / `mxnext` façade on CPU: the reference's OWN config and builders import and build
+their graph on the stand-in modules; graph queries, MXNet reshape codes and shape inference; the committed graph
+fixture is what those builders produce."""
+import importlib
+import os
+import sys
+
+import pytest
+
+from simpledet_b200.facade import executor as E
+from simpledet_b200.facade import symbol as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIX = os.path.join(ROOT, "tests", "golden", "faster_r50v1_fpn_1x_test_symbol.json")
+SHAPES = dict(data=(1, 3, 800, 1333), im_info=(1, 3), im_id=(1,), rec_id=(1,))
+
+
+def test_mx_reshape_codes():
+    assert E.mx_reshape((2, 3, 4, 5), (0, -1)) == (2, 60)
+    assert E.mx_reshape((2, 3, 4, 5), (-3, -2)) == (6, 4, 5)              # symbol/builder.py:896
+    assert E.mx_reshape((1, 6, 50, 84), (0, 2, -1, 0)) == (1, 2, 150, 84)  # models/FPN/builder.py:262
+    assert E.mx_reshape((2, 12, 5), (0, -4, 3, -1, 0)) == (2, 3, 4, 5)
+    assert E.mx_reshape((2, 3, 4), (-2,)) == (2, 3, 4)
+
+
+def test_fixture_graph_shapes_and_ops():
+    sym = S.fromjson(open(FIX).read())
+    args, outs, aux = sym.infer_shape(**SHAPES)
+    assert sym.list_outputs() == ["rec_id", "im_id", "im_info", "bbox_cls_score_reshape_output", "decode_bbox_output"]
+    assert outs == [(1,), (1,), (1, 3), (1, 1000, 81), (1, 1000, 324)]
+    assert all(s is not None for s in args + aux)
+    ops = {n.op for n in sym._topo() if n.op}
+    # the detection operators are in the graph under the reference's registration strings
+    assert {"_contrib_Proposal_v3", "_contrib_ROIAlign_v2", "_contrib_DecodeBBox", "Custom"} <= ops
+    custom = {n.attrs["op_type"] for n in sym._topo() if n.op == "Custom"}
+    assert custom == {"get_top_proposal", "assign_layer_fpn"}
+    nparam = sum(__import__("math").prod(s) for n, s in zip(sym.list_arguments(), args) if n not in SHAPES)
+    assert 41e6 < nparam < 43e6   # ResNet-50 FPN Faster R-CNN: ~41.8 M parameters
+    # the executor recognises assign_layer_fpn -> 4 x ROIAlign_v2 -> add_n as ONE fused FPN RoIAlign
+    ex = E.Executor(sym, device="cpu")
+    assert len(ex._fusions) == 1
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/config"), reason="reference checkout not present")
+def test_reference_builders_run_unchanged_on_the_facade():
+    from simpledet_b200 import facade
+
+    facade.install("/root/reference")
+    cfg = importlib.import_module("config.faster_r50v1_fpn_1x")
+    sym = cfg.get_config(is_train=False)[6].test_symbol
+    want = S.fromjson(open(FIX).read())
+    assert [n.name for n in sym._topo()] == [n.name for n in want._topo()]
+    assert [n.op for n in sym._topo()] == [n.op for n in want._topo()]
+    assert sym.infer_shape(**SHAPES)[1] == want.infer_shape(**SHAPES)[1]
+    # rpn-only symbol of the same config
+    rpn = cfg.get_config(is_train=False)[6].rpn_test_symbol
+    assert rpn.infer_shape(**SHAPES)[1][-2:] == [(1, 1000, 4), (1, 1000, 1)]
+    for m in [k for k in sys.modules if k.split(".")[0] in ("config", "symbol", "models", "core", "utils", "operator_py")]:
+        sys.modules.pop(m, None)   # leave no half-imported reference packages behind for other tests

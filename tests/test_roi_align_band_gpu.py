@@ -19,9 +19,11 @@ def _t(a, dev):
 
 def _single(data, rois, pooled, scale, dev, expect_band=True):
     d, r = _t(data, dev), _t(rois, dev)
-    out, _, _, used = ops.roi_align_v2_raw(d, r, pooled, scale, with_argmax=False, return_path=True)
+    out, _, _, used = ops.roi_align_v2_raw(d, r, pooled, scale, with_argmax=False, path=2, return_path=True)
     if expect_band:
         assert used == BAND, f"band path not taken (path_used={used})"
+    else:
+        assert used == 1
     ref, _, _ = oracle.roi_align_v2_forward(data, rois, pooled, scale)
     o = out.cpu().numpy()
     assert np.array_equal(o, ref), f"band kernel differs from the oracle at {np.argwhere(o != ref)[:5]}"
@@ -96,7 +98,7 @@ def _fpn(B, N, C, pooled, dev, seed, check_oracle):
     rois_np = synth.random_rois(rng, B, N)
     feats = [_t(f, dev) for f in feats_np]
     rois = _t(rois_np, dev)
-    out, _, _, lv, used = ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=False,
+    out, _, _, lv, used = ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=False, path=2,
                                                 return_path=True)
     assert used == BAND
     per, _, _, lv1, used1 = ops.fpn_roi_align_raw(feats, rois, synth.FPN_STRIDES, pooled, with_argmax=False, path=1,
