@@ -614,6 +614,9 @@ size_t plan_workspace_bytes(int B, int N) {
 
 // mode: 0 = automatic, 1 = per-roi kernel only, 2 = band-stationary kernel (+ per-roi leftovers),
 //       3 = channels-last kernel (features re-laid to NHWC in the scratch that follows the plan workspace).
+// Automatic = the planned per-roi kernel: with NCHW features it is the fastest of the three on both measured shapes
+// (profiles/r02_roialign_paths.md); the channels-last kernel wins when the features ARE channels-last, which is the
+// separate entry point sdet_fpn_roi_align_v2_forward_nhwc.  2 and 3 stay selectable for measurement.
 // g_last_path reports what ran: 0 inline per-roi, 1 planned per-roi, 2 band-stationary, 3 channels-last.
 thread_local int g_last_path = 0;
 
@@ -655,7 +658,7 @@ int launch_fwd(RoiAlignArgs& a, void* workspace, size_t workspace_bytes, cudaStr
       if (mode == 3 && !cl_ok)
         return sdet::fail(SDET_ERR_WORKSPACE, "channels-last path: needs no argmax planes, even C and a workspace of "
                           "sdet_fpn_roi_align_v2_workspace() = %zu bytes", need + scratch);
-      if (cl_ok && (mode == 3 || mode == 0)) {
+      if (cl_ok && mode == 3) {
         PlanSched sc{};
         if (int rc = plan_and_order(a, w, total, sc, st)) return rc;
         RoiAlignArgs t = a;  // levels re-pointed at the NHWC copies
@@ -665,7 +668,7 @@ int launch_fwd(RoiAlignArgs& a, void* workspace, size_t workspace_bytes, cudaStr
       }
     }
     BandArgs ba{};
-    if ((mode == 0 || mode == 2) && band_setup(a, w + per_roi_workspace_bytes(total), ba)) {
+    if (mode == 2 && band_setup(a, w + per_roi_workspace_bytes(total), ba)) {
       if (int rc = band_launch(a, ba, static_cast<PlanRecord*>(workspace), st)) return rc;
       g_last_path = 2;
       a.plans = workspace;

@@ -80,7 +80,7 @@ def roi_align_v2_raw(data, rois, pooled_size, spatial_scale, with_argmax=True, u
     ay = torch.empty_like(out) if with_argmax else None
     L = _lib.lib()
     nbytes = L.sdet_roi_align_v2_workspace(B, N) if use_plan else 0
-    if use_plan and not with_argmax and path in (0, 3):  # room for the NHWC re-layout: channels-last kernel
+    if use_plan and not with_argmax and path == 3:  # room for the NHWC re-layout: channels-last kernel
         nbytes = L.sdet_fpn_roi_align_v2_workspace(B, N, C, (ctypes.c_int * 1)(H), (ctypes.c_int * 1)(W), 1)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=data.device) if nbytes else None
     used = ctypes.c_int(-1)
@@ -159,7 +159,7 @@ def fpn_roi_align_raw(feats, rois, strides, out_size, roi_canonical_scale=224,
     levels = torch.empty((B, N), device=rois.device, dtype=torch.int32)
     L = _lib.lib()
     nbytes = L.sdet_roi_align_v2_workspace(B, N) if use_plan else 0
-    if use_plan and not with_argmax and path in (0, 3):  # room for the NHWC re-layout: channels-last kernel
+    if use_plan and not with_argmax and path == 3:  # room for the NHWC re-layout: channels-last kernel
         nbytes = L.sdet_fpn_roi_align_v2_workspace(B, N, C, Hs, Ws, len(feats))
     ws = _ws_cached(nbytes, rois.device) if nbytes else None
     used = ctypes.c_int(-1)

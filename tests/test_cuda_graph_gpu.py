@@ -17,18 +17,22 @@ def test_hot_path_replays_from_a_cuda_graph():
         pytest.skip("needs a GPU")
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(5)
-    sets = [{k: torch.from_numpy(v).to(dev) for k, v in bench.make_inputs_np(rng, 1).items()} for _ in range(2)]
+    sets = [{k: torch.from_numpy(v).to(dev) for k, v in bench.Infer.make_inputs(rng, 1).items()} for _ in range(2)]
     static = {k: v.clone() for k, v in sets[0].items()}
-    eager = [[t.clone() for t in bench.hot_path_step(ops, s)] for s in sets]   # also warms every lazy init
+    def step(d):
+        out = bench.Infer.step(ops, d)
+        return [out["rois"], *out["result"]]
+
+    eager = [[t.clone() for t in step(s)] for s in sets]   # also warms every lazy init
     torch.cuda.synchronize()
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
-        bench.hot_path_step(ops, static)
+        step(static)
     torch.cuda.current_stream().wait_stream(side)
     g = torch.cuda.CUDAGraph()
     n0 = _lib.launch_count()
     with torch.cuda.graph(g):
-        outs = bench.hot_path_step(ops, static)
+        outs = step(static)
     launches = _lib.launch_count() - n0
     assert launches >= 10
     for i in (1, 0, 1):
