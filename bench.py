@@ -54,7 +54,8 @@ class Infer:
     text = ("faster_r50v1_fpn_1x inference hot path, synthetic 800x1333: 5x Proposal_v3 -> get_top_proposal(1000)"
             " -> FPN RoIAlign_v2 7x7 (1000 rois x 256 ch) -> DecodeBBox(81) -> per-class NMS(80)")
     train = False
-    kernel = "roi_align_band_kernel (fused FPN RoIAlign 7x7, band-stationary, %d rois x 256 ch)"
+    kernel = ("roi_align_cl_kernel (fused FPN RoIAlign 7x7 over channels-last FPN features, %d rois x 256 ch; "
+              "whole operator: plan + order + gather kernels)")
 
     @staticmethod
     def make_inputs(rng, B):
@@ -65,7 +66,8 @@ class Infer:
             d[f"cls_prob{s}"] = np.concatenate([1 - fg, fg], 1).astype(np.float32)
             d[f"bbox_pred{s}"] = (rng.standard_normal((B, 12, h, w)) * 0.3).astype(np.float32)
         for s, (h, w) in zip(STRIDES_ROI, level_shapes(STRIDES_ROI)):
-            d[f"feat{s}"] = rng.standard_normal((B, C_FEAT, h, w)).astype(np.float32)
+            # FPN features in the layout the tensor-core convolutions that produce them emit: channels-last (B,H,W,C)
+            d[f"feat{s}"] = rng.standard_normal((B, h, w, C_FEAT)).astype(np.float32)
         d["im_info"] = np.tile(np.array([[IMG_H, IMG_W, 1.0]], np.float32), (B, 1))
         z = rng.standard_normal((B, N_ROI, K_CLS)).astype(np.float32) * 2
         z[..., 0] += 3  # mostly background, a few confident classes
@@ -84,7 +86,7 @@ class Infer:
         feats = [d[f"feat{s}"] for s in STRIDES_ROI]
         if ev:
             ev[0].record()
-        roi_feat = ops.fpn_roi_align_raw(feats, rois, STRIDES_ROI, POOLED, 224, 4, with_argmax=False)[0]
+        roi_feat = ops.fpn_roi_align_nhwc(feats, rois, STRIDES_ROI, POOLED, 224, 4)[0]  # (B, N, C, 7, 7)
         if ev:
             ev[1].record()
         # (RoI head: 2 fc + cls/reg fc on tensor cores — library GEMMs, not on this path)
@@ -97,6 +99,14 @@ class Infer:
     def roofline_bytes(out, d, B):
         """sz(out) + sum_l min(sz(feat_l), sum of window bytes on l) + sz(rois)."""
         return roialign_algorithmic_bytes(out["rois"].cpu().numpy(), B, POOLED, False)
+
+    @staticmethod
+    def prepare_cpu(d):
+        """The reference's operators read NCHW: re-lay the features once, outside the timed region."""
+        d = dict(d)
+        for s in STRIDES_ROI:
+            d[f"feat{s}"] = np.ascontiguousarray(d[f"feat{s}"].transpose(0, 3, 1, 2))
+        return d
 
     @staticmethod
     def cpu(d, n_images):
@@ -147,7 +157,10 @@ class RetinaTrain:
         d["bbox_loss"] = rng.standard_normal((B, 36, 22300), dtype=np.float32)
         d["reg_label"] = lab[:, :22300].copy()
         for s, (h, w) in zip(cls.STRIDES, level_shapes(cls.STRIDES)):
-            d[f"cls{s}"] = (rng.random((B, 9 * cls.K, h, w), dtype=np.float32) ** 6)
+            # class probabilities of a freshly initialised head (bias -4.6, models/retinanet/builder.py prior 0.01)
+            # with unit-variance logits: ~5 % of the 720*H*W pairs clear the 0.05 threshold
+            z = rng.standard_normal((B, 9 * cls.K, h, w), dtype=np.float32) - np.float32(4.6)
+            d[f"cls{s}"] = (1.0 / (1.0 + np.exp(-z))).astype(np.float32)
             d[f"reg{s}"] = rng.standard_normal((B, 36, h, w), dtype=np.float32) * 0.3
         d["im_info"] = np.tile(np.array([[IMG_H, IMG_W, 1.0]], np.float32), (B, 1))
         return d
@@ -444,6 +457,8 @@ def time_cpu(wl, d, budget_s=12.0):
 
     oracle.build()
     oracle.set_threads()
+    if hasattr(wl, "prepare_cpu"):
+        d = wl.prepare_cpu(d)
     t0 = time.perf_counter()
     wl.cpu(d, 1)
     one = time.perf_counter() - t0
@@ -472,6 +487,8 @@ def run_reference(args):
     oracle.build()
     rng = np.random.default_rng(0)
     d = wl.make_inputs(rng, 1)
+    if hasattr(wl, "prepare_cpu"):
+        d = wl.prepare_cpu(d)
     cores = oracle.set_threads() or 1  # (torchrun exports OMP_NUM_THREADS=1: undo it for the CPU arm)
     for _ in range(min(args.warmup, 1)):
         wl.cpu(d, 1)
@@ -671,22 +688,29 @@ def run_ours(args):
         from simpledet_b200 import synth
 
         trng = np.random.default_rng(0)
-        feats = [torch.randn((1, C_FEAT, h, w), device=dev) for h, w in level_shapes(STRIDES_ROI)]
+        feats_cl = [torch.randn((1, h, w, C_FEAT), device=dev) for h, w in level_shapes(STRIDES_ROI)]
+        feats_nchw = [f.permute(0, 3, 1, 2).contiguous() for f in feats_cl]
         rois_np = synth.random_rois(trng, 1, 512)
         rois = torch.from_numpy(rois_np).to(dev)
         flush = torch.empty(128 * 1024 * 1024, device=dev)
-        tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(30)]
-        for _ in range(3):
-            ops.fpn_roi_align_raw(feats, rois, STRIDES_ROI, 14, with_argmax=False)
-        torch.cuda.synchronize()
-        for a, b_ in tev:
-            flush.fill_(1.0)  # 512 MB write: evicts the 126 MB L2
-            a.record()
-            ops.fpn_roi_align_raw(feats, rois, STRIDES_ROI, 14, with_argmax=False)
-            b_.record()
-        torch.cuda.synchronize()
-        ts = sorted(a.elapsed_time(b_) for a, b_ in tev)
-        target = (ts[len(ts) // 2] * 1e3, roialign_algorithmic_bytes(rois_np, 1, 14, False))
+
+        def timed(fn):
+            tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(30)]
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            for a, b_ in tev:
+                flush.fill_(1.0)  # 512 MB write: evicts the 126 MB L2
+                a.record()
+                fn()
+                b_.record()
+            torch.cuda.synchronize()
+            ts = sorted(a.elapsed_time(b_) for a, b_ in tev)
+            return ts[len(ts) // 2] * 1e3
+
+        t_alg = roialign_algorithmic_bytes(rois_np, 1, 14, False)
+        target = (timed(lambda: ops.fpn_roi_align_nhwc(feats_cl, rois, STRIDES_ROI, 14)),
+                  timed(lambda: ops.fpn_roi_align_raw(feats_nchw, rois, STRIDES_ROI, 14, with_argmax=False)), t_alg)
         del flush
 
     if rank != 0:
@@ -733,13 +757,19 @@ def run_ours(args):
                      "share_of_step": round(k_us / (1e3 * ms / K), 4)},
     }
     if target is not None:
-        t_us, t_alg = target
-        out_json["roofline_target"] = {
-            "kernel": "fused FPN RoIAlign_v2 forward, north-star shape 512 rois x 256 ch x 14x14 (whole operator: plan + "
-                      "layout + band kernel), L2 flushed before every launch",
-            "bound": "hbm", "achieved": round(t_alg / (t_us * 1e-6) / 1e9, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(t_alg / (t_us * 1e-6) / 1e9 / peak, 4), "algorithmic_bytes_per_launch": t_alg,
-            "us_per_launch": round(t_us, 2), "peak_source": peak_src}
+        t_cl, t_nchw, t_alg = target
+
+        def entry(us, what):
+            return {"kernel": what, "bound": "hbm", "achieved": round(t_alg / (us * 1e-6) / 1e9, 1), "peak": peak,
+                    "unit": "GB/s", "frac": round(t_alg / (us * 1e-6) / 1e9 / peak, 4),
+                    "algorithmic_bytes_per_launch": t_alg, "us_per_launch": round(us, 2), "peak_source": peak_src}
+
+        out_json["roofline_target"] = entry(
+            t_cl, "fused FPN RoIAlign_v2 forward, north-star shape 512 rois x 256 ch x 14x14, channels-last features "
+                  "(whole operator: plan + order + roi_align_cl_kernel), L2 flushed before every launch")
+        out_json["roofline_target_nchw"] = entry(
+            t_nchw, "same shape through the NCHW operator contract (sdet_fpn_roi_align_v2_forward_ex, automatic path: "
+                    "plan + order + per-roi kernel), L2 flushed before every launch")
     if wl.train:
         nbytes = GRAD_BUCKET_FLOATS * 4
         out_json["allreduce"] = {"bytes": nbytes, "ms": None if ar_ms is None else round(ar_ms, 3), "ranks": world,

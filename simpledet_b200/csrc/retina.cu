@@ -4,12 +4,14 @@
 //
 // The reference decodes every one of the 720*H*W (anchor, class) pairs into a (count,5) buffer and
 // thrust-sorts all of them (12 M keys on P3) to keep 1000.  Here one coalesced pass over cls_prob
-// keeps only the pairs that survive `score > thresh` and the min-size test as 64-bit keys
-// (score, reference index); one CTA per image then radix-selects the top `pre` keys and decodes just
-// the winners.  Zeroed pairs never need materialising: with thresh >= 0 every survivor scores > 0,
+// histograms the scores of the pairs that survive `score > thresh` and the min-size test (4608 bins of 2^13 ulps
+// above the threshold), a second pass writes out as 64-bit keys (score, reference index) only the pairs in the
+// bins that can still reach the top `pre` - a few thousand keys whatever the score distribution - and one CTA per
+// image radix-selects and sorts the top `pre` of those and decodes just the winners.  Zeroed pairs never need materialising: with thresh >= 0 every survivor scores > 0,
 // so they sort after all survivors and contribute all-zero output rows.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "common.cuh"
 #include "topk.cuh"
@@ -48,6 +50,8 @@ struct RetinaParams {
   int A, K, H, W, min_size, pre, pre_pow2, out_channel;
   unsigned long long* cand;  // (B, count) keys
   int* cand_count;           // (B)
+  uint32_t* hist;            // (B, kScoreBins) survivors per score bin
+  uint32_t thresh_ord;       // score_to_sortable(thresh)
   float* out;                // (B, pre_param, 4)
   float* out_score;          // (B, pre_param, out_channel)
   int out_rows;
@@ -79,10 +83,79 @@ __device__ __forceinline__ float4 retina_decode(const RetinaParams& p, int b, in
   return o;
 }
 
-// Pass 1: stream cls_prob in memory order, keep survivors as keys (warp-aggregated append).
-__global__ void __launch_bounds__(256) retina_candidates_kernel(const __grid_constant__ RetinaParams p) {
+constexpr int kScoreBins = 4608;  // bins of 2^13 ulps above the threshold: (0.05, 1] spans 4506 of them
+constexpr int kScoreShift = 13;
+
+__device__ __forceinline__ int score_bin(const RetinaParams& p, float s) {  // s > thresh
+  const uint32_t d = (sdet::score_to_sortable(s) - p.thresh_ord) >> kScoreShift;
+  return d < (uint32_t)kScoreBins ? (int)d : kScoreBins - 1;  // anything further up shares the top bin
+}
+
+// Is (image b, flat cls_prob index i) a survivor?  FilterBoxKernel :218 zeroes score <= thresh, :205-216 boxes
+// smaller than min_size.
+__device__ __forceinline__ bool retina_survivor(const RetinaParams& p, int b, int i, int HW, int AK, float im_h,
+                                                float im_w, float min_size, float s, unsigned long long& key) {
+  if (!(s > p.thresh)) return false;
+  const int a = i / HW, r = i - a * HW, h = r / p.W, w = r - h * p.W;
+  if (p.min_size > 0 || min_size > 1.f) {  // a decoded box is at least 1 pixel wide: nothing to test otherwise
+    const float4 bx = retina_decode(p, b, a / p.K, h, w, im_h, im_w);
+    const float iw = __fadd_rn(__fsub_rn(bx.z, bx.x), 1.0f), ih = __fadd_rn(__fsub_rn(bx.w, bx.y), 1.0f);
+    if (iw < min_size || ih < min_size) return false;
+  }
+  key = sdet::make_key(s, (uint32_t)(r * AK + a));  // reference index (h*W+w)*AK + a
+  return true;
+}
+
+// Pass 1: stream cls_prob in memory order, histogram the survivors' scores (per-CTA shared histogram, merged once).
+__global__ void __launch_bounds__(256) retina_hist_kernel(const __grid_constant__ RetinaParams p) {
+  __shared__ uint32_t s_h[kScoreBins];
   const int b = blockIdx.y;
   const int HW = p.H * p.W, AK = p.A * p.K, count = AK * HW;
+  const float im_h = __ldg(p.im_info + b * 3), im_w = __ldg(p.im_info + b * 3 + 1);
+  const float min_size = __fmul_rn((float)p.min_size, __ldg(p.im_info + b * 3 + 2));
+  const float* sc = p.cls_prob + (size_t)b * count;
+  for (int i = threadIdx.x; i < kScoreBins; i += blockDim.x) s_h[i] = 0;
+  __syncthreads();
+  const int span = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += span) {
+    const float s = __ldg(sc + i);
+    unsigned long long key;
+    if (retina_survivor(p, b, i, HW, AK, im_h, im_w, min_size, s, key)) atomicAdd(&s_h[score_bin(p, s)], 1u);
+  }
+  __syncthreads();
+  uint32_t* gh = p.hist + (size_t)b * kScoreBins;
+  for (int i = threadIdx.x; i < kScoreBins; i += blockDim.x)
+    if (s_h[i]) atomicAdd(gh + i, s_h[i]);
+}
+
+// Pass 2: find the lowest bin that can still hold one of the top `pre` survivors, stream cls_prob again and keep
+// the survivors at or above it as keys (warp-aggregated append).
+__global__ void __launch_bounds__(256) retina_candidates_kernel(const __grid_constant__ RetinaParams p) {
+  __shared__ uint32_t s_part[256];
+  __shared__ int s_cut;
+  const int b = blockIdx.y;
+  const int HW = p.H * p.W, AK = p.A * p.K, count = AK * HW;
+  {  // suffix sums of the histogram, 18 bins per thread: cut = highest bin with (survivors in bins >= cut) >= pre
+    constexpr int kPer = kScoreBins / 256;
+    const uint32_t* gh = p.hist + (size_t)b * kScoreBins;
+    uint32_t mine = 0;
+    for (int j = 0; j < kPer; ++j) mine += gh[threadIdx.x * kPer + j];
+    s_part[threadIdx.x] = mine;
+    if (threadIdx.x == 0) s_cut = 0;
+    __syncthreads();
+    uint32_t above = 0;  // survivors in the bins of the threads above this one
+    for (int t = threadIdx.x + 1; t < 256; ++t) above += s_part[t];
+    if (above < (uint32_t)p.pre && above + mine >= (uint32_t)p.pre) {  // the cut lies in this thread's bins
+      int j = kPer - 1;
+      for (; j > 0; --j) {
+        above += gh[threadIdx.x * kPer + j];
+        if (above >= (uint32_t)p.pre) break;
+      }
+      s_cut = threadIdx.x * kPer + j;
+    }
+    __syncthreads();
+  }
+  const int cut = s_cut;  // 0 when there are fewer than `pre` survivors: keep them all
   const float im_h = __ldg(p.im_info + b * 3), im_w = __ldg(p.im_info + b * 3 + 1);
   const float min_size = __fmul_rn((float)p.min_size, __ldg(p.im_info + b * 3 + 2));
   const float* sc = p.cls_prob + (size_t)b * count;
@@ -95,15 +168,7 @@ __global__ void __launch_bounds__(256) retina_candidates_kernel(const __grid_con
     unsigned long long key = 0;
     if (i < count) {
       const float s = __ldg(sc + i);
-      if (s > p.thresh) {  // FilterBoxKernel :218: zeroed when score <= thresh
-        const int a = i / HW, r = i - a * HW, h = r / p.W, w = r - h * p.W;
-        const float4 bx = retina_decode(p, b, a / p.K, h, w, im_h, im_w);
-        const float iw = __fadd_rn(__fsub_rn(bx.z, bx.x), 1.0f), ih = __fadd_rn(__fsub_rn(bx.w, bx.y), 1.0f);
-        if (!(iw < min_size || ih < min_size)) {
-          keep = true;
-          key = sdet::make_key(s, (uint32_t)(r * AK + a));  // reference index (h*W+w)*AK + a
-        }
-      }
+      keep = retina_survivor(p, b, i, HW, AK, im_h, im_w, min_size, s, key) && score_bin(p, s) >= cut;
     }
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     if (m) {
@@ -181,7 +246,7 @@ extern "C" int sdet_gen_anchor(float* out, int H, int W, int feature_stride, con
 
 extern "C" size_t sdet_gen_proposal_retina_workspace(int B, int AK, int H, int W) {
   if (B <= 0 || AK <= 0 || H <= 0 || W <= 0) return 0;
-  return align_up((size_t)B * 4, 256) + (size_t)B * AK * H * W * 8;
+  return align_up((size_t)B * 4 + (size_t)B * kScoreBins * 4, 256) + (size_t)B * AK * H * W * 8;
 }
 
 extern "C" int sdet_gen_proposal_retina(const float* cls_prob, const float* bbox_pred, const float* im_info,
@@ -214,11 +279,21 @@ extern "C" int sdet_gen_proposal_retina(const float* cls_prob, const float* bbox
   p.pre = (int)std::min<size_t>((size_t)rpn_pre_nms_top_n, count);
   p.pre_pow2 = sdet::next_pow2(p.pre);
   p.out_channel = output_one_hot ? K + 1 : 1;
+  const size_t head = (size_t)B * 4 + (size_t)B * kScoreBins * 4;
   p.cand_count = static_cast<int*>(workspace);
-  p.cand = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + align_up((size_t)B * 4, 256));
+  p.hist = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + (size_t)B * 4);
+  p.thresh_ord = 0;  // filled below (host copy of score_to_sortable)
+  {
+    uint32_t u;
+    std::memcpy(&u, &thresh, 4);
+    p.thresh_ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  }
+  p.cand = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + align_up(head, 256));
   p.out = out; p.out_score = out_score; p.out_rows = rpn_pre_nms_top_n;
-  SDET_CUDA(cudaMemsetAsync(p.cand_count, 0, (size_t)B * 4, st));
-  dim3 grid((unsigned)std::min<size_t>((count + 255) / 256, 148 * 16), (unsigned)B);
+  SDET_CUDA(cudaMemsetAsync(workspace, 0, head, st));
+  dim3 grid((unsigned)std::min<size_t>((count + 255) / 256, 148 * 8), (unsigned)B);
+  retina_hist_kernel<<<grid, 256, 0, st>>>(p);
+  SDET_LAUNCH_CHECK("retina_hist_kernel");
   retina_candidates_kernel<<<grid, 256, 0, st>>>(p);
   SDET_LAUNCH_CHECK("retina_candidates_kernel");
   const size_t smem = (size_t)sdet::next_pow2(p.pre) * 8;
