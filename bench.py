@@ -295,13 +295,14 @@ class DcnSoftNms:
     over 80 classes x <=1000 boxes per image.  Inference: no collective."""
     name = "dcn_softnms"
     text = ("dcn faster_r50v1_fpn + soft-NMS hot path, bs=2/GPU: 3 x DeformableConvolution(256->256, 3x3, dg=4) on "
-            "(2,256,50,84) [deformable im2col + cuBLAS GEMM] + batched linear soft-NMS (80 classes x <=1000 boxes/img)")
+            "(2,256,50,84) channels-last [deformable im2col + cuBLAS GEMM] + batched linear soft-NMS (80 classes x <=1000 "
+            "boxes/img)")
     train = False
-    kernel = "deform_im2col_tiled_kernel (DCNv1 sampling, %d x 256 x 50 x 84, dg=4)"
+    kernel = "deform_im2col_cl_kernel (DCNv1 sampling over channels-last features, %d x 256 x 50 x 84, dg=4)"
 
     @staticmethod
     def make_inputs(rng, B):
-        d = {"data": rng.standard_normal((B, 256, 50, 84), dtype=np.float32),
+        d = {"data": rng.standard_normal((B, 50, 84, 256), dtype=np.float32),  # channels-last (B,H,W,C)
              "offset": rng.standard_normal((B, 72, 50, 84), dtype=np.float32) * 2,
              "weight": rng.standard_normal((256, 256, 3, 3), dtype=np.float32) * 0.02}
         P, m = B * 80, 1000
@@ -319,25 +320,32 @@ class DcnSoftNms:
         from simpledet_b200 import _lib
 
         x = d["data"]
-        B, C, H, W = x.shape
+        B, H, W, C = x.shape
         L = _lib.lib()
         st = torch.cuda.current_stream().cuda_stream
-        wmat = d["weight"].reshape(C, C * 9)
-        col = torch.empty((B, C * 9, H * W), device=x.device)
+        wp = d["weight"].permute(2, 3, 1, 0).reshape(9 * C, C)   # W'[(tap, c)][f]
+        col_t = torch.empty((B, H * W, 9 * C), device=x.device)
         for blk in range(3):
             if ev and blk == 0:
                 ev[0].record()
-            _lib.check(L.sdet_deformable_im2col(x.data_ptr(), d["offset"].data_ptr(), col.data_ptr(), B, C, H, W, 3, 3, 1, 1,
-                                                1, 1, 1, 1, 4, st))
+            _lib.check(L.sdet_deformable_im2col_nhwc(x.data_ptr(), d["offset"].data_ptr(), col_t.data_ptr(), B, C, H, W, 3, 3,
+                                                     1, 1, 1, 1, 1, 1, 4, st))
             if ev and blk == 0:
                 ev[1].record()
-            x = torch.matmul(wmat, col).reshape(B, C, H, W)   # dense contraction: cuBLAS (tensor-core library work)
+            x = torch.matmul(col_t, wp).view(B, H, W, C)   # dense contraction: cuBLAS (library work); output channels-last
         ob, oi, oc = ops.soft_nms_batched(d["dets"], 0.5, 0.5, 0.001, 1, counts=d["counts"])
-        return {"result": (x[:, :8].contiguous(), oc)}
+        return {"result": (x[..., :8].contiguous(), oc)}
 
     @staticmethod
     def roofline_bytes(out, d, B):
         return 4 * (B * 256 * 50 * 84 + B * 72 * 50 * 84 + B * 256 * 9 * 50 * 84)   # sz(data)+sz(offset)+sz(col)
+
+    @staticmethod
+    def prepare_cpu(d):
+        """The numpy restatement reads NCHW: the 16 channels it samples, re-laid once outside the timed region."""
+        d = dict(d)
+        d["data_nchw16"] = np.ascontiguousarray(d["data"][..., :16].transpose(0, 3, 1, 2))
+        return d
 
     @staticmethod
     def cpu(d, n_images):
@@ -346,7 +354,7 @@ class DcnSoftNms:
 
         for b in range(n_images):
             # the numpy restatement of deformable_im2col is slow: one deformable group's worth of channels per image
-            np_ops.deformable_im2col(d["data"][b:b + 1, :16], d["offset"][b:b + 1, :18], (3, 3), (1, 1), (1, 1), (1, 1), 1)
+            np_ops.deformable_im2col(d["data_nchw16"][b:b + 1], d["offset"][b:b + 1, :18], (3, 3), (1, 1), (1, 1), (1, 1), 1)
             for p in range(b * 80, (b + 1) * 80):
                 oracle.soft_nms(d["dets"][p, :d["counts"][p]], 0.5, 0.5, 0.001, 1)
 

@@ -35,6 +35,12 @@ def main():
     def fwd():
         _lib.check(L.sdet_deformable_im2col(data.data_ptr(), offset.data_ptr(), col.data_ptr(), *geom, st))
 
+    data_cl = data.permute(0, 2, 3, 1).contiguous()
+    col_t = torch.empty((B, H * W, 9 * C), device=dev)
+
+    def fwd_cl():
+        _lib.check(L.sdet_deformable_im2col_nhwc(data_cl.data_ptr(), offset.data_ptr(), col_t.data_ptr(), *geom, st))
+
     def bwd():
         _lib.check(L.sdet_deformable_col2im(gcol.data_ptr(), data.data_ptr(), offset.data_ptr(), gdata.data_ptr(),
                                             goff.data_ptr(), *geom, st))
@@ -55,10 +61,12 @@ def main():
 
     nbytes = 4 * (data.numel() + offset.numel() + col.numel())
     t_f = time_op(fwd)
+    t_cl = time_op(fwd_cl)
     t_b = time_op(bwd)
     nb_b = 4 * (gcol.numel() + 2 * data.numel() + 2 * offset.numel())  # read gcol, data, offset; write both grads
     print(json.dumps({"shape": [B, C, H, W], "dg": a.dg, "im2col_us": round(t_f, 2), "im2col_alg_bytes": nbytes,
-                      "im2col_GBps": round(nbytes / t_f / 1e3, 1), "col2im_us": round(t_b, 2),
+                      "im2col_GBps": round(nbytes / t_f / 1e3, 1), "im2col_nhwc_us": round(t_cl, 2),
+                      "im2col_nhwc_GBps": round(nbytes / t_cl / 1e3, 1), "col2im_us": round(t_b, 2),
                       "col2im_alg_bytes": nb_b, "col2im_GBps": round(nb_b / t_b / 1e3, 1)}))
 
 

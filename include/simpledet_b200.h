@@ -394,6 +394,12 @@ int sdet_soft_nms(const float* dets, const int* counts, int problems, int m, flo
 int sdet_deformable_im2col(const float* data, const float* offset, float* col, int B, int C, int H, int W,
                            int kernel_h, int kernel_w, int pad_h, int pad_w, int stride_h, int stride_w,
                            int dilate_h, int dilate_w, int num_deformable_group, void* stream);
+/* Channels-last sampling: data (B,H,W,C), same offset tensor, col_t (B, Ho*Wo, KH*KW, C) - the K index of the
+ * following GEMM is (tap, channel), its output (B, Ho*Wo, F) is channels-last too.  Same values as
+ * sdet_deformable_im2col, element for element.  C / num_deformable_group must be even. */
+int sdet_deformable_im2col_nhwc(const float* data, const float* offset, float* col_t, int B, int C, int H, int W,
+                                int kernel_h, int kernel_w, int pad_h, int pad_w, int stride_h, int stride_w,
+                                int dilate_h, int dilate_w, int num_deformable_group, void* stream);
 int sdet_deformable_col2im(const float* grad_col, const float* data, const float* offset, float* grad_data,
                            float* grad_offset, int B, int C, int H, int W, int kernel_h, int kernel_w,
                            int pad_h, int pad_w, int stride_h, int stride_w, int dilate_h, int dilate_w,

@@ -109,6 +109,7 @@ _SIGNATURES = {
     "sdet_sigmoid_ce_backward": [_P, _P, _P, c_int, c_size_t, c_float, _P, c_size_t, _P],
     "sdet_soft_nms": [_P, _P, c_int, c_int, c_float, c_float, c_float, c_int, _P, _P, _P, _P],
     "sdet_deformable_im2col": [_P, _P, _P] + [c_int] * 13 + [_P],
+    "sdet_deformable_im2col_nhwc": [_P, _P, _P] + [c_int] * 13 + [_P],
     "sdet_deformable_col2im": [_P, _P, _P, _P, _P] + [c_int] * 13 + [_P],
     "sdet_nms_workspace": [c_int, c_int],
     "_nms": [_P, POINTER(c_int), _P, c_int, c_int, c_float, c_int],

@@ -38,6 +38,15 @@ def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor
     return t.contiguous()
 
 
+def _dev_any_layout(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    """The checks of _dev without forcing NCHW contiguity (for operators that take channels-last tensors as they are)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: simpledet_b200 ops are CUDA-only (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t
+
+
 def _p(t: torch.Tensor | None):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -965,13 +974,31 @@ class _DeformConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, data, offset, weight, bias, geo):
         kh, kw, ph_, pw_, sh, sw, dh, dw, ng, dg = geo
-        data, offset, weight = _dev(data, "data"), _dev(offset, "offset"), _dev(weight, "weight")
+        data, offset, weight = _dev_any_layout(data, "data"), _dev(offset, "offset"), _dev(weight, "weight")
         B, C, H, W = data.shape
         F = weight.shape[0]
         Ho = (H + 2 * ph_ - (dh * (kh - 1) + 1)) // sh + 1
         Wo = (W + 2 * pw_ - (dw * (kw - 1) + 1)) // sw + 1
         if tuple(offset.shape) != (B, dg * 2 * kh * kw, Ho, Wo):
             raise ValueError(f"offset must be {(B, dg * 2 * kh * kw, Ho, Wo)}, got {tuple(offset.shape)}")
+        P, T = Ho * Wo, kh * kw
+        if ng == 1 and (C // dg) % 2 == 0:
+            # channels-last: sample into col_t (B, P, T*C), contract with W'[(tap, c)][f]; input and output stay NHWC
+            # in memory (the tensors handed back are NCHW-shaped views, torch's channels_last format)
+            x = data.permute(0, 2, 3, 1)
+            if not x.is_contiguous():
+                x = x.contiguous()  # NCHW-contiguous input: one re-layout pass
+            col_t = torch.empty((B, P, T * C), device=data.device, dtype=torch.float32)
+            check(_lib.lib().sdet_deformable_im2col_nhwc(_p(x), _p(offset), _p(col_t), B, C, H, W, kh, kw, ph_, pw_,
+                                                         sh, sw, dh, dw, dg, _stream()))
+            wp = weight.permute(2, 3, 1, 0).reshape(T * C, F)
+            out = torch.matmul(col_t, wp)  # library GEMM (cuBLAS via torch)
+            if bias is not None:
+                out = out + bias.view(1, 1, F)
+            ctx.save_for_backward(data, offset, weight, col_t)
+            ctx.geo, ctx.has_bias, ctx.cl = geo, bias is not None, True
+            return out.view(B, Ho, Wo, F).permute(0, 3, 1, 2)
+        data = data.contiguous()
         col = torch.empty((B, C * kh * kw, Ho * Wo), device=data.device, dtype=torch.float32)
         check(_lib.lib().sdet_deformable_im2col(_p(data), _p(offset), _p(col), B, C, H, W, kh, kw, ph_, pw_, sh,
                                                 sw, dh, dw, dg, _stream()))
@@ -982,7 +1009,7 @@ class _DeformConvFn(torch.autograd.Function):
         if bias is not None:
             out = out + bias.view(1, F, 1, 1)
         ctx.save_for_backward(data, offset, weight, col)
-        ctx.geo, ctx.has_bias = geo, bias is not None
+        ctx.geo, ctx.has_bias, ctx.cl = geo, bias is not None, False
         return out
 
     @staticmethod
@@ -991,12 +1018,22 @@ class _DeformConvFn(torch.autograd.Function):
         kh, kw, ph_, pw_, sh, sw, dh, dw, ng, dg = ctx.geo
         B, C, H, W = data.shape
         F = weight.shape[0]
-        gout = _dev(gout, "gout")
+        gout = gout if gout.is_cuda else _dev(gout, "gout")
         P = gout.shape[2] * gout.shape[3]
-        go = gout.reshape(B, ng, F // ng, P)
-        wg = weight.reshape(ng, F // ng, (C // ng) * kh * kw)
-        gcol = torch.einsum("gfk,bgfp->bgkp", wg, go).reshape(B, C * kh * kw, P).contiguous()
-        gweight = torch.einsum("bgfp,bgkp->gfk", go, col.reshape(B, ng, (C // ng) * kh * kw, P)).reshape(weight.shape)
+        data, offset = data.contiguous(), offset.contiguous()
+        if ctx.cl:
+            T = kh * kw
+            go = gout.permute(0, 2, 3, 1).reshape(B, P, F)
+            wp = weight.permute(2, 3, 1, 0).reshape(T * C, F)
+            gcol_t = torch.matmul(go, wp.t())                                    # (B, P, T*C)
+            gcol = gcol_t.view(B, P, T, C).permute(0, 3, 2, 1).reshape(B, C * T, P).contiguous()
+            gweight = torch.einsum("bpk,bpf->kf", col, go).view(kh, kw, C, F).permute(3, 2, 0, 1).contiguous()
+        else:
+            gout = gout.contiguous()
+            go = gout.reshape(B, ng, F // ng, P)
+            wg = weight.reshape(ng, F // ng, (C // ng) * kh * kw)
+            gcol = torch.einsum("gfk,bgfp->bgkp", wg, go).reshape(B, C * kh * kw, P).contiguous()
+            gweight = torch.einsum("bgfp,bgkp->gfk", go, col.reshape(B, ng, (C // ng) * kh * kw, P)).reshape(weight.shape)
         gdata = torch.empty_like(data)
         goff = torch.empty_like(offset)
         check(_lib.lib().sdet_deformable_col2im(_p(gcol), _p(data), _p(offset), _p(gdata), _p(goff), B, C, H, W, kh,

@@ -43,6 +43,40 @@ def test_im2col_matches_restatement(cuda, stride, dilate, pad, dg):
     np.testing.assert_allclose(col.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("stride,dilate,pad,dg,C", [(1, 1, 1, 4, 8), (2, 1, 1, 1, 6), (1, 2, 2, 2, 132), (1, 1, 1, 4, 256)])
+def test_im2col_channels_last_is_the_same_columns(cuda, stride, dilate, pad, dg, C):
+    """sdet_deformable_im2col_nhwc: col_t[b, p, t, c] == col[b, c*9 + t, p] bit for bit (same arithmetic, other layout),
+    including pixels past the last full block of 32, clamped borders and samples outside the image."""
+    rng = np.random.default_rng(stride * 100 + dilate * 10 + dg)
+    B, H, W = 2, 13, 19
+    data = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    Ho = (H + 2 * pad - (dilate * 2 + 1)) // stride + 1
+    Wo = (W + 2 * pad - (dilate * 2 + 1)) // stride + 1
+    offset = (rng.standard_normal((B, dg * 18, Ho, Wo)) * 3).astype(np.float32)
+    offset[0, 0] = 0.0
+    offset[0, 1] = 50.0
+    d, o = _t(data, cuda), _t(offset, cuda)
+    geo = (3, 3, pad, pad, stride, stride, dilate, dilate, dg)
+    col = _im2col(d, o, geo)
+    x = d.permute(0, 2, 3, 1).contiguous()
+    col_t = torch.empty((B, Ho * Wo, 9, C), device=cuda)
+    check(_lib.lib().sdet_deformable_im2col_nhwc(x.data_ptr(), o.data_ptr(), col_t.data_ptr(), B, C, H, W, 3, 3, pad, pad,
+                                                 stride, stride, dilate, dilate, dg, None))
+    torch.cuda.synchronize()
+    assert torch.equal(col_t.permute(0, 3, 2, 1).reshape(B, C * 9, Ho * Wo), col)
+
+
+def test_channels_last_input_gives_the_same_output(cuda):
+    torch.manual_seed(3)
+    x = torch.randn(2, 16, 20, 24, device=cuda)
+    w = torch.randn(32, 16, 3, 3, device=cuda) * 0.1
+    off = torch.randn(2, 4 * 18, 20, 24, device=cuda)
+    kw = dict(kernel=(3, 3), pad=(1, 1), num_filter=32, num_deformable_group=4, no_bias=True)
+    y0 = ops.DeformableConvolution(x, off, w, **kw)
+    y1 = ops.DeformableConvolution(x.contiguous(memory_format=torch.channels_last), off, w, **kw)
+    assert y0.shape == (2, 32, 20, 24) and torch.equal(y0, y1)
+
+
 def test_zero_offset_equals_convolution(cuda):
     torch.manual_seed(0)
     x = torch.randn(2, 16, 20, 24, device=cuda)
