@@ -431,28 +431,23 @@ class ClockSampler:
 
 def bind_to_gpu_numa_node(local_rank):
     """Pin this rank (and the pinned buffers it allocates next) to the CPUs of its GPU's NUMA node: 8 ranks pushing
-    ~200 MB/step of pinned H2D across the socket interconnect is what bent the end-to-end curve at N=4/8."""
+    ~200 MB/step of pinned H2D across the socket interconnect is what bent the end-to-end curve at N=4/8.
+    The CPU list comes from sysfs (`local_cpulist` of the GPU's PCI device); nothing is bound unless the list holds
+    at least 8 CPUs this process may use (a wrong, tiny set would serialise the launch thread)."""
     try:
-        out = subprocess.run(["nvidia-smi", "topo", "-C", "-i", str(local_rank)], capture_output=True, text=True, timeout=10).stdout
-        cpus = None
-        for line in out.splitlines():
-            if ":" in line and any(ch.isdigit() for ch in line.split(":")[-1]):
-                cpus = line.split(":")[-1].strip()
-        if cpus is None:
-            out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=10).stdout
-            for line in out.splitlines():
-                f = line.split()
-                if f and f[0] == f"GPU{local_rank}":
-                    cand = [x for x in f if x[0].isdigit() and ("-" in x or "," in x)]
-                    cpus = cand[0] if cand else None
-        if not cpus:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if not bus:
             return None
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/local_cpulist"
+        cpus = open(path).read().strip()
         ids = set()
         for part in cpus.split(","):
             a, _, b = part.partition("-")
             ids.update(range(int(a), int(b or a) + 1))
         ids &= os.sched_getaffinity(0)
-        if ids:
+        if len(ids) >= 8:
             os.sched_setaffinity(0, ids)
             return cpus
     except Exception:
