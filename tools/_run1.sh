@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_dcn_gpu.py -x -q -m gpu 2>&1 | tail -3
-python benchmarks/dcn_bench.py
-ncu --set full --clock-control none --import-source on -k regex:deform_im2col_cl_kernel -c 1 -o gpurun_out/r02_dcn_cl -f python benchmarks/dcn_bench.py --iters 1 > /dev/null 2>&1
+python -m pytest tests -x -q -m gpu -k "soft or nms or Nms" 2>&1 | tail -4
+timeout 600 python bench.py --workload dcn_softnms --no-cpu-baseline | tail -1 | cut -c1-220
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_dcn_softnms.csv python bench.py --workload dcn_softnms --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
