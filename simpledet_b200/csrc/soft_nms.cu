@@ -22,10 +22,10 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 
 __device__ __forceinline__ int block_scan_excl(int v, int* s_warp, int* total) {
-  // exclusive prefix sum of v over the CTA (kThreads = 256 -> 8 warps); all threads call
+  // exclusive prefix sum of v over the CTA; all threads call
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int inc = v;
   for (int o = 1; o < 32; o <<= 1) {
