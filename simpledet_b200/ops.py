@@ -18,7 +18,7 @@ import torch
 from . import _lib
 from ._lib import check
 
-__all__ = ["fpn_roi_align_nhwc", "gpu_nms", "greedy_nms", "bbox_overlaps_cython", "assign_layer_fpn", "BboxPostProcessing", "ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_raw",
+__all__ = ["decode_retina", "fpn_roi_align_nhwc", "gpu_nms", "greedy_nms", "bbox_overlaps_cython", "assign_layer_fpn", "BboxPostProcessing", "ROIAlign_v2", "roi_align_v2_raw", "ROIPooling_v1", "roi_pooling_v1_raw",
            "fpn_roi_align", "fpn_roi_align_raw", "DecodeBBox", "Proposal_v3", "Proposal_v3_fpn", "NMS", "nms_sorted", "get_top_proposal",
            "multiclass_nms", "ProposalTarget", "FocalLoss", "BBoxNorm",
            "SigmoidCrossEntropy", "soft_nms", "soft_nms_batched",
@@ -1282,6 +1282,94 @@ def BboxPostProcessing(cls_score, bbox_xyxy, max_det_per_image=100, min_det_scor
 
 
 # Registry keyed by the reference's operator names (what symbol/builder.py binds by string).
+
+# --------------------------------------------------------------------------------------------
+# CustomOp 'decode_retina' (models/retinanet/decode_retina.py:35-146; the test branch of
+# models/retinanet/builder.py:395-413 when the config does not ask for GenProposalRetina)
+# --------------------------------------------------------------------------------------------
+def decode_retina(cls_probs, bbox_preds, im_info, stride, scales, ratios, per_level_top_n, thresh):
+    """-> (bbox_xyxy (1, L*per_level_top_n, 4), cls_score (1, L*per_level_top_n, num_class)), float32, zero-padded.
+
+    Per level: pairs with score > thresh (0.0 on the coarsest level), the per_level_top_n best of them, anchors =
+    cell * stride + base anchor (AnchorTarget2D.base_anchor, core/detection_input.py:374-400), nonlinear_pred
+    decode in float64 with the float32 exp and the BBOX_XFORM_CLIP clamp the numpy code has, clip to the image.
+    The reference keeps the selected pairs in np.argpartition's (unspecified) order; here each level's block is
+    ordered by descending score, ties by flat index - the same set of rows.  Batch size 1 like the reference.
+    A host-composed operator: the selection is torch.topk (library), everything stays on the device and nothing
+    synchronises."""
+    import math
+
+    import numpy as np
+
+    L_ = len(stride)
+    cls_probs = [_dev(c, f"cls_prob[{i}]") for i, c in enumerate(cls_probs)]
+    bbox_preds = [_dev(c, f"bbox_pred[{i}]") for i, c in enumerate(bbox_preds)]
+    im_info = _dev(im_info, "im_info")
+    if cls_probs[0].shape[0] != 1:
+        raise ValueError("Multiple images each device is not implemented")  # the reference's message
+    A = len(scales) * len(ratios)
+    K = cls_probs[0].shape[1] // A
+    dev = cls_probs[0].device
+    top = int(per_level_top_n)
+    boxes_out = torch.zeros((1, top * L_, 4), device=dev, dtype=torch.float32)
+    score_out = torch.zeros((1, top * L_, K + 1), device=dev, dtype=torch.float32)
+    clip = float(np.float32(math.log(1000.0 / 16.0)))  # np.minimum(float32 array, python float) stays float32
+    hmax, wmax = im_info[0, 0].double() - 1.0, im_info[0, 1].double() - 1.0
+    blocks, nvalid = [], []
+    for s_, cp, bp in zip(stride, cls_probs, bbox_preds):
+        H, W = cp.shape[2], cp.shape[3]
+        # base anchors: aspect-major, np.round = round-half-even, float64
+        side = float(s_)
+        ctr = 0.5 * (side - 1)
+        asp = np.asarray(ratios, np.float64)
+        wr = np.round(np.sqrt(side * side / asp))
+        hr = np.round(wr * asp)
+        sc = np.asarray(scales, np.float64)
+        ws_, hs_ = np.outer(wr, sc).ravel(), np.outer(hr, sc).ravel()
+        base = torch.from_numpy(np.stack([ctr - 0.5 * (ws_ - 1), ctr - 0.5 * (hs_ - 1), ctr + 0.5 * (ws_ - 1),
+                                          ctr + 0.5 * (hs_ - 1)], 1)).to(dev)                      # (A, 4) float64
+        thr = float(thresh) if s_ != max(stride) else 0.0
+        flat = cp.reshape(-1)                                                                       # (a, k, y, x) order
+        k_ = min(top, flat.numel())
+        vals, inds = torch.topk(torch.where(flat > thr, flat, torch.full_like(flat, -1.0)), k_, sorted=True)
+        ok = vals > thr
+        x = inds % W
+        y = (inds // W) % H
+        cls = (inds // (H * W)) % K
+        a = inds // (H * W * K)
+        cell = torch.stack([x, y, x, y], 1).to(torch.float32) * float(s_)
+        anchors = (cell.double() + base[a]).to(torch.float32).double()   # float32 `+=` float64 rounds to float32 first
+        d = bp.reshape(A, 4, H, W)[a, :, y, x]                                                      # (k, 4) float32
+        wdt = anchors[:, 2] - anchors[:, 0] + 1.0
+        hgt = anchors[:, 3] - anchors[:, 1] + 1.0
+        cx = anchors[:, 0] + 0.5 * (wdt - 1.0)
+        cy = anchors[:, 1] + 0.5 * (hgt - 1.0)
+        pcx = d[:, 0].double() * wdt + cx
+        pcy = d[:, 1].double() * hgt + cy
+        pw = torch.exp(torch.clamp(d[:, 2], max=clip)).double() * wdt
+        ph = torch.exp(torch.clamp(d[:, 3], max=clip)).double() * hgt
+        bx = torch.stack([pcx - 0.5 * (pw - 1.0), pcy - 0.5 * (ph - 1.0), pcx + 0.5 * (pw - 1.0),
+                          pcy + 0.5 * (ph - 1.0)], 1)
+        lim = torch.stack([wmax, hmax, wmax, hmax])
+        bx = torch.clamp(torch.minimum(bx, lim), min=0.0)
+        blocks.append((bx.to(torch.float32), vals, cls, ok))
+        nvalid.append(ok.sum())
+    # the reference concatenates the levels' kept rows: row offsets are running counts of valid rows (on the device);
+    # rows that did not pass the threshold are sent to a scratch row past the end
+    nrow = top * L_
+    bbuf = torch.zeros((nrow + 1, 4), device=dev, dtype=torch.float32)
+    sbuf = torch.zeros((nrow + 1, K + 1), device=dev, dtype=torch.float32)
+    off = torch.zeros((), device=dev, dtype=torch.long)
+    for (bx, vals, cls, ok), n in zip(blocks, nvalid):
+        rank = torch.cumsum(ok.long(), 0) - 1 + off          # valid rows are a prefix of the sorted block
+        rows = torch.where(ok, rank, torch.full_like(rank, nrow)).clamp(max=nrow)
+        bbuf.index_put_((rows,), bx)
+        sbuf.index_put_((rows, cls + 1), vals)
+        off = off + n
+    boxes_out[0] = bbuf[:nrow]
+    score_out[0] = sbuf[:nrow]
+    return boxes_out, score_out
+
 OPS = {
     "_contrib_ROIAlign_v2": ROIAlign_v2,
     "ROIPooling_v1": ROIPooling_v1,
@@ -1305,6 +1393,7 @@ OPS = {
     "get_top_proposal": get_top_proposal,  # mx.operator.register('get_top_proposal')
     "assign_layer_fpn": assign_layer_fpn,  # mx.operator.register('assign_layer_fpn')
     "BboxPostProcessing": BboxPostProcessing,  # mx.operator.register('BboxPostProcessing')
+    "decode_retina": decode_retina,            # mx.operator.register("decode_retina")
     # plain callables of operator_py (same names and argument meaning)
     "gpu_nms": gpu_nms,
     "greedy_nms": greedy_nms,
