@@ -145,10 +145,11 @@ __device__ __forceinline__ void patch_bin(const float* __restrict__ q, const int
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      wt[i][j][0] = __fmul_rn(ha[i][0], wb[j][0]);  // top-left      (roi_align_v2-inl.h:133-136)
-      wt[i][j][1] = __fmul_rn(ha[i][1], wb[j][0]);  // bottom-left
-      wt[i][j][2] = __fmul_rn(ha[i][0], wb[j][1]);  // top-right
-      wt[i][j][3] = __fmul_rn(ha[i][1], wb[j][1]);  // bottom-right
+      // (top-left, bottom-left) = (1-fy, fy) * (1-fx) and (top-right, bottom-right) = (1-fy, fy) * fx
+      // (roi_align_v2-inl.h:133-136), two products per packed instruction, each rounded like a lone multiply
+      const uint64_t hp = pack2(ha[i][0], ha[i][1]);
+      unpack2(fma2(hp, pack2(wb[j][0], wb[j][0]), nz2), wt[i][j][0], wt[i][j][1]);
+      unpack2(fma2(hp, pack2(wb[j][1], wb[j][1]), nz2), wt[i][j][2], wt[i][j][3]);
     }
   int ro[2 + CY], co[2 + CX];
   ro[0] = 0;
