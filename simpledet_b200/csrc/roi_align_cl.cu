@@ -262,30 +262,6 @@ __device__ __forceinline__ void patch_row(const RoiAlignArgs& a, const PlanRecor
   for (int pw = 0; pw < PW; ++pw) {
     const AxisRec wr = s_w[pw];
     const int cx = wr.cls;
-#ifdef SDET_CL_PREFETCH
-    if (pw + 1 < PW) {  // pull the next bin's patch into L1 while this one is computed
-      const int lo_n = s_w[pw + 1].lo0, cls_n = s_w[pw + 1].cls, pk = s_w[pw + 1].pack;
-      if (cls_n >= 0) {
-        const float* qn = reinterpret_cast<const float*>(r0v) + lo_n * C;
-        int ro[4], co[4];
-        ro[0] = 0; co[0] = 0;
-        if (CY == 2) { ro[1] = (hr.pack & 1023) * rs; ro[2] = ((hr.pack >> 10) & 1023) * rs; ro[3] = (hr.pack >> 20) * rs; }
-        else { ro[1] = rs; ro[2] = 2 * rs; ro[3] = 0; }
-        if (cls_n == 2) { co[1] = (pk & 1023) * C; co[2] = ((pk >> 10) & 1023) * C; co[3] = (pk >> 20) * C; }
-        else { co[1] = C; co[2] = 2 * C; co[3] = 0; }
-        const int ncn = 2 + cls_n;
-#pragma unroll
-        for (int r = 0; r < 2 + CY; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (c < ncn) {
-#pragma unroll
-              for (int g = 0; g < kG; ++g)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(qn + g * kClGroup + ro[r] + co[c]));
-            }
-      }
-    }
-#endif
     if (cx >= 0) {
       float m[2 * kG];
       const float* q = reinterpret_cast<const float*>(r0v) + wr.lo0 * C;
