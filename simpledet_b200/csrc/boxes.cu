@@ -644,16 +644,18 @@ size_t nms_ws_bytes(int P, int n) {
 
 int run_mask_and_scan(const float* dets, const int* counts, int P, int n, float thr, int ge,
                       unsigned long long* mask, const ScanOut& so, cudaStream_t st, const float* sets = nullptr) {
+  // every limit is checked before anything is enqueued
+  const int nbuf = scan_smem_bytes(n, 2) <= 96 * 1024 ? 2 : 1;
+  const size_t smem = scan_smem_bytes(n, nbuf);
+  if (n > 12288 || smem > 200 * 1024)
+    return sdet::fail(SDET_ERR_UNSUPPORTED, "NMS over %d boxes needs %zu B shared memory", n, smem);
+  if (P > 65535) return sdet::fail(SDET_ERR_UNSUPPORTED, "more than 65535 NMS problems in one call (grid.z)");
   const int cbs = (n + 63) / 64;
   const long long tiles = (long long)P * cbs * (cbs + 1) / 2;
   const int tpc = (int)std::max<long long>(1, std::min<long long>(cbs, tiles / 1200));
   dim3 grid((unsigned)((cbs + tpc - 1) / tpc), (unsigned)cbs, (unsigned)P);
   nms_mask_kernel<<<grid, 64, 0, st>>>(dets, counts, n, thr, ge, mask, sets, tpc);
   SDET_LAUNCH_CHECK("nms_mask_kernel");
-  const int nbuf = scan_smem_bytes(n, 2) <= 96 * 1024 ? 2 : 1;
-  const size_t smem = scan_smem_bytes(n, nbuf);
-  if (n > 12288 || smem > 200 * 1024)
-    return sdet::fail(SDET_ERR_UNSUPPORTED, "NMS over %d boxes needs %zu B shared memory", n, smem);
   if (smem > 48 * 1024)  // per device and cheap: set on every launch, no process-wide cache
     SDET_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   nms_scan_kernel<<<(unsigned)P, 256, smem, st>>>(dets, counts, n, mask, so, nbuf);

@@ -16,7 +16,7 @@ constexpr int kRadixBits = 11;
 constexpr int kRadixBins = 1 << kRadixBits;
 
 __device__ __forceinline__ uint32_t score_to_sortable(float s) {
-  const uint32_t u = __float_as_uint(s);
+  const uint32_t u = __float_as_uint(s + 0.f);  // -0.0 -> +0.0: thrust::greater ties them, the index decides
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // larger float -> larger uint
 }
 __device__ __forceinline__ uint64_t make_key(float s, uint32_t idx) {

@@ -32,16 +32,27 @@ def _dev(t: torch.Tensor | None, name: str, dtype=torch.float32) -> torch.Tensor
         return None
     if not t.is_cuda:
         raise RuntimeError(f"{name}: simpledet_b200 ops are CUDA-only (no CPU fallback)")
+    _same_device(t, name)
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype} (the reference path is fp32, "
                         "symbol/builder.py:882-894)")
     return t.contiguous()
 
 
+def _same_device(t: torch.Tensor, name: str) -> None:
+    """The C ABI launches on the calling thread's current device and stream: a tensor that lives elsewhere would be
+    dereferenced on the wrong GPU.  Fail loudly instead (wrap the call in `with torch.cuda.device(t.device):`)."""
+    cur = torch.cuda.current_device()
+    if t.device.index != cur:
+        raise RuntimeError(f"{name} is on cuda:{t.device.index} but the current device is cuda:{cur}: "
+                           "run the operator under `with torch.cuda.device(tensor.device):`")
+
+
 def _dev_any_layout(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
     """The checks of _dev without forcing NCHW contiguity (for operators that take channels-last tensors as they are)."""
     if not t.is_cuda:
         raise RuntimeError(f"{name}: simpledet_b200 ops are CUDA-only (no CPU fallback)")
+    _same_device(t, name)
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
     return t
@@ -114,6 +125,8 @@ class _ROIAlignV2Fn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, ograd):
+        if not ctx.saved_tensors:  # data did not require grad (only rois did): their gradient is identically zero
+            return None, None, None, None, None
         ax, ay = ctx.saved_tensors
         B, C, H, W = ctx.dshape
         N = ctx.rshape[1]
@@ -224,6 +237,7 @@ class _FpnRoiAlignFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rois, strides, ph, pw, scale0, lvl0, *feats):
         need = any(f.requires_grad for f in feats)
+        ctx.num_inputs = 6 + len(feats)
         out, ax, ay, levels = fpn_roi_align_raw(feats, rois, strides, (ph, pw), scale0, lvl0,
                                                 with_argmax=need)
         if need:
@@ -234,6 +248,8 @@ class _FpnRoiAlignFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, ograd):
+        if not ctx.saved_tensors:  # no feature map required grad
+            return (None,) * ctx.num_inputs
         ax, ay, levels = ctx.saved_tensors
         ograd = _dev(ograd, "ograd")
         grads = [torch.empty(s, device=ograd.device, dtype=torch.float32) for s in ctx.shapes]
@@ -756,11 +772,11 @@ def ProposalTarget(rois, gt_boxes, num_classes, batch_images, image_rois, fg_thr
         raise ValueError("image_rois must be > 0 (ProposalTarget_v2 handles -1)")
     dev = rois.device
     NC4 = 4 * int(num_classes)
-    o_rois = torch.empty((B, IR, 4), device=dev)
-    o_lab = torch.empty((B, IR), device=dev)
-    o_tgt = torch.empty((B, IR, NC4), device=dev)
-    o_wgt = torch.empty((B, IR, NC4), device=dev)
-    o_iou = torch.empty((B, IR), device=dev)
+    o_rois = torch.empty((B, IR, 4), device=dev, dtype=torch.float32)
+    o_lab = torch.empty((B, IR), device=dev, dtype=torch.float32)
+    o_tgt = torch.empty((B, IR, NC4), device=dev, dtype=torch.float32)
+    o_wgt = torch.empty((B, IR, NC4), device=dev, dtype=torch.float32)
+    o_iou = torch.empty((B, IR), device=dev, dtype=torch.float32)
     kept = torch.empty((B, IR), device=dev, dtype=torch.int32) if return_debug else None
     T = R + G
     if priorities is not None:
@@ -858,7 +874,7 @@ class _SigmoidCEFn(torch.autograd.Function):
     def forward(ctx, data, label, grad_scale):
         data, label = _dev(data, "data"), _dev(label, "label")
         R, D = data.shape
-        out = torch.empty((R,), device=data.device)
+        out = torch.empty((R,), device=data.device, dtype=torch.float32)
         ws = _ws(8 * R, data.device)
         check(_lib.lib().sdet_sigmoid_ce_forward(_p(data), _p(label), _p(out), R, D, _p(ws), 8 * R, _stream()))
         ctx.save_for_backward(data, label)
@@ -898,11 +914,11 @@ def ProposalTarget_v2(rois, gt_boxes, valid_ranges, num_classes, batch_images, i
     IR = R if int(image_rois) == -1 else int(image_rois)
     dev = rois.device
     NC4 = 4 * int(num_classes)
-    o_rois = torch.empty((B, IR, 4), device=dev)
-    o_lab = torch.empty((B, IR), device=dev)
-    o_tgt = torch.empty((B, IR, NC4), device=dev)
-    o_wgt = torch.empty((B, IR, NC4), device=dev)
-    o_iou = torch.empty((B, IR), device=dev)
+    o_rois = torch.empty((B, IR, 4), device=dev, dtype=torch.float32)
+    o_lab = torch.empty((B, IR), device=dev, dtype=torch.float32)
+    o_tgt = torch.empty((B, IR, NC4), device=dev, dtype=torch.float32)
+    o_wgt = torch.empty((B, IR, NC4), device=dev, dtype=torch.float32)
+    o_iou = torch.empty((B, IR), device=dev, dtype=torch.float32)
     kept = torch.empty((B, IR), device=dev, dtype=torch.int32) if return_debug else None
     T = R + G
     if priorities is not None:
