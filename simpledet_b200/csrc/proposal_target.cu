@@ -126,7 +126,7 @@ proposal_target_kernel(const __grid_constant__ PTParams p) {
   uint32_t* s_prio = reinterpret_cast<uint32_t*>(s_kept + IR + T);            // T (current draw)
   int* s_gsrc = reinterpret_cast<int*>(s_prio + T);                           // G source rows of valid gt
   __shared__ int s_warp[33];
-  __shared__ int s_total;
+  __shared__ int s_total, s_last[2];
 
   const float* rois = p.rois + (size_t)b * R * 4;
   const float* gt = p.gt + (size_t)b * G * 5;
@@ -334,8 +334,19 @@ __device__ __forceinline__ void dda_point(int xs, int ys, int dx, int dy, double
   }
 }
 
+struct EdgeRec {
+  double sl;
+  int xs, ys, dx, dy, npts, start;
+  bool flip;
+};
+constexpr int kMaxEdges = 512;
+
 __global__ void __launch_bounds__(256) poly_mask_kernel(const MaskParams p) {
   extern __shared__ int s_tog[];  // M*M + 2 toggle counters, then the OR-accumulated mask (M*M bytes as ints)
+  __shared__ EdgeRec s_edge[kMaxEdges];
+  __shared__ unsigned s_chunk[400];
+  __shared__ int s_cpar[400];
+  __shared__ int s_total, s_last[2];
   const int row = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int M = p.M, MM = M * M;
   float* out = p.mask + ((size_t)b * p.NM + row) * MM;
@@ -369,40 +380,63 @@ __global__ void __launch_bounds__(256) poly_mask_kernel(const MaskParams p) {
         X = (int)__dadd_rn(__dmul_rn(5.0, a), .5);
         Y = (int)__dadd_rn(__dmul_rn(5.0, c), .5);
       };
-      for (int e = tid; e < k; e += blockDim.x) {  // one edge per thread
-        int xs, ys, xe, ye;
-        vert(e, xs, ys);
-        vert(e + 1, xe, ye);
-        int dx = abs(xe - xs), dy = abs(ys - ye);
-        const bool flip = (dx >= dy && xs > xe) || (dx < dy && ys > ye);
-        if (flip) {
-          int t = xs; xs = xe; xe = t;
-          t = ys; ys = ye; ye = t;
-        }
-        const double sl = dx >= dy ? __ddiv_rn((double)(ye - ys), (double)dx) : __ddiv_rn((double)(xe - xs), (double)dy);
-        const int npts = max(dx, dy) + 1;
-        // previous point of the concatenated point list: the last point of the previous edge
-        int pu = 0, pv = 0;
-        bool have_prev = false;
-        if (e > 0) {
-          int axs, ays, axe, aye;
-          vert(e - 1, axs, ays);
-          vert(e, axe, aye);
-          int adx = abs(axe - axs), ady = abs(ays - aye);
-          const bool af = (adx >= ady && axs > axe) || (adx < ady && ays > aye);
-          if (af) {
-            int t = axs; axs = axe; axe = t;
-            t = ays; ays = aye; aye = t;
+      // edges in batches of kMaxEdges (COCO polygons can have more vertices than fit the shared table)
+      for (int e0 = 0; e0 < k; e0 += kMaxEdges) {
+        const int nb = min(kMaxEdges, k - e0);
+        // ---- one thread per edge: the edge's DDA parameters and point count into shared memory
+        for (int e = tid; e < nb; e += blockDim.x) {
+          int xs, ys, xe, ye;
+          vert(e0 + e, xs, ys);
+          vert(e0 + e + 1, xe, ye);
+          const int dx = abs(xe - xs), dy = abs(ys - ye);
+          const bool flip = (dx >= dy && xs > xe) || (dx < dy && ys > ye);
+          if (flip) {
+            int t = xs; xs = xe; xe = t;
+            t = ys; ys = ye; ye = t;
           }
-          const double asl = adx >= ady ? __ddiv_rn((double)(aye - ays), (double)adx)
-                                        : __ddiv_rn((double)(axe - axs), (double)ady);
-          dda_point(axs, ays, adx, ady, asl, af, max(adx, ady), pu, pv);
-          have_prev = true;
+          EdgeRec er;
+          er.xs = xs; er.ys = ys; er.dx = dx; er.dy = dy; er.flip = flip;
+          er.sl = dx >= dy ? __ddiv_rn((double)(ye - ys), (double)dx) : __ddiv_rn((double)(xe - xs), (double)dy);
+          er.npts = max(dx, dy) + 1;
+          er.start = 0;
+          s_edge[e] = er;
         }
-        for (int d = 0; d < npts; ++d) {
-          int u, v;
-          dda_point(xs, ys, dx, dy, sl, flip, d, u, v);
-          if (have_prev && u != pu) {
+        __syncthreads();
+        if (tid == 0) {  // start of every edge in the concatenated point list
+          int acc = 0;
+          for (int e = 0; e < nb; ++e) {
+            s_edge[e].start = acc;
+            acc += s_edge[e].npts;
+          }
+          s_total = acc;
+        }
+        __syncthreads();
+        // ---- one thread per POINT of the concatenated list (rleFrPoly walks them in order and compares each with
+        // its predecessor; both are functions of (edge, d) alone, so every point is independent)
+        const int total = s_total;
+        for (int i = tid; i < total; i += blockDim.x) {
+          int lo = 0, hi = nb - 1;  // last edge whose start <= i
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_edge[mid].start <= i) lo = mid;
+            else hi = mid - 1;
+          }
+          const EdgeRec er = s_edge[lo];
+          const int d = i - er.start;
+          int u, v, pu, pv;
+          dda_point(er.xs, er.ys, er.dx, er.dy, er.sl, er.flip, d, u, v);
+          if (d > 0) {
+            dda_point(er.xs, er.ys, er.dx, er.dy, er.sl, er.flip, d - 1, pu, pv);
+          } else if (lo > 0) {  // the last point of the previous edge
+            const EdgeRec pr = s_edge[lo - 1];
+            dda_point(pr.xs, pr.ys, pr.dx, pr.dy, pr.sl, pr.flip, pr.npts - 1, pu, pv);
+          } else if (e0 > 0) {  // ... which belongs to the previous batch
+            pu = s_last[0];
+            pv = s_last[1];
+          } else {
+            continue;  // the very first point has no predecessor
+          }
+          if (u != pu) {
             double xd = (double)(u < pu ? u : u - 1);
             xd = __dsub_rn(__ddiv_rn(__dadd_rn(xd, .5), 5.0), .5);
             if (!(floor(xd) != xd || xd < 0 || xd > (double)(M - 1))) {
@@ -415,19 +449,44 @@ __global__ void __launch_bounds__(256) poly_mask_kernel(const MaskParams p) {
               atomicAdd(&s_tog[min(pos, MM)], 1);
             }
           }
-          pu = u;
-          pv = v;
-          have_prev = true;
+        }
+        __syncthreads();
+        if (tid == 0) {  // hand the batch's last point to the next batch
+          const EdgeRec pr = s_edge[nb - 1];
+          int lu, lv;
+          dda_point(pr.xs, pr.ys, pr.dx, pr.dy, pr.sl, pr.flip, pr.npts - 1, lu, lv);
+          s_last[0] = lu;
+          s_last[1] = lv;
+        }
+        __syncthreads();
+      }
+      // ---- parity prefix over the positions: ballot inside 32-position chunks, then the chunks' parities in order
+      const int nchunk = (MM + 31) / 32;
+      for (int cidx = tid >> 5; cidx < nchunk; cidx += blockDim.x >> 5) {
+        const int j = cidx * 32 + (tid & 31);
+        const unsigned bits = __ballot_sync(0xffffffffu, j < MM && (s_tog[j] & 1));
+        if ((tid & 31) == 0) s_chunk[cidx] = bits;
+      }
+      __syncthreads();
+      if (tid < 32) {  // exclusive parity of the chunks before each chunk (nchunk <= 392 for M <= 112)
+        int carry = 0;
+        for (int c0_ = 0; c0_ < nchunk; c0_ += 32) {
+          const int cidx = c0_ + tid;
+          const int par = cidx < nchunk ? (__popc(s_chunk[cidx]) & 1) : 0;
+          int inc = par;  // inclusive xor-scan over the warp
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= o) inc ^= t;
+          }
+          if (cidx < nchunk) s_cpar[cidx] = carry ^ inc ^ par;
+          carry ^= __shfl_sync(0xffffffffu, inc, 31);
         }
       }
       __syncthreads();
-      // parity prefix over positions (serial per 32-position chunk, chunks combined by thread 0)
-      if (tid == 0) {
-        int par = 0;
-        for (int j = 0; j < MM; ++j) {
-          par ^= (s_tog[j] & 1);
-          if (par) s_acc[j] = 1;
-        }
+      for (int j = tid; j < MM; j += blockDim.x) {
+        const unsigned bits = s_chunk[j >> 5];
+        const int par = s_cpar[j >> 5] ^ (__popc(bits & (0xffffffffu >> (31 - (j & 31)))) & 1);
+        if (par) s_acc[j] = 1;
       }
       __syncthreads();
       offset += cur_len;
