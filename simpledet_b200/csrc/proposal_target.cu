@@ -89,9 +89,10 @@ __device__ void block_priority_sort(int* list, int n, const uint32_t* prio, unsi
     keys[i] = i < n ? (((unsigned long long)prio[list[i]] << 32) | (unsigned)list[i]) : ~0ull;
   __syncthreads();
   for (int size = 2; size <= np2; size <<= 1)
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+    for (int sh = 31 - __clz(size >> 1); sh >= 0; --sh) {  // stride = 1 << sh: shifts, not divisions, per element
+      const int stride = 1 << sh;
       for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
-        const int lo = ((t / stride) * (stride << 1)) + (t % stride), hi = lo + stride;
+        const int lo = ((t >> sh) << (sh + 1)) | (t & (stride - 1)), hi = lo + stride;
         const bool asc = ((lo & size) == 0);
         const unsigned long long a = keys[lo], c = keys[hi];
         if ((a > c) == asc) {
@@ -239,14 +240,10 @@ proposal_target_kernel(const __grid_constant__ PTParams p) {
     __syncthreads();
   }
 
-  // ---- outputs.  Everything is zero-initialised by the reference (-inl.h:188-192).
+  // ---- outputs.  Everything is zero-initialised by the reference (-inl.h:188-192): the two (IR, 4*num_classes)
+  // planes were zero-filled by the launcher (a wide memset, not 650 KB of stores from this one CTA).
   float* o_tgt = p.tgt + (size_t)b * IR * NC4;
   float* o_wgt = p.wgt + (size_t)b * IR * NC4;
-  for (size_t e = tid; e < (size_t)IR * NC4; e += blockDim.x) {
-    o_tgt[e] = 0.f;
-    o_wgt[e] = 0.f;
-  }
-  __syncthreads();
   for (int i = tid; i < IR; i += blockDim.x) {
     const size_t row = (size_t)b * IR + i;
     float4 rb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -542,6 +539,8 @@ static int proposal_target_core(const float* rois, const float* gt_boxes, const 
   if (smem > 220 * 1024) return sdet::fail(SDET_ERR_UNSUPPORTED, "ProposalTarget needs %zu B shared memory", smem);
   if (smem > 48 * 1024)  // per device and cheap: set on every launch, no process-wide cache
     SDET_CUDA(cudaFuncSetAttribute(proposal_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SDET_CUDA(cudaMemsetAsync(bbox_targets, 0, sizeof(float) * (size_t)B * image_rois * p.NC4, (cudaStream_t)stream));
+  SDET_CUDA(cudaMemsetAsync(bbox_weights, 0, sizeof(float) * (size_t)B * image_rois * p.NC4, (cudaStream_t)stream));
   proposal_target_kernel<<<(unsigned)B, kThreads, smem, (cudaStream_t)stream>>>(p);
   SDET_LAUNCH_CHECK("proposal_target_kernel");
   return SDET_OK;
