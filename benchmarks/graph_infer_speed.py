@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--weights", default="zero")
     ap.add_argument("--tf32", type=int, default=1)
     ap.add_argument("--channels-last", type=int, default=1)
+    ap.add_argument("--graph", type=int, default=0, help="1: replay the forward pass from one CUDA graph")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.backends.cudnn.allow_tf32 = bool(a.tf32)
@@ -36,20 +37,21 @@ def main():
         shapes, rng_std=None if a.weights == "zero" else 0.02)
     feed = dict(data=torch.ones(shapes["data"], device=dev), im_info=torch.tensor([[400.0, 666.5, 2.0]], device=dev),
                 im_id=torch.ones(1, device=dev), rec_id=torch.ones(1, device=dev))
+    step = ex.capture(**feed) if a.graph else ex.forward
     with torch.no_grad():
         for _ in range(3):
-            ex.forward(**feed)
+            step(**feed)
         torch.cuda.synchronize()
         n0 = _lib.launch_count()
         tic = time.time()
         for _ in range(a.count):
-            ex.forward(**feed)
+            step(**feed)
             torch.cuda.synchronize()   # output.wait_to_read() per iteration, as the reference script does
         toc = time.time()
     ms = (toc - tic) / a.count * 1000
     print(json.dumps({"graph": "faster_r50v1_fpn_1x test_symbol (551 nodes, 41.8 M parameters)", "weights": a.weights,
                       "ms_per_iter": round(ms, 3), "images_per_s": round(1000 / ms, 2), "count": a.count,
-                      "tf32_conv": bool(a.tf32), "channels_last": bool(a.channels_last),
+                      "tf32_conv": bool(a.tf32), "channels_last": bool(a.channels_last), "cuda_graph": bool(a.graph),
                       "sdet_launches_per_iter": (_lib.launch_count() - n0) // a.count}))
 
 

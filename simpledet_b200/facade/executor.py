@@ -239,14 +239,64 @@ class Executor:
     channels_last memory format (what the tensor-core convolutions prefer) and hands the FPN levels to the fused
     RoIAlign as NHWC - no re-layout pass."""
 
-    def __init__(self, sym: S.Symbol, device="cuda:0", channels_last=True, fuse_fpn_roi_align=True):
+    def __init__(self, sym: S.Symbol, device="cuda:0", channels_last=True, fuse_fpn_roi_align=True, fold_bn=True):
         import torch
 
         self.sym, self.device = sym, torch.device(device)
-        self.channels_last, self.fuse = channels_last, fuse_fpn_roi_align
+        self.channels_last, self.fuse, self.fold_bn = channels_last, fuse_fpn_roi_align, fold_bn
         self.params: dict = {}
         self.order = sym._topo()
         self._fusions = self._find_fpn_roi_align() if fuse_fpn_roi_align else {}
+        self._bn_of_conv = self._find_conv_bn() if fold_bn else {}
+        self._folded = None  # conv node id -> (weight, bias) with the BatchNorm folded in; rebuilt after init_params
+
+    # ---- pattern: Convolution -> BatchNorm on moving statistics (the frozen BN of the detection backbones) ==> the
+    # affine map is folded into the convolution's weights once, the BatchNorm node becomes a pass-through
+    def _find_conv_bn(self):
+        uses: dict[int, int] = {}
+        for node in self.order:
+            for s_ in node.inputs:
+                for n, _ in s_.entries:
+                    uses[id(n)] = uses.get(id(n), 0) + 1
+        for n, _ in self.sym.entries:
+            uses[id(n)] = uses.get(id(n), 0) + 1
+        pairs = {}
+        for node in self.order:
+            if node.op != "BatchNorm":
+                continue
+            names = _flat_names(node)
+            ins = [e for s_ in node.inputs for e in s_.entries]
+            byname = dict(zip(names, ins))
+            src = byname.get("data", ins[0])[0]
+            stat = [byname.get(k) for k in ("gamma", "beta", "moving_mean", "moving_var")]
+            if src.op != "Convolution" or uses.get(id(src), 0) != 1 or any(e is None or e[0].op is not None for e in stat):
+                continue
+            cn = dict(zip(_flat_names(src), [e for s_ in src.inputs for e in s_.entries]))
+            if cn.get("weight") is None or cn["weight"][0].op is not None or ("bias" in cn and cn["bias"][0].op is not None):
+                continue
+            pairs[id(src)] = node
+        return pairs
+
+    def _fold(self, torch):
+        folded = {}
+        for node in self.order:
+            bn = self._bn_of_conv.get(id(node))
+            if bn is None:
+                continue
+            cn = dict(zip(_flat_names(node), [e for s_ in node.inputs for e in s_.entries]))
+            bnn = dict(zip(_flat_names(bn), [e for s_ in bn.inputs for e in s_.entries]))
+            P = lambda e: self.params[e[0].name]  # noqa: E731
+            w = P(cn["weight"]).double()
+            b = P(cn["bias"]).double() if "bias" in cn else torch.zeros(w.shape[0], device=w.device, dtype=torch.float64)
+            gamma = torch.ones_like(P(bnn["gamma"])) if _b(bn.attrs.get("fix_gamma", True)) else P(bnn["gamma"])
+            scale = gamma.double() / torch.sqrt(P(bnn["moving_var"]).double() + float(_t(bn.attrs.get("eps", 1e-3))))
+            wf = (w * scale.view(-1, 1, 1, 1)).float()
+            bf = ((b - P(bnn["moving_mean"]).double()) * scale + P(bnn["beta"]).double()).float()
+            if self.channels_last:
+                wf = wf.contiguous(memory_format=torch.channels_last)
+            folded[id(node)] = (wf, bf)
+        self._folded = folded
+        self._folded_bn = {id(bn) for bn in self._bn_of_conv.values()}
 
     # ---- parameters
     def init_params(self, input_shapes: dict, arg_params=None, aux_params=None, rng_std=None):
@@ -275,6 +325,7 @@ class Executor:
                 self.params[name] = torch.zeros(shp, device=self.device)
             else:
                 self.params[name] = torch.randn(shp, device=self.device, generator=g) * rng_std
+        self._folded = None
         return self
 
     # ---- pattern: assign_layer_fpn -> L x ROIAlign_v2 -> add_n  ==> one fused FPN RoIAlign
@@ -310,6 +361,8 @@ class Executor:
         from .. import ops
 
         vals: dict[int, list] = {}
+        if self.fold_bn and self._folded is None:
+            self._fold(torch)
         for node in self.order:
             if node.op is None:
                 if node.name in inputs:
@@ -352,6 +405,34 @@ class Executor:
             vals[id(node)] = self._run(node, ins, ops, torch)
         return [vals[id(n)][i] for n, i in self.sym.entries]
 
+    def capture(self, **inputs):
+        """Record one forward pass into a CUDA graph and return `run(**inputs) -> outputs` that replays it (inputs are
+        copied into the graph's static buffers; the outputs are the graph's static output tensors).  The ~700 small
+        launches of a detection graph are host-bound when issued one by one; every detection operator behind `OPS`
+        is capture-safe (no allocation, no host synchronisation: tests/test_cuda_graph_gpu.py)."""
+        import torch
+
+        static = {k: (v.t if hasattr(v, "t") and not callable(getattr(v, "t")) else torch.as_tensor(v)).to(
+            self.device, torch.float32).clone() for k, v in inputs.items()}
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(3):  # cuDNN autotuning, lazy workspaces, BatchNorm folding
+                self.forward(**static)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph), torch.no_grad():
+            outs = self.forward(**static)
+
+        def run(**new_inputs):
+            for k, v in new_inputs.items():
+                static[k].copy_(v.t if hasattr(v, "t") and not callable(getattr(v, "t")) else torch.as_tensor(v))
+            graph.replay()
+            return outs
+
+        run.graph = graph
+        return run
+
     def _is_fused_member(self, node):
         return any(node in ras for _, ras, _r in self._fusions.values())
 
@@ -371,7 +452,10 @@ class Executor:
             data = arg.get("data", x[0])
             if self.channels_last and data.dim() == 4:
                 data = data.contiguous(memory_format=torch.channels_last)
-            return [F.conv2d(data, arg["weight"], arg.get("bias"), _tup(a.get("stride", 1)), _tup(a.get("pad", 0)),
+            w, bias = arg["weight"], arg.get("bias")
+            if self._folded and id(node) in self._folded:
+                w, bias = self._folded[id(node)]
+            return [F.conv2d(data, w, bias, _tup(a.get("stride", 1)), _tup(a.get("pad", 0)),
                              _tup(a.get("dilate", 1)), int(_t(a.get("num_group", 1))))]
         if op == "FullyConnected":
             data = arg.get("data", x[0])
@@ -380,6 +464,8 @@ class Executor:
             return [F.linear(data, arg["weight"], arg.get("bias"))]
         if op == "BatchNorm":  # inference form (use_global_stats / is_train=False): moving statistics
             data = arg.get("data", x[0])
+            if self._folded and id(node) in self._folded_bn:
+                return [data]  # already applied by the convolution that feeds it
             g = torch.ones_like(arg["gamma"]) if _b(a.get("fix_gamma", True)) else arg["gamma"]
             return [F.batch_norm(data, arg["moving_mean"], arg["moving_var"], g, arg["beta"], False, 0.0,
                                  float(_t(a.get("eps", 1e-3))))]

@@ -93,6 +93,7 @@ class DataParallelExecutorGroup:
     def reshape(self, data_shapes, label_shapes):
         self.data_shapes, self.label_shapes = data_shapes, label_shapes
         self.batch_size = data_shapes[0].shape[0]
+        self._run = None
 
     def set_params(self, arg_params, aux_params, allow_extra=False):
         for name, arr in list((arg_params or {}).items()) + list((aux_params or {}).items()):
@@ -100,6 +101,8 @@ class DataParallelExecutorGroup:
                 self.exe.params[name].copy_(arr.t if isinstance(arr, nd.NDArray) else torch.as_tensor(arr))
             elif not allow_extra:
                 raise ValueError(f"Find name '{name}' that is not in the arguments")
+        self.exe._folded = None  # folded BatchNorm weights and the recorded graph were built from the old values
+        self._run = None
 
     def get_params(self, arg_params, aux_params):
         for n in self.param_names:
@@ -111,7 +114,18 @@ class DataParallelExecutorGroup:
         if isinstance(data_batch, list):
             data_batch = data_batch[0]
         feed = {d.name: v for d, v in zip(self.data_shapes, data_batch.data)}
-        self.outputs = self.exe.forward(**feed)
+        # inference with fixed shapes: record the pass once, replay it afterwards (the ~700 launches of a detection
+        # graph are host-bound one by one); any change of parameters or shapes drops the recording
+        if getattr(self, "_run", None) is None and getattr(self, "_graph_ok", True) and self.exe.device.type == "cuda":
+            try:
+                self._run = self.exe.capture(**feed)
+            except Exception as exc:  # keep working eagerly, say why once
+                self._graph_ok = False
+                import warnings
+
+                warnings.warn(f"CUDA-graph capture of the bound symbol failed, running eagerly: {exc}")
+        with torch.no_grad():
+            self.outputs = self._run(**feed) if getattr(self, "_run", None) is not None else self.exe.forward(**feed)
 
     def get_outputs(self, merge_multi_context=True, begin=0, end=None):
         outs = [nd.NDArray(o) for o in self.outputs]

@@ -57,3 +57,33 @@ def test_reference_builders_run_unchanged_on_the_facade():
     assert rpn.infer_shape(**SHAPES)[1][-2:] == [(1, 1000, 4), (1, 1000, 1)]
     for m in [k for k in sys.modules if k.split(".")[0] in ("config", "symbol", "models", "core", "utils", "operator_py")]:
         sys.modules.pop(m, None)   # leave no half-imported reference packages behind for other tests
+
+
+def test_frozen_batchnorm_is_folded_into_the_convolution():
+    """Convolution -> BatchNorm on moving statistics (fixbn) runs as ONE convolution with folded weights; same
+    values up to fp32 rounding, and a BatchNorm whose input is shared is left alone."""
+    import torch
+
+    from simpledet_b200.facade import mxnext_impl as X
+
+    data = S.Variable("data")
+    c1 = X.conv(data, "c1", 8, kernel=3, stride=1)
+    r = X.relu(X.fixbn(c1, "bn1"))
+    c2 = X.conv(r, "c2", 4, kernel=1)
+    shared = X.add_n(X.fixbn(c2, "bn2"), c2, name="sum")  # c2 has two consumers: bn2 must not be folded
+    shapes = dict(data=(1, 3, 16, 20))
+    x = torch.randn(shapes["data"], generator=torch.Generator().manual_seed(2))
+    res = {}
+    for fold in (False, True):
+        ex = E.Executor(shared, "cpu", channels_last=False, fuse_fpn_roi_align=False, fold_bn=fold)
+        ex.init_params(shapes, rng_std=0.3)
+        g = torch.Generator().manual_seed(1)
+        for k, v in ex.params.items():
+            if k.endswith("moving_var"):
+                ex.params[k] = torch.rand(v.shape, generator=g) + 0.5
+            if k.endswith(("moving_mean", "beta")):
+                ex.params[k] = torch.randn(v.shape, generator=g)
+        ex._folded = None
+        assert len(ex._bn_of_conv) == (1 if fold else 0)
+        res[fold] = ex.forward(data=x)[0]
+    torch.testing.assert_close(res[True], res[False], rtol=1e-5, atol=1e-5)

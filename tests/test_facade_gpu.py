@@ -86,3 +86,58 @@ def test_faster_r50v1_fpn_graph_runs(cuda):
         assert [tuple(o.shape) for o in outs] == [(1,), (1,), (1, 3), (1, 1000, 81), (1, 1000, 324)]
         assert all(torch.isfinite(o).all() for o in outs)
         np.testing.assert_allclose(outs[3].sum(-1).cpu().numpy(), 1.0, rtol=1e-4)   # class scores are a softmax
+
+
+def test_graph_capture_replays_the_same_outputs(cuda):
+    """Executor.capture: the whole mini FPN graph (convolutions + every detection operator) recorded once and replayed
+    with new inputs gives what the eager pass gives."""
+    sym = _mini_fpn_graph()
+    shapes = dict(data=(1, 3, 128, 160), im_info=(1, 3))
+    gen = torch.Generator(device=cuda).manual_seed(3)
+    ex = facade.Executor(sym, cuda).init_params(shapes, rng_std=0.05)
+    im_info = torch.tensor([[128.0, 160.0, 1.0]], device=cuda)
+    a = torch.randn(shapes["data"], device=cuda, generator=gen)
+    b = torch.randn(shapes["data"], device=cuda, generator=gen)
+    with torch.no_grad():
+        want = [[o.clone() for o in ex.forward(data=x, im_info=im_info)] for x in (a, b)]
+    run = ex.capture(data=a, im_info=im_info)
+    for x, w in ((b, want[1]), (a, want[0]), (b, want[1])):
+        got = run(data=x, im_info=im_info)
+        torch.cuda.synchronize()
+        for g, t in zip(got, w):
+            assert torch.equal(g, t)
+
+
+def test_module_executor_group_records_and_replays(cuda):
+    """The DetModule-facing executor group: the first forward records the pass into a CUDA graph, later ones replay it;
+    set_params drops the recording (and the folded BatchNorm weights).  Outputs equal the eager executor's."""
+    from simpledet_b200 import facade as F
+    from simpledet_b200.facade import module as M
+    from simpledet_b200.facade import ndarray as nd
+
+    mx = F.install()
+    sym = _mini_fpn_graph()
+    shapes = [nd.DataDesc("data", (1, 3, 128, 160)), nd.DataDesc("im_info", (1, 3))]
+    names = [n for n in sym.list_arguments() if n not in ("data", "im_info")]
+    grp = M.DataParallelExecutorGroup(sym, [mx.gpu(0)], None, shapes, None, names, False, False)
+    gen = torch.Generator(device=cuda).manual_seed(5)
+    params = {n: nd.NDArray(torch.randn(grp.exe.params[n].shape, device=cuda, generator=gen) * 0.05) for n in names}
+    grp.set_params(params, {})
+    im_info = torch.tensor([[128.0, 160.0, 1.0]], device=cuda)
+    xs = [torch.randn((1, 3, 128, 160), device=cuda, generator=gen) for _ in range(2)]
+    eager = facade.Executor(sym, cuda)
+    eager.init_params({"data": (1, 3, 128, 160), "im_info": (1, 3)})
+    for n in names:
+        eager.params[n].copy_(params[n].t)
+    eager._folded = None
+    for x in (xs[0], xs[1], xs[0]):
+        grp.forward(nd.DataBatch([nd.NDArray(x), nd.NDArray(im_info)]))
+        got = [o.t for o in grp.get_outputs()]
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            want = eager.forward(data=x, im_info=im_info)
+        for g, w in zip(got, want):
+            assert torch.equal(g, w)
+    assert grp._run is not None and getattr(grp, "_graph_ok", True)
+    grp.set_params(params, {})
+    assert grp._run is None
