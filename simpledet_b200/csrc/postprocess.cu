@@ -45,21 +45,34 @@ class_sort_kernel(const float* __restrict__ cls_score, const float* __restrict__
   const int p = blockIdx.x, b = p / ncls, cid = first_class + p % ncls;
   if (threadIdx.x == 0) s_valid = 0;
   __syncthreads();
-  int mine = 0;
-  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+  // survivors are appended (warp-aggregated) in any order - the sort fixes it - so that only next_pow2(survivors)
+  // keys are sorted, not n_pad: most classes of an image keep a handful of the N candidates
+  const int lane = threadIdx.x & 31;
+  for (int i0 = 0; i0 < N; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
     uint64_t key = 0ull;
+    bool keep = false;
     if (i < N) {
       const float s = __ldg(cls_score + ((size_t)b * N + i) * K + cid);
       if (s > min_score) {  // detection_test.py:243
         key = sdet::make_key(s, (uint32_t)i);
-        ++mine;
+        keep = true;
       }
     }
-    s_keys[i] = key;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_valid, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (keep) s_keys[base + __popc(m & ((1u << lane) - 1))] = key;
+    }
   }
-  if (mine) atomicAdd(&s_valid, mine);
   __syncthreads();
-  sdet::block_bitonic_sort_desc(reinterpret_cast<uint64_t*>(s_keys), n_pad);
+  int sort_n = 1;
+  while (sort_n < s_valid) sort_n <<= 1;
+  for (int i = s_valid + threadIdx.x; i < sort_n; i += blockDim.x) s_keys[i] = 0ull;
+  __syncthreads();
+  sdet::block_bitonic_sort_desc(reinterpret_cast<uint64_t*>(s_keys), sort_n);
   const int nv = s_valid;
   if (threadIdx.x == 0) counts[p] = nv;
   for (int j = threadIdx.x; j < n_pad; j += blockDim.x) {
