@@ -301,6 +301,27 @@ def test_gen_proposal_retina_few_survivors(cuda):
     assert np.count_nonzero(rs) == 2
 
 
+def test_gen_proposal_retina_dense_and_tied_scores(cuda):
+    """The histogram pre-filter's corner cases: (a) nearly every pair passes the threshold and the scores sit in a few
+    exact values, so the cut bin holds far more than `pre` keys and the order is decided by the reference index;
+    (b) scores far above the binned range (> 1) share the top bin; (c) thresh = 0."""
+    rng = np.random.default_rng(54)
+    B, A, K, H, W, stride = 2, 9, 8, 11, 17, 16
+    cls = rng.choice(np.array([0.25, 0.5, 0.75], np.float32), (B, A * K, H, W))
+    cls[1] = (rng.uniform(0, 1, (A * K, H, W)) ** 2).astype(np.float32)
+    cls[1, :3] *= 1000.0
+    deltas = (rng.standard_normal((B, 4 * A, H, W)) * 0.3).astype(np.float32)
+    im_info = np.array([[H * stride, W * stride, 1.0]] * B, np.float32)
+    anchors = oracle.gen_anchor(H, W, stride, (4, 5, 6), (0.5, 1, 2))
+    for thresh, pre in ((0.05, 300), (0.0, 1000), (0.6, 50)):
+        kw = dict(num_anchors=A, rpn_pre_nms_top_n=pre, rpn_min_size=0, thresh=thresh)
+        rb, rs = oracle.gen_proposal_retina(cls, deltas, im_info, anchors, **kw)
+        gb, gs = ops.GenProposalRetina(_t(cls, cuda), _t(deltas, cuda), _t(im_info, cuda), _t(anchors, cuda),
+                                       feature_stride=stride, **kw)
+        assert np.array_equal(gs.cpu().numpy(), rs), (thresh, pre)
+        np.testing.assert_allclose(gb.cpu().numpy(), rb, rtol=1e-5, atol=1e-3)
+
+
 def test_final_detections(cuda):
     """detection_test.py:233-291: per-class NMS then sorted(result, key=score)[-max_det:] per image,
     including equal scores across classes (the later class survives the cut)."""

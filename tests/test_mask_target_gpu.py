@@ -71,3 +71,28 @@ def test_mask_target_filter_scales(cuda):
                                  valid_ranges=_t(vr, cuda))
     assert np.array_equal(res[0].cpu().numpy(), ref[0]) and np.array_equal(res[1].cpu().numpy(), ref[1])
     assert np.array_equal(res[4].cpu().numpy(), ref[5])
+
+
+def test_polygon_with_more_edges_than_one_batch(cuda):
+    """A 700-vertex polygon (COCO has them): poly_mask_kernel walks its edges in batches of 512 and hands the last
+    point of a batch to the next one.  Exact against the oracle rasteriser."""
+    nv = 700
+    ang = np.linspace(0, 2 * np.pi, nv, endpoint=False)
+    rad = 45 + 12 * np.sin(9 * ang) + 3 * np.cos(31 * ang)
+    xs, ys = 160 + rad * np.cos(ang), 140 + rad * np.sin(ang) * 0.8
+    PL = 2 + 1 + 2 * nv + 5
+    polys = np.full((1, 2, PL), -1, np.float32)
+    polys[0, 0, :3] = [3, 1, 2 * nv]
+    polys[0, 0, 3:3 + 2 * nv] = np.stack([xs, ys], 1).reshape(-1)
+    gt = np.full((1, 2, 5), -1, np.float32)
+    gt[0, 0] = [xs.min(), ys.min(), xs.max(), ys.max(), 3]
+    rois = np.zeros((1, 8, 4), np.float32)
+    rois[0, 0] = gt[0, 0, :4] + [2, -3, -4, 5]
+    pr = np.zeros((1, 3, 10), np.uint32)
+    for M in (28, 56):
+        res = ops.ProposalMaskTarget(_t(rois, cuda), _t(gt, cuda), _t(polys, cuda), 81, 1, 4, M, 0.5, 0.5, 0.0, False,
+                                     priorities=_t(pr.astype(np.int64), cuda))
+        kept = res[0].cpu().numpy()[0, 0]
+        want = oracle.poly2mask(kept, polys[0, 0], M)
+        got = res[4].cpu().numpy()[0, 0]
+        assert np.array_equal(got, want) and 0.2 < want.mean() < 0.9
