@@ -31,6 +31,8 @@ SOURCES = [
     ("proposal_target.cc", True),         # SampleROI, BBoxOverlap, targets (:22-227) + ProposalTargetOp::Forward
     ("proposal_target_v2.cc", True),
     ("contrib/generate_anchor.cc", False),  # GenAnchorOp<cpu>::Forward + gen_anchor_utils (generate_anchor-inl.h:139-183)
+    ("contrib/focal_loss.cc", False),     # FocalLossOp::Forward / Backward as mshadow expressions (focal_loss-inl.h:100-231)
+    ("contrib/bbox_norm.cc", False),      # BBoxNormOp::Backward (bbox_norm-inl.h:99-129)
 ]
 # -O2 without -march: like MXNet's x86-64 CPU build there is no FMA instruction to contract into;
 # -ffp-contract=off makes that explicit.

@@ -101,6 +101,28 @@ def forward(op: str, kwargs: dict, inputs, out_shapes=None, dev: str = "cpu", re
     return outputs
 
 
+def backward(op: str, kwargs: dict, out_grads, inputs, outputs, reqs=None):
+    """Backward of a legacy OperatorProperty operator (FocalLoss, BBoxNorm): -> list of in_grad arrays, one per
+    input, written by the operator's own Backward."""
+    L = lib()
+    ogs = [np.ascontiguousarray(a, np.float32) for a in out_grads]
+    ins = [np.ascontiguousarray(a, np.float32) for a in inputs]
+    outs = [np.ascontiguousarray(a, np.float32) for a in outputs]
+    igs = [np.zeros(a.shape, np.float32) for a in ins]
+    reqs = reqs or [K_WRITE] * len(ins)
+
+    def ptrs(arrs):
+        return (ctypes.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs])
+
+    gnd, gdims = _shape_rows(ogs)
+    ind, idims = _shape_rows(ins)
+    ond, odims = _shape_rows(outs)
+    _check(L.ref_backward(op.encode(), _kw(kwargs), len(ogs), ptrs(ogs), gnd, gdims.ctypes.data_as(ctypes.c_void_p),
+                          len(ins), ptrs(ins), ind, idims.ctypes.data_as(ctypes.c_void_p), len(outs), ptrs(outs), ond,
+                          odims.ctypes.data_as(ctypes.c_void_p), ptrs(igs), (ctypes.c_int * len(ins))(*reqs)))
+    return igs
+
+
 def set_rand_const(v: int):
     """Every rand() the reference's std::random_shuffle draws returns v.  v = 0: each shuffle rotates its list
     right by one (libstdc++ Fisher-Yates, j = rand() % (i+1)); v = 27719 = lcm(1..12) - 1: identity for lists

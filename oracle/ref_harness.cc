@@ -145,4 +145,36 @@ int ref_forward(const char* op, const char* kwargs, const char* dev, int n_in, v
   });
 }
 
+// Backward of a legacy OperatorProperty operator: out_grad / in_data / out_data in, in_grad out (float32 over caller
+// memory; shapes as rows of 8 int64).  The operator object is created exactly as ref_forward creates it.
+int ref_backward(const char* op, const char* kwargs, int n_og, void** og_ptrs, const int* og_ndims, const int64_t* og_dims,
+                 int n_in, void** in_ptrs, const int* in_ndims, const int64_t* in_dims, int n_out, void** out_ptrs,
+                 const int* out_ndims, const int64_t* out_dims, void** ig_ptrs, const int* reqs) {
+  return guarded([&] {
+    std::vector<mxnet::TBlob> out_grad, in_data, out_data, in_grad, aux;
+    std::vector<mxnet::TShape> in_shape;
+    std::vector<mxnet::OpReqType> req;
+    for (int i = 0; i < n_og; ++i)
+      out_grad.emplace_back(static_cast<float*>(og_ptrs[i]), make_shape(og_ndims[i], og_dims + 8 * i));
+    for (int i = 0; i < n_in; ++i) {
+      in_shape.push_back(make_shape(in_ndims[i], in_dims + 8 * i));
+      in_data.emplace_back(static_cast<float*>(in_ptrs[i]), in_shape.back());
+      in_grad.emplace_back(static_cast<float*>(ig_ptrs[i]), in_shape.back());
+      req.push_back((mxnet::OpReqType)reqs[i]);
+    }
+    for (int i = 0; i < n_out; ++i)
+      out_data.emplace_back(static_cast<float*>(out_ptrs[i]), make_shape(out_ndims[i], out_dims + 8 * i));
+    if (ref_op_kind(op) != 1) throw dmlc::Error(std::string(op) + " is not an OperatorProperty operator");
+    std::unique_ptr<mxnet::OperatorProperty> prop(mxnet::shim_reg::PropEntry::All()[op].make());
+    prop->Init(parse_kwargs(kwargs));
+    mxnet::OpContext ctx;
+    ctx.is_train = 1;
+    for (int i = 0; i < 4; ++i) ctx.requested.emplace_back();  // BackwardResource: at most one temp space in these operators
+    std::vector<int> in_type(n_in, mshadow::kFloat32);
+    std::unique_ptr<mxnet::Operator> o(prop->CreateOperatorEx(mxnet::Context::CPU(), &in_shape, &in_type));
+    if (!o) throw dmlc::Error("CreateOperatorEx returned NULL");
+    o->Backward(ctx, out_grad, in_data, out_data, req, in_grad, aux);
+  });
+}
+
 }  // extern "C"

@@ -138,14 +138,211 @@ inline Shape<5> Shape5(index_t a, index_t b, index_t c, index_t d, index_t e) {
 }
 
 // dense host view; stride_ == shape_[dim-1] always
+// ---- a small mshadow::expr: lazily evaluated element-wise expressions over contiguous tensors.  An expression
+// answers Eval(i) for the flat index i of the DESTINATION and shape() (empty for scalars).  Operator precedence and
+// F<OP> nesting build the same tree mshadow builds, and every node rounds like mshadow's CPU Plan does (one DType
+// operation per node), so `dst = expr` reproduces the reference's CPU arithmetic operation for operation.
+namespace op {
+struct plus { template <typename DType> MSHADOW_XINLINE static DType Map(DType a, DType b) { return a + b; } };
+struct minus { template <typename DType> MSHADOW_XINLINE static DType Map(DType a, DType b) { return a - b; } };
+struct mul { template <typename DType> MSHADOW_XINLINE static DType Map(DType a, DType b) { return a * b; } };
+struct div { template <typename DType> MSHADOW_XINLINE static DType Map(DType a, DType b) { return a / b; } };
+struct identity { template <typename DType> MSHADOW_XINLINE static DType Map(DType a) { return a; } };
+}  // namespace op
+namespace red {
+struct sum {
+  template <typename DType> MSHADOW_XINLINE static void Reduce(volatile DType& dst, volatile DType src) { dst += src; }  // NOLINT
+  template <typename DType> MSHADOW_XINLINE static void SetInitValue(DType& v) { v = 0; }  // NOLINT
+};
+}  // namespace red
+namespace expr {
+typedef std::vector<index_t> ShapeVec;
+inline size_t ShapeSize(const ShapeVec& v) { size_t n = 1; for (auto d : v) n *= (size_t)d; return n; }
+template <typename SubType, typename DType>
+struct Exp {
+  const SubType& self() const { return *static_cast<const SubType*>(this); }
+};
+template <typename DType>
+struct ScalarExp : public Exp<ScalarExp<DType>, DType> {
+  DType scalar_;
+  ScalarExp(DType s) : scalar_(s) {}  // NOLINT
+  DType Eval(size_t) const { return scalar_; }
+  ShapeVec shape() const { return {}; }
+};
+template <typename OP, typename TA, typename TB, typename DType>
+struct BinaryMapExp : public Exp<BinaryMapExp<OP, TA, TB, DType>, DType> {
+  TA lhs_;
+  TB rhs_;
+  BinaryMapExp(const TA& l, const TB& r) : lhs_(l), rhs_(r) {}
+  DType Eval(size_t i) const { return OP::Map(lhs_.Eval(i), rhs_.Eval(i)); }
+  ShapeVec shape() const { ShapeVec a = lhs_.shape(); return a.empty() ? rhs_.shape() : a; }
+};
+template <typename OP, typename TA, typename DType>
+struct UnaryMapExp : public Exp<UnaryMapExp<OP, TA, DType>, DType> {
+  TA src_;
+  explicit UnaryMapExp(const TA& s) : src_(s) {}
+  DType Eval(size_t i) const { return OP::Map(src_.Eval(i)); }
+  ShapeVec shape() const { return src_.shape(); }
+};
+template <typename OP, typename TA, typename DType>
+inline UnaryMapExp<OP, TA, DType> F(const Exp<TA, DType>& a) { return UnaryMapExp<OP, TA, DType>(a.self()); }
+template <typename OP, typename TA, typename TB, typename DType>
+inline BinaryMapExp<OP, TA, TB, DType> F(const Exp<TA, DType>& a, const Exp<TB, DType>& b) {
+  return BinaryMapExp<OP, TA, TB, DType>(a.self(), b.self());
+}
+#define SHIM_EXPR_BINARY(sym, opname)                                                                      \
+  template <typename TA, typename TB, typename DType>                                                      \
+  inline BinaryMapExp<op::opname, TA, TB, DType> operator sym(const Exp<TA, DType>& a, const Exp<TB, DType>& b) { \
+    return BinaryMapExp<op::opname, TA, TB, DType>(a.self(), b.self());                                    \
+  }
+SHIM_EXPR_BINARY(+, plus)
+SHIM_EXPR_BINARY(-, minus)
+SHIM_EXPR_BINARY(*, mul)
+SHIM_EXPR_BINARY(/, div)
+#undef SHIM_EXPR_BINARY
+// broadcast_with_axis(src, axis, size): a new axis of `size` AFTER `axis` (extension/broadcast_with_axis.h)
+template <typename TA, typename DType>
+struct BroadcastWithAxisExp : public Exp<BroadcastWithAxisExp<TA, DType>, DType> {
+  TA src_;
+  size_t trailing_, size_;
+  ShapeVec shape_;
+  BroadcastWithAxisExp(const TA& s, int axis, int size) : src_(s), size_((size_t)size) {
+    const ShapeVec ss = s.shape();
+    trailing_ = 1;
+    for (size_t d = (size_t)axis + 1; d < ss.size(); ++d) trailing_ *= (size_t)ss[d];
+    shape_ = ss;
+    shape_.insert(shape_.begin() + axis + 1, (index_t)size);
+  }
+  DType Eval(size_t i) const {
+    const size_t inner = i % trailing_, outer = i / (trailing_ * size_);
+    return src_.Eval(outer * trailing_ + inner);
+  }
+  ShapeVec shape() const { return shape_; }
+};
+template <typename TA, typename DType>
+inline BroadcastWithAxisExp<TA, DType> broadcast_with_axis(const Exp<TA, DType>& src, int axis, int size) {
+  return BroadcastWithAxisExp<TA, DType>(src.self(), axis, size);
+}
+// broadcast_scalar(1-element source, shape) and broadcast_keepdim(1-element source, 0, size): every element is src[0]
+template <typename TA, typename DType>
+struct BroadcastScalarExp : public Exp<BroadcastScalarExp<TA, DType>, DType> {
+  TA src_;
+  ShapeVec shape_;
+  BroadcastScalarExp(const TA& s, const ShapeVec& shp) : src_(s), shape_(shp) {}
+  DType Eval(size_t) const { return src_.Eval(0); }
+  ShapeVec shape() const { return shape_; }
+};
+template <typename TA, typename DType, int dim>
+inline BroadcastScalarExp<TA, DType> broadcast_scalar(const Exp<TA, DType>& src, Shape<dim> shape) {
+  ShapeVec v;
+  for (int d = 0; d < dim; ++d) v.push_back(shape[d]);
+  return BroadcastScalarExp<TA, DType>(src.self(), v);
+}
+template <typename TA, typename DType>
+inline BroadcastScalarExp<TA, DType> broadcast_keepdim(const Exp<TA, DType>& src, int axis, int size) {
+  CHECK(ShapeSize(src.self().shape()) == 1 && axis == 0) << "shim: broadcast_keepdim only of a 1-element vector along axis 0";
+  return BroadcastScalarExp<TA, DType>(src.self(), ShapeVec{(index_t)size});
+}
+// broadcast<dimcast>(1-D source, shape): dst[..., i_dimcast, ...] = src[i_dimcast]
+template <typename TA, typename DType>
+struct Broadcast1DExp : public Exp<Broadcast1DExp<TA, DType>, DType> {
+  TA src_;
+  size_t trailing_, extent_;
+  ShapeVec shape_;
+  Broadcast1DExp(const TA& s, int dimcast, const ShapeVec& shp) : src_(s), shape_(shp) {
+    trailing_ = 1;
+    for (size_t d = (size_t)dimcast + 1; d < shp.size(); ++d) trailing_ *= (size_t)shp[d];
+    extent_ = (size_t)shp[dimcast];
+  }
+  DType Eval(size_t i) const { return src_.Eval((i / trailing_) % extent_); }
+  ShapeVec shape() const { return shape_; }
+};
+template <int dimcast, typename TA, typename DType, int dimdst>
+inline Broadcast1DExp<TA, DType> broadcast(const Exp<TA, DType>& src, Shape<dimdst> shape) {
+  ShapeVec v;
+  for (int d = 0; d < dimdst; ++d) v.push_back(shape[d]);
+  return Broadcast1DExp<TA, DType>(src.self(), dimcast, v);
+}
+// reduce_keepdim<Reducer, false>(src, axis): reduce along `axis`, keep it with extent 1 (extension/reduce_with_axis.h)
+template <typename Reducer, typename TA, typename DType>
+struct ReduceKeepdimExp : public Exp<ReduceKeepdimExp<Reducer, TA, DType>, DType> {
+  TA src_;
+  size_t trailing_, extent_;
+  ShapeVec shape_;
+  ReduceKeepdimExp(const TA& s, int axis) : src_(s) {
+    const ShapeVec ss = s.shape();
+    trailing_ = 1;
+    for (size_t d = (size_t)axis + 1; d < ss.size(); ++d) trailing_ *= (size_t)ss[d];
+    extent_ = (size_t)ss[axis];
+    shape_ = ss;
+    shape_[axis] = 1;
+  }
+  DType Eval(size_t i) const {
+    const size_t inner = i % trailing_, outer = i / trailing_;
+    DType res;
+    Reducer::SetInitValue(res);
+    for (size_t k = 0; k < extent_; ++k) Reducer::Reduce(res, src_.Eval((outer * extent_ + k) * trailing_ + inner));
+    return res;
+  }
+  ShapeVec shape() const { return shape_; }
+};
+template <typename Reducer, bool mask, typename TA, typename DType>
+inline ReduceKeepdimExp<Reducer, TA, DType> reduce_keepdim(const Exp<TA, DType>& src, int axis) {
+  return ReduceKeepdimExp<Reducer, TA, DType>(src.self(), axis);
+}
+// sumall_except_dim<dimkeep>(src): 1-D of extent shape[dimkeep]; CPU order of MapReduceKeepHighDim: for the kept
+// index c, sum over the leading dims, then the trailing ones, innermost last
+template <typename TA, typename DType>
+struct SumAllExceptDimExp : public Exp<SumAllExceptDimExp<TA, DType>, DType> {
+  TA src_;
+  size_t leading_, extent_, trailing_;
+  SumAllExceptDimExp(const TA& s, int dimkeep) : src_(s) {
+    const ShapeVec ss = s.shape();
+    leading_ = trailing_ = 1;
+    for (int d = 0; d < dimkeep; ++d) leading_ *= (size_t)ss[d];
+    for (size_t d = (size_t)dimkeep + 1; d < ss.size(); ++d) trailing_ *= (size_t)ss[d];
+    extent_ = (size_t)ss[dimkeep];
+  }
+  DType Eval(size_t c) const {
+    DType res = 0;
+    for (size_t n = 0; n < leading_; ++n)
+      for (size_t t = 0; t < trailing_; ++t) res += src_.Eval((n * extent_ + c) * trailing_ + t);
+    return res;
+  }
+  ShapeVec shape() const { return ShapeVec{(index_t)extent_}; }
+};
+template <int dimkeep, typename TA, typename DType>
+inline SumAllExceptDimExp<TA, DType> sumall_except_dim(const Exp<TA, DType>& src) {
+  return SumAllExceptDimExp<TA, DType>(src.self(), dimkeep);
+}
+}  // namespace expr
+
 template <typename Device, int dimension, typename DType = float>
-struct Tensor {
+struct Tensor : public expr::Exp<Tensor<Device, dimension, DType>, DType> {
   DType* dptr_ = nullptr;
   Shape<dimension> shape_;
+  DType Eval(size_t i) const { return dptr_[i]; }
+  expr::ShapeVec shape() const { expr::ShapeVec v; for (int d = 0; d < dimension; ++d) v.push_back(shape_[d]); return v; }
+  // dst = expr: the destination is written in flat index order; the expression may read the destination itself
+  // (grad = where(..., grad)) only at the same index, as in mshadow
+  template <typename E>
+  Tensor& operator=(const expr::Exp<E, DType>& e) {
+    const E& x = e.self();
+    const size_t n = MSize();
+    for (size_t i = 0; i < n; ++i) dptr_[i] = x.Eval(i);
+    return *this;
+  }
+  template <typename E>
+  Tensor& operator*=(const expr::Exp<E, DType>& e) { const E& x = e.self(); for (size_t i = 0; i < MSize(); ++i) dptr_[i] *= x.Eval(i); return *this; }
+  template <typename E>
+  Tensor& operator/=(const expr::Exp<E, DType>& e) { const E& x = e.self(); for (size_t i = 0; i < MSize(); ++i) dptr_[i] /= x.Eval(i); return *this; }
+  template <typename E>
+  Tensor& operator+=(const expr::Exp<E, DType>& e) { const E& x = e.self(); for (size_t i = 0; i < MSize(); ++i) dptr_[i] += x.Eval(i); return *this; }
   index_t stride_ = 0;
   Stream<Device>* stream_ = nullptr;
   Tensor() { for (int i = 0; i < dimension; ++i) shape_[i] = 0; }
   Tensor(DType* p, const Shape<dimension>& s) : dptr_(p), shape_(s), stride_(s[dimension - 1]) {}
+  Tensor(DType* p, const Shape<dimension>& s, Stream<Device>* st) : dptr_(p), shape_(s), stride_(s[dimension - 1]), stream_(st) {}
   Tensor(DType* p, const Shape<dimension>& s, index_t stride, Stream<Device>* st)
       : dptr_(p), shape_(s), stride_(stride), stream_(st) {}
   index_t size(int i) const { return shape_[i]; }
@@ -168,13 +365,25 @@ struct Tensor {
   Tensor& operator=(DType v) { std::fill(dptr_, dptr_ + MSize(), v); return *this; }
 };
 template <typename Device, typename DType>
-struct Tensor<Device, 1, DType> {
+struct Tensor<Device, 1, DType> : public expr::Exp<Tensor<Device, 1, DType>, DType> {
   DType* dptr_ = nullptr;
   Shape<1> shape_;
+  DType Eval(size_t i) const { return dptr_[i]; }
+  expr::ShapeVec shape() const { return expr::ShapeVec{shape_[0]}; }
+  template <typename E>
+  Tensor& operator=(const expr::Exp<E, DType>& e) {
+    const E& x = e.self();
+    // (temp = f(temp) reads its own element before writing it: evaluate first)
+    std::vector<DType> tmp(MSize());
+    for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = x.Eval(i);
+    std::copy(tmp.begin(), tmp.end(), dptr_);
+    return *this;
+  }
   index_t stride_ = 0;
   Stream<Device>* stream_ = nullptr;
   Tensor() { shape_[0] = 0; }
   Tensor(DType* p, const Shape<1>& s) : dptr_(p), shape_(s), stride_(s[0]) {}
+  Tensor(DType* p, const Shape<1>& s, Stream<Device>* st) : dptr_(p), shape_(s), stride_(s[0]), stream_(st) {}
   Tensor(DType* p, const Shape<1>& s, index_t stride, Stream<Device>* st) : dptr_(p), shape_(s), stride_(stride), stream_(st) {}
   index_t size(int) const { return shape_[0]; }
   size_t MSize() const { return (size_t)shape_[0]; }
@@ -685,7 +894,43 @@ struct floor { template <typename DType> MSHADOW_XINLINE static DType Map(DType 
 struct ceil { template <typename DType> MSHADOW_XINLINE static DType Map(DType a) { return DType(::ceilf(a)); } };
 template <> MSHADOW_XINLINE double floor::Map<double>(double a) { return ::floor(a); }
 template <> MSHADOW_XINLINE double ceil::Map<double>(double a) { return ::ceil(a); }
+// MXNet's src/operator/mshadow_op.h (not in the reference tree), float instantiations: math::exp / log / pow are
+// ::expf / ::logf / ::powf for float operands
+struct identity { template <typename DType> MSHADOW_XINLINE static DType Map(DType a) { return a; } };
+struct negation { template <typename DType> MSHADOW_XINLINE static DType Map(DType a) { return DType(-a); } };
+struct sigmoid { template <typename DType> MSHADOW_XINLINE static DType Map(DType a) { return DType(1.0f / (1.0f + ::expf(-a))); } };
+struct log { template <typename DType> MSHADOW_XINLINE static DType Map(DType a) { return DType(::logf(a)); } };
+struct power { template <typename DType> MSHADOW_XINLINE static DType Map(DType a, DType b) { return DType(::powf(a, b)); } };
+struct plus { template <typename DType> MSHADOW_XINLINE static DType Map(DType a, DType b) { return a + b; } };
+struct eq { template <typename DType> MSHADOW_XINLINE static DType Map(DType a, DType b) { return a == b ? DType(1) : DType(0); } };
+struct le { template <typename DType> MSHADOW_XINLINE static DType Map(DType a, DType b) { return a <= b ? DType(1) : DType(0); } };
 }  // namespace mshadow_op
+// src/operator/tensor/indexing_op.h one_hot and control_flow_op.h where (MXNet, not in the reference tree)
+#define KERNEL_ASSIGN(out, req, val)       \
+  {                                        \
+    switch (req) {                         \
+      case kNullOp: break;                 \
+      case kWriteTo:                       \
+      case kWriteInplace: (out) = (val); break; \
+      case kAddTo: (out) += (val); break;  \
+    }                                      \
+  }
+template <int req>
+struct one_hot {
+  template <typename DType, typename IType>
+  MSHADOW_XINLINE static void Map(int i, DType* out, const IType* indices, int depth, DType on_value) {
+    const int offset = i * depth;
+    const int j = static_cast<int>(indices[i]);
+    if (j >= 0 && j < depth) KERNEL_ASSIGN(out[offset + j], req, on_value);
+  }
+};
+template <int req>
+struct where {
+  template <typename DType, typename CType>
+  MSHADOW_XINLINE static void Map(int i, DType* out, const CType* cond, const DType* x, const DType* y) {
+    KERNEL_ASSIGN(out[i], req, (0 != cond[i] ? x[i] : y[i]));
+  }
+};
 }  // namespace op
 }  // namespace mxnet
 
@@ -715,6 +960,9 @@ inline T atomicAdd(T* addr, T v) { T old = *addr; *addr = old + v; return old; }
       case ::mxnet::kAddTo: LOG(FATAL) << "shim: kAddTo"; break; \
     }                                                      \
   }
+// operator_common.h
+#define UNIFORM_TYPE_CHECK(type, expected, arg) \
+  CHECK_EQ(type, expected) << "This layer requires uniform type. Expected vs given at " << arg
 #define SHAPE_ASSIGN_CHECK(shape_array, index, shape)                            \
   {                                                                              \
     if ((shape_array)[index].ndim() == 0) (shape_array)[index] = ::mxnet::TShape(shape); \

@@ -56,6 +56,18 @@ def main():
     ref_cxx.set_rand_const(0)
     outs = ref_cxx.forward("ProposalTarget", dict(T.BASE, batch_images=2, image_rois=32), [trois, tgt])
     g.update(pt_rois=trois, pt_gt=tgt, **{f"pt_out{i}": o for i, o in enumerate(outs)})
+    # FocalLoss (three parameter sets) and BBoxNorm: forward + the operators' own Backward
+    for m, kw in enumerate(T.FOCAL_MODES):
+        data, label, ograd = T.focal_case(30 + m)
+        (out,) = ref_cxx.forward("_contrib_FocalLoss", dict(kw, workspace=8), [data, label])
+        gd, _ = ref_cxx.backward("_contrib_FocalLoss", dict(kw, workspace=8), [ograd], [data, label], [out])
+        g.update({f"fl{m}_out": out, f"fl{m}_gdata": gd})
+    brng = np.random.default_rng(41)
+    bdata = brng.standard_normal((2, 12, 35)).astype(np.float32)
+    blabel = brng.integers(-1, 3, (2, 3 * 35)).astype(np.float32)
+    bgout = brng.standard_normal((2, 12, 35)).astype(np.float32)
+    bg, _ = ref_cxx.backward("_contrib_BBoxNorm", {}, [bgout], [bdata, blabel], [bdata])
+    g.update(bn_label=blabel, bn_gout=bgout, bn_gdata=bg)
     path = os.path.join(HERE, "reference_cxx_ops.npz")
     np.savez_compressed(path, **g)
     print("wrote", path, os.path.getsize(path), "bytes")

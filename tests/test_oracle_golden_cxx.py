@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 import oracle
-from test_oracle_ref_cxx import BASE, oracle_under_constant_rand
+from test_oracle_ref_cxx import BASE, FOCAL_MODES, focal_case, oracle_under_constant_rand
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_cxx_ops.npz"))
 
@@ -42,3 +42,14 @@ def test_proposal_target():
     o = oracle_under_constant_rand(G["pt_rois"], G["pt_gt"], dict(BASE, image_rois=32), 0)
     for i in range(5):
         assert np.array_equal(o[i], G[f"pt_out{i}"]), i
+
+
+def test_focal_loss_and_bbox_norm():
+    for m, kw in enumerate(FOCAL_MODES):
+        data, label, ograd = focal_case(30 + m)
+        out = oracle.sigmoid(data)
+        assert np.array_equal(out, G[f"fl{m}_out"])
+        gd = oracle.focal_loss_backward(out, label, kw["alpha"], kw["gamma"], kw["grad_scale"], kw["normalization"],
+                                        ograd if kw["out_grad"] else None)
+        assert np.array_equal(gd, G[f"fl{m}_gdata"]), m
+    assert np.array_equal(oracle.bbox_norm_backward(G["bn_gout"], G["bn_label"]), G["bn_gdata"])

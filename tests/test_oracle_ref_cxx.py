@@ -274,3 +274,49 @@ def test_proposal_target_shapes_and_visible_outputs():
     assert shapes == [(2, 64, 4), (2, 64), (2, 64, 324), (2, 64, 324), (2, 64)] and nvis == 4
     _, nvis = ref_cxx.infer_shape("ProposalTarget", dict(BASE, batch_images=2, output_iou=True), [(2, 300, 4), (2, 20, 5)])
     assert nvis == 5
+
+
+# ------------------------------------------------------------------------------------------------ FocalLoss / BBoxNorm
+# focal_loss-inl.h / bbox_norm-inl.h are written as mshadow expression templates; the shim evaluates the same
+# expression trees element by element (oracle/shim/mxnet_shim.h, namespace mshadow::expr).
+def focal_case(seed, B=2, N=60, K=7):
+    rng = np.random.default_rng(seed)
+    data = (rng.standard_normal((B, N, K)) * 2.5 - 2).astype(np.float32)
+    label = rng.integers(-1, K + 1, (B, N)).astype(np.float32)   # -1 ignore, 0 background, 1..K foreground
+    ograd = rng.standard_normal((B, N, K)).astype(np.float32)
+    return data, label, ograd
+
+
+FOCAL_MODES = [dict(alpha=0.25, gamma=2.0, normalization="valid", grad_scale=1.0, out_grad=False),
+               dict(alpha=0.5, gamma=1.5, normalization="batch", grad_scale=0.3, out_grad=True),
+               dict(alpha=0.1, gamma=0.0, normalization="null", grad_scale=2.0, out_grad=False)]
+
+
+@pytest.mark.parametrize("mode", range(len(FOCAL_MODES)))
+def test_focal_loss_forward_backward(mode):
+    kw = FOCAL_MODES[mode]
+    data, label, ograd = focal_case(30 + mode)
+    shapes, nvis = ref_cxx.infer_shape("_contrib_FocalLoss", dict(kw, workspace=8), [data.shape, label.shape])
+    assert shapes == [data.shape] and nvis == 1
+    (out,) = ref_cxx.forward("_contrib_FocalLoss", dict(kw, workspace=8), [data, label])
+    assert np.array_equal(out, oracle.sigmoid(data))
+    gd, gl = ref_cxx.backward("_contrib_FocalLoss", dict(kw, workspace=8), [ograd], [data, label], [out])
+    want = oracle.focal_loss_backward(out, label, kw["alpha"], kw["gamma"], kw["grad_scale"], kw["normalization"],
+                                      ograd if kw["out_grad"] else None)
+    assert np.array_equal(gd, want), np.abs(gd - want).max()
+    assert np.abs(want).max() > 0 and not (want[label == -1] != 0).any()
+
+
+def test_bbox_norm_backward():
+    rng = np.random.default_rng(41)
+    B, A4, P = 2, 12, 35
+    data = rng.standard_normal((B, A4, P)).astype(np.float32)
+    label = rng.integers(-1, 3, (B, (A4 // 4) * P)).astype(np.float32)
+    gout = rng.standard_normal((B, A4, P)).astype(np.float32)
+    (out,) = ref_cxx.forward("_contrib_BBoxNorm", {}, [data, label])
+    assert np.array_equal(out, data)                                   # identity forward (bbox_norm-inl.h:96)
+    gd, gl = ref_cxx.backward("_contrib_BBoxNorm", {}, [gout], [data, label], [out])
+    assert np.array_equal(gd, oracle.bbox_norm_backward(gout, label)) and not gl.any()
+    zero = np.zeros_like(label)                                        # no positive label: divisor max(0 + 1, 1) = 1
+    gd0, _ = ref_cxx.backward("_contrib_BBoxNorm", {}, [gout], [data, zero], [out])
+    assert np.array_equal(gd0, oracle.bbox_norm_backward(gout, zero))
