@@ -73,6 +73,8 @@ class LogMessageNull {
 // ------------------------------------------------------------------------------------------ mshadow
 namespace mshadow {
 typedef int32_t index_t;  // mshadow/base.h with MSHADOW_INT64_TENSOR_SIZE == 0 (the 1.6.0 build of docker/Dockerfile)
+typedef float real_t;
+typedef float default_real_t;
 struct cpu {
   static const bool kDevCPU = true;
   static const int kDevMask = 1 << 0;
@@ -599,7 +601,8 @@ class FieldEntry {
   static bool less(...) { return false; }
   template <typename U> static int ndim_of(const U& v, decltype(std::declval<U>().ndim())* = nullptr) { return (int)v.ndim(); }
   static int ndim_of(...) { return -1; }
-  template <typename U> static bool has_zero(const U& v, decltype(std::declval<U>().ndim())* = nullptr) {
+  template <typename U> static bool has_zero(const U& v, decltype(std::declval<U>().ndim())* = nullptr,
+                                             decltype(std::declval<U>()[0])* = nullptr) {
     for (uint32_t i = 0; i < v.ndim(); ++i) if (v[i] == 0) return true;
     return false;
   }
@@ -754,6 +757,10 @@ struct Resource {
   mshadow::Tensor<xpu, ndim, DType> get_space_typed(mshadow::Shape<ndim> shape, mshadow::Stream<xpu>*) const {
     space->resize(shape.Size() * sizeof(DType) + 64);
     return mshadow::Tensor<xpu, ndim, DType>(reinterpret_cast<DType*>(space->data()), shape);
+  }
+  template <typename xpu, int ndim>
+  mshadow::Tensor<xpu, ndim, mshadow::real_t> get_space(mshadow::Shape<ndim> shape, mshadow::Stream<xpu>* s) const {
+    return get_space_typed<xpu, ndim, mshadow::real_t>(shape, s);
   }
   template <int ndim, typename DType>
   mshadow::Tensor<cpu, ndim, DType> get_host_space_typed(mshadow::Shape<ndim> shape) const {
