@@ -601,12 +601,13 @@ class FieldEntry {
   static bool less(...) { return false; }
   template <typename U> static int ndim_of(const U& v, decltype(std::declval<U>().ndim())* = nullptr) { return (int)v.ndim(); }
   static int ndim_of(...) { return -1; }
-  template <typename U> static bool has_zero(const U& v, decltype(std::declval<U>().ndim())* = nullptr,
-                                             decltype(std::declval<U>()[0])* = nullptr) {
+  // tuple-like values (ndim() and operator[]): any zero entry?  Other types (NumericalParam has no operator[]): no
+  template <typename U> static auto has_zero_impl(const U& v, int) -> decltype((void)v.ndim(), (void)v[0], bool()) {
     for (uint32_t i = 0; i < v.ndim(); ++i) if (v[i] == 0) return true;
     return false;
   }
-  static bool has_zero(...) { return false; }
+  template <typename U> static bool has_zero_impl(const U&, long) { return false; }
+  template <typename U> static bool has_zero(const U& v) { return has_zero_impl(v, 0); }
   template <typename U> void assign_enum(U*, int) {}
   void assign_enum(int* p, int v) { *p = v; }
   void apply() {
