@@ -101,7 +101,7 @@ def forward(op: str, kwargs: dict, inputs, out_shapes=None, dev: str = "cpu", re
     return outputs
 
 
-def backward(op: str, kwargs: dict, out_grads, inputs, outputs, reqs=None):
+def backward(op: str, kwargs: dict, out_grads, inputs, outputs, reqs=None, dev: str = "cpu"):
     """Backward of a legacy OperatorProperty operator (FocalLoss, BBoxNorm): -> list of in_grad arrays, one per
     input, written by the operator's own Backward."""
     L = lib()
@@ -117,7 +117,7 @@ def backward(op: str, kwargs: dict, out_grads, inputs, outputs, reqs=None):
     gnd, gdims = _shape_rows(ogs)
     ind, idims = _shape_rows(ins)
     ond, odims = _shape_rows(outs)
-    _check(L.ref_backward(op.encode(), _kw(kwargs), len(ogs), ptrs(ogs), gnd, gdims.ctypes.data_as(ctypes.c_void_p),
+    _check(L.ref_backward(op.encode(), _kw(kwargs), dev.encode(), len(ogs), ptrs(ogs), gnd, gdims.ctypes.data_as(ctypes.c_void_p),
                           len(ins), ptrs(ins), ind, idims.ctypes.data_as(ctypes.c_void_p), len(outs), ptrs(outs), ond,
                           odims.ctypes.data_as(ctypes.c_void_p), ptrs(igs), (ctypes.c_int * len(ins))(*reqs)))
     return igs

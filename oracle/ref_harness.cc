@@ -128,7 +128,9 @@ int ref_forward(const char* op, const char* kwargs, const char* dev, int n_in, v
       prop->Init(kw);
       std::vector<int> in_type(n_in, mshadow::kFloat32);
       for (size_t i = 0; i < prop->ForwardResource(in_shape).size(); ++i) ctx.requested.emplace_back();
-      std::unique_ptr<mxnet::Operator> o(prop->CreateOperatorEx(mxnet::Context::CPU(), &in_shape, &in_type));
+      mxnet::Context dctx = mxnet::Context::CPU();
+      if (std::string(dev) == "gpu") dctx.dev_type = mxnet::Context::kGPU;  // operators whose .cu is in the build
+      std::unique_ptr<mxnet::Operator> o(prop->CreateOperatorEx(dctx, &in_shape, &in_type));
       if (!o) throw dmlc::Error("CreateOperatorEx returned NULL");
       o->Forward(ctx, in_data, req, out_data, aux);
     } else if (kind == 2) {
@@ -147,7 +149,7 @@ int ref_forward(const char* op, const char* kwargs, const char* dev, int n_in, v
 
 // Backward of a legacy OperatorProperty operator: out_grad / in_data / out_data in, in_grad out (float32 over caller
 // memory; shapes as rows of 8 int64).  The operator object is created exactly as ref_forward creates it.
-int ref_backward(const char* op, const char* kwargs, int n_og, void** og_ptrs, const int* og_ndims, const int64_t* og_dims,
+int ref_backward(const char* op, const char* kwargs, const char* dev, int n_og, void** og_ptrs, const int* og_ndims, const int64_t* og_dims,
                  int n_in, void** in_ptrs, const int* in_ndims, const int64_t* in_dims, int n_out, void** out_ptrs,
                  const int* out_ndims, const int64_t* out_dims, void** ig_ptrs, const int* reqs) {
   return guarded([&] {
@@ -171,7 +173,9 @@ int ref_backward(const char* op, const char* kwargs, int n_og, void** og_ptrs, c
     ctx.is_train = 1;
     for (int i = 0; i < 4; ++i) ctx.requested.emplace_back();  // BackwardResource: at most one temp space in these operators
     std::vector<int> in_type(n_in, mshadow::kFloat32);
-    std::unique_ptr<mxnet::Operator> o(prop->CreateOperatorEx(mxnet::Context::CPU(), &in_shape, &in_type));
+    mxnet::Context dctx = mxnet::Context::CPU();
+    if (std::string(dev) == "gpu") dctx.dev_type = mxnet::Context::kGPU;
+    std::unique_ptr<mxnet::Operator> o(prop->CreateOperatorEx(dctx, &in_shape, &in_type));
     if (!o) throw dmlc::Error("CreateOperatorEx returned NULL");
     o->Backward(ctx, out_grad, in_data, out_data, req, in_grad, aux);
   });

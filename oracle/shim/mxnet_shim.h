@@ -30,6 +30,16 @@
 #define MSHADOW_CINLINE inline
 #define MSHADOW_FORCE_INLINE inline
 #define MSHADOW_USE_CUDA 0
+// CUDA source compiled as plain C++: a __global__ function is an ordinary function run by ONE thread of a 1x1 grid,
+// so a grid-stride loop visits every index in order
+#ifndef __CUDACC__
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+struct ShimDim3 { unsigned x, y, z; };
+static const ShimDim3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+#endif
 #define MXNET_USE_CUDA 0
 
 // ------------------------------------------------------------------------------------------ dmlc
@@ -365,6 +375,8 @@ struct Tensor : public expr::Exp<Tensor<Device, dimension, DType>, DType> {
   }
   Tensor& operator=(const Tensor&) = default;
   Tensor& operator=(DType v) { std::fill(dptr_, dptr_ + MSize(), v); return *this; }
+  Tensor& operator*=(DType v) { for (size_t i = 0; i < MSize(); ++i) dptr_[i] *= v; return *this; }
+  Tensor& operator+=(DType v) { for (size_t i = 0; i < MSize(); ++i) dptr_[i] += v; return *this; }
 };
 template <typename Device, typename DType>
 struct Tensor<Device, 1, DType> : public expr::Exp<Tensor<Device, 1, DType>, DType> {
@@ -395,6 +407,8 @@ struct Tensor<Device, 1, DType> : public expr::Exp<Tensor<Device, 1, DType>, DTy
   Tensor& operator=(const Tensor&) = default;
   Tensor& operator=(DType v) { std::fill(dptr_, dptr_ + MSize(), v); return *this; }
   // the only expression-template uses in the files we build: elementwise -= and /= with an equal-shape vector
+  Tensor& operator*=(DType v) { for (size_t i = 0; i < MSize(); ++i) dptr_[i] *= v; return *this; }
+  Tensor& operator+=(DType v) { for (size_t i = 0; i < MSize(); ++i) dptr_[i] += v; return *this; }
   Tensor& operator-=(const Tensor& o) { for (index_t i = 0; i < shape_[0]; ++i) dptr_[i] -= o.dptr_[i]; return *this; }
   Tensor& operator/=(const Tensor& o) { for (index_t i = 0; i < shape_[0]; ++i) dptr_[i] /= o.dptr_[i]; return *this; }
 };
@@ -950,6 +964,14 @@ inline T atomicAdd(T* addr, T v) { T old = *addr; *addr = old + v; return old; }
   static ::mxnet::shim_reg::PropEntry& SHIM_CAT(__shim_prop_##name, __COUNTER__) =                  \
       ::mxnet::shim_reg::PropEntry::Register(#name, []() -> ::mxnet::OperatorProperty* { return new OperatorPropertyType(); })
 // operator_common.h's form for MXNET_USE_CUDA == 0
+#ifdef SHIM_GPU_DISPATCH  // the file's .cu (with CreateOp<gpu>) is part of the build: a GPU context gets the gpu operator
+#define DO_BIND_DISPATCH(Method, ...)                                             \
+  if (ctx.dev_mask() == ::mshadow::cpu::kDevMask) {                               \
+    return Method<::mshadow::cpu>(__VA_ARGS__);                                   \
+  } else {                                                                        \
+    return Method<::mshadow::gpu>(__VA_ARGS__);                                   \
+  }
+#else
 #define DO_BIND_DISPATCH(Method, ...)                                             \
   if (ctx.dev_mask() == ::mshadow::cpu::kDevMask) {                               \
     return Method<::mshadow::cpu>(__VA_ARGS__);                                   \
@@ -957,6 +979,7 @@ inline T atomicAdd(T* addr, T v) { T old = *addr; *addr = old + v; return old; }
     LOG(FATAL) << "GPU is not enabled";                                           \
     return nullptr;                                                               \
   }
+#endif
 #define ADD_FILELINE "\n\nFrom:" __FILE__
 // operator_common.h's Assign(out, req, exp) for the plain-value uses in the files we build
 #define Assign(out, req, exp)                              \

@@ -68,6 +68,12 @@ def main():
     bgout = brng.standard_normal((2, 12, 35)).astype(np.float32)
     bg, _ = ref_cxx.backward("_contrib_BBoxNorm", {}, [bgout], [bdata, blabel], [bdata])
     g.update(bn_label=blabel, bn_gout=bgout, bn_gdata=bg)
+    # SigmoidCrossEntropy (GPU path on the host)
+    sdata, slabel = T.sigmoid_ce_case()
+    souts = ref_cxx.forward("_contrib_SigmoidCrossEntropy", dict(grad_scale=0.37), [sdata, slabel], dev="gpu")
+    (sg, _) = ref_cxx.backward("_contrib_SigmoidCrossEntropy", dict(grad_scale=0.37), [np.ones_like(souts[0])],
+                               [sdata, slabel], souts, dev="gpu")
+    g.update(sce_out=souts[0], sce_gdata=sg)
     path = os.path.join(HERE, "reference_cxx_ops.npz")
     np.savez_compressed(path, **g)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 import oracle
-from test_oracle_ref_cxx import BASE, FOCAL_MODES, focal_case, oracle_under_constant_rand
+from test_oracle_ref_cxx import BASE, FOCAL_MODES, focal_case, oracle_under_constant_rand, sigmoid_ce_case
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_cxx_ops.npz"))
 
@@ -53,3 +53,9 @@ def test_focal_loss_and_bbox_norm():
                                         ograd if kw["out_grad"] else None)
         assert np.array_equal(gd, G[f"fl{m}_gdata"]), m
     assert np.array_equal(oracle.bbox_norm_backward(G["bn_gout"], G["bn_label"]), G["bn_gdata"])
+
+
+def test_sigmoid_cross_entropy():
+    data, label = sigmoid_ce_case()
+    assert np.array_equal(oracle.sigmoid_ce_forward(data, label), G["sce_out"])
+    assert np.array_equal(oracle.sigmoid_ce_backward(data, label, 0.37), G["sce_gdata"])

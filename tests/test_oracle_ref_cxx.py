@@ -320,3 +320,28 @@ def test_bbox_norm_backward():
     zero = np.zeros_like(label)                                        # no positive label: divisor max(0 + 1, 1) = 1
     gd0, _ = ref_cxx.backward("_contrib_BBoxNorm", {}, [gout], [data, zero], [out])
     assert np.array_equal(gd0, oracle.bbox_norm_backward(gout, zero))
+
+
+# ------------------------------------------------------------------------------------------------ SigmoidCrossEntropy
+def sigmoid_ce_case(seed=43, R=9, D=50):
+    rng = np.random.default_rng(seed)
+    data = (rng.standard_normal((R, D)) * 3).astype(np.float32)
+    label = rng.integers(-1, 2, (R, D)).astype(np.float32)   # -1 ignore, 0 / 1 targets
+    label[4] = -1                                             # a row with no valid target: loss 0 / (0 + 1e-5)
+    return data, label
+
+
+def test_sigmoid_cross_entropy_gpu_path_on_the_host():
+    """The operator exists for the GPU only; its kernels (sigmoid_cross_entropy.cu:43-83) and the mshadow reductions
+    around them run serially on the host (the build strips the `<<<...>>>` launch configurations, nothing else)."""
+    data, label = sigmoid_ce_case()
+    shapes, nvis = ref_cxx.infer_shape("_contrib_SigmoidCrossEntropy", dict(grad_scale=1.0), [data.shape, label.shape])
+    assert nvis == 1 and shapes == [(9,), (9, 50), (9,), (9, 50), (9,)]
+    with pytest.raises(RuntimeError):                         # sigmoid_cross_entropy.cc:41: the CPU operator is a stub
+        ref_cxx.forward("_contrib_SigmoidCrossEntropy", dict(grad_scale=1.0), [data, label], dev="cpu")
+    for scale in (1.0, 0.37):
+        outs = ref_cxx.forward("_contrib_SigmoidCrossEntropy", dict(grad_scale=scale), [data, label], dev="gpu")
+        assert np.array_equal(outs[0], oracle.sigmoid_ce_forward(data, label)) and outs[0][4] == 0
+        (gd, _) = ref_cxx.backward("_contrib_SigmoidCrossEntropy", dict(grad_scale=scale), [np.ones_like(outs[0])],
+                                   [data, label], outs, dev="gpu")
+        assert np.array_equal(gd, oracle.sigmoid_ce_backward(data, label, scale))
