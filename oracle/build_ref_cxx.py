@@ -33,12 +33,17 @@ SOURCES = [
     ("contrib/generate_anchor.cc", False),  # GenAnchorOp<cpu>::Forward + gen_anchor_utils (generate_anchor-inl.h:139-183)
     ("contrib/focal_loss.cc", False),     # FocalLossOp::Forward / Backward as mshadow expressions (focal_loss-inl.h:100-231)
     ("contrib/bbox_norm.cc", False),      # BBoxNormOp::Backward (bbox_norm-inl.h:99-129)
-    # SigmoidCrossEntropy exists for the GPU only (the .cc says NotImplemented): its two element-wise kernels and
-    # the mshadow reductions around them (sigmoid_cross_entropy.cu:43-120) run on the host.  Plain C++ cannot parse
-    # a `<<<grid, block, smem>>>` launch configuration, so THIS ONE FILE passes through a filter that deletes those
-    # (and nothing else) on its way to the compiler - a temporary copy, never written into the repository.
+    # GPU-only operators.  Plain C++ cannot parse `kernel<<<grid, block, ...>>>(args)`, so the .cu files below pass
+    # through ONE textual rewrite on their way to the compiler (a temporary copy, never written into the repository):
+    #     kernel<<<cfg>>>(args)   ->   shim_launch(cfg).run([&](auto... a) { kernel(a...); }, args)
+    # and nothing else; shim_launch (oracle/shim/mxnet_shim.h) runs every thread of every block in turn.
+    # SigmoidCrossEntropy: the .cc says NotImplemented for the CPU; kernels + mshadow reductions :43-120.
     ("contrib/sigmoid_cross_entropy.cc", False, ["-DSHIM_GPU_DISPATCH"]),
-    ("contrib/sigmoid_cross_entropy.cu", False, [], "strip_launch_config"),
+    ("contrib/sigmoid_cross_entropy.cu", False, [], "rewrite_launches"),
+    # Proposal_v3: the GPU operator SimpleDet runs (the CPU twin in the .cc indexes its scores out of range);
+    # thrust::stable_sort_by_key / cudaMemcpy come from oracle/shim/thrust, the shim's host stand-ins.
+    ("contrib/proposal_v3.cc", False, ["-DSHIM_GPU_DISPATCH"]),
+    ("contrib/proposal_v3.cu", False, [], "rewrite_launches"),
 ]
 # -O2 without -march: like MXNet's x86-64 CPU build there is no FMA instruction to contract into;
 # -ffp-contract=off makes that explicit.
@@ -68,13 +73,15 @@ def main() -> int:
             src, rename_rand = entry[0], entry[1]
             extra = list(entry[2]) if len(entry) > 2 else []
             path = os.path.join(REF, src)
-            if len(entry) > 3 and entry[3] == "strip_launch_config":
+            if len(entry) > 3 and entry[3] == "rewrite_launches":
                 import re
 
-                text = re.sub(r"<<<.*?>>>", "", open(path).read(), flags=re.S)
+                text = re.sub(r"\b([A-Za-z_]\w*)\s*<<<(.*?)>>>\s*\(",
+                              lambda m: "shim_launch(%s).run([&](auto... a) { %s(a...); }, " % (m.group(2), m.group(1)),
+                              open(path).read(), flags=re.S)
                 path = os.path.join(tmp, os.path.basename(src) + ".cc")
                 open(path, "w").write(text)
-                extra += ["-iquote", os.path.dirname(os.path.join(REF, src))]
+                extra += ["-iquote", os.path.dirname(os.path.join(REF, src)), "-DSHIM_CUDA_DEVICE_MATH"]
             obj = os.path.join(tmp, src.replace("/", "_").replace(".", "_") + ".o")
             cmd = ["g++", *CXXFLAGS, *extra, *inc, "-include", os.path.join(SHIM, "mxnet_shim.h"), "-x", "c++", "-c",
                    path, "-o", obj]

@@ -37,8 +37,86 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
-struct ShimDim3 { unsigned x, y, z; };
-static const ShimDim3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+// ---- serial emulation of a kernel launch.  The build recipe rewrites `kernel<<<grid, block, ...>>>(args)` into
+// `shim_launch(grid, block, ...).run([&](auto... a) { kernel(a...); }, args)`: every thread of every block runs the
+// kernel body in turn with blockIdx / threadIdx set.  __shared__ variables are function statics; a block whose
+// threads reached __syncthreads() is simply run a second time - exact for the load -> barrier -> compute kernels
+// in these files (the second pass sees the complete shared data and overwrites what the first one wrote).
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}  // NOLINT
+};
+static dim3 blockIdx(0, 0, 0), threadIdx(0, 0, 0), blockDim(1, 1, 1), gridDim(1, 1, 1);
+static bool shim_saw_sync = false;
+#define __shared__ static
+inline void __syncthreads() { shim_saw_sync = true; }
+struct shim_launch {
+  dim3 grid, block;
+  shim_launch() {}
+  template <typename S = void*>
+  shim_launch(dim3 g, dim3 b, size_t = 0, S = S()) : grid(g), block(b) {}
+  template <typename F, typename... Args>
+  void run(F f, Args... args) const {
+    gridDim = grid;
+    blockDim = block;
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+      for (unsigned by = 0; by < grid.y; ++by)
+        for (unsigned bx = 0; bx < grid.x; ++bx) {
+          blockIdx = dim3(bx, by, bz);
+          for (int pass = 0; pass < 2; ++pass) {
+            shim_saw_sync = false;
+            for (unsigned tz = 0; tz < block.z; ++tz)
+              for (unsigned ty = 0; ty < block.y; ++ty)
+                for (unsigned tx = 0; tx < block.x; ++tx) {
+                  threadIdx = dim3(tx, ty, tz);
+                  f(args...);
+                }
+            if (!shim_saw_sync) break;
+          }
+        }
+    blockIdx = threadIdx = dim3(0, 0, 0);
+    blockDim = gridDim = dim3(1, 1, 1);
+  }
+};
+// the slice of the CUDA runtime these files call: one address space, nothing can fail
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+inline cudaError_t cudaMemcpy(void* dst, const void* src, size_t n, cudaMemcpyKind) { std::memmove(dst, src, n); return cudaSuccess; }
+inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char* cudaGetErrorString(cudaError_t) { return "no error"; }
+// CUDA's global min / max overload set (math_functions.hpp): integers by comparison, floating point through fmin /
+// fmax, mixed float/double promoted to double
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }
+inline size_t min(size_t a, size_t b) { return a < b ? a : b; }
+inline size_t max(size_t a, size_t b) { return a > b ? a : b; }
+inline float min(float a, float b) { return ::fminf(a, b); }
+inline float max(float a, float b) { return ::fmaxf(a, b); }
+inline double min(double a, double b) { return ::fmin(a, b); }
+inline double max(double a, double b) { return ::fmax(a, b); }
+inline double min(float a, double b) { return ::fmin((double)a, b); }
+inline double max(float a, double b) { return ::fmax((double)a, b); }
+inline double min(double a, float b) { return ::fmin(a, (double)b); }
+inline double max(double a, float b) { return ::fmax(a, (double)b); }
+#ifdef SHIM_CUDA_DEVICE_MATH
+// In device code the unqualified math functions have float overloads (exp(float) IS expf there, while g++ binds a
+// host-side `exp(float_value)` to ::exp(double) - which is what decodebbox.cc really does on the CPU).  Only the .cu
+// translation units get these.
+inline float exp(float x) { return ::expf(x); }
+inline float log(float x) { return ::logf(x); }
+inline float sqrt(float x) { return ::sqrtf(x); }
+inline float floor(float x) { return ::floorf(x); }
+inline float ceil(float x) { return ::ceilf(x); }
+inline float round(float x) { return ::roundf(x); }
+inline float fabs(float x) { return ::fabsf(x); }
+inline float pow(float x, float y) { return ::powf(x, y); }
+#endif
 #endif
 #define MXNET_USE_CUDA 0
 
@@ -112,6 +190,11 @@ template <> MSHADOW_XINLINE double MinValue<double>() { return -DBL_MAX; }
 struct CUstream_st;
 typedef CUstream_st* cudaStream_t;  // only the handle type: the shim never touches the CUDA runtime
 namespace mshadow {
+namespace cuda {
+const int kMaxThreadsPerBlock = 1024;
+const int kBaseThreadNum = 256;
+inline void CheckLaunchParam(dim3, dim3, const char* = "") {}
+}  // namespace cuda
 template <typename Device> struct Stream {
   static cudaStream_t GetStream(Stream<Device>*) { return nullptr; }
 };
@@ -777,10 +860,11 @@ struct Resource {
   mshadow::Tensor<xpu, ndim, mshadow::real_t> get_space(mshadow::Shape<ndim> shape, mshadow::Stream<xpu>* s) const {
     return get_space_typed<xpu, ndim, mshadow::real_t>(shape, s);
   }
+  mutable std::shared_ptr<std::vector<char>> host_space = std::make_shared<std::vector<char>>();
   template <int ndim, typename DType>
   mshadow::Tensor<cpu, ndim, DType> get_host_space_typed(mshadow::Shape<ndim> shape) const {
-    space->resize(shape.Size() * sizeof(DType) + 64);
-    return mshadow::Tensor<cpu, ndim, DType>(reinterpret_cast<DType*>(space->data()), shape);
+    host_space->resize(shape.Size() * sizeof(DType) + 64);  // (its own buffer: the device space must stay where it is)
+    return mshadow::Tensor<cpu, ndim, DType>(reinterpret_cast<DType*>(host_space->data()), shape);
   }
 };
 struct ResourceRequest {

@@ -345,3 +345,53 @@ def test_sigmoid_cross_entropy_gpu_path_on_the_host():
         (gd, _) = ref_cxx.backward("_contrib_SigmoidCrossEntropy", dict(grad_scale=scale), [np.ones_like(outs[0])],
                                    [data, label], outs, dev="gpu")
         assert np.array_equal(gd, oracle.sigmoid_ce_backward(data, label, scale))
+
+
+# ------------------------------------------------------------------------------------------------ Proposal_v3 (GPU operator)
+# proposal_v3.cu is the operator SimpleDet runs (its CPU twin in proposal_v3.cc:372 reads the scores out of range).
+# The build turns its launches into serial loops over every thread (oracle/build_ref_cxx.py, shim_launch) and gives it
+# CUDA's float math overloads; thrust::stable_sort_by_key is std::stable_sort.
+def rpn_case(seed, B=2, A=3, H=20, W=30, stride=16, shrink=(7, 20)):
+    rng = np.random.default_rng(seed)
+    logit = rng.standard_normal((B, A, H, W)).astype(np.float32) * 2 - 1
+    fg = 1 / (1 + np.exp(-logit))
+    cls = np.concatenate([1 - fg, fg], 1).astype(np.float32)
+    cls[0, A:, 3, 4:9] = cls[0, A, 3, 4]                      # equal scores: the stable sort keeps index order
+    reg = (rng.standard_normal((B, 4 * A, H, W)) * 0.3).astype(np.float32)
+    reg[0, 2, 5, 5] = 9.0                                      # dw above the exp clip
+    info = np.array([[H * stride - shrink[0], W * stride - shrink[1], 1.0], [H * stride, W * stride, 1.5]], np.float32)[:B]
+    return cls, reg, info
+
+
+PROPOSAL_V3_CASES = [
+    dict(seed=0, kw=dict(rpn_pre_nms_top_n=300, rpn_post_nms_top_n=100, threshold=0.7, rpn_min_size=8, scales=(8,),
+                         ratios=(0.5, 1, 2), feature_stride=16)),
+    dict(seed=1, kw=dict(rpn_pre_nms_top_n=6000, rpn_post_nms_top_n=300, threshold=0.5, rpn_min_size=40, scales=(4, 8),
+                         ratios=(0.5, 1, 2), feature_stride=16), A=6),          # pre > count, many boxes filtered
+    dict(seed=2, kw=dict(rpn_pre_nms_top_n=200, rpn_post_nms_top_n=200, threshold=0.3, rpn_min_size=0, scales=(8,),
+                         ratios=(1,), feature_stride=32), A=1, H=9, W=13, stride=32, shrink=(40, 70)),  # padded cells
+]
+
+
+@pytest.mark.parametrize("case", range(len(PROPOSAL_V3_CASES)))
+@pytest.mark.parametrize("is_train", [False, True])
+@pytest.mark.parametrize("iou_loss", [False, True])
+def test_proposal_v3_gpu_operator(case, is_train, iou_loss):
+    c = dict(PROPOSAL_V3_CASES[case])
+    kw = dict(c.pop("kw"), is_train=is_train, iou_loss=iou_loss)
+    cls, reg, info = rpn_case(**c)
+    out, score = ref_cxx.forward("_contrib_Proposal_v3", dict(kw, output_score=True, workspace=64), [cls, reg, info], dev="gpu")
+    r, sc = oracle.proposal_v3(cls, reg, info, **kw)
+    n = r.shape[1]
+    if n == out.shape[1]:
+        assert np.array_equal(out, r), np.abs(out - r).max()
+        assert np.array_equal(score, sc)
+    else:
+        # is_train with fewer anchors than rpn_post_nms_top_n (P6 of an FPN in training: 819 < 2000).  The operator's
+        # output keeps rpn_post_nms_top_n rows per image, but the loop shrinks its row count to n = min(post, pre)
+        # and ALSO uses n as the per-image stride (proposal_v3.cu:471-476, :629-631): image b's n rows land at flat
+        # row b*n of the (B, post) buffer, the rest is never written.  The oracle returns (B, n) rows; they must be
+        # the rows the reference wrote, wherever it put them.
+        B = out.shape[0]
+        assert np.array_equal(out.reshape(-1, 4)[:B * n], r.reshape(-1, 4))
+        assert np.array_equal(score.reshape(-1)[:B * n], sc.reshape(-1))
