@@ -7,11 +7,15 @@
  * statement WITHOUT FMA contraction; nvcc's contraction of the reference build is a property of
  * its compiler flags, not of the algorithm.
  *
- * Parity pin: the reference has no fixtures for these ops ("parity unpinned").
- * greedy_nms / soft_nms / bbox_overlaps ARE pinned: the reference's own Cython
- * (operator_py/cython/{cpu_nms,bbox}.pyx) is compiled here into oracle/_ref by
- * oracle/build_ref.py and compared with these restatements in tests/test_oracle_ref.py; golden
- * vectors generated from it are committed under tests/golden/.
+ * Parity pin: the reference holds no fixtures for these ops, so they are pinned against the
+ * reference's own code, compiled here into oracle/_ref (test infrastructure, git-ignored):
+ *   - greedy_nms / soft_nms / bbox_overlaps: its Cython (operator_py/cython/{cpu_nms,bbox}.pyx), oracle/build_ref.py,
+ *     tests/test_oracle_ref.py;
+ *   - decode_bbox, gen_anchor, proposal_v3, proposal (v1), proposal_v2, contrib_nms, gen_proposal,
+ *     gen_proposal_retina: its operator_cxx sources, unmodified, through oracle/shim (the .cu operators run on
+ *     the host: every `<<<>>>` launch becomes a serial loop over all threads), oracle/build_ref_cxx.py,
+ *     tests/test_oracle_ref_cxx.py - bit for bit.
+ * The same cases are committed as vectors under tests/golden/ (tests/test_oracle_golden*.py run anywhere).
  *
  *   oracle_decode_bbox        operator_cxx/contrib/decodebbox.cc:34-133
  *   oracle_proposal_v3        operator_cxx/contrib/proposal_v3.cu:65-419,463-637 (+ anchors

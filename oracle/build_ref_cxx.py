@@ -44,6 +44,17 @@ SOURCES = [
     # thrust::stable_sort_by_key / cudaMemcpy come from oracle/shim/thrust, the shim's host stand-ins.
     ("contrib/proposal_v3.cc", False, ["-DSHIM_GPU_DISPATCH"]),
     ("contrib/proposal_v3.cu", False, [], "rewrite_launches"),
+    # the same treatment for the remaining proposal-family GPU operators
+    ("contrib/proposal.cc", False, ["-DSHIM_GPU_DISPATCH"]),
+    ("contrib/proposal.cu", False, [], "rewrite_launches"),
+    ("contrib/proposal_v2.cc", False, ["-DSHIM_GPU_DISPATCH"]),
+    ("contrib/proposal_v2.cu", False, [], "rewrite_launches"),
+    ("contrib/nms.cc", False, ["-DSHIM_GPU_DISPATCH"]),
+    ("contrib/nms.cu", False, [], "rewrite_launches"),
+    ("contrib/generate_proposal.cc", False, ["-DSHIM_GPU_DISPATCH"]),
+    ("contrib/generate_proposal.cu", False, [], "rewrite_launches"),
+    ("contrib/generate_proposal_retina.cc", False, ["-DSHIM_GPU_DISPATCH"]),
+    ("contrib/generate_proposal_retina.cu", False, [], "rewrite_launches"),
 ]
 # -O2 without -march: like MXNet's x86-64 CPU build there is no FMA instruction to contract into;
 # -ffp-contract=off makes that explicit.

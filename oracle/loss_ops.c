@@ -1,8 +1,10 @@
 /*
  * ORACLE — TEST INFRASTRUCTURE ONLY.  Not product code.
  *
- * CPU restatement of the detection losses' arithmetic (all "parity unpinned": no fixtures in the
- * reference).  mshadow expression templates evaluate element-wise in float, left to right.
+ * CPU restatement of the detection losses' arithmetic.  The reference holds no fixtures; all three are pinned bit
+ * for bit against the reference's own operator sources compiled through oracle/shim (tests/test_oracle_ref_cxx.py,
+ * vectors in tests/golden/reference_cxx_ops.npz).  mshadow expression templates evaluate element-wise in float,
+ * left to right.
  *   oracle_focal_loss_backward   operator_cxx/contrib/focal_loss-inl.h:180-230
  *   oracle_bbox_norm_backward    operator_cxx/contrib/bbox_norm-inl.h:99-129
  *   oracle_sigmoid_ce_forward/backward   operator_cxx/contrib/sigmoid_cross_entropy.cu:45-129

@@ -1,6 +1,7 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY.  numpy restatements of the reference's pure-Python operators
 (the originals import mxnet at module top, so the numpy bodies are restated here; each function
-cites the reference file:line it follows).  "Parity unpinned" unless noted."""
+cites the reference file:line it follows).  Pinned by goldens generated from the reference's own Python
+(tests/golden/make_golden*.py, tests/test_oracle_golden*.py) except where a function says "PARITY UNPINNED"."""
 import numpy as np
 
 import oracle

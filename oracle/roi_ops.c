@@ -12,8 +12,10 @@
  *
  * Parity pin: ROIPooling_v1 is pinned by the reference's docstring example
  * (roi_pooling_v1.cc:265-285, see tests/test_oracle_golden.py).  ROIAlign_v2
- * has no fixture anywhere in the reference => "parity unpinned" beyond this
- * line-by-line restatement.
+ * has no fixture anywhere in the reference; both operators
+ * are pinned bit for bit against the reference's own sources (roi_align_v2.cc/.cu,
+ * roi_pooling_v1.cc) compiled through oracle/shim: tests/test_oracle_ref_cxx.py,
+ * vectors in tests/golden/reference_cxx_ops.npz.
  *
  * Functions follow (reference file:line, relative to /root/reference):
  *   oracle_roi_align_v2_forward   operator_cxx/contrib/roi_align_v2-inl.h:61-153

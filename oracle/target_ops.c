@@ -3,7 +3,9 @@
  *
  * CPU restatement of ProposalTarget (operator_cxx/proposal_target-inl.h:123-256 op,
  * operator_cxx/proposal_target.cc:22-227 SampleROI / BBoxOverlap / ExpandBboxRegressionTargets /
- * NonLinearTransformAndNormalization).  Parity unpinned by the reference (no fixtures).
+ * NonLinearTransformAndNormalization).  No fixtures in the reference; pinned bit for bit against the
+ * reference's own proposal_target.cc / proposal_target_v2.cc compiled through oracle/shim with a controlled rand()
+ * (tests/test_oracle_ref_cxx.py, vectors in tests/golden/reference_cxx_ops.npz).
  *
  * Randomness.  The reference calls std::random_shuffle on the global rand() state shared by all
  * device threads (proposal_target.cc:83,102,118) — not reproducible even against itself.  What IS

@@ -168,6 +168,7 @@ struct ScanOut {
   int* nkeep;        // (P) or nullptr
   int out_rows;      // rows per problem in out/out_score
   int write_rows;    // rows actually written (PrepareOutput's `count`)
+  int clip_to_count; // 1: a problem writes min(write_rows, its box count) rows and zero-fills the rest of out_rows
   int pad_mode;      // 0: zeros, 1: wrap keep[i % nkeep] (Proposal is_train)
   int level_B;       // 0: problem p writes rows [p*out_rows, ...).  >0: p = l*B + b writes image b's
                      //    slice l of a (B, L*out_rows) level-major concat (models/FPN/builder.py:316-317)
@@ -270,11 +271,13 @@ nms_scan_kernel(const float* __restrict__ dets, const int* __restrict__ counts, 
     for (int i = tid; i < n_max; i += blockDim.x) o.keep[(size_t)p * n_max + i] = i < nk ? s_keep[i] : 0;
   if (o.out) {  // PrepareOutput, proposal_v3.cu:387-419 / nms.cu:208-231
     const float* d = dets + (size_t)p * n_max * 5;
-    for (int i = tid; i < o.write_rows; i += blockDim.x) {
+    const int wr = o.clip_to_count ? min(o.write_rows, n) : o.write_rows;
+    for (int i = tid; i < (o.clip_to_count ? o.out_rows : o.write_rows); i += blockDim.x) {
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
       float s = 0.f;
       int k = -1;
-      if (i < nk) k = s_keep[i];
+      if (i >= wr) k = -1;  // beyond what this level can fill: a zero row (ProposalTarget skips y2 == 0 rows)
+      else if (i < nk) k = s_keep[i];
       else if (o.pad_mode == 1 && nk > 0) k = s_keep[i % nk];
       if (k >= 0) {
         b = make_float4(d[(size_t)k * 5], d[(size_t)k * 5 + 1], d[(size_t)k * 5 + 2], d[(size_t)k * 5 + 3]);
@@ -901,12 +904,16 @@ extern "C" int sdet_proposal_v3_fpn(const float* const* cls_prob, const float* c
       cand_keys += (size_t)B * L.nchunks * L.pre;
     }
   }
-  // rows per level in the output: `post` (:472-475); with is_train it depends on the level's pre
-  int post = rpn_post_nms_top_n;
+  // rows per level in the output: `post` (:472-475); with is_train a level writes min(post, its pre) rows (wrap-
+  // padded).  When the levels differ (P6 of an 800x1333 FPN has 819 anchors, rpn_post_nms_top_n is 2000) every level
+  // keeps `post` rows like the reference's per-level outputs and the small level's remaining rows are ZERO.  (The
+  // reference leaves them unwritten and, for images after the first, writes the level's rows with the shrunken
+  // stride, i.e. into the previous image's block - proposal_v3.cu:471-476,:629-631, tests/test_oracle_ref_cxx.py;
+  // that is not reproduced.)
+  int post = rpn_post_nms_top_n, clip = 0;
   if (is_train) {
-    post = std::min(rpn_post_nms_top_n, pre_min);
-    if (num_levels > 1 && pre_min != pre_max && rpn_post_nms_top_n > pre_min)
-      return sdet::fail(SDET_ERR_UNSUPPORTED, "is_train with levels smaller than rpn_post_nms_top_n");
+    if (pre_min == pre_max) post = std::min(rpn_post_nms_top_n, pre_min);
+    else if (rpn_post_nms_top_n > pre_min) clip = 1;
   }
   const int P = B * num_levels;
   const size_t need = proposal_ws_bytes(P, pre_max) + align_up(cand_keys * 8, 256);
@@ -940,6 +947,7 @@ extern "C" int sdet_proposal_v3_fpn(const float* const* cls_prob, const float* c
   so.out_score = out_score;
   so.out_rows = post;
   so.write_rows = post;
+  so.clip_to_count = clip;
   so.pad_mode = is_train ? 1 : 0;
   so.level_B = num_levels > 1 ? B : 0;
   so.level_L = num_levels;

@@ -636,7 +636,9 @@ def Proposal_v3_fpn(cls_probs, bbox_preds, im_info, feature_strides, rpn_pre_nms
             raise ValueError("each level needs cls_prob (B,2A,H,W) and bbox_pred (B,4A,H,W)")
     pres = [min(rpn_pre_nms_top_n if rpn_pre_nms_top_n > 0 else A * c.shape[2] * c.shape[3],
                 A * c.shape[2] * c.shape[3]) for c in cls_probs]
-    post = rpn_post_nms_top_n if not is_train else min(rpn_post_nms_top_n, min(pres))
+    # is_train: a level writes min(post, its pre) rows; equal levels shrink the output, unequal ones keep `post` rows
+    # per level with zero rows after what a small level (P6) can fill - sdet_proposal_v3_fpn's rule
+    post = rpn_post_nms_top_n if (not is_train or min(pres) != max(pres)) else min(rpn_post_nms_top_n, min(pres))
     dev = cls_probs[0].device
     out = torch.empty((B, L_ * post, 4), device=dev, dtype=torch.float32)
     score = torch.empty((B, L_ * post, 1), device=dev, dtype=torch.float32)

@@ -74,6 +74,59 @@ def main():
     (sg, _) = ref_cxx.backward("_contrib_SigmoidCrossEntropy", dict(grad_scale=0.37), [np.ones_like(souts[0])],
                                [sdata, slabel], souts, dev="gpu")
     g.update(sce_out=souts[0], sce_gdata=sg)
+    # Proposal_v3: the GPU operator run serially on the host (inference and training padding, box-delta and IoU decode)
+    for ci, c in enumerate(T.PROPOSAL_V3_CASES):
+        c = dict(c)
+        kw = c.pop("kw")
+        cls, reg, info = T.rpn_case(**c)
+        for tr in (False, True):
+            for iou in (False, True):
+                o, s_ = ref_cxx.forward("_contrib_Proposal_v3", dict(kw, is_train=tr, iou_loss=iou, output_score=True, workspace=64),
+                                        [cls, reg, info], dev="gpu")
+                n = min(kw["rpn_post_nms_top_n"], kw["rpn_pre_nms_top_n"], cls.shape[1] // 2 * cls.shape[2] * cls.shape[3]) if tr \
+                    else kw["rpn_post_nms_top_n"]
+                B = o.shape[0]                      # training with count < post: the written rows are the flat prefix
+                g[f"p3_{ci}_{int(tr)}_{int(iou)}_out"] = o.reshape(-1, 4)[:B * n].reshape(B, n, 4)
+                g[f"p3_{ci}_{int(tr)}_{int(iou)}_score"] = s_.reshape(-1)[:B * n].reshape(B, n, 1)
+    # Proposal / Proposal_v2 / GenProposal on the same cases, _contrib_NMS, GenProposalRetina (GPU operators on the host)
+    for ci, c in enumerate(T.PROPOSAL_V3_CASES):
+        c = dict(c)
+        kw = c.pop("kw")
+        cls, reg, info = T.rpn_case(**c)
+        B, A2, H, W = cls.shape
+        count = A2 // 2 * H * W
+        pre = min(kw["rpn_pre_nms_top_n"], count)
+        vr = np.array([[0, 64], [32, 1e5]], np.float32)[:B]
+        anchors = ref_cxx.forward("_contrib_GenAnchor", dict(feature_stride=kw["feature_stride"], scales=kw["scales"], ratios=kw["ratios"]),
+                                  [np.zeros((1, A2, H, W), np.float32)])[0].reshape(-1, 4)
+        for iou in (False, True):
+            for tr in (False, True):
+                o, s_ = ref_cxx.forward("_contrib_Proposal", dict(kw, is_train=tr, iou_loss=iou, output_score=True, workspace=64),
+                                        [cls, reg, info], dev="gpu")
+                n = min(kw["rpn_post_nms_top_n"], pre) if tr else kw["rpn_post_nms_top_n"]
+                g[f"p1_{ci}_{int(tr)}_{int(iou)}_out"], g[f"p1_{ci}_{int(tr)}_{int(iou)}_score"] = T.written(o, n, 4), T.written(s_, n, 1)
+            for filt in (False, True):
+                o, s_ = ref_cxx.forward("_contrib_Proposal_v2", dict(kw, filter_scales=filt, iou_loss=iou, output_score=True, workspace=64),
+                                        [cls, reg, info, vr], dev="gpu")
+                n = min(kw["rpn_post_nms_top_n"], pre)
+                g[f"p2_{ci}_{int(filt)}_{int(iou)}_out"], g[f"p2_{ci}_{int(filt)}_{int(iou)}_score"] = T.written(o, n, 4), T.written(s_, n, 1)
+            k = dict(feature_stride=kw["feature_stride"], rpn_pre_nms_top_n=150, rpn_min_size=kw["rpn_min_size"], iou_loss=iou)
+            (o,) = ref_cxx.forward("_contrib_GenProposal", dict(k, workspace=64), [cls, reg, info, anchors], dev="gpu")
+            g[f"gp_{ci}_{int(iou)}"] = o[:, :min(150, count)]
+    ndata = T.nms_case()
+    for pre, post in T.NMS_CASES:
+        kw = dict(rpn_pre_nms_top_n=pre, rpn_post_nms_top_n=post, threshold=0.6)
+        o, s_ = ref_cxx.forward("_contrib_NMS", dict(kw, output_score=True, workspace=64), [ndata], dev="gpu")
+        n = min(post, pre, ndata.shape[1])
+        g[f"nms_{pre}_{post}_out"], g[f"nms_{pre}_{post}_score"] = T.written(o, n, 4), T.written(s_, n, 1)
+    for K, thresh, pre, one_hot in T.RETINA_CASES:
+        cls, reg, info, anchors = T.retina_case(K)
+        kw = dict(num_anchors=9, rpn_pre_nms_top_n=pre, rpn_min_size=40, thresh=thresh, anchor_mean=(0.0, 0.1, 0.0, -0.1),
+                  anchor_std=(0.1, 0.1, 0.2, 0.2), output_one_hot=one_hot)
+        o, s_ = ref_cxx.forward("_contrib_GenProposalRetina", dict(kw, feature_stride=32, workspace=256),
+                                [cls, reg, info, anchors], dev="gpu")
+        # one-hot score rows are sparse; the npz is compressed
+        g[f"gr_{K}_{pre}_box"], g[f"gr_{K}_{pre}_score"] = o, s_
     path = os.path.join(HERE, "reference_cxx_ops.npz")
     np.savez_compressed(path, **g)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -212,6 +212,34 @@ def test_proposal_v3_fpn_equals_per_level_concat(cuda):
     np.testing.assert_allclose(out.cpu().numpy(), rb, rtol=1e-5, atol=1e-3)
 
 
+def test_proposal_v3_fpn_training_with_a_small_level(cuda):
+    """FPN training: P6 has fewer anchors than rpn_post_nms_top_n (819 < 2000 at 800x1333).  Every level keeps `post`
+    rows; a level writes min(post, its anchors) rows (kept boxes, then wrap-around padding like proposal_v3.cu:368-390)
+    and the rest are zero rows, which ProposalTarget ignores."""
+    rng = np.random.default_rng(22)
+    B, A = 2, 3
+    strides = (8, 16, 32, 64)
+    shapes = [(-(-256 // s), -(-384 // s)) for s in strides]          # 32x48 ... 4x6 (72 anchors)
+    cls = [rng.uniform(0, 1, (B, 2 * A, h, w)).astype(np.float32) for h, w in shapes]
+    dl = [(rng.standard_normal((B, 4 * A, h, w)) * 0.3).astype(np.float32) for h, w in shapes]
+    im_info = np.array([[256, 384, 1.0], [250, 380, 1.3]], np.float32)
+    post = 150
+    kw = dict(scales=(8,), ratios=(0.5, 1, 2), rpn_pre_nms_top_n=400, rpn_post_nms_top_n=post, threshold=0.7,
+              rpn_min_size=0, is_train=True)
+    out, sc = ops.Proposal_v3_fpn([_t(c, cuda) for c in cls], [_t(d, cuda) for d in dl], _t(im_info, cuda), strides, **kw)
+    out, sc = out.cpu().numpy(), sc.cpu().numpy()
+    assert out.shape == (B, len(strides) * post, 4)
+    for l, (c, d, s) in enumerate(zip(cls, dl, strides)):
+        rb, rs = oracle.proposal_v3(c, d, im_info, feature_stride=s, **kw)   # (B, min(post, anchors), .)
+        n = rb.shape[1]
+        assert n == min(post, A * c.shape[2] * c.shape[3])
+        blk, sblk = out[:, l * post:(l + 1) * post], sc[:, l * post:(l + 1) * post]
+        assert np.array_equal(sblk[:, :n], rs), l
+        np.testing.assert_allclose(blk[:, :n], rb, rtol=1e-5, atol=1e-3)
+        assert not blk[:, n:].any() and not sblk[:, n:].any()
+    assert (shapes[-1][0] * shapes[-1][1] * A) < post                  # the case is exercised
+
+
 @pytest.mark.parametrize("version,is_train,filt", [(1, False, False), (1, True, False), (2, False, True)])
 def test_proposal_legacy(cuda, version, is_train, filt):
     """_contrib_Proposal / _contrib_Proposal_v2: filter and padded-cell mask BEFORE the sort."""

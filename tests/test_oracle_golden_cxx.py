@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 import oracle
-from test_oracle_ref_cxx import BASE, FOCAL_MODES, focal_case, oracle_under_constant_rand, sigmoid_ce_case
+from test_oracle_ref_cxx import (BASE, FOCAL_MODES, NMS_CASES, PROPOSAL_V3_CASES, RETINA_CASES, focal_case, nms_case,
+                                 oracle_under_constant_rand, retina_case, rpn_case, sigmoid_ce_case)
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_cxx_ops.npz"))
 
@@ -59,3 +60,52 @@ def test_sigmoid_cross_entropy():
     data, label = sigmoid_ce_case()
     assert np.array_equal(oracle.sigmoid_ce_forward(data, label), G["sce_out"])
     assert np.array_equal(oracle.sigmoid_ce_backward(data, label, 0.37), G["sce_gdata"])
+
+
+def test_proposal_v3():
+    for ci, c in enumerate(PROPOSAL_V3_CASES):
+        c = dict(c)
+        kw = c.pop("kw")
+        cls, reg, info = rpn_case(**c)
+        for tr in (False, True):
+            for iou in (False, True):
+                r, sc = oracle.proposal_v3(cls, reg, info, is_train=tr, iou_loss=iou, **kw)
+                assert np.array_equal(r, G[f"p3_{ci}_{int(tr)}_{int(iou)}_out"]), (ci, tr, iou)
+                assert np.array_equal(sc, G[f"p3_{ci}_{int(tr)}_{int(iou)}_score"]), (ci, tr, iou)
+
+
+def test_proposal_v1_v2_gen_proposal():
+    for ci, c in enumerate(PROPOSAL_V3_CASES):
+        c = dict(c)
+        kw = c.pop("kw")
+        cls, reg, info = rpn_case(**c)
+        B, A2, H, W = cls.shape
+        vr = np.array([[0, 64], [32, 1e5]], np.float32)[:B]
+        anchors = oracle.gen_anchor(H, W, kw["feature_stride"], kw["scales"], kw["ratios"])
+        for iou in (False, True):
+            for tr in (False, True):
+                r, sc = oracle.proposal_legacy(cls, reg, info, version=1, is_train=tr, iou_loss=iou, **kw)
+                assert np.array_equal(r, G[f"p1_{ci}_{int(tr)}_{int(iou)}_out"]), (ci, tr, iou)
+                assert np.array_equal(sc, G[f"p1_{ci}_{int(tr)}_{int(iou)}_score"])
+            for filt in (False, True):
+                r, sc = oracle.proposal_legacy(cls, reg, info, version=2, valid_ranges=vr, filter_scales=filt, iou_loss=iou, **kw)
+                assert np.array_equal(r, G[f"p2_{ci}_{int(filt)}_{int(iou)}_out"]), (ci, filt, iou)
+                assert np.array_equal(sc, G[f"p2_{ci}_{int(filt)}_{int(iou)}_score"])
+            gp = oracle.gen_proposal(cls, reg, info, anchors, feature_stride=kw["feature_stride"], rpn_pre_nms_top_n=150,
+                                     rpn_min_size=kw["rpn_min_size"], iou_loss=iou)
+            n = G[f"gp_{ci}_{int(iou)}"].shape[1]
+            assert np.array_equal(gp[:, :n], G[f"gp_{ci}_{int(iou)}"])
+
+
+def test_contrib_nms_and_gen_proposal_retina():
+    data = nms_case()
+    for pre, post in NMS_CASES:
+        r, sc = oracle.contrib_nms(data, rpn_pre_nms_top_n=pre, rpn_post_nms_top_n=post, threshold=0.6)
+        n = G[f"nms_{pre}_{post}_out"].shape[1]
+        assert np.array_equal(r[:, :n], G[f"nms_{pre}_{post}_out"]) and np.array_equal(sc[:, :n], G[f"nms_{pre}_{post}_score"])
+    for K, thresh, pre, one_hot in RETINA_CASES:
+        cls, reg, info, anchors = retina_case(K)
+        rb, rs = oracle.gen_proposal_retina(cls, reg, info, anchors, num_anchors=9, rpn_pre_nms_top_n=pre, rpn_min_size=40,
+                                            thresh=thresh, anchor_mean=(0.0, 0.1, 0.0, -0.1), anchor_std=(0.1, 0.1, 0.2, 0.2),
+                                            output_one_hot=one_hot)
+        assert np.array_equal(rb, G[f"gr_{K}_{pre}_box"]) and np.array_equal(rs, G[f"gr_{K}_{pre}_score"]), K

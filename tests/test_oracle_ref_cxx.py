@@ -395,3 +395,99 @@ def test_proposal_v3_gpu_operator(case, is_train, iou_loss):
         B = out.shape[0]
         assert np.array_equal(out.reshape(-1, 4)[:B * n], r.reshape(-1, 4))
         assert np.array_equal(score.reshape(-1)[:B * n], sc.reshape(-1))
+
+
+# ------------------------------------------------------------------------- the rest of the proposal family (GPU operators)
+# proposal.cu, proposal_v2.cu, nms.cu, generate_proposal.cu, generate_proposal_retina.cu: same build treatment as
+# proposal_v3.cu.  All of them shrink `rpn_post_nms_top_n` to min(post, pre) and then use the shrunken value as the
+# per-image stride of the (B, post_param, .) output (proposal.cu / nms.cu PrepareOutput call sites), so when
+# pre < post the rows of image b land at flat row b*n: `written()` reads them from where the reference put them.
+def written(buf, n, last):
+    B = buf.shape[0]
+    return buf.reshape(-1, last)[:B * n].reshape(B, n, last)
+
+
+@pytest.mark.parametrize("case", range(len(PROPOSAL_V3_CASES)))
+@pytest.mark.parametrize("iou_loss", [False, True])
+def test_proposal_v1_v2_gpu_operators(case, iou_loss):
+    c = dict(PROPOSAL_V3_CASES[case])
+    kw = dict(c.pop("kw"), iou_loss=iou_loss)
+    cls, reg, info = rpn_case(**c)
+    for is_train in (False, True):
+        out, score = ref_cxx.forward("_contrib_Proposal", dict(kw, is_train=is_train, output_score=True, workspace=64),
+                                     [cls, reg, info], dev="gpu")
+        r, sc = oracle.proposal_legacy(cls, reg, info, version=1, is_train=is_train, **kw)
+        assert np.array_equal(written(out, r.shape[1], 4), r), (is_train,)
+        assert np.array_equal(written(score, r.shape[1], 1), sc)
+    vr = np.array([[0, 64], [32, 1e5]], np.float32)[:cls.shape[0]]
+    for filt in (False, True):
+        out, score = ref_cxx.forward("_contrib_Proposal_v2", dict(kw, filter_scales=filt, output_score=True, workspace=64),
+                                     [cls, reg, info, vr], dev="gpu")
+        r, sc = oracle.proposal_legacy(cls, reg, info, version=2, valid_ranges=vr, filter_scales=filt, **kw)
+        assert np.array_equal(written(out, r.shape[1], 4), r), (filt,)
+        assert np.array_equal(written(score, r.shape[1], 1), sc)
+
+
+def nms_case(seed=3, B=2, count=500):
+    from simpledet_b200 import synth
+    rng = np.random.default_rng(seed)
+    sc = rng.uniform(0, 1, (B, count, 1)).astype(np.float32)
+    sc[0, 10:20] = sc[0, 10]                                  # equal scores: stable order
+    return np.concatenate([synth.random_rois(rng, B, count), sc], 2)
+
+
+NMS_CASES = [(300, 100), (6000, 300), (200, 400)]             # pre < count; pre > count; post > pre (shrunken stride)
+
+
+@pytest.mark.parametrize("already_sorted", [False, True])
+@pytest.mark.parametrize("pre,post", NMS_CASES)
+def test_contrib_nms_gpu_operator(already_sorted, pre, post):
+    data = nms_case()
+    if already_sorted:
+        data = np.stack([x[np.argsort(-x[:, 4], kind="stable")] for x in data])
+    kw = dict(rpn_pre_nms_top_n=pre, rpn_post_nms_top_n=post, threshold=0.6, already_sorted=already_sorted)
+    out, score = ref_cxx.forward("_contrib_NMS", dict(kw, output_score=True, workspace=64), [data], dev="gpu")
+    r, sc = oracle.contrib_nms(data, **kw)
+    n = min(post, pre, data.shape[1])
+    assert np.array_equal(written(out, n, 4), r[:, :n]) and np.array_equal(written(score, n, 1), sc[:, :n])
+
+
+@pytest.mark.parametrize("case", range(len(PROPOSAL_V3_CASES)))
+@pytest.mark.parametrize("iou_loss", [False, True])
+def test_gen_proposal_gpu_operator(case, iou_loss):
+    c = dict(PROPOSAL_V3_CASES[case])
+    kw = c.pop("kw")
+    cls, reg, info = rpn_case(**c)
+    B, A2, H, W = cls.shape
+    anchors = oracle.gen_anchor(H, W, kw["feature_stride"], kw["scales"], kw["ratios"])
+    for pre in (150, A2 // 2 * H * W + 40):                   # more rows than anchors: the tail is never written
+        k = dict(feature_stride=kw["feature_stride"], rpn_pre_nms_top_n=pre, rpn_min_size=kw["rpn_min_size"], iou_loss=iou_loss)
+        (out,) = ref_cxx.forward("_contrib_GenProposal", dict(k, workspace=64), [cls, reg, info, anchors], dev="gpu")
+        n = min(pre, A2 // 2 * H * W)
+        assert np.array_equal(out[:, :n], oracle.gen_proposal(cls, reg, info, anchors, **k)[:, :n])
+
+
+RETINA_CASES = [(80, 0.05, 1000, True), (80, 0.0, 300, True), (1, 0.3, 1000, True), (8, 0.05, 100, False)]
+
+
+def retina_case(K, seed=52, B=2, A=9, H=13, W=21, stride=32):
+    rng = np.random.default_rng(seed + K)
+    cls = (rng.uniform(0, 1, (B, A * K, H, W)) ** 4).astype(np.float32)
+    if K > 4:
+        cls[0, :4] = cls[0, 4:8]                              # equal scores across classes
+    reg = (rng.standard_normal((B, 4 * A, H, W)) * 0.5).astype(np.float32)
+    info = np.array([[H * stride - 20, W * stride - 40, 1.0], [H * stride, W * stride, 1.6]], np.float32)
+    anchors = oracle.gen_anchor(H, W, stride, tuple(4 * 2 ** (i / 3) for i in range(3)), (0.5, 1, 2))
+    return cls, reg, info, anchors
+
+
+@pytest.mark.parametrize("K,thresh,pre,one_hot", RETINA_CASES)
+def test_gen_proposal_retina_gpu_operator(K, thresh, pre, one_hot):
+    cls, reg, info, anchors = retina_case(K)
+    kw = dict(num_anchors=9, rpn_pre_nms_top_n=pre, rpn_min_size=40, thresh=thresh, anchor_mean=(0.0, 0.1, 0.0, -0.1),
+              anchor_std=(0.1, 0.1, 0.2, 0.2), output_one_hot=one_hot)
+    box, score = ref_cxx.forward("_contrib_GenProposalRetina", dict(kw, feature_stride=32, workspace=256),
+                                 [cls, reg, info, anchors], dev="gpu")
+    rb, rs = oracle.gen_proposal_retina(cls, reg, info, anchors, **kw)
+    assert np.array_equal(box, rb) and np.array_equal(score, rs)
+    assert (rs != 0).any()
