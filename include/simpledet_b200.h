@@ -339,11 +339,20 @@ int sdet_proposal_target_v2(const float* rois, const float* gt_boxes, const floa
  *   models/maskrcnn/input.py:166-175) is rasterised into mask_target[b,i] (mask_size^2, values
  *   0/1) in the roi-normalised frame; other rows are filled with -1 (ignored by
  *   SigmoidCrossEntropy).  num_mask_rows = (int)(image_rois * fg_fraction).  gt_index / fg_count
- *   are the optional outputs of sdet_proposal_target (int32, device).
- *   Not built: output_ratio (MS-RCNN mask ratio), filter_scales / valid_ranges (num_args = 4). */
+ *   are the optional outputs of sdet_proposal_target[_v2] (int32, device); filter_scales / valid_ranges
+ *   (num_args = 4) is sdet_proposal_target_v2 in front of the same call.
+ *   sdet_poly_mask_target_ratio = output_ratio=True (Mask Scoring R-CNN, models/msrcnn/builder.py:219-239;
+ *   convertPoly2MaskWithRatio, proposal_mask_target.cc:20-152): the mask with the vertex transform carried out in
+ *   double as that variant does, plus mask_ratio (B, num_mask_rows) = |polygon in the roi crop| / (|polygon| + 1e-4)
+ *   counted on the reference's integer rasters, clamped from below at 1e-10; rows >= fg_count[b] are 0.  A roi whose
+ *   polygon crosses more than 16384 pixel columns in one segment (32768 over all segments) gets NaN. */
 int sdet_poly_mask_target(const float* rois_out, const float* gt_polys, const int* gt_index,
                           const int* fg_count, float* mask_target, int B, int image_rois, int G,
                           int poly_len, int num_mask_rows, int mask_size, void* stream);
+int sdet_poly_mask_target_ratio(const float* rois_out, const float* gt_polys, const int* gt_index,
+                                const int* fg_count, float* mask_target, float* mask_ratio, int B,
+                                int image_rois, int G, int poly_len, int num_mask_rows, int mask_size,
+                                void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * _contrib_FocalLoss  (operator_cxx/contrib/focal_loss-inl.h:52-79 params, :90-114 forward =

@@ -315,21 +315,36 @@ def poly2mask(roi, poly, mask_size):
     return out.reshape(mask_size, mask_size)
 
 
+def poly2mask_ratio(roi, poly, mask_size):
+    """convertPoly2MaskWithRatio (proposal_mask_target.cc:20-152) -> ((M,M) float32 mask, ratio as float64)."""
+    roi, poly = _f32(roi), _f32(poly)
+    out = np.empty(mask_size * mask_size, np.float32)
+    f = lib().oracle_poly2mask_ratio
+    f.restype = ctypes.c_double
+    ratio = f(_p(roi), _p(poly), int(mask_size), _p(out))
+    return out.reshape(mask_size, mask_size), ratio
+
+
 def proposal_mask_target(rois, gt_boxes, gt_polys, priorities, num_classes, image_rois, mask_size,
-                         fg_fraction=0.25, **kw):
+                         fg_fraction=0.25, output_ratio=False, **kw):
     """ProposalMaskTarget (proposal_mask_target-inl.h:139-337, proposal_mask_target.cc:219-379) =
     ProposalTarget + masks of the first fg rows; mask_target (B, int(IR*fg_fraction), M, M) is
-    pre-filled with -1 (-inl.h:242-243)."""
+    pre-filled with -1 (-inl.h:242-243).  output_ratio adds mask_ratio (B, int(IR*fg_fraction)), pre-filled
+    with 0 (-inl.h:244), and switches the mask's vertex transform to double (.cc:368-371)."""
     r = proposal_target(rois, gt_boxes, priorities, num_classes, image_rois, fg_fraction, return_match=True, **kw)
     o_rois, gt_index, fg_count = r[0], r[6], r[7]
     gt_polys = _f32(gt_polys)
     B = o_rois.shape[0]
     nm = int(image_rois * fg_fraction)
     mask = np.full((B, nm, mask_size, mask_size), -1, np.float32)
+    ratio = np.zeros((B, nm), np.float32)
     for b in range(B):
         for i in range(min(int(fg_count[b]), nm)):
-            mask[b, i] = poly2mask(o_rois[b, i], gt_polys[b, gt_index[b, i]], mask_size)
-    return r[:5] + (mask,)
+            if output_ratio:
+                mask[b, i], ratio[b, i] = poly2mask_ratio(o_rois[b, i], gt_polys[b, gt_index[b, i]], mask_size)
+            else:
+                mask[b, i] = poly2mask(o_rois[b, i], gt_polys[b, gt_index[b, i]], mask_size)
+    return r[:5] + ((mask, ratio) if output_ratio else (mask,))
 
 
 # ---------------------------------------------------------------------------------------------

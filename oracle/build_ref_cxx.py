@@ -30,6 +30,8 @@ SOURCES = [
     ("contrib/decodebbox.cc", False),     # BBoxTransformXYWH/XYXY (:34-133) + DecodeBBoxOp::Forward
     ("proposal_target.cc", True),         # SampleROI, BBoxOverlap, targets (:22-227) + ProposalTargetOp::Forward
     ("proposal_target_v2.cc", True),
+    # ProposalMaskTarget: the operator against a stand-in maskApi.h (oracle/shim/coco_api: cocoapi is not in the tree)
+    ("proposal_mask_target.cc", True),
     ("contrib/generate_anchor.cc", False),  # GenAnchorOp<cpu>::Forward + gen_anchor_utils (generate_anchor-inl.h:139-183)
     ("contrib/focal_loss.cc", False),     # FocalLossOp::Forward / Backward as mshadow expressions (focal_loss-inl.h:100-231)
     ("contrib/bbox_norm.cc", False),      # BBoxNormOp::Backward (bbox_norm-inl.h:99-129)

@@ -107,3 +107,75 @@ void oracle_poly2mask(const float* roi, const float* poly, int mask_size, float*
   }
   free(seg);
 }
+
+/* proposal_mask_target.cc:20-152 convertPoly2MaskWithRatio (output_ratio=True, Mask Scoring R-CNN): the roi mask
+ * with the vertex transform carried out in DOUBLE (`poly_index` is a double there; the plain variant above works in
+ * float), plus  ratio = |polygon ∩ roi crop| / (|polygon| + 1e-4)  counted on two integer rasters: the crop
+ * (crop_h x crop_w, roi corners truncated to int) and the polygon's own extent joined with the roi (full_h x full_w).
+ * Returns the ratio as the double the reference returns; the operator stores it into a float. */
+double oracle_poly2mask_ratio(const float* roi, const float* poly, int mask_size, float* mask) {
+  float w = roi[2] - roi[0], h = roi[3] - roi[1];
+  w = 1.f > w ? 1.f : w;
+  h = 1.f > h ? 1.f : h;
+  const int n_seg = (int)poly[1];
+  const int MM = mask_size * mask_size;
+  const int rx1 = (int)roi[0], rx2 = (int)roi[2], ry1 = (int)roi[1], ry2 = (int)roi[3];
+  const long crop_w = rx2 - rx1 + 1, crop_h = ry2 - ry1 + 1;
+  double ox1 = roi[0], ox2 = roi[2], oy1 = roi[1], oy2 = roi[3];
+  unsigned char* seg = (unsigned char*)malloc((size_t)MM);
+  unsigned char* crop = (unsigned char*)calloc((size_t)(crop_w * crop_h > 0 ? crop_w * crop_h : 1), 1);
+  unsigned char* tmp = (unsigned char*)malloc((size_t)(crop_w * crop_h > 0 ? crop_w * crop_h : 1));
+  for (int j = 0; j < MM; ++j) mask[j] = 0.f;
+  int offset = 2 + n_seg;
+  for (int i = 0; i < n_seg; ++i) {
+    const int cur_len = (int)poly[i + 2];
+    double* xys = (double*)malloc(sizeof(double) * (size_t)(cur_len > 0 ? cur_len : 1));
+    double* xyc = (double*)malloc(sizeof(double) * (size_t)(cur_len > 0 ? cur_len : 1));
+    for (int j = 0; j < cur_len; ++j) {
+      if (j % 2 == 0) {                       /* a y coordinate (:51-58) */
+        const double py = poly[offset + j + 1];
+        oy1 = oy1 < py ? oy1 : py;
+        oy2 = oy2 < py ? py : oy2;
+        xys[j] = (py - roi[1]) * mask_size / h;
+        xyc[j + 1] = py - roi[1];
+      } else {                                /* an x coordinate (:59-65) */
+        const double px = poly[offset + j - 1];
+        ox1 = ox1 < px ? ox1 : px;
+        ox2 = ox2 < px ? px : ox2;
+        xys[j] = (px - roi[0]) * mask_size / w;
+        xyc[j - 1] = px - roi[0];
+      }
+    }
+    oracle_rle_fr_poly_mask(xys, cur_len / 2, mask_size, mask_size, seg);
+    for (int j = 0; j < MM; ++j) if (seg[j] == 1) mask[j] = 1.f;
+    oracle_rle_fr_poly_mask(xyc, cur_len / 2, crop_h, crop_w, tmp);
+    for (long j = 0; j < crop_w * crop_h; ++j) crop[j] |= tmp[j];
+    free(xys);
+    free(xyc);
+    offset += cur_len;
+  }
+  const int ix1 = (int)ox1, ix2 = (int)ox2, iy1 = (int)oy1, iy2 = (int)oy2;
+  const long full_w = ix2 - ix1 + 1, full_h = iy2 - iy1 + 1;
+  unsigned char* full = (unsigned char*)calloc((size_t)(full_w * full_h > 0 ? full_w * full_h : 1), 1);
+  unsigned char* ftmp = (unsigned char*)malloc((size_t)(full_w * full_h > 0 ? full_w * full_h : 1));
+  offset = 2 + n_seg;
+  for (int i = 0; i < n_seg; ++i) {
+    const int cur_len = (int)poly[i + 2];
+    double* xyo = (double*)malloc(sizeof(double) * (size_t)(cur_len > 0 ? cur_len : 1));
+    for (int j = 0; j < cur_len; ++j) {
+      if (j % 2 == 0) xyo[j + 1] = (double)poly[offset + j + 1] - oy1;   /* :89-92 */
+      else xyo[j - 1] = (double)poly[offset + j - 1] - ox1;             /* :93-96 */
+    }
+    oracle_rle_fr_poly_mask(xyo, cur_len / 2, full_h, full_w, ftmp);
+    for (long j = 0; j < full_w * full_h; ++j) full[j] |= ftmp[j];
+    free(xyo);
+    offset += cur_len;
+  }
+  double origin_sum = 0, crop_sum = 0;
+  for (long j = 0; j < full_w * full_h; ++j) origin_sum += full[j];
+  for (long j = 0; j < crop_w * crop_h; ++j) crop_sum += crop[j];
+  double ratio = crop_sum / (origin_sum + 0.0001);
+  ratio = ratio < 1e-10 ? 1e-10 : ratio;
+  free(seg); free(crop); free(tmp); free(full); free(ftmp);
+  return ratio;
+}

@@ -949,6 +949,7 @@ struct PropEntry {
   PropEntry& add_argument(const std::string&, const std::string&, const std::string&) { return *this; }
   template <typename T> PropEntry& add_arguments(const T&) { return *this; }
   PropEntry& set_return_type(const std::string&) { return *this; }
+  PropEntry& set_key_var_num_args(const std::string&) { return *this; }
   static std::map<std::string, PropEntry>& All() { static std::map<std::string, PropEntry> r; return r; }
   static PropEntry& Register(const std::string& name, std::function<OperatorProperty*()> f) {
     PropEntry& e = All()[name];

@@ -101,6 +101,7 @@ _SIGNATURES = {
                                 c_float, c_float, c_float, c_int, c_int, c_int, POINTER(c_float),
                                 POINTER(c_float), POINTER(c_float), c_uint64, _P, c_int, _P, _P, _P, _P],
     "sdet_poly_mask_target": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "sdet_poly_mask_target_ratio": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "sdet_focal_loss_forward": [_P, _P, c_size_t, _P],
     "sdet_focal_loss_backward": [_P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float, c_int, _P,
                                  c_size_t, _P],

@@ -315,6 +315,8 @@ struct MaskParams {
   const int* fg_count;     // (B)
   float* mask;             // (B,NM,M,M)
   int IR, G, PL, NM, M;
+  int double_xy;           // 1: the roi-frame vertex transform in double (convertPoly2MaskWithRatio, .cc:51-65)
+  float* ratio;            // (B,NM) mask ratio, poly_ratio_kernel only
 };
 
 __device__ __forceinline__ void dda_point(int xs, int ys, int dx, int dy, double sl, bool flip, int d, int& u,
@@ -372,8 +374,14 @@ __global__ void __launch_bounds__(256) poly_mask_kernel(const MaskParams p) {
       // vertex j in upsampled integer coordinates; note the (y', x') order of :182-187
       auto vert = [&](int j, int& X, int& Y) {
         j = (j == k) ? 0 : j;
-        const double a = (double)__fdiv_rn(__fmul_rn(__fsub_rn(poly[offset + 2 * j + 1], roi[1]), (float)M), h);
-        const double c = (double)__fdiv_rn(__fmul_rn(__fsub_rn(poly[offset + 2 * j], roi[0]), (float)M), w);
+        double a, c;
+        if (p.double_xy) {  // `poly_index` is a double in the ratio variant: ((py - roi[1]) * mask_size) / h in double
+          a = __ddiv_rn(__dmul_rn(__dsub_rn((double)poly[offset + 2 * j + 1], (double)roi[1]), (double)M), (double)h);
+          c = __ddiv_rn(__dmul_rn(__dsub_rn((double)poly[offset + 2 * j], (double)roi[0]), (double)M), (double)w);
+        } else {
+          a = (double)__fdiv_rn(__fmul_rn(__fsub_rn(poly[offset + 2 * j + 1], roi[1]), (float)M), h);
+          c = (double)__fdiv_rn(__fmul_rn(__fsub_rn(poly[offset + 2 * j], roi[0]), (float)M), w);
+        }
         X = (int)__dadd_rn(__dmul_rn(5.0, a), .5);
         Y = (int)__dadd_rn(__dmul_rn(5.0, c), .5);
       };
@@ -492,6 +500,282 @@ __global__ void __launch_bounds__(256) poly_mask_kernel(const MaskParams p) {
   for (int j = tid; j < MM; j += blockDim.x) out[j] = s_acc[j] ? 1.f : 0.f;
 }
 
+
+// --------------------------------------------------------------------------------------------
+// mask_ratio of ProposalMaskTarget(output_ratio=True) - convertPoly2MaskWithRatio, proposal_mask_target.cc:20-152:
+//   ratio = |polygon ∩ roi crop| / (|polygon| + 1e-4), both areas COUNTED on integer rasters produced by rleFrPoly:
+//   the crop raster (crop_h x crop_w, roi corners truncated to int, polygon shifted by the roi corner) and the raster
+//   of the polygon's own extent joined with the roi (full_h x full_w, shifted by the extent's corner).
+// Those rasters are image-sized (up to ~1 M pixels per roi), but a count needs no pixels.  rleFrPoly's output is the
+// sorted list of toggle positions a_0 <= a_1 <= ... (column-major pixel index): the segment covers [a_0,a_1) u
+// [a_2,a_3) u ...  So per segment: generate the toggle positions (the same point-parallel walk as poly_mask_kernel),
+// sort them, tag each with on (even rank) / off (odd rank); merge all segments' events by position (a second sort),
+// prefix-sum the +1/-1 tags = how many segments cover the interval that starts at each event, and add up the
+// intervals with coverage > 0 - the union over segments the reference forms pixel by pixel (:122-141).
+// One CTA per (image, foreground row); events live in shared memory.  A roi whose polygon produces more events than
+// the tables hold (kSegCap per segment, kEvCap in total - thousands of column crossings) gets ratio = NaN, loudly.
+// --------------------------------------------------------------------------------------------
+constexpr int kEvCap = 32768, kSegCap = 16384, kRatioThreads = 512;
+
+__device__ void bitonic_sort_u32(unsigned* a, int n2) {  // n2 a power of two, every thread of the CTA calls it
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned x = a[i], y = a[ixj];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) {
+            a[i] = y;
+            a[ixj] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kRatioThreads) poly_ratio_kernel(const MaskParams p) {
+  extern __shared__ unsigned s_ev[];  // kEvCap merged events (pos << 1 | on), then kSegCap positions of one segment
+  unsigned* s_seg = s_ev + kEvCap;
+  __shared__ EdgeRec s_edge[kMaxEdges];
+  __shared__ int s_scan[kRatioThreads];
+  __shared__ float s_red[4][kRatioThreads / 32];
+  __shared__ int s_total, s_last[2], s_nseg_ev, s_nev, s_over, s_count;
+  const int row = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  float* out = p.ratio + (size_t)b * p.NM + row;
+  const int nfg = min(p.fg_count[b], p.NM);
+  if (row >= nfg) {  // rows beyond the foreground count keep the initial 0 (-inl.h:244)
+    if (tid == 0) *out = 0.f;
+    return;
+  }
+  const int gi = p.gt_index[(size_t)b * p.IR + row];
+  if (gi < 0) {  // no ground truth: nothing rasterised, 0 / 1e-4 clamped from below (:143-144)
+    if (tid == 0) *out = (float)1e-10;
+    return;
+  }
+  const float* roi = p.rois_out + ((size_t)b * p.IR + row) * 4;
+  const float* poly = p.gt_polys + ((size_t)b * p.G + gi) * p.PL;
+  const int n_seg = (int)poly[1];
+  // ---- the polygon's extent joined with the roi (:45, :54-62): min / max over every vertex
+  float mnx = roi[0], mxx = roi[2], mny = roi[1], mxy = roi[3];
+  {
+    int offset = 2 + n_seg;
+    for (int sg = 0; sg < n_seg; ++sg) {
+      const int k = (int)poly[sg + 2] / 2;
+      for (int j = tid; j < k; j += blockDim.x) {
+        const float x = poly[offset + 2 * j], y = poly[offset + 2 * j + 1];
+        mnx = fmin_ref(mnx, x);
+        mxx = fmax_ref(mxx, x);
+        mny = fmin_ref(mny, y);
+        mxy = fmax_ref(mxy, y);
+      }
+      offset += (int)poly[sg + 2];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      mnx = fmin_ref(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+      mxx = fmax_ref(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+      mny = fmin_ref(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+      mxy = fmax_ref(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    if ((tid & 31) == 0) {
+      s_red[0][tid >> 5] = mnx;
+      s_red[1][tid >> 5] = mxx;
+      s_red[2][tid >> 5] = mny;
+      s_red[3][tid >> 5] = mxy;
+    }
+    if (tid == 0) s_over = 0;
+    __syncthreads();
+    for (int wi = 0; wi < kRatioThreads / 32; ++wi) {
+      mnx = fmin_ref(mnx, s_red[0][wi]);
+      mxx = fmax_ref(mxx, s_red[1][wi]);
+      mny = fmin_ref(mny, s_red[2][wi]);
+      mxy = fmax_ref(mxy, s_red[3][wi]);
+    }
+  }
+  int counts[2];
+  for (int z = 0; z < 2; ++z) {
+    // raster size and the corner the polygon is shifted by
+    double bx, by;
+    int W, H;
+    if (z == 0) {  // the roi crop (:41-46, :57, :64)
+      const int x1 = (int)roi[0], x2 = (int)roi[2], y1 = (int)roi[1], y2 = (int)roi[3];
+      W = x2 - x1 + 1;
+      H = y2 - y1 + 1;
+      bx = (double)roi[0];
+      by = (double)roi[1];
+    } else {       // the extent (:76-82, :89-96)
+      W = (int)(double)mxx - (int)(double)mnx + 1;
+      H = (int)(double)mxy - (int)(double)mny + 1;
+      bx = (double)mnx;
+      by = (double)mny;
+    }
+    if (W <= 0 || H <= 0 || (long long)W * H > (1ll << 30)) {
+      if (tid == 0) s_over = 1;
+      counts[z] = 0;
+      __syncthreads();
+      continue;
+    }
+    const int HW = W * H;
+    if (tid == 0) s_nev = 0;
+    __syncthreads();
+    int offset = 2 + n_seg;
+    for (int sg = 0; sg < n_seg; ++sg) {
+      const int cur_len = (int)poly[sg + 2];
+      const int k = cur_len / 2;
+      if (tid == 0) s_nseg_ev = 0;
+      __syncthreads();
+      auto vert = [&](int j, int& X, int& Y) {  // natural (x, y) order here
+        j = (j == k) ? 0 : j;
+        const double a = __dsub_rn((double)poly[offset + 2 * j], bx);
+        const double c = __dsub_rn((double)poly[offset + 2 * j + 1], by);
+        X = (int)__dadd_rn(__dmul_rn(5.0, a), .5);
+        Y = (int)__dadd_rn(__dmul_rn(5.0, c), .5);
+      };
+      for (int e0 = 0; e0 < k; e0 += kMaxEdges) {
+        const int nb = min(kMaxEdges, k - e0);
+        for (int e = tid; e < nb; e += blockDim.x) {
+          int xs, ys, xe, ye;
+          vert(e0 + e, xs, ys);
+          vert(e0 + e + 1, xe, ye);
+          const int dx = abs(xe - xs), dy = abs(ys - ye);
+          const bool flip = (dx >= dy && xs > xe) || (dx < dy && ys > ye);
+          if (flip) {
+            int t = xs; xs = xe; xe = t;
+            t = ys; ys = ye; ye = t;
+          }
+          EdgeRec er;
+          er.xs = xs; er.ys = ys; er.dx = dx; er.dy = dy; er.flip = flip;
+          er.sl = dx >= dy ? __ddiv_rn((double)(ye - ys), (double)dx) : __ddiv_rn((double)(xe - xs), (double)dy);
+          er.npts = max(dx, dy) + 1;
+          er.start = 0;
+          s_edge[e] = er;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int acc = 0;
+          for (int e = 0; e < nb; ++e) {
+            s_edge[e].start = acc;
+            acc += s_edge[e].npts;
+          }
+          s_total = acc;
+        }
+        __syncthreads();
+        const int total = s_total;
+        for (int i = tid; i < total; i += blockDim.x) {
+          int lo = 0, hi = nb - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_edge[mid].start <= i) lo = mid;
+            else hi = mid - 1;
+          }
+          const EdgeRec er = s_edge[lo];
+          const int d = i - er.start;
+          int u, v, pu, pv;
+          dda_point(er.xs, er.ys, er.dx, er.dy, er.sl, er.flip, d, u, v);
+          if (d > 0) {
+            dda_point(er.xs, er.ys, er.dx, er.dy, er.sl, er.flip, d - 1, pu, pv);
+          } else if (lo > 0) {
+            const EdgeRec pr = s_edge[lo - 1];
+            dda_point(pr.xs, pr.ys, pr.dx, pr.dy, pr.sl, pr.flip, pr.npts - 1, pu, pv);
+          } else if (e0 > 0) {
+            pu = s_last[0];
+            pv = s_last[1];
+          } else {
+            continue;
+          }
+          if (u != pu) {
+            double xd = (double)(u < pu ? u : u - 1);
+            xd = __dsub_rn(__ddiv_rn(__dadd_rn(xd, .5), 5.0), .5);
+            if (!(floor(xd) != xd || xd < 0 || xd > (double)(W - 1))) {
+              double yd = (double)(v < pv ? v : pv);
+              yd = __dsub_rn(__ddiv_rn(__dadd_rn(yd, .5), 5.0), .5);
+              if (yd < 0) yd = 0;
+              else if (yd > (double)H) yd = (double)H;
+              yd = ceil(yd);
+              const int pos = (int)xd * H + (int)yd;  // <= H*W
+              const int slot = atomicAdd(&s_nseg_ev, 1);
+              if (slot < kSegCap) s_seg[slot] = (unsigned)pos;
+            }
+          }
+        }
+        __syncthreads();
+        if (tid == 0) {
+          const EdgeRec pr = s_edge[nb - 1];
+          int lu, lv;
+          dda_point(pr.xs, pr.ys, pr.dx, pr.dy, pr.sl, pr.flip, pr.npts - 1, lu, lv);
+          s_last[0] = lu;
+          s_last[1] = lv;
+        }
+        __syncthreads();
+      }
+      // ---- this segment's positions in order: even rank switches the segment on, odd rank off
+      const int nraw = s_nseg_ev, base = s_nev;
+      const int n = min(nraw, kSegCap);
+      if (nraw > kSegCap || base + n > kEvCap) {
+        if (tid == 0) s_over = 1;
+      } else if (n > 0) {
+        int n2 = 1;
+        while (n2 < n) n2 <<= 1;
+        for (int i = n + tid; i < n2; i += blockDim.x) s_seg[i] = 0xffffffffu;
+        __syncthreads();
+        bitonic_sort_u32(s_seg, n2);
+        for (int i = tid; i < n; i += blockDim.x) s_ev[base + i] = (s_seg[i] << 1) | ((i & 1) ? 0u : 1u);
+      }
+      __syncthreads();
+      if (tid == 0 && !(nraw > kSegCap || base + n > kEvCap)) s_nev = base + n;
+      __syncthreads();
+      offset += cur_len;
+    }
+    // ---- merge by position, coverage = running sum of on / off, add up the covered intervals
+    const int n = s_nev;
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int i = n + tid; i < n2; i += blockDim.x) s_ev[i] = 0xffffffffu;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    if (n > 1) bitonic_sort_u32(s_ev, n2);
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int i0 = min(n, tid * per), i1 = min(n, i0 + per);
+    int local = 0;
+    for (int i = i0; i < i1; ++i) local += (s_ev[i] & 1u) ? 1 : -1;
+    s_scan[tid] = local;
+    __syncthreads();
+    if (tid == 0) {  // exclusive prefix of the per-thread sums
+      int acc = 0;
+      for (int t = 0; t < (int)blockDim.x; ++t) {
+        const int v = s_scan[t];
+        s_scan[t] = acc;
+        acc += v;
+      }
+    }
+    __syncthreads();
+    int cover = s_scan[tid], area = 0;
+    for (int i = i0; i < i1; ++i) {
+      const unsigned e = s_ev[i];
+      cover += (e & 1u) ? 1 : -1;
+      const int pos = (int)(e >> 1);
+      const int nxt = (i + 1 < n) ? (int)(s_ev[i + 1] >> 1) : HW;
+      if (cover > 0) area += nxt - pos;
+    }
+    for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(0xffffffffu, area, o);
+    if ((tid & 31) == 0 && area) atomicAdd(&s_count, area);
+    __syncthreads();
+    counts[z] = s_count;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (s_over) {
+      *out = __int_as_float(0x7fc00000);
+    } else {
+      double r = __ddiv_rn((double)counts[0], __dadd_rn((double)counts[1], 0.0001));  // :143
+      r = r < 1e-10 ? 1e-10 : r;                                                          // :144 max(ratio, 1e-10)
+      *out = (float)r;
+    }
+  }
+}
+
 size_t pt_smem_bytes(int T, int G, int IR) {
   int np2 = 1;
   while (np2 < T) np2 <<= 1;
@@ -580,6 +864,27 @@ extern "C" int sdet_proposal_target_v2(const float* rois, const float* gt_boxes,
                               fg_count, stream);
 }
 
+// mask_ratio == nullptr: convertPoly2Mask; else convertPoly2MaskWithRatio (double vertex transform + the ratio)
+static int run_poly_mask(const float* rois_out, const float* gt_polys, const int* gt_index, const int* fg_count,
+                         float* mask_target, float* mask_ratio, int B, int image_rois, int G, int poly_len,
+                         int num_mask_rows, int mask_size, void* stream) {
+  MaskParams p{rois_out, gt_polys, gt_index, fg_count, mask_target, image_rois, G, poly_len, num_mask_rows, mask_size,
+               mask_ratio ? 1 : 0, mask_ratio};
+  const size_t smem = sizeof(int) * (size_t)(2 * mask_size * mask_size + 2);
+  if (smem > 48 * 1024)  // per device and cheap: set on every launch, no process-wide cache
+    SDET_CUDA(cudaFuncSetAttribute(poly_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)num_mask_rows, (unsigned)B);
+  poly_mask_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  SDET_LAUNCH_CHECK("poly_mask_kernel");
+  if (mask_ratio) {
+    const size_t rsmem = sizeof(unsigned) * (size_t)(kEvCap + kSegCap);
+    SDET_CUDA(cudaFuncSetAttribute(poly_ratio_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+    poly_ratio_kernel<<<grid, kRatioThreads, rsmem, (cudaStream_t)stream>>>(p);
+    SDET_LAUNCH_CHECK("poly_ratio_kernel");
+  }
+  return SDET_OK;
+}
+
 extern "C" int sdet_poly_mask_target(const float* rois_out, const float* gt_polys, const int* gt_index,
                                      const int* fg_count, float* mask_target, int B, int image_rois, int G,
                                      int poly_len, int num_mask_rows, int mask_size, void* stream) {
@@ -587,12 +892,18 @@ extern "C" int sdet_poly_mask_target(const float* rois_out, const float* gt_poly
   SDET_REQUIRE(B > 0 && image_rois > 0 && G > 0 && poly_len > 2 && num_mask_rows > 0 && mask_size > 0, "bad shape");
   SDET_REQUIRE(num_mask_rows <= image_rois, "mask rows exceed image_rois");
   if (mask_size > 112) return sdet::fail(SDET_ERR_UNSUPPORTED, "mask_size > 112");
-  MaskParams p{rois_out, gt_polys, gt_index, fg_count, mask_target, image_rois, G, poly_len, num_mask_rows, mask_size};
-  const size_t smem = sizeof(int) * (size_t)(2 * mask_size * mask_size + 2);
-  if (smem > 48 * 1024)  // per device and cheap: set on every launch, no process-wide cache
-    SDET_CUDA(cudaFuncSetAttribute(poly_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)num_mask_rows, (unsigned)B);
-  poly_mask_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
-  SDET_LAUNCH_CHECK("poly_mask_kernel");
-  return SDET_OK;
+  return run_poly_mask(rois_out, gt_polys, gt_index, fg_count, mask_target, nullptr, B, image_rois, G, poly_len,
+                       num_mask_rows, mask_size, stream);
+}
+
+extern "C" int sdet_poly_mask_target_ratio(const float* rois_out, const float* gt_polys, const int* gt_index,
+                                           const int* fg_count, float* mask_target, float* mask_ratio, int B,
+                                           int image_rois, int G, int poly_len, int num_mask_rows, int mask_size,
+                                           void* stream) {
+  SDET_REQUIRE(rois_out && gt_polys && gt_index && fg_count && mask_target && mask_ratio, "NULL argument");
+  SDET_REQUIRE(B > 0 && image_rois > 0 && G > 0 && poly_len > 2 && num_mask_rows > 0 && mask_size > 0, "bad shape");
+  SDET_REQUIRE(num_mask_rows <= image_rois, "mask rows exceed image_rois");
+  if (mask_size > 112) return sdet::fail(SDET_ERR_UNSUPPORTED, "mask_size > 112");
+  return run_poly_mask(rois_out, gt_polys, gt_index, fg_count, mask_target, mask_ratio, B, image_rois, G, poly_len,
+                       num_mask_rows, mask_size, stream);
 }

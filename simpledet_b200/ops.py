@@ -954,9 +954,9 @@ def ProposalMaskTarget(rois, gt_boxes, gt_polys, num_classes, batch_images, imag
     """mx.sym.ProposalMaskTarget (models/maskrcnn/builder.py:184-203): ProposalTarget's outputs +
     mask_target (B, int(image_rois*fg_fraction), M, M) with -1 = ignore.  filter_scales=True takes the
     4th input valid_ranges (B,2) (models/tridentnet/builder.py:377-398): gt boxes outside the range are
-    not appended to the candidates (proposal_mask_target-inl.h:222-229)."""
-    if output_ratio:
-        raise NotImplementedError("output_ratio (Mask Scoring R-CNN's mask/box area ratio) is not built")
+    not appended to the candidates (proposal_mask_target-inl.h:222-229).  output_ratio=True (Mask Scoring R-CNN,
+    models/msrcnn/builder.py:219-239) appends mask_ratio (B, int(image_rois*fg_fraction)): the share of the
+    instance's polygon area that lies inside the roi (convertPoly2MaskWithRatio, proposal_mask_target.cc:20-152)."""
     if filter_scales and valid_ranges is None:
         raise ValueError("filter_scales=True needs valid_ranges (B,2)")
     del num_args
@@ -980,6 +980,11 @@ def ProposalMaskTarget(rois, gt_boxes, gt_polys, num_classes, batch_images, imag
     NM = int(IR * fg_fraction)
     M = int(mask_size)
     mask = torch.empty((B, NM, M, M), device=dev, dtype=torch.float32)
+    if output_ratio:
+        ratio = torch.empty((B, NM), device=dev, dtype=torch.float32)
+        check(_lib.lib().sdet_poly_mask_target_ratio(_p(outs[0]), _p(gt_polys), _p(gt_index), _p(fg_count), _p(mask),
+                                                     _p(ratio), B, IR, G, PL, NM, M, _stream()))
+        return tuple(outs) + (mask, ratio)
     check(_lib.lib().sdet_poly_mask_target(_p(outs[0]), _p(gt_polys), _p(gt_index), _p(fg_count), _p(mask), B, IR, G,
                                            PL, NM, M, _stream()))
     return tuple(outs) + (mask,)

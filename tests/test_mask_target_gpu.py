@@ -96,3 +96,60 @@ def test_polygon_with_more_edges_than_one_batch(cuda):
         want = oracle.poly2mask(kept, polys[0, 0], M)
         got = res[4].cpu().numpy()[0, 0]
         assert np.array_equal(got, want) and 0.2 < want.mean() < 0.9
+
+
+@pytest.mark.parametrize("M", [14, 28])
+def test_mask_target_output_ratio(cuda, M):
+    """Mask Scoring R-CNN form (output_iou + output_ratio, models/msrcnn/builder.py:219-239): seven outputs; the mask
+    follows the ratio variant's double vertex transform and mask_ratio is the count ratio on the reference's integer
+    rasters - computed on the device from sorted toggle positions, no raster is ever materialised.  The oracle's
+    restatement is pinned against the reference operator (tests/test_oracle_ref_cxx.py)."""
+    rng = np.random.default_rng(100 + M)
+    B, R, G, PL, IR = 2, 400, 12, 2500, 128
+    rois, gt, polys = _scene(rng, B, R, G, PL)
+    if M == 28:
+        rois = (np.round(rois * 4) / 4).astype(np.float32)    # quarter-pixel corners, some negative: int() truncates
+    pr = rng.integers(0, 2 ** 32, (B, 4, R + G), dtype=np.uint64).astype(np.uint32)
+    ref = oracle.proposal_mask_target(rois, gt, polys, pr, 81, IR, M, fg_fraction=0.25, fg_thresh=0.5,
+                                      bg_thresh_hi=0.5, bg_thresh_lo=0.0, output_ratio=True)
+    res = ops.ProposalMaskTarget(_t(rois, cuda), _t(gt, cuda), _t(polys, cuda), 81, B, IR, M, 0.5, 0.5, 0.0, False,
+                                 output_iou=True, output_ratio=True, priorities=_t(pr.astype(np.int64), cuda))
+    assert len(res) == 7 and res[5].shape == (B, 32, M, M) and res[6].shape == (B, 32)
+    for i in (0, 1, 3, 4):
+        assert np.array_equal(res[i].cpu().numpy(), ref[i]), i
+    np.testing.assert_allclose(res[2].cpu().numpy(), ref[2], rtol=1e-5, atol=1e-6)   # log() targets: 1 ulp (as elsewhere)
+    assert np.array_equal(res[5].cpu().numpy(), ref[5])
+    got, want = res[6].cpu().numpy(), ref[6]
+    assert np.array_equal(got, want), (got - want)[got != want]
+    assert ((want > 0.05) & (want < 0.999)).sum() > 10          # real partial overlaps, not a trivial vector
+
+
+def test_mask_ratio_overlapping_segments_and_empty_rows(cuda):
+    """Two overlapping segments (the union is counted once), a polygon that sticks far out of the roi (small ratio),
+    and rows past the foreground count (ratio 0, mask -1)."""
+    sq = lambda x1, y1, x2, y2: [x1, y1, x2, y1, x2, y2, x1, y2]
+    polys = np.full((1, 3, 60), -1, np.float32)
+    row = [7, 2, 8, 8] + sq(100.3, 80.2, 220.7, 190.4) + sq(180.5, 150.1, 300.9, 260.6)
+    polys[0, 0, :len(row)] = row
+    tri = [40.2, 300.7, 900.4, 320.1, 470.3, 700.9]
+    polys[0, 1, :3 + len(tri)] = [9, 1, len(tri)] + tri
+    gt = np.full((1, 3, 5), -1, np.float32)
+    gt[0, 0] = [100.3, 80.2, 300.9, 260.6, 7]
+    gt[0, 1] = [40.2, 300.7, 900.4, 700.9, 9]
+    rois = np.zeros((1, 8, 4), np.float32)
+    rois[0, 0] = [120.5, 95.25, 290.0, 240.75]
+    rois[0, 1] = [60.0, 310.0, 700.5, 690.0]
+    rois[0, 2] = [98.0, 77.0, 303.0, 262.0]
+    pr = np.zeros((1, 3, 11), np.uint32)
+    pr[0, :, :] = np.arange(11)
+    kw = dict(fg_fraction=0.5, fg_thresh=0.5, bg_thresh_hi=0.5, bg_thresh_lo=0.0)
+    ref = oracle.proposal_mask_target(rois, gt, polys, pr, 81, 16, 28, output_ratio=True, **kw)
+    res = ops.ProposalMaskTarget(_t(rois, cuda), _t(gt, cuda), _t(polys, cuda), 81, 1, 16, 28, 0.5, 0.5, 0.0, False,
+                                 fg_fraction=0.5, output_iou=True, output_ratio=True,
+                                 priorities=_t(pr.astype(np.int64), cuda))
+    assert np.array_equal(res[0].cpu().numpy(), ref[0])
+    assert np.array_equal(res[5].cpu().numpy(), ref[5]) and np.array_equal(res[6].cpu().numpy(), ref[6])
+    r = ref[6][0]
+    nfg = int((ref[1][0] > 0).sum())
+    assert nfg == 5 and r.shape == (8,) and (r[:nfg] > 0.3).all() and (r[:nfg] <= 1).all() and not r[nfg:].any()
+    assert (ref[5][0, nfg:] == -1).all()

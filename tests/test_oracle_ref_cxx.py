@@ -175,7 +175,8 @@ def _pt_inputs(rng, B, R, G, n_gt, n_fg_like):
     return rois, gt
 
 
-def oracle_under_constant_rand(rois, gt, kw, rand_const, v2=False, valid_ranges=None):
+def oracle_under_constant_rand(rois, gt, kw, rand_const, v2=False, valid_ranges=None, polys=None, mask_size=None,
+                               output_ratio=False):
     """The oracle's ProposalTarget with the priorities that reproduce what libstdc++'s std::random_shuffle does
     when every rand() returns `rand_const` (0: rotate right by one; 27719: identity for lists <= 12)."""
     B, R, _ = rois.shape
@@ -219,6 +220,9 @@ def oracle_under_constant_rand(rois, gt, kw, rand_const, v2=False, valid_ranges=
             pr[b, 2 + r] = T
             for pos, i in enumerate(sh(neg, r + 1)):
                 pr[b, 2 + r, i] = pos
+    if polys is not None:
+        return oracle.proposal_mask_target(rois, gt, polys, pr, image_rois=IR, mask_size=mask_size,
+                                           output_ratio=output_ratio, **okw)
     return oracle.proposal_target(rois, gt, pr, image_rois=IR, **okw)
 
 
@@ -491,3 +495,54 @@ def test_gen_proposal_retina_gpu_operator(K, thresh, pre, one_hot):
     rb, rs = oracle.gen_proposal_retina(cls, reg, info, anchors, **kw)
     assert np.array_equal(box, rb) and np.array_equal(score, rs)
     assert (rs != 0).any()
+
+
+# -------------------------------------------------------------------------------------------------- ProposalMaskTarget
+# proposal_mask_target.cc compiled against a stand-in maskApi.h (oracle/shim/coco_api/common/maskApi.h: cocoapi is not
+# in the reference tree).  Pins the operator - matching, sampling, the polygon transform into roi coordinates
+# (y first, :184-186), the union over segments - not the rasteriser, which is restated on both sides.
+MASK_KW = dict(num_classes=81, image_rois=64, fg_thresh=0.5, bg_thresh_hi=0.5, bg_thresh_lo=0.0, proposal_without_gt=False)
+
+
+@pytest.mark.parametrize("M", [14, 28])
+@pytest.mark.parametrize("filter_scales,few_fg", [(False, False), (True, False), (False, True)])
+def test_proposal_mask_target_operator(M, filter_scales, few_fg):
+    rng = np.random.default_rng(60 + M)
+    B, R, G, PL = 2, 200, 8, 400
+    rois, gt, polys = synth.mask_scene(rng, B, R, G, PL)
+    if few_fg:                                                # fewer foreground rois than mask rows: -1 rows stay (-inl.h:242)
+        rois[:, 5:R - 20] = synth.random_rois(rng, B, R - 25, min_side=8, max_side=30)
+    vr = np.array([[0, 150], [120, 1e5]], np.float32)
+    kw = dict(MASK_KW, filter_scales=filter_scales)
+    ref_cxx.set_rand_const(0)
+    ins = [rois, gt, polys] + ([vr] if filter_scales else [])
+    outs = ref_cxx.forward("ProposalMaskTarget", dict(kw, num_args=len(ins), batch_images=B, mask_size=M), ins)
+    assert len(outs) >= 6 and outs[5].shape == (B, 16, M, M)
+    o = oracle_under_constant_rand(rois, gt, kw, 0, v2=True, valid_ranges=vr if filter_scales else None, polys=polys,
+                                   mask_size=M)
+    for i, name in enumerate(("rois", "label", "bbox_target", "bbox_weight", "match_gt_iou", "mask_target")):
+        assert np.array_equal(outs[i], o[i]), name
+    assert (o[5] == 1).sum() > 50 and (o[5] == 0).any() and (o[5] == -1).any() == few_fg
+
+
+@pytest.mark.parametrize("M,few_fg", [(14, False), (28, True)])
+def test_proposal_mask_target_output_ratio(M, few_fg):
+    """Mask Scoring R-CNN form (models/msrcnn/builder.py:219-239): output_iou + output_ratio, 7 outputs.  The ratio
+    is counted on integer rasters the size of the roi and of the polygon's extent (proposal_mask_target.cc:20-152),
+    and the mask's vertex transform runs in double there - the masks differ from the plain operator's in a few
+    pixels, which the last assertion shows."""
+    rng = np.random.default_rng(70 + M)
+    B, R, G, PL = 2, 200, 8, 400
+    rois, gt, polys = synth.mask_scene(rng, B, R, G, PL)
+    rois = np.round(rois * 4) / 4 if few_fg else rois         # quarter-pixel corners: int truncation differs from floor
+    if few_fg:
+        rois[:, 5:R - 20] = synth.random_rois(rng, B, R - 25, min_side=8, max_side=30)
+    ref_cxx.set_rand_const(0)
+    outs = ref_cxx.forward("ProposalMaskTarget", dict(MASK_KW, num_args=3, batch_images=B, mask_size=M, output_iou=True,
+                                                      output_ratio=True), [rois, gt, polys])
+    assert len(outs) == 7 and outs[6].shape == (B, 16)
+    o = oracle_under_constant_rand(rois, gt, MASK_KW, 0, polys=polys, mask_size=M, output_ratio=True)
+    for i, name in enumerate(("rois", "label", "bbox_target", "bbox_weight", "match_gt_iou", "mask_target", "mask_ratio")):
+        assert np.array_equal(outs[i], o[i]), name
+    r = o[6]
+    assert ((r > 0) & (r <= 1)).sum() >= 5 and (r == 0).any() == few_fg and np.unique(r).size > 4
