@@ -26,13 +26,13 @@ OUT = os.path.join(HERE, "_ref", "libref_cxx.so")
 SOURCES = [
     ("contrib/roi_align_v2.cc", False),   # functor roi_align_v2-inl.h:61-153, CPU gather backward, registration
     ("contrib/roi_align_v2.cu", False),   # ROIAlignBackwardKernelGPU_v2 (:17-85) + driver (:88-143)
-    ("roi_pooling_v1.cc", False),         # ROIPoolForward_v1 / ROIPoolBackwardAcc_v1 (:40-221) + op
+    ("roi_pooling_v1.cc", False, ["-DSHIM_GPU_DISPATCH"]),  # ROIPoolForward_v1 / ROIPoolBackwardAcc_v1 (:40-221) + op
     ("contrib/decodebbox.cc", False),     # BBoxTransformXYWH/XYXY (:34-133) + DecodeBBoxOp::Forward
     ("proposal_target.cc", True),         # SampleROI, BBoxOverlap, targets (:22-227) + ProposalTargetOp::Forward
     ("proposal_target_v2.cc", True),
     # ProposalMaskTarget: the operator against a stand-in maskApi.h (oracle/shim/coco_api: cocoapi is not in the tree)
     ("proposal_mask_target.cc", True),
-    ("contrib/generate_anchor.cc", False),  # GenAnchorOp<cpu>::Forward + gen_anchor_utils (generate_anchor-inl.h:139-183)
+    ("contrib/generate_anchor.cc", False, ["-DSHIM_GPU_DISPATCH"]),  # GenAnchorOp<cpu>::Forward + gen_anchor_utils (generate_anchor-inl.h:139-183)
     ("contrib/focal_loss.cc", False),     # FocalLossOp::Forward / Backward as mshadow expressions (focal_loss-inl.h:100-231)
     ("contrib/bbox_norm.cc", False),      # BBoxNormOp::Backward (bbox_norm-inl.h:99-129)
     # GPU-only operators.  Plain C++ cannot parse `kernel<<<grid, block, ...>>>(args)`, so the .cu files below pass
@@ -57,6 +57,9 @@ SOURCES = [
     ("contrib/generate_proposal.cu", False, [], "rewrite_launches"),
     ("contrib/generate_proposal_retina.cc", False, ["-DSHIM_GPU_DISPATCH"]),
     ("contrib/generate_proposal_retina.cu", False, [], "rewrite_launches"),
+    # GPU twins of operators whose .cc is already pinned: the kernels the reference actually runs
+    ("roi_pooling_v1.cu", False, [], "rewrite_launches"),
+    ("contrib/generate_anchor.cu", False, [], "rewrite_launches"),
 ]
 # -O2 without -march: like MXNet's x86-64 CPU build there is no FMA instruction to contract into;
 # -ffp-contract=off makes that explicit.
@@ -89,7 +92,7 @@ def main() -> int:
             if len(entry) > 3 and entry[3] == "rewrite_launches":
                 import re
 
-                text = re.sub(r"\b([A-Za-z_]\w*)\s*<<<(.*?)>>>\s*\(",
+                text = re.sub(r"\b([A-Za-z_]\w*(?:<[\w:, ]+>)?)\s*<<<(.*?)>>>\s*\(",
                               lambda m: "shim_launch(%s).run([&](auto... a) { %s(a...); }, " % (m.group(2), m.group(1)),
                               open(path).read(), flags=re.S)
                 path = os.path.join(tmp, os.path.basename(src) + ".cc")

@@ -192,6 +192,7 @@ typedef CUstream_st* cudaStream_t;  // only the handle type: the shim never touc
 namespace mshadow {
 namespace cuda {
 const int kMaxThreadsPerBlock = 1024;
+const int kMaxGridDim = 65535;
 const int kBaseThreadNum = 256;
 inline void CheckLaunchParam(dim3, dim3, const char* = "") {}
 }  // namespace cuda

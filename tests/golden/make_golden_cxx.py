@@ -127,6 +127,16 @@ def main():
                                 [cls, reg, info, anchors], dev="gpu")
         # one-hot score rows are sparse; the npz is compressed
         g[f"gr_{K}_{pre}_box"], g[f"gr_{K}_{pre}_score"] = o, s_
+    # ProposalMaskTarget with output_iou + output_ratio (rand() == 0), against the stand-in maskApi.h
+    for M, few_fg in T.MASK_RATIO_CASES:
+        rois, gtb, polys = T.mask_ratio_case(M, few_fg)
+        ref_cxx.set_rand_const(0)
+        outs = ref_cxx.forward("ProposalMaskTarget", dict(T.MASK_KW, num_args=3, batch_images=rois.shape[0], mask_size=M,
+                                                          output_iou=True, output_ratio=True), [rois, gtb, polys])
+        for i in (0, 1, 4):
+            g[f"pm_{M}_out{i}"] = outs[i]
+        g[f"pm_{M}_mask"] = outs[5].astype(np.int8)
+        g[f"pm_{M}_ratio"] = outs[6]
     path = os.path.join(HERE, "reference_cxx_ops.npz")
     np.savez_compressed(path, **g)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 import oracle
-from test_oracle_ref_cxx import (BASE, FOCAL_MODES, NMS_CASES, PROPOSAL_V3_CASES, RETINA_CASES, focal_case, nms_case,
+from test_oracle_ref_cxx import (BASE, FOCAL_MODES, MASK_KW, MASK_RATIO_CASES, NMS_CASES, mask_ratio_case, PROPOSAL_V3_CASES, RETINA_CASES, focal_case, nms_case,
                                  oracle_under_constant_rand, retina_case, rpn_case, sigmoid_ce_case)
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_cxx_ops.npz"))
@@ -109,3 +109,12 @@ def test_contrib_nms_and_gen_proposal_retina():
                                             thresh=thresh, anchor_mean=(0.0, 0.1, 0.0, -0.1), anchor_std=(0.1, 0.1, 0.2, 0.2),
                                             output_one_hot=one_hot)
         assert np.array_equal(rb, G[f"gr_{K}_{pre}_box"]) and np.array_equal(rs, G[f"gr_{K}_{pre}_score"]), K
+
+
+def test_proposal_mask_target_with_ratio():
+    for M, few_fg in MASK_RATIO_CASES:
+        rois, gt, polys = mask_ratio_case(M, few_fg)
+        o = oracle_under_constant_rand(rois, gt, MASK_KW, 0, polys=polys, mask_size=M, output_ratio=True)
+        for i in (0, 1, 4):
+            assert np.array_equal(o[i], G[f"pm_{M}_out{i}"]), (M, i)
+        assert np.array_equal(o[5], G[f"pm_{M}_mask"].astype(np.float32)) and np.array_equal(o[6], G[f"pm_{M}_ratio"])

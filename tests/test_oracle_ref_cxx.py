@@ -93,7 +93,8 @@ def test_roi_align_param_checks():
 
 
 # ------------------------------------------------------------------------------------------------ ROIPooling_v1
-def test_roi_pooling_v1():
+@pytest.mark.parametrize("dev", ["cpu", "gpu"])   # gpu: roi_pooling_v1.cu's kernels run serially on the host
+def test_roi_pooling_v1(dev):
     rng = np.random.default_rng(4)
     data = rng.standard_normal((2, 5, 30, 40)).astype(np.float32)
     r = synth.random_rois(rng, 1, 50, 480, 640)[0]
@@ -102,15 +103,19 @@ def test_roi_pooling_v1():
     rois[1, 1:] = [700, 500, 800, 600]  # outside: empty bins
     for pooled, scale in (((7, 7), 1 / 16), ((2, 3), 1 / 16), ((6, 6), 0.7 / 16)):
         kw = dict(pooled_size=pooled, spatial_scale=scale)
-        out, idx = ref_cxx.forward("ROIPooling_v1", kw, [data, rois])
+        out, idx = ref_cxx.forward("ROIPooling_v1", kw, [data, rois], dev=dev)
         ro, ri = oracle.roi_pool_v1_forward(data, rois, pooled, scale)
         assert np.array_equal(out, ro) and np.array_equal(idx, ri)
+        # Backward (ROIPoolBackwardAcc_v1: the .cc gathers per input pixel, the .cu likewise - no atomics)
+        og = rng.standard_normal(out.shape).astype(np.float32)
+        gd, _ = ref_cxx.backward("ROIPooling_v1", kw, [og], [data, rois], [out, idx], dev=dev)
+        assert np.array_equal(gd, oracle.roi_pool_v1_backward(og, idx, rois, data.shape))
     # the docstring vector of the reference (roi_pooling_v1.cc:265-285)
     x = np.arange(48, dtype=np.float32).reshape(1, 1, 8, 6)
     y = np.array([[0, 0, 0, 4, 4]], np.float32)
-    out, _ = ref_cxx.forward("ROIPooling_v1", dict(pooled_size=(2, 2), spatial_scale=1.0), [x, y])
+    out, _ = ref_cxx.forward("ROIPooling_v1", dict(pooled_size=(2, 2), spatial_scale=1.0), [x, y], dev=dev)
     assert out.ravel().tolist() == [14, 16, 26, 28]
-    out, _ = ref_cxx.forward("ROIPooling_v1", dict(pooled_size=(2, 2), spatial_scale=0.7), [x, y])
+    out, _ = ref_cxx.forward("ROIPooling_v1", dict(pooled_size=(2, 2), spatial_scale=0.7), [x, y], dev=dev)
     assert out.ravel().tolist() == [7, 9, 19, 21]
 
 
@@ -146,9 +151,11 @@ def test_decode_bbox_defaults():
                                                      (32, (2.0, 4.0), (0.33, 1.7), (7, 9))])
 def test_gen_anchor(stride, scales, ratios, hw):
     cls_prob = np.zeros((1, 2 * len(scales) * len(ratios), hw[0], hw[1]), np.float32)
-    (out,) = ref_cxx.forward("_contrib_GenAnchor", dict(feature_stride=stride, scales=scales, ratios=ratios), [cls_prob])
     ref = oracle.gen_anchor(hw[0], hw[1], stride, scales, ratios)
-    assert np.array_equal(out.reshape(-1, 4), ref)
+    for dev in ("cpu", "gpu"):                    # generate_anchor.cc and generate_anchor.cu's kernel
+        (out,) = ref_cxx.forward("_contrib_GenAnchor", dict(feature_stride=stride, scales=scales, ratios=ratios), [cls_prob],
+                                 dev=dev)
+        assert np.array_equal(out.reshape(-1, 4), ref), dev
 
 
 # ------------------------------------------------------------------------------------------------ ProposalTarget
@@ -525,18 +532,26 @@ def test_proposal_mask_target_operator(M, filter_scales, few_fg):
     assert (o[5] == 1).sum() > 50 and (o[5] == 0).any() and (o[5] == -1).any() == few_fg
 
 
-@pytest.mark.parametrize("M,few_fg", [(14, False), (28, True)])
-def test_proposal_mask_target_output_ratio(M, few_fg):
-    """Mask Scoring R-CNN form (models/msrcnn/builder.py:219-239): output_iou + output_ratio, 7 outputs.  The ratio
-    is counted on integer rasters the size of the roi and of the polygon's extent (proposal_mask_target.cc:20-152),
-    and the mask's vertex transform runs in double there - the masks differ from the plain operator's in a few
-    pixels, which the last assertion shows."""
+def mask_ratio_case(M, few_fg):
     rng = np.random.default_rng(70 + M)
     B, R, G, PL = 2, 200, 8, 400
     rois, gt, polys = synth.mask_scene(rng, B, R, G, PL)
-    rois = np.round(rois * 4) / 4 if few_fg else rois         # quarter-pixel corners: int truncation differs from floor
+    rois = (np.round(rois * 4) / 4).astype(np.float32) if few_fg else rois   # quarter-pixel corners: int() truncates
     if few_fg:
         rois[:, 5:R - 20] = synth.random_rois(rng, B, R - 25, min_side=8, max_side=30)
+    return rois, gt, polys
+
+
+MASK_RATIO_CASES = [(14, False), (28, True)]
+
+
+@pytest.mark.parametrize("M,few_fg", MASK_RATIO_CASES)
+def test_proposal_mask_target_output_ratio(M, few_fg):
+    """Mask Scoring R-CNN form (models/msrcnn/builder.py:219-239): output_iou + output_ratio, 7 outputs.  The ratio
+    is counted on integer rasters the size of the roi and of the polygon's extent (proposal_mask_target.cc:20-152),
+    and the mask's vertex transform runs in double there (float in the plain operator)."""
+    rois, gt, polys = mask_ratio_case(M, few_fg)
+    B = rois.shape[0]
     ref_cxx.set_rand_const(0)
     outs = ref_cxx.forward("ProposalMaskTarget", dict(MASK_KW, num_args=3, batch_images=B, mask_size=M, output_iou=True,
                                                       output_ratio=True), [rois, gt, polys])
