@@ -80,6 +80,10 @@ def install(reference_root: str | None = None):
     symm.Group = S.Group
     symm.Symbol = S.Symbol
     symm.contrib = S._OpNamespace("_contrib_")
+    # builders probe the operator list (models/retinanet/builder.py:357 picks GenProposalRetina over the CustomOp)
+    symm.contrib.__all__ = ["ROIAlign_v2", "DecodeBBox", "Proposal", "Proposal_v2", "Proposal_v3", "NMS", "GenAnchor",
+                            "GenProposal", "GenProposalRetina", "FocalLoss", "BBoxNorm", "SigmoidCrossEntropy",
+                            "DeformableConvolution", "ModulatedDeformableConvolution"]
     symm.load = lambda fname: (_ for _ in ()).throw(NotImplementedError("symbol.load"))
     sys.modules["mxnet.symbol"] = sys.modules["mxnet.sym"] = symm
 
@@ -135,11 +139,30 @@ def install(reference_root: str | None = None):
     bb = _mod("mxnext.backbone")
     bb.__path__ = []
     _mod("mxnext.backbone.resnet_v1", Builder=X.ResNetV1Builder)
+    _mod("mxnext.backbone.resnet_v1b", Builder=X.ResNetV1bBuilder)
+    h = X.resnet_v1b_helper
+    _mod("mxnext.backbone.resnet_v1b_helper", depth_config=h.depth_config, resnet_unit=h.resnet_unit,
+         resnet_stage=h.resnet_stage, resnet_c1=h.resnet_c1, resnet_c2=h.resnet_c2, resnet_c3=h.resnet_c3,
+         resnet_c4=h.resnet_c4, resnet_c5=h.resnet_c5)
     tvm = _mod("mxnext.tvm")
     tvm.__path__ = []
     _mod("mxnext.tvm.proposal", proposal=X.tvm_proposal)
     _mod("mxnext.tvm.get_top_proposal", get_top_proposal=X.tvm_get_top_proposal)
     _mod("mxnext.tvm.fpn_roi_assign", fpn_roi_assign=X.tvm_fpn_roi_assign)
+
+    # ---- pycocotools: the mask detectors import it at module top (models/maskrcnn/process_output.py:2) for the
+    # test-time RLE encoding.  Not in this image: an import-time stand-in whose functions say so when called.
+    import importlib.util as _ilu
+
+    if _ilu.find_spec("pycocotools") is None:
+        def _absent(*a, **k):
+            raise ImportError("pycocotools is not installed: RLE encoding / COCO evaluation are outside this package")
+
+        pct = _mod("pycocotools")
+        pct.__path__ = []
+        pct.mask = _mod("pycocotools.mask", encode=_absent, decode=_absent, frPyObjects=_absent, merge=_absent, area=_absent)
+        pct.coco = _mod("pycocotools.coco", COCO=_absent)
+        pct.cocoeval = _mod("pycocotools.cocoeval", COCOeval=_absent)
 
     # ---- the reference's compiled helpers (operator_py/cython/*.pyx): numpy-facing drop-ins over the device ops
     def _bbox_overlaps_cython(boxes, query_boxes):

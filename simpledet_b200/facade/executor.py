@@ -81,6 +81,42 @@ def _shape_conv(a, ins, names):
     return ins, [(x[0], nf, _conv_out(x[2], k[0], s[0], p[0], d[0]), _conv_out(x[3], k[1], s[1], p[1], d[1]))]
 
 
+def _shape_deconv(a, ins, names):
+    x = ins[0]
+    k, s, p = _tup(a["kernel"]), _tup(a.get("stride", 1)), _tup(a.get("pad", 0))
+    adj = _tup(a.get("adj", 0))
+    nf, g = int(_t(a["num_filter"])), int(_t(a.get("num_group", 1)))
+    ins = list(ins)
+    for i, n in enumerate(names):
+        if n == "weight":
+            ins[i] = (x[1], nf // g, k[0], k[1])     # MXNet Deconvolution: (in_channels, num_filter / group, kh, kw)
+        elif n == "bias":
+            ins[i] = (nf,)
+    o = lambda n, j: (n - 1) * s[j] - 2 * p[j] + k[j] + adj[j]
+    return ins, [(x[0], nf, o(x[2], 0), o(x[3], 1))]
+
+
+def _shape_deform_conv(a, ins, names):
+    ins2, outs = _shape_conv(a, ins, names)          # data, offset, weight[, bias]: the output is a convolution's
+    k, dg = _tup(a["kernel"]), int(_t(a.get("num_deformable_group", 1)))
+    o = outs[0]
+    ins2[1] = (o[0], 2 * dg * k[0] * k[1], o[2], o[3])
+    return ins2, outs
+
+
+def _shape_gen_anchor(a, ins, names):
+    c = ins[0]                                       # cls_prob (B, A*K, H, W): generate_anchor-inl.h InferShape
+    A = len(_t(a["scales"])) * len(_t(a["ratios"]))
+    return ins, [(c[2] * c[3] * A, 4)]
+
+
+def _shape_gen_proposal_retina(a, ins, names):
+    c = ins[0]
+    A, pre = int(_t(a["num_anchors"])), int(_t(a.get("rpn_pre_nms_top_n", 6000)))
+    oc = c[1] // A + 1 if _b(a.get("output_one_hot", True)) else 1
+    return ins, [(c[0], pre, 4), (c[0], pre, oc)]
+
+
 def _shape_fc(a, ins, names):
     x = ins[0]
     nh = int(_t(a["num_hidden"]))
@@ -174,6 +210,9 @@ def _shape_custom(a, ins, names):
     if t == "BboxPostProcessing":
         B, m = ins[0][0], int(_t(a["max_det_per_image"]))
         return ins, [(B, m, 1), (B, m, 4), (B, m, 1)]
+    if t == "decode_retina":
+        n_in = len(ins)
+        raise NotImplementedError("decode_retina through the symbol graph (the builder prefers GenProposalRetina)")
     raise NotImplementedError(f"Custom op_type {t!r}")
 
 
@@ -189,6 +228,10 @@ SHAPE_RULES = {
     "Flatten": lambda a, ins, n: (ins, [(ins[0][0], math.prod(ins[0][1:]))]),
     "_contrib_Proposal_v3": _shape_proposal, "_contrib_Proposal": _shape_proposal,
     "_contrib_ROIAlign_v2": _shape_roialign, "_contrib_DecodeBBox": _shape_decode, "Custom": _shape_custom,
+    "Deconvolution": _shape_deconv, "_contrib_DeformableConvolution": _shape_deform_conv,
+    "_contrib_GenAnchor": _shape_gen_anchor, "_contrib_GenProposalRetina": _shape_gen_proposal_retina,
+    "_full": lambda a, ins, n: (ins, [tuple(_t(a["shape"]))]), "full": lambda a, ins, n: (ins, [tuple(_t(a["shape"]))]),
+    "transpose": lambda a, ins, n: (ins, [tuple(ins[0][i] for i in _t(a["axes"]))]),
 }
 
 
@@ -525,7 +568,45 @@ class Executor:
             return [torch.softmax(x[0], 1 if str(a.get("mode", "instance")) == "channel" else -1)]
         if op == "SoftmaxOutput":
             return [torch.softmax(x[0], 1 if _b(a.get("multi_output", False)) else -1)]
+        if op == "Deconvolution":
+            data = arg.get("data", x[0])
+            return [F.conv_transpose2d(data, arg["weight"], arg.get("bias"), _tup(a.get("stride", 1)), _tup(a.get("pad", 0)),
+                                       _tup(a.get("adj", 0)), int(_t(a.get("num_group", 1))))]
+        if op in ("full", "_full"):
+            return [torch.full(tuple(_t(a["shape"])), float(_t(a["value"])), device=self.device, dtype=torch.float32)]
+        if op == "transpose":
+            return [x[0].permute(*_t(a["axes"]))]
         # ---- detection operators: by registration string, through the C ABI
+        if op == "_contrib_DeformableConvolution":
+            data, offset = arg.get("data", x[0]), arg.get("offset", x[1])
+            return [ops.OPS[op](data, offset.contiguous(), arg["weight"], arg.get("bias"), kernel=_tup(a["kernel"]),
+                                stride=_tup(a.get("stride", 1)), dilate=_tup(a.get("dilate", 1)), pad=_tup(a.get("pad", 0)),
+                                num_filter=int(_t(a["num_filter"])), num_group=int(_t(a.get("num_group", 1))),
+                                num_deformable_group=int(_t(a.get("num_deformable_group", 1))),
+                                no_bias=_b(a.get("no_bias", False)))]
+        if op == "_contrib_GenAnchor":
+            return [ops.OPS[op](x[0], feature_stride=int(_t(a["feature_stride"])),
+                                scales=tuple(float(v) for v in _t(a["scales"])),
+                                ratios=tuple(float(v) for v in _t(a["ratios"])))]
+        if op == "_contrib_GenProposalRetina":
+            return list(ops.OPS[op](arg["cls_prob"].contiguous(), arg["bbox_pred"].contiguous(), arg["im_info"].contiguous(),
+                                    arg["anchors"].contiguous(), feature_stride=int(_t(a.get("feature_stride", 16))),
+                                    rpn_pre_nms_top_n=int(_t(a.get("rpn_pre_nms_top_n", 6000))),
+                                    rpn_min_size=int(_t(a.get("rpn_min_size", 16))), num_anchors=int(_t(a["num_anchors"])),
+                                    thresh=float(_t(a.get("thresh", 0.0))),
+                                    anchor_mean=tuple(float(v) for v in _t(a["anchor_mean"])),
+                                    anchor_std=tuple(float(v) for v in _t(a["anchor_std"])),
+                                    output_one_hot=_b(a.get("output_one_hot", True))))
+        if op == "_contrib_Proposal":
+            r = ops.OPS[op](arg["cls_prob"].contiguous(), arg["bbox_pred"].contiguous(), arg["im_info"].contiguous(),
+                            rpn_pre_nms_top_n=int(_t(a.get("rpn_pre_nms_top_n", 6000))),
+                            rpn_post_nms_top_n=int(_t(a.get("rpn_post_nms_top_n", 300))),
+                            threshold=float(_t(a.get("threshold", 0.7))), rpn_min_size=int(_t(a.get("rpn_min_size", 16))),
+                            scales=tuple(float(s) for s in _t(a.get("scales", (4, 8, 16, 32)))),
+                            ratios=tuple(float(s) for s in _t(a.get("ratios", (0.5, 1, 2)))),
+                            feature_stride=int(_t(a.get("feature_stride", 16))), output_score=True,
+                            iou_loss=_b(a.get("iou_loss", False)))
+            return list(r)
         if op == "_contrib_Proposal_v3":
             r = ops.OPS[op](arg["cls_prob"].contiguous(), arg["bbox_pred"].contiguous(), arg["im_info"].contiguous(),
                             rpn_pre_nms_top_n=int(_t(a.get("rpn_pre_nms_top_n", 6000))),

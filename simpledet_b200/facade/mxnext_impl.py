@@ -35,6 +35,10 @@ def one_init():
     return _Init("ones")
 
 
+def constant(value):
+    return _Init("constant", value=value)
+
+
 def var(name, init=None, lr_mult=None, wd_mult=None, shape=None, dtype=None, **kw):
     return S.Variable(name, shape=shape, lr_mult=lr_mult, wd_mult=wd_mult, dtype=dtype, init=init, **kw)
 
@@ -119,6 +123,10 @@ def reshape(data, shape, name=None):
     return sym.Reshape(data=data, shape=tuple(shape), name=name)
 
 
+def transpose(data, axes, name=None):
+    return sym.transpose(data=data, axes=tuple(axes), name=name)
+
+
 def flatten(data, name=None):
     return sym.Flatten(data=data, name=name)
 
@@ -157,6 +165,9 @@ def smooth_l1(data, scalar=1.0, name=None):
 
 def loss(data, grad_scale=1.0, name=None):
     return sym.MakeLoss(data=data, grad_scale=grad_scale, name=name)
+
+
+make_loss = loss
 
 
 def stop_grad(data, name=None):
@@ -235,6 +246,11 @@ class ResNetV1Builder:
             x = cls.unit(x, f"{name}_unit{i}", filter, 1, dilate, False, norm)
         return x
 
+    @classmethod
+    def resnet_stage(cls, data, name, num_block, filter, stride, dilate, norm_type, norm_mom=0.9, ndev=None, **kw):
+        """The C5 head of the C4 detectors (symbol/builder.py:624-634): one stage on top of the roi features."""
+        return cls.stage(data, name, num_block, filter, stride, dilate, norm_type)
+
     def get_backbone(self, variant, depth, endpoint, normalizer, fp16):
         units = self.depth_config[depth]
         data = var("data")
@@ -257,6 +273,76 @@ class ResNetV1Builder:
     # the reference also calls these through thin wrappers
     def get_stage_endpoints(self, *a, **kw):
         return self.get_backbone(*a, **kw)
+
+
+# ---- mxnext.backbone.resnet_v1b / resnet_v1b_helper ----------------------------------------------------------------------
+class resnet_v1b_helper:
+    """ResNet-v1b (stride on the 3x3 convolution).  Interface from the call sites in models/dcn/builder.py:56-110 and
+    symbol/builder.py:745-775; unit structure and parameter names are those of `dcn_resnet_unit`
+    (models/dcn/builder.py:8-36), which is this unit with conv2 swapped for a deformable convolution."""
+    depth_config = {18: (2, 2, 2, 2), 34: (3, 4, 6, 3), 50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 152: (3, 8, 36, 3),
+                    200: (3, 24, 36, 3)}
+
+    @staticmethod
+    def resnet_unit(input, name, filter, stride, dilate, proj, norm, **kw):
+        c1 = relu(norm(conv(input, name=name + "_conv1", filter=filter // 4), name=name + "_bn1"), name=name + "_relu1")
+        c2 = relu(norm(conv(c1, name=name + "_conv2", filter=filter // 4, kernel=3, stride=stride, dilate=dilate),
+                       name=name + "_bn2"), name=name + "_relu2")
+        c3 = norm(conv(c2, name=name + "_conv3", filter=filter), name=name + "_bn3")
+        sc = norm(conv(input, name=name + "_sc", filter=filter, stride=stride), name=name + "_sc_bn") if proj else input
+        return relu(add(c3, sc, name=name + "_plus"), name=name + "_relu")
+
+    @classmethod
+    def resnet_stage(cls, data, name, num_block, filter, stride, dilate, norm, **kw):
+        for i in range(1, num_block + 1):
+            data = cls.resnet_unit(data, f"{name}_unit{i}", filter, stride if i == 1 else 1, dilate, i == 1, norm)
+        return data
+
+    @staticmethod
+    def resnet_c1(data, norm):
+        c = relu(norm(conv(data, name="conv0", filter=64, kernel=7, stride=2), name="bn0"), name="relu0")
+        return pool(c, name="pool0", kernel=3, stride=2, pad=1, pool_type="max")
+
+    @classmethod
+    def resnet_c2(cls, data, num_block, stride, dilate, norm):
+        return cls.resnet_stage(data, "stage1", num_block, 256, stride, dilate, norm)
+
+    @classmethod
+    def resnet_c3(cls, data, num_block, stride, dilate, norm):
+        return cls.resnet_stage(data, "stage2", num_block, 512, stride, dilate, norm)
+
+    @classmethod
+    def resnet_c4(cls, data, num_block, stride, dilate, norm):
+        return cls.resnet_stage(data, "stage3", num_block, 1024, stride, dilate, norm)
+
+    @classmethod
+    def resnet_c5(cls, data, num_block, stride, dilate, norm):
+        return cls.resnet_stage(data, "stage4", num_block, 2048, stride, dilate, norm)
+
+
+class ResNetV1bBuilder:
+    def get_backbone(self, variant, depth, endpoint, normalizer, fp16):
+        h = resnet_v1b_helper
+        n2, n3, n4, n5 = h.depth_config[depth]
+        data = var("data")
+        if fp16:
+            data = to_fp16(data, "data_fp16")
+        c1 = h.resnet_c1(data, normalizer)
+        c2 = h.resnet_c2(c1, n2, 1, 1, normalizer)
+        c3 = h.resnet_c3(c2, n3, 2, 1, normalizer)
+        c4 = h.resnet_c4(c3, n4, 2, 1, normalizer)
+        if endpoint == "c4":
+            return c4
+        c5 = h.resnet_c5(c4, n5, 2, 1, normalizer)
+        if endpoint == "c5":
+            return c5
+        if endpoint == "c4c5":
+            return c4, c5
+        if endpoint == "fpn":
+            return c2, c3, c4, c5
+        raise NotImplementedError(endpoint)
+
+    resnet_stage = resnet_v1b_helper.resnet_stage
 
 
 # ---- mxnext.tvm.* -----------------------------------------------------------------------------------------------------------

@@ -27,18 +27,28 @@ class Node:
 _AUTO_ARGS = {
     "Convolution": ("weight", "bias"), "FullyConnected": ("weight", "bias"), "Deconvolution": ("weight", "bias"),
     "BatchNorm": ("gamma", "beta", "moving_mean", "moving_var"),
+    "_contrib_DeformableConvolution": ("weight", "bias"), "_contrib_ModulatedDeformableConvolution": ("weight", "bias"),
 }
 _AUX = {"moving_mean", "moving_var"}
 # operators with several outputs: name -> callable(attrs) -> (total outputs, visible outputs)
 _MULTI_OUT = {
     "_contrib_Proposal_v3": lambda a: (2, 2 if _truthy(a.get("output_score", False)) else 1),
     "_contrib_Proposal": lambda a: (2, 2 if _truthy(a.get("output_score", False)) else 1),
+    "_contrib_Proposal_v2": lambda a: (2, 2 if _truthy(a.get("output_score", False)) else 1),
+    "_contrib_NMS": lambda a: (2, 2 if _truthy(a.get("output_score", False)) else 1),
+    "_contrib_GenProposalRetina": lambda a: (2, 2),          # generate_proposal_retina-inl.h: bbox, score
     "_contrib_ROIAlign_v2": lambda a: (3, 1),
+    "ROIPooling_v1": lambda a: (2, 1),
+    "ProposalTarget_v2": lambda a: (5, 5 if _truthy(a.get("output_iou", False)) else 4),
+    "ProposalMaskTarget": lambda a: ((lambda n: (n, n))(5 + int(_truthy(a.get("output_iou", False)))
+                                                        + int(_truthy(a.get("output_ratio", False))))),
     "ProposalTarget": lambda a: (5, 5 if _truthy(a.get("output_iou", False)) else 4),
     "BatchNorm": lambda a: (1, 1),
     "SliceChannel": lambda a: (int(a["num_outputs"]), int(a["num_outputs"])),
     "split": lambda a: (int(a["num_outputs"]), int(a["num_outputs"])),
 }
+# non-symbol positional arguments of the creation operators, in order
+_POSITIONAL_ATTRS = {"full": ("shape", "value"), "zeros": ("shape",), "ones": ("shape",), "arange": ("start", "stop", "step")}
 CUSTOM_OUTPUTS = {"get_top_proposal": 2, "assign_layer_fpn": None, "BboxPostProcessing": 3, "bbox_target": 4,
                   "decode_retina": 2}
 
@@ -191,6 +201,8 @@ class Symbol:
     def __truediv__(self, o): return self._bin(o, "elemwise_div", "_div_scalar")
     def __rtruediv__(self, o): return self._bin(o, "elemwise_div", "_div_scalar", rev=True)
     def __neg__(self): return self._bin(-1.0, "elemwise_mul", "_mul_scalar")
+    def __pow__(self, o): return self._bin(o, "_power", "_power_scalar")
+    def __rpow__(self, o): return self._bin(o, "_power", "_rpower_scalar")
 
     def reshape(self, shape=None, **kw):
         return make_op("Reshape", [self], dict(shape=tuple(shape if shape is not None else kw["shape"])))
@@ -210,6 +222,16 @@ def make_op(op: str, inputs: list, attrs: dict[str, Any], name: str | None = Non
             import ast
 
             n = len(ast.literal_eval(str(attrs["rcnn_stride"])))
+        if n is None:  # a CustomOpProp registered by the reference itself (mx.operator.register): ask it
+            from . import ndarray as _nd
+
+            prop_cls = _nd._CUSTOM.get(attrs.get("op_type"))
+            if prop_cls is not None:
+                try:
+                    kw = {k: str(v) for k, v in attrs.items() if k != "op_type" and not k.startswith("__")}
+                    n = len(prop_cls(**kw).list_outputs())
+                except Exception:  # a prop that needs arguments the graph does not carry: single output
+                    n = None
         total = visible = n or 1
     node = Node(op, name, inputs, attrs, total, arg_names)
     return Symbol([(node, i) for i in range(visible)]) if visible > 1 else Symbol([(node, 0)])
@@ -244,6 +266,8 @@ class _OpNamespace:
                 elif isinstance(a, (list, tuple)) and a and all(isinstance(x, Symbol) for x in a):
                     inputs.extend(a)
                     arg_names.extend([None] * len(a))
+                elif op in _POSITIONAL_ATTRS:          # creation ops: mx.sym.full(shape, val), zeros(shape), ...
+                    attrs[_POSITIONAL_ATTRS[op][len(attrs)]] = a
             for k, v in list(kwargs.items()):
                 if isinstance(v, Symbol):
                     inputs.append(v)

@@ -1,19 +1,35 @@
 #!/usr/bin/env python
-"""Writes tests/golden/faster_r50v1_fpn_1x_test_symbol.json: the inference graph that the REFERENCE'S OWN
-config/faster_r50v1_fpn_1x.py + symbol/builder.py + models/FPN/builder.py build when they run, unchanged, on the
-`mxnet` / `mxnext` façade (simpledet_b200.facade).  The GPU box has no reference checkout; the graph travels as this
-fixture.  Run:  python tests/golden/make_golden_graph.py     (needs /root/reference)"""
+"""Writes tests/golden/<config>_test_symbol.json: the inference graphs that the REFERENCE'S OWN config/*.py +
+symbol/builder.py + models/*/builder.py build when they run, unchanged, on the `mxnet` / `mxnext` façade
+(simpledet_b200.facade).  The GPU box has no reference checkout; the graphs travel as these fixtures.  One interpreter
+per config: the reference caches the RPN sub-graph in a class attribute (symbol/builder.py FasterRcnn._rpn_output).
+Run:  python tests/golden/make_golden_graph.py     (needs /root/reference)"""
 import importlib
 import os
+import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from simpledet_b200 import facade  # noqa: E402
+ROOT = os.path.dirname(os.path.dirname(HERE))
+# BASELINE.json configs 2-5: Faster R-CNN FPN, RetinaNet, Mask R-CNN, DCNv1 Faster R-CNN C4
+CONFIGS = ["faster_r50v1_fpn_1x", "retina_r50v1_fpn_1x", "mask_r50v1_fpn_1x", "dcn.faster_dcn_r50v1bc4_c5_512roi_1x"]
 
-facade.install("/root/reference")
-cfg = importlib.import_module("config.faster_r50v1_fpn_1x")
-sym = cfg.get_config(is_train=False)[6].test_symbol
-path = os.path.join(HERE, "faster_r50v1_fpn_1x_test_symbol.json")
-open(path, "w").write(sym.tojson())
-print("wrote", path, os.path.getsize(path), "bytes;", len(sym._topo()), "nodes; outputs", sym.list_outputs())
+
+def one(name):
+    sys.path.insert(0, ROOT)
+    from simpledet_b200 import facade
+
+    facade.install("/root/reference")
+    cfg = importlib.import_module("config." + name)
+    sym = cfg.get_config(is_train=False)[6].test_symbol
+    path = os.path.join(HERE, name.split(".")[-1] + "_test_symbol.json")
+    open(path, "w").write(sym.tojson())
+    print("wrote", path, os.path.getsize(path), "bytes;", len(sym._topo()), "nodes; outputs", sym.list_outputs())
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        one(sys.argv[1])
+    else:
+        for c in CONFIGS:
+            subprocess.run([sys.executable, os.path.abspath(__file__), c], check=True)

@@ -87,3 +87,162 @@ def test_frozen_batchnorm_is_folded_into_the_convolution():
         assert len(ex._bn_of_conv) == (1 if fold else 0)
         res[fold] = ex.forward(data=x)[0]
     torch.testing.assert_close(res[True], res[False], rtol=1e-5, atol=1e-5)
+
+
+# ---- other detectors of the reference on the same stand-ins ("the four configs import and run unchanged")
+_PROBE = r"""
+import importlib, json, math, sys
+sys.path.insert(0, {root!r})
+from simpledet_b200 import facade
+from simpledet_b200.facade import executor as E
+facade.install("/root/reference")
+cfg = importlib.import_module("config." + {name!r})
+shapes = dict(data=(1, 3, 800, 1333), im_info=(1, 3), im_id=(1,), rec_id=(1,))
+test = cfg.get_config(is_train=False)[6].test_symbol
+try:
+    args, outs, aux = test.infer_shape(**shapes)
+    npar = sum(math.prod(s) for n, s in zip(test.list_arguments(), args) if n not in shapes)
+    fusions = len(E.Executor(test, device="cpu")._fusions)
+except NotImplementedError:          # graph built, an operator of it has no shape rule in the executor
+    outs = npar = fusions = None
+train = cfg.get_config(is_train=True)[6].train_symbol
+print(json.dumps(dict(outs=outs, npar=npar, ops=sorted({{n.op for n in test._topo() if n.op}}), fusions=fusions,
+                      train_ops=sorted({{n.op for n in train._topo() if n.op}}), train_outs=train.list_outputs())))
+"""
+
+# name -> (visible outputs after rec_id / im_id / im_info, parameter count in millions, operators that must be present)
+DETECTORS = {
+    "retina_r50v1_fpn_1x": ([(1, 5000, 81), (1, 5000, 4)], (37, 39), {"_contrib_GenAnchor", "_contrib_GenProposalRetina"},
+                            {"_contrib_FocalLoss", "_contrib_BBoxNorm"}),
+    "mask_r50v1_fpn_1x": ([(1, 100, 1), (1, 100, 4), (1, 100, 1), (100, 81, 28, 28), (1,)], (43, 46),
+                          {"_contrib_Proposal_v3", "_contrib_ROIAlign_v2", "Deconvolution", "Custom"},
+                          {"ProposalMaskTarget", "_contrib_SigmoidCrossEntropy"}),
+    # the test graph carries five fc1 weights: three stages + the 1st / 2nd heads re-applied to 3rd-stage rois
+    "cascade_r50v1_fpn_1x": ([(1, 1000, 81), (1, 1000, 4)], (95, 99), {"_contrib_DecodeBBox", "_contrib_ROIAlign_v2"},
+                             {"ProposalTarget"}),
+    "faster_r50v1c4_c5_512roi_1x": ([(1, 1000, 81), (1, 1000, 4)], (27, 30), {"_contrib_Proposal", "_contrib_ROIAlign_v2"},
+                                    {"ProposalTarget"}),
+    "dcn.faster_dcn_r50v1bc4_c5_512roi_1x": ([(1, 300, 81), (1, 300, 4)], (28, 32), {"_contrib_DeformableConvolution"},
+                                             {"ProposalTarget", "_contrib_DeformableConvolution"}),
+    # Mask Scoring R-CNN: the graphs build (its training graph is the ProposalMaskTarget(output_ratio=True) caller);
+    # the test graph's index gymnastics (arange / stack / gather_nd) are not wired into the executor
+    "ms_r50v1_fpn_1x": (None, None, {"_contrib_Proposal_v3", "gather_nd"}, {"ProposalMaskTarget"}),
+}
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/config"), reason="reference checkout not present")
+@pytest.mark.parametrize("name", sorted(DETECTORS))
+def test_other_reference_detectors_build_on_the_facade(name):
+    """Each config is built in its own interpreter: the reference caches the RPN sub-graph in a class attribute
+    (symbol/builder.py FasterRcnn._rpn_output), so two detectors built in one process share nodes - there as here."""
+    import json
+    import subprocess
+
+    r = subprocess.run([sys.executable, "-c", _PROBE.format(root=ROOT, name=name)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    outs, npar, need, need_train = DETECTORS[name]
+    if outs is not None:
+        assert [tuple(s) for s in got["outs"][3:]] == outs
+        assert npar[0] * 1e6 < got["npar"] < npar[1] * 1e6, got["npar"]
+        assert got["fusions"] is not None
+    assert need <= set(got["ops"]) and need_train <= set(got["train_ops"])
+    assert got["train_outs"]
+
+
+# ---- executor glue for the other detectors, without a GPU: every detection operator replaced by a stub that checks the
+# ---- arguments it is handed (names, shapes, attribute parsing) and returns tensors of the operator's output shapes
+def _stubs(torch, log):
+    def proposal(cls_prob, bbox_pred, im_info, rpn_pre_nms_top_n, rpn_post_nms_top_n, threshold, rpn_min_size, scales,
+                 ratios, feature_stride, output_score, iou_loss):
+        B, A2, H, W = cls_prob.shape
+        assert A2 == 2 * len(scales) * len(ratios) and tuple(bbox_pred.shape) == (B, 2 * A2, H, W)
+        assert tuple(im_info.shape) == (B, 3) and output_score and 0 < threshold < 1
+        log.append(("proposal", feature_stride))
+        return torch.rand(B, rpn_post_nms_top_n, 4) * 100, torch.rand(B, rpn_post_nms_top_n, 1)
+
+    def gen_anchor(cls_prob, feature_stride, scales, ratios):
+        log.append(("gen_anchor", feature_stride))
+        return torch.zeros(cls_prob.shape[2] * cls_prob.shape[3] * len(scales) * len(ratios), 4)
+
+    def gen_proposal_retina(cls_prob, bbox_pred, im_info, anchors, feature_stride, rpn_pre_nms_top_n, rpn_min_size,
+                            num_anchors, thresh, anchor_mean, anchor_std, output_one_hot):
+        B, AK, H, W = cls_prob.shape
+        assert tuple(bbox_pred.shape) == (B, 4 * num_anchors, H, W) and tuple(anchors.shape) == (H * W * num_anchors, 4)
+        assert len(anchor_mean) == len(anchor_std) == 4 and 0 <= thresh < 1 and AK % num_anchors == 0
+        log.append(("gen_proposal_retina", feature_stride, thresh))
+        return torch.zeros(B, rpn_pre_nms_top_n, 4), torch.zeros(B, rpn_pre_nms_top_n, AK // num_anchors + 1)
+
+    def get_top_proposal(bbox, score, top_n):
+        assert bbox.shape[:2] == score.shape[:2]
+        return bbox[:, :top_n].contiguous(), score[:, :top_n].contiguous()
+
+    def decode_bbox(rois, bbox_pred, im_info, mean, std, class_agnostic):
+        assert rois.shape[:2] == bbox_pred.shape[:2] and len(mean) == len(std) == 4
+        return rois.clone() if class_agnostic else bbox_pred.clone()
+
+    def post_processing(cls_score, bbox_xyxy, max_det_per_image, min_det_score, nms_type, nms_thr):
+        B = cls_score.shape[0]
+        assert bbox_xyxy.shape[:2] == cls_score.shape[:2] and nms_type == "nms" and 0 < nms_thr < 1
+        log.append(("post", max_det_per_image))
+        return (torch.rand(B, max_det_per_image, 1), torch.rand(B, max_det_per_image, 4) * 100,
+                torch.zeros(B, max_det_per_image, 1))
+
+    def deform_conv(data, offset, weight, bias, kernel, stride, dilate, pad, num_filter, num_group, num_deformable_group,
+                    no_bias):
+        B, C, H, W = data.shape
+        Ho = (H + 2 * pad[0] - (dilate[0] * (kernel[0] - 1) + 1)) // stride[0] + 1
+        Wo = (W + 2 * pad[1] - (dilate[1] * (kernel[1] - 1) + 1)) // stride[1] + 1
+        assert tuple(offset.shape) == (B, 2 * num_deformable_group * kernel[0] * kernel[1], Ho, Wo)
+        assert tuple(weight.shape) == (num_filter, C // num_group, *kernel) and (bias is None) == no_bias
+        log.append(("dcn", C))
+        return torch.zeros(B, num_filter, Ho, Wo)
+
+    return {"_contrib_Proposal_v3": proposal, "_contrib_Proposal": proposal, "_contrib_GenAnchor": gen_anchor,
+            "_contrib_GenProposalRetina": gen_proposal_retina, "get_top_proposal": get_top_proposal,
+            "_contrib_DecodeBBox": decode_bbox, "BboxPostProcessing": post_processing,
+            "_contrib_DeformableConvolution": deform_conv}
+
+
+@pytest.mark.parametrize("name,outs", [
+    ("retina_r50v1_fpn_1x", [(1, 5000, 81), (1, 5000, 4)]),
+    ("mask_r50v1_fpn_1x", [(1, 100, 1), (1, 100, 4), (1, 100, 1), (100, 81, 28, 28), (1,)]),
+    ("faster_dcn_r50v1bc4_c5_512roi_1x", [(1, 300, 81), (1, 300, 4)]),
+])
+def test_executor_glue_of_the_other_detectors(name, outs, monkeypatch):
+    import torch
+
+    from simpledet_b200 import ops
+
+    sym = S.fromjson(open(os.path.join(ROOT, "tests", "golden", name + "_test_symbol.json")).read())
+    shapes = dict(data=(1, 3, 128, 192), im_info=(1, 3), im_id=(1,), rec_id=(1,))
+    log = []
+    for k, fn in _stubs(torch, log).items():
+        monkeypatch.setitem(ops.OPS, k, fn)
+
+    def roi_align(data, rois, pooled_size, spatial_scale, with_argmax=True, **kw):
+        assert rois.shape[0] == data.shape[0] and rois.shape[2] == 4 and 0 < spatial_scale < 1
+        o = torch.zeros(rois.shape[0], rois.shape[1], data.shape[1], *pooled_size)
+        return o, o, o
+
+    def fpn_roi_align(feats, rois, strides, out_size, scale0, lvl0, with_argmax=True):
+        assert len(feats) == len(strides) and all(f.shape[1] == feats[0].shape[1] for f in feats)
+        log.append(("fpn_roi_align", tuple(out_size)))
+        return (torch.zeros(rois.shape[0], rois.shape[1], feats[0].shape[1], *out_size),)
+
+    monkeypatch.setattr(ops, "roi_align_v2_raw", roi_align)
+    monkeypatch.setattr(ops, "fpn_roi_align_raw", fpn_roi_align)
+    ex = E.Executor(sym, device="cpu", channels_last=False).init_params(shapes, rng_std=0.01)
+    feed = dict(data=torch.ones(shapes["data"]), im_info=torch.tensor([[128.0, 192.0, 1.0]]), im_id=torch.ones(1),
+                rec_id=torch.ones(1))
+    with torch.no_grad():
+        got = ex.forward(**feed)
+    assert [tuple(o.shape) for o in got[3:]] == outs
+    kinds = {e[0] for e in log}
+    if name.startswith("retina"):
+        assert sorted(e[1] for e in log if e[0] == "gen_proposal_retina") == [8, 16, 32, 64, 128]
+        assert [e[2] for e in log if e[0] == "gen_proposal_retina" and e[1] == 128] == [0.0]   # builder.py:372
+    elif name.startswith("mask"):
+        assert ("fpn_roi_align", (7, 7)) in log and ("fpn_roi_align", (14, 14)) in log and "post" in kinds
+    else:
+        assert "dcn" in kinds and "proposal" in kinds

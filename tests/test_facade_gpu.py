@@ -141,3 +141,35 @@ def test_module_executor_group_records_and_replays(cuda):
     assert grp._run is not None and getattr(grp, "_graph_ok", True)
     grp.set_params(params, {})
     assert grp._run is None
+
+
+@pytest.mark.parametrize("name,outs", [
+    ("retina_r50v1_fpn_1x", [(1, 5000, 81), (1, 5000, 4)]),
+    ("mask_r50v1_fpn_1x", [(1, 100, 1), (1, 100, 4), (1, 100, 1), (100, 81, 28, 28), (1,)]),
+    ("faster_dcn_r50v1bc4_c5_512roi_1x", [(1, 300, 81), (1, 300, 4)]),
+])
+def test_other_detectors_of_the_reference_run(cuda, name, outs):
+    """BASELINE configs 3-5 as the reference's own builders emit them (fixtures written by
+    tests/golden/make_golden_graph.py): RetinaNet (GenAnchor + GenProposalRetina per level), Mask R-CNN (Proposal_v3 x5,
+    two fused FPN RoIAlign sizes, BboxPostProcessing, the deconvolution mask head) and DCNv1 Faster R-CNN C4 (legacy
+    Proposal, DeformableConvolution in the backbone), 800x1333, random weights."""
+    sym = S.fromjson(open(os.path.join(ROOT, "tests", "golden", name + "_test_symbol.json")).read())
+    shapes = dict(data=(1, 3, 800, 1333), im_info=(1, 3), im_id=(1,), rec_id=(1,))
+    gen = torch.Generator(device=cuda).manual_seed(5)
+    feed = dict(data=torch.randn(shapes["data"], device=cuda, generator=gen), im_info=torch.tensor([[800.0, 1333.0, 1.0]], device=cuda),
+                im_id=torch.ones(1, device=cuda), rec_id=torch.ones(1, device=cuda))
+    ex = facade.Executor(sym, cuda).init_params(shapes, rng_std=0.02)
+    with torch.no_grad():
+        got = ex.forward(**feed)
+    torch.cuda.synchronize()
+    assert [tuple(o.shape) for o in got[3:]] == outs
+    assert all(torch.isfinite(o).all() for o in got)
+    if name.startswith("retina"):
+        score, box = got[3], got[4]
+        assert float(score.max()) <= 1.0 and float(score.min()) >= 0.0
+        kept = score.sum(-1) > 0                                  # rows that passed the score threshold are real boxes
+        assert int(kept.sum()) > 0 and bool((box[kept][:, 2] >= box[kept][:, 0]).all())
+    elif name.startswith("mask"):
+        assert float(got[6].min()) >= 0.0 and float(got[6].max()) <= 1.0     # mask_prob is a sigmoid
+    else:
+        np.testing.assert_allclose(got[3].sum(-1).cpu().numpy(), 1.0, rtol=1e-4)
