@@ -4,7 +4,8 @@ tests/golden/faster_r50v1_fpn_1x_test_symbol.json), run by the façade executor:
 the C ABI for every detection operator.  `--weights zero` is the reference harness's setting, `random` the realistic
 variant of SURVEY §8d.
 
-  python benchmarks/graph_infer_speed.py [--count 100] [--weights zero|random] [--tf32 1]"""
+  python benchmarks/graph_infer_speed.py [--count 100] [--weights zero|random] [--tf32 1] [--graph 1]
+         [--config faster_r50v1_fpn_1x|retina_r50v1_fpn_1x|mask_r50v1_fpn_1x|faster_dcn_r50v1bc4_c5_512roi_1x]"""
 import argparse
 import json
 import os
@@ -26,12 +27,13 @@ def main():
     ap.add_argument("--tf32", type=int, default=1)
     ap.add_argument("--channels-last", type=int, default=1)
     ap.add_argument("--graph", type=int, default=0, help="1: replay the forward pass from one CUDA graph")
+    ap.add_argument("--config", default="faster_r50v1_fpn_1x", help="which committed graph fixture (tests/golden/*_test_symbol.json)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.backends.cudnn.allow_tf32 = bool(a.tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(a.tf32)
     torch.backends.cudnn.benchmark = True
-    sym = S.fromjson(open(os.path.join(ROOT, "tests", "golden", "faster_r50v1_fpn_1x_test_symbol.json")).read())
+    sym = S.fromjson(open(os.path.join(ROOT, "tests", "golden", a.config + "_test_symbol.json")).read())
     shapes = dict(data=(1, 3, 800, 1333), im_info=(1, 3), im_id=(1,), rec_id=(1,))
     ex = facade.Executor(sym, dev, channels_last=bool(a.channels_last)).init_params(
         shapes, rng_std=None if a.weights == "zero" else 0.02)
@@ -49,7 +51,9 @@ def main():
             torch.cuda.synchronize()   # output.wait_to_read() per iteration, as the reference script does
         toc = time.time()
     ms = (toc - tic) / a.count * 1000
-    print(json.dumps({"graph": "faster_r50v1_fpn_1x test_symbol (551 nodes, 41.8 M parameters)", "weights": a.weights,
+    npar = sum(v.numel() for v in ex.params.values())
+    print(json.dumps({"graph": "%s test_symbol (%d nodes, %.1f M parameters)" % (a.config, len(sym._topo()), npar / 1e6),
+                      "weights": a.weights,
                       "ms_per_iter": round(ms, 3), "images_per_s": round(1000 / ms, 2), "count": a.count,
                       "tf32_conv": bool(a.tf32), "channels_last": bool(a.channels_last), "cuda_graph": bool(a.graph),
                       "sdet_launches_per_iter": (_lib.launch_count() - n0) // a.count}))
