@@ -226,7 +226,12 @@ int sdet_gen_proposal_retina(const float* cls_prob, const float* bbox_pred, cons
  * (models/FPN/builder.py:267-317).  cls_prob[l] (B,2A,H[l],W[l]), bbox_pred[l] (B,4A,H[l],W[l]);
  * the pointer / H / W / feature_stride arrays are HOST arrays of length num_levels.
  * out (B, num_levels*post, 4), out_score (B, num_levels*post, 1): level-major per image, each
- * level's slice exactly what sdet_proposal_v3 writes for that level. */
+ * level's slice exactly what sdet_proposal_v3 writes for that level.
+ * is_train: when every level has the same anchor count, post = min(rpn_post_nms_top_n, count) like sdet_proposal_v3.
+ * When they differ and a level has fewer anchors than rpn_post_nms_top_n (P6 of an 800x1333 FPN: 819 < 2000), post
+ * stays rpn_post_nms_top_n for every level; the small level writes min(post, its count) rows (kept boxes, then the
+ * reference's wrap-around padding) and ZERO rows after them, which ProposalTarget drops (y2 > 0 test).  (The
+ * reference leaves those rows unwritten and strides images by the shrunken count, proposal_v3.cu:471-476,:629-631.) */
 size_t sdet_proposal_v3_fpn_workspace(int B, int A, const int* H, const int* W, int num_levels,
                                       int rpn_pre_nms_top_n);
 int sdet_proposal_v3_fpn(const float* const* cls_prob, const float* const* bbox_pred,
