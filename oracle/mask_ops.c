@@ -5,7 +5,9 @@
  * (operator_cxx/proposal_mask_target.cc:155-213 convertPoly2Mask).  The rasteriser itself
  * (rleFrPoly / rleDecode) comes from RogerChern/cocoapi common/maskApi.c, which is NOT vendored in
  * the reference and is cloned unpinned (doc/INSTALL.md:90-93): restated here from the published
- * pycocotools algorithm — PARITY UNPINNED.
+ * pycocotools algorithm — PARITY UNPINNED.  What IS pinned: everything the reference's
+ * operator does around the rasteriser (oracle_poly2mask / oracle_poly2mask_ratio against proposal_mask_target.cc
+ * compiled with a stand-in maskApi.h, tests/test_oracle_ref_cxx.py::test_proposal_mask_target_*).
  *
  *   oracle_rle_fr_poly_mask   maskApi.c rleFrPoly + rleDecode: polygon (k vertices, x/y doubles)
  *                             -> h*w bytes, COLUMN-major like the RLE

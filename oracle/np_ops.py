@@ -219,7 +219,8 @@ def box_voting(top_dets, all_dets, thresh=0.5, scoring_method="ID", beta=1.0, ov
 
 
 # ---- DCNv1 sampling: restated from the published formulation (upstream MXNet
-# src/operator/contrib/nn/deformable_im2col.h/.cuh; not in the reference tree) — PARITY UNPINNED ----
+# src/operator/contrib/nn/deformable_im2col.h/.cuh; not in the reference tree) — PARITY UNPINNED (cross-checked against
+# torchvision.ops.deform_conv2d, an independent implementation: tests/test_oracle_dcn_torchvision.py) ----
 def deformable_im2col(data, offset, kernel, stride=(1, 1), dilate=(1, 1), pad=(0, 0), num_deformable_group=1):
     """data (B,C,H,W), offset (B, dg*2*KH*KW, Ho, Wo) -> col (B, C*KH*KW, Ho*Wo), float32 arithmetic."""
     f = np.float32
