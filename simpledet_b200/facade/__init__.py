@@ -140,10 +140,11 @@ def install(reference_root: str | None = None):
     bb.__path__ = []
     _mod("mxnext.backbone.resnet_v1", Builder=X.ResNetV1Builder)
     _mod("mxnext.backbone.resnet_v1b", Builder=X.ResNetV1bBuilder)
-    h = X.resnet_v1b_helper
-    _mod("mxnext.backbone.resnet_v1b_helper", depth_config=h.depth_config, resnet_unit=h.resnet_unit,
-         resnet_stage=h.resnet_stage, resnet_c1=h.resnet_c1, resnet_c2=h.resnet_c2, resnet_c3=h.resnet_c3,
-         resnet_c4=h.resnet_c4, resnet_c5=h.resnet_c5)
+    _mod("mxnext.backbone.resnet_v2", Builder=X.ResNetV2Builder)
+    for hname, h in (("resnet_v1b_helper", X.resnet_v1b_helper), ("resnet_v1_helper", X.resnet_v1_helper)):
+        setattr(bb, hname, _mod("mxnext.backbone." + hname, depth_config=h.depth_config, resnet_unit=h.resnet_unit,
+                                resnet_stage=h.resnet_stage, resnet_c1=h.resnet_c1, resnet_c2=h.resnet_c2,
+                                resnet_c3=h.resnet_c3, resnet_c4=h.resnet_c4, resnet_c5=h.resnet_c5))
     tvm = _mod("mxnext.tvm")
     tvm.__path__ = []
     _mod("mxnext.tvm.proposal", proposal=X.tvm_proposal)

@@ -43,6 +43,17 @@ def var(name, init=None, lr_mult=None, wd_mult=None, shape=None, dtype=None, **k
     return S.Variable(name, shape=shape, lr_mult=lr_mult, wd_mult=wd_mult, dtype=dtype, init=init, **kw)
 
 
+_SHARED_VARS = {}
+
+
+def shared_var(name, **kw):
+    """One variable node per name, however often it is asked for (TridentNet's branches share weights this way:
+    models/tridentnet/builder_v2.py:25-35)."""
+    if name not in _SHARED_VARS:
+        _SHARED_VARS[name] = var(name, **kw)
+    return _SHARED_VARS[name]
+
+
 def _pair(v):
     return tuple(v) if isinstance(v, (tuple, list)) else (int(v), int(v))
 
@@ -91,12 +102,17 @@ def global_avg_pool(data, name=None):
     return sym.Pooling(data=data, kernel=(1, 1), pool_type="avg", global_pool=True, name=name)
 
 
+_BN_PARAMS = ("gamma", "beta", "moving_mean", "moving_var")
+
+
 def fixbn(data, name, eps=1e-5, **kw):
-    return sym.BatchNorm(data=data, name=name, use_global_stats=True, fix_gamma=False, eps=eps)
+    shared = {k: kw[k] for k in _BN_PARAMS if kw.get(k) is not None}   # TridentNet shares BN parameters across branches
+    return sym.BatchNorm(data=data, name=name, use_global_stats=True, fix_gamma=False, eps=eps, **shared)
 
 
 def bn(data, name, eps=1e-5, mom=0.9, **kw):
-    return sym.BatchNorm(data=data, name=name, use_global_stats=False, fix_gamma=False, eps=eps, momentum=mom)
+    shared = {k: kw[k] for k in _BN_PARAMS if kw.get(k) is not None}
+    return sym.BatchNorm(data=data, name=name, use_global_stats=False, fix_gamma=False, eps=eps, momentum=mom, **shared)
 
 
 def convrelu(data, name, filter, kernel=1, stride=1, pad=-1, dilate=1, no_bias=False, init=None, **kw):
@@ -209,11 +225,14 @@ def bbox_norm(data, label, name=None, **kw):
 
 # ---- mxnext.complicate -----------------------------------------------------------------------------------------------
 def normalizer_factory(type="local", ndev=None, eps=1e-5, mom=0.9, wd_mult=1.0, lr_mult=1.0):
+    if callable(type):   # models/tridentnet/resnet_v1.py:126 hands an already-built normalizer back to the factory
+        return type
+
     def fix_bn(data, name=None, **kw):
-        return fixbn(data, name, eps=eps)
+        return fixbn(data, name, eps=eps, **kw)
 
     def local_bn(data, name=None, **kw):
-        return bn(data, name, eps=eps, mom=mom)
+        return bn(data, name, eps=eps, mom=mom, **kw)
 
     def dummy(data, name=None, **kw):
         return data
@@ -249,7 +268,35 @@ class ResNetV1Builder:
     @classmethod
     def resnet_stage(cls, data, name, num_block, filter, stride, dilate, norm_type, norm_mom=0.9, ndev=None, **kw):
         """The C5 head of the C4 detectors (symbol/builder.py:624-634): one stage on top of the roi features."""
-        return cls.stage(data, name, num_block, filter, stride, dilate, norm_type)
+        return cls.stage(data, name, num_block, filter, stride, dilate, normalizer_factory(norm_type, ndev=ndev, mom=norm_mom))
+
+    # the piecewise interface TridentNet's builder subclasses (models/tridentnet/resnet_v1.py:195-240)
+    @classmethod
+    def resnet_unit(cls, data, name, filter, stride, dilate, proj, norm_type, norm_mom=0.9, ndev=None):
+        return cls.unit(data, name, filter, stride, dilate, proj, normalizer_factory(norm_type, ndev=ndev, mom=norm_mom))
+
+    @classmethod
+    def resnet_c1(cls, data, use_3x3_conv0, use_bn_preprocess, norm_type, norm_mom=0.9, ndev=None):
+        if use_3x3_conv0 or use_bn_preprocess:
+            raise NotImplementedError("3x3 conv0 / BN preprocessing stems are not in the stand-in")
+        norm = normalizer_factory(norm_type, ndev=ndev, mom=norm_mom)
+        return max_pool(convnormrelu(norm, data, "conv0", 64, kernel=7, stride=2), name="pool0", kernel=3, stride=2)
+
+    @classmethod
+    def resnet_c2(cls, data, num_block, stride, dilate, norm_type, norm_mom=0.9, ndev=None):
+        return cls.resnet_stage(data, "stage1", num_block, 256, stride, dilate, norm_type, norm_mom, ndev)
+
+    @classmethod
+    def resnet_c3(cls, data, num_block, stride, dilate, norm_type, norm_mom=0.9, ndev=None):
+        return cls.resnet_stage(data, "stage2", num_block, 512, stride, dilate, norm_type, norm_mom, ndev)
+
+    @classmethod
+    def resnet_c4(cls, data, num_block, stride, dilate, norm_type, norm_mom=0.9, ndev=None):
+        return cls.resnet_stage(data, "stage3", num_block, 1024, stride, dilate, norm_type, norm_mom, ndev)
+
+    @classmethod
+    def resnet_c5(cls, data, num_block, stride, dilate, norm_type, norm_mom=0.9, ndev=None):
+        return cls.resnet_stage(data, "stage4", num_block, 2048, stride, dilate, norm_type, norm_mom, ndev)
 
     def get_backbone(self, variant, depth, endpoint, normalizer, fp16):
         units = self.depth_config[depth]
@@ -273,6 +320,79 @@ class ResNetV1Builder:
     # the reference also calls these through thin wrappers
     def get_stage_endpoints(self, *a, **kw):
         return self.get_backbone(*a, **kw)
+
+
+# ---- mxnext.backbone.resnet_v2 ---------------------------------------------------------------------------------------------
+class ResNetV2Builder:
+    """Pre-activation ResNet (He et al. 2016, the layout of MXNet's resnet-v2 checkpoints: bn -> relu -> conv three
+    times, the projection shortcut taken from the first activation; parameter names stage{s}_unit{u}_bn{1,2,3},
+    _conv{1,2,3}, _sc; stem bn_data / conv0 / bn0; the closing bn1 + relu1 belong to whoever consumes the last
+    stage, symbol/builder.py:571-572).  Interface from the call sites: symbol/builder.py:564-574,655-660 and the
+    piecewise methods TridentNet's builder overrides (models/tridentnet/resnet_v2.py:195-265)."""
+    depth_config = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 152: (3, 8, 36, 3), 200: (3, 24, 36, 3)}
+
+    @classmethod
+    def resnet_unit(cls, data, name, filter, stride, dilate, proj, norm_type, norm_mom=0.9, ndev=None):
+        norm = normalizer_factory(norm_type, ndev=ndev, mom=norm_mom)
+        a1 = relu(norm(data, name=name + "_bn1"), name=name + "_relu1")
+        c1 = conv(a1, name=name + "_conv1", filter=filter // 4)
+        a2 = relu(norm(c1, name=name + "_bn2"), name=name + "_relu2")
+        c2 = conv(a2, name=name + "_conv2", filter=filter // 4, kernel=3, stride=stride, dilate=dilate)
+        a3 = relu(norm(c2, name=name + "_bn3"), name=name + "_relu3")
+        c3 = conv(a3, name=name + "_conv3", filter=filter)
+        sc = conv(a1, name=name + "_sc", filter=filter, stride=stride) if proj else data
+        return add(c3, sc, name=name + "_plus")
+
+    @classmethod
+    def resnet_stage(cls, data, name, num_block, filter, stride, dilate, norm_type, norm_mom=0.9, ndev=None, **kw):
+        data = cls.resnet_unit(data, f"{name}_unit1", filter, stride, dilate, True, norm_type, norm_mom, ndev)
+        for i in range(2, num_block + 1):
+            data = cls.resnet_unit(data, f"{name}_unit{i}", filter, 1, dilate, False, norm_type, norm_mom, ndev)
+        return data
+
+    @classmethod
+    def resnet_c1(cls, data, use_3x3_conv0, use_bn_preprocess, norm_type, norm_mom=0.9, ndev=None):
+        if use_3x3_conv0:
+            raise NotImplementedError("3x3 conv0 stem is not in the stand-in")
+        norm = normalizer_factory(norm_type, ndev=ndev, mom=norm_mom)
+        if use_bn_preprocess:
+            data = sym.BatchNorm(data=data, name="bn_data", use_global_stats=True, fix_gamma=True, eps=2e-5)
+        c = relu(norm(conv(data, name="conv0", filter=64, kernel=7, stride=2), name="bn0"), name="relu0")
+        return pool(c, name="pool0", kernel=3, stride=2, pad=1, pool_type="max")
+
+    @classmethod
+    def resnet_c2(cls, data, num_block, stride, dilate, norm_type, norm_mom=0.9, ndev=None):
+        return cls.resnet_stage(data, "stage1", num_block, 256, stride, dilate, norm_type, norm_mom, ndev)
+
+    @classmethod
+    def resnet_c3(cls, data, num_block, stride, dilate, norm_type, norm_mom=0.9, ndev=None):
+        return cls.resnet_stage(data, "stage2", num_block, 512, stride, dilate, norm_type, norm_mom, ndev)
+
+    @classmethod
+    def resnet_c4(cls, data, num_block, stride, dilate, norm_type, norm_mom=0.9, ndev=None):
+        return cls.resnet_stage(data, "stage3", num_block, 1024, stride, dilate, norm_type, norm_mom, ndev)
+
+    @classmethod
+    def resnet_c5(cls, data, num_block, stride, dilate, norm_type, norm_mom=0.9, ndev=None):
+        return cls.resnet_stage(data, "stage4", num_block, 2048, stride, dilate, norm_type, norm_mom, ndev)
+
+    def get_backbone(self, variant, depth, endpoint, normalizer, fp16):
+        n2, n3, n4, n5 = self.depth_config[depth]
+        data = var("data")
+        if fp16:
+            data = to_fp16(data, "data_fp16")
+        c1 = self.resnet_c1(data, False, variant == "mxnet", normalizer)   # MXNet's checkpoints carry bn_data
+        c2 = self.resnet_c2(c1, n2, 1, 1, normalizer)
+        c3 = self.resnet_c3(c2, n3, 2, 1, normalizer)
+        c4 = self.resnet_c4(c3, n4, 2, 1, normalizer)
+        if endpoint == "c4":
+            return c4
+        c5 = self.resnet_c5(c4, n5, 2, 1, normalizer)
+        if endpoint == "c5":
+            return c5
+        if endpoint == "c4c5":
+            return c4, c5
+        raise NotImplementedError(endpoint)
 
 
 # ---- mxnext.backbone.resnet_v1b / resnet_v1b_helper ----------------------------------------------------------------------
@@ -318,6 +438,21 @@ class resnet_v1b_helper:
     @classmethod
     def resnet_c5(cls, data, num_block, stride, dilate, norm):
         return cls.resnet_stage(data, "stage4", num_block, 2048, stride, dilate, norm)
+
+
+class resnet_v1_helper(resnet_v1b_helper):
+    """The same helper interface for ResNet-v1 in the MSRA layout (stride on the first 1x1 convolution of a unit):
+    `from mxnext.backbone import resnet_v1_helper` (models/tridentnet/builder_v2.py:4,183)."""
+
+    @staticmethod
+    def resnet_unit(input, name, filter, stride, dilate, proj, norm, **kw):
+        c1 = relu(norm(conv(input, name=name + "_conv1", filter=filter // 4, stride=stride), name=name + "_bn1"),
+                  name=name + "_relu1")
+        c2 = relu(norm(conv(c1, name=name + "_conv2", filter=filter // 4, kernel=3, dilate=dilate), name=name + "_bn2"),
+                  name=name + "_relu2")
+        c3 = norm(conv(c2, name=name + "_conv3", filter=filter), name=name + "_bn3")
+        sc = norm(conv(input, name=name + "_sc", filter=filter, stride=stride), name=name + "_sc_bn") if proj else input
+        return relu(add(c3, sc, name=name + "_plus"), name=name + "_relu")
 
 
 class ResNetV1bBuilder:

@@ -127,6 +127,11 @@ DETECTORS = {
     # Mask Scoring R-CNN: the graphs build (its training graph is the ProposalMaskTarget(output_ratio=True) caller);
     # the test graph's index gymnastics (arange / stack / gather_nd) are not wired into the executor
     "ms_r50v1_fpn_1x": (None, None, {"_contrib_Proposal_v3", "gather_nd"}, {"ProposalMaskTarget"}),
+    # TridentNet (three weight-sharing branches stacked into the batch axis): the callers of Proposal_v2 and
+    # ProposalTarget_v2 (valid_ranges); ResNet-v1 helper and pre-activation ResNet-v2 stand-ins
+    "tridentnet_r50v1c4_c5_1x": (None, None, {"_contrib_Proposal", "stack"}, {"_contrib_Proposal_v2", "ProposalTarget_v2"}),
+    "tridentnet_r50v2c4_c5_1x": (None, None, {"_contrib_Proposal", "stack"}, {"_contrib_Proposal_v2", "ProposalTarget_v2"}),
+    "faster_r50v2c4_c5_256roi_1x": ([(1, 1000, 81), (1, 1000, 4)], (25, 31), {"_contrib_Proposal"}, {"ProposalTarget"}),
 }
 
 
