@@ -127,6 +127,7 @@ def install(reference_root: str | None = None):
               AttrScope=module_mod.AttrScope, name=types.SimpleNamespace(Prefix=module_mod.AttrScope))
     mx.__path__ = []
     mx.__simpledet_facade__ = True
+    mx.contrib = types.SimpleNamespace(symbol=symm.contrib, sym=symm.contrib)   # mx.contrib.symbol.DeformableConvolution
 
     # ---- mxnext
     simple = {k: getattr(X, k) for k in dir(X) if not k.startswith("_") and callable(getattr(X, k))}
@@ -177,6 +178,17 @@ def install(reference_root: str | None = None):
                               torch.from_numpy(np.ascontiguousarray(query_boxes, np.float32)).to(dev))
         return o.cpu().numpy()
 
+    def _bbox_selfoverlaps_cython(boxes, query_boxes):
+        import numpy as np
+        import torch
+
+        from .. import ops
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        o = ops.bbox_overlaps(torch.from_numpy(np.ascontiguousarray(boxes, np.float32)).to(dev),
+                              torch.from_numpy(np.ascontiguousarray(query_boxes, np.float32)).to(dev), mode="ioa")
+        return o.cpu().numpy()
+
     def _soft_nms(boxes_in, sigma=0.5, Nt=0.3, threshold=0.001, method=0):
         import numpy as np
         import torch
@@ -205,6 +217,7 @@ def install(reference_root: str | None = None):
             cy = _mod("operator_py.cython")
             cy.__path__ = []
             _mod("operator_py.cython.bbox", bbox_overlaps_cython=_bbox_overlaps_cython)
+            _mod("operator_py.cython.bbox_self", bbox_selfoverlaps_cython=_bbox_selfoverlaps_cython)
             _mod("operator_py.cython.cpu_nms", soft_nms=_soft_nms, greedy_nms=_greedy_nms, cpu_nms=_greedy_nms)
             _mod("operator_py.cython.gpu_nms", gpu_nms=lambda dets, thresh, device_id=0: __import__(
                 "simpledet_b200.ops", fromlist=["gpu_nms"]).gpu_nms(dets, thresh, device_id))

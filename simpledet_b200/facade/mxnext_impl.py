@@ -71,6 +71,33 @@ def conv(data, name, filter, kernel=1, stride=1, pad=-1, dilate=1, num_group=1, 
     return sym.Convolution(**kw)
 
 
+def dwconv(data, name, filter, kernel=3, stride=1, pad=-1, dilate=1, no_bias=True, init=None, **kw):
+    """Depthwise convolution (models/efficientnet/builder.py:47): one group per channel."""
+    return conv(data, name, filter, kernel, stride, pad, dilate, num_group=int(filter), no_bias=no_bias, init=init)
+
+
+def gn(data, name=None, num_group=32, eps=1e-5, **kw):
+    return contrib.GroupNorm(data=data, name=name, eps=eps, num_group=num_group)
+
+
+def merge_sum(symbols, name=None):
+    return add_n(*symbols, name=name)
+
+
+def reluconvbn(data, filter=None, init=None, norm=None, name=None, prefix="", kernel=3, stride=1, pad=-1, filters=None,
+               **kw):
+    """NAS-FPN's / FPG's cell op (models/NASFPN/builder.py:63 positional, models/FPG/builder.py:94 by keyword with
+    `filters`): relu -> conv -> norm, parameters under `prefix`."""
+    r = relu(data, name=prefix + name + "_relu")
+    c = conv(r, prefix + name + "_conv", filter if filter is not None else filters, kernel=kernel, stride=stride, pad=pad,
+             no_bias=False, init=init)
+    return norm(c, name=prefix + name + "_bn")
+
+
+def relu6(data, name=None):
+    return sym.clip(data=data, a_min=0.0, a_max=6.0, name=name)
+
+
 def fc(data, name, filter, no_bias=False, flatten=True, init=None, weight=None, bias=None, lr_mult=1.0, wd_mult=1.0):
     weight = weight if weight is not None else var(name + "_weight", init=init, lr_mult=lr_mult, wd_mult=wd_mult)
     kw = dict(data=data, weight=weight, num_hidden=int(filter), no_bias=bool(no_bias), flatten=flatten, name=name)
@@ -237,10 +264,18 @@ def normalizer_factory(type="local", ndev=None, eps=1e-5, mom=0.9, wd_mult=1.0, 
     def dummy(data, name=None, **kw):
         return data
 
-    table = {"fixbn": fix_bn, "fix_bn": fix_bn, "local": local_bn, "localbn": local_bn, "local_bn": local_bn,
-             "dummy": dummy}
+    def sync_bn(data, name=None, **kw):
+        shared = {k: kw[k] for k in _BN_PARAMS if kw.get(k) is not None}
+        return contrib.SyncBatchNorm(data=data, name=name, fix_gamma=False, eps=eps, momentum=mom, ndev=ndev, key=name,
+                                     **shared)
+
+    def gn(data, name=None, **kw):
+        return contrib.GroupNorm(data=data, name=name, eps=eps, num_group=32)
+
+    table = {"fixbn": fix_bn, "fix_bn": fix_bn, "fix": fix_bn, "local": local_bn, "localbn": local_bn,
+             "local_bn": local_bn, "syncbn": sync_bn, "sync_bn": sync_bn, "gn": gn, "dummy": dummy}
     if type not in table:
-        raise NotImplementedError(f"normalizer {type!r}: only fixbn / local / dummy are built in the stand-in")
+        raise NotImplementedError(f"normalizer {type!r}: only fixbn / local / syncbn / gn / dummy are in the stand-in")
     return table[type]
 
 

@@ -28,6 +28,7 @@ _AUTO_ARGS = {
     "Convolution": ("weight", "bias"), "FullyConnected": ("weight", "bias"), "Deconvolution": ("weight", "bias"),
     "BatchNorm": ("gamma", "beta", "moving_mean", "moving_var"),
     "_contrib_DeformableConvolution": ("weight", "bias"), "_contrib_ModulatedDeformableConvolution": ("weight", "bias"),
+    "_contrib_SyncBatchNorm": ("gamma", "beta", "moving_mean", "moving_var"), "_contrib_GroupNorm": ("gamma", "beta"),
 }
 _AUX = {"moving_mean", "moving_var"}
 # operators with several outputs: name -> callable(attrs) -> (total outputs, visible outputs)
@@ -201,6 +202,10 @@ class Symbol:
     def __truediv__(self, o): return self._bin(o, "elemwise_div", "_div_scalar")
     def __rtruediv__(self, o): return self._bin(o, "elemwise_div", "_div_scalar", rev=True)
     def __neg__(self): return self._bin(-1.0, "elemwise_mul", "_mul_scalar")
+    def __lt__(self, o): return self._bin(o, "_lesser", "_lesser_scalar")
+    def __le__(self, o): return self._bin(o, "_lesser_equal", "_lesser_equal_scalar")
+    def __gt__(self, o): return self._bin(o, "_greater", "_greater_scalar")
+    def __ge__(self, o): return self._bin(o, "_greater_equal", "_greater_equal_scalar")
     def __pow__(self, o): return self._bin(o, "_power", "_power_scalar")
     def __rpow__(self, o): return self._bin(o, "_power", "_rpower_scalar")
 
