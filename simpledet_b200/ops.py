@@ -1393,6 +1393,101 @@ def decode_retina(cls_probs, bbox_preds, im_info, stride, scales, ratios, per_le
     score_out[0] = sbuf[:nrow]
     return boxes_out, score_out
 
+
+def _bbox_target_impl(proposal, gt_bbox, num_class, add_gt_to_proposal, image_rois, fg_fraction, fg_thresh, bg_thresh_hi,
+                      bg_thresh_lo, bbox_target_std, rng, overlaps):
+    """The body of `bbox_target` over tensors on one device, with the IoU operator passed in (the product passes the
+    CUDA `bbox_overlaps`; tests/test_bbox_target_host.py drives the same host logic on CPU tensors)."""
+    import numpy as np
+
+    B, R, C = proposal.shape[0], int(image_rois), int(num_class)
+    dev = proposal.device
+    inv = [1.0 / float(s) for s in bbox_target_std]
+    fg_per_image = int(np.round(float(fg_fraction) * R))        # np.round: half to even (bbox_target.py:27)
+    rois = torch.zeros((B, R, 4), device=dev, dtype=torch.float32)
+    label = torch.zeros((B, R), device=dev, dtype=torch.float32)
+    target = torch.zeros((B, R, 4 * C), device=dev, dtype=torch.float32)
+    weight = torch.zeros((B, R, 4 * C), device=dev, dtype=torch.float32)
+    for b in range(B):
+        gt = gt_bbox[b][gt_bbox[b][:, 4] != -1]                 # class == -1 is padding
+        prop = proposal[b][proposal[b][:, 3] != 0]              # y2 == 0 is padding
+        if add_gt_to_proposal:
+            prop = torch.cat([prop, gt[:, :4]], 0)
+        if gt.shape[0] == 0:
+            raise ValueError("bbox_target: an image without ground-truth boxes (the reference's argmax over an empty "
+                             "axis raises too)")
+        ov = overlaps(prop.contiguous(), gt[:, :4].contiguous())
+        mx, arg = ov.max(dim=1)                                  # first maximum, like numpy's argmax
+        mx_h = mx.cpu().numpy()
+        fg = np.where(mx_h >= fg_thresh)[0]
+        nfg = int(np.minimum(fg_per_image, fg.size))
+        if fg.size > 0:
+            fg = rng.choice(fg, size=nfg, replace=False)
+        bg = np.where((mx_h < bg_thresh_hi) & (mx_h >= bg_thresh_lo))[0]
+        nbg = int(np.minimum(R - nfg, bg.size))
+        if bg.size > 0:
+            bg = rng.choice(bg, size=nbg, replace=False)
+        keep = np.append(fg, bg).astype(np.int64)
+        if keep.size != R:
+            raise ValueError(f"bbox_target: image {b} has {keep.size} candidates for image_rois={R}; the reference "
+                             "returns ragged lists here, which it cannot stack either")
+        keep = torch.from_numpy(keep).to(dev)
+        agt = gt[arg[keep]]
+        lab = agt[:, 4].clone()
+        lab[nfg:] = 0
+        ex = prop[keep]
+        # detectron_bbox_utils.bbox_transform_inv:205-219, float32 throughout (python scalars are weak)
+        ew = ex[:, 2] - ex[:, 0] + 1.0
+        eh = ex[:, 3] - ex[:, 1] + 1.0
+        ecx = ex[:, 0] + 0.5 * ew
+        ecy = ex[:, 1] + 0.5 * eh
+        gw = agt[:, 2] - agt[:, 0] + 1.0
+        gh = agt[:, 3] - agt[:, 1] + 1.0
+        gcx = agt[:, 0] + 0.5 * gw
+        gcy = agt[:, 1] + 0.5 * gh
+        t = torch.stack([inv[0] * (gcx - ecx) / ew, inv[1] * (gcy - ecy) / eh, inv[2] * torch.log(gw / ew),
+                         inv[3] * torch.log(gh / eh)], 1)
+        cls = (lab > 0).to(torch.long) if C == 2 else lab.to(torch.long)
+        pos = torch.nonzero(cls > 0)[:, 0]
+        col = 4 * cls[pos][:, None] + torch.arange(4, device=dev)[None, :]
+        target[b][pos[:, None], col] = t[pos]
+        weight[b][pos[:, None], col] = 1.0
+        rois[b], label[b] = ex, lab
+    return rois, label, target, weight
+
+
+def bbox_target(proposal, gt_bbox, num_class, add_gt_to_proposal, image_rois, fg_fraction, fg_thresh, bg_thresh_hi,
+                bg_thresh_lo, bbox_target_std, rng=None):
+    """CustomOp 'bbox_target' (operator_py/bbox_target.py:12-170; the Detectron-style roi sampler of
+    models/crowdhuman/builder.py:380-396).  proposal (B,K,4), gt_bbox (B,M,5) float32 on the device ->
+    (sampled_proposal (B,R,4), bbox_cls (B,R), bbox_target (B,R,4C), bbox_target_weight (B,R,4C)), R = image_rois.
+
+    A host-composed operator: IoU (the `bbox_overlaps_cython` kernel), the arg-max match, the gather and the float32
+    target arithmetic run on the device; the sampling is the reference's own two `numpy.random.choice(..., replace=
+    False)` draws per image on the host, in the reference's order (foreground, then background), so under
+    `numpy.random.seed(s)` the sampled rows are the reference's rows.  `rng` defaults to the global `numpy.random`
+    module like the reference; a `numpy.random.RandomState` may be passed instead.  Where the reference cannot work
+    either (an image with fewer candidates than image_rois: ragged lists; an image without gt: argmax of an empty
+    axis) a ValueError says so.  No gradient flows (need_top_grad=False, zero in_grad)."""
+    import numpy as np
+
+    proposal = _dev(proposal, "proposal")
+    gt_bbox = _dev(gt_bbox, "gt_bbox")
+    if proposal.dim() != 3 or proposal.shape[2] != 4 or gt_bbox.dim() != 3 or gt_bbox.shape[2] != 5 \
+            or gt_bbox.shape[0] != proposal.shape[0]:
+        raise ValueError("bbox_target: proposal (B,K,4), gt_bbox (B,M,5)")
+    if isinstance(add_gt_to_proposal, str):
+        add_gt_to_proposal = add_gt_to_proposal == "True"     # CustomOp kwargs arrive as strings
+    if isinstance(bbox_target_std, str):
+        from ast import literal_eval
+        bbox_target_std = literal_eval(bbox_target_std)
+    with torch.no_grad():
+        return _bbox_target_impl(proposal.detach(), gt_bbox.detach(), int(num_class), bool(add_gt_to_proposal),
+                                 int(image_rois), float(fg_fraction), float(fg_thresh), float(bg_thresh_hi),
+                                 float(bg_thresh_lo), bbox_target_std, rng if rng is not None else np.random,
+                                 bbox_overlaps)
+
+
 OPS = {
     "_contrib_ROIAlign_v2": ROIAlign_v2,
     "ROIPooling_v1": ROIPooling_v1,
@@ -1417,6 +1512,7 @@ OPS = {
     "assign_layer_fpn": assign_layer_fpn,  # mx.operator.register('assign_layer_fpn')
     "BboxPostProcessing": BboxPostProcessing,  # mx.operator.register('BboxPostProcessing')
     "decode_retina": decode_retina,            # mx.operator.register("decode_retina")
+    "bbox_target": bbox_target,                # mx.operator.register('bbox_target')
     # plain callables of operator_py (same names and argument meaning)
     "gpu_nms": gpu_nms,
     "greedy_nms": greedy_nms,
