@@ -501,6 +501,24 @@ int sdet_anchor_target(const float* im_info, const float* gt_bbox, int gt_stride
                        const uint32_t* priorities, unsigned long long seed, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Test-time mask paste: models/maskrcnn/utils.py:26-67 `segm_results` (expand_boxes :7-23, cv2.resize of the
+ * zero-ringed mask to the expanded integer box, `> 0.5`, paste into an im_h x im_w image, pycocotools
+ * `mask.encode` = column-major run lengths) without materialising the image.  boxes (N,4) float32 x1,y1,x2,y2 in
+ * image coordinates, cls (N) int32 index into the K mask channels (the background channel already removed, as
+ * mask_test.py:171 does), masks (N,K,M,M) float32 probabilities, M <= 62.
+ *   sdet_mask_paste_count: col_counts (N, im_w) int32; entry (n, j) = number of value flips the pasted mask of
+ *     detection n has in image column x_0(n) + j (x_0 = first pasted column; 0 for j past the pasted width), walking
+ *     the image in column-major order.
+ *   sdet_mask_paste_write: col_offsets (N, im_w) int64 = exclusive prefix sum of col_counts in row-major (n, j)
+ *     order; positions[col_offsets[n][j] + k] = flat column-major index x*im_h + y of the k-th flip of that column.
+ * The RLE counts of detection n are the differences of consecutive positions of rows (n, *), bracketed by 0 and
+ * im_h*im_w (first count = run of zeros, as pycocotools).  A box with no pixel inside the image, an inverted box or
+ * a class outside [0, K) pastes nothing (the reference raises on the first, pastes nothing on the second). */
+int sdet_mask_paste_count(const float* boxes, const int* cls, const float* masks, int N, int K, int M, int im_h,
+                          int im_w, int* col_counts, void* stream);
+int sdet_mask_paste_write(const float* boxes, const int* cls, const float* masks, int N, int K, int M, int im_h,
+                          int im_w, const long long* col_offsets, int* positions, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -465,3 +465,38 @@ def set_threads(n=None):
         except OSError:
             continue
     return 0
+
+
+# ---- test-time mask paste (oracle/paste_ops.c) ---------------------------------------------------------------------
+def resize_linear_f32(src, dsize):
+    """cv2.resize(src float32 (sh, sw), dsize=(dw, dh)) with the default INTER_LINEAR, as the installed wheel computes it."""
+    src = _f32(src)
+    dw, dh = int(dsize[0]), int(dsize[1])
+    dst = np.empty((dh, dw), np.float32)
+    lib().oracle_resize_linear_f32(_p(src), src.shape[0], src.shape[1], _p(dst), dh, dw)
+    return dst
+
+
+def segm_paste(box, mask, im_h, im_w):
+    """models/maskrcnn/utils.py:39-59 for one detection -> (im_mask (im_h, im_w) uint8, ok); ok False where the
+    reference's slice assignment cannot work (box entirely outside the image)."""
+    box, mask = _f32(box), _f32(mask)
+    M = mask.shape[-1]
+    rb = np.empty(4, np.int32)
+    lib().oracle_expand_box_int(_p(box), M, _p(rb))
+    w, h = max(int(rb[2] - rb[0]) + 1, 1), max(int(rb[3] - rb[1]) + 1, 1)
+    scratch = np.empty((M + 2) * (M + 2) + w * h, np.float32)
+    im = np.zeros((im_h, im_w), np.uint8)
+    rc = lib().oracle_segm_paste(_p(box), _p(mask), M, int(im_h), int(im_w), _p(im), _p(scratch))
+    return im, rc == 0
+
+
+def rle_encode(im):
+    """pycocotools rleEncode of one (h, w) uint8 mask -> run lengths (uint32), the first run counting zeros."""
+    im = np.ascontiguousarray(im, np.uint8)
+    h, w = im.shape
+    counts = np.empty(h * w + 1, np.uint32)
+    fn = lib().oracle_rle_encode
+    fn.restype = ctypes.c_long
+    k = fn(_p(im), h, w, _p(counts))
+    return counts[:k].copy()

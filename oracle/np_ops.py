@@ -356,3 +356,53 @@ def anchor_target(im_info, gt_bbox, strides, shorts, longs, scales, aspects, all
         wgts.append(all_wgt[o:o + n].reshape(fh * fw, A * 4).T)
         o += n
     return np.concatenate(labs, 1).reshape(-1), np.concatenate(tgts, 1), np.concatenate(wgts, 1)
+
+
+# ---- pycocotools RLE strings + segm_results (models/maskrcnn/utils.py:26-67) --------------------------------------
+def rle_to_string(counts):
+    """cocoapi common/maskApi.c rleToString (published algorithm; pycocotools absent here: parity unpinned): each
+    count, from the 4th on as the difference to the count two places back, in 5-bit groups, least significant first,
+    bit 5 = continuation, bit 4 of the last group = sign, + 48."""
+    out = bytearray()
+    cnts = [int(c) for c in counts]
+    for i, x in enumerate(cnts):
+        if i > 2:
+            x -= cnts[i - 2]
+        more = True
+        while more:
+            c = x & 0x1F
+            x >>= 5                      # arithmetic shift, like the C `long`
+            more = (x != -1) if (c & 0x10) else (x != 0)
+            if more:
+                c |= 0x20
+            out.append(c + 48)
+    return bytes(out)
+
+
+def rle_from_string(s):
+    """maskApi.c rleFrString: the inverse of rle_to_string."""
+    cnts, p, s = [], 0, bytes(s)
+    while p < len(s):
+        x, k, more = 0, 0, True
+        while more:
+            c = s[p] - 48
+            x |= (c & 0x1F) << (5 * k)
+            more = bool(c & 0x20)
+            p += 1
+            k += 1
+            if not more and (c & 0x10):
+                x |= -1 << (5 * k)
+        if len(cnts) > 2:
+            x += cnts[-2]
+        cnts.append(x)
+    return np.asarray(cnts, np.int64)
+
+
+def segm_results(bbox_xyxy, cls, masks, im_h, im_w):
+    """models/maskrcnn/utils.py:26-67 -> list of {'size': [im_h, im_w], 'counts': bytes} (what mask_util.encode
+    returns per mask); a box with no pixel inside the image (the reference raises there) gives the empty mask."""
+    out = []
+    for box, m, c in zip(np.asarray(bbox_xyxy, np.float32), masks, cls):
+        im, _ = oracle.segm_paste(box, m[int(c)], im_h, im_w)
+        out.append({"size": [int(im_h), int(im_w)], "counts": rle_to_string(oracle.rle_encode(im))})
+    return out

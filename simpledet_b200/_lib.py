@@ -91,6 +91,8 @@ _SIGNATURES = {
     "sdet_contrib_nms_workspace": [c_int, c_int, c_int],
     "sdet_contrib_nms": [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P, c_size_t, _P],
     "sdet_get_top_proposal": [_P, _P, _P, _P, c_int, c_int, c_int, _P],
+    "sdet_mask_paste_count": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "sdet_mask_paste_write": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
     "sdet_multiclass_nms_workspace": [c_int, c_int, c_int, c_int],
     "sdet_multiclass_nms": [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P,
                             _P, _P, c_size_t, _P],

@@ -1394,6 +1394,186 @@ def decode_retina(cls_probs, bbox_preds, im_info, stride, scales, ratios, per_le
     return boxes_out, score_out
 
 
+# --------------------------------------------------------------------------------------------
+# test-time mask paste + COCO result records  (models/maskrcnn/utils.py:26-67, mask_test.py:283-313,
+# detection_test.py:268-291)
+# --------------------------------------------------------------------------------------------
+def rle_counts_to_strings(counts, row_ptr):
+    """cocoapi maskApi.c rleToString for many masks at once, on the host (numpy): `counts` is the concatenation of
+    the masks' run lengths, mask n owning counts[row_ptr[n]:row_ptr[n+1]].  -> list of bytes, what
+    pycocotools.mask.encode puts under 'counts'.  Each count (from a mask's 4th on: its difference to the count two
+    places back) becomes 5-bit groups, least significant first, 0x20 = continuation, 0x10 of the last group = sign,
+    + 48."""
+    import numpy as np
+
+    counts = np.asarray(counts, np.int64)
+    row_ptr = np.asarray(row_ptr, np.int64)
+    n = counts.size
+    if n == 0:
+        return [b"" for _ in range(len(row_ptr) - 1)]
+    idx_in_row = np.arange(n, dtype=np.int64) - np.repeat(row_ptr[:-1], np.diff(row_ptr))
+    x = counts.copy()
+    d = idx_in_row > 2
+    x[d] -= counts[np.nonzero(d)[0] - 2]
+    chars = np.zeros((n, 13), np.uint8)           # 64-bit value: at most 13 groups of 5 bits
+    length = np.zeros(n, np.int64)
+    alive = np.ones(n, bool)
+    for k in range(13):
+        c = x & 0x1F
+        x = x >> 5                                # arithmetic shift on int64, like the C `long`
+        more = np.where((c & 0x10) != 0, x != -1, x != 0)
+        c = np.where(more, c | 0x20, c) + 48
+        chars[alive, k] = c[alive]
+        length[alive] = k + 1
+        alive = alive & more
+        if not alive.any():
+            break
+    keep = np.arange(13)[None, :] < length[:, None]
+    flat = chars[keep]                            # row-major: each count's characters in order
+    ends = np.cumsum(length)
+    char_ptr = np.concatenate([[0], ends])[row_ptr]
+    raw = flat.tobytes()
+    return [raw[char_ptr[i]:char_ptr[i + 1]] for i in range(len(row_ptr) - 1)]
+
+
+def _segm_results_impl(bbox_xyxy, cls, masks, im_h, im_w, count_fn, write_fn):
+    """The host side of `segm_results` around the two passes (count_fn / write_fn: the C-ABI calls on CUDA tensors in
+    the product, the host emulation of the same kernel source in tests/test_mask_paste_host.py)."""
+    import numpy as np
+
+    N = int(bbox_xyxy.shape[0])
+    im_h, im_w = int(im_h), int(im_w)
+    if N == 0:
+        return np.array([], dtype=object)
+    dev = bbox_xyxy.device
+    col_counts = torch.empty((N, im_w), device=dev, dtype=torch.int32)
+    count_fn(bbox_xyxy, cls, masks, col_counts)
+    incl = torch.cumsum(col_counts.reshape(-1).to(torch.int64), 0)
+    col_offsets = (incl - col_counts.reshape(-1)).contiguous()                 # exclusive scan, (N * im_w) int64
+    total = int(incl[-1].item())                                               # the one synchronisation
+    positions = torch.empty((max(total, 1),), device=dev, dtype=torch.int32)
+    if total:
+        write_fn(bbox_xyxy, cls, masks, col_offsets, positions)
+    per_det = col_counts.sum(1, dtype=torch.int64).cpu().numpy()               # flips per detection
+    pos = positions[:total].cpu().numpy().astype(np.int64)
+    # run lengths: differences of consecutive flip positions, bracketed by 0 and im_h * im_w
+    det_ptr = np.concatenate([[0], np.cumsum(per_det)])
+    row_ptr = det_ptr + np.arange(N + 1)                                        # one more count than flips per mask
+    ext = np.empty(total + 2 * N, np.int64)                                     # per mask: 0, its flips, im_h*im_w
+    ext_ptr = det_ptr + 2 * np.arange(N + 1)
+    is_flip = np.ones(total + 2 * N, bool)
+    is_flip[ext_ptr[:-1]] = False
+    is_flip[ext_ptr[1:] - 1] = False
+    ext[ext_ptr[:-1]] = 0
+    ext[ext_ptr[1:] - 1] = im_h * im_w
+    ext[is_flip] = pos
+    diffs = np.diff(ext)
+    keep = np.ones(diffs.size, bool)
+    keep[ext_ptr[1:-1] - 1] = False                                             # the differences across two masks
+    strings = rle_counts_to_strings(diffs[keep], row_ptr)
+    out = np.empty(N, dtype=object)
+    for i in range(N):
+        out[i] = {"size": [im_h, im_w], "counts": strings[i]}
+    return out
+
+
+def segm_results(bbox_xyxy, cls, masks, im_h, im_w):
+    """models/maskrcnn/utils.py:26-67 `segm_results` (the body of mask_test.py's pTest.process_output,
+    models/maskrcnn/process_output.py:6-19): bbox_xyxy (N,4) float32, cls (N) int, masks (N,K,M,M) float32 (background
+    channel already removed) -> numpy object array of N dicts {'size': [im_h, im_w], 'counts': bytes}, what
+    `pycocotools.mask.encode` returns for the pasted binary masks.  Inputs may be numpy arrays (copied to the
+    current CUDA device, like the reference's host arrays) or CUDA tensors.
+
+    expand_boxes, the int32 truncation, cv2.resize's bilinear interpolation (as the opencv-python wheel's IPP path
+    rounds it), `> 0.5` and the paste run in two launches that never materialise the im_h x im_w images: only the
+    positions where a pasted mask flips leave the device; the run-length strings are formed on the host.  A box with
+    no pixel inside the image gives the empty mask (the reference raises there)."""
+    import numpy as np
+
+    def dev_of(a, dtype):
+        t = torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a
+        if not t.is_cuda:
+            t = t.to(torch.device("cuda", torch.cuda.current_device()))
+        return t.to(dtype).contiguous()
+
+    boxes = _dev(dev_of(bbox_xyxy, torch.float32), "bbox_xyxy")
+    masks_t = _dev(dev_of(masks, torch.float32), "masks")
+    cls_t = _dev(dev_of(cls, torch.int32), "cls", dtype=torch.int32)
+    if boxes.dim() != 2 or boxes.shape[1] != 4 or masks_t.dim() != 4 or masks_t.shape[0] != boxes.shape[0] \
+            or masks_t.shape[2] != masks_t.shape[3] or cls_t.shape != (boxes.shape[0],):
+        raise ValueError("segm_results: bbox_xyxy (N,4), cls (N), masks (N,K,M,M)")
+    N, K, M = int(masks_t.shape[0]), int(masks_t.shape[1]), int(masks_t.shape[2])
+    L = _lib.lib()
+
+    def count_fn(b, c, m, col_counts):
+        check(L.sdet_mask_paste_count(_p(b), _p(c), _p(m), N, K, M, int(im_h), int(im_w), _p(col_counts), _stream()))
+
+    def write_fn(b, c, m, col_offsets, positions):
+        check(L.sdet_mask_paste_write(_p(b), _p(c), _p(m), N, K, M, int(im_h), int(im_w), _p(col_offsets),
+                                      _p(positions), _stream()))
+
+    return _segm_results_impl(boxes, cls_t, masks_t, im_h, im_w, count_fn, write_fn)
+
+
+def coco_bbox_records(image_id, dets_by_category, max_det_per_image):
+    """detection_test.py:268-289 for one image: dets_by_category {dataset category id: (n,5) float32 rows
+    [x1,y1,x2,y2,score]} (insertion order = the reference's class loop) -> the image's COCO result dicts, the
+    `max_det_per_image` best in ascending score order (Python's stable sort, then [-max:])."""
+    result = []
+    for cid, det in dets_by_category.items():
+        if det.shape[0] == 0:
+            continue
+        xs, ys = det[:, 0], det[:, 1]
+        ws, hs = det[:, 2] - xs + 1, det[:, 3] - ys + 1
+        scores = det[:, 4]
+        result += [{"image_id": int(image_id), "category_id": int(cid),
+                    "bbox": [float(xs[k]), float(ys[k]), float(ws[k]), float(hs[k])], "score": float(scores[k])}
+                   for k in range(det.shape[0])]
+    return sorted(result, key=lambda r: r["score"])[-int(max_det_per_image):]
+
+
+def coco_records_from_final_detections(image_ids, out, count, category_ids):
+    """The same records from `final_detections`' device result: out (B, max_det, 6) rows [x, y, w, h, score, class
+    index] ascending by score, count (B); category_ids = coco.getCatIds() (class index -> dataset id).  One
+    device-to-host copy; the rows are already the reference's selection and order."""
+    out_h, cnt_h = out.cpu().numpy(), count.cpu().numpy()
+    recs = []
+    for b, iid in enumerate(image_ids):
+        n = int(cnt_h[b])
+        rows = out_h[b, :n]                                             # the valid rows come first
+        recs += [{"image_id": int(iid), "category_id": int(category_ids[int(r[5])]),
+                  "bbox": [float(r[0]), float(r[1]), float(r[2]), float(r[3])], "score": float(r[4])} for r in rows]
+    return recs
+
+
+def coco_segm_records(image_id, dets_by_category, segms_by_category, mask_scores_by_category, max_det_per_image):
+    """mask_test.py:283-313 for one image: like coco_bbox_records plus 'mask_score' and 'segmentation' (the RLE dict
+    with its counts decoded to str)."""
+    result = []
+    for cid, det in dets_by_category.items():
+        if det.shape[0] == 0:
+            continue
+        seg, ms = segms_by_category[cid], mask_scores_by_category[cid]
+        xs, ys = det[:, 0], det[:, 1]
+        ws, hs = det[:, 2] - xs + 1, det[:, 3] - ys + 1
+        scores = det[:, -1]
+        result += [{"image_id": int(image_id), "category_id": int(cid),
+                    "bbox": [float(xs[k]), float(ys[k]), float(ws[k]), float(hs[k])], "score": float(scores[k]),
+                    "mask_score": float(ms[k]),
+                    "segmentation": {"size": seg[k]["size"], "counts": seg[k]["counts"].decode("utf8")}}
+                   for k in range(det.shape[0])]
+    return sorted(result, key=lambda r: r["score"])[-int(max_det_per_image):]
+
+
+def write_coco_json(coco_result, path):
+    """detection_test.py:286-290 / mask_test.py:317-321: json.dump(coco_result, f, sort_keys=True, indent=2)."""
+    import json
+
+    with open(path, "w") as f:
+        json.dump(coco_result, f, sort_keys=True, indent=2)
+
+
+
 def _bbox_target_impl(proposal, gt_bbox, num_class, add_gt_to_proposal, image_rois, fg_fraction, fg_thresh, bg_thresh_hi,
                       bg_thresh_lo, bbox_target_std, rng, overlaps):
     """The body of `bbox_target` over tensors on one device, with the IoU operator passed in (the product passes the
@@ -1513,6 +1693,7 @@ OPS = {
     "BboxPostProcessing": BboxPostProcessing,  # mx.operator.register('BboxPostProcessing')
     "decode_retina": decode_retina,            # mx.operator.register("decode_retina")
     "bbox_target": bbox_target,                # mx.operator.register('bbox_target')
+    "segm_results": segm_results,              # models/maskrcnn/utils.py:26
     # plain callables of operator_py (same names and argument meaning)
     "gpu_nms": gpu_nms,
     "greedy_nms": greedy_nms,

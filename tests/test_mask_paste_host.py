@@ -1,0 +1,191 @@
+"""Test-time mask paste (models/maskrcnn/utils.py:26-67) and the COCO result writers, on the CPU:
+  * the oracle's cv2.resize restatement against the installed cv2, bit for bit (skipped where cv2 is missing);
+  * the oracle's whole segm_results against vectors from the reference's own function run on cv2
+    (tests/golden/make_golden_mask_paste.py);
+  * the SOURCE of the two CUDA kernels (simpledet_b200/csrc/mask_paste_core.cuh) compiled for the host and run thread
+    by thread (tests/c_abi/mask_paste_emul.cc) under the product's own host logic (ops._segm_results_impl) against
+    the same vectors - the kernels were written after the round's GPU budget was spent;
+  * the run-length string codec (round trip, vectorised vs scalar) and the COCO record / JSON writers against the
+    reference's loops restated inline."""
+import ctypes
+import io
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import np_ops
+from simpledet_b200 import ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = np.load(os.path.join(ROOT, "tests", "golden", "reference_mask_paste.npz"))
+NAMES = [str(n) for n in G["names"]]
+
+
+def case(name):
+    im_h, im_w = (int(v) for v in G[f"{name}_hw"])
+    return im_h, im_w, G[f"{name}_box"], G[f"{name}_cls"], G[f"{name}_masks"], [bytes(c) for c in G[f"{name}_counts"]]
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emul") / "libmask_paste_emul.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17", "-I",
+                    os.path.join(ROOT, "simpledet_b200", "csrc"), "-o", so,
+                    os.path.join(ROOT, "tests", "c_abi", "mask_paste_emul.cc")], check=True)
+    return ctypes.CDLL(so)
+
+
+def run_emulated(emul, box, cls, masks, im_h, im_w):
+    N, K, M = masks.shape[0], masks.shape[1], masks.shape[2]
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+
+    def count_fn(b, c, m, col_counts):
+        assert emul.emul_mask_paste_count(P(b), P(c), P(m), N, K, M, im_h, im_w, P(col_counts)) == 0
+
+    def write_fn(b, c, m, col_offsets, positions):
+        assert col_offsets.dtype == torch.int64 and positions.dtype == torch.int32
+        assert emul.emul_mask_paste_write(P(b), P(c), P(m), N, K, M, im_h, im_w, P(col_offsets), P(positions)) == 0
+
+    return ops._segm_results_impl(torch.from_numpy(box).contiguous(), torch.from_numpy(cls.astype(np.int32)),
+                                  torch.from_numpy(masks).contiguous(), im_h, im_w, count_fn, write_fn)
+
+
+def test_resize_against_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for it in range(700):
+        s = 30 if it % 3 else 16
+        src = np.zeros((s, s), np.float32)
+        src[1:-1, 1:-1] = rng.random((s - 2, s - 2), dtype=np.float32)
+        dw, dh = (1 + it % 20, 1 + it // 20) if it < 400 else (int(rng.integers(1, 1400)), int(rng.integers(1, 900)))
+        assert np.array_equal(cv2.resize(src, (dw, dh)), oracle.resize_linear_f32(src, (dw, dh))), (s, dw, dh)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_against_the_reference_function(name):
+    im_h, im_w, box, cls, masks, want = case(name)
+    got = np_ops.segm_results(box, cls, masks, im_h, im_w)
+    assert [g["counts"] for g in got] == want
+    assert all(g["size"] == [im_h, im_w] for g in got)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_kernel_source_on_the_host_against_the_reference_function(emul, name):
+    im_h, im_w, box, cls, masks, want = case(name)
+    got = run_emulated(emul, box, cls, masks, im_h, im_w)
+    assert got.dtype == object and got.shape == (len(want),)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g["size"] == [im_h, im_w]
+        assert g["counts"] == w, (i, box[i], np_ops.rle_from_string(g["counts"])[:8], np_ops.rle_from_string(w)[:8])
+
+
+def test_kernel_source_on_the_host_random_boxes_against_the_oracle(emul):
+    """Many more geometries than the golden file holds: boxes hanging over every border, one-pixel boxes, boxes
+    entirely outside (empty mask here; the reference raises), an out-of-range class."""
+    rng = np.random.default_rng(3)
+    im_h, im_w, n, k, m = 150, 200, 160, 2, 28
+    xy = rng.uniform(-60, [im_w + 20, im_h + 20], (n, 2))
+    wh = np.where(rng.random((n, 2)) < 0.15, rng.uniform(0, 3, (n, 2)), rng.uniform(3, 260, (n, 2)))
+    box = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+    box[0] = [-500, -500, -400, -400]
+    box[1] = [im_w + 5, 10, im_w + 50, 60]
+    z = rng.standard_normal((n, k, m // 4, m // 4)).astype(np.float32)
+    masks = 1 / (1 + np.exp(-2 * np.kron(z, np.ones((4, 4), np.float32))))
+    masks = np.ascontiguousarray(masks, np.float32)
+    cls = rng.integers(0, k, n).astype(np.int32)
+    got = run_emulated(emul, box, cls, masks, im_h, im_w)
+    want = np_ops.segm_results(box, cls, masks, im_h, im_w)
+    nonempty = 0
+    for i in range(n):
+        assert got[i]["counts"] == want[i]["counts"], (i, box[i])
+        nonempty += len(np_ops.rle_from_string(want[i]["counts"])) > 1
+    assert nonempty > n // 2
+    assert np_ops.rle_from_string(got[0]["counts"]).tolist() == [im_h * im_w]      # entirely outside: one run of zeros
+    cls[5] = k                                                                     # not a channel of `masks`
+    assert np_ops.rle_from_string(run_emulated(emul, box, cls, masks, im_h, im_w)[5]["counts"]).tolist() == [im_h * im_w]
+
+
+def test_rle_strings():
+    rng = np.random.default_rng(1)
+    rows = [rng.integers(0, 5, 40), np.array([0, 7, 3, 1_000_000, 2, 5, 999_990, 12]), np.array([320 * 240]),
+            rng.integers(0, 2 ** 31 - 1, 9), np.array([0, 1])]
+    ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])])
+    got = ops.rle_counts_to_strings(np.concatenate(rows), ptr)
+    for g, r in zip(got, rows):
+        assert g == np_ops.rle_to_string(r)
+        assert np.array_equal(np_ops.rle_from_string(g), r)
+        assert all(48 <= b < 48 + 64 for b in g)
+    assert ops.rle_counts_to_strings(np.zeros(0, np.int64), np.array([0, 0])) == [b""]
+
+
+def reference_bbox_loop(output_dict, max_det_per_image):
+    """detection_test.py:268-289, restated as written."""
+    coco_result = []
+    for iid in output_dict:
+        result = []
+        for cid in output_dict[iid]["det_xyxys"]:
+            det = output_dict[iid]["det_xyxys"][cid]
+            if det.shape[0] == 0:
+                continue
+            scores = det[:, 4]
+            xs = det[:, 0]
+            ys = det[:, 1]
+            ws = det[:, 2] - xs + 1
+            hs = det[:, 3] - ys + 1
+            result += [{'image_id': int(iid), 'category_id': int(cid),
+                        'bbox': [float(xs[k]), float(ys[k]), float(ws[k]), float(hs[k])], 'score': float(scores[k])}
+                       for k in range(det.shape[0])]
+        result = sorted(result, key=lambda x: x['score'])[-max_det_per_image:]
+        coco_result += result
+    return coco_result
+
+
+def test_coco_writers(tmp_path):
+    rng = np.random.default_rng(2)
+    cat_ids = [1, 2, 3, 5, 8, 13]
+    output_dict = {}
+    for iid in (42, 7, 139):
+        dets = {}
+        for cid in cat_ids:
+            n = int(rng.integers(0, 9))
+            xy = rng.uniform(0, 300, (n, 2))
+            d = np.concatenate([xy, xy + rng.uniform(1, 90, (n, 2)), rng.random((n, 1))], 1).astype(np.float32)
+            if n > 2:
+                d[1, 4] = d[0, 4]                                   # a score tie inside a class
+            dets[cid] = d
+        dets[cat_ids[2]][:1, 4] = dets[cat_ids[0]][:1, 4] if dets[cat_ids[0]].shape[0] and dets[cat_ids[2]].shape[0] else 0.5
+        output_dict[iid] = {"det_xyxys": dets}
+    for max_det in (100, 10):
+        want = reference_bbox_loop(output_dict, max_det)
+        got = []
+        for iid in output_dict:
+            got += ops.coco_bbox_records(iid, output_dict[iid]["det_xyxys"], max_det)
+        assert got == want
+        path = tmp_path / f"r{max_det}.json"
+        ops.write_coco_json(got, str(path))
+        buf = io.StringIO()
+        json.dump(want, buf, sort_keys=True, indent=2)               # detection_test.py:286-290
+        assert path.read_text() == buf.getvalue()
+    # the mask variant (mask_test.py:283-313): same rows plus mask_score and the RLE with a str under 'counts'
+    iid = 42
+    dets = output_dict[iid]["det_xyxys"]
+    segs = {c: [{"size": [4, 5], "counts": np_ops.rle_to_string([3, 2, 15])} for _ in range(d.shape[0])] for c, d in dets.items()}
+    msc = {c: rng.random(d.shape[0]).astype(np.float32) for c, d in dets.items()}
+    recs = ops.coco_segm_records(iid, dets, segs, msc, 100)
+    base = ops.coco_bbox_records(iid, dets, 100)
+    assert [{k: r[k] for k in ("image_id", "category_id", "bbox", "score")} for r in recs] == base
+    assert all(isinstance(r["segmentation"]["counts"], str) and r["segmentation"]["size"] == [4, 5] for r in recs)
+    json.dumps(recs)
+
+
+def test_product_entry_point_needs_the_device():
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    im_h, im_w, box, cls, masks, _ = case(NAMES[0])
+    with pytest.raises(Exception):
+        ops.segm_results(box, cls, masks, im_h, im_w)

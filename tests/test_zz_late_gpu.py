@@ -27,3 +27,56 @@ def test_bbox_target_against_the_reference_operator(cuda):
         out = ops.OPS["bbox_target"](torch.from_numpy(G[f"{name}_prop"]).to(cuda),
                                      torch.from_numpy(G[f"{name}_gt"]).to(cuda), **kwargs_of(name))
         check_case(name, out)
+
+
+# ---- test-time mask paste (models/maskrcnn/utils.py:26-67) ----------------------------------------------------------
+def test_segm_results_against_the_reference_function(cuda):
+    """ops.segm_results on the device against the reference's own segm_results run on cv2
+    (tests/golden/make_golden_mask_paste.py); numpy inputs, like the reference's host arrays."""
+    from test_mask_paste_host import NAMES, case
+
+    for name in NAMES:
+        im_h, im_w, box, cls, masks, want = case(name)
+        got = ops.OPS["segm_results"](box, cls, masks, im_h, im_w)
+        assert [g["counts"] for g in got] == want, name
+        assert all(g["size"] == [im_h, im_w] for g in got)
+
+
+def test_segm_results_at_test_size_against_the_oracle(cuda):
+    """100 detections on an 800 x 1333 image (mask_r50v1_fpn_1x's test size), CUDA tensors in."""
+    from oracle import np_ops
+
+    rng = np.random.default_rng(9)
+    im_h, im_w, n, k, m = 800, 1333, 100, 80, 28
+    xy = rng.uniform(-10, [im_w - 40, im_h - 40], (n, 2))
+    wh = rng.uniform(12, [700, 500], (n, 2))
+    box = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+    box[0] = [-3.0, -2.0, im_w + 2.0, im_h + 1.0]
+    z = rng.standard_normal((n, 7, 7)).astype(np.float32)
+    one = (1 / (1 + np.exp(-2 * np.kron(z, np.ones((4, 4), np.float32))))).astype(np.float32)
+    cls = rng.integers(0, k, n).astype(np.int32)
+    masks = np.zeros((n, k, m, m), np.float32)
+    masks[np.arange(n), cls] = one
+    got = ops.segm_results(torch.from_numpy(box).to(cuda), torch.from_numpy(cls).to(cuda),
+                           torch.from_numpy(masks).to(cuda), im_h, im_w)
+    want = np_ops.segm_results(box, cls, masks, im_h, im_w)
+    for i in range(n):
+        assert got[i]["counts"] == want[i]["counts"], (i, box[i])
+
+
+def test_coco_records_from_final_detections(cuda):
+    from oracle import np_ops
+
+    rng = np.random.default_rng(4)
+    B, N, K = 2, 300, 6
+    score = rng.random((B, N, K)).astype(np.float32) * (rng.random((B, N, K)) < 0.2)
+    xy = rng.uniform(0, 500, (B, N, K, 2))
+    bbox = np.concatenate([xy, xy + rng.uniform(10, 200, (B, N, K, 2))], -1).reshape(B, N, K * 4).astype(np.float32)
+    out, cnt = ops.final_detections(torch.from_numpy(score).to(cuda), torch.from_numpy(bbox).to(cuda), 0.5, 0.05, 100)
+    cats = [1, 2, 3, 5, 8, 13]
+    recs = ops.coco_records_from_final_detections([11, 12], out, cnt, cats)
+    want = []
+    for b, iid in enumerate((11, 12)):
+        per = np_ops.do_nms(score[b], bbox[b], 0.5, 0.05)
+        want += ops.coco_bbox_records(iid, {cats[c]: d for c, d in per.items()}, 100)
+    assert recs == want
