@@ -152,6 +152,35 @@ def _same(a, ins, names):
     return ins, [ins[0]]
 
 
+def _shape_elemwise(a, ins, names):
+    """Binary elementwise: an input whose shape is not known yet (a label variable) takes the other's."""
+    known = next((i for i in ins if i is not None), None)
+    ins = [known if i is None else i for i in ins]
+    return ins, [known]
+
+
+def _shape_softmax_output(a, ins, names):
+    d = ins[0]
+    if len(ins) > 1 and ins[1] is None:  # SoftmaxOutputProp::InferShape: the label's shape follows from the data's
+        ins = [d, (d[0],) + tuple(d[2:]) if _b(a.get("multi_output", False)) else (d[0],)] + list(ins[2:])
+    return ins, [d]
+
+
+def _shape_focal_loss(a, ins, names):
+    d = ins[0]
+    if len(ins) > 1 and ins[1] is None:  # focal_loss-inl.h InferShape: label (batch, anchors) from data (batch, anchors, classes)
+        ins = [d, (d[0], d[1])] + list(ins[2:])
+    return ins, [d]
+
+
+def _shape_proposal_target(a, ins, names):
+    B, R, C = int(_t(a["batch_images"])), int(_t(a["image_rois"])), int(_t(a["num_classes"]))
+    outs = [(B, R, 4), (B, R), (B, R, 4 * C), (B, R, 4 * C)]
+    if _b(a.get("output_iou", False)):
+        outs.append((B, R))
+    return ins, outs
+
+
 def _shape_concat(a, ins, names):
     d = int(_t(a.get("dim", 1)))
     out = list(ins[0])
@@ -210,6 +239,9 @@ def _shape_custom(a, ins, names):
     if t == "BboxPostProcessing":
         B, m = ins[0][0], int(_t(a["max_det_per_image"]))
         return ins, [(B, m, 1), (B, m, 4), (B, m, 1)]
+    if t == "bbox_target":
+        B, R, C = ins[0][0], int(_t(a["image_rois"])), int(_t(a["num_class"]))
+        return ins, [(B, R, 4), (B, R), (B, R, 4 * C), (B, R, 4 * C)]
     if t == "decode_retina":
         n_in = len(ins)
         raise NotImplementedError("decode_retina through the symbol graph (the builder prefers GenProposalRetina)")
@@ -219,9 +251,11 @@ def _shape_custom(a, ins, names):
 SHAPE_RULES = {
     "Convolution": _shape_conv, "FullyConnected": _shape_fc, "BatchNorm": _shape_bn, "Pooling": _shape_pool,
     "Activation": _same, "relu": _same, "Cast": _same, "BlockGrad": _same, "softmax": _same, "SoftmaxActivation": _same,
-    "SoftmaxOutput": _same, "Dropout": _same, "MakeLoss": _same, "smooth_l1": _same, "identity": _same,
+    "SoftmaxOutput": _shape_softmax_output, "Dropout": _same, "MakeLoss": _same, "smooth_l1": _same, "identity": _same,
     "_plus_scalar": _same, "_minus_scalar": _same, "_mul_scalar": _same, "_div_scalar": _same,
-    "elemwise_add": _same, "elemwise_sub": _same, "elemwise_mul": _same, "elemwise_div": _same, "add_n": _same,
+    "elemwise_add": _shape_elemwise, "elemwise_sub": _shape_elemwise, "elemwise_mul": _shape_elemwise,
+    "elemwise_div": _shape_elemwise, "add_n": _same, "ProposalTarget": _shape_proposal_target,
+    "_contrib_FocalLoss": _shape_focal_loss, "_contrib_BBoxNorm": _same,
     "broadcast_add": _same, "broadcast_mul": _same,
     "Concat": _shape_concat, "UpSampling": _shape_upsample, "slice_like": _shape_slice_like, "slice_axis": _shape_slice_axis,
     "Reshape": lambda a, ins, n: (ins, [mx_reshape(ins[0], a["shape"])]),
@@ -282,10 +316,16 @@ class Executor:
     channels_last memory format (what the tensor-core convolutions prefer) and hands the FPN levels to the fused
     RoIAlign as NHWC - no re-layout pass."""
 
-    def __init__(self, sym: S.Symbol, device="cuda:0", channels_last=True, fuse_fpn_roi_align=True, fold_bn=True):
+    def __init__(self, sym: S.Symbol, device="cuda:0", channels_last=True, fuse_fpn_roi_align=True, fold_bn=True,
+                 is_train=False):
         import torch
 
         self.sym, self.device = sym, torch.device(device)
+        # is_train: MXNet's forward(is_train=True) - loss operators get their MXNet backward (facade/train.py),
+        # RoIAlign goes through the autograd operators, BatchNorm without use_global_stats uses batch statistics,
+        # frozen BatchNorm is NOT folded into the convolution (the convolution's weights are being trained)
+        self.is_train = bool(is_train)
+        fold_bn = fold_bn and not self.is_train
         self.channels_last, self.fuse, self.fold_bn = channels_last, fuse_fpn_roi_align, fold_bn
         self.params: dict = {}
         self.order = sym._topo()
@@ -428,7 +468,10 @@ class Executor:
                     feats.append(vals[id(fn)][fi])
                 ph, pw = _tup(ras[0].attrs["pooled_size"])
                 scale0, lvl0 = int(_t(asg.attrs["roi_canonical_scale"])), int(_t(asg.attrs["roi_canonical_level"]))
-                if self.channels_last and all(f.is_contiguous(memory_format=torch.channels_last) for f in feats):
+                if self.is_train:   # the autograd operator: gradients flow into every FPN level
+                    out = ops.fpn_roi_align([f.contiguous() for f in feats], rois.contiguous(), tuple(strides), (ph, pw),
+                                            scale0, lvl0)
+                elif self.channels_last and all(f.is_contiguous(memory_format=torch.channels_last) for f in feats):
                     out, _ = ops.fpn_roi_align_nhwc([f.permute(0, 2, 3, 1) for f in feats], rois.contiguous(), strides,
                                                     (ph, pw), scale0, lvl0)
                 else:
@@ -510,6 +553,10 @@ class Executor:
             if self._folded and id(node) in self._folded_bn:
                 return [data]  # already applied by the convolution that feeds it
             g = torch.ones_like(arg["gamma"]) if _b(a.get("fix_gamma", True)) else arg["gamma"]
+            if self.is_train and not _b(a.get("use_global_stats", False)):
+                # batch statistics; MXNet's momentum weighs the OLD moving value, torch's the new batch value
+                return [F.batch_norm(data, arg["moving_mean"], arg["moving_var"], g, arg["beta"], True,
+                                     1.0 - float(_t(a.get("momentum", 0.9))), float(_t(a.get("eps", 1e-3))))]
             return [F.batch_norm(data, arg["moving_mean"], arg["moving_var"], g, arg["beta"], False, 0.0,
                                  float(_t(a.get("eps", 1e-3))))]
         if op in ("Activation", "relu"):
@@ -523,6 +570,23 @@ class Executor:
             if str(a.get("pool_type", "max")) == "max":
                 return [F.max_pool2d(x[0], k, s, p, ceil_mode=ceil)]
             return [F.avg_pool2d(x[0], k, s, p, ceil_mode=ceil)]
+        if self.is_train and op in ("SoftmaxOutput", "MakeLoss", "BlockGrad", "smooth_l1"):
+            from . import train as T
+
+            if op == "SoftmaxOutput":
+                return [T.softmax_output(arg.get("data", x[0]), arg.get("label", x[1]), _b(a.get("multi_output", False)),
+                                         str(a.get("normalization", "null")), _b(a.get("use_ignore", False)),
+                                         float(_t(a.get("ignore_label", -1))), float(_t(a.get("grad_scale", 1.0))))]
+            if op == "MakeLoss":
+                return [T.make_loss(x[0], float(_t(a.get("grad_scale", 1.0))), str(a.get("normalization", "null")),
+                                    float(_t(a.get("valid_thresh", 0.0))))]
+            if op == "BlockGrad":
+                return [x[0].detach()]
+            return [T.smooth_l1(x[0], float(_t(a.get("scalar", 1.0))))]
+        if op == "smooth_l1":
+            from . import train as T
+
+            return [T.smooth_l1(x[0], float(_t(a.get("scalar", 1.0))))]
         if op in ("Cast", "BlockGrad", "identity", "Dropout", "MakeLoss"):
             return [x[0]]
         if op == "UpSampling":
@@ -617,6 +681,31 @@ class Executor:
                             feature_stride=int(_t(a.get("feature_stride", 16))), output_score=True,
                             iou_loss=_b(a.get("iou_loss", False)))
             return list(r)
+        if op == "_contrib_ROIAlign_v2" and self.is_train:
+            out = ops.OPS[op](arg["data"].contiguous(), arg["rois"].contiguous(), _tup(a["pooled_size"]),
+                              float(_t(a["spatial_scale"])))
+            return [out, out, out]   # argmax_x / argmax_y are not visible outputs of the symbol
+        if op == "ProposalTarget":
+            kw = dict(num_classes=int(_t(a["num_classes"])), batch_images=int(_t(a["batch_images"])),
+                      image_rois=int(_t(a["image_rois"])), fg_thresh=float(_t(a["fg_thresh"])),
+                      bg_thresh_hi=float(_t(a["bg_thresh_hi"])), bg_thresh_lo=float(_t(a["bg_thresh_lo"])),
+                      proposal_without_gt=_b(a.get("proposal_without_gt", False)),
+                      fg_fraction=float(_t(a.get("fg_fraction", 0.25))), class_agnostic=_b(a.get("class_agnostic", False)),
+                      output_iou=_b(a.get("output_iou", False)),
+                      bbox_mean=tuple(float(v) for v in _t(a.get("bbox_mean", (0, 0, 0, 0)))),
+                      bbox_std=tuple(float(v) for v in _t(a.get("bbox_std", (0.1, 0.1, 0.2, 0.2)))),
+                      bbox_weight=tuple(float(v) for v in _t(a.get("bbox_weight", (1, 1, 1, 1)))))
+            with torch.no_grad():   # ProposalTargetProp: no gradient to either input
+                return list(ops.OPS[op](arg.get("rois", x[0]).detach().contiguous(),
+                                        arg.get("gt_boxes", x[1]).detach().contiguous(), **kw))
+        if op == "_contrib_FocalLoss":
+            return [ops.OPS[op](arg.get("data", x[0]).contiguous(), arg.get("label", x[1]).contiguous(),
+                                alpha=float(_t(a.get("alpha", 0.25))), gamma=float(_t(a.get("gamma", 2.0))),
+                                normalization=str(a.get("normalization", "null")),
+                                grad_scale=float(_t(a.get("grad_scale", 1.0))))]
+        if op == "_contrib_BBoxNorm":
+            return [ops.OPS[op](arg.get("data", x[0]).contiguous(), arg.get("label", x[1]).contiguous(),
+                                normalization=str(a.get("normalization", "valid")))]
         if op == "_contrib_ROIAlign_v2":
             out, ax, ay = ops.roi_align_v2_raw(arg["data"].contiguous(), arg["rois"].contiguous(), _tup(a["pooled_size"]),
                                                float(_t(a["spatial_scale"])), with_argmax=False)
@@ -632,6 +721,11 @@ class Executor:
             if t == "assign_layer_fpn":
                 return list(ops.OPS[t](x[0].contiguous(), tuple(_t(a["rcnn_stride"])), int(_t(a["roi_canonical_scale"])),
                                        int(_t(a["roi_canonical_level"]))))
+            if t == "bbox_target":
+                return list(ops.OPS[t](x[0].contiguous(), x[1].contiguous(), int(_t(a["num_class"])),
+                                       _b(a["add_gt_to_proposal"]), int(_t(a["image_rois"])), float(_t(a["fg_fraction"])),
+                                       float(_t(a["fg_thresh"])), float(_t(a["bg_thresh_hi"])), float(_t(a["bg_thresh_lo"])),
+                                       tuple(float(v) for v in _t(a["bbox_target_std"]))))
             if t == "BboxPostProcessing":
                 return list(ops.OPS[t](x[0].contiguous(), x[1].contiguous(), int(_t(a["max_det_per_image"])),
                                        float(_t(a["min_det_score"])), str(a.get("nms_type", "nms")), float(_t(a["nms_thr"]))))

@@ -80,3 +80,67 @@ def test_coco_records_from_final_detections(cuda):
         per = np_ops.do_nms(score[b], bbox[b], 0.5, 0.05)
         want += ops.coco_bbox_records(iid, {cats[c]: d for c, d in per.items()}, 100)
     assert recs == want
+
+
+# ---- the reference's TRAIN graphs through the façade Trainer, real operators --------------------------------------------
+def test_faster_rcnn_fpn_train_step_on_the_device(cuda):
+    """config/faster_r50v1_fpn_1x.py's train symbol (fixture written by the reference's own builders on the façade):
+    forward + backward + MXNet SGD update on the device - Proposal_v3 x 5, get_top_proposal, ProposalTarget, the fused
+    FPN RoIAlign (autograd), SoftmaxOutput / smooth_l1 / MakeLoss with MXNet's gradients."""
+    from simpledet_b200.facade import symbol as S
+    from simpledet_b200.facade import train as T
+
+    sym = S.fromjson(open(os.path.join(GOLD, "faster_r50v1_fpn_1x_train_symbol.json")).read())
+    B, H, W = 2, 256, 384
+    shapes = dict(data=(B, 3, H, W), im_info=(B, 3), gt_bbox=(B, 100, 5))
+    labels = ("rpn_cls_label", "rpn_reg_target", "rpn_reg_weight")
+    tr = T.Trainer(sym, shapes, device=cuda, fixed_param=("conv0", "stage1", "gamma", "beta"), rng_std=0.02,
+                   label_names=labels)
+    s_total = sum((H // st) * (W // st) for st in (4, 8, 16, 32, 64))
+    g = torch.Generator().manual_seed(0)
+    gt = torch.full((B, 100, 5), -1.0)
+    for b in range(B):
+        xy = torch.rand(6, 2, generator=g) * torch.tensor([W - 120.0, H - 120.0])
+        gt[b, :6, :4] = torch.cat([xy, xy + 30 + torch.rand(6, 2, generator=g) * 80], 1)
+        gt[b, :6, 4] = torch.randint(1, 81, (6,), generator=g).float()
+    feed = dict(data=torch.randn(shapes["data"], generator=g), im_info=torch.tensor([[H, W, 1.0]] * B), gt_bbox=gt,
+                rpn_cls_label=torch.randint(-1, 2, (B, 3, s_total), generator=g).float(),
+                rpn_reg_target=torch.randn(B, 12, s_total, generator=g),
+                rpn_reg_weight=(torch.rand(B, 12, s_total, generator=g) < 0.1).float())
+    before = tr.ex.params["bbox_fc1_weight"].detach().clone()
+    for _ in range(2):
+        outs = tr.forward_backward(**feed)
+        assert all(torch.isfinite(o).all() for o in outs)
+        grads = tr.grads()
+        assert set(grads) == set(tr.trainable) and all(torch.isfinite(v).all() for v in grads.values())
+        assert float(grads["stage2_unit1_conv1_weight"].abs().sum()) > 0 and float(grads["P2_lateral_weight"].abs().sum()) > 0
+        tr.update(lr=0.001, momentum=0.9, wd=1e-4, rescale_grad=1.0)
+    assert tuple(outs[3].shape) == (B * 512, 81) and tuple(outs[5].shape) == (B, 512)
+    assert not torch.equal(before, tr.ex.params["bbox_fc1_weight"].detach())
+
+
+def test_retinanet_train_step_on_the_device(cuda):
+    from simpledet_b200.facade import executor as E
+    from simpledet_b200.facade import symbol as S
+    from simpledet_b200.facade import train as T
+
+    sym = S.fromjson(open(os.path.join(GOLD, "retina_r50v1_fpn_1x_train_symbol.json")).read())
+    B, H, W = 2, 256, 384
+    shapes = dict(data=(B, 3, H, W))
+    byname = dict(zip(sym.list_arguments(), E.infer_shapes(sym, shapes)[0]))
+    labels = ("rpn_cls_label", "rpn_reg_target", "rpn_reg_weight")
+    tr = T.Trainer(sym, shapes, device=cuda, fixed_param=("conv0", "stage1", "gamma", "beta"), rng_std=0.02,
+                   label_names=labels)
+    g = torch.Generator().manual_seed(0)
+    n_anchor = byname["rpn_cls_label"][1]
+    cls = torch.zeros(byname["rpn_cls_label"])
+    cls[:, torch.randperm(n_anchor, generator=g)[:60]] = torch.randint(1, 81, (60,), generator=g).float()
+    cls[:, torch.randperm(n_anchor, generator=g)[:200]] = -1.0
+    feed = dict(data=torch.randn(shapes["data"], generator=g), rpn_cls_label=cls,
+                rpn_reg_target=torch.randn(byname["rpn_reg_target"], generator=g),
+                rpn_reg_weight=(torch.rand(byname["rpn_reg_weight"], generator=g) < 0.02).float())
+    outs = tr.forward_backward(**feed)
+    grads = tr.grads()
+    assert all(torch.isfinite(o).all() for o in outs) and set(grads) == set(tr.trainable)
+    assert all(torch.isfinite(v).all() for v in grads.values())
+    assert sum(float(v.abs().sum()) > 0 for v in grads.values()) > 0.9 * len(grads)
