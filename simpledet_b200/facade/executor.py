@@ -173,6 +173,53 @@ def _shape_focal_loss(a, ins, names):
     return ins, [d]
 
 
+def _shape_proposal_mask_target(a, ins, names):
+    B, R, C = int(_t(a["batch_images"])), int(_t(a["image_rois"])), int(_t(a["num_classes"]))
+    M, nfg = int(_t(a["mask_size"])), int(int(_t(a["image_rois"])) * float(_t(a.get("fg_fraction", 0.25))))
+    outs = [(B, R, 4), (B, R), (B, R, 4 * C), (B, R, 4 * C)]
+    if _b(a.get("output_iou", False)):
+        outs.append((B, R))
+    outs.append((B, nfg, M, M))
+    if _b(a.get("output_ratio", False)):
+        outs.append((B, nfg))
+    return ins, outs
+
+
+def _shape_split(a, ins, names):
+    n, ax = int(_t(a["num_outputs"])), int(_t(a.get("axis", 1)))
+    d = list(ins[0])
+    ax %= len(d)
+    d[ax] //= n
+    if _b(a.get("squeeze_axis", False)):
+        d.pop(ax)
+    return ins, [tuple(d)] * n
+
+
+def _arange_len(a):
+    start, stop = float(_t(a.get("start", 0))), a.get("stop")
+    stop = None if stop in (None, "None") else float(_t(stop))
+    if stop is None:
+        start, stop = 0.0, start
+    return start, stop, float(_t(a.get("step", 1.0))), int(_t(a.get("repeat", 1)))
+
+
+def _shape_arange(a, ins, names):
+    start, stop, step, rep = _arange_len(a)
+    return ins, [(max(0, math.ceil((stop - start) / step)) * rep,)]
+
+
+def _shape_stack(a, ins, names):
+    ax = int(_t(a.get("axis", 0)))
+    d = list(ins[0])
+    d.insert(ax % (len(d) + 1), len(ins))
+    return ins, [tuple(d)]
+
+
+def _shape_gather_nd(a, ins, names):
+    d, i = ins
+    return ins, [tuple(i[1:]) + tuple(d[i[0]:])]
+
+
 def _shape_proposal_target(a, ins, names):
     B, R, C = int(_t(a["batch_images"])), int(_t(a["image_rois"])), int(_t(a["num_classes"]))
     outs = [(B, R, 4), (B, R), (B, R, 4 * C), (B, R, 4 * C)]
@@ -256,6 +303,9 @@ SHAPE_RULES = {
     "elemwise_add": _shape_elemwise, "elemwise_sub": _shape_elemwise, "elemwise_mul": _shape_elemwise,
     "elemwise_div": _shape_elemwise, "add_n": _same, "ProposalTarget": _shape_proposal_target,
     "_contrib_FocalLoss": _shape_focal_loss, "_contrib_BBoxNorm": _same,
+    "ProposalMaskTarget": _shape_proposal_mask_target, "_contrib_SigmoidCrossEntropy": lambda a, ins, n: (ins, [(ins[0][0],)]),
+    "split": _shape_split, "SliceChannel": _shape_split, "arange": _shape_arange, "_arange": _shape_arange,
+    "stack": _shape_stack, "gather_nd": _shape_gather_nd, "concat": _shape_concat,
     "broadcast_add": _same, "broadcast_mul": _same,
     "Concat": _shape_concat, "UpSampling": _shape_upsample, "slice_like": _shape_slice_like, "slice_axis": _shape_slice_axis,
     "Reshape": lambda a, ins, n: (ins, [mx_reshape(ins[0], a["shape"])]),
@@ -620,8 +670,20 @@ class Executor:
             return [{"_plus_scalar": lambda v: v + s, "_mul_scalar": lambda v: v * s,
                      "_minus_scalar": lambda v: (s - v) if rev else (v - s),
                      "_div_scalar": lambda v: (s / v) if rev else (v / s)}[op](x[0])]
-        if op == "Concat":
+        if op in ("Concat", "concat"):
             return [torch.cat(x, int(_t(a.get("dim", 1))))]
+        if op in ("split", "SliceChannel"):
+            n, ax = int(_t(a["num_outputs"])), int(_t(a.get("axis", 1)))
+            parts = torch.chunk(x[0], n, ax)
+            return [p.squeeze(ax) for p in parts] if _b(a.get("squeeze_axis", False)) else list(parts)
+        if op in ("arange", "_arange"):
+            start, stop, step, rep = _arange_len(a)
+            return [torch.arange(start, stop, step, device=self.device, dtype=torch.float32).repeat_interleave(rep)]
+        if op == "stack":
+            return [torch.stack(x, int(_t(a.get("axis", 0))))]
+        if op == "gather_nd":   # data[indices[0], indices[1], ...]: the mask channel of each roi's class
+            idx = x[1].to(torch.long)
+            return [x[0][tuple(idx[i] for i in range(idx.shape[0]))]]
         if op == "Reshape":
             return [x[0].reshape(mx_reshape(tuple(x[0].shape), a["shape"]))]
         if op == "Flatten":
@@ -698,6 +760,22 @@ class Executor:
             with torch.no_grad():   # ProposalTargetProp: no gradient to either input
                 return list(ops.OPS[op](arg.get("rois", x[0]).detach().contiguous(),
                                         arg.get("gt_boxes", x[1]).detach().contiguous(), **kw))
+        if op == "ProposalMaskTarget":
+            kw = dict(num_classes=int(_t(a["num_classes"])), batch_images=int(_t(a["batch_images"])),
+                      image_rois=int(_t(a["image_rois"])), mask_size=int(_t(a["mask_size"])),
+                      fg_thresh=float(_t(a["fg_thresh"])), bg_thresh_hi=float(_t(a["bg_thresh_hi"])),
+                      bg_thresh_lo=float(_t(a["bg_thresh_lo"])), proposal_without_gt=_b(a.get("proposal_without_gt", False)),
+                      fg_fraction=float(_t(a.get("fg_fraction", 0.25))), class_agnostic=_b(a.get("class_agnostic", False)),
+                      output_iou=_b(a.get("output_iou", False)), output_ratio=_b(a.get("output_ratio", False)),
+                      bbox_mean=tuple(float(v) for v in _t(a.get("bbox_mean", (0, 0, 0, 0)))),
+                      bbox_std=tuple(float(v) for v in _t(a.get("bbox_std", (0.1, 0.1, 0.2, 0.2)))),
+                      bbox_weight=tuple(float(v) for v in _t(a.get("bbox_weight", (1, 1, 1, 1)))))
+            with torch.no_grad():
+                return list(ops.OPS[op](arg.get("rois", x[0]).detach().contiguous(),
+                                        arg.get("gt_boxes", x[1]).detach().contiguous(),
+                                        arg.get("gt_polys", x[2]).detach().contiguous(), **kw))
+        if op == "_contrib_SigmoidCrossEntropy":
+            return [ops.OPS[op](x[0].contiguous(), x[1].contiguous(), grad_scale=float(_t(a.get("grad_scale", 1.0))))]
         if op == "_contrib_FocalLoss":
             return [ops.OPS[op](arg.get("data", x[0]).contiguous(), arg.get("label", x[1]).contiguous(),
                                 alpha=float(_t(a.get("alpha", 0.25))), gamma=float(_t(a.get("gamma", 2.0))),

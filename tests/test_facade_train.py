@@ -118,8 +118,8 @@ def _train_stubs(monkeypatch, log):
                 (torch.rand(B, R, 4 * num_classes, generator=g) < 0.05).float())
 
     def fpn_roi_align(feats, rois, strides, out_size, scale0, lvl0):
-        assert len(feats) == len(strides) == 4 and all(f.requires_grad for f in feats)
-        log.append(("fpn_roi_align", tuple(out_size)))
+        assert len(feats) == len(strides) == 4 and all(f.requires_grad for f in feats) and not rois.requires_grad
+        log.append(("fpn_roi_align", tuple(out_size), rois.shape[1]))
         pooled = sum(torch.nn.functional.adaptive_avg_pool2d(f, out_size) for f in feats)     # (B, C, ph, pw)
         return pooled[:, None].expand(-1, rois.shape[1], -1, -1, -1) * (1 + 0 * rois.sum(-1)[..., None, None, None])
 
@@ -132,6 +132,27 @@ def _train_stubs(monkeypatch, log):
         log.append(("bbox_norm", tuple(data.shape)))
         return data
 
+    def proposal_mask_target(rois, gt_boxes, gt_polys, num_classes, batch_images, image_rois, mask_size, fg_thresh,
+                             bg_thresh_hi, bg_thresh_lo, proposal_without_gt, fg_fraction, class_agnostic, output_iou,
+                             output_ratio, bbox_mean, bbox_std, bbox_weight):
+        assert output_iou and not output_ratio and gt_polys.shape[:2] == gt_boxes.shape[:2]
+        base = proposal_target(rois, gt_boxes, num_classes, batch_images, image_rois, fg_thresh, bg_thresh_hi, bg_thresh_lo,
+                               proposal_without_gt, fg_fraction, class_agnostic, output_iou, bbox_mean, bbox_std, bbox_weight)
+        nfg = int(image_rois * fg_fraction)
+        log.append(("proposal_mask_target", nfg, mask_size))
+        g = torch.Generator().manual_seed(2)
+        tgt = torch.randint(-1, 2, (batch_images, nfg, mask_size, mask_size), generator=g).float()
+        return (*base, torch.rand(batch_images, image_rois, generator=g), tgt)
+
+    def sigmoid_ce(data, label, grad_scale):
+        assert data.requires_grad and data.shape == label.shape and data.dim() == 2
+        log.append(("sigmoid_ce", tuple(data.shape)))
+        keep = (label >= 0).float()
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(data, label.clamp(min=0), weight=keep, reduction="none")
+        return T.make_loss(loss.sum(1) / keep.sum(1).clamp(min=1), grad_scale)
+
+    monkeypatch.setitem(ops.OPS, "ProposalMaskTarget", proposal_mask_target)
+    monkeypatch.setitem(ops.OPS, "_contrib_SigmoidCrossEntropy", sigmoid_ce)
     for k, fn in {"_contrib_Proposal_v3": proposal, "get_top_proposal": get_top_proposal, "ProposalTarget": proposal_target,
                   "_contrib_FocalLoss": focal_loss, "_contrib_BBoxNorm": bbox_norm}.items():
         monkeypatch.setitem(ops.OPS, k, fn)
@@ -170,7 +191,7 @@ def test_faster_rcnn_fpn_train_graph_through_the_trainer(monkeypatch):
     res = tr.forward_backward(**feed)
     assert [tuple(o.shape) for o in res] == outs and all(torch.isfinite(o).all() for o in res)
     assert sorted(e[1] for e in log if e[0] == "proposal") == [4, 8, 16, 32, 64]
-    assert ("proposal_target", 512) in log and ("fpn_roi_align", (7, 7)) in log
+    assert ("proposal_target", 512) in log and ("fpn_roi_align", (7, 7), 512) in log
     grads = tr.grads()
     assert set(grads) == set(tr.trainable)                                      # every trainable parameter got one
     for name in ("stage2_unit1_conv1_weight", "stage4_unit3_conv3_weight", "P2_lateral_weight", "rpn_conv_weight",
@@ -209,3 +230,33 @@ def test_retinanet_train_graph_through_the_trainer(monkeypatch):
     grads = tr.grads()
     assert set(grads) == set(tr.trainable)
     assert sum(float(v.abs().sum()) > 0 for v in grads.values()) > 0.9 * len(grads)
+
+
+def test_mask_rcnn_train_graph_through_the_trainer(monkeypatch):
+    """models/maskrcnn/builder.py:184-320: ProposalMaskTarget's six outputs, the first 128 rois of each image into the
+    14x14 RoIAlign, split / arange / stack / gather_nd picking each roi's class channel, SigmoidCrossEntropy."""
+    sym = S.fromjson(open(os.path.join(ROOT, "tests", "golden", "mask_r50v1_fpn_1x_train_symbol.json")).read())
+    B, H, W = 2, 128, 192
+    shapes = dict(data=(B, 3, H, W), im_info=(B, 3), gt_bbox=(B, 100, 5), gt_poly=(B, 100, 2500))
+    _, outs, _ = E.infer_shapes(sym, shapes)
+    assert outs[-1] == (1,) and outs[3] == (B * 512, 81)
+    log = []
+    _train_stubs(monkeypatch, log)
+    labels = ("rpn_cls_label", "rpn_reg_target", "rpn_reg_weight")
+    tr = T.Trainer(sym, shapes, device="cpu", fixed_param=("conv0", "stage1", "gamma", "beta"), rng_std=0.02,
+                   label_names=labels)
+    s_total = sum((H // st) * (W // st) for st in (4, 8, 16, 32, 64))
+    g = torch.Generator().manual_seed(0)
+    feed = dict(data=torch.randn(shapes["data"], generator=g), im_info=torch.tensor([[H, W, 1.0]] * B),
+                gt_bbox=torch.full((B, 100, 5), -1.0), gt_poly=torch.full((B, 100, 2500), -1.0),
+                rpn_cls_label=torch.randint(-1, 2, (B, 3, s_total), generator=g).float(),
+                rpn_reg_target=torch.randn(B, 12, s_total, generator=g),
+                rpn_reg_weight=(torch.rand(B, 12, s_total, generator=g) < 0.1).float())
+    res = tr.forward_backward(**feed)
+    assert [tuple(o.shape) for o in res] == outs and all(torch.isfinite(o).all() for o in res)
+    assert ("proposal_mask_target", 128, 28) in log and ("sigmoid_ce", (1, B * 128 * 28 * 28)) in log
+    assert ("fpn_roi_align", (7, 7), 512) in log and ("fpn_roi_align", (14, 14), 128) in log
+    grads = tr.grads()
+    assert set(grads) == set(tr.trainable)
+    for name in ("mask_fcn_logit_weight", "bbox_fc1_weight", "P2_lateral_weight", "stage3_unit2_conv2_weight"):
+        assert float(grads[name].abs().sum()) > 0, name

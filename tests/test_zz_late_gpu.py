@@ -144,3 +144,31 @@ def test_retinanet_train_step_on_the_device(cuda):
     assert all(torch.isfinite(o).all() for o in outs) and set(grads) == set(tr.trainable)
     assert all(torch.isfinite(v).all() for v in grads.values())
     assert sum(float(v.abs().sum()) > 0 for v in grads.values()) > 0.9 * len(grads)
+
+
+def test_mask_rcnn_train_step_on_the_device(cuda):
+    """config/mask_r50v1_fpn_1x.py's train symbol: as the Faster R-CNN step plus ProposalMaskTarget (polygon
+    rasteriser on the device), the 14x14 RoIAlign on the 128 foreground slots, the class-channel gather and
+    SigmoidCrossEntropy."""
+    from simpledet_b200 import synth
+    from simpledet_b200.facade import symbol as S
+    from simpledet_b200.facade import train as T
+
+    sym = S.fromjson(open(os.path.join(GOLD, "mask_r50v1_fpn_1x_train_symbol.json")).read())
+    B, H, W = 2, 512, 832
+    shapes = dict(data=(B, 3, H, W), im_info=(B, 3), gt_bbox=(B, 100, 5), gt_poly=(B, 100, 2500))
+    tr = T.Trainer(sym, shapes, device=cuda, fixed_param=("conv0", "stage1", "gamma", "beta"), rng_std=0.02,
+                   label_names=("rpn_cls_label", "rpn_reg_target", "rpn_reg_weight"))
+    s_total = sum((H // st) * (W // st) for st in (4, 8, 16, 32, 64))
+    _, gt, polys = synth.mask_scene(np.random.default_rng(3), B, 64, 100, 2500)
+    g = torch.Generator().manual_seed(0)
+    feed = dict(data=torch.randn(shapes["data"], generator=g), im_info=torch.tensor([[H, W, 1.0]] * B),
+                gt_bbox=torch.from_numpy(gt), gt_poly=torch.from_numpy(polys),
+                rpn_cls_label=torch.randint(-1, 2, (B, 3, s_total), generator=g).float(),
+                rpn_reg_target=torch.randn(B, 12, s_total, generator=g),
+                rpn_reg_weight=(torch.rand(B, 12, s_total, generator=g) < 0.1).float())
+    outs = tr.forward_backward(**feed)
+    grads = tr.grads()
+    assert all(torch.isfinite(o).all() for o in outs) and tuple(outs[-1].shape) == (1,)
+    assert set(grads) == set(tr.trainable) and all(torch.isfinite(v).all() for v in grads.values())
+    assert float(grads["mask_fcn_logit_weight"].abs().sum()) > 0
