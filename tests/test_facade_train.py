@@ -151,6 +151,21 @@ def _train_stubs(monkeypatch, log):
         loss = torch.nn.functional.binary_cross_entropy_with_logits(data, label.clamp(min=0), weight=keep, reduction="none")
         return T.make_loss(loss.sum(1) / keep.sum(1).clamp(min=1), grad_scale)
 
+    def roi_align(data, rois, pooled_size, spatial_scale):
+        assert data.requires_grad and rois.shape[0] == data.shape[0] and rois.shape[2] == 4 and 0 < spatial_scale < 1
+        log.append(("roi_align", tuple(pooled_size)))
+        pooled = torch.nn.functional.adaptive_avg_pool2d(data, tuple(pooled_size))
+        return pooled[:, None].expand(-1, rois.shape[1], -1, -1, -1) * (1 + 0 * rois.sum(-1)[..., None, None, None])
+
+    def deform_conv(data, offset, weight, bias, kernel, stride, dilate, pad, num_filter, num_group, num_deformable_group,
+                    no_bias):
+        assert offset.shape[1] == 2 * num_deformable_group * kernel[0] * kernel[1] and offset.requires_grad
+        log.append(("dcn", data.shape[1]))
+        return torch.nn.functional.conv2d(data, weight, bias, stride, pad, dilate, num_group) + 0 * offset.sum()
+
+    monkeypatch.setitem(ops.OPS, "_contrib_ROIAlign_v2", roi_align)
+    monkeypatch.setitem(ops.OPS, "_contrib_DeformableConvolution", deform_conv)
+    monkeypatch.setitem(ops.OPS, "_contrib_Proposal", proposal)
     monkeypatch.setitem(ops.OPS, "ProposalMaskTarget", proposal_mask_target)
     monkeypatch.setitem(ops.OPS, "_contrib_SigmoidCrossEntropy", sigmoid_ce)
     for k, fn in {"_contrib_Proposal_v3": proposal, "get_top_proposal": get_top_proposal, "ProposalTarget": proposal_target,
@@ -260,3 +275,36 @@ def test_mask_rcnn_train_graph_through_the_trainer(monkeypatch):
     assert set(grads) == set(tr.trainable)
     for name in ("mask_fcn_logit_weight", "bbox_fc1_weight", "P2_lateral_weight", "stage3_unit2_conv2_weight"):
         assert float(grads[name].abs().sum()) > 0, name
+
+
+def test_dcn_c4_train_graph_through_the_trainer(monkeypatch):
+    """config/dcn/faster_dcn_r50v1bc4_c5_512roi_1x.py: legacy Proposal, a single-level ROIAlign_v2 through the
+    autograd operator, three DeformableConvolution blocks whose offset branches must receive gradients too."""
+    sym = S.fromjson(open(os.path.join(ROOT, "tests", "golden", "faster_dcn_r50v1bc4_c5_512roi_1x_train_symbol.json")).read())
+    for node in sym._topo():           # 512 rois per image through a ResNet stage is minutes on a CPU: sample 24
+        if node.op == "ProposalTarget":
+            node.attrs["image_rois"] = 24
+    B, H, W = 2, 128, 192
+    shapes = dict(data=(B, 3, H, W), im_info=(B, 3), gt_bbox=(B, 100, 5))
+    args, outs, _ = E.infer_shapes(sym, shapes)
+    byname = dict(zip(sym.list_arguments(), args))
+    assert outs[2:] == [(B * 24, 81), (B * 24, 8), (B, 24)]
+    log = []
+    _train_stubs(monkeypatch, log)
+    labels = ("rpn_cls_label", "rpn_reg_target", "rpn_reg_weight")
+    tr = T.Trainer(sym, shapes, device="cpu", fixed_param=("conv0", "stage1", "gamma", "beta"), rng_std=0.02,
+                   label_names=labels)
+    g = torch.Generator().manual_seed(0)
+    feed = dict(data=torch.randn(shapes["data"], generator=g), im_info=torch.tensor([[H, W, 1.0]] * B),
+                gt_bbox=torch.full((B, 100, 5), -1.0),
+                rpn_cls_label=torch.randint(-1, 2, byname["rpn_cls_label"], generator=g).float(),
+                rpn_reg_target=torch.randn(byname["rpn_reg_target"], generator=g),
+                rpn_reg_weight=(torch.rand(byname["rpn_reg_weight"], generator=g) < 0.1).float())
+    res = tr.forward_backward(**feed)
+    assert [tuple(o.shape) for o in res] == outs and all(torch.isfinite(o).all() for o in res)
+    kinds = [e[0] for e in log]
+    assert kinds.count("dcn") == 3 and "roi_align" in kinds and "proposal" in kinds and "proposal_target" in kinds
+    grads = tr.grads()
+    assert set(grads) == set(tr.trainable)
+    offs = [n for n in grads if "offset" in n and n.endswith("weight")]
+    assert len(offs) == 3 and all(n in grads for n in offs)

@@ -172,3 +172,34 @@ def test_mask_rcnn_train_step_on_the_device(cuda):
     assert all(torch.isfinite(o).all() for o in outs) and tuple(outs[-1].shape) == (1,)
     assert set(grads) == set(tr.trainable) and all(torch.isfinite(v).all() for v in grads.values())
     assert float(grads["mask_fcn_logit_weight"].abs().sum()) > 0
+
+
+def test_dcn_c4_train_step_on_the_device(cuda):
+    """config/dcn/faster_dcn_r50v1bc4_c5_512roi_1x.py's train symbol: legacy Proposal, ROIAlign_v2 forward + backward
+    on C4, three DeformableConvolution blocks (im2col / col2im kernels) inside the C5 head."""
+    from simpledet_b200.facade import executor as E
+    from simpledet_b200.facade import symbol as S
+    from simpledet_b200.facade import train as T
+
+    sym = S.fromjson(open(os.path.join(GOLD, "faster_dcn_r50v1bc4_c5_512roi_1x_train_symbol.json")).read())
+    B, H, W = 2, 256, 384
+    shapes = dict(data=(B, 3, H, W), im_info=(B, 3), gt_bbox=(B, 100, 5))
+    byname = dict(zip(sym.list_arguments(), E.infer_shapes(sym, shapes)[0]))
+    tr = T.Trainer(sym, shapes, device=cuda, fixed_param=("conv0", "stage1", "gamma", "beta"), rng_std=0.02,
+                   label_names=("rpn_cls_label", "rpn_reg_target", "rpn_reg_weight"))
+    g = torch.Generator().manual_seed(0)
+    gt = torch.full((B, 100, 5), -1.0)
+    for b in range(B):
+        xy = torch.rand(5, 2, generator=g) * torch.tensor([W - 150.0, H - 150.0])
+        gt[b, :5, :4] = torch.cat([xy, xy + 40 + torch.rand(5, 2, generator=g) * 100], 1)
+        gt[b, :5, 4] = torch.randint(1, 81, (5,), generator=g).float()
+    feed = dict(data=torch.randn(shapes["data"], generator=g), im_info=torch.tensor([[H, W, 1.0]] * B), gt_bbox=gt,
+                rpn_cls_label=torch.randint(-1, 2, byname["rpn_cls_label"], generator=g).float(),
+                rpn_reg_target=torch.randn(byname["rpn_reg_target"], generator=g),
+                rpn_reg_weight=(torch.rand(byname["rpn_reg_weight"], generator=g) < 0.1).float())
+    outs = tr.forward_backward(**feed)
+    grads = tr.grads()
+    assert all(torch.isfinite(o).all() for o in outs)
+    assert set(grads) == set(tr.trainable) and all(torch.isfinite(v).all() for v in grads.values())
+    offs = [n for n in grads if "offset" in n and n.endswith("weight")]
+    assert len(offs) == 3
