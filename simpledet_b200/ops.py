@@ -1482,7 +1482,7 @@ def segm_results(bbox_xyxy, cls, masks, im_h, im_w):
     models/maskrcnn/process_output.py:6-19): bbox_xyxy (N,4) float32, cls (N) int, masks (N,K,M,M) float32 (background
     channel already removed) -> numpy object array of N dicts {'size': [im_h, im_w], 'counts': bytes}, what
     `pycocotools.mask.encode` returns for the pasted binary masks.  Inputs may be numpy arrays (copied to the
-    current CUDA device, like the reference's host arrays) or CUDA tensors.
+    current CUDA device, like the reference's host arrays) or CUDA tensors (CPU tensors raise: no CPU fallback).
 
     expand_boxes, the int32 truncation, cv2.resize's bilinear interpolation (as the opencv-python wheel's IPP path
     rounds it), `> 0.5` and the paste run in two launches that never materialise the im_h x im_w images: only the
@@ -1490,11 +1490,10 @@ def segm_results(bbox_xyxy, cls, masks, im_h, im_w):
     no pixel inside the image gives the empty mask (the reference raises there)."""
     import numpy as np
 
-    def dev_of(a, dtype):
-        t = torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a
-        if not t.is_cuda:
-            t = t.to(torch.device("cuda", torch.cuda.current_device()))
-        return t.to(dtype).contiguous()
+    def dev_of(a, dtype):   # numpy arrays go to the current device; tensors must already be there (CPU tensors raise)
+        if isinstance(a, np.ndarray):
+            a = torch.from_numpy(np.ascontiguousarray(a)).to(torch.device("cuda", torch.cuda.current_device()))
+        return a.to(dtype).contiguous()
 
     boxes = _dev(dev_of(bbox_xyxy, torch.float32), "bbox_xyxy")
     masks_t = _dev(dev_of(masks, torch.float32), "masks")

@@ -65,3 +65,16 @@ def test_product_entry_point_refuses_cpu_tensors():
     with pytest.raises(Exception):
         ops.bbox_target(torch.from_numpy(G[f"{name}_prop"]), torch.from_numpy(G[f"{name}_gt"]), **kwargs_of(name))
     assert ops.OPS["bbox_target"] is ops.bbox_target
+
+
+def test_product_wrapper_with_the_device_checks_lifted(monkeypatch):
+    """ops.bbox_target itself (string attributes as the CustomOp hands them over, the global numpy RNG) with only the
+    CUDA tensor check and the IoU kernel replaced."""
+    monkeypatch.setattr(ops, "_dev", lambda t, name, dtype=torch.float32: t.contiguous())
+    monkeypatch.setattr(ops, "bbox_overlaps", cpu_overlaps)
+    for name in (str(n) for n in G["names"]):
+        kw = kwargs_of(name)
+        kw["add_gt_to_proposal"] = str(bool(kw["add_gt_to_proposal"]))      # CustomOpProp passes strings
+        kw["bbox_target_std"] = str(kw["bbox_target_std"])
+        np.random.seed(int(G[f"{name}_seed"]))
+        check_case(name, ops.OPS["bbox_target"](torch.from_numpy(G[f"{name}_prop"]), torch.from_numpy(G[f"{name}_gt"]), **kw))

@@ -189,3 +189,27 @@ def test_product_entry_point_needs_the_device():
     im_h, im_w, box, cls, masks, _ = case(NAMES[0])
     with pytest.raises(Exception):
         ops.segm_results(box, cls, masks, im_h, im_w)
+
+
+def test_product_wrapper_over_the_emulated_kernels(emul, monkeypatch):
+    """ops.segm_results itself (argument marshalling, ctypes argument order, the scan, the string encoder) with the
+    library's two entry points replaced by the host emulation of the same kernel source and the CUDA-only tensor
+    checks lifted - everything of the product path that is not the launch itself."""
+    from simpledet_b200 import _lib
+
+    class FakeLib:
+        sdet_mask_paste_count = emul.emul_mask_paste_count      # same argument list + a trailing stream (ignored)
+        sdet_mask_paste_write = emul.emul_mask_paste_write
+
+    def dev(t, name, dtype=torch.float32):
+        assert t.dtype == dtype, (name, t.dtype)
+        return t.contiguous()
+
+    monkeypatch.setattr(_lib, "lib", lambda: FakeLib)
+    monkeypatch.setattr(ops, "_dev", dev)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    for name in NAMES:
+        im_h, im_w, box, cls, masks, want = case(name)
+        got = ops.segm_results(torch.from_numpy(box), torch.from_numpy(cls.astype(np.int64)), torch.from_numpy(masks),
+                               im_h, im_w)
+        assert [g["counts"] for g in got] == want
