@@ -309,6 +309,7 @@ SHAPE_RULES = {
     "broadcast_add": _same, "broadcast_mul": _same,
     "Concat": _shape_concat, "UpSampling": _shape_upsample, "slice_like": _shape_slice_like, "slice_axis": _shape_slice_axis,
     "Reshape": lambda a, ins, n: (ins, [mx_reshape(ins[0], a["shape"])]),
+    "reshape": lambda a, ins, n: (ins, [mx_reshape(ins[0], a["shape"])]),
     "Flatten": lambda a, ins, n: (ins, [(ins[0][0], math.prod(ins[0][1:]))]),
     "_contrib_Proposal_v3": _shape_proposal, "_contrib_Proposal": _shape_proposal,
     "_contrib_ROIAlign_v2": _shape_roialign, "_contrib_DecodeBBox": _shape_decode, "Custom": _shape_custom,
@@ -684,7 +685,7 @@ class Executor:
         if op == "gather_nd":   # data[indices[0], indices[1], ...]: the mask channel of each roi's class
             idx = x[1].to(torch.long)
             return [x[0][tuple(idx[i] for i in range(idx.shape[0]))]]
-        if op == "Reshape":
+        if op in ("Reshape", "reshape"):
             return [x[0].reshape(mx_reshape(tuple(x[0].shape), a["shape"]))]
         if op == "Flatten":
             return [x[0].reshape(x[0].shape[0], -1)]

@@ -49,7 +49,8 @@ _MULTI_OUT = {
     "split": lambda a: (int(a["num_outputs"]), int(a["num_outputs"])),
 }
 # non-symbol positional arguments of the creation operators, in order
-_POSITIONAL_ATTRS = {"full": ("shape", "value"), "zeros": ("shape",), "ones": ("shape",), "arange": ("start", "stop", "step")}
+_POSITIONAL_ATTRS = {"full": ("shape", "value"), "zeros": ("shape",), "ones": ("shape",), "arange": ("start", "stop", "step"),
+                     "Reshape": ("shape",), "reshape": ("shape",)}   # mx.symbol.Reshape(data, (-3, -2)): models/tridentnet/resnet_v2.py:99
 CUSTOM_OUTPUTS = {"get_top_proposal": 2, "assign_layer_fpn": None, "BboxPostProcessing": 3, "bbox_target": 4,
                   "decode_retina": 2}
 
