@@ -12,9 +12,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 # BASELINE.json configs 2-5: Faster R-CNN FPN, RetinaNet, Mask R-CNN, DCNv1 Faster R-CNN C4
-CONFIGS = ["faster_r50v1_fpn_1x", "retina_r50v1_fpn_1x", "mask_r50v1_fpn_1x", "dcn.faster_dcn_r50v1bc4_c5_512roi_1x"]
+CONFIGS = ["faster_r50v1_fpn_1x", "retina_r50v1_fpn_1x", "mask_r50v1_fpn_1x", "dcn.faster_dcn_r50v1bc4_c5_512roi_1x",
+                 "crowdhuman.faster_r50v1b_fpn_1x"]
 # the TRAIN graphs the façade's Trainer runs (simpledet_b200/facade/train.py): <config>_train_symbol.json
-TRAIN_CONFIGS = ["faster_r50v1_fpn_1x", "retina_r50v1_fpn_1x", "mask_r50v1_fpn_1x", "dcn.faster_dcn_r50v1bc4_c5_512roi_1x"]
+TRAIN_CONFIGS = ["faster_r50v1_fpn_1x", "retina_r50v1_fpn_1x", "mask_r50v1_fpn_1x", "dcn.faster_dcn_r50v1bc4_c5_512roi_1x",
+                 "crowdhuman.faster_r50v1b_fpn_1x"]
 
 
 def one(name, train=False):
@@ -24,7 +26,8 @@ def one(name, train=False):
     facade.install("/root/reference")
     cfg = importlib.import_module("config." + name)
     sym = cfg.get_config(is_train=True)[6].train_symbol if train else cfg.get_config(is_train=False)[6].test_symbol
-    path = os.path.join(HERE, name.split(".")[-1] + ("_train_symbol.json" if train else "_test_symbol.json"))
+    stem = name.replace(".", "_") if name.startswith("crowdhuman.") else name.split(".")[-1]
+    path = os.path.join(HERE, stem + ("_train_symbol.json" if train else "_test_symbol.json"))
     open(path, "w").write(sym.tojson())
     print("wrote", path, os.path.getsize(path), "bytes;", len(sym._topo()), "nodes; outputs", sym.list_outputs())
 

@@ -308,3 +308,40 @@ def test_dcn_c4_train_graph_through_the_trainer(monkeypatch):
     assert set(grads) == set(tr.trainable)
     offs = [n for n in grads if "offset" in n and n.endswith("weight")]
     assert len(offs) == 3 and all(n in grads for n in offs)
+
+
+def test_crowdhuman_train_graph_hands_bbox_target_its_attributes(monkeypatch):
+    """config/crowdhuman/faster_r50v1b_fpn_1x.py: mx.sym.Custom(op_type='bbox_target') (models/crowdhuman/builder.py:
+    380-396) reaches OPS['bbox_target'] with the attributes the CustomOpProp would parse."""
+    from simpledet_b200 import ops
+
+    sym = S.fromjson(open(os.path.join(ROOT, "tests", "golden", "crowdhuman_faster_r50v1b_fpn_1x_train_symbol.json")).read())
+    B, H, W = 2, 128, 192
+    shapes = dict(data=(B, 3, H, W), im_info=(B, 3), gt_bbox=(B, 100, 5))
+    _, outs, _ = E.infer_shapes(sym, shapes)
+    assert outs[3:] == [(B * 512, 2), (B * 512, 8), (B, 512)]
+    log = []
+    _train_stubs(monkeypatch, log)
+
+    def bbox_target(proposal, gt_bbox, num_class, add_gt_to_proposal, image_rois, fg_fraction, fg_thresh, bg_thresh_hi,
+                    bg_thresh_lo, bbox_target_std):
+        assert (num_class, add_gt_to_proposal, image_rois, fg_fraction) == (2, True, 512, 0.5)
+        assert (fg_thresh, bg_thresh_hi, bg_thresh_lo, bbox_target_std) == (0.5, 0.5, 0.0, (0.1, 0.1, 0.2, 0.2))
+        assert tuple(gt_bbox.shape) == (B, 100, 5) and proposal.shape[2] == 4
+        log.append(("bbox_target", image_rois))
+        g = torch.Generator().manual_seed(5)
+        return (proposal[:, :image_rois].contiguous(), torch.randint(0, 2, (B, image_rois), generator=g).float(),
+                torch.randn(B, image_rois, 8, generator=g), (torch.rand(B, image_rois, 8, generator=g) < 0.2).float())
+
+    monkeypatch.setitem(ops.OPS, "bbox_target", bbox_target)
+    tr = T.Trainer(sym, shapes, device="cpu", fixed_param=("conv0", "stage1", "gamma", "beta"), rng_std=0.02,
+                   label_names=("rpn_cls_label", "rpn_reg_target", "rpn_reg_weight"))
+    s_total = sum((H // st) * (W // st) for st in (4, 8, 16, 32, 64))
+    g = torch.Generator().manual_seed(0)
+    res = tr.forward_backward(data=torch.randn(shapes["data"], generator=g), im_info=torch.tensor([[H, W, 1.0]] * B),
+                              gt_bbox=torch.full((B, 100, 5), -1.0),
+                              rpn_cls_label=torch.randint(-1, 2, (B, 3, s_total), generator=g).float(),
+                              rpn_reg_target=torch.randn(B, 12, s_total, generator=g),
+                              rpn_reg_weight=(torch.rand(B, 12, s_total, generator=g) < 0.1).float())
+    assert [tuple(o.shape) for o in res] == outs and ("bbox_target", 512) in log
+    assert set(tr.grads()) == set(tr.trainable)
