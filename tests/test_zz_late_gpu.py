@@ -203,3 +203,33 @@ def test_dcn_c4_train_step_on_the_device(cuda):
     assert set(grads) == set(tr.trainable) and all(torch.isfinite(v).all() for v in grads.values())
     offs = [n for n in grads if "offset" in n and n.endswith("weight")]
     assert len(offs) == 3
+
+
+def test_crowdhuman_train_step_with_bbox_target_on_the_device(cuda):
+    """config/crowdhuman/faster_r50v1b_fpn_1x.py's train symbol: the CustomOp 'bbox_target' inside the graph, between
+    get_top_proposal and the fused FPN RoIAlign."""
+    from simpledet_b200.facade import symbol as S
+    from simpledet_b200.facade import train as T
+
+    sym = S.fromjson(open(os.path.join(GOLD, "crowdhuman_faster_r50v1b_fpn_1x_train_symbol.json")).read())
+    B, H, W = 2, 256, 384
+    shapes = dict(data=(B, 3, H, W), im_info=(B, 3), gt_bbox=(B, 100, 5))
+    tr = T.Trainer(sym, shapes, device=cuda, fixed_param=("conv0", "stage1", "gamma", "beta"), rng_std=0.02,
+                   label_names=("rpn_cls_label", "rpn_reg_target", "rpn_reg_weight"))
+    s_total = sum((H // st) * (W // st) for st in (4, 8, 16, 32, 64))
+    g = torch.Generator().manual_seed(0)
+    gt = torch.full((B, 100, 5), -1.0)
+    for b in range(B):
+        xy = torch.rand(8, 2, generator=g) * torch.tensor([W - 150.0, H - 150.0])
+        gt[b, :8, :4] = torch.cat([xy, xy + 40 + torch.rand(8, 2, generator=g) * 100], 1)
+        gt[b, :8, 4] = 1.0
+    np.random.seed(0)
+    outs = tr.forward_backward(data=torch.randn(shapes["data"], generator=g), im_info=torch.tensor([[H, W, 1.0]] * B),
+                               gt_bbox=gt, rpn_cls_label=torch.randint(-1, 2, (B, 3, s_total), generator=g).float(),
+                               rpn_reg_target=torch.randn(B, 12, s_total, generator=g),
+                               rpn_reg_weight=(torch.rand(B, 12, s_total, generator=g) < 0.1).float())
+    grads = tr.grads()
+    assert all(torch.isfinite(o).all() for o in outs) and tuple(outs[3].shape) == (B * 512, 2)
+    assert set(grads) == set(tr.trainable) and all(torch.isfinite(v).all() for v in grads.values())
+    lab = outs[5]
+    assert ((lab == 0) | (lab == 1)).all() and int((lab == 1).sum()) >= 2 * 8      # at least the gt boxes themselves
