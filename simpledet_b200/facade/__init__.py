@@ -149,6 +149,7 @@ def install(reference_root: str | None = None):
     tvm = _mod("mxnext.tvm")
     tvm.__path__ = []
     _mod("mxnext.tvm.proposal", proposal=X.tvm_proposal)
+    _mod("mxnext.tvm.decode_bbox", decode_bbox=X.tvm_decode_bbox)
     _mod("mxnext.tvm.get_top_proposal", get_top_proposal=X.tvm_get_top_proposal)
     _mod("mxnext.tvm.fpn_roi_assign", fpn_roi_assign=X.tvm_fpn_roi_assign)
 

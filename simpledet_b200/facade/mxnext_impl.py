@@ -529,6 +529,14 @@ def tvm_proposal(cls_prob, bbox_pred, im_info, anchors=None, name="proposal", fe
                                name=f"{name}_stride{feature_stride}")
 
 
+def tvm_decode_bbox(F, rois, bbox_pred, im_info, bbox_mean=(0.0, 0.0, 0.0, 0.0), bbox_std=(0.1, 0.1, 0.2, 0.2),
+                    class_agnostic=True, name=None, **kw):
+    """mxnext.tvm.decode_bbox.decode_bbox (models/FreeAnchor/ops.py:166,267): the TVM-built twin of
+    _contrib_DecodeBBox; the stand-in emits the operator itself."""
+    return contrib.DecodeBBox(rois=rois, bbox_pred=bbox_pred, im_info=im_info, bbox_mean=tuple(bbox_mean),
+                              bbox_std=tuple(bbox_std), class_agnostic=bool(class_agnostic), name=name)
+
+
 def tvm_get_top_proposal(F, bbox, score, top_n, batch_size=1, **kw):
     return sym.Custom(bbox=bbox, score=score, op_type="get_top_proposal", top_n=top_n, name="get_top_proposal")
 

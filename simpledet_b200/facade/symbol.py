@@ -210,8 +210,13 @@ class Symbol:
     def __pow__(self, o): return self._bin(o, "_power", "_power_scalar")
     def __rpow__(self, o): return self._bin(o, "_power", "_rpower_scalar")
 
-    def reshape(self, shape=None, **kw):
-        return make_op("Reshape", [self], dict(shape=tuple(shape if shape is not None else kw["shape"])))
+    def reshape(self, *shape, **kw):
+        """Symbol.reshape(shape) / reshape(d0, d1, ...) / reshape(-1) / reshape(shape=...), as mx.sym.Symbol takes them."""
+        if not shape:
+            shape = kw["shape"]
+        elif len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = shape[0]
+        return make_op("Reshape", [self], dict(shape=tuple(int(d) for d in shape)))
 
     def astype(self, dtype):
         return make_op("Cast", [self], dict(dtype=str(dtype)))

@@ -136,6 +136,8 @@ DETECTORS = {
     # graphs): SyncBatchNorm + feature-pyramid grids, GroupNorm heads with symbol comparisons in the loss
     "FPG.faster_r50v1b_fpg6@128_syncbn_1x": (None, None, {"_contrib_SyncBatchNorm", "_contrib_ROIAlign_v2"}, {"ProposalTarget"}),
     "fcos_r50v1_fpn_1x": (None, None, {"_contrib_GroupNorm"}, {"_contrib_GroupNorm"}),
+    # FreeAnchor: mxnext.tvm.decode_bbox (the TVM twin of _contrib_DecodeBBox) in the loss and in the test-time proposal
+    "FreeAnchor.free_anchor_r50v1_fpn_1x": (None, None, {"_contrib_DecodeBBox"}, {"_contrib_DecodeBBox"}),
 }
 
 
