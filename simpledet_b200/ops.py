@@ -1573,6 +1573,43 @@ def write_coco_json(coco_result, path):
 
 
 
+def mask_test_records(im_id, im_info, im_h, im_w, post_cls_score, post_box, post_cls, mask, category_ids,
+                      max_det_per_image=100, mask_score=None):
+    """One image of mask_test.py's result loop (:159-200 un-padding and rescaling, :207 process_output =
+    segm_results, :236-311 per-class grouping and COCO records; the `multi_branch_nms is None` route every shipped
+    Mask R-CNN config takes).  Inputs are the squeezed network outputs of one image as numpy arrays or CUDA tensors:
+    post_cls_score (D,), post_box (D,4) in network-input pixels, post_cls (D,) with -1 padding, mask (D, 1+K, M, M)
+    with the background channel first; im_info = (h, w, scale); im_h, im_w = roidb[rec_id]['h'], ['w'];
+    category_ids = coco.getCatIds().  -> the image's COCO result dicts (bbox + score + mask_score + segmentation)."""
+    import numpy as np
+
+    def host(a):
+        return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+
+    info = host(im_info).reshape(-1)
+    scale = info[2]
+    cls_all = host(post_cls).reshape(-1).astype(np.int32)
+    valid = np.where(cls_all > -1)[0]                                   # remove pad bbox and mask
+    bbox_xyxy = (host(post_box).reshape(-1, 4) / scale)[valid]          # scale to the original image
+    cls_score = host(post_cls_score).reshape(-1)[valid]
+    cls = cls_all[valid]
+    ms = np.zeros_like(cls_score) if mask_score is None else host(mask_score).reshape(-1)[valid]
+    if isinstance(mask, torch.Tensor):
+        vt = torch.from_numpy(valid).to(mask.device)
+        m = mask[:, 1:][vt].contiguous()                                # remove bg; stays on the device
+    else:
+        m = np.ascontiguousarray(np.asarray(mask)[:, 1:][valid])
+    segm = segm_results(np.ascontiguousarray(bbox_xyxy, np.float32), cls, m, im_h, im_w) if len(valid) else np.array([], object)
+    dets, segs, mscores = {}, {}, {}
+    for cid in np.unique(cls):
+        ind = np.where(cls == cid)[0]
+        det = np.concatenate((bbox_xyxy[ind], cls_score[ind].reshape(-1, 1)), axis=1).astype(np.float32)
+        dataset_cid = category_ids[int(cid)]
+        dets[dataset_cid], segs[dataset_cid], mscores[dataset_cid] = det, segm[ind], ms[ind]
+    return coco_segm_records(im_id, dets, segs, mscores, max_det_per_image)
+
+
+
 def _bbox_target_impl(proposal, gt_bbox, num_class, add_gt_to_proposal, image_rois, fg_fraction, fg_thresh, bg_thresh_hi,
                       bg_thresh_lo, bbox_target_std, rng, overlaps):
     """The body of `bbox_target` over tensors on one device, with the IoU operator passed in (the product passes the

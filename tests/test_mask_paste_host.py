@@ -213,3 +213,44 @@ def test_product_wrapper_over_the_emulated_kernels(emul, monkeypatch):
         got = ops.segm_results(torch.from_numpy(box), torch.from_numpy(cls.astype(np.int64)), torch.from_numpy(masks),
                                im_h, im_w)
         assert [g["counts"] for g in got] == want
+
+
+def test_mask_test_records_against_the_reference_loop(monkeypatch):
+    """mask_test.py:159-200 + :236-311 for one image, restated as written, over the oracle's segm_results; the product
+    function runs with its segm_results call answered by the same oracle (its device twin is exercised elsewhere)."""
+    rng = np.random.default_rng(8)
+    D, K, M, im_h, im_w = 20, 4, 28, 120, 160
+    info = np.array([240.0, 320.0, 2.0], np.float32)
+    post_cls = rng.integers(0, K, D).astype(np.float32)
+    post_cls[[3, 11, 19]] = -1                                          # padding rows
+    xy = rng.uniform(0, [200, 140], (D, 2))
+    post_box = np.concatenate([xy, xy + rng.uniform(20, 100, (D, 2))], 1).astype(np.float32)
+    post_score = rng.random(D).astype(np.float32)
+    post_score[5] = post_score[6]
+    mask = rng.random((D, 1 + K, M, M)).astype(np.float32)
+    cats = [1, 2, 3, 5]
+
+    # -- the reference, restated
+    m = mask[:, 1:, :, :]
+    box = post_box / info[2]
+    cls = post_cls.astype(np.int32)
+    valid = np.where(cls > -1)[0]
+    bbox_xyxy, cls_score, cls, m = box[valid], post_score[valid], cls[valid], m[valid]
+    mask_score = np.zeros_like(cls_score)
+    segm = np.array(np_ops.segm_results(bbox_xyxy, cls, m, im_h, im_w))
+    result = []
+    for cid in np.unique(cls):
+        ind = np.where(cls == cid)[0]
+        det = np.concatenate((bbox_xyxy[ind], cls_score[ind].reshape(-1, 1)), axis=1).astype(np.float32)
+        xs, ys = det[:, 0], det[:, 1]
+        ws, hs = det[:, 2] - xs + 1, det[:, 3] - ys + 1
+        result += [{'image_id': 9, 'category_id': int(cats[cid]), 'bbox': [float(xs[k]), float(ys[k]), float(ws[k]), float(hs[k])],
+                    'score': float(det[k, -1]), 'mask_score': float(mask_score[ind][k]),
+                    'segmentation': {"size": segm[ind][k]["size"], "counts": segm[ind][k]["counts"].decode('utf8')}}
+                   for k in range(det.shape[0])]
+    want = sorted(result, key=lambda x: x['score'])[-10:]
+
+    monkeypatch.setattr(ops, "segm_results", lambda b, c, mm, h, w: np.array(np_ops.segm_results(b, c, mm, h, w), dtype=object))
+    got = ops.mask_test_records(9, info, im_h, im_w, post_score, post_box, post_cls, mask, cats, max_det_per_image=10)
+    assert got == want and len(got) == 10
+    json.dumps(got)

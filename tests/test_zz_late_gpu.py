@@ -233,3 +233,28 @@ def test_crowdhuman_train_step_with_bbox_target_on_the_device(cuda):
     assert set(grads) == set(tr.trainable) and all(torch.isfinite(v).all() for v in grads.values())
     lab = outs[5]
     assert ((lab == 0) | (lab == 1)).all() and int((lab == 1).sum()) >= 2 * 8      # at least the gt boxes themselves
+
+
+def test_mask_test_records_on_the_device(cuda):
+    """mask_test.py's per-image loop with the masks left on the device (CUDA tensor in, records out)."""
+    from oracle import np_ops
+
+    rng = np.random.default_rng(8)
+    D, K, M, im_h, im_w = 40, 6, 28, 300, 400
+    info = np.array([600.0, 800.0, 2.0], np.float32)
+    post_cls = rng.integers(0, K, D).astype(np.float32)
+    post_cls[[3, 11, 19]] = -1
+    xy = rng.uniform(0, [600, 400], (D, 2))
+    post_box = np.concatenate([xy, xy + rng.uniform(30, 200, (D, 2))], 1).astype(np.float32)
+    post_score = rng.random(D).astype(np.float32)
+    z = rng.standard_normal((D, 1 + K, 7, 7)).astype(np.float32)
+    mask = np.ascontiguousarray(1 / (1 + np.exp(-2 * np.kron(z, np.ones((4, 4), np.float32)))), np.float32)
+    cats = [1, 2, 3, 5, 8, 13]
+    got = ops.mask_test_records(9, info, im_h, im_w, post_score, post_box, post_cls, torch.from_numpy(mask).to(cuda), cats, 100)
+    cls = post_cls.astype(np.int32)
+    valid = np.where(cls > -1)[0]
+    want_segm = np_ops.segm_results((post_box / info[2])[valid], cls[valid], mask[:, 1:][valid], im_h, im_w)
+    by_score = {float(post_score[v]): s["counts"].decode("utf8") for v, s in zip(valid, want_segm)}
+    assert len(got) == len(valid) and [r["score"] for r in got] == sorted(r["score"] for r in got)
+    for r in got:
+        assert r["segmentation"]["counts"] == by_score[r["score"]] and r["segmentation"]["size"] == [im_h, im_w]
