@@ -7,14 +7,16 @@ mkdir -p gpurun_out
 NEW1="tests/test_mask_target_gpu.py::test_mask_target_output_ratio"
 NEW2="tests/test_mask_target_gpu.py::test_mask_ratio_overlapping_segments_and_empty_rows"
 NEW3="tests/test_facade_gpu.py::test_other_detectors_of_the_reference_run"
-timeout 240 python -m pytest tests -q -m gpu -p no:cacheprovider --deselect $NEW1 --deselect $NEW2 --deselect $NEW3 \
+timeout 240 python -m pytest tests -q -m gpu -p no:cacheprovider --deselect $NEW1 --deselect $NEW2 --deselect $NEW3 --ignore tests/test_zz_late_gpu.py \
   > gpurun_out/final_tests_a.txt 2>&1; echo "A rc=$?" >> gpurun_out/final_tests_a.txt
 timeout 60 python -m pytest $NEW1 $NEW2 -q -m gpu -p no:cacheprovider > gpurun_out/final_tests_b.txt 2>&1; echo "B rc=$?" >> gpurun_out/final_tests_b.txt
 timeout 90 python -m pytest $NEW3 -q -m gpu -p no:cacheprovider > gpurun_out/final_tests_c.txt 2>&1; echo "C rc=$?" >> gpurun_out/final_tests_c.txt
+# the additions of round 2's last session (never run on a device by the builder): own process, -rA shows XPASS / XFAIL
+timeout 300 python -m pytest tests/test_zz_late_gpu.py -q -m gpu -rA -p no:cacheprovider > gpurun_out/final_tests_late.txt 2>&1; echo "LATE rc=$?" >> gpurun_out/final_tests_late.txt
 timeout 60 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" > gpurun_out/final_smoke.txt 2>&1
 timeout 150 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err
 for c in retina_r50v1_fpn_1x mask_r50v1_fpn_1x faster_dcn_r50v1bc4_c5_512roi_1x; do
   timeout 40 python benchmarks/graph_infer_speed.py --config $c --count 20 --weights random --graph 1 >> gpurun_out/final_graphs.txt 2>&1
 done
 tail -3 gpurun_out/final_tests_a.txt; tail -3 gpurun_out/final_tests_b.txt; tail -3 gpurun_out/final_tests_c.txt
-tail -1 gpurun_out/final_smoke.txt; cut -c1-400 gpurun_out/final_bench.json; tail -3 gpurun_out/final_graphs.txt
+tail -14 gpurun_out/final_tests_late.txt; tail -1 gpurun_out/final_smoke.txt; cut -c1-400 gpurun_out/final_bench.json; tail -3 gpurun_out/final_graphs.txt
