@@ -132,7 +132,7 @@ DETECTORS = {
     "tridentnet_r50v1c4_c5_1x": (None, None, {"_contrib_Proposal", "stack"}, {"_contrib_Proposal_v2", "ProposalTarget_v2"}),
     "tridentnet_r50v2c4_c5_1x": (None, None, {"_contrib_Proposal", "stack"}, {"_contrib_Proposal_v2", "ProposalTarget_v2"}),
     "faster_r50v2c4_c5_256roi_1x": ([(1, 1000, 81), (1, 1000, 4)], (25, 31), {"_contrib_Proposal"}, {"ProposalTarget"}),
-    # samples of the rest of the model zoo (tools/facade_sweep.py builds all 116 configs: 111 inference / 108 training
+    # samples of the rest of the model zoo (tools/facade_sweep.py builds all 116 configs: 113 inference / 110 training
     # graphs): SyncBatchNorm + feature-pyramid grids, GroupNorm heads with symbol comparisons in the loss
     "FPG.faster_r50v1b_fpg6@128_syncbn_1x": (None, None, {"_contrib_SyncBatchNorm", "_contrib_ROIAlign_v2"}, {"ProposalTarget"}),
     "fcos_r50v1_fpn_1x": (None, None, {"_contrib_GroupNorm"}, {"_contrib_GroupNorm"}),
