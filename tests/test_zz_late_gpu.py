@@ -258,3 +258,24 @@ def test_mask_test_records_on_the_device(cuda):
     assert len(got) == len(valid) and [r["score"] for r in got] == sorted(r["score"] for r in got)
     for r in got:
         assert r["segmentation"]["counts"] == by_score[r["score"]] and r["segmentation"]["size"] == [im_h, im_w]
+
+
+def test_tridentnet_inference_graph_on_the_device(cuda):
+    """config/tridentnet_r50v1c4_c5_1x.py's test symbol (fixture from the reference's own builders): three
+    weight-sharing dilation branches stacked into the batch axis, ONE legacy Proposal over the 3-image batch, ROIAlign_v2
+    on C4, the C5 head on 3 x 300 rois, DecodeBBox."""
+    from simpledet_b200 import facade
+    from simpledet_b200.facade import symbol as S
+
+    sym = S.fromjson(open(os.path.join(GOLD, "tridentnet_r50v1c4_c5_1x_test_symbol.json")).read())
+    shapes = dict(data=(1, 3, 800, 1333), im_info=(1, 3), im_id=(1,), rec_id=(1,))
+    gen = torch.Generator(device=cuda).manual_seed(5)
+    feed = dict(data=torch.randn(shapes["data"], device=cuda, generator=gen), im_info=torch.tensor([[800.0, 1333.0, 1.0]], device=cuda),
+                im_id=torch.ones(1, device=cuda), rec_id=torch.ones(1, device=cuda))
+    ex = facade.Executor(sym, cuda).init_params(shapes, rng_std=0.02)
+    with torch.no_grad():
+        got = ex.forward(**feed)
+    torch.cuda.synchronize()
+    assert [tuple(o.shape) for o in got[3:]] == [(900, 81), (900, 4)]
+    assert all(torch.isfinite(o).all() for o in got)
+    np.testing.assert_allclose(got[3].sum(-1).cpu().numpy(), 1.0, rtol=1e-4)
