@@ -222,6 +222,8 @@ def _stubs(torch, log):
     # TridentNet: three dilation branches with shared weights stacked into the batch axis (mx.symbol.stack + Reshape),
     # one legacy Proposal over the 3-image batch, 3 x 300 rois through the C5 head
     ("tridentnet_r50v1c4_c5_1x", [(900, 81), (900, 4)]),
+    # Cascade R-CNN: three fused FPN RoIAlign stages chained through DecodeBBox, the ensembled score of five head passes
+    ("cascade_r50v1_fpn_1x", [(1, 1000, 81), (1, 1000, 4)]),
 ])
 def test_executor_glue_of_the_other_detectors(name, outs, monkeypatch):
     import torch
@@ -258,6 +260,8 @@ def test_executor_glue_of_the_other_detectors(name, outs, monkeypatch):
         assert [e[2] for e in log if e[0] == "gen_proposal_retina" and e[1] == 128] == [0.0]   # builder.py:372
     elif name.startswith("mask"):
         assert ("fpn_roi_align", (7, 7)) in log and ("fpn_roi_align", (14, 14)) in log and "post" in kinds
+    elif name.startswith("cascade"):
+        assert [e for e in log if e[0] == "fpn_roi_align"] == [("fpn_roi_align", (7, 7))] * 3 and "proposal" in kinds
     elif name.startswith("tridentnet"):
         assert kinds == {"proposal"} and len(log) == 1          # ONE Proposal call for the three branches
     else:

@@ -345,3 +345,42 @@ def test_crowdhuman_train_graph_hands_bbox_target_its_attributes(monkeypatch):
                               rpn_reg_weight=(torch.rand(B, 12, s_total, generator=g) < 0.1).float())
     assert [tuple(o.shape) for o in res] == outs and ("bbox_target", 512) in log
     assert set(tr.grads()) == set(tr.trainable)
+
+
+def test_cascade_rcnn_train_graph_through_the_trainer(monkeypatch):
+    """config/cascade_r50v1_fpn_1x.py: three ProposalTarget -> fused RoIAlign -> head -> DecodeBBox stages, nine loss
+    heads; every stage's head parameters must receive gradients."""
+    sym = S.fromjson(open(os.path.join(ROOT, "tests", "golden", "cascade_r50v1_fpn_1x_train_symbol.json")).read())
+    for node in sym._topo():               # 3 x 512 rois per image through two 1024-wide FC layers: keep the CPU run short
+        if node.op == "ProposalTarget":
+            node.attrs["image_rois"] = 64
+    B, H, W = 2, 128, 192
+    shapes = dict(data=(B, 3, H, W), im_info=(B, 3), gt_bbox=(B, 100, 5))
+    _, outs, _ = E.infer_shapes(sym, shapes)
+    assert len(outs) == 12 and outs[3:6] == outs[6:9] == outs[9:12] == [(B * 64, 81), (B * 64, 8), (B, 64)]
+    log = []
+    _train_stubs(monkeypatch, log)
+
+    def decode_bbox(rois, bbox_pred, im_info, mean, std, class_agnostic):
+        assert class_agnostic and rois.shape[:2] == bbox_pred.shape[:2] and not rois.requires_grad
+        log.append(("decode", tuple(std)))
+        return rois.detach().clone()
+
+    from simpledet_b200 import ops
+    monkeypatch.setitem(ops.OPS, "_contrib_DecodeBBox", decode_bbox)
+    tr = T.Trainer(sym, shapes, device="cpu", fixed_param=("conv0", "stage1", "gamma", "beta"), rng_std=0.02,
+                   label_names=("rpn_cls_label", "rpn_reg_target", "rpn_reg_weight"))
+    s_total = sum((H // st) * (W // st) for st in (4, 8, 16, 32, 64))
+    g = torch.Generator().manual_seed(0)
+    res = tr.forward_backward(data=torch.randn(shapes["data"], generator=g), im_info=torch.tensor([[H, W, 1.0]] * B),
+                              gt_bbox=torch.full((B, 100, 5), -1.0),
+                              rpn_cls_label=torch.randint(-1, 2, (B, 3, s_total), generator=g).float(),
+                              rpn_reg_target=torch.randn(B, 12, s_total, generator=g),
+                              rpn_reg_weight=(torch.rand(B, 12, s_total, generator=g) < 0.1).float())
+    assert [tuple(o.shape) for o in res] == outs
+    assert [e[1] for e in log if e[0] == "proposal_target"] == [64, 64, 64]
+    assert len([e for e in log if e[0] == "fpn_roi_align"]) == 3 and len([e for e in log if e[0] == "decode"]) == 2
+    grads = tr.grads()
+    assert set(grads) == set(tr.trainable)
+    heads = [n for n in grads if n.startswith("bbox_") and n.endswith("weight")]
+    assert len(heads) >= 12 and all(float(grads[n].abs().sum()) > 0 for n in heads), heads

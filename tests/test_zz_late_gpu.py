@@ -279,3 +279,41 @@ def test_tridentnet_inference_graph_on_the_device(cuda):
     assert [tuple(o.shape) for o in got[3:]] == [(900, 81), (900, 4)]
     assert all(torch.isfinite(o).all() for o in got)
     np.testing.assert_allclose(got[3].sum(-1).cpu().numpy(), 1.0, rtol=1e-4)
+
+
+def test_cascade_rcnn_inference_and_train_step_on_the_device(cuda):
+    """config/cascade_r50v1_fpn_1x.py: the test graph (three fused FPN RoIAlign stages chained through DecodeBBox) and
+    one training step (three ProposalTarget stages, nine loss heads) with the real operators."""
+    from simpledet_b200 import facade
+    from simpledet_b200.facade import symbol as S
+    from simpledet_b200.facade import train as T
+
+    sym = S.fromjson(open(os.path.join(GOLD, "cascade_r50v1_fpn_1x_test_symbol.json")).read())
+    shapes = dict(data=(1, 3, 800, 1333), im_info=(1, 3), im_id=(1,), rec_id=(1,))
+    gen = torch.Generator(device=cuda).manual_seed(5)
+    ex = facade.Executor(sym, cuda).init_params(shapes, rng_std=0.02)
+    with torch.no_grad():
+        got = ex.forward(data=torch.randn(shapes["data"], device=cuda, generator=gen),
+                         im_info=torch.tensor([[800.0, 1333.0, 1.0]], device=cuda), im_id=torch.ones(1, device=cuda),
+                         rec_id=torch.ones(1, device=cuda))
+    assert [tuple(o.shape) for o in got[3:]] == [(1, 1000, 81), (1, 1000, 4)] and all(torch.isfinite(o).all() for o in got)
+
+    sym = S.fromjson(open(os.path.join(GOLD, "cascade_r50v1_fpn_1x_train_symbol.json")).read())
+    B, H, W = 2, 256, 384
+    shapes = dict(data=(B, 3, H, W), im_info=(B, 3), gt_bbox=(B, 100, 5))
+    tr = T.Trainer(sym, shapes, device=cuda, fixed_param=("conv0", "stage1", "gamma", "beta"), rng_std=0.02,
+                   label_names=("rpn_cls_label", "rpn_reg_target", "rpn_reg_weight"))
+    s_total = sum((H // st) * (W // st) for st in (4, 8, 16, 32, 64))
+    g = torch.Generator().manual_seed(0)
+    gt = torch.full((B, 100, 5), -1.0)
+    for b in range(B):
+        xy = torch.rand(6, 2, generator=g) * torch.tensor([W - 120.0, H - 120.0])
+        gt[b, :6, :4] = torch.cat([xy, xy + 30 + torch.rand(6, 2, generator=g) * 80], 1)
+        gt[b, :6, 4] = torch.randint(1, 81, (6,), generator=g).float()
+    outs = tr.forward_backward(data=torch.randn(shapes["data"], generator=g), im_info=torch.tensor([[H, W, 1.0]] * B),
+                               gt_bbox=gt, rpn_cls_label=torch.randint(-1, 2, (B, 3, s_total), generator=g).float(),
+                               rpn_reg_target=torch.randn(B, 12, s_total, generator=g),
+                               rpn_reg_weight=(torch.rand(B, 12, s_total, generator=g) < 0.1).float())
+    grads = tr.grads()
+    assert len(outs) == 12 and all(torch.isfinite(o).all() for o in outs)
+    assert set(grads) == set(tr.trainable) and all(torch.isfinite(v).all() for v in grads.values())
