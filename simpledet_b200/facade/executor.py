@@ -311,7 +311,8 @@ SHAPE_RULES = {
     "Reshape": lambda a, ins, n: (ins, [mx_reshape(ins[0], a["shape"])]),
     "reshape": lambda a, ins, n: (ins, [mx_reshape(ins[0], a["shape"])]),
     "Flatten": lambda a, ins, n: (ins, [(ins[0][0], math.prod(ins[0][1:]))]),
-    "_contrib_Proposal_v3": _shape_proposal, "_contrib_Proposal": _shape_proposal,
+    "_contrib_Proposal_v3": _shape_proposal, "_contrib_Proposal": _shape_proposal, "_contrib_Proposal_v2": _shape_proposal,
+    "ProposalTarget_v2": _shape_proposal_target,
     "_contrib_ROIAlign_v2": _shape_roialign, "_contrib_DecodeBBox": _shape_decode, "Custom": _shape_custom,
     "Deconvolution": _shape_deconv, "_contrib_DeformableConvolution": _shape_deform_conv,
     "_contrib_GenAnchor": _shape_gen_anchor, "_contrib_GenProposalRetina": _shape_gen_proposal_retina,
@@ -748,7 +749,17 @@ class Executor:
             out = ops.OPS[op](arg["data"].contiguous(), arg["rois"].contiguous(), _tup(a["pooled_size"]),
                               float(_t(a["spatial_scale"])))
             return [out, out, out]   # argmax_x / argmax_y are not visible outputs of the symbol
-        if op == "ProposalTarget":
+        if op == "_contrib_Proposal_v2":   # TridentNet: Proposal + valid_ranges (models/tridentnet/builder.py:239)
+            return list(ops.OPS[op](arg["cls_prob"].contiguous(), arg["bbox_pred"].contiguous(), arg["im_info"].contiguous(),
+                                    arg["valid_ranges"].contiguous(),
+                                    rpn_pre_nms_top_n=int(_t(a.get("rpn_pre_nms_top_n", 6000))),
+                                    rpn_post_nms_top_n=int(_t(a.get("rpn_post_nms_top_n", 300))),
+                                    threshold=float(_t(a.get("threshold", 0.7))), rpn_min_size=int(_t(a.get("rpn_min_size", 16))),
+                                    scales=tuple(float(v) for v in _t(a.get("scales", (4, 8, 16, 32)))),
+                                    ratios=tuple(float(v) for v in _t(a.get("ratios", (0.5, 1, 2)))),
+                                    feature_stride=int(_t(a.get("feature_stride", 16))), output_score=True,
+                                    iou_loss=_b(a.get("iou_loss", False)), filter_scales=_b(a.get("filter_scales", False))))
+        if op in ("ProposalTarget", "ProposalTarget_v2"):
             kw = dict(num_classes=int(_t(a["num_classes"])), batch_images=int(_t(a["batch_images"])),
                       image_rois=int(_t(a["image_rois"])), fg_thresh=float(_t(a["fg_thresh"])),
                       bg_thresh_hi=float(_t(a["bg_thresh_hi"])), bg_thresh_lo=float(_t(a["bg_thresh_lo"])),
@@ -759,6 +770,11 @@ class Executor:
                       bbox_std=tuple(float(v) for v in _t(a.get("bbox_std", (0.1, 0.1, 0.2, 0.2)))),
                       bbox_weight=tuple(float(v) for v in _t(a.get("bbox_weight", (1, 1, 1, 1)))))
             with torch.no_grad():   # ProposalTargetProp: no gradient to either input
+                if op == "ProposalTarget_v2":
+                    return list(ops.OPS[op](arg.get("rois", x[0]).detach().contiguous(),
+                                            arg.get("gt_boxes", x[1]).detach().contiguous(),
+                                            arg.get("valid_ranges", x[2]).detach().contiguous(),
+                                            filter_scales=_b(a.get("filter_scales", False)), **kw))
                 return list(ops.OPS[op](arg.get("rois", x[0]).detach().contiguous(),
                                         arg.get("gt_boxes", x[1]).detach().contiguous(), **kw))
         if op == "ProposalMaskTarget":

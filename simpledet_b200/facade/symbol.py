@@ -289,6 +289,11 @@ class _OpNamespace:
             name = name or _auto_name(op)
             if full in _AUTO_ARGS:  # missing parameter inputs become variables named <op name>_<arg>
                 given = set(arg_names)
+                # a variable handed to an auxiliary-state slot (TridentNet shares moving_mean / moving_var between
+                # branches by passing them in) is an auxiliary state, as in MXNet: the slot decides, not the creator
+                for sym_in, an in zip(inputs, arg_names):
+                    if an in _AUX and len(sym_in.entries) == 1 and sym_in.entries[0][0].op is None:
+                        sym_in.entries[0][0].attrs["__aux__"] = True
                 for an in _AUTO_ARGS[full]:
                     if an in given:
                         continue

@@ -384,3 +384,59 @@ def test_cascade_rcnn_train_graph_through_the_trainer(monkeypatch):
     assert set(grads) == set(tr.trainable)
     heads = [n for n in grads if n.startswith("bbox_") and n.endswith("weight")]
     assert len(heads) >= 12 and all(float(grads[n].abs().sum()) > 0 for n in heads), heads
+
+
+def test_tridentnet_train_graph_reaches_proposal_v2_and_proposal_target_v2(monkeypatch):
+    """config/tridentnet_r50v1c4_c5_1x.py: three branches in the batch axis, `_contrib_Proposal_v2` and
+    `ProposalTarget_v2` with valid_ranges / filter_scales (models/tridentnet/builder.py:239, :377-398); the shared
+    moving statistics handed to BatchNorm as variables are auxiliary states, not trainable arguments."""
+    from simpledet_b200 import ops
+
+    sym = S.fromjson(open(os.path.join(ROOT, "tests", "golden", "tridentnet_r50v1c4_c5_1x_train_symbol.json")).read())
+    assert len(sym.list_auxiliary_states()) == 106 and not any("moving" in n for n in sym.list_arguments())
+    for node in sym._topo():
+        if node.op == "ProposalTarget_v2":
+            node.attrs["image_rois"] = 16
+    B, H, W, NB = 2, 128, 192, 3
+    shapes = dict(data=(B, 3, H, W), im_info=(B, 3), gt_bbox=(B, 100, 5), valid_ranges=(B, NB, 2),
+                  rpn_cls_label=(B, NB, 15, 8, 12), rpn_reg_target=(B, NB, 60, 8, 12), rpn_reg_weight=(B, NB, 60, 8, 12))
+    _, outs, _ = E.infer_shapes(sym, shapes)
+    assert outs == [(B * NB, 2, 15, 8, 12), (B * NB, 60, 8, 12), (B * NB * 16, 81), (B * NB * 16, 8), (B * NB, 16)]
+    log = []
+    _train_stubs(monkeypatch, log)
+
+    def proposal_v2(cls_prob, bbox_pred, im_info, valid_ranges, rpn_pre_nms_top_n, rpn_post_nms_top_n, threshold,
+                    rpn_min_size, scales, ratios, feature_stride, output_score, iou_loss, filter_scales):
+        n = cls_prob.shape[0]
+        assert n == B * NB and tuple(valid_ranges.shape) == (n, 2) and tuple(im_info.shape) == (n, 3) and filter_scales
+        log.append(("proposal_v2", rpn_post_nms_top_n))
+        g = torch.Generator().manual_seed(3)
+        xy = torch.rand(n, rpn_post_nms_top_n, 2, generator=g) * 100
+        return torch.cat([xy, xy + 30], 2), torch.rand(n, rpn_post_nms_top_n, 1, generator=g)
+
+    def proposal_target_v2(rois, gt_boxes, valid_ranges, num_classes, batch_images, image_rois, fg_thresh, bg_thresh_hi,
+                           bg_thresh_lo, proposal_without_gt, fg_fraction, class_agnostic, output_iou, bbox_mean, bbox_std,
+                           bbox_weight, filter_scales):
+        assert batch_images == B * NB and tuple(valid_ranges.shape) == (B * NB, 2) and filter_scales and class_agnostic
+        assert tuple(gt_boxes.shape) == (B * NB, 100, 5)
+        log.append(("proposal_target_v2", image_rois))
+        g = torch.Generator().manual_seed(4)
+        return (rois[:, :image_rois].contiguous(), torch.randint(0, 81, (batch_images, image_rois), generator=g).float(),
+                torch.randn(batch_images, image_rois, 8, generator=g), (torch.rand(batch_images, image_rois, 8, generator=g) < 0.3).float())
+
+    monkeypatch.setitem(ops.OPS, "_contrib_Proposal_v2", proposal_v2)
+    monkeypatch.setitem(ops.OPS, "ProposalTarget_v2", proposal_target_v2)
+    labels = ("rpn_cls_label", "rpn_reg_target", "rpn_reg_weight")
+    data_shapes = {k: v for k, v in shapes.items() if k not in labels}
+    tr = T.Trainer(sym, shapes, device="cpu", fixed_param=("conv0", "stage1", "gamma", "beta"), rng_std=0.02)
+    assert not set(tr.trainable) & set(shapes)
+    g = torch.Generator().manual_seed(0)
+    feed = dict(data=torch.randn(shapes["data"], generator=g), im_info=torch.tensor([[H, W, 1.0]] * B),
+                gt_bbox=torch.full((B, 100, 5), -1.0), valid_ranges=torch.tensor([[[0.0, 90.0], [30.0, 160.0], [90.0, -1.0]]] * B),
+                rpn_cls_label=torch.randint(-1, 2, shapes["rpn_cls_label"], generator=g).float(),
+                rpn_reg_target=torch.randn(shapes["rpn_reg_target"], generator=g),
+                rpn_reg_weight=(torch.rand(shapes["rpn_reg_weight"], generator=g) < 0.1).float())
+    res = tr.forward_backward(**feed)
+    assert [tuple(o.shape) for o in res] == outs and ("proposal_v2", 500) in log and ("proposal_target_v2", 16) in log
+    grads = tr.grads()
+    assert set(grads) == set(tr.trainable) and len(data_shapes) == 4

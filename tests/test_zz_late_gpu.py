@@ -317,3 +317,31 @@ def test_cascade_rcnn_inference_and_train_step_on_the_device(cuda):
     grads = tr.grads()
     assert len(outs) == 12 and all(torch.isfinite(o).all() for o in outs)
     assert set(grads) == set(tr.trainable) and all(torch.isfinite(v).all() for v in grads.values())
+
+
+def test_tridentnet_train_step_on_the_device(cuda):
+    """config/tridentnet_r50v1c4_c5_1x.py's train symbol: `_contrib_Proposal_v2` and `ProposalTarget_v2` (valid_ranges,
+    filter_scales) inside the graph, three weight-sharing branches in the batch axis."""
+    from simpledet_b200.facade import symbol as S
+    from simpledet_b200.facade import train as T
+
+    sym = S.fromjson(open(os.path.join(GOLD, "tridentnet_r50v1c4_c5_1x_train_symbol.json")).read())
+    B, H, W, NB = 2, 256, 384, 3
+    fh, fw = H // 16, W // 16
+    shapes = dict(data=(B, 3, H, W), im_info=(B, 3), gt_bbox=(B, 100, 5), valid_ranges=(B, NB, 2),
+                  rpn_cls_label=(B, NB, 15, fh, fw), rpn_reg_target=(B, NB, 60, fh, fw), rpn_reg_weight=(B, NB, 60, fh, fw))
+    tr = T.Trainer(sym, shapes, device=cuda, fixed_param=("conv0", "stage1", "gamma", "beta"), rng_std=0.02)
+    g = torch.Generator().manual_seed(0)
+    gt = torch.full((B, 100, 5), -1.0)
+    for b in range(B):
+        xy = torch.rand(6, 2, generator=g) * torch.tensor([W - 150.0, H - 150.0])
+        gt[b, :6, :4] = torch.cat([xy, xy + 20 + torch.rand(6, 2, generator=g) * 120], 1)
+        gt[b, :6, 4] = torch.randint(1, 81, (6,), generator=g).float()
+    outs = tr.forward_backward(data=torch.randn(shapes["data"], generator=g), im_info=torch.tensor([[H, W, 1.0]] * B),
+                               gt_bbox=gt, valid_ranges=torch.tensor([[[0.0, 90.0], [30.0, 160.0], [90.0, -1.0]]] * B),
+                               rpn_cls_label=torch.randint(-1, 2, shapes["rpn_cls_label"], generator=g).float(),
+                               rpn_reg_target=torch.randn(shapes["rpn_reg_target"], generator=g),
+                               rpn_reg_weight=(torch.rand(shapes["rpn_reg_weight"], generator=g) < 0.1).float())
+    grads = tr.grads()
+    assert all(torch.isfinite(o).all() for o in outs) and tuple(outs[4].shape) == (B * NB, 128)
+    assert set(grads) == set(tr.trainable) and all(torch.isfinite(v).all() for v in grads.values())
