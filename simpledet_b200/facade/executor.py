@@ -208,6 +208,24 @@ def _shape_arange(a, ins, names):
     return ins, [(max(0, math.ceil((stop - start) / step)) * rep,)]
 
 
+def _shape_sum(a, ins, names):
+    ax = a.get("axis")
+    d = list(ins[0])
+    if ax in (None, "None", ()):
+        return ins, [(1,)]
+    axes = [int(v) % len(d) for v in (_t(ax) if isinstance(_t(ax), (tuple, list)) else (_t(ax),))]
+    keep = _b(a.get("keepdims", False))
+    out = [1 if i in axes else v for i, v in enumerate(d)] if keep else [v for i, v in enumerate(d) if i not in axes]
+    return ins, [tuple(out) or (1,)]
+
+
+def _shape_expand_dims(a, ins, names):
+    d = list(ins[0])
+    ax = int(_t(a["axis"]))
+    d.insert(ax if ax >= 0 else len(d) + 1 + ax, 1)
+    return ins, [tuple(d)]
+
+
 def _shape_stack(a, ins, names):
     ax = int(_t(a.get("axis", 0)))
     d = list(ins[0])
@@ -286,6 +304,8 @@ def _shape_custom(a, ins, names):
     if t == "BboxPostProcessing":
         B, m = ins[0][0], int(_t(a["max_det_per_image"]))
         return ins, [(B, m, 1), (B, m, 4), (B, m, 1)]
+    if t == "maskiou_compute":
+        return ins, [(ins[1][0], 1), (ins[1][0], 1)]
     if t == "bbox_target":
         B, R, C = ins[0][0], int(_t(a["image_rois"])), int(_t(a["num_class"]))
         return ins, [(B, R, 4), (B, R), (B, R, 4 * C), (B, R, 4 * C)]
@@ -304,7 +324,8 @@ SHAPE_RULES = {
     "elemwise_div": _shape_elemwise, "add_n": _same, "ProposalTarget": _shape_proposal_target,
     "_contrib_FocalLoss": _shape_focal_loss, "_contrib_BBoxNorm": _same,
     "ProposalMaskTarget": _shape_proposal_mask_target, "_contrib_SigmoidCrossEntropy": lambda a, ins, n: (ins, [(ins[0][0],)]),
-    "split": _shape_split, "SliceChannel": _shape_split, "arange": _shape_arange, "_arange": _shape_arange,
+    "sum": _shape_sum, "expand_dims": _shape_expand_dims, "_power_scalar": _same, "maximum": _shape_elemwise,
+    "minimum": _shape_elemwise, "split": _shape_split, "SliceChannel": _shape_split, "arange": _shape_arange, "_arange": _shape_arange,
     "stack": _shape_stack, "gather_nd": _shape_gather_nd, "concat": _shape_concat,
     "broadcast_add": _same, "broadcast_mul": _same,
     "Concat": _shape_concat, "UpSampling": _shape_upsample, "slice_like": _shape_slice_like, "slice_axis": _shape_slice_axis,
@@ -667,6 +688,20 @@ class Executor:
             return [x[0] * x[1]]
         if op == "elemwise_div":
             return [x[0] / x[1]]
+        if op == "_power_scalar":
+            return [x[0] ** float(a["scalar"])]
+        if op in ("maximum", "minimum"):
+            if len(x) == 2:
+                return [torch.maximum(x[0], x[1]) if op == "maximum" else torch.minimum(x[0], x[1])]
+            return [x[0].clamp(min=float(_t(a["scalar"]))) if op == "maximum" else x[0].clamp(max=float(_t(a["scalar"])))]
+        if op == "sum":
+            ax = a.get("axis")
+            if ax in (None, "None", ()):
+                return [x[0].sum().reshape(1)]
+            axes = _t(ax) if isinstance(_t(ax), (tuple, list)) else (_t(ax),)
+            return [x[0].sum(tuple(int(v) for v in axes), keepdim=_b(a.get("keepdims", False)))]
+        if op == "expand_dims":
+            return [x[0].unsqueeze(int(_t(a["axis"])))]
         if op.endswith("_scalar"):
             s, rev = float(a["scalar"]), bool(a.get("__rev__", False))
             return [{"_plus_scalar": lambda v: v + s, "_mul_scalar": lambda v: v * s,
@@ -816,6 +851,9 @@ class Executor:
             if t == "assign_layer_fpn":
                 return list(ops.OPS[t](x[0].contiguous(), tuple(_t(a["rcnn_stride"])), int(_t(a["roi_canonical_scale"])),
                                        int(_t(a["roi_canonical_level"]))))
+            if t == "maskiou_compute":
+                with torch.no_grad():
+                    return list(ops.OPS[t](*[v.detach().contiguous() for v in x[:4]]))
             if t == "bbox_target":
                 return list(ops.OPS[t](x[0].contiguous(), x[1].contiguous(), int(_t(a["num_class"])),
                                        _b(a["add_gt_to_proposal"]), int(_t(a["image_rois"])), float(_t(a["fg_fraction"])),

@@ -50,7 +50,9 @@ _MULTI_OUT = {
 }
 # non-symbol positional arguments of the creation operators, in order
 _POSITIONAL_ATTRS = {"full": ("shape", "value"), "zeros": ("shape",), "ones": ("shape",), "arange": ("start", "stop", "step"),
-                     "Reshape": ("shape",), "reshape": ("shape",)}   # mx.symbol.Reshape(data, (-3, -2)): models/tridentnet/resnet_v2.py:99
+                     "Reshape": ("shape",), "reshape": ("shape",),
+                     "maximum": ("scalar",), "minimum": ("scalar",),   # mx.sym.maximum(sym, 1.): models/msrcnn/builder.py:167
+                     "repeat": ("repeats", "axis"), "tile": ("reps",)}   # mx.symbol.Reshape(data, (-3, -2)): models/tridentnet/resnet_v2.py:99
 CUSTOM_OUTPUTS = {"get_top_proposal": 2, "assign_layer_fpn": None, "BboxPostProcessing": 3, "bbox_target": 4,
                   "decode_retina": 2}
 

@@ -1610,6 +1610,31 @@ def mask_test_records(im_id, im_info, im_h, im_w, post_cls_score, post_box, post
 
 
 
+def maskiou_compute(mask_pred_logits, mask_target, mask_ratio, mask_inds):
+    """CustomOp 'maskiou_compute' (models/msrcnn/maskiou_compute.py:10-44; Mask Scoring R-CNN's MaskIoU regression
+    target, fed by ProposalMaskTarget(output_ratio=True)): mask_pred_logits, mask_target (R,M,M), mask_ratio (R) or
+    (R,1), mask_inds (R) class per slot -> (maskiou_target (R,1), weight_list (R,1)) float32.
+    iou = max(sum(target * pred), 0) / max(sum(target) / ratio + sum(pred) - sum(target * pred), 1) with pred =
+    `mask_pred_logits` > 0.5 (the operator's own threshold on its first input, which models/msrcnn/builder.py feeds with the
+    sigmoid probabilities `mask_pred_prob`); the sums are small integers (exact in float32), the
+    division by the ratio and the quotient are float64 like numpy's, rounded to float32 on output.  Host-composed on the
+    device (elementwise + row reductions from the library); no gradient (need_top_grad=False, zero in_grad)."""
+    logits = _dev(mask_pred_logits, "mask_pred_logits")
+    target = _dev(mask_target, "mask_target")
+    ratio = _dev(mask_ratio, "mask_ratio").reshape(-1)
+    inds = _dev(mask_inds, "mask_inds").reshape(-1)
+    with torch.no_grad():
+        pred = logits > 0.5
+        inter = (target * pred).sum((1, 2))                          # float32, exact
+        pred_sum = pred.sum((1, 2)).double()
+        tgt_sum = target.sum((1, 2)).double() / ratio.double()
+        union = torch.clamp(tgt_sum + pred_sum - inter.double(), min=1.0)
+        iou = (torch.clamp(inter, min=0.0).double() / union).to(torch.float32).reshape(-1, 1)
+        weight = (inds > 0).to(torch.float32).reshape(-1, 1)
+    return iou, weight
+
+
+
 def _bbox_target_impl(proposal, gt_bbox, num_class, add_gt_to_proposal, image_rois, fg_fraction, fg_thresh, bg_thresh_hi,
                       bg_thresh_lo, bbox_target_std, rng, overlaps):
     """The body of `bbox_target` over tensors on one device, with the IoU operator passed in (the product passes the
@@ -1730,6 +1755,7 @@ OPS = {
     "decode_retina": decode_retina,            # mx.operator.register("decode_retina")
     "bbox_target": bbox_target,                # mx.operator.register('bbox_target')
     "segm_results": segm_results,              # models/maskrcnn/utils.py:26
+    "maskiou_compute": maskiou_compute,        # mx.operator.register('maskiou_compute')
     # plain callables of operator_py (same names and argument meaning)
     "gpu_nms": gpu_nms,
     "greedy_nms": greedy_nms,

@@ -13,10 +13,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 # BASELINE.json configs 2-5: Faster R-CNN FPN, RetinaNet, Mask R-CNN, DCNv1 Faster R-CNN C4
 CONFIGS = ["faster_r50v1_fpn_1x", "retina_r50v1_fpn_1x", "mask_r50v1_fpn_1x", "dcn.faster_dcn_r50v1bc4_c5_512roi_1x",
-                 "crowdhuman.faster_r50v1b_fpn_1x", "cascade_r50v1_fpn_1x", "tridentnet_r50v1c4_c5_1x"]
+                 "crowdhuman.faster_r50v1b_fpn_1x", "cascade_r50v1_fpn_1x", "tridentnet_r50v1c4_c5_1x", "ms_r50v1_fpn_1x"]
 # the TRAIN graphs the façade's Trainer runs (simpledet_b200/facade/train.py): <config>_train_symbol.json
 TRAIN_CONFIGS = ["faster_r50v1_fpn_1x", "retina_r50v1_fpn_1x", "mask_r50v1_fpn_1x", "dcn.faster_dcn_r50v1bc4_c5_512roi_1x",
-                 "crowdhuman.faster_r50v1b_fpn_1x", "cascade_r50v1_fpn_1x", "tridentnet_r50v1c4_c5_1x"]
+                 "crowdhuman.faster_r50v1b_fpn_1x", "cascade_r50v1_fpn_1x", "tridentnet_r50v1c4_c5_1x", "ms_r50v1_fpn_1x"]
 
 
 def one(name, train=False):

@@ -44,3 +44,20 @@ def bbox_post_processing_oracle(cls_score, bbox, max_det, min_score, thr):
 def test_bbox_post_processing():
     s, b, c = bbox_post_processing_oracle(G["bp_cls_score"], G["bp_bbox"], 50, 0.3, 0.5)
     assert np.array_equal(s, G["bp_score"]) and np.array_equal(b, G["bp_box"]) and np.array_equal(c, G["bp_cls"])
+
+
+def test_maskiou_compute_host_composition(monkeypatch):
+    """ops.maskiou_compute (torch elementwise + reductions) against the reference's CustomOp run unmodified
+    (tests/golden/make_golden_maskiou.py), on CPU tensors with only the CUDA tensor check lifted; its device twin is in
+    tests/test_zz_late_gpu.py."""
+    import torch
+
+    from simpledet_b200 import ops
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_maskiou_compute.npz"))
+    monkeypatch.setattr(ops, "_dev", lambda t, name, dtype=torch.float32: t.contiguous())
+    iou, w = ops.OPS["maskiou_compute"](*[torch.from_numpy(g[k]) for k in ("logits", "target", "ratio", "inds")])
+    assert np.array_equal(iou.numpy(), g["iou"]) and np.array_equal(w.numpy(), g["weight"])
+    iou2, _ = ops.maskiou_compute(torch.from_numpy(g["logits"]), torch.from_numpy(g["target"]),
+                                  torch.from_numpy(g["ratio"]).reshape(-1, 1), torch.from_numpy(g["inds"]))
+    assert torch.equal(iou, iou2)

@@ -135,14 +135,18 @@ def _train_stubs(monkeypatch, log):
     def proposal_mask_target(rois, gt_boxes, gt_polys, num_classes, batch_images, image_rois, mask_size, fg_thresh,
                              bg_thresh_hi, bg_thresh_lo, proposal_without_gt, fg_fraction, class_agnostic, output_iou,
                              output_ratio, bbox_mean, bbox_std, bbox_weight):
-        assert output_iou and not output_ratio and gt_polys.shape[:2] == gt_boxes.shape[:2]
+        assert output_iou and gt_polys.shape[:2] == gt_boxes.shape[:2]
         base = proposal_target(rois, gt_boxes, num_classes, batch_images, image_rois, fg_thresh, bg_thresh_hi, bg_thresh_lo,
                                proposal_without_gt, fg_fraction, class_agnostic, output_iou, bbox_mean, bbox_std, bbox_weight)
         nfg = int(image_rois * fg_fraction)
         log.append(("proposal_mask_target", nfg, mask_size))
         g = torch.Generator().manual_seed(2)
         tgt = torch.randint(-1, 2, (batch_images, nfg, mask_size, mask_size), generator=g).float()
-        return (*base, torch.rand(batch_images, image_rois, generator=g), tgt)
+        out = (*base, torch.rand(batch_images, image_rois, generator=g), tgt)
+        if output_ratio:       # Mask Scoring R-CNN: the share of the instance inside the roi
+            log.append(("mask_ratio", nfg))
+            out += (torch.rand(batch_images, nfg, generator=g).clamp(min=0.05),)
+        return out
 
     def sigmoid_ce(data, label, grad_scale):
         assert data.requires_grad and data.shape == label.shape and data.dim() == 2
@@ -440,3 +444,33 @@ def test_tridentnet_train_graph_reaches_proposal_v2_and_proposal_target_v2(monke
     assert [tuple(o.shape) for o in res] == outs and ("proposal_v2", 500) in log and ("proposal_target_v2", 16) in log
     grads = tr.grads()
     assert set(grads) == set(tr.trainable) and len(data_shapes) == 4
+
+
+def test_mask_scoring_rcnn_train_graph_through_the_trainer(monkeypatch):
+    """config/ms_r50v1_fpn_1x.py: ProposalMaskTarget(output_ratio=True) -> CustomOp 'maskiou_compute' (the real
+    host-composed operator, CUDA tensor check lifted) -> the MaskIoU head's L2 loss written with sum / maximum / **."""
+    from simpledet_b200 import ops
+
+    sym = S.fromjson(open(os.path.join(ROOT, "tests", "golden", "ms_r50v1_fpn_1x_train_symbol.json")).read())
+    B, H, W = 2, 128, 192
+    shapes = dict(data=(B, 3, H, W), im_info=(B, 3), gt_bbox=(B, 100, 5), gt_poly=(B, 100, 2500))
+    _, outs, _ = E.infer_shapes(sym, shapes)
+    assert outs[-2:] == [(1,), (1,)]
+    log = []
+    _train_stubs(monkeypatch, log)
+    monkeypatch.setattr(ops, "_dev", lambda t, name, dtype=torch.float32: t.contiguous())
+    tr = T.Trainer(sym, shapes, device="cpu", fixed_param=("conv0", "stage1", "gamma", "beta"), rng_std=0.02,
+                   label_names=("rpn_cls_label", "rpn_reg_target", "rpn_reg_weight"))
+    s_total = sum((H // st) * (W // st) for st in (4, 8, 16, 32, 64))
+    g = torch.Generator().manual_seed(0)
+    res = tr.forward_backward(data=torch.randn(shapes["data"], generator=g), im_info=torch.tensor([[H, W, 1.0]] * B),
+                              gt_bbox=torch.full((B, 100, 5), -1.0), gt_poly=torch.full((B, 100, 2500), -1.0),
+                              rpn_cls_label=torch.randint(-1, 2, (B, 3, s_total), generator=g).float(),
+                              rpn_reg_target=torch.randn(B, 12, s_total, generator=g),
+                              rpn_reg_weight=(torch.rand(B, 12, s_total, generator=g) < 0.1).float())
+    assert [tuple(o.shape) for o in res] == outs and all(torch.isfinite(o).all() for o in res)
+    assert ("mask_ratio", 128) in log and float(res[-1]) >= 0
+    grads = tr.grads()
+    assert set(grads) == set(tr.trainable)
+    iou_head = [n for n in grads if "iou" in n and n.endswith("weight")]
+    assert iou_head and all(float(grads[n].abs().sum()) > 0 for n in iou_head), iou_head

@@ -345,3 +345,34 @@ def test_tridentnet_train_step_on_the_device(cuda):
     grads = tr.grads()
     assert all(torch.isfinite(o).all() for o in outs) and tuple(outs[4].shape) == (B * NB, 128)
     assert set(grads) == set(tr.trainable) and all(torch.isfinite(v).all() for v in grads.values())
+
+
+def test_maskiou_compute_against_the_reference_operator(cuda):
+    g = np.load(os.path.join(GOLD, "reference_maskiou_compute.npz"))
+    iou, w = ops.OPS["maskiou_compute"](*[torch.from_numpy(g[k]).to(cuda) for k in ("logits", "target", "ratio", "inds")])
+    assert np.array_equal(iou.cpu().numpy(), g["iou"]) and np.array_equal(w.cpu().numpy(), g["weight"])
+
+
+def test_mask_scoring_rcnn_train_step_on_the_device(cuda):
+    """config/ms_r50v1_fpn_1x.py's train symbol: ProposalMaskTarget(output_ratio=True) (the mask_ratio kernel) feeding
+    the CustomOp 'maskiou_compute' and the MaskIoU head."""
+    from simpledet_b200 import synth
+    from simpledet_b200.facade import symbol as S
+    from simpledet_b200.facade import train as T
+
+    sym = S.fromjson(open(os.path.join(GOLD, "ms_r50v1_fpn_1x_train_symbol.json")).read())
+    B, H, W = 2, 512, 832
+    shapes = dict(data=(B, 3, H, W), im_info=(B, 3), gt_bbox=(B, 100, 5), gt_poly=(B, 100, 2500))
+    tr = T.Trainer(sym, shapes, device=cuda, fixed_param=("conv0", "stage1", "gamma", "beta"), rng_std=0.02,
+                   label_names=("rpn_cls_label", "rpn_reg_target", "rpn_reg_weight"))
+    s_total = sum((H // st) * (W // st) for st in (4, 8, 16, 32, 64))
+    _, gt, polys = synth.mask_scene(np.random.default_rng(3), B, 64, 100, 2500)
+    g = torch.Generator().manual_seed(0)
+    outs = tr.forward_backward(data=torch.randn(shapes["data"], generator=g), im_info=torch.tensor([[H, W, 1.0]] * B),
+                               gt_bbox=torch.from_numpy(gt), gt_poly=torch.from_numpy(polys),
+                               rpn_cls_label=torch.randint(-1, 2, (B, 3, s_total), generator=g).float(),
+                               rpn_reg_target=torch.randn(B, 12, s_total, generator=g),
+                               rpn_reg_weight=(torch.rand(B, 12, s_total, generator=g) < 0.1).float())
+    grads = tr.grads()
+    assert len(outs) == 8 and all(torch.isfinite(o).all() for o in outs)
+    assert set(grads) == set(tr.trainable) and all(torch.isfinite(v).all() for v in grads.values())
