@@ -3,7 +3,7 @@
 and cv2; CPU only): 120 random detections on an 800 x 1333 image through (a) the reference's own segm_results
 (models/maskrcnn/utils.py:26-67) on the installed cv2 with a stand-in pycocotools encoder and (b) the host emulation of
 mask_paste.cu's kernels (tests/c_abi/mask_paste_emul.cc) under ops._segm_results_impl; compares the RLE strings.
-    python tools/mask_paste_stress.py SEED"""
+    python tests/stress_mask_paste.py SEED   (test infrastructure: it imports the oracle)"""
 import ctypes
 import os
 import subprocess
